@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures in this directory by RUNNING THE REFERENCE ITSELF.
+
+Needs /root/reference (this container only): oracle/Makefile compiles the unmodified reference CPU sources
+into oracle/_ref/libpfref.so; this script drives it through oracle/pfref.py and stores
+
+  <scene>.npz   inputs  = what SceneBuilderD3D11::build hands to the renderer (core/d3d11/scene_builder.cpp:209-223)
+                outputs = SceneBuilderD3D9::build's fills / tiles / clips / z-buffers (core/d3d9/scene_builder.cpp:97-109)
+                          in the order- and id-independent canonical form of tests/scenes.py
+  area_lut.npz  the 256 x 256 RGBA8 area LUT as decoded by the reference (core/renderer.cpp:17-21)
+  digests.json  sha256 of the canonical outputs of the configurations too large to commit (tiger 4096)
+
+Usage: python tests/golden/make_golden.py
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import pfref  # noqa: E402
+import scenes  # noqa: E402
+
+# name -> (asset, size, native size of the SVG view box)
+SVG_SCENES = {
+    "tiger_512": ("tiger.svg", 512, 900.0),
+    "tiger_1024": ("tiger.svg", 1024, 900.0),      # BASELINE.json configs[0]
+    "features_2048": ("features.svg", 2048, 720.0),  # BASELINE.json configs[1], SVG half
+}
+DIGEST_ONLY = {
+    "tiger_4096": ("tiger.svg", 4096, 900.0),      # BASELINE.json configs[2]
+}
+# demo/common/app.cpp:21-101 blocks: 1 rect, 2 clip circle, 16 gradient stroke (4 shadow, 8 image, 32 render target
+# need render-target passes: SURVEY.md section 8 row f3)
+DEMO_SCENES = {
+    "demo_clip_512": (512, 1.0, 1 | 2 | 16),
+}
+
+
+def canonical_extra(ref):
+    extra = {"ref_group_hashes": ref["group_hashes"], "ref_n_batches": np.int32(len(ref["batches"]))}
+    for i, b in enumerate(ref["batches"]):
+        for k in ("tiles", "fills", "clips", "z"):
+            extra["ref%d_%s" % (i, k)] = b[k]
+    return extra
+
+
+def canonical_digest(ref):
+    parts = [ref["group_hashes"]]
+    for b in ref["batches"]:
+        parts += [b["tiles"], b["fills"], b["clips"], b["z"]]
+    return scenes.digest(*parts)
+
+
+def main():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    digests = {}
+    lut = None
+    for name, (asset, size, native) in {**SVG_SCENES, **DIGEST_ONLY}.items():
+        s = pfref.RefScene.from_svg(pfref.asset(asset), size, size, size / native)
+        scene = s.build_d3d11()
+        ref = scenes.canonical_from_reference(s.build_d3d9())
+        if lut is None:
+            lut = s.area_lut()
+        digests[name] = {"canonical_sha256": canonical_digest(ref), "counts": s.counts(),
+                         "fills": int(sum(len(b["fills"]) for b in ref["batches"])),
+                         "tiles": int(sum(len(b["tiles"]) for b in ref["batches"])),
+                         "alpha_tiles": int(len(ref["group_hashes"]))}
+        if name in SVG_SCENES:
+            scenes.save_scene(scenes.golden_path(name), scene, canonical_extra(ref))
+        s.close()
+        print(name, digests[name])
+    for name, (size, scale, features) in DEMO_SCENES.items():
+        s = pfref.RefScene.demo(size, size, scale, pfref.asset("sea.png"), features)
+        scene = s.build_d3d11()
+        ref = scenes.canonical_from_reference(s.build_d3d9())
+        digests[name] = {"canonical_sha256": canonical_digest(ref), "counts": s.counts()}
+        scenes.save_scene(scenes.golden_path(name), scene, canonical_extra(ref))
+        s.close()
+        print(name, digests[name])
+    np.savez_compressed(os.path.join(HERE, "area_lut.npz"), lut=lut)
+    with open(os.path.join(HERE, "digests.json"), "w") as fp:
+        json.dump(digests, fp, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
