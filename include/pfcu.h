@@ -1,0 +1,167 @@
+/* pfcu -- C ABI of the B200-native GPU-driven rasterization path (bound, dice, bin, propagate, sort, fill, tile).
+ *
+ * This is the drop-in boundary. It replaces, for this path only, what floppyhammer/pathfinder-cpp's
+ * RendererD3D11 (pathfinder/core/d3d11/renderer.cpp:113-1079) reaches through the abstract GPU layer
+ * (pathfinder/gpu/device.h:24-147, command_encoder.h:158-273, queue.h:11-25), the GpuMemoryAllocator
+ * (pathfinder/gpu_mem/allocator.h:55-108) and the seven compute shaders (pathfinder/shaders/d3d11/[name].comp).
+ * Inputs are exactly the vectors SceneBuilderD3D11 produces (pathfinder/core/d3d11/scene_builder.h:50-55,
+ * gpu_data.h:54-205); the host adapter that calls these entry points from the reference's own Renderer
+ * interface is pathfinder-cpp_b200/host/renderer_cuda.{h,cpp}; INTEGRATION.md shows the wiring.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types. Every call returns PFCU_OK (0) or a negative
+ * pfcu_status and records a message retrievable with pfcu_last_error() (thread-local). All work is enqueued
+ * on ONE CUDA stream per context (pfcu_set_stream; default: a private non-blocking stream). Host buffers
+ * passed to upload calls are consumed before the call returns (staged through pinned memory), so the caller
+ * may free them immediately -- the same lifetime rule as CommandEncoder::write_buffer
+ * (pathfinder/gpu/command_encoder.cpp:205-239). There is NO CPU fallback: without a CUDA device every entry
+ * point fails with PFCU_ERR_CUDA.
+ */
+#ifndef PFCU_H
+#define PFCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFCU_ABI_VERSION 1
+
+typedef enum {
+    PFCU_OK = 0,
+    PFCU_ERR_INVALID = -1,  /* bad argument / unknown batch or page (reference: Logger::error + early return) */
+    PFCU_ERR_CUDA = -2,     /* CUDA runtime error, no device */
+    PFCU_ERR_OOM = -3,      /* device allocation failed */
+    PFCU_ERR_OVERFLOW = -4, /* a stage ran out of space twice (reference: "Ran out of space ...", renderer.cpp:551,575) */
+    PFCU_ERR_STATE = -5     /* call sequence violated (e.g. draw before prepare) */
+} pfcu_status;
+
+typedef struct pfcu_ctx pfcu_ctx;
+
+/* ---- records shared with the reference host code (pathfinder/core/d3d11/gpu_data.h), POD, std430-compatible */
+typedef struct { /* BackdropInfoD3D11, gpu_data.h:54-60 */
+    int32_t initial_backdrop, tile_x_offset;
+    uint32_t path_index;
+} pfcu_backdrop_info;
+typedef struct { /* PropagateMetadataD3D11, gpu_data.h:62-74 */
+    int32_t tile_rect[4];
+    uint32_t tile_offset, path_index, z_write, clip_path_index, backdrop_offset, pad0, pad1, pad2;
+} pfcu_propagate_metadata;
+typedef struct { /* DiceMetadataD3D11, gpu_data.h:76-82 */
+    uint32_t global_path_id, first_global_segment_index, first_batch_segment_index, pad;
+} pfcu_dice_metadata;
+typedef struct { /* TilePathInfoD3D11, gpu_data.h:84-94 */
+    int16_t tile_min_x, tile_min_y, tile_max_x, tile_max_y;
+    uint32_t first_tile_index;
+    uint16_t color;
+    uint8_t ctrl;
+    int8_t backdrop;
+} pfcu_tile_path_info;
+
+/* TileBatchDataD3D11 + PrepareTilesInfoD3D11 (gpu_data.h:97-165) flattened. */
+typedef struct {
+    uint32_t batch_id;
+    uint32_t path_count, tile_count, segment_count, column_count;
+    int32_t path_source;   /* 0 = draw segments, 1 = clip segments (PathSource) */
+    int32_t clip_batch_id; /* ClippedPathInfo::clip_batch_id or -1 */
+    const pfcu_backdrop_info *backdrops;               /* column_count */
+    const pfcu_propagate_metadata *propagate_metadata; /* path_count */
+    const pfcu_dice_metadata *dice_metadata;           /* path_count */
+    const pfcu_tile_path_info *tile_path_info;         /* path_count */
+    float transform[6];                                /* m11 m21 m12 m22 m13 m23 (Transform2) */
+} pfcu_batch_desc;
+
+/* ---- parity taps (device results copied to the host) */
+typedef struct {
+    float from_x, from_y, to_x, to_y;
+    uint32_t path_index;
+} pfcu_line; /* 20 B: one flattened line, output of dice */
+typedef struct {
+    uint32_t tile_index; /* dense, batch-local */
+    uint16_t from_x, from_y, to_x, to_y;
+} pfcu_fill; /* 12 B */
+typedef struct {
+    int32_t alpha_tile_id;      /* frame-global mask slot (the clip's for solid-draw x alpha-clip) or -1 */
+    int32_t clip_alpha_tile_id; /* mask slot min()-ed into this tile's mask or -1 */
+    int32_t fill_count;
+    int8_t backdrop;
+    int8_t backdrop_delta;
+    int8_t backdrop_d3d9; /* the value the reference's hybrid tiler stores for the same tile (tiler.cpp:433-434) */
+    uint8_t listed;
+} pfcu_tile; /* 16 B */
+
+/* Per-frame counters (also the units of the throughput metrics). */
+typedef struct {
+    uint32_t batches, segments, lines, fills, alpha_tiles, dense_tiles, listed_tiles, listed_after_cull;
+    uint32_t fb_tiles, max_list_len, overflow_flags, retries;
+    uint32_t kernel_launches; /* kernels enqueued for this frame, including retries */
+    uint32_t reserved[3];
+    float gpu_ms; /* CUDA-event time of the frame on the context's stream (prepare..last draw), last attempt */
+} pfcu_frame_stats;
+
+/* ---- lifecycle */
+int pfcu_abi_version(void);
+const char *pfcu_last_error(void);
+int pfcu_create(int device_ordinal, pfcu_ctx **out);
+void pfcu_destroy(pfcu_ctx *ctx);
+/* Run on the caller's stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream). NULL restores
+ * the private stream. */
+int pfcu_set_stream(pfcu_ctx *ctx, void *cuda_stream);
+/* The stream work is enqueued on (cudaStream_t), for event timing by the caller. */
+void *pfcu_get_stream(pfcu_ctx *ctx);
+
+/* ---- static resources (Renderer::Renderer, pathfinder/core/renderer.cpp:13-37) */
+/* 256 x 256 RGBA8 area LUT as decoded by the reference from shaders/area_lut.png. */
+int pfcu_set_area_lut(pfcu_ctx *ctx, const uint8_t *rgba, int width, int height);
+
+/* ---- per-target state: Renderer::set_dest_texture + Scene view box (core/renderer.h:81, core/scene.cpp:170-179) */
+/* rgba8_dev == NULL: the context owns the destination (width*4 pitch). Otherwise render into caller memory
+ * (device pointer, pitch in bytes, 16-byte aligned rows). view_box = {left, top, right, bottom}. */
+int pfcu_set_target(pfcu_ctx *ctx, int width, int height, void *rgba8_dev, size_t pitch_bytes,
+                    const float view_box[4]);
+
+/* ---- per-scene uploads */
+/* RendererD3D11::upload_scene (d3d11/renderer.cpp:346-350): which 0 = draw, 1 = clip.
+ * points: xy float pairs; indices: SegmentIndicesD3D11 {first_point_index, flag} pairs. */
+int pfcu_upload_scene(pfcu_ctx *ctx, int which, const float *points, uint32_t n_points, const uint32_t *indices,
+                      uint32_t n_segments);
+/* Renderer::upload_texture_metadata (core/renderer.cpp:167-251): rows of 1280 RGBA16F texels. */
+int pfcu_upload_paint_metadata(pfcu_ctx *ctx, const uint16_t *half_texels, uint32_t n_rows);
+/* Renderer::allocate_pattern_texture_page / upload_texel_data (core/renderer.cpp:46-61,95-114). */
+int pfcu_alloc_page(pfcu_ctx *ctx, uint32_t page, int width, int height);
+int pfcu_upload_page_region(pfcu_ctx *ctx, uint32_t page, int x, int y, int width, int height, const uint8_t *rgba);
+
+/* ---- frame: RendererD3D11::draw (d3d11/renderer.cpp:302-336) */
+int pfcu_begin_frame(pfcu_ctx *ctx);
+/* prepare_tiles (renderer.cpp:510-616): bound + dice + bin + propagate + fill + sort for one batch.
+ * Clip batches must be prepared before the batches they clip (the reference submits them first, :318-327). */
+int pfcu_prepare_batch(pfcu_ctx *ctx, const pfcu_batch_desc *desc);
+/* draw_tiles (renderer.cpp:365-448): composite a prepared draw batch into the destination (target_page < 0) or
+ * into a pattern page (render target). color_page < 0: the 1 x 1 dummy texture. sampling_flags:
+ * TextureSamplingFlags (REPEAT_U 1, REPEAT_V 2, NEAREST_MIN 4, NEAREST_MAG 8). clear != 0: LOAD_ACTION_CLEAR. */
+int pfcu_draw_batch(pfcu_ctx *ctx, uint32_t batch_id, int target_page, int color_page, uint32_t sampling_flags,
+                    int clear, const float clear_color[4]);
+/* Waits for the frame, checks the device-side capacity flags and, when a stage overflowed, grows its buffer
+ * and replays the recorded frame (the reference's retry loops, renderer.cpp:537-577, without the mid-frame
+ * read-backs). stats may be NULL. */
+int pfcu_end_frame(pfcu_ctx *ctx, pfcu_frame_stats *stats);
+
+/* ---- results */
+int pfcu_read_target(pfcu_ctx *ctx, uint8_t *host_rgba8);                    /* width*height*4, tightly packed */
+int pfcu_read_page(pfcu_ctx *ctx, uint32_t page, uint8_t *host_rgba8);
+void *pfcu_target_device_ptr(pfcu_ctx *ctx, size_t *pitch_bytes);            /* zero-copy consumers */
+
+/* ---- parity taps: pass NULL to query the element count. Valid after pfcu_end_frame. */
+int64_t pfcu_read_lines(pfcu_ctx *ctx, uint32_t batch_id, pfcu_line *out);
+int64_t pfcu_read_fills(pfcu_ctx *ctx, uint32_t batch_id, pfcu_fill *out); /* sorted by tile, then coordinates */
+int64_t pfcu_read_tiles(pfcu_ctx *ctx, uint32_t batch_id, pfcu_tile *out);
+int64_t pfcu_read_z(pfcu_ctx *ctx, uint32_t batch_id, int32_t *out);       /* per framebuffer tile */
+/* Sorted, z-culled per-framebuffer-tile lists, CSR: offsets has fb_tiles + 1 entries. */
+int64_t pfcu_read_tile_lists(pfcu_ctx *ctx, uint32_t batch_id, uint32_t *offsets, uint32_t *dense_tile_indices);
+int pfcu_read_mask(pfcu_ctx *ctx, uint32_t alpha_tile_id, uint8_t out[256]); /* 16 x 16 coverage, row-major */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFCU_H */

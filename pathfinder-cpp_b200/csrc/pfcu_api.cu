@@ -1,0 +1,846 @@
+// C-ABI (include/pfcu.h) over the kernels: context, device arena, frame recording / replay, parity taps.
+//
+// Replaces, for this path, the reference's RendererD3D11 host orchestration
+// (pathfinder/core/d3d11/renderer.cpp:302-616) and its GpuMemoryAllocator (pathfinder/gpu_mem/allocator.cpp):
+// buffers are device-local, keyed by batch slot, grown geometrically and reused across frames; the whole frame is
+// enqueued on one stream without a single mid-frame host read-back (the reference has three per batch,
+// renderer.cpp:705-724,832-845,943-950). Capacity overflows are detected once, at pfcu_end_frame, and answered by
+// growing the buffer and replaying the recorded frame.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pfcu_device.h"
+
+using namespace pfcu;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                       \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail(_e == cudaErrorMemoryAllocation ? PFCU_ERR_OOM : PFCU_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                                         \
+    } while (0)
+
+size_t round_up_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(round_up_pow2(bytes), 256);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return static_cast<T *>(p);
+    }
+};
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = std::max<size_t>(round_up_pow2(bytes), 4096);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int MAX_PAGES = 64;
+constexpr int MAX_SLOTS = 256;
+
+struct Page {
+    DevBuf px;
+    int w = 0, h = 0;
+};
+
+struct BatchSlot {
+    pfcu_batch_desc desc{};
+    PinnedBuf host_meta;  // the four metadata vectors, packed, kept for replay
+    size_t off_backdrops = 0, off_meta = 0, off_dice = 0, off_tpi = 0, meta_bytes = 0;
+    DevBuf dev_meta, tile_word, fill_cursor, col_backdrop, tile_state, lines, line_path, fills, z, fb_count,
+        fb_cursor, prims, alpha_tiles, scan_desc0, scan_desc1;
+    uint32_t line_cap = 0, fill_cap = 0;
+    BatchView view{};
+    bool prepared = false;
+};
+
+enum CmdKind { CMD_PREPARE, CMD_DRAW };
+struct Cmd {
+    CmdKind kind;
+    int slot;
+    int target_page, color_page, clear;
+    uint32_t sampling_flags;
+    float clear_color[4];
+};
+
+}  // namespace
+
+struct pfcu_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // static resources
+    DevBuf lut;
+    int lut_w = 0, lut_h = 0;
+    DevBuf dummy_px;
+    // target
+    DevBuf own_target;
+    TargetView target{};
+    float view_box[4] = {0, 0, 0, 0};
+    // scene
+    DevBuf points[2], indices[2];
+    uint32_t n_points[2] = {0, 0}, n_segments[2] = {0, 0};
+    PinnedBuf stage_scene[2];
+    DevBuf metadata;
+    uint32_t metadata_rows = 0;
+    PinnedBuf stage_metadata;
+    Page pages[MAX_PAGES];
+    PinnedBuf stage_page;
+    // frame
+    std::vector<BatchSlot> slots;
+    int slots_used = 0;
+    std::vector<Cmd> cmds;
+    bool frame_open = false, in_flight = false, event_begin_recorded = false;
+    DevBuf counters;  // BatchCounters[MAX_SLOTS] + frame alpha counter at the end
+    DevBuf masks;
+    uint32_t mask_cap = 0;
+    PinnedBuf host_counters;
+    uint32_t launches = 0, retries = 0;
+    pfcu_frame_stats last_stats{};
+};
+
+namespace {
+
+uint32_t *frame_alpha_counter(pfcu_ctx *c) {
+    return reinterpret_cast<uint32_t *>(c->counters.as<BatchCounters>() + MAX_SLOTS);
+}
+
+int find_slot(pfcu_ctx *c, uint32_t batch_id) {
+    for (int i = 0; i < c->slots_used; i++)
+        if (c->slots[i].prepared && c->slots[i].desc.batch_id == batch_id) return i;
+    return -1;
+}
+
+int sync_if_in_flight(pfcu_ctx *c) {
+    if (c->in_flight) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->in_flight = false;
+    }
+    return PFCU_OK;
+}
+
+// (Re)build the device view of a slot and enqueue prepare_tiles for it.
+int enqueue_prepare(pfcu_ctx *c, int slot_index) {
+    BatchSlot &s = c->slots[slot_index];
+    const pfcu_batch_desc &d = s.desc;
+    const uint32_t fbt = (uint32_t)(((c->target.width + TILE - 1) / TILE) * ((c->target.height + TILE - 1) / TILE));
+    const size_t D = std::max<uint32_t>(d.tile_count, 1), C = std::max<uint32_t>(d.column_count, 1);
+    const size_t T = std::max<uint32_t>(fbt, 1);
+    CUDA_TRY(s.dev_meta.ensure(s.meta_bytes));
+    CUDA_TRY(s.tile_word.ensure(D * 4));
+    CUDA_TRY(s.fill_cursor.ensure(D * 4));
+    CUDA_TRY(s.col_backdrop.ensure(C * 4));
+    CUDA_TRY(s.tile_state.ensure(D * sizeof(TileState)));
+    CUDA_TRY(s.lines.ensure((size_t)s.line_cap * sizeof(float4)));
+    CUDA_TRY(s.line_path.ensure((size_t)s.line_cap * 4));
+    CUDA_TRY(s.fills.ensure((size_t)s.fill_cap * sizeof(uint2)));
+    CUDA_TRY(s.z.ensure(T * 4));
+    CUDA_TRY(s.fb_count.ensure(T * 4));
+    CUDA_TRY(s.fb_cursor.ensure(T * 4));
+    CUDA_TRY(s.prims.ensure(D * sizeof(TilePrim)));
+    CUDA_TRY(s.alpha_tiles.ensure(D * sizeof(AlphaTile)));
+    CUDA_TRY(s.scan_desc0.ensure((D / 2048 + 2) * 8));
+    CUDA_TRY(s.scan_desc1.ensure((T / 2048 + 2) * 8));
+    if (s.meta_bytes)
+        CUDA_TRY(cudaMemcpyAsync(s.dev_meta.p, s.host_meta.p, s.meta_bytes, cudaMemcpyHostToDevice, c->stream));
+
+    BatchView v{};
+    const char *m = s.dev_meta.as<char>();
+    v.backdrops = reinterpret_cast<const pfcu_backdrop_info *>(m + s.off_backdrops);
+    v.meta = reinterpret_cast<const pfcu_propagate_metadata *>(m + s.off_meta);
+    v.dice = reinterpret_cast<const pfcu_dice_metadata *>(m + s.off_dice);
+    v.tpi = reinterpret_cast<const pfcu_tile_path_info *>(m + s.off_tpi);
+    const int which = d.path_source ? 1 : 0;
+    v.points = c->points[which].as<float2>();
+    v.indices = c->indices[which].as<uint2>();
+    v.n_points = c->n_points[which];
+    v.n_segments_total = c->n_segments[which];
+    v.path_count = d.path_count;
+    v.tile_count = d.tile_count;
+    v.segment_count = d.segment_count;
+    v.column_count = d.column_count;
+    memcpy(v.transform, d.transform, sizeof(v.transform));
+    v.identity_transform = d.transform[0] == 1.0f && d.transform[1] == 0.0f && d.transform[2] == 0.0f &&
+                           d.transform[3] == 1.0f && d.transform[4] == 0.0f && d.transform[5] == 0.0f;
+    memcpy(v.view_box, c->view_box, sizeof(v.view_box));
+    v.fb_tw = (c->target.width + TILE - 1) / TILE;
+    v.fb_th = (c->target.height + TILE - 1) / TILE;
+    v.counters = c->counters.as<BatchCounters>() + slot_index;
+    v.tile_word = s.tile_word.as<uint32_t>();
+    v.fill_cursor = s.fill_cursor.as<uint32_t>();
+    v.col_backdrop = s.col_backdrop.as<int32_t>();
+    v.tile_state = s.tile_state.as<TileState>();
+    v.lines = s.lines.as<float4>();
+    v.line_path = s.line_path.as<uint32_t>();
+    v.line_capacity = s.line_cap;
+    v.fills = s.fills.as<uint2>();
+    v.fill_capacity = s.fill_cap;
+    v.z = s.z.as<int32_t>();
+    v.fb_count = s.fb_count.as<uint32_t>();
+    v.fb_cursor = s.fb_cursor.as<uint32_t>();
+    v.prims = s.prims.as<TilePrim>();
+    v.prim_capacity = d.tile_count;
+    v.alpha_tiles = s.alpha_tiles.as<AlphaTile>();
+    v.alpha_capacity = d.tile_count;
+    v.scan_desc[0] = s.scan_desc0.as<unsigned long long>();
+    v.scan_desc[1] = s.scan_desc1.as<unsigned long long>();
+    v.clip_meta = nullptr;
+    v.clip_tile_state = nullptr;
+    v.clip_path_count = 0;
+    if (d.clip_batch_id >= 0) {
+        const int cs = find_slot(c, (uint32_t)d.clip_batch_id);
+        if (cs >= 0 && cs != slot_index) {
+            v.clip_meta = c->slots[cs].view.meta;
+            v.clip_tile_state = c->slots[cs].view.tile_state;
+            v.clip_path_count = c->slots[cs].desc.path_count;
+        }
+    }
+    v.frame_alpha_counter = frame_alpha_counter(c);
+    v.masks = c->masks.as<uint8_t>();
+    v.mask_capacity = c->mask_cap;
+    s.view = v;
+    s.prepared = true;
+
+    PaintView pv{};
+    pv.area_lut = c->lut.as<uint8_t>();
+    pv.lut_w = c->lut_w;
+    pv.lut_h = c->lut_h;
+
+    CUDA_TRY(launch_init(v, c->stream));
+    CUDA_TRY(launch_dice(v, c->stream));
+    CUDA_TRY(launch_bin_count(v, c->stream));
+    CUDA_TRY(launch_scan_tiles(v, c->stream));
+    CUDA_TRY(launch_bin_scatter(v, c->stream));
+    CUDA_TRY(launch_propagate(v, c->stream));
+    CUDA_TRY(launch_scan_fb(v, c->stream));
+    CUDA_TRY(launch_list_scatter(v, c->stream));
+    CUDA_TRY(launch_fill(v, pv, c->stream));
+    c->launches += 9;
+    c->in_flight = true;
+    return PFCU_OK;
+}
+
+int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
+    BatchSlot &s = c->slots[cmd.slot];
+    TargetView t = c->target;
+    int clear = cmd.clear;
+    if (cmd.target_page >= 0) {
+        if (cmd.target_page >= MAX_PAGES || !c->pages[cmd.target_page].px.p)
+            return fail(PFCU_ERR_INVALID, "render target page %d not allocated", cmd.target_page);
+        Page &pg = c->pages[cmd.target_page];
+        t.pixels = pg.px.as<uint8_t>();
+        t.pitch = (size_t)pg.w * 4;
+        t.width = pg.w;
+        t.height = pg.h;
+        clear = 1;  // d3d11/renderer.cpp:382-386
+    }
+    PaintView pv{};
+    pv.metadata = c->metadata.as<uint16_t>();
+    pv.metadata_rows = c->metadata_rows;
+    pv.color_px = c->dummy_px.as<uint8_t>();
+    pv.color_w = pv.color_h = 1;
+    pv.sampling_flags = 0;
+    if (cmd.color_page >= 0 && cmd.color_page < MAX_PAGES && c->pages[cmd.color_page].px.p) {
+        Page &pg = c->pages[cmd.color_page];
+        pv.color_px = pg.px.as<uint8_t>();
+        pv.color_w = pg.w;
+        pv.color_h = pg.h;
+        pv.sampling_flags = cmd.sampling_flags;
+    }
+    pv.area_lut = c->lut.as<uint8_t>();
+    pv.lut_w = c->lut_w;
+    pv.lut_h = c->lut_h;
+    // masks may have been reallocated since the batch was prepared (growth happens only between attempts)
+    s.view.masks = c->masks.as<uint8_t>();
+    s.view.mask_capacity = c->mask_cap;
+    CUDA_TRY(launch_composite(s.view, pv, t, clear, cmd.clear_color, c->stream));
+    c->launches += 1;
+    c->in_flight = true;
+    return PFCU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pfcu_abi_version(void) { return PFCU_ABI_VERSION; }
+const char *pfcu_last_error(void) { return g_last_error.c_str(); }
+
+int pfcu_create(int device_ordinal, pfcu_ctx **out) {
+    if (!out) return fail(PFCU_ERR_INVALID, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(PFCU_ERR_CUDA, "no CUDA device (%s); pfcu has no CPU fallback", cudaGetErrorString(e));
+    if (device_ordinal < 0 || device_ordinal >= n) return fail(PFCU_ERR_INVALID, "device %d out of range", device_ordinal);
+    CUDA_TRY(cudaSetDevice(device_ordinal));
+    pfcu_ctx *c = new pfcu_ctx;
+    c->device = device_ordinal;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CUDA_TRY(cudaEventCreate(&c->ev_begin));
+    CUDA_TRY(cudaEventCreate(&c->ev_end));
+    CUDA_TRY(c->counters.ensure(sizeof(BatchCounters) * (MAX_SLOTS + 1)));
+    CUDA_TRY(cudaMemset(c->counters.p, 0, sizeof(BatchCounters) * (MAX_SLOTS + 1)));
+    CUDA_TRY(c->host_counters.ensure(sizeof(BatchCounters) * (MAX_SLOTS + 1)));
+    CUDA_TRY(c->dummy_px.ensure(16));
+    CUDA_TRY(cudaMemset(c->dummy_px.p, 0, 16));
+    c->slots.resize(MAX_SLOTS);
+    *out = c;
+    return PFCU_OK;
+}
+
+void pfcu_destroy(pfcu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto &s : c->slots) {
+        s.host_meta.release();
+        for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
+                          &s.line_path, &s.fills, &s.z, &s.fb_count, &s.fb_cursor, &s.prims, &s.alpha_tiles,
+                          &s.scan_desc0, &s.scan_desc1})
+            b->release();
+    }
+    for (auto &p : c->pages) p.px.release();
+    for (int i = 0; i < 2; i++) {
+        c->points[i].release();
+        c->indices[i].release();
+        c->stage_scene[i].release();
+    }
+    c->lut.release();
+    c->dummy_px.release();
+    c->own_target.release();
+    c->metadata.release();
+    c->stage_metadata.release();
+    c->stage_page.release();
+    c->counters.release();
+    c->masks.release();
+    c->host_counters.release();
+    cudaEventDestroy(c->ev_begin);
+    cudaEventDestroy(c->ev_end);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int pfcu_set_stream(pfcu_ctx *c, void *cuda_stream) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return PFCU_OK;
+}
+
+void *pfcu_get_stream(pfcu_ctx *c) { return c ? (void *)c->stream : nullptr; }
+
+int pfcu_set_area_lut(pfcu_ctx *c, const uint8_t *rgba, int width, int height) {
+    if (!c || !rgba || width <= 0 || height <= 0) return fail(PFCU_ERR_INVALID, "bad area LUT");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    CUDA_TRY(c->lut.ensure((size_t)width * height * 4));
+    CUDA_TRY(cudaMemcpy(c->lut.p, rgba, (size_t)width * height * 4, cudaMemcpyHostToDevice));
+    c->lut_w = width;
+    c->lut_h = height;
+    return PFCU_OK;
+}
+
+int pfcu_set_target(pfcu_ctx *c, int width, int height, void *rgba8_dev, size_t pitch_bytes, const float view_box[4]) {
+    if (!c || width <= 0 || height <= 0 || !view_box) return fail(PFCU_ERR_INVALID, "bad target");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    if (rgba8_dev) {
+        if (pitch_bytes < (size_t)width * 4 || (pitch_bytes & 15) || ((uintptr_t)rgba8_dev & 15))
+            return fail(PFCU_ERR_INVALID, "target rows must be 16-byte aligned and at least width*4 bytes");
+        c->target.pixels = static_cast<uint8_t *>(rgba8_dev);
+        c->target.pitch = pitch_bytes;
+    } else {
+        const size_t pitch = ((size_t)width * 4 + 15) & ~(size_t)15;
+        CUDA_TRY(c->own_target.ensure(pitch * height));
+        CUDA_TRY(cudaMemsetAsync(c->own_target.p, 0, pitch * height, c->stream));
+        c->target.pixels = c->own_target.as<uint8_t>();
+        c->target.pitch = pitch;
+    }
+    c->target.width = width;
+    c->target.height = height;
+    memcpy(c->view_box, view_box, sizeof(c->view_box));
+    return PFCU_OK;
+}
+
+int pfcu_upload_scene(pfcu_ctx *c, int which, const float *points, uint32_t n_points, const uint32_t *indices,
+                      uint32_t n_segments) {
+    if (!c || which < 0 || which > 1 || (n_points && !points) || (n_segments && !indices))
+        return fail(PFCU_ERR_INVALID, "bad scene upload");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    const size_t pb = (size_t)n_points * 8, ib = (size_t)n_segments * 8;
+    CUDA_TRY(c->points[which].ensure(std::max<size_t>(pb, 8)));
+    CUDA_TRY(c->indices[which].ensure(std::max<size_t>(ib, 8)));
+    CUDA_TRY(c->stage_scene[which].ensure(pb + ib + 16));
+    char *st = static_cast<char *>(c->stage_scene[which].p);
+    if (pb) {
+        memcpy(st, points, pb);
+        CUDA_TRY(cudaMemcpyAsync(c->points[which].p, st, pb, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (ib) {
+        memcpy(st + pb, indices, ib);
+        CUDA_TRY(cudaMemcpyAsync(c->indices[which].p, st + pb, ib, cudaMemcpyHostToDevice, c->stream));
+    }
+    c->n_points[which] = n_points;
+    c->n_segments[which] = n_segments;
+    c->in_flight = true;
+    return PFCU_OK;
+}
+
+int pfcu_upload_paint_metadata(pfcu_ctx *c, const uint16_t *half_texels, uint32_t n_rows) {
+    if (!c || (n_rows && !half_texels)) return fail(PFCU_ERR_INVALID, "bad metadata upload");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    const size_t bytes = (size_t)n_rows * 1280 * 4 * 2;
+    CUDA_TRY(c->metadata.ensure(std::max<size_t>(bytes, 16)));
+    CUDA_TRY(c->stage_metadata.ensure(std::max<size_t>(bytes, 16)));
+    if (bytes) {
+        memcpy(c->stage_metadata.p, half_texels, bytes);
+        CUDA_TRY(cudaMemcpyAsync(c->metadata.p, c->stage_metadata.p, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->in_flight = true;
+    }
+    c->metadata_rows = n_rows;
+    return PFCU_OK;
+}
+
+int pfcu_alloc_page(pfcu_ctx *c, uint32_t page, int width, int height) {
+    if (!c || page >= MAX_PAGES || width <= 0 || height <= 0) return fail(PFCU_ERR_INVALID, "bad page");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    Page &pg = c->pages[page];
+    CUDA_TRY(pg.px.ensure((size_t)width * height * 4));
+    CUDA_TRY(cudaMemset(pg.px.p, 0, (size_t)width * height * 4));
+    pg.w = width;
+    pg.h = height;
+    return PFCU_OK;
+}
+
+int pfcu_upload_page_region(pfcu_ctx *c, uint32_t page, int x, int y, int width, int height, const uint8_t *rgba) {
+    if (!c || page >= MAX_PAGES || !c->pages[page].px.p) return fail(PFCU_ERR_INVALID, "texture page not allocated");
+    Page &pg = c->pages[page];
+    if (!rgba || x < 0 || y < 0 || width <= 0 || height <= 0 || x + width > pg.w || y + height > pg.h)
+        return fail(PFCU_ERR_INVALID, "tried to write invalid region of a texture");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    CUDA_TRY(cudaMemcpy2D(pg.px.as<uint8_t>() + ((size_t)y * pg.w + x) * 4, (size_t)pg.w * 4, rgba, (size_t)width * 4,
+                          (size_t)width * 4, height, cudaMemcpyHostToDevice));
+    return PFCU_OK;
+}
+
+int pfcu_begin_frame(pfcu_ctx *c) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    if (!c->target.pixels) return fail(PFCU_ERR_STATE, "pfcu_set_target has not been called");
+    CUDA_TRY(cudaSetDevice(c->device));
+    for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
+    c->slots_used = 0;
+    c->cmds.clear();
+    c->launches = 0;
+    c->retries = 0;
+    c->frame_open = true;
+    c->event_begin_recorded = false;
+    return PFCU_OK;
+}
+
+int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
+    if (!c || !d) return fail(PFCU_ERR_INVALID, "null argument");
+    if (!c->frame_open) return fail(PFCU_ERR_STATE, "pfcu_begin_frame has not been called");
+    if (c->slots_used >= MAX_SLOTS) return fail(PFCU_ERR_INVALID, "too many batches in one frame");
+    if ((d->path_count && (!d->propagate_metadata || !d->dice_metadata || !d->tile_path_info)) ||
+        (d->column_count && !d->backdrops))
+        return fail(PFCU_ERR_INVALID, "batch metadata missing");
+    if (d->tile_count >= (1u << 24)) return fail(PFCU_ERR_INVALID, "tile_count exceeds the 24-bit alpha tile id range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int slot_index = c->slots_used;
+    BatchSlot &s = c->slots[slot_index];
+    if (!c->event_begin_recorded) {
+        CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
+        c->event_begin_recorded = true;
+        // first batch of the frame: reset the frame-global alpha tile counter
+        CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
+        if (!c->mask_cap) {
+            c->mask_cap = 16384;
+            CUDA_TRY(c->masks.ensure((size_t)c->mask_cap * 256));
+        }
+    }
+    s.desc = *d;
+    // pack the metadata vectors into pinned memory (stable for the async copy and for replay)
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    s.off_backdrops = 0;
+    s.off_meta = align16(s.off_backdrops + (size_t)d->column_count * sizeof(pfcu_backdrop_info));
+    s.off_dice = align16(s.off_meta + (size_t)d->path_count * sizeof(pfcu_propagate_metadata));
+    s.off_tpi = align16(s.off_dice + (size_t)d->path_count * sizeof(pfcu_dice_metadata));
+    s.meta_bytes = align16(s.off_tpi + (size_t)d->path_count * sizeof(pfcu_tile_path_info));
+    CUDA_TRY(s.host_meta.ensure(std::max<size_t>(s.meta_bytes, 16)));
+    char *hm = static_cast<char *>(s.host_meta.p);
+    if (d->column_count) memcpy(hm + s.off_backdrops, d->backdrops, (size_t)d->column_count * sizeof(pfcu_backdrop_info));
+    if (d->path_count) {
+        memcpy(hm + s.off_meta, d->propagate_metadata, (size_t)d->path_count * sizeof(pfcu_propagate_metadata));
+        memcpy(hm + s.off_dice, d->dice_metadata, (size_t)d->path_count * sizeof(pfcu_dice_metadata));
+        memcpy(hm + s.off_tpi, d->tile_path_info, (size_t)d->path_count * sizeof(pfcu_tile_path_info));
+    }
+    s.desc.backdrops = nullptr;  // the caller's vectors are not retained
+    s.desc.propagate_metadata = nullptr;
+    s.desc.dice_metadata = nullptr;
+    s.desc.tile_path_info = nullptr;
+    // capacities persist across frames; first guess from the segment count (dice.comp's 16K start, renderer.cpp:45)
+    s.line_cap = std::max<uint32_t>(s.line_cap, (uint32_t)round_up_pow2(std::max<size_t>(16384, (size_t)d->segment_count * 8)));
+    s.fill_cap = std::max<uint32_t>(s.fill_cap, (uint32_t)round_up_pow2(std::max<size_t>(65536, (size_t)s.line_cap * 2)));
+    c->slots_used++;
+    Cmd cmd{};
+    cmd.kind = CMD_PREPARE;
+    cmd.slot = slot_index;
+    c->cmds.push_back(cmd);
+    return enqueue_prepare(c, slot_index);
+}
+
+int pfcu_draw_batch(pfcu_ctx *c, uint32_t batch_id, int target_page, int color_page, uint32_t sampling_flags, int clear,
+                    const float clear_color[4]) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    if (!c->frame_open) return fail(PFCU_ERR_STATE, "pfcu_begin_frame has not been called");
+    const int slot = find_slot(c, batch_id);
+    if (slot < 0) return fail(PFCU_ERR_STATE, "batch %u has not been prepared in this frame", batch_id);
+    CUDA_TRY(cudaSetDevice(c->device));
+    Cmd cmd{};
+    cmd.kind = CMD_DRAW;
+    cmd.slot = slot;
+    cmd.target_page = target_page;
+    cmd.color_page = color_page;
+    cmd.sampling_flags = sampling_flags;
+    cmd.clear = clear;
+    for (int i = 0; i < 4; i++) cmd.clear_color[i] = clear_color ? clear_color[i] : 0.0f;
+    c->cmds.push_back(cmd);
+    return enqueue_draw(c, cmd);
+}
+
+int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    if (!c->frame_open) return fail(PFCU_ERR_STATE, "no frame is open");
+    CUDA_TRY(cudaSetDevice(c->device));
+    BatchCounters *hc = static_cast<BatchCounters *>(c->host_counters.p);
+    const size_t cbytes = sizeof(BatchCounters) * (MAX_SLOTS + 1);
+    for (int attempt = 0;; attempt++) {
+        if (c->event_begin_recorded) CUDA_TRY(cudaEventRecord(c->ev_end, c->stream));
+        // the one read-back of the frame: counters of every batch + the frame alpha counter
+        const size_t used = sizeof(BatchCounters) * (size_t)std::max(c->slots_used, 1);
+        CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, used, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(hc + MAX_SLOTS, frame_alpha_counter(c), sizeof(BatchCounters), cudaMemcpyDeviceToHost,
+                                 c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->in_flight = false;
+        (void)cbytes;
+        uint32_t overflow = 0;
+        const uint32_t frame_alpha = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
+        for (int i = 0; i < c->slots_used; i++) {
+            BatchSlot &s = c->slots[i];
+            overflow |= hc[i].overflow;
+            if (hc[i].n_lines > s.line_cap) s.line_cap = (uint32_t)round_up_pow2(hc[i].n_lines);
+            if (hc[i].n_fills > s.fill_cap) s.fill_cap = (uint32_t)round_up_pow2(hc[i].n_fills);
+            // a line overflow hides the true fill count: make sure fills can grow with the lines
+            if ((hc[i].overflow & OVF_LINES) && s.fill_cap < s.line_cap * 2) s.fill_cap = s.line_cap * 2;
+        }
+        if (frame_alpha > c->mask_cap) {
+            overflow |= OVF_ALPHA;
+            c->mask_cap = (uint32_t)round_up_pow2(frame_alpha);
+            CUDA_TRY(c->masks.ensure((size_t)c->mask_cap * 256));
+        }
+        if (!overflow) break;
+        if (attempt >= 3) {
+            c->frame_open = false;
+            return fail(PFCU_ERR_OVERFLOW, "ran out of space after %d attempts (flags 0x%x)", attempt + 1, overflow);
+        }
+        // grow and replay the recorded frame
+        c->retries++;
+        for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
+        CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
+        CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
+        for (const Cmd &cmd : c->cmds) {
+            const int r = cmd.kind == CMD_PREPARE ? enqueue_prepare(c, cmd.slot) : enqueue_draw(c, cmd);
+            if (r) {
+                c->frame_open = false;
+                return r;
+            }
+        }
+    }
+    pfcu_frame_stats st{};
+    st.batches = (uint32_t)c->slots_used;
+    for (int i = 0; i < c->slots_used; i++) {
+        st.segments += c->slots[i].desc.segment_count;
+        st.lines += hc[i].n_lines;
+        st.fills += hc[i].n_fills;
+        st.dense_tiles += c->slots[i].desc.tile_count;
+        st.listed_tiles += hc[i].n_list_entries;
+    }
+    st.alpha_tiles = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
+    st.fb_tiles = (uint32_t)(((c->target.width + TILE - 1) / TILE) * ((c->target.height + TILE - 1) / TILE));
+    st.retries = c->retries;
+    st.kernel_launches = c->launches;
+    if (c->event_begin_recorded) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) st.gpu_ms = ms;
+    }
+    c->last_stats = st;
+    if (stats) *stats = st;
+    c->frame_open = false;
+    return PFCU_OK;
+}
+
+int pfcu_read_target(pfcu_ctx *c, uint8_t *host) {
+    if (!c || !host || !c->target.pixels) return fail(PFCU_ERR_INVALID, "no target");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy2D(host, (size_t)c->target.width * 4, c->target.pixels, c->target.pitch,
+                          (size_t)c->target.width * 4, c->target.height, cudaMemcpyDeviceToHost));
+    return PFCU_OK;
+}
+
+int pfcu_read_page(pfcu_ctx *c, uint32_t page, uint8_t *host) {
+    if (!c || !host || page >= MAX_PAGES || !c->pages[page].px.p) return fail(PFCU_ERR_INVALID, "texture page not allocated");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(host, c->pages[page].px.p, (size_t)c->pages[page].w * c->pages[page].h * 4, cudaMemcpyDeviceToHost));
+    return PFCU_OK;
+}
+
+void *pfcu_target_device_ptr(pfcu_ctx *c, size_t *pitch) {
+    if (!c) return nullptr;
+    if (pitch) *pitch = c->target.pitch;
+    return c->target.pixels;
+}
+
+// ------------------------------------------------------------------------------------------------ parity taps
+
+static int tap_slot(pfcu_ctx *c, uint32_t batch_id) {
+    if (!c) {
+        fail(PFCU_ERR_INVALID, "ctx is null");
+        return -1;
+    }
+    for (int i = 0; i < c->slots_used; i++)
+        if (c->slots[i].desc.batch_id == batch_id) return i;
+    fail(PFCU_ERR_INVALID, "batch %u not in the last frame", batch_id);
+    return -1;
+}
+
+#define TAP_TRY(expr)                                                           \
+    do {                                                                        \
+        cudaError_t _e = (expr);                                                \
+        if (_e != cudaSuccess) {                                                \
+            fail(PFCU_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));       \
+            return -1;                                                          \
+        }                                                                       \
+    } while (0)
+
+int64_t pfcu_read_lines(pfcu_ctx *c, uint32_t batch_id, pfcu_line *out) {
+    const int si = tap_slot(c, batch_id);
+    if (si < 0) return -1;
+    cudaSetDevice(c->device);
+    TAP_TRY(cudaStreamSynchronize(c->stream));
+    BatchSlot &s = c->slots[si];
+    BatchCounters bc;
+    TAP_TRY(cudaMemcpy(&bc, s.view.counters, sizeof(bc), cudaMemcpyDeviceToHost));
+    const uint32_t n = std::min(bc.n_lines, s.line_cap);
+    if (!out) return n;
+    std::vector<float4> l(n);
+    std::vector<uint32_t> p(n);
+    if (n) {
+        TAP_TRY(cudaMemcpy(l.data(), s.view.lines, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+        TAP_TRY(cudaMemcpy(p.data(), s.view.line_path, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    }
+    for (uint32_t i = 0; i < n; i++) out[i] = pfcu_line{l[i].x, l[i].y, l[i].z, l[i].w, p[i]};
+    return n;
+}
+
+int64_t pfcu_read_fills(pfcu_ctx *c, uint32_t batch_id, pfcu_fill *out) {
+    const int si = tap_slot(c, batch_id);
+    if (si < 0) return -1;
+    cudaSetDevice(c->device);
+    TAP_TRY(cudaStreamSynchronize(c->stream));
+    BatchSlot &s = c->slots[si];
+    BatchCounters bc;
+    TAP_TRY(cudaMemcpy(&bc, s.view.counters, sizeof(bc), cudaMemcpyDeviceToHost));
+    const uint32_t n = std::min(bc.n_fills, s.fill_cap);
+    if (!out) return n;
+    const uint32_t D = s.desc.tile_count;
+    std::vector<uint32_t> word(D), cursor(D);
+    std::vector<uint2> f(n);
+    if (D) {
+        TAP_TRY(cudaMemcpy(word.data(), s.view.tile_word, (size_t)D * 4, cudaMemcpyDeviceToHost));
+        TAP_TRY(cudaMemcpy(cursor.data(), s.view.fill_cursor, (size_t)D * 4, cudaMemcpyDeviceToHost));
+    }
+    if (n) TAP_TRY(cudaMemcpy(f.data(), s.view.fills, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost));
+    size_t w = 0;
+    for (uint32_t t = 0; t < D; t++) {
+        const uint32_t cnt = word[t] & 0x00ffffffu, end = std::min(cursor[t], n);
+        const uint32_t begin = end >= cnt ? end - cnt : 0;
+        const size_t w0 = w;
+        for (uint32_t k = begin; k < end && w < n; k++) {
+            pfcu_fill q;
+            q.tile_index = t;
+            q.from_x = (uint16_t)(f[k].x & 0xffff);
+            q.from_y = (uint16_t)(f[k].x >> 16);
+            q.to_x = (uint16_t)(f[k].y & 0xffff);
+            q.to_y = (uint16_t)(f[k].y >> 16);
+            out[w++] = q;
+        }
+        std::sort(out + w0, out + w, [](const pfcu_fill &a, const pfcu_fill &b) {
+            if (a.from_x != b.from_x) return a.from_x < b.from_x;
+            if (a.from_y != b.from_y) return a.from_y < b.from_y;
+            if (a.to_x != b.to_x) return a.to_x < b.to_x;
+            return a.to_y < b.to_y;
+        });
+    }
+    return (int64_t)w;
+}
+
+int64_t pfcu_read_tiles(pfcu_ctx *c, uint32_t batch_id, pfcu_tile *out) {
+    const int si = tap_slot(c, batch_id);
+    if (si < 0) return -1;
+    cudaSetDevice(c->device);
+    TAP_TRY(cudaStreamSynchronize(c->stream));
+    BatchSlot &s = c->slots[si];
+    const uint32_t D = s.desc.tile_count;
+    if (!out) return D;
+    BatchCounters bc;
+    TAP_TRY(cudaMemcpy(&bc, s.view.counters, sizeof(bc), cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> word(D);
+    std::vector<TileState> st(D);
+    std::vector<AlphaTile> at(D);
+    if (D) {
+        TAP_TRY(cudaMemcpy(word.data(), s.view.tile_word, (size_t)D * 4, cudaMemcpyDeviceToHost));
+        TAP_TRY(cudaMemcpy(st.data(), s.view.tile_state, (size_t)D * sizeof(TileState), cudaMemcpyDeviceToHost));
+        TAP_TRY(cudaMemcpy(at.data(), s.view.alpha_tiles, (size_t)D * sizeof(AlphaTile), cudaMemcpyDeviceToHost));
+    }
+    for (uint32_t t = 0; t < D; t++) {
+        pfcu_tile q{};
+        q.alpha_tile_id = st[t].alpha;
+        q.clip_alpha_tile_id = -1;
+        if ((st[t].packed & (1u << 25)) && st[t].alpha >= 0) {
+            const uint32_t local = (uint32_t)st[t].alpha - bc.first_alpha;
+            if (local < D && at[local].tile_index == t) q.clip_alpha_tile_id = at[local].clip_alpha;
+        }
+        q.fill_count = (int32_t)(word[t] & 0x00ffffffu);
+        q.backdrop = (int8_t)(st[t].packed & 0xff);
+        q.backdrop_delta = (int8_t)((st[t].packed >> 8) & 0xff);
+        q.backdrop_d3d9 = (int8_t)((st[t].packed >> 16) & 0xff);
+        q.listed = (uint8_t)((st[t].packed >> 24) & 1);
+        out[t] = q;
+    }
+    return D;
+}
+
+int64_t pfcu_read_z(pfcu_ctx *c, uint32_t batch_id, int32_t *out) {
+    const int si = tap_slot(c, batch_id);
+    if (si < 0) return -1;
+    cudaSetDevice(c->device);
+    TAP_TRY(cudaStreamSynchronize(c->stream));
+    BatchSlot &s = c->slots[si];
+    const uint32_t T = (uint32_t)(s.view.fb_tw * s.view.fb_th);
+    if (out && T) TAP_TRY(cudaMemcpy(out, s.view.z, (size_t)T * 4, cudaMemcpyDeviceToHost));
+    return T;
+}
+
+int64_t pfcu_read_tile_lists(pfcu_ctx *c, uint32_t batch_id, uint32_t *offsets, uint32_t *tiles) {
+    const int si = tap_slot(c, batch_id);
+    if (si < 0) return -1;
+    cudaSetDevice(c->device);
+    TAP_TRY(cudaStreamSynchronize(c->stream));
+    BatchSlot &s = c->slots[si];
+    const uint32_t T = (uint32_t)(s.view.fb_tw * s.view.fb_th), D = s.desc.tile_count;
+    std::vector<uint32_t> cnt(T), cur(T);
+    std::vector<int32_t> z(T);
+    std::vector<TilePrim> prims(D);
+    if (T) {
+        TAP_TRY(cudaMemcpy(cnt.data(), s.view.fb_count, (size_t)T * 4, cudaMemcpyDeviceToHost));
+        TAP_TRY(cudaMemcpy(cur.data(), s.view.fb_cursor, (size_t)T * 4, cudaMemcpyDeviceToHost));
+        TAP_TRY(cudaMemcpy(z.data(), s.view.z, (size_t)T * 4, cudaMemcpyDeviceToHost));
+    }
+    if (D) TAP_TRY(cudaMemcpy(prims.data(), s.view.prims, (size_t)D * sizeof(TilePrim), cudaMemcpyDeviceToHost));
+    int64_t total = 0;
+    std::vector<uint32_t> keys;
+    for (uint32_t t = 0; t < T; t++) {
+        if (offsets) offsets[t] = (uint32_t)total;
+        const uint32_t end = std::min(cur[t], D), begin = end >= cnt[t] ? end - cnt[t] : 0;
+        keys.clear();
+        for (uint32_t k = begin; k < end; k++)
+            if ((int32_t)prims[k].key >= z[t]) keys.push_back(prims[k].key);
+        std::sort(keys.begin(), keys.end());
+        if (tiles) memcpy(tiles + total, keys.data(), keys.size() * 4);
+        total += (int64_t)keys.size();
+    }
+    if (offsets) offsets[T] = (uint32_t)total;
+    return total;
+}
+
+int pfcu_read_mask(pfcu_ctx *c, uint32_t alpha_tile_id, uint8_t out[256]) {
+    if (!c || !out) return fail(PFCU_ERR_INVALID, "null argument");
+    if (alpha_tile_id >= c->mask_cap) return fail(PFCU_ERR_INVALID, "alpha tile id out of range");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy(out, c->masks.as<uint8_t>() + (size_t)alpha_tile_id * 256, 256, cudaMemcpyDeviceToHost));
+    return PFCU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+// Internal device-side contract between the C-ABI (pfcu_api.cu) and the kernels
+// (pfcu_geom.cu: dice / bin, compiled with -fmad=false for bit-exactness against the reference's x86 tiler;
+//  pfcu_tiles.cu: init / scan / propagate / list building; pfcu_raster.cu: fill / composite).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pfcu.h"
+
+namespace pfcu {
+
+constexpr int TILE = 16;
+constexpr uint32_t CURVE_IS_QUADRATIC = 0x80000000u;  // pathfinder/core/data/data.h:19
+constexpr uint32_t CURVE_IS_CUBIC = 0x40000000u;      // pathfinder/core/data/data.h:20
+constexpr float FLATTENING_TOLERANCE = 1.0f;          // pathfinder/core/d3d9/tiler.cpp:15
+constexpr float FLOAT_EPSILON = 0.0001f;              // pathfinder/common/math/basic.h:11
+// The reference recursion / tile walk are unbounded; the oracle (oracle/pf_oracle.c) uses the same bounds.
+constexpr int MAX_FLATTEN_DEPTH = 24;
+constexpr int MAX_DDA_STEPS = 65536;
+
+// Device counters of one batch (one 64-byte line).
+struct BatchCounters {
+    uint32_t n_lines;        // lines emitted by dice (may exceed capacity: overflow)
+    uint32_t n_fills;        // total fills (from the scan)
+    uint32_t n_alpha;        // alpha tiles allocated by this batch
+    uint32_t first_alpha;    // frame-global id of this batch's first alpha tile
+    uint32_t n_listed;       // tiles stitched into framebuffer-tile lists
+    uint32_t overflow;       // bit 0 lines, bit 1 fills, bit 2 alpha tiles (masks), bit 3 list entries
+    uint32_t scan_ticket[2]; // dynamic tile ids for the two look-back scans
+    uint32_t n_list_entries; // total list entries (from the scan over framebuffer tiles)
+    uint32_t pad[7];
+};
+static_assert(sizeof(BatchCounters) == 64, "BatchCounters");
+
+enum OverflowBits { OVF_LINES = 1, OVF_FILLS = 2, OVF_ALPHA = 4, OVF_LIST = 8 };
+
+// Packed per-dense-tile state written by propagate.
+//   x: alpha tile id (int32, -1 none)
+//   y: bits 0-7 backdrop, 8-15 backdrop delta, 16-23 hybrid-equivalent backdrop, 24 listed, 25 has own mask
+struct TileState {
+    int32_t alpha;
+    uint32_t packed;
+};
+
+// One entry of a framebuffer tile's list (what tile.comp reads per layer, tile.comp:765-768).
+//   x: dense tile index (sort key == paint order), y: alpha tile id, z: paint | ctrl << 16 | backdrop << 24
+struct TilePrim {
+    uint32_t key;
+    int32_t alpha;
+    uint32_t ctrl_word;
+    uint32_t pad;
+};
+
+struct AlphaTile {
+    uint32_t tile_index;  // dense tile that owns the mask
+    int32_t clip_alpha;   // mask slot to min() with, or -1
+};
+
+// Everything a kernel needs to know about one batch. Passed by value.
+struct BatchView {
+    // inputs (device copies of the host vectors)
+    const pfcu_backdrop_info *backdrops;
+    const pfcu_propagate_metadata *meta;
+    const pfcu_dice_metadata *dice;
+    const pfcu_tile_path_info *tpi;
+    const float2 *points;
+    const uint2 *indices;
+    uint32_t n_points, n_segments_total;
+    uint32_t path_count, tile_count, segment_count, column_count;
+    float transform[6];
+    int identity_transform;
+    float view_box[4];
+    int fb_tw, fb_th;
+    // working set
+    BatchCounters *counters;
+    uint32_t *tile_word;    // [tile_count] low 24 bits: fill count; high 8 bits: backdrop delta
+    uint32_t *fill_cursor;  // [tile_count] exclusive fill offsets -> end offsets after bin scatter
+    int32_t *col_backdrop;  // [column_count]
+    TileState *tile_state;  // [tile_count]
+    float4 *lines;          // [line_capacity]
+    uint32_t *line_path;    // [line_capacity]
+    uint32_t line_capacity;
+    uint2 *fills;           // [fill_capacity] x = from_x | from_y << 16, y = to_x | to_y << 16
+    uint32_t fill_capacity;
+    int32_t *z;             // [fb tiles]
+    uint32_t *fb_count;     // [fb tiles] list lengths (before cull)
+    uint32_t *fb_cursor;    // [fb tiles] exclusive offsets -> end offsets after list scatter
+    TilePrim *prims;        // [prim_capacity]
+    uint32_t prim_capacity;
+    AlphaTile *alpha_tiles; // [alpha_capacity] batch-local
+    uint32_t alpha_capacity;
+    unsigned long long *scan_desc[2];  // look-back descriptors (tile_count / fb tiles)
+    // clip batch (may be null)
+    const pfcu_propagate_metadata *clip_meta;
+    const TileState *clip_tile_state;
+    uint32_t clip_path_count;
+    // frame-global
+    uint32_t *frame_alpha_counter;  // next free mask slot
+    uint8_t *masks;                 // 256 B per slot
+    uint32_t mask_capacity;         // slots
+};
+
+struct TargetView {
+    uint8_t *pixels;  // RGBA8
+    size_t pitch;     // bytes
+    int width, height;
+};
+
+struct PaintView {
+    const uint16_t *metadata;  // RGBA16F texels, 1280 per row
+    uint32_t metadata_rows;
+    const uint8_t *color_px;   // colour texture page (RGBA8) or a 1 x 1 dummy
+    int color_w, color_h;
+    uint32_t sampling_flags;
+    const uint8_t *area_lut;   // 256 x 256 RGBA8
+    int lut_w, lut_h;
+};
+
+// ---- launchers (each enqueues exactly one kernel on `s` and returns the CUDA status) --------------------------
+cudaError_t launch_init(const BatchView &b, cudaStream_t s);
+cudaError_t launch_dice(const BatchView &b, cudaStream_t s);
+cudaError_t launch_bin_count(const BatchView &b, cudaStream_t s);
+cudaError_t launch_scan_tiles(const BatchView &b, cudaStream_t s);
+cudaError_t launch_bin_scatter(const BatchView &b, cudaStream_t s);
+cudaError_t launch_propagate(const BatchView &b, cudaStream_t s);
+cudaError_t launch_scan_fb(const BatchView &b, cudaStream_t s);
+cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s);
+cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s);
+cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
+                             const float clear_color[4], cudaStream_t s);
+// tap helper: sorted + z-culled lists for the parity reader
+cudaError_t launch_export_lists(const BatchView &b, uint32_t *offsets, uint32_t *tiles, uint32_t *total,
+                                cudaStream_t s);
+
+int sm_count();
+
+}  // namespace pfcu

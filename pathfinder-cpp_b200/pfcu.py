@@ -1,0 +1,247 @@
+"""ctypes binding of the C-ABI in include/pfcu.h (lib/libpfcu.so) + a thin `Renderer` that sequences a frame
+the way the reference's RendererD3D11::draw does (pathfinder/core/d3d11/renderer.cpp:302-336).
+
+This is harness glue for tests/, bench.py and __graft_entry__.py; the product is the shared library. There is
+no fallback of any kind: if the library is missing or no CUDA device is present, construction raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpfcu.so")
+NONE = 0xFFFFFFFF
+
+EXPORTS = [
+    "pfcu_abi_version", "pfcu_last_error", "pfcu_create", "pfcu_destroy", "pfcu_set_stream", "pfcu_get_stream",
+    "pfcu_set_area_lut", "pfcu_set_target", "pfcu_upload_scene", "pfcu_upload_paint_metadata", "pfcu_alloc_page",
+    "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
+    "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
+    "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask",
+]
+
+LINE_DT = np.dtype([("from_x", "<f4"), ("from_y", "<f4"), ("to_x", "<f4"), ("to_y", "<f4"), ("path_index", "<u4")])
+FILL_DT = np.dtype([("tile_index", "<u4"), ("from_x", "<u2"), ("from_y", "<u2"), ("to_x", "<u2"), ("to_y", "<u2")])
+TILE_DT = np.dtype([("alpha_tile_id", "<i4"), ("clip_alpha_tile_id", "<i4"), ("fill_count", "<i4"),
+                    ("backdrop", "i1"), ("backdrop_delta", "i1"), ("backdrop_d3d9", "i1"), ("listed", "u1")])
+
+
+class BatchDesc(C.Structure):
+    _fields_ = [("batch_id", C.c_uint32), ("path_count", C.c_uint32), ("tile_count", C.c_uint32),
+                ("segment_count", C.c_uint32), ("column_count", C.c_uint32), ("path_source", C.c_int32),
+                ("clip_batch_id", C.c_int32), ("backdrops", C.c_void_p), ("propagate_metadata", C.c_void_p),
+                ("dice_metadata", C.c_void_p), ("tile_path_info", C.c_void_p), ("transform", C.c_float * 6)]
+
+
+class FrameStats(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("batches", "segments", "lines", "fills", "alpha_tiles", "dense_tiles",
+                                          "listed_tiles", "listed_after_cull", "fb_tiles", "max_list_len",
+                                          "overflow_flags", "retries", "kernel_launches")] + \
+               [("reserved", C.c_uint32 * 3), ("gpu_ms", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
+
+
+class PfcuError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Loads lib/libpfcu.so. Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PfcuError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(make -C pathfinder-cpp_b200)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
+        L.pfcu_last_error.restype = C.c_char_p
+        L.pfcu_create.argtypes = [i32, C.POINTER(vp)]
+        L.pfcu_destroy.argtypes = [vp]
+        L.pfcu_destroy.restype = None
+        L.pfcu_set_stream.argtypes = [vp, vp]
+        L.pfcu_get_stream.argtypes = [vp]
+        L.pfcu_get_stream.restype = vp
+        L.pfcu_set_area_lut.argtypes = [vp, vp, i32, i32]
+        L.pfcu_set_target.argtypes = [vp, i32, i32, vp, sz, vp]
+        L.pfcu_upload_scene.argtypes = [vp, i32, vp, u32, vp, u32]
+        L.pfcu_upload_paint_metadata.argtypes = [vp, vp, u32]
+        L.pfcu_alloc_page.argtypes = [vp, u32, i32, i32]
+        L.pfcu_upload_page_region.argtypes = [vp, u32, i32, i32, i32, i32, vp]
+        L.pfcu_begin_frame.argtypes = [vp]
+        L.pfcu_prepare_batch.argtypes = [vp, C.POINTER(BatchDesc)]
+        L.pfcu_draw_batch.argtypes = [vp, u32, i32, i32, u32, i32, vp]
+        L.pfcu_end_frame.argtypes = [vp, C.POINTER(FrameStats)]
+        L.pfcu_read_target.argtypes = [vp, vp]
+        L.pfcu_read_page.argtypes = [vp, u32, vp]
+        L.pfcu_target_device_ptr.argtypes = [vp, C.POINTER(sz)]
+        L.pfcu_target_device_ptr.restype = vp
+        for n in ("pfcu_read_lines", "pfcu_read_fills", "pfcu_read_tiles", "pfcu_read_z"):
+            getattr(L, n).argtypes = [vp, u32, vp]
+            getattr(L, n).restype = C.c_int64
+        L.pfcu_read_tile_lists.argtypes = [vp, u32, vp, vp]
+        L.pfcu_read_tile_lists.restype = C.c_int64
+        L.pfcu_read_mask.argtypes = [vp, u32, vp]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PfcuError("pfcu error %d: %s" % (rc, lib().pfcu_last_error().decode()))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def make_desc(batch, keep):
+    info = batch["info"]
+    d = BatchDesc()
+    d.batch_id, d.path_count, d.tile_count = int(info[0]), int(info[1]), int(info[2])
+    d.segment_count, d.column_count, d.path_source = int(info[3]), int(info[4]), int(info[5])
+    d.clip_batch_id = -1 if int(info[6]) == NONE else int(info[6])
+    arrays = [np.ascontiguousarray(batch[k]) for k in ("backdrops", "propagate_metadata", "dice_metadata",
+                                                        "tile_path_info")]
+    keep.extend(arrays)
+    d.backdrops, d.propagate_metadata, d.dice_metadata, d.tile_path_info = [a.ctypes.data for a in arrays]
+    for i in range(6):
+        d.transform[i] = float(batch["transform"][i])
+    return d
+
+
+class Renderer:
+    """One pfcu context bound to one GPU. Usage mirrors Canvas::draw (pathfinder/core/canvas.cpp:557-567):
+    `set_scene(scene)` once per scene (upload), `draw(clear)` per frame."""
+
+    def __init__(self, device=0, area_lut=None):
+        self.L = lib()
+        h = C.c_void_p()
+        _check(self.L.pfcu_create(device, C.byref(h)))
+        self.h = h
+        self.scene = None
+        self._descs = None
+        if area_lut is not None:
+            self.set_area_lut(area_lut)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.pfcu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        _check(self.L.pfcu_set_stream(self.h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def set_area_lut(self, lut):
+        lut = np.ascontiguousarray(lut, "u1")
+        _check(self.L.pfcu_set_area_lut(self.h, _p(lut), lut.shape[1], lut.shape[0]))
+
+    def set_target(self, width, height, view_box, device_ptr=None, pitch=0):
+        vb = np.ascontiguousarray(view_box, "<f4")
+        _check(self.L.pfcu_set_target(self.h, int(width), int(height), device_ptr, pitch, _p(vb)))
+        self.width, self.height = int(width), int(height)
+
+    # -- scene upload: RendererD3D11::upload_scene + Palette::build_paint_info's uploads
+    def upload_segments(self, scene):
+        for which, name in ((0, "draw"), (1, "clip")):
+            pts = np.ascontiguousarray(scene[name + "_points"], "<f4")
+            idx = np.ascontiguousarray(scene[name + "_indices"], "<u4")
+            _check(self.L.pfcu_upload_scene(self.h, which, _p(pts), len(pts), _p(idx), len(idx)))
+
+    def upload_paints(self, scene):
+        md = np.ascontiguousarray(scene["metadata"], "<u2")
+        _check(self.L.pfcu_upload_paint_metadata(self.h, _p(md), md.shape[0]))
+        for page, px in scene.get("pages", {}).items():
+            px = np.ascontiguousarray(px, "u1")
+            _check(self.L.pfcu_alloc_page(self.h, int(page), px.shape[1], px.shape[0]))
+            _check(self.L.pfcu_upload_page_region(self.h, int(page), 0, 0, px.shape[1], px.shape[0], _p(px)))
+
+    def set_scene(self, scene, target_ptr=None, pitch=0):
+        self.scene = scene
+        self.set_target(scene["width"], scene["height"], scene["view_box"], target_ptr, pitch)
+        self.upload_segments(scene)
+        self.upload_paints(scene)
+        self._keep = []
+        self._descs = {"clip": [make_desc(b, self._keep) for b in scene["clip_batches"]],
+                       "draw": [make_desc(b, self._keep) for b in scene["draw_batches"]]}
+
+    # -- frame
+    def draw(self, clear=True, clear_color=(0.0, 0.0, 0.0, 0.0), upload=False):
+        """RendererD3D11::draw: clip batches in reverse, then prepare + composite every draw batch.
+        upload=True re-uploads the segments first (what the reference does every frame, renderer.cpp:314)."""
+        scene = self.scene
+        if upload:
+            self.upload_segments(scene)
+        L = self.L
+        _check(L.pfcu_begin_frame(self.h))
+        for d, b in reversed(list(zip(self._descs["clip"], scene["clip_batches"]))):
+            if d.path_count > 0:
+                _check(L.pfcu_prepare_batch(self.h, C.byref(d)))
+        cc = np.array(clear_color, "<f4")
+        zero = np.zeros(4, "<f4")
+        first = bool(clear)
+        for d, b in zip(self._descs["draw"], scene["draw_batches"]):
+            _check(L.pfcu_prepare_batch(self.h, C.byref(d)))
+            info = b["info"]
+            color_page = -1 if int(info[7]) == NONE else int(info[7])
+            flags = 0 if int(info[8]) == NONE else int(info[8])
+            if int(info[10]) == NONE:
+                _check(L.pfcu_draw_batch(self.h, d.batch_id, -1, color_page, flags, int(first), _p(cc)))
+                first = False
+            else:
+                _check(L.pfcu_draw_batch(self.h, d.batch_id, int(info[11]), color_page, flags, 1, _p(zero)))
+        st = FrameStats()
+        _check(L.pfcu_end_frame(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def pixels(self):
+        px = np.zeros((self.height, self.width, 4), "u1")
+        _check(self.L.pfcu_read_target(self.h, _p(px)))
+        return px
+
+    # -- parity taps
+    def _tap(self, fn, batch_id, dt):
+        n = fn(self.h, batch_id, None)
+        if n < 0:
+            _check(int(n))
+        a = np.zeros(n, dt)
+        if n:
+            m = fn(self.h, batch_id, _p(a))
+            a = a[:m]
+        return a
+
+    def lines(self, batch_id):
+        return self._tap(self.L.pfcu_read_lines, batch_id, LINE_DT)
+
+    def fills(self, batch_id):
+        return self._tap(self.L.pfcu_read_fills, batch_id, FILL_DT)
+
+    def tiles(self, batch_id):
+        return self._tap(self.L.pfcu_read_tiles, batch_id, TILE_DT)
+
+    def z(self, batch_id):
+        return self._tap(self.L.pfcu_read_z, batch_id, "<i4")
+
+    def tile_lists(self, batch_id):
+        fbt = ((self.width + 15) // 16) * ((self.height + 15) // 16)
+        n = self.L.pfcu_read_tile_lists(self.h, batch_id, None, None)
+        off = np.zeros(fbt + 1, "<u4")
+        t = np.zeros(max(int(n), 1), "<u4")
+        self.L.pfcu_read_tile_lists(self.h, batch_id, _p(off), _p(t))
+        return off, t[:n]
+
+    def mask(self, alpha_id):
+        m = np.zeros(256, "u1")
+        _check(self.L.pfcu_read_mask(self.h, int(alpha_id), _p(m)))
+        return m.reshape(16, 16)

@@ -1,0 +1,156 @@
+"""GPU tests (pytest -m gpu): the CUDA path, called through the C-ABI, against the reference fixtures and the oracle.
+
+* dice / bin / propagate outputs: BIT-EXACT against the reference's hybrid CPU tiler (tests/golden fixtures) and
+  against the oracle's taps (lines, fills, tiles, z, sorted lists);
+* pixels: within 1/255 per channel of the oracle's restatement of fill.comp + tile.comp.
+"""
+import numpy as np
+import pytest
+
+import parity
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = ["tiger_512", "tiger_1024", "features_2048", "demo_clip_512"]
+PIXEL_TOL = 1  # 1/255 per channel, BASELINE.json north_star
+
+
+@pytest.fixture(scope="module")
+def renderer(area_lut):
+    import pfcu
+
+    r = pfcu.Renderer(0, area_lut)
+    yield r
+    r.close()
+
+
+def cuda_taps(r, scene):
+    taps = {}
+    for kind in ("clip", "draw"):
+        for b in scene[kind + "_batches"]:
+            if int(b["info"][1]) > 0 or kind == "draw":
+                bid = int(b["info"][0])
+                taps[bid] = (r.tiles(bid), r.fills(bid))
+    return taps
+
+
+def oracle_frame(scene, lut):
+    import pforacle
+
+    fr = pforacle.Frame(scene, lut)
+    px = fr.render()
+    return fr, px
+
+
+def raw_sorted(records):
+    """Rows of a structured array as raw uint32 words, lexicographically sorted (bit-exact multiset compare)."""
+    w = np.frombuffer(records.tobytes(), "<u4").reshape(len(records), -1)
+    return w[np.lexsort(w.T[::-1])]
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_geometry_bit_exact_vs_reference_fixture(renderer, name):
+    scene, extra = scenes.load_scene(scenes.golden_path(name))
+    renderer.set_scene(scene)
+    stats = renderer.draw(clear=True)
+    mine = parity.canonical_scene(scene, cuda_taps(renderer, scene))
+    parity.assert_canonical_equal(mine, parity.reference_from_extra(extra), name)
+    assert stats["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_taps_bit_exact_vs_oracle(renderer, area_lut, name):
+    scene, _ = scenes.load_scene(scenes.golden_path(name))
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    fr, _ = oracle_frame(scene, area_lut)
+    for kind in ("clip", "draw"):
+        for b in scene[kind + "_batches"]:
+            if int(b["info"][1]) == 0:
+                continue
+            bid = int(b["info"][0])
+            slot = fr.slots[bid]
+            # dice: same multiset of flattened lines, bit for bit (compare the raw 20-byte records)
+            lo, lc = fr.lines(slot), renderer.lines(bid)
+            assert len(lo) == len(lc), "line count %d != %d" % (len(lc), len(lo))
+            ro, rc = raw_sorted(lo), raw_sorted(lc)
+            assert np.array_equal(ro, rc), "flattened lines differ"
+            # bin: identical CSR fills (both canonical-sorted)
+            assert np.array_equal(fr.fills(slot), renderer.fills(bid)), "fills differ"
+            # propagate: backdrops, deltas, list membership, hybrid-equivalent backdrop
+            to, tc = fr.tiles(slot), renderer.tiles(bid)
+            for f in ("fill_count", "backdrop", "backdrop_delta", "backdrop_d3d9", "listed"):
+                assert np.array_equal(to[f], tc[f]), f
+            assert np.array_equal(to["alpha_tile_id"] >= 0, tc["alpha_tile_id"] >= 0)
+            assert np.array_equal(to["clip_alpha_tile_id"] >= 0, tc["clip_alpha_tile_id"] >= 0)
+            # z-buffer and sorted, culled lists
+            assert np.array_equal(fr.z(slot)[0], renderer.z(bid)), "z differs"
+            oo, ot = fr.tile_lists(slot)
+            co, ct = renderer.tile_lists(bid)
+            assert np.array_equal(oo, co) and np.array_equal(ot, ct), "tile lists differ"
+    fr.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN)
+def test_pixels_within_tolerance_of_oracle(renderer, area_lut, name):
+    scene, _ = scenes.load_scene(scenes.golden_path(name))
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    got = renderer.pixels()
+    fr, want = oracle_frame(scene, area_lut)
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert diff.max() <= PIXEL_TOL, "max diff %d at %s" % (diff.max(), np.unravel_index(diff.argmax(), diff.shape))
+    fr.close()
+
+
+def test_masks_match_oracle(renderer, area_lut):
+    """fill stage alone: every sampled 16 x 16 coverage mask within 1/255 of fill.comp's restatement."""
+    scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    fr, _ = oracle_frame(scene, area_lut)
+    bid = int(scene["draw_batches"][0]["info"][0])
+    to, tc = fr.tiles(fr.slots[bid]), renderer.tiles(bid)
+    own = np.nonzero((to["alpha_tile_id"] >= 0) & (to["fill_count"] > 0))[0]
+    worst = 0
+    for i in own[:: max(1, len(own) // 400)]:
+        a = fr.mask(int(to["alpha_tile_id"][i])).astype(int)
+        b = renderer.mask(int(tc["alpha_tile_id"][i])).astype(int)
+        worst = max(worst, np.abs(a - b).max())
+    assert worst <= 1
+    fr.close()
+
+
+def test_repeat_frames_are_identical_and_reuse_buffers(renderer):
+    scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    a = renderer.pixels()
+    st = renderer.draw(clear=True, upload=True)
+    b = renderer.pixels()
+    assert st["retries"] == 0
+    assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
+
+
+def test_empty_and_degenerate_scenes(renderer):
+    """Empty scene, zero-area path, non-finite control points, a path entirely outside the view box."""
+    paths = [
+        {"contours": [(np.array([[10, 10], [10, 10], [10, 10]], "<f4"), np.array([0, 0, 0], "u1"))], "paint": 0},
+        {"contours": [(np.array([[5, 5], [np.nan, 7], [9, np.inf], [20, 20]], "<f4"), np.array([0, 1, 2, 0], "u1"))],
+         "paint": 0},
+        {"contours": [(np.array([[-500, -500], [-400, -500], [-400, -400]], "<f4"), np.array([0, 0, 0], "u1"))],
+         "paint": 0},
+        {"contours": [(np.array([[8, 8], [40, 8], [40, 40], [8, 40]], "<f4"), np.array([0, 0, 0, 0], "u1"))], "paint": 1},
+    ]
+    colors = np.array([[255, 0, 0, 255], [0, 0, 255, 128]], "u1")
+    scene = scenes.build_scene_from_outlines(64, 48, paths, colors)
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    px = renderer.pixels()
+    assert px.shape == (48, 64, 4)
+    assert px[20, 20, 3] == 128 and px[2, 2, 3] == 0
+    empty = scenes.build_scene_from_outlines(32, 32, [], np.array([[0, 0, 0, 255]], "u1"))
+    renderer.set_scene(empty)
+    st = renderer.draw(clear=True)
+    assert st["fills"] == 0 and renderer.pixels().max() == 0
