@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- the headline measurement of BASELINE.json: dice -> composite of tiger.svg at 4096 x 4096.
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path (one JSON line on rank 0)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU path (hybrid SceneBuilderD3D9)
+
+A step is one whole frame (every batch of the scene: bound, dice, bin, propagate, sort, fill, tile).
+  value   : segments/s with all inputs resident in HBM, frame replayed as one CUDA graph, CUDA-event time per step on
+            the launching stream, L2 flushed between steps (not timed), max over ranks.
+  e2e     : the same metric through the public C-ABI with HOST buffers: every step uploads the scene's segments and
+            batch metadata (pinned staging -> H2D), runs the frame, and reads the frame counters back (D2H).
+  roofline: the composite ("tile") kernel, algorithmic bytes of SURVEY.md section 8d / measured HBM copy bandwidth.
+N > 1 (torchrun): the scene-sharded configuration -- every rank renders its own frames, no data-path collective
+(SURVEY.md section 8e), weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "pathfinder-cpp_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import scenes  # noqa: E402
+
+WORKLOADS = {
+    # name: (fixture, asset, size, native size)
+    "tiger4096": ("tiger_4096_scene", "tiger.svg", 4096, 900.0),
+    "tiger1024": ("tiger_1024", "tiger.svg", 1024, 900.0),
+    "tiger512": ("tiger_512", "tiger.svg", 512, 900.0),
+    "features2048": ("features_2048", "features.svg", 2048, 720.0),
+}
+METRIC = "segments/s (dice->composite), tiger.svg at 4096x4096"
+UNIT = "segments/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fp:
+            return float(json.load(fp)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                power.append(float(r[3]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_workload(name):
+    fixture, asset, size, native = WORKLOADS[name]
+    scene, _ = scenes.load_scene(scenes.golden_path(fixture))
+    return scene, asset, size, native
+
+
+def n_segments(scene):
+    return int(sum(int(b["info"][3]) for b in scene["draw_batches"] + scene["clip_batches"]))
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+
+def reference_cpu(asset, size, native, steps, warmup, budget_s=20.0):
+    """The reference's own CPU implementation of the path: SceneBuilderD3D9::build (hybrid tiler), as shipped
+    (4 worker threads, core/d3d9/scene_builder.cpp:13). Falls back to the C restatement when libpfref.so is absent."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pfref
+
+    if pfref.available():
+        s = pfref.RefScene.from_svg(pfref.asset(asset), size, size, size / native)
+        s.time_d3d9_build(max(warmup, 1))
+        probe = float(np.median(s.time_d3d9_build(3)))
+        n = int(max(1, min(steps, budget_s * 1000.0 / max(probe, 1e-3))))
+        t = s.time_d3d9_build(n)
+        s.close()
+        return dict(ms=t, kind="reference", cores=4, steps=n,
+                    sample="%d x SceneBuilderD3D9::build (tiling only; the reference has no CPU rasteriser), %s @ %d^2"
+                           % (n, asset, size))
+    import pforacle
+
+    scene, _ = scenes.load_scene(scenes.golden_path(WORKLOADS["tiger4096"][0]))
+    fr = pforacle.Frame(scene, None)
+    ts = []
+    for i in range(warmup + steps):
+        lib = pforacle.lib()
+        lib.pfo_frame_reset(fr.h)
+        t0 = time.perf_counter()
+        fr.prepare_all(geometry_only=True)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    fr.close()
+    return dict(ms=np.array(ts[warmup:]), kind="port", cores=1, steps=steps,
+                sample="%d x oracle/pf_oracle.c geometry (dice+bin+propagate), %s @ %d^2" % (steps, asset, size))
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    scene, asset, size, native = load_workload(args.workload)
+    segs = n_segments(scene)
+    r = reference_cpu(asset, size, native, args.steps, args.warmup)
+    ms = float(np.mean(r["ms"]))
+    value = segs / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "reference asset %s parsed by the reference front end" % asset,
+        "config": {"workload": "%s@%dx%d" % (asset, size, size), "threads": r["cores"],
+                   "note": "CPU tiling only (no pixels): the reference has no CPU rasteriser"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+
+def algorithmic_bytes(r, scene):
+    """B_fill and B_tile from the frame's own unit counts (read through the parity taps)."""
+    F = A = Ac = L = La = 0
+    T = ((scene["width"] + 15) // 16) * ((scene["height"] + 15) // 16)
+    paints = set()
+    for b in scene["draw_batches"]:
+        bid = int(b["info"][0])
+        tiles = r.tiles(bid)
+        off, lst = r.tile_lists(bid)
+        F += int(tiles["fill_count"][tiles["alpha_tile_id"] >= 0].sum())
+        own = (tiles["alpha_tile_id"] >= 0) & (tiles["fill_count"] > 0)
+        A += int(own.sum())
+        Ac += int((tiles["clip_alpha_tile_id"] >= 0).sum())
+        L += len(lst)
+        La += int((tiles["alpha_tile_id"][lst] >= 0).sum())
+        paints.update(int(c) for c in np.unique(b["tile_path_info"]["color"]))
+    G = sum(int(px.size) for px in scene.get("pages", {}).values())
+    P = len(paints)
+    b_fill = 12 * F + 24 * A + 256 * A + 256 * Ac
+    b_tile = 4 * T + 16 * L + 256 * La + 80 * P + G + 1024 * T
+    return dict(F=F, A=A, A_c=Ac, L=L, L_a=La, T=T, P=P, G=G, B_fill=b_fill, B_tile=b_tile)
+
+
+def run_ours(args, rank, world):
+    import torch
+
+    import pfcu
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scene, asset, size, native = load_workload(args.workload)
+    segs = n_segments(scene)
+    lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
+    stream = torch.cuda.Stream()
+    r = pfcu.Renderer(local, lut)
+    r.set_stream(stream.cuda_stream)
+    r.set_scene(scene)
+    first = r.draw(clear=True)      # sizes every buffer (may retry once)
+    steady = r.draw(clear=True)     # steady state: no allocation, no retry
+    assert steady["retries"] == 0, steady
+    bytes_ = algorithmic_bytes(r, scene)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    # ---- per-kernel times (events around every kernel), for the roofline of the dominant kernel
+    r.set_profiling(True)
+    stage_samples = []
+    for _ in range(max(5, args.warmup)):
+        flush_l2()
+        r.draw(clear=True)
+        stage_samples.append(r.stage_times())
+    r.set_profiling(False)
+    stage_ms = {k: float(np.median([s[k] for s in stage_samples])) for k in stage_samples[0]}
+
+    # ---- value: whole frame as one CUDA graph, inputs resident
+    r.draw(clear=True)
+    r.graph_capture()
+    for _ in range(max(args.warmup, 3)):
+        flush_l2()
+        r.graph_launch()
+    gstats = r.graph_finish()
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush_l2()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r.graph_launch()
+        e1.record(stream)
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+    total_ms = float(step_ms.sum())
+    gstats = r.graph_finish()
+
+    # ---- e2e: public C-ABI with host buffers, H2D + frame + D2H counters every step (wall clock, synchronised)
+    for _ in range(3):
+        r.draw(clear=True, upload=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        st = r.draw(clear=True, upload=True)  # pfcu_end_frame synchronises and reads the counters back
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop()
+    h2d = int(sum(scene[k].nbytes for k in ("draw_points", "draw_indices", "clip_points", "clip_indices")))
+    for b in scene["draw_batches"] + scene["clip_batches"]:
+        h2d += int(sum(b[k].nbytes for k in ("backdrops", "propagate_metadata", "dice_metadata", "tile_path_info")))
+    d2h = 64 * (len(scene["draw_batches"]) + len(scene["clip_batches"]) + 1)
+    # with the framebuffer read back to the host as well (what a CPU consumer of the pixels would pay)
+    px_ms = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        r.draw(clear=True, upload=True)
+        r.pixels()
+        px_ms.append((time.perf_counter() - t0) * 1e3)
+
+    if world > 1:
+        t = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        r.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * args.steps * segs / (total_ms / 1e3)
+    e2e_value = world * args.steps * segs / (e2e_ms / 1e3)
+    peak, peak_src = measured_peak()
+    comp_ms = stage_ms["composite"]
+    achieved = bytes_["B_tile"] / (comp_ms * 1e-3) / 1e9 if comp_ms > 0 else 0.0
+    fill_gbs = bytes_["B_fill"] / (stage_ms["fill"] * 1e-3) / 1e9 if stage_ms["fill"] > 0 else 0.0
+    both = (bytes_["B_fill"] + bytes_["B_tile"]) / ((stage_ms["fill"] + comp_ms) * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic-free: reference asset %s, scene fixture built by the reference front end"
+                                % asset,
+        "config": {"workload": "%s@%dx%d" % (asset, size, size), "sharding": "scene-per-rank, no collective",
+                   "timing": "CUDA events per step on the launching stream, whole frame = 1 CUDA graph",
+                   "l2": "256 MiB memset between steps (not timed); working set < L2", "frames_per_s": world * args.steps / (total_ms / 1e3),
+                   "units": {k: gstats[k] for k in ("segments", "lines", "fills", "alpha_tiles", "dense_tiles",
+                                                    "listed_tiles", "fb_tiles")}},
+        "roofline": {"bound": "hbm", "kernel": "k_composite (tile)", "achieved": achieved, "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes": bytes_["B_tile"], "kernel_ms": comp_ms,
+                     "fill": {"achieved": fill_gbs, "frac": fill_gbs / peak, "algorithmic_bytes": bytes_["B_fill"],
+                              "kernel_ms": stage_ms["fill"]},
+                     "fill_plus_tile": {"achieved": both, "frac": both / peak},
+                     "stage_ms": stage_ms, "counts": bytes_},
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "with_frame_readback_ms": float(np.median(px_ms)),
+                "frame_readback_bytes": int(scene["width"]) * int(scene["height"]) * 4},
+        "gpu_launches": int(gstats["kernel_launches"]) * args.steps,
+        "clocks": clocks,
+        "first_frame": {"retries": first["retries"], "gpu_ms": first["gpu_ms"]},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        c = reference_cpu(asset, size, native, 400, 3, budget_s=12.0)
+        ms = float(np.median(c["ms"]))
+        line["cpu_baseline"] = {"value": segs / (ms / 1e3), "unit": UNIT, "cores": c["cores"], "kind": c["kind"],
+                                "sample": c["sample"], "ms_per_frame": ms, "host_cpus": os.cpu_count()}
+    print(json.dumps(line))
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="tiger4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,32 @@ int pfcu_draw_batch(pfcu_ctx *ctx, uint32_t batch_id, int target_page, int color
  * read-backs). stats may be NULL. */
 int pfcu_end_frame(pfcu_ctx *ctx, pfcu_frame_stats *stats);
 
+/* ---- measurement */
+enum {
+    PFCU_STAGE_INIT = 0, /* "bound" */
+    PFCU_STAGE_DICE,
+    PFCU_STAGE_BIN_COUNT,
+    PFCU_STAGE_SCAN_TILES,
+    PFCU_STAGE_BIN_SCATTER,
+    PFCU_STAGE_PROPAGATE,
+    PFCU_STAGE_SCAN_FB,
+    PFCU_STAGE_LIST_SCATTER, /* "sort" (ordering itself happens on chip in the tile kernel) */
+    PFCU_STAGE_FILL,
+    PFCU_STAGE_COMPOSITE, /* "tile" */
+    PFCU_NUM_STAGES
+};
+/* enabled != 0: bracket every kernel of subsequent frames with CUDA events on the context's stream. */
+int pfcu_set_profiling(pfcu_ctx *ctx, int enabled);
+/* Per-stage device time (ms, summed over batches) of the last frame ended with profiling on. n <= PFCU_NUM_STAGES. */
+int pfcu_get_stage_times(pfcu_ctx *ctx, float *ms, int n);
+
+/* ---- whole-frame CUDA graph: replay the last completed frame with device-resident inputs (no host memory is
+ * touched, no allocation, no read-back inside the graph). Segment points may be re-uploaded between replays
+ * (animation); the batch structure must stay the same. */
+int pfcu_graph_capture(pfcu_ctx *ctx);
+int pfcu_graph_launch(pfcu_ctx *ctx);                          /* asynchronous, on the context's stream */
+int pfcu_graph_finish(pfcu_ctx *ctx, pfcu_frame_stats *stats); /* waits, reads the counters, reports overflow */
+
 /* ---- results */
 int pfcu_read_target(pfcu_ctx *ctx, uint8_t *host_rgba8);                    /* width*height*4, tightly packed */
 int pfcu_read_page(pfcu_ctx *ctx, uint32_t page, uint8_t *host_rgba8);

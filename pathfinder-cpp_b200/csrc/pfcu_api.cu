@@ -151,6 +151,17 @@ struct pfcu_ctx {
     PinnedBuf host_counters;
     uint32_t launches = 0, retries = 0;
     pfcu_frame_stats last_stats{};
+    // per-stage profiling (pfcu_set_profiling): event pairs around every kernel of the frame
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_stage;  // stage of the kernel that ends at event i + 1 (-1: frame start marker)
+    size_t prof_used = 0;
+    float stage_ms[PFCU_NUM_STAGES] = {};
+    // whole-frame CUDA graph (pfcu_graph_capture)
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_launches_per_frame = 0;
+    bool capturing = false;
 };
 
 namespace {
@@ -173,8 +184,30 @@ int sync_if_in_flight(pfcu_ctx *c) {
     return PFCU_OK;
 }
 
+// Profiling: mark(-1) opens a segment, mark(stage) closes the segment that just ran `stage`.
+int prof_mark(pfcu_ctx *c, int stage) {
+    if (!c->profiling || c->capturing) return PFCU_OK;
+    if (c->prof_used == c->prof_events.size()) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreate(&e));
+        c->prof_events.push_back(e);
+        c->prof_stage.push_back(-1);
+    }
+    c->prof_stage[c->prof_used] = stage;
+    CUDA_TRY(cudaEventRecord(c->prof_events[c->prof_used], c->stream));
+    c->prof_used++;
+    return PFCU_OK;
+}
+
+#define LAUNCH_STAGE(stage, expr)        \
+    do {                                 \
+        CUDA_TRY(expr);                  \
+        int _r = prof_mark(c, stage);    \
+        if (_r) return _r;               \
+    } while (0)
+
 // (Re)build the device view of a slot and enqueue prepare_tiles for it.
-int enqueue_prepare(pfcu_ctx *c, int slot_index) {
+int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     BatchSlot &s = c->slots[slot_index];
     const pfcu_batch_desc &d = s.desc;
     const uint32_t fbt = (uint32_t)(((c->target.width + TILE - 1) / TILE) * ((c->target.height + TILE - 1) / TILE));
@@ -195,7 +228,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index) {
     CUDA_TRY(s.alpha_tiles.ensure(D * sizeof(AlphaTile)));
     CUDA_TRY(s.scan_desc0.ensure((D / 2048 + 2) * 8));
     CUDA_TRY(s.scan_desc1.ensure((T / 2048 + 2) * 8));
-    if (s.meta_bytes)
+    if (s.meta_bytes && upload_meta)
         CUDA_TRY(cudaMemcpyAsync(s.dev_meta.p, s.host_meta.p, s.meta_bytes, cudaMemcpyHostToDevice, c->stream));
 
     BatchView v{};
@@ -260,15 +293,19 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index) {
     pv.lut_w = c->lut_w;
     pv.lut_h = c->lut_h;
 
-    CUDA_TRY(launch_init(v, c->stream));
-    CUDA_TRY(launch_dice(v, c->stream));
-    CUDA_TRY(launch_bin_count(v, c->stream));
-    CUDA_TRY(launch_scan_tiles(v, c->stream));
-    CUDA_TRY(launch_bin_scatter(v, c->stream));
-    CUDA_TRY(launch_propagate(v, c->stream));
-    CUDA_TRY(launch_scan_fb(v, c->stream));
-    CUDA_TRY(launch_list_scatter(v, c->stream));
-    CUDA_TRY(launch_fill(v, pv, c->stream));
+    {
+        int r = prof_mark(c, -1);
+        if (r) return r;
+    }
+    LAUNCH_STAGE(PFCU_STAGE_INIT, launch_init(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_DICE, launch_dice(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_BIN_COUNT, launch_bin_count(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_SCAN_TILES, launch_scan_tiles(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_BIN_SCATTER, launch_bin_scatter(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_PROPAGATE, launch_propagate(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_SCAN_FB, launch_scan_fb(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_LIST_SCATTER, launch_list_scatter(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, c->stream));
     c->launches += 9;
     c->in_flight = true;
     return PFCU_OK;
@@ -307,7 +344,11 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
     // masks may have been reallocated since the batch was prepared (growth happens only between attempts)
     s.view.masks = c->masks.as<uint8_t>();
     s.view.mask_capacity = c->mask_cap;
-    CUDA_TRY(launch_composite(s.view, pv, t, clear, cmd.clear_color, c->stream));
+    {
+        int r = prof_mark(c, -1);
+        if (r) return r;
+    }
+    LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, c->stream));
     c->launches += 1;
     c->in_flight = true;
     return PFCU_OK;
@@ -371,6 +412,9 @@ void pfcu_destroy(pfcu_ctx *c) {
     c->counters.release();
     c->masks.release();
     c->host_counters.release();
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_begin);
     cudaEventDestroy(c->ev_end);
     cudaStreamDestroy(c->own_stream);
@@ -502,6 +546,7 @@ int pfcu_begin_frame(pfcu_ctx *c) {
     c->retries = 0;
     c->frame_open = true;
     c->event_begin_recorded = false;
+    c->prof_used = 0;
     return PFCU_OK;
 }
 
@@ -614,6 +659,7 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
         }
         // grow and replay the recorded frame
         c->retries++;
+        c->prof_used = 0;
         for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
         CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
         CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
@@ -642,9 +688,105 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) st.gpu_ms = ms;
     }
+    for (int k = 0; k < PFCU_NUM_STAGES; k++) c->stage_ms[k] = 0.f;
+    if (c->profiling) {
+        for (size_t i = 1; i < c->prof_used; i++) {
+            const int stage = c->prof_stage[i];
+            if (stage < 0) continue;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, c->prof_events[i - 1], c->prof_events[i]) == cudaSuccess) c->stage_ms[stage] += ms;
+        }
+    }
     c->last_stats = st;
     if (stats) *stats = st;
     c->frame_open = false;
+    return PFCU_OK;
+}
+
+int pfcu_set_profiling(pfcu_ctx *c, int enabled) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    c->profiling = enabled != 0;
+    return PFCU_OK;
+}
+
+int pfcu_get_stage_times(pfcu_ctx *c, float *ms, int n) {
+    if (!c || !ms) return fail(PFCU_ERR_INVALID, "null argument");
+    for (int k = 0; k < n; k++) ms[k] = k < PFCU_NUM_STAGES ? c->stage_ms[k] : 0.f;
+    return PFCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ CUDA graph
+
+int pfcu_graph_capture(pfcu_ctx *c) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    if (c->frame_open) return fail(PFCU_ERR_STATE, "end the frame before capturing it");
+    if (c->cmds.empty()) return fail(PFCU_ERR_STATE, "no frame has been recorded");
+    CUDA_TRY(cudaSetDevice(c->device));
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    if (c->graph) cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr;
+    c->graph = nullptr;
+    // All buffers are already sized by the frame that was just completed, so replaying the command list performs
+    // no allocation; the batch metadata is resident, so no host memory is touched by the graph.
+    for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
+    const uint32_t launches_before = c->launches;
+    c->capturing = true;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        c->capturing = false;
+        return fail(PFCU_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+    }
+    int rc = PFCU_OK;
+    if (cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream) != cudaSuccess) rc = PFCU_ERR_CUDA;
+    for (const Cmd &cmd : c->cmds) {
+        if (rc) break;
+        rc = cmd.kind == CMD_PREPARE ? enqueue_prepare(c, cmd.slot, false) : enqueue_draw(c, cmd);
+    }
+    e = cudaStreamEndCapture(c->stream, &c->graph);
+    c->capturing = false;
+    c->in_flight = false;
+    c->graph_launches_per_frame = c->launches - launches_before;
+    c->launches = launches_before;
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(PFCU_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    CUDA_TRY(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+    return PFCU_OK;
+}
+
+int pfcu_graph_launch(pfcu_ctx *c) {
+    if (!c || !c->graph_exec) return fail(PFCU_ERR_STATE, "no captured frame");
+    CUDA_TRY(cudaGraphLaunch(c->graph_exec, c->stream));
+    c->in_flight = true;
+    return PFCU_OK;
+}
+
+int pfcu_graph_finish(pfcu_ctx *c, pfcu_frame_stats *stats) {
+    if (!c || !c->graph_exec) return fail(PFCU_ERR_STATE, "no captured frame");
+    CUDA_TRY(cudaSetDevice(c->device));
+    BatchCounters *hc = static_cast<BatchCounters *>(c->host_counters.p);
+    const size_t used = sizeof(BatchCounters) * (size_t)std::max(c->slots_used, 1);
+    CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, used, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(hc + MAX_SLOTS, frame_alpha_counter(c), sizeof(BatchCounters), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->in_flight = false;
+    pfcu_frame_stats st = c->last_stats;
+    st.lines = st.fills = st.listed_tiles = 0;
+    uint32_t overflow = 0;
+    for (int i = 0; i < c->slots_used; i++) {
+        overflow |= hc[i].overflow;
+        st.lines += hc[i].n_lines;
+        st.fills += hc[i].n_fills;
+        st.listed_tiles += hc[i].n_list_entries;
+    }
+    st.alpha_tiles = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
+    if (st.alpha_tiles > c->mask_cap) overflow |= OVF_ALPHA;
+    st.overflow_flags = overflow;
+    st.kernel_launches = c->graph_launches_per_frame;
+    st.retries = 0;
+    if (stats) *stats = st;
+    if (overflow) return fail(PFCU_ERR_OVERFLOW, "captured frame overflowed (flags 0x%x): re-run it with pfcu_end_frame", overflow);
     return PFCU_OK;
 }
 

@@ -129,9 +129,6 @@ cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s);
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s);
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
                              const float clear_color[4], cudaStream_t s);
-// tap helper: sorted + z-culled lists for the parity reader
-cudaError_t launch_export_lists(const BatchView &b, uint32_t *offsets, uint32_t *tiles, uint32_t *total,
-                                cudaStream_t s);
 
 int sm_count();
 

@@ -18,8 +18,11 @@ EXPORTS = [
     "pfcu_set_area_lut", "pfcu_set_target", "pfcu_upload_scene", "pfcu_upload_paint_metadata", "pfcu_alloc_page",
     "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
     "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
-    "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask",
+    "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
+    "pfcu_get_stage_times", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
 ]
+STAGES = ["init", "dice", "bin_count", "scan_tiles", "bin_scatter", "propagate", "scan_fb", "list_scatter", "fill",
+          "composite"]
 
 LINE_DT = np.dtype([("from_x", "<f4"), ("from_y", "<f4"), ("to_x", "<f4"), ("to_y", "<f4"), ("path_index", "<u4")])
 FILL_DT = np.dtype([("tile_index", "<u4"), ("from_x", "<u2"), ("from_y", "<u2"), ("to_x", "<u2"), ("to_y", "<u2")])
@@ -87,6 +90,11 @@ def lib():
         L.pfcu_read_tile_lists.argtypes = [vp, u32, vp, vp]
         L.pfcu_read_tile_lists.restype = C.c_int64
         L.pfcu_read_mask.argtypes = [vp, u32, vp]
+        L.pfcu_set_profiling.argtypes = [vp, i32]
+        L.pfcu_get_stage_times.argtypes = [vp, vp, i32]
+        L.pfcu_graph_capture.argtypes = [vp]
+        L.pfcu_graph_launch.argtypes = [vp]
+        L.pfcu_graph_finish.argtypes = [vp, C.POINTER(FrameStats)]
         _lib = L
     return _lib
 
@@ -203,6 +211,26 @@ class Renderer:
                 _check(L.pfcu_draw_batch(self.h, d.batch_id, int(info[11]), color_page, flags, 1, _p(zero)))
         st = FrameStats()
         _check(L.pfcu_end_frame(self.h, C.byref(st)))
+        return st.as_dict()
+
+    # -- measurement
+    def set_profiling(self, enabled):
+        _check(self.L.pfcu_set_profiling(self.h, int(bool(enabled))))
+
+    def stage_times(self):
+        ms = np.zeros(len(STAGES), "<f4")
+        _check(self.L.pfcu_get_stage_times(self.h, _p(ms), len(STAGES)))
+        return dict(zip(STAGES, (float(x) for x in ms)))
+
+    def graph_capture(self):
+        _check(self.L.pfcu_graph_capture(self.h))
+
+    def graph_launch(self):
+        _check(self.L.pfcu_graph_launch(self.h))
+
+    def graph_finish(self):
+        st = FrameStats()
+        _check(self.L.pfcu_graph_finish(self.h, C.byref(st)))
         return st.as_dict()
 
     def pixels(self):

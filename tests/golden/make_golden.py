@@ -74,6 +74,9 @@ def main():
                          "alpha_tiles": int(len(ref["group_hashes"]))}
         if name in SVG_SCENES:
             scenes.save_scene(scenes.golden_path(name), scene, canonical_extra(ref))
+        else:
+            # inputs only (what bench.py renders); the outputs are pinned by the digest
+            scenes.save_scene(scenes.golden_path(name + "_scene"), scene)
         s.close()
         print(name, digests[name])
     for name, (size, scale, features) in DEMO_SCENES.items():

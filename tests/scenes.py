@@ -315,11 +315,14 @@ def build_scene_from_outlines(width, height, paths, colors_rgba8, strip=None):
             points.append(pts)
             points.append(pts[:1])
             n_points += k + 1
-            lo = np.minimum(lo, pts.min(axis=0))
-            hi = np.maximum(hi, pts.max(axis=0))
+            ok = pts[np.isfinite(pts).all(axis=1)]  # test scenes may carry non-finite points; keep bounds finite
+            if len(ok):
+                lo = np.minimum(lo, ok.min(axis=0))
+                hi = np.maximum(hi, ok.max(axis=0))
         n_seg = len(indices) - first_seg
         # outline.bounds ∩ view box (Rect::intersection, common/math/rect.h:160-173); {} when disjoint
-        if lo[0] > view_box[2] or hi[0] < view_box[0] or lo[1] > view_box[3] or hi[1] < view_box[1]:
+        if not np.isfinite(lo).all() or lo[0] > view_box[2] or hi[0] < view_box[0] or lo[1] > view_box[3] or \
+                hi[1] < view_box[1]:
             bounds = np.zeros(4, "<f4")
         else:
             bounds = np.array([max(lo[0], view_box[0]), max(lo[1], view_box[1]), min(hi[0], view_box[2]),
