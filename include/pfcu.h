@@ -76,7 +76,7 @@ typedef struct {
 typedef struct {
     float from_x, from_y, to_x, to_y;
     uint32_t path_index;
-} pfcu_line; /* 20 B: one flattened line, output of dice */
+} pfcu_line; /* 20 B: one flattened line after the view-box clip, output of dice */
 typedef struct {
     uint32_t tile_index; /* dense, batch-local */
     uint16_t from_x, from_y, to_x, to_y;
@@ -151,9 +151,9 @@ int pfcu_end_frame(pfcu_ctx *ctx, pfcu_frame_stats *stats);
 enum {
     PFCU_STAGE_INIT = 0, /* "bound" */
     PFCU_STAGE_DICE,
-    PFCU_STAGE_BIN_COUNT,
+    PFCU_STAGE_BIN,
     PFCU_STAGE_SCAN_TILES,
-    PFCU_STAGE_BIN_SCATTER,
+    PFCU_STAGE_FILL_SCATTER,
     PFCU_STAGE_PROPAGATE,
     PFCU_STAGE_SCAN_FB,
     PFCU_STAGE_LIST_SCATTER, /* "sort" (ordering itself happens on chip in the tile kernel) */

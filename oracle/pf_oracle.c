@@ -36,6 +36,8 @@ typedef struct {
     /* outputs */
     pfo_line *lines;
     size_t n_lines, cap_lines;
+    pfo_line *clipped; /* lines that survive the view-box clip, clipped (what the tile walk consumes) */
+    size_t n_clipped, cap_clipped;
     pfo_fill *fills;
     size_t n_fills, cap_fills;
     pfo_tile *tiles;      /* tile_count */
@@ -101,6 +103,7 @@ static void batch_free(batch_t *b) {
     free(b->dice);
     free(b->tpi);
     free(b->lines);
+    free(b->clipped);
     free(b->fills);
     free(b->tiles);
     free(b->col_backdrop);
@@ -403,6 +406,18 @@ static void process_line(pfo_frame *f, batch_t *b, const pfo_line *ln) {
     /* view box with an open top (tiler.cpp:141-152) */
     float box[4] = {f->view_box[0], -INFINITY, f->view_box[2], f->view_box[3]};
     if (!clip_line(l, box)) return;
+    if (b->n_clipped == b->cap_clipped) {
+        b->cap_clipped = b->cap_clipped ? b->cap_clipped * 2 : 4096;
+        b->clipped = (pfo_line *)realloc(b->clipped, b->cap_clipped * sizeof(pfo_line));
+    }
+    {
+        pfo_line *cl = &b->clipped[b->n_clipped++];
+        cl->from_x = l[0];
+        cl->from_y = l[1];
+        cl->to_x = l[2];
+        cl->to_y = l[3];
+        cl->path_index = ln->path_index;
+    }
 
     const float ts = (float)TILE;
     float tlx = l[0] * (1.0f / TILE), tly = l[1] * (1.0f / TILE);
@@ -787,6 +802,12 @@ size_t pfo_batch_lines(const pfo_frame *f, int slot, pfo_line *out) {
     const batch_t *b = &f->batches[slot];
     if (out) memcpy(out, b->lines, b->n_lines * sizeof(pfo_line));
     return b->n_lines;
+}
+
+size_t pfo_batch_clipped_lines(const pfo_frame *f, int slot, pfo_line *out) {
+    const batch_t *b = &f->batches[slot];
+    if (out) memcpy(out, b->clipped, b->n_clipped * sizeof(pfo_line));
+    return b->n_clipped;
 }
 
 size_t pfo_batch_fills(const pfo_frame *f, int slot, pfo_fill *out) {

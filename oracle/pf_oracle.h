@@ -105,6 +105,9 @@ int pfo_frame_prepare_batch(pfo_frame *f, const pfo_batch_desc *desc);
  *         [4] listed tiles [5] listed after z-cull [6] max list length. */
 void pfo_batch_counts(const pfo_frame *f, int slot, uint32_t counts[8]);
 size_t pfo_batch_lines(const pfo_frame *f, int slot, pfo_line *out);
+/* The same lines after the view-box clip of tiler.cpp:138-153 (lines entirely outside are dropped): the CUDA dice
+ * stage emits these. */
+size_t pfo_batch_clipped_lines(const pfo_frame *f, int slot, pfo_line *out);
 /* Canonical order: by tile_index, then (from_x, from_y, to_x, to_y). */
 size_t pfo_batch_fills(const pfo_frame *f, int slot, pfo_fill *out);
 size_t pfo_batch_tiles(const pfo_frame *f, int slot, pfo_tile *out);

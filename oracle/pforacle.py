@@ -51,7 +51,7 @@ def lib():
         L.pfo_frame_prepare_batch.argtypes = [vp, C.POINTER(BatchDesc)]
         L.pfo_frame_prepare_batch_geometry_only.argtypes = [vp, C.POINTER(BatchDesc)]
         L.pfo_batch_counts.argtypes = [vp, C.c_int, vp]
-        for name in ("pfo_batch_lines", "pfo_batch_fills", "pfo_batch_tiles"):
+        for name in ("pfo_batch_lines", "pfo_batch_clipped_lines", "pfo_batch_fills", "pfo_batch_tiles"):
             getattr(L, name).restype = sz
             getattr(L, name).argtypes = [vp, C.c_int, vp]
         L.pfo_batch_z.restype = sz
@@ -151,6 +151,9 @@ class Frame:
 
     def lines(self, slot):
         return self._get(lib().pfo_batch_lines, slot, LINE_DT)
+
+    def clipped_lines(self, slot):
+        return self._get(lib().pfo_batch_clipped_lines, slot, LINE_DT)
 
     def fills(self, slot):
         return self._get(lib().pfo_batch_fills, slot, FILL_DT)

@@ -101,9 +101,9 @@ struct BatchSlot {
     pfcu_batch_desc desc{};
     PinnedBuf host_meta;  // the four metadata vectors, packed, kept for replay
     size_t off_backdrops = 0, off_meta = 0, off_dice = 0, off_tpi = 0, meta_bytes = 0;
-    DevBuf dev_meta, tile_word, fill_cursor, col_backdrop, tile_state, lines, line_path, fills, z, fb_count,
-        fb_cursor, prims, alpha_tiles, scan_desc0, scan_desc1;
-    uint32_t line_cap = 0, fill_cap = 0;
+    DevBuf dev_meta, tile_word, fill_cursor, col_backdrop, tile_state, lines, line_meta, staging, fills, fb, listed,
+        listed_rank, prims, alpha_tiles, scan_desc0, scan_desc1;
+    uint32_t line_cap = 0, fill_cap = 0, staging_cap = 0;
     BatchView view{};
     bool prepared = false;
 };
@@ -135,8 +135,9 @@ struct pfcu_ctx {
     DevBuf points[2], indices[2];
     uint32_t n_points[2] = {0, 0}, n_segments[2] = {0, 0};
     PinnedBuf stage_scene[2];
-    DevBuf metadata;
-    uint32_t metadata_rows = 0;
+    DevBuf paints;  // Paint table decoded from the RGBA16F metadata texels
+    uint32_t n_paints = 0;
+    int all_solid = 1;
     PinnedBuf stage_metadata;
     Page pages[MAX_PAGES];
     PinnedBuf stage_page;
@@ -219,11 +220,12 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     CUDA_TRY(s.col_backdrop.ensure(C * 4));
     CUDA_TRY(s.tile_state.ensure(D * sizeof(TileState)));
     CUDA_TRY(s.lines.ensure((size_t)s.line_cap * sizeof(float4)));
-    CUDA_TRY(s.line_path.ensure((size_t)s.line_cap * 4));
+    CUDA_TRY(s.line_meta.ensure((size_t)s.line_cap * sizeof(uint2)));
+    CUDA_TRY(s.staging.ensure((size_t)s.staging_cap * sizeof(StagedFill)));
     CUDA_TRY(s.fills.ensure((size_t)s.fill_cap * sizeof(uint2)));
-    CUDA_TRY(s.z.ensure(T * 4));
-    CUDA_TRY(s.fb_count.ensure(T * 4));
-    CUDA_TRY(s.fb_cursor.ensure(T * 4));
+    CUDA_TRY(s.fb.ensure(T * sizeof(FbTile)));
+    CUDA_TRY(s.listed.ensure(D * sizeof(ListedRec)));
+    CUDA_TRY(s.listed_rank.ensure(D * 4));
     CUDA_TRY(s.prims.ensure(D * sizeof(TilePrim)));
     CUDA_TRY(s.alpha_tiles.ensure(D * sizeof(AlphaTile)));
     CUDA_TRY(s.scan_desc0.ensure((D / 2048 + 2) * 8));
@@ -258,13 +260,15 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.col_backdrop = s.col_backdrop.as<int32_t>();
     v.tile_state = s.tile_state.as<TileState>();
     v.lines = s.lines.as<float4>();
-    v.line_path = s.line_path.as<uint32_t>();
+    v.line_meta = s.line_meta.as<uint2>();
     v.line_capacity = s.line_cap;
+    v.staging = s.staging.as<StagedFill>();
+    v.staging_capacity = s.staging_cap;
     v.fills = s.fills.as<uint2>();
     v.fill_capacity = s.fill_cap;
-    v.z = s.z.as<int32_t>();
-    v.fb_count = s.fb_count.as<uint32_t>();
-    v.fb_cursor = s.fb_cursor.as<uint32_t>();
+    v.fb = s.fb.as<FbTile>();
+    v.listed = s.listed.as<ListedRec>();
+    v.listed_rank = s.listed_rank.as<uint32_t>();
     v.prims = s.prims.as<TilePrim>();
     v.prim_capacity = d.tile_count;
     v.alpha_tiles = s.alpha_tiles.as<AlphaTile>();
@@ -299,9 +303,9 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     }
     LAUNCH_STAGE(PFCU_STAGE_INIT, launch_init(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_DICE, launch_dice(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_BIN_COUNT, launch_bin_count(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_BIN, launch_bin(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_SCAN_TILES, launch_scan_tiles(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_BIN_SCATTER, launch_bin_scatter(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_FILL_SCATTER, launch_fill_scatter(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_PROPAGATE, launch_propagate(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_SCAN_FB, launch_scan_fb(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_LIST_SCATTER, launch_list_scatter(v, c->stream));
@@ -326,8 +330,9 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
         clear = 1;  // d3d11/renderer.cpp:382-386
     }
     PaintView pv{};
-    pv.metadata = c->metadata.as<uint16_t>();
-    pv.metadata_rows = c->metadata_rows;
+    pv.paints = c->paints.as<Paint>();
+    pv.n_paints = c->n_paints;
+    pv.all_solid = c->all_solid;
     pv.color_px = c->dummy_px.as<uint8_t>();
     pv.color_w = pv.color_h = 1;
     pv.sampling_flags = 0;
@@ -393,8 +398,8 @@ void pfcu_destroy(pfcu_ctx *c) {
     for (auto &s : c->slots) {
         s.host_meta.release();
         for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
-                          &s.line_path, &s.fills, &s.z, &s.fb_count, &s.fb_cursor, &s.prims, &s.alpha_tiles,
-                          &s.scan_desc0, &s.scan_desc1})
+                          &s.line_meta, &s.staging, &s.fills, &s.fb, &s.listed, &s.listed_rank, &s.prims,
+                          &s.alpha_tiles, &s.scan_desc0, &s.scan_desc1})
             b->release();
     }
     for (auto &p : c->pages) p.px.release();
@@ -406,7 +411,7 @@ void pfcu_destroy(pfcu_ctx *c) {
     c->lut.release();
     c->dummy_px.release();
     c->own_target.release();
-    c->metadata.release();
+    c->paints.release();
     c->stage_metadata.release();
     c->stage_page.release();
     c->counters.release();
@@ -492,20 +497,65 @@ int pfcu_upload_scene(pfcu_ctx *c, int which, const float *points, uint32_t n_po
     return PFCU_OK;
 }
 
+static float half_bits_to_float(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1fu;
+    uint32_t man = h & 0x3ffu, bits;
+    if (exp == 0) {
+        if (man == 0) {
+            bits = sign;
+        } else {  // subnormal half
+            int e = -1;
+            do {
+                e++;
+                man <<= 1;
+            } while (!(man & 0x400u));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+        }
+    } else if (exp == 31) {
+        bits = sign | 0x7f800000u | (man << 13);
+    } else {
+        bits = sign | ((exp + 112u) << 23) | (man << 13);
+    }
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+
 int pfcu_upload_paint_metadata(pfcu_ctx *c, const uint16_t *half_texels, uint32_t n_rows) {
     if (!c || (n_rows && !half_texels)) return fail(PFCU_ERR_INVALID, "bad metadata upload");
     CUDA_TRY(cudaSetDevice(c->device));
     int r = sync_if_in_flight(c);
     if (r) return r;
-    const size_t bytes = (size_t)n_rows * 1280 * 4 * 2;
-    CUDA_TRY(c->metadata.ensure(std::max<size_t>(bytes, 16)));
-    CUDA_TRY(c->stage_metadata.ensure(std::max<size_t>(bytes, 16)));
-    if (bytes) {
-        memcpy(c->stage_metadata.p, half_texels, bytes);
-        CUDA_TRY(cudaMemcpyAsync(c->metadata.p, c->stage_metadata.p, bytes, cudaMemcpyHostToDevice, c->stream));
+    // The reference samples 9 RGBA16F texels per pixel row and layer (tile.comp:707-717); the values only depend on
+    // the paint, so they are decoded here once per upload into a float table (exact: half -> float is lossless).
+    const uint32_t n_paints = n_rows * 128;  // TEXTURE_METADATA_ENTRIES_PER_ROW
+    const size_t bytes = (size_t)std::max<uint32_t>(n_paints, 1) * sizeof(Paint);
+    CUDA_TRY(c->paints.ensure(bytes));
+    CUDA_TRY(c->stage_metadata.ensure(bytes));
+    Paint *table = static_cast<Paint *>(c->stage_metadata.p);
+    int all_solid = 1;
+    for (uint32_t i = 0; i < n_paints; i++) {
+        const uint16_t *t = half_texels + ((size_t)(i / 128) * 1280 + (size_t)(i % 128) * 10) * 4;
+        auto texel = [&](int e) {
+            return make_float4(half_bits_to_float(t[e * 4 + 0]), half_bits_to_float(t[e * 4 + 1]),
+                               half_bits_to_float(t[e * 4 + 2]), half_bits_to_float(t[e * 4 + 3]));
+        };
+        Paint p{};
+        p.m0 = texel(0);
+        p.m1 = texel(1);
+        p.base = texel(2);
+        p.fp0 = texel(3);
+        p.fp1 = texel(4);
+        p.ctrl = (int32_t)texel(8).x;  // int(extra.x), tile.comp:725
+        if (p.ctrl != 0) all_solid = 0;
+        table[i] = p;
+    }
+    if (n_paints) {
+        CUDA_TRY(cudaMemcpyAsync(c->paints.p, table, (size_t)n_paints * sizeof(Paint), cudaMemcpyHostToDevice, c->stream));
         c->in_flight = true;
     }
-    c->metadata_rows = n_rows;
+    c->n_paints = n_paints;
+    c->all_solid = all_solid;
     return PFCU_OK;
 }
 
@@ -594,6 +644,7 @@ int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
     // capacities persist across frames; first guess from the segment count (dice.comp's 16K start, renderer.cpp:45)
     s.line_cap = std::max<uint32_t>(s.line_cap, (uint32_t)round_up_pow2(std::max<size_t>(16384, (size_t)d->segment_count * 8)));
     s.fill_cap = std::max<uint32_t>(s.fill_cap, (uint32_t)round_up_pow2(std::max<size_t>(65536, (size_t)s.line_cap * 2)));
+    s.staging_cap = std::max<uint32_t>(s.staging_cap, (uint32_t)round_up_pow2((size_t)s.line_cap * 4));
     c->slots_used++;
     Cmd cmd{};
     cmd.kind = CMD_PREPARE;
@@ -637,13 +688,16 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->in_flight = false;
         (void)cbytes;
-        uint32_t overflow = 0;
+        uint32_t overflow = 0, dda_anomaly = 0;
         const uint32_t frame_alpha = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
         for (int i = 0; i < c->slots_used; i++) {
             BatchSlot &s = c->slots[i];
-            overflow |= hc[i].overflow;
+            dda_anomaly |= hc[i].overflow & OVF_DDA;  // not a capacity problem: reported, never retried
+            overflow |= hc[i].overflow & ~(uint32_t)OVF_DDA;
             if (hc[i].n_lines > s.line_cap) s.line_cap = (uint32_t)round_up_pow2(hc[i].n_lines);
             if (hc[i].n_fills > s.fill_cap) s.fill_cap = (uint32_t)round_up_pow2(hc[i].n_fills);
+            if (hc[i].n_staging > s.staging_cap) s.staging_cap = (uint32_t)round_up_pow2(hc[i].n_staging);
+            if ((hc[i].overflow & (OVF_LINES | OVF_STAGING)) && s.fill_cap < s.staging_cap) s.fill_cap = s.staging_cap;
             // a line overflow hides the true fill count: make sure fills can grow with the lines
             if ((hc[i].overflow & OVF_LINES) && s.fill_cap < s.line_cap * 2) s.fill_cap = s.line_cap * 2;
         }
@@ -652,6 +706,7 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
             c->mask_cap = (uint32_t)round_up_pow2(frame_alpha);
             CUDA_TRY(c->masks.ensure((size_t)c->mask_cap * 256));
         }
+        c->last_stats.overflow_flags = dda_anomaly;
         if (!overflow) break;
         if (attempt >= 3) {
             c->frame_open = false;
@@ -683,6 +738,7 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
     st.alpha_tiles = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
     st.fb_tiles = (uint32_t)(((c->target.width + TILE - 1) / TILE) * ((c->target.height + TILE - 1) / TILE));
     st.retries = c->retries;
+    st.overflow_flags = c->last_stats.overflow_flags;
     st.kernel_launches = c->launches;
     if (c->event_begin_recorded) {
         float ms = 0.f;
@@ -846,12 +902,12 @@ int64_t pfcu_read_lines(pfcu_ctx *c, uint32_t batch_id, pfcu_line *out) {
     const uint32_t n = std::min(bc.n_lines, s.line_cap);
     if (!out) return n;
     std::vector<float4> l(n);
-    std::vector<uint32_t> p(n);
+    std::vector<uint2> p(n);
     if (n) {
         TAP_TRY(cudaMemcpy(l.data(), s.view.lines, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
-        TAP_TRY(cudaMemcpy(p.data(), s.view.line_path, (size_t)n * 4, cudaMemcpyDeviceToHost));
+        TAP_TRY(cudaMemcpy(p.data(), s.view.line_meta, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost));
     }
-    for (uint32_t i = 0; i < n; i++) out[i] = pfcu_line{l[i].x, l[i].y, l[i].z, l[i].w, p[i]};
+    for (uint32_t i = 0; i < n; i++) out[i] = pfcu_line{l[i].x, l[i].y, l[i].z, l[i].w, p[i].x};
     return n;
 }
 
@@ -940,7 +996,11 @@ int64_t pfcu_read_z(pfcu_ctx *c, uint32_t batch_id, int32_t *out) {
     TAP_TRY(cudaStreamSynchronize(c->stream));
     BatchSlot &s = c->slots[si];
     const uint32_t T = (uint32_t)(s.view.fb_tw * s.view.fb_th);
-    if (out && T) TAP_TRY(cudaMemcpy(out, s.view.z, (size_t)T * 4, cudaMemcpyDeviceToHost));
+    if (out && T) {
+        std::vector<FbTile> fb(T);
+        TAP_TRY(cudaMemcpy(fb.data(), s.view.fb, (size_t)T * sizeof(FbTile), cudaMemcpyDeviceToHost));
+        for (uint32_t t = 0; t < T; t++) out[t] = fb[t].z;
+    }
     return T;
 }
 
@@ -951,23 +1011,18 @@ int64_t pfcu_read_tile_lists(pfcu_ctx *c, uint32_t batch_id, uint32_t *offsets, 
     TAP_TRY(cudaStreamSynchronize(c->stream));
     BatchSlot &s = c->slots[si];
     const uint32_t T = (uint32_t)(s.view.fb_tw * s.view.fb_th), D = s.desc.tile_count;
-    std::vector<uint32_t> cnt(T), cur(T);
-    std::vector<int32_t> z(T);
+    std::vector<FbTile> fb(T);
     std::vector<TilePrim> prims(D);
-    if (T) {
-        TAP_TRY(cudaMemcpy(cnt.data(), s.view.fb_count, (size_t)T * 4, cudaMemcpyDeviceToHost));
-        TAP_TRY(cudaMemcpy(cur.data(), s.view.fb_cursor, (size_t)T * 4, cudaMemcpyDeviceToHost));
-        TAP_TRY(cudaMemcpy(z.data(), s.view.z, (size_t)T * 4, cudaMemcpyDeviceToHost));
-    }
+    if (T) TAP_TRY(cudaMemcpy(fb.data(), s.view.fb, (size_t)T * sizeof(FbTile), cudaMemcpyDeviceToHost));
     if (D) TAP_TRY(cudaMemcpy(prims.data(), s.view.prims, (size_t)D * sizeof(TilePrim), cudaMemcpyDeviceToHost));
     int64_t total = 0;
     std::vector<uint32_t> keys;
     for (uint32_t t = 0; t < T; t++) {
         if (offsets) offsets[t] = (uint32_t)total;
-        const uint32_t end = std::min(cur[t], D), begin = end >= cnt[t] ? end - cnt[t] : 0;
+        const uint32_t begin = std::min(fb[t].begin, D), end = std::min(fb[t].begin + fb[t].count, D);
         keys.clear();
         for (uint32_t k = begin; k < end; k++)
-            if ((int32_t)prims[k].key >= z[t]) keys.push_back(prims[k].key);
+            if ((int32_t)prims[k].key >= fb[t].z) keys.push_back(prims[k].key);
         std::sort(keys.begin(), keys.end());
         if (tiles) memcpy(tiles + total, keys.data(), keys.size() * 4);
         total += (int64_t)keys.size();

@@ -1,6 +1,6 @@
 // Internal device-side contract between the C-ABI (pfcu_api.cu) and the kernels
 // (pfcu_geom.cu: dice / bin, compiled with -fmad=false for bit-exactness against the reference's x86 tiler;
-//  pfcu_tiles.cu: init / scan / propagate / list building; pfcu_raster.cu: fill / composite).
+//  pfcu_tiles.cu: init / scan / scatter / propagate / list building; pfcu_raster.cu: fill / composite).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -21,41 +21,75 @@ constexpr int MAX_DDA_STEPS = 65536;
 
 // Device counters of one batch (one 64-byte line).
 struct BatchCounters {
-    uint32_t n_lines;        // lines emitted by dice (may exceed capacity: overflow)
-    uint32_t n_fills;        // total fills (from the scan)
-    uint32_t n_alpha;        // alpha tiles allocated by this batch
-    uint32_t first_alpha;    // frame-global id of this batch's first alpha tile
-    uint32_t n_listed;       // tiles stitched into framebuffer-tile lists
-    uint32_t overflow;       // bit 0 lines, bit 1 fills, bit 2 alpha tiles (masks), bit 3 list entries
-    uint32_t scan_ticket[2]; // dynamic tile ids for the two look-back scans
-    uint32_t n_list_entries; // total list entries (from the scan over framebuffer tiles)
+    uint32_t n_lines;         // clipped lines emitted by dice (may exceed capacity: overflow)
+    uint32_t n_fills;         // total fills (from the scan)
+    uint32_t n_staging;       // staging slots reserved by dice (upper bound of fills per line, summed)
+    uint32_t first_alpha;     // frame-global id of this batch's first alpha tile
+    uint32_t n_listed;        // tiles stitched into framebuffer-tile lists (before z-cull)
+    uint32_t overflow;        // OverflowBits
+    uint32_t scan_ticket[2];  // dynamic tile ids for the two look-back scans
+    uint32_t n_list_entries;  // total list entries (from the scan over framebuffer tiles)
     uint32_t pad[7];
 };
 static_assert(sizeof(BatchCounters) == 64, "BatchCounters");
 
-enum OverflowBits { OVF_LINES = 1, OVF_FILLS = 2, OVF_ALPHA = 4, OVF_LIST = 8 };
+enum OverflowBits { OVF_LINES = 1, OVF_FILLS = 2, OVF_ALPHA = 4, OVF_LIST = 8, OVF_STAGING = 16, OVF_DDA = 32 };
 
 // Packed per-dense-tile state written by propagate.
-//   x: alpha tile id (int32, -1 none)
-//   y: bits 0-7 backdrop, 8-15 backdrop delta, 16-23 hybrid-equivalent backdrop, 24 listed, 25 has own mask
+//   alpha : alpha tile id (int32, -1 none)
+//   packed: bits 0-7 backdrop, 8-15 backdrop delta, 16-23 hybrid-equivalent backdrop, 24 listed, 25 owns a mask,
+//           26-27 mask ctrl bits of the path (winding / even-odd)
 struct TileState {
     int32_t alpha;
     uint32_t packed;
 };
 
+// One fill waiting for its final position (bin -> scan -> scatter). tile == ~0u marks an unused slot.
+struct StagedFill {
+    uint32_t tile, from, to, pad;
+};
+
 // One entry of a framebuffer tile's list (what tile.comp reads per layer, tile.comp:765-768).
-//   x: dense tile index (sort key == paint order), y: alpha tile id, z: paint | ctrl << 16 | backdrop << 24
 struct TilePrim {
+    uint32_t key;        // dense tile index: sort key == paint order
+    int32_t alpha;       // mask slot or -1
+    uint32_t ctrl_word;  // paint | ctrl << 16 | backdrop << 24
+    uint32_t pad;
+};
+
+// A listed tile on its way into a framebuffer tile's list (propagate -> scan -> list scatter).
+struct ListedRec {
     uint32_t key;
     int32_t alpha;
     uint32_t ctrl_word;
+    uint32_t map;  // framebuffer tile index
+};
+
+// Per framebuffer tile: list range + z (one 16-byte load in the composite kernel).
+struct FbTile {
+    uint32_t begin;  // from the scan
+    uint32_t count;  // entries before z-cull (atomic rank counter in propagate)
+    int32_t z;       // largest dense tile index of an occluding solid tile (propagate.comp:204-206)
     uint32_t pad;
 };
 
 struct AlphaTile {
     uint32_t tile_index;  // dense tile that owns the mask
     int32_t clip_alpha;   // mask slot to min() with, or -1
+    uint32_t packed;      // bits 0-7 backdrop, bit 8 winding rule
+    uint32_t fill_count;
 };
+
+// Per-paint constants decoded once per metadata upload from the RGBA16F texels (tile.comp:694-726).
+struct Paint {
+    float4 base;  // base colour
+    float4 m0;    // colour texture matrix (m11 m21 m12 m22)
+    float4 m1;    // xy: colour texture offset
+    float4 fp0, fp1;
+    int32_t ctrl;  // composite << 10 | combine << 8 | filter << 4
+    int32_t pad[3];
+};
+static_assert(sizeof(Paint) == 96, "Paint");
 
 // Everything a kernel needs to know about one batch. Passed by value.
 struct BatchView {
@@ -75,17 +109,19 @@ struct BatchView {
     // working set
     BatchCounters *counters;
     uint32_t *tile_word;    // [tile_count] low 24 bits: fill count; high 8 bits: backdrop delta
-    uint32_t *fill_cursor;  // [tile_count] exclusive fill offsets -> end offsets after bin scatter
+    uint32_t *fill_cursor;  // [tile_count] exclusive fill offsets -> end offsets after the scatter
     int32_t *col_backdrop;  // [column_count]
     TileState *tile_state;  // [tile_count]
-    float4 *lines;          // [line_capacity]
-    uint32_t *line_path;    // [line_capacity]
+    float4 *lines;          // [line_capacity] clipped lines
+    uint2 *line_meta;       // [line_capacity] x: path index, y: first staging slot
     uint32_t line_capacity;
+    StagedFill *staging;    // [staging_capacity]
+    uint32_t staging_capacity;
     uint2 *fills;           // [fill_capacity] x = from_x | from_y << 16, y = to_x | to_y << 16
     uint32_t fill_capacity;
-    int32_t *z;             // [fb tiles]
-    uint32_t *fb_count;     // [fb tiles] list lengths (before cull)
-    uint32_t *fb_cursor;    // [fb tiles] exclusive offsets -> end offsets after list scatter
+    FbTile *fb;             // [fb tiles]
+    ListedRec *listed;      // [tile_count]
+    uint32_t *listed_rank;  // [tile_count]
     TilePrim *prims;        // [prim_capacity]
     uint32_t prim_capacity;
     AlphaTile *alpha_tiles; // [alpha_capacity] batch-local
@@ -108,8 +144,9 @@ struct TargetView {
 };
 
 struct PaintView {
-    const uint16_t *metadata;  // RGBA16F texels, 1280 per row
-    uint32_t metadata_rows;
+    const Paint *paints;
+    uint32_t n_paints;
+    int all_solid;             // every paint has ctrl == 0: base colour only, src-over
     const uint8_t *color_px;   // colour texture page (RGBA8) or a 1 x 1 dummy
     int color_w, color_h;
     uint32_t sampling_flags;
@@ -120,9 +157,9 @@ struct PaintView {
 // ---- launchers (each enqueues exactly one kernel on `s` and returns the CUDA status) --------------------------
 cudaError_t launch_init(const BatchView &b, cudaStream_t s);
 cudaError_t launch_dice(const BatchView &b, cudaStream_t s);
-cudaError_t launch_bin_count(const BatchView &b, cudaStream_t s);
+cudaError_t launch_bin(const BatchView &b, cudaStream_t s);
 cudaError_t launch_scan_tiles(const BatchView &b, cudaStream_t s);
-cudaError_t launch_bin_scatter(const BatchView &b, cudaStream_t s);
+cudaError_t launch_fill_scatter(const BatchView &b, cudaStream_t s);
 cudaError_t launch_propagate(const BatchView &b, cudaStream_t s);
 cudaError_t launch_scan_fb(const BatchView &b, cudaStream_t s);
 cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s);

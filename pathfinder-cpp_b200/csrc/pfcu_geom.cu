@@ -4,18 +4,71 @@
 // CMakeLists.txt:58-62).
 //
 //   dice  : pathfinder/shaders/d3d11/dice.comp:127-223 stage, with the arithmetic of the hybrid tiler's
-//           recursive flattening (core/d3d9/tiler.cpp:284-315, core/data/segment.cpp:12-135) and its contour
-//           walk (core/data/contour.cpp:110-173) so the lines are the ones the CPU tiler bins.
+//           recursive flattening (core/d3d9/tiler.cpp:284-315, core/data/segment.cpp:12-135), its contour walk
+//           (core/data/contour.cpp:110-173) and its view-box clip (tiler.cpp:46-125,138-153), so the lines are the
+//           ones the CPU tiler bins.
 //   bin   : pathfinder/shaders/d3d11/bin.comp:140-248 stage, with the arithmetic of
-//           core/d3d9/tiler.cpp:46-279 (view-box clip + tile walk) and core/d3d9/object_builder.cpp:19-114
+//           core/d3d9/tiler.cpp:155-279 (tile walk) and core/d3d9/object_builder.cpp:19-114
 //           (fill conversion: clamp [0,4095], round-to-nearest-even; backdrop bookkeeping).
 //
-// B200 mapping. No linked lists and no overflow-and-retry read-backs: bin runs twice over the lines
-// (count -> device-wide scan -> scatter), so each tile's fills land contiguously (CSR) for the fill kernel's
-// coalesced reads. Line allocation in dice is warp-aggregated (one atomic per warp).
+// B200 mapping. No linked lists, no overflow-and-retry read-backs, and the tile walk runs ONCE: dice reserves, per
+// clipped line, an upper bound of staging slots (2 fills per visited tile) with one atomic per warp; bin writes its
+// fills there and counts them per tile with fire-and-forget reductions; a device-wide scan then gives every tile a
+// contiguous range and a fully parallel scatter (pfcu_tiles.cu) moves the staged fills into it (CSR), so the fill
+// kernel reads each tile's fills with coalesced loads.
 #include "pfcu_device.h"
 
 namespace pfcu {
+
+// ------------------------------------------------------------------------------------------------ shared helpers
+
+__device__ __forceinline__ float lerp_clamped(float a, float bq, float t) {  // common/math/basic.h:50-53
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+    return a + (bq - a) * t;
+}
+
+__device__ __forceinline__ unsigned outcode(float x, float y, float left, float right, float bottom) {
+    unsigned c = 0;  // compute_outcode, tiler.cpp:46-62; the top bound is -inf (tiler.cpp:143-144) so TOP never sets
+    if (x < left) c |= 1u; else if (x > right) c |= 2u;
+    if (y > bottom) c |= 8u;
+    return c;
+}
+
+// clip_line_segment_to_rect (Cohen-Sutherland), tiler.cpp:65-125, against the view box with an open top.
+__device__ __forceinline__ bool clip_to_view_box(float &l0, float &l1, float &l2, float &l3, float left, float right,
+                                                 float bottom) {
+    unsigned of = outcode(l0, l1, left, right, bottom), ot = outcode(l2, l3, left, right, bottom);
+    for (int guard = 0; guard < 16; guard++) {
+        if (of == 0 && ot == 0) return true;
+        if ((of & ot) != 0) return false;
+        const bool clip_from = of > ot;
+        const unsigned oc = clip_from ? of : ot;
+        float px = clip_from ? l0 : l2, py = clip_from ? l1 : l3;
+        if (oc & 1u) {
+            py = lerp_clamped(l1, l3, (left - l0) / (l2 - l0));
+            px = left;
+        } else if (oc & 2u) {
+            py = lerp_clamped(l1, l3, (right - l0) / (l2 - l0));
+            px = right;
+        } else if (oc & 8u) {
+            px = lerp_clamped(l0, l2, (bottom - l1) / (l3 - l1));
+            py = bottom;
+        }
+        if (clip_from) { l0 = px; l1 = py; of = outcode(px, py, left, right, bottom); }
+        else { l2 = px; l3 = py; ot = outcode(px, py, left, right, bottom); }
+    }
+    return false;
+}
+
+// Upper bound of the fills one clipped line can emit: the tile walk (tiler.cpp:191-278) visits
+// |dx| + |dy| + 1 tiles and adds at most two fills per tile.
+__device__ __forceinline__ uint32_t fill_bound(float l0, float l1, float l2, float l3) {
+    const long long tx0 = (int)floorf(l0 * 0.0625f), ty0 = (int)floorf(l1 * 0.0625f);
+    const long long tx1 = (int)floorf(l2 * 0.0625f), ty1 = (int)floorf(l3 * 0.0625f);
+    long long d = llabs(tx1 - tx0) + llabs(ty1 - ty0) + 1;
+    if (d > MAX_DDA_STEPS) d = MAX_DDA_STEPS;
+    return (uint32_t)(2 * d);
+}
 
 // ------------------------------------------------------------------------------------------------ dice
 
@@ -90,9 +143,19 @@ __device__ __forceinline__ void flatten(Cubic cur, Emit &&emit) {
 
 __device__ __forceinline__ bool finite2(float2 p) { return isfinite(p.x) && isfinite(p.y); }
 
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, unsigned lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v += t;
+    }
+    return v;
+}
+
 __global__ void __launch_bounds__(128) k_dice(BatchView b) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31;
+    const float left = b.view_box[0], right = b.view_box[2], bottom = b.view_box[3];
     uint32_t path = 0, npt = 0;
     Cubic c;
     bool active = false;
@@ -143,35 +206,49 @@ __global__ void __launch_bounds__(128) k_dice(BatchView b) {
         }
     }
 
-    // Pass 1: count this segment's lines.
-    uint32_t n = 0;
+    // Pass 1: count this segment's surviving lines and the staging slots they may need.
+    uint32_t n = 0, slots = 0;
+    auto count = [&](float2 from, float2 to) {
+        float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
+        if (clip_to_view_box(l0, l1, l2, l3, left, right, bottom)) {
+            n++;
+            slots += fill_bound(l0, l1, l2, l3);
+        }
+    };
     if (active) {
-        if (npt == 2) n = 1;
-        else if (npt == 3) flatten<false>(c, [&](float2, float2) { n++; });
-        else flatten<true>(c, [&](float2, float2) { n++; });
+        if (npt == 2) count(c.p0, c.p3);
+        else if (npt == 3) flatten<false>(c, count);
+        else flatten<true>(c, count);
     }
-    // Warp-aggregated reservation: one atomic per warp.
-    uint32_t incl = n;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (unsigned)d) incl += v;
+    // Warp-aggregated reservation: one atomic per warp and per counter.
+    const uint32_t incl_n = warp_incl_scan(n, lane), incl_s = warp_incl_scan(slots, lane);
+    const uint32_t total_n = __shfl_sync(0xffffffffu, incl_n, 31), total_s = __shfl_sync(0xffffffffu, incl_s, 31);
+    uint32_t base_n = 0, base_s = 0;
+    if (lane == 31 && total_n) {
+        base_n = atomicAdd(&b.counters->n_lines, total_n);
+        base_s = atomicAdd(&b.counters->n_staging, total_s);
     }
-    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t base = 0;
-    if (lane == 31 && total) base = atomicAdd(&b.counters->n_lines, total);
-    base = __shfl_sync(0xffffffffu, base, 31);
+    base_n = __shfl_sync(0xffffffffu, base_n, 31);
+    base_s = __shfl_sync(0xffffffffu, base_s, 31);
     if (!n) return;
-    uint32_t at = base + incl - n;
+    uint32_t at = base_n + incl_n - n, slot = base_s + incl_s - slots;
     if (at + n > b.line_capacity) {
         atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
         return;
     }
-    // Pass 2: emit.
+    if (slot + slots > b.staging_capacity) {
+        atomicOr(&b.counters->overflow, (uint32_t)OVF_STAGING);
+        return;
+    }
+    // Pass 2: emit the clipped lines.
     auto emit = [&](float2 from, float2 to) {
-        b.lines[at] = make_float4(from.x, from.y, to.x, to.y);
-        b.line_path[at] = path;
-        at++;
+        float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
+        if (clip_to_view_box(l0, l1, l2, l3, left, right, bottom)) {
+            b.lines[at] = make_float4(l0, l1, l2, l3);
+            b.line_meta[at] = make_uint2(path, slot);
+            at++;
+            slot += fill_bound(l0, l1, l2, l3);
+        }
     };
     if (npt == 2) emit(c.p0, c.p3);
     else if (npt == 3) flatten<false>(c, emit);
@@ -191,11 +268,10 @@ struct PathTiles {
     uint32_t tile_offset, backdrop_offset;
 };
 
-// ObjectBuilder::add_fill, core/d3d9/object_builder.cpp:19-64
-template <bool SCATTER>
-__device__ __forceinline__ void add_fill(const BatchView &b, const PathTiles &pt, float fx, float fy, float tx,
-                                         float ty, int tcx, int tcy) {
-    if (!(pt.min_x <= tcx && tcx <= pt.max_x - 1 && pt.min_y <= tcy && tcy <= pt.max_y - 1)) return;
+// ObjectBuilder::add_fill, core/d3d9/object_builder.cpp:19-64. Returns true when a fill was staged.
+__device__ __forceinline__ bool add_fill(const BatchView &b, const PathTiles &pt, float fx, float fy, float tx,
+                                         float ty, int tcx, int tcy, uint32_t slot) {
+    if (!(pt.min_x <= tcx && tcx <= pt.max_x - 1 && pt.min_y <= tcy && tcy <= pt.max_y - 1)) return false;
     const float ulx = (float)tcx * 16.0f, uly = (float)tcy * 16.0f;
     float s0 = (fx - ulx) * 256.0f, s1 = (fy - uly) * 256.0f, s2 = (tx - ulx) * 256.0f, s3 = (ty - uly) * 256.0f;
     // clamp(0, 4095) then round to nearest even (F32x4::clamp / round, common/f32x4.h:56-66)
@@ -204,15 +280,12 @@ __device__ __forceinline__ void add_fill(const BatchView &b, const PathTiles &pt
     s2 = rintf(fminf(s2 > 0.0f ? s2 : 0.0f, 4095.0f));
     s3 = rintf(fminf(s3 > 0.0f ? s3 : 0.0f, 4095.0f));
     const uint32_t u0 = (uint32_t)s0, u1 = (uint32_t)s1, u2 = (uint32_t)s2, u3 = (uint32_t)s3;
-    if (u0 == u2) return;  // degenerate (vertical after quantisation)
+    if (u0 == u2) return false;  // degenerate (vertical after quantisation)
     const uint32_t ti = pt.tile_offset + (uint32_t)(tcx - pt.min_x) +
                         (uint32_t)(pt.max_x - pt.min_x) * (uint32_t)(tcy - pt.min_y);
-    if (!SCATTER) {
-        atomicAdd(&b.tile_word[ti], 1u);
-    } else {
-        const uint32_t pos = atomicAdd(&b.fill_cursor[ti], 1u);
-        if (pos < b.fill_capacity) b.fills[pos] = make_uint2(u0 | (u1 << 16), u2 | (u3 << 16));
-    }
+    *reinterpret_cast<uint4 *>(&b.staging[slot]) = make_uint4(ti, u0 | (u1 << 16), u2 | (u3 << 16), 0u);
+    atomicAdd(&b.tile_word[ti], 1u);  // no return value: compiles to a fire-and-forget RED
+    return true;
 }
 
 // ObjectBuilder::adjust_alpha_tile_backdrop, core/d3d9/object_builder.cpp:95-114
@@ -228,50 +301,16 @@ __device__ __forceinline__ void adjust_backdrop(const BatchView &b, const PathTi
     atomicAdd(&b.tile_word[pt.tile_offset + (uint32_t)ox + (uint32_t)w * (uint32_t)oy], (uint32_t)delta << 24);
 }
 
-__device__ __forceinline__ float lerp_clamped(float a, float bq, float t) {  // common/math/basic.h:50-53
-    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
-    return a + (bq - a) * t;
-}
-
-__device__ __forceinline__ unsigned outcode(float x, float y, float left, float right, float bottom) {
-    unsigned c = 0;  // compute_outcode, tiler.cpp:46-62; the top bound is -inf (tiler.cpp:143-144) so TOP never sets
-    if (x < left) c |= 1u; else if (x > right) c |= 2u;
-    if (y > bottom) c |= 8u;
-    return c;
-}
-
-template <bool SCATTER>
 __global__ void __launch_bounds__(128) k_bin(BatchView b) {
     const uint32_t n_lines = min(b.counters->n_lines, b.line_capacity);
-    const float left = b.view_box[0], right = b.view_box[2], bottom = b.view_box[3];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += gridDim.x * blockDim.x) {
         const float4 ln = b.lines[i];
-        const uint32_t path = b.line_path[i];
-        float l0 = ln.x, l1 = ln.y, l2 = ln.z, l3 = ln.w;
-        // clip_line_segment_to_rect (Cohen-Sutherland), tiler.cpp:65-125
-        unsigned of = outcode(l0, l1, left, right, bottom), ot = outcode(l2, l3, left, right, bottom);
-        bool inside = false;
-        for (int guard = 0; guard < 16; guard++) {
-            if (of == 0 && ot == 0) { inside = true; break; }
-            if ((of & ot) != 0) break;
-            const bool clip_from = of > ot;
-            const unsigned oc = clip_from ? of : ot;
-            float px = clip_from ? l0 : l2, py = clip_from ? l1 : l3;
-            if (oc & 1u) {
-                py = lerp_clamped(l1, l3, (left - l0) / (l2 - l0));
-                px = left;
-            } else if (oc & 2u) {
-                py = lerp_clamped(l1, l3, (right - l0) / (l2 - l0));
-                px = right;
-            } else if (oc & 8u) {
-                px = lerp_clamped(l0, l2, (bottom - l1) / (l3 - l1));
-                py = bottom;
-            }
-            if (clip_from) { l0 = px; l1 = py; of = outcode(px, py, left, right, bottom); }
-            else { l2 = px; l3 = py; ot = outcode(px, py, left, right, bottom); }
-        }
-        if (!inside) continue;
-
+        const uint2 lm = b.line_meta[i];
+        const uint32_t path = lm.x;
+        const float l0 = ln.x, l1 = ln.y, l2 = ln.z, l3 = ln.w;
+        uint32_t slot = lm.y;
+        const uint32_t slot_end = slot + fill_bound(l0, l1, l2, l3);
+        if (slot_end > b.staging_capacity) continue;  // dice flagged the overflow; the frame will be replayed
         PathTiles pt;
         {
             const int4 r = __ldg(reinterpret_cast<const int4 *>(&b.meta[path].tile_rect[0]));
@@ -300,16 +339,18 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
             next_t = next_t < 1.0f ? next_t : 1.0f;
             if (tcx == to_tx && tcy == to_ty) next_dir = 0;
             const float nx = l0 + vx * next_t, ny = l1 + vy * next_t;  // LineSegmentF::sample
-            add_fill<SCATTER>(b, pt, cur_x, cur_y, nx, ny, tcx, tcy);
+            if (slot + 2 > slot_end) {  // the walk left the |dx|+|dy|+1 envelope (only with non-finite arithmetic)
+                atomicOr(&b.counters->overflow, (uint32_t)OVF_DDA);
+                break;
+            }
+            if (add_fill(b, pt, cur_x, cur_y, nx, ny, tcx, tcy, slot)) slot++;
             if (step_y < 0 && next_dir == 2) {
-                add_fill<SCATTER>(b, pt, nx, ny, (float)tcx * ts, (float)tcy * ts, tcx, tcy);
+                if (add_fill(b, pt, nx, ny, (float)tcx * ts, (float)tcy * ts, tcx, tcy, slot)) slot++;
             } else if (step_y > 0 && last_dir == 2) {
-                add_fill<SCATTER>(b, pt, (float)tcx * ts, (float)tcy * ts, cur_x, cur_y, tcx, tcy);
+                if (add_fill(b, pt, (float)tcx * ts, (float)tcy * ts, cur_x, cur_y, tcx, tcy, slot)) slot++;
             }
-            if (!SCATTER) {
-                if (step_x < 0 && last_dir == 1) adjust_backdrop(b, pt, tcx, tcy, 1);
-                else if (step_x > 0 && next_dir == 1) adjust_backdrop(b, pt, tcx, tcy, -1);
-            }
+            if (step_x < 0 && last_dir == 1) adjust_backdrop(b, pt, tcx, tcy, 1);
+            else if (step_x > 0 && next_dir == 1) adjust_backdrop(b, pt, tcx, tcy, -1);
             if (next_dir == 1) { t_max_x += t_delta_x; tcx += step_x; }
             else if (next_dir == 2) { t_max_y += t_delta_y; tcy += step_y; }
             else break;
@@ -317,20 +358,13 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
             cur_y = ny;
             last_dir = next_dir;
         }
+        for (; slot < slot_end; slot++) b.staging[slot].tile = 0xffffffffu;  // unused slots
     }
 }
 
-static int bin_grid() { return sm_count() * 8; }
-
-cudaError_t launch_bin_count(const BatchView &b, cudaStream_t s) {
+cudaError_t launch_bin(const BatchView &b, cudaStream_t s) {
     if (!b.segment_count) return cudaSuccess;
-    k_bin<false><<<bin_grid(), 128, 0, s>>>(b);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_bin_scatter(const BatchView &b, cudaStream_t s) {
-    if (!b.segment_count) return cudaSuccess;
-    k_bin<true><<<bin_grid(), 128, 0, s>>>(b);
+    k_bin<<<sm_count() * 8, 128, 0, s>>>(b);
     return cudaGetLastError();
 }
 

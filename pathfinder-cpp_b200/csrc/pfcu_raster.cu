@@ -2,12 +2,14 @@
 //
 //   fill : pathfinder/shaders/d3d11/fill.comp:51-154. One warp per alpha tile; a lane owns one pixel column of two
 //          4-row groups (the LUT's four channels are four consecutive rows). The tile's fills are contiguous
-//          (CSR from the bin scatter), read once with coalesced 8-byte loads and broadcast by shuffle; coverage is
+//          (CSR from the scatter), read once with coalesced 8-byte loads and broadcast by shuffle; coverage is
 //          accumulated in registers; the 16 x 16 mask is written once, 1 byte per pixel.
 //   tile : pathfinder/shaders/d3d11/tile.comp:737-850 with the shading functions of tile.comp:126-134 (combine),
 //          :319-347 (radial gradient), :354-392 (blur), :459-582 (composite), :586-607 (mask), :694-726 (paint
-//          metadata). One CTA per framebuffer tile; its list is sorted by paint order and z-culled on chip
-//          (sort.comp:49-83), layers are blended in fp32 registers and each thread stores 4 pixels = 16 bytes.
+//          metadata, decoded once per upload into a float table). One WARP per framebuffer tile (no block barriers):
+//          one 16-byte load gives the tile's list range and z; the list is sorted by paint order and z-culled on
+//          chip (sort.comp:49-83); a lane blends 8 pixels of one row in fp32 registers and stores them with two
+//          16-byte stores. Scenes whose paints are all solid take a specialised instantiation.
 #include <cuda_fp16.h>
 
 #include "pfcu_device.h"
@@ -103,16 +105,16 @@ __global__ void __launch_bounds__(256) k_fill(BatchView b, PaintView p) {
     for (uint32_t a = warp; a < n_alpha; a += n_warps) {
         const uint32_t id = first_alpha + a;
         if (id >= b.mask_capacity) break;
-        const AlphaTile at = b.alpha_tiles[a];
+        AlphaTile at;
+        *reinterpret_cast<uint4 *>(&at) = *reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]);
         const uint32_t ti = at.tile_index;
         if (ti >= b.tile_count) continue;
-        const TileState st = b.tile_state[ti];
-        const uint32_t count = b.tile_word[ti] & 0x00ffffffu;
+        const uint32_t count = at.fill_count;
         uint32_t end = b.fill_cursor[ti];
         if (end > b.fill_capacity) end = b.fill_capacity;
         const uint32_t begin = end >= count ? end - count : 0u;
-        const float backdrop = (float)(int8_t)(st.packed & 0xffu);
-        const bool winding = ((st.packed >> 26) & 0x1u) != 0;
+        const float backdrop = (float)(int8_t)(at.packed & 0xffu);
+        const bool winding = (at.packed & 0x100u) != 0;
         float4 cov0 = make_float4(backdrop, backdrop, backdrop, backdrop), cov1 = cov0;
         const float fragy0 = (float)(g0 * 4) + 0.5f, fragy1 = (float)((g0 + 2) * 4) + 0.5f;
         for (uint32_t c = begin; c < end; c += 32) {
@@ -146,20 +148,11 @@ __global__ void __launch_bounds__(256) k_fill(BatchView b, PaintView p) {
 
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s) {
     if (!b.tile_count || !p.area_lut) return cudaSuccess;
-    k_fill<<<sm_count() * 4, 256, 0, s>>>(b, p);
+    k_fill<<<sm_count() * 16, 256, 0, s>>>(b, p);
     return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------ tile
-
-__device__ __forceinline__ float4 metadata_texel(const PaintView &p, int color_entry, int entry) {
-    const int x = color_entry % 128 * 10 + entry, y = color_entry / 128;  // tile.comp:708
-    if ((uint32_t)y >= p.metadata_rows) return make_float4(0.f, 0.f, 0.f, 0.f);
-    const uint2 raw = __ldg(reinterpret_cast<const uint2 *>(p.metadata) + (size_t)y * 1280 + x);
-    const __half2 lo = *reinterpret_cast<const __half2 *>(&raw.x), hi = *reinterpret_cast<const __half2 *>(&raw.y);
-    const float2 a = __half22float2(lo), c = __half22float2(hi);
-    return make_float4(a.x, a.y, c.x, c.y);
-}
 
 struct ColorSampler {
     const uint8_t *px;
@@ -290,55 +283,39 @@ __device__ void composite_rgb(const float d[3], const float s[3], int op, float 
     }
 }
 
-// Everything about a paint that does not depend on the pixel (computeTileVaryings, tile.comp:694-726).
-struct PaintConsts {
-    float4 m0, m1, base, fp0, fp1;
-    int ctrl;
-};
-
-__device__ __forceinline__ PaintConsts load_paint(const PaintView &p, int color_entry) {
-    PaintConsts pc;
-    pc.m0 = metadata_texel(p, color_entry, 0);
-    pc.m1 = metadata_texel(p, color_entry, 1);
-    pc.base = metadata_texel(p, color_entry, 2);
-    pc.ctrl = (int)metadata_texel(p, color_entry, 8).x;
-    if ((pc.ctrl >> 8) & 0x3) {
-        pc.fp0 = metadata_texel(p, color_entry, 3);
-        pc.fp1 = metadata_texel(p, color_entry, 4);
-    } else {
-        pc.fp0 = pc.fp1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    return pc;
-}
-
 // calculateColor, tile.comp:611-675: premultiplied source colour of one layer at one pixel.
-__device__ __forceinline__ float4 shade(const PaintConsts &pc, const ColorSampler &cs, float fragx, float fragy,
+template <bool SOLID>
+__device__ __forceinline__ float4 shade(const Paint &pc, const ColorSampler &cs, float fragx, float fragy,
                                         float mask_alpha, float fb_w, float fb_h) {
     float4 color = pc.base;
-    const int combine = (pc.ctrl >> 8) & 0x3;
-    if (combine != 0) {
-        const float cu = pc.m0.x * fragx + pc.m0.z * fragy + pc.m1.x;
-        const float cv = pc.m0.y * fragx + pc.m0.w * fragy + pc.m1.y;
-        const int filter = (pc.ctrl >> 4) & 0xf;
-        float4 c0;
-        if (filter == 0x1) c0 = filter_radial(cs, cu, cv, pc.fp0, pc.fp1);
-        else if (filter == 0x3) c0 = filter_blur(cs, cu, cv, pc.fp0, pc.fp1);
-        else c0 = cs(cu, cv);
-        if (combine == 0x1) color = make_float4(c0.x, c0.y, c0.z, c0.w * color.w);  // SRC_IN, tile.comp:128-129
-        else if (combine == 0x2) color.w = c0.w * color.w;                          // DEST_IN, tile.comp:130-131
+    if (!SOLID) {
+        const int combine = (pc.ctrl >> 8) & 0x3;
+        if (combine != 0) {
+            const float cu = pc.m0.x * fragx + pc.m0.z * fragy + pc.m1.x;
+            const float cv = pc.m0.y * fragx + pc.m0.w * fragy + pc.m1.y;
+            const int filter = (pc.ctrl >> 4) & 0xf;
+            float4 c0;
+            if (filter == 0x1) c0 = filter_radial(cs, cu, cv, pc.fp0, pc.fp1);
+            else if (filter == 0x3) c0 = filter_blur(cs, cu, cv, pc.fp0, pc.fp1);
+            else c0 = cs(cu, cv);
+            if (combine == 0x1) color = make_float4(c0.x, c0.y, c0.z, c0.w * color.w);  // SRC_IN, tile.comp:128-129
+            else if (combine == 0x2) color.w = c0.w * color.w;                          // DEST_IN, tile.comp:130-131
+        }
     }
     color.w *= mask_alpha;
-    const int op = (pc.ctrl >> 10) & 0xf;
-    if (op != 0) {  // composite(), tile.comp:564-582; the "dest" it samples is the colour texture (FIXME upstream, :820-826)
-        const float4 dc = cs(fragx / fb_w, fragy / fb_h);
-        const float d[3] = {dc.x, dc.y, dc.z}, s[3] = {color.x, color.y, color.z};
-        float blended[3];
-        composite_rgb(d, s, op, blended);
-        const float sa = color.w, da = dc.w;
-        color.x = sa * (1.0f - da) * color.x + sa * da * blended[0] + (1.0f - sa) * dc.x;
-        color.y = sa * (1.0f - da) * color.y + sa * da * blended[1] + (1.0f - sa) * dc.y;
-        color.z = sa * (1.0f - da) * color.z + sa * da * blended[2] + (1.0f - sa) * dc.z;
-        color.w = 1.0f;
+    if (!SOLID) {
+        const int op = (pc.ctrl >> 10) & 0xf;
+        if (op != 0) {  // composite(), tile.comp:564-582; its "dest" is the colour texture (FIXME upstream, :820-826)
+            const float4 dc = cs(fragx / fb_w, fragy / fb_h);
+            const float d[3] = {dc.x, dc.y, dc.z}, s[3] = {color.x, color.y, color.z};
+            float blended[3];
+            composite_rgb(d, s, op, blended);
+            const float sa = color.w, da = dc.w;
+            color.x = sa * (1.0f - da) * color.x + sa * da * blended[0] + (1.0f - sa) * dc.x;
+            color.y = sa * (1.0f - da) * color.y + sa * da * blended[1] + (1.0f - sa) * dc.y;
+            color.z = sa * (1.0f - da) * color.z + sa * da * blended[2] + (1.0f - sa) * dc.z;
+            color.w = 1.0f;
+        }
     }
     color.x *= color.w;
     color.y *= color.w;
@@ -346,7 +323,8 @@ __device__ __forceinline__ float4 shade(const PaintConsts &pc, const ColorSample
     return color;
 }
 
-constexpr int MAX_SORTED = 128;  // list entries sorted in shared memory; longer lists fall back to selection
+constexpr int MAX_SORTED = 64;      // list entries sorted in shared memory per warp; longer lists use selection
+constexpr int COMPOSITE_WARPS = 4;  // framebuffer tiles per CTA
 
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
     const uint32_t r = (uint32_t)__float2int_rn(clampf(c.x, 0.f, 1.f) * 255.0f);
@@ -362,52 +340,58 @@ __device__ __forceinline__ float4 unpack_rgba8(uint32_t v) {
                        (float)(v >> 24) * k);
 }
 
-__global__ void __launch_bounds__(64) k_composite(BatchView b, PaintView p, TargetView tg, int clear, float4 clear_color) {
-    __shared__ TilePrim s_prims[MAX_SORTED];
-    __shared__ uint32_t s_min[2];
-    const int tile_x = (int)blockIdx.x, tile_y = (int)blockIdx.y;
-    const uint32_t map = (uint32_t)tile_y * (uint32_t)b.fb_tw + (uint32_t)tile_x;
-    const uint32_t count = b.fb_count[map];
-    if (count == 0 && !clear) return;  // tile.comp:743-744
-    uint32_t end = b.fb_cursor[map];
-    if (end > b.prim_capacity) end = b.prim_capacity;
-    const uint32_t begin = end >= count ? end - count : 0u;
-    const uint32_t n = end - begin;
-    const int z = b.z[map];
-    const int tid = (int)threadIdx.x;
+template <bool SOLID>
+__global__ void __launch_bounds__(COMPOSITE_WARPS * 32) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
+                                                                    float4 clear_color) {
+    __shared__ uint4 s_prims[COMPOSITE_WARPS][MAX_SORTED];
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
+    const uint32_t map = blockIdx.x * COMPOSITE_WARPS + wib;
+    if (map >= n_fb) return;
+    const int tile_x = (int)(map % (uint32_t)b.fb_tw), tile_y = (int)(map / (uint32_t)b.fb_tw);
+    const uint4 fbt = __ldg(reinterpret_cast<const uint4 *>(&b.fb[map]));  // begin, count, z
+    uint32_t n = fbt.y;
+    if (n == 0 && !clear) return;  // tile.comp:743-744
+    const uint32_t begin = fbt.x;
+    if (begin + n > b.prim_capacity) n = begin < b.prim_capacity ? b.prim_capacity - begin : 0u;
+    const int z = (int)fbt.z;
 
-    // Sort by paint order and z-cull on chip (sort.comp:49-83): rank sort, keys are unique.
-    uint32_t n_sorted = 0;
-    const bool in_smem = n <= MAX_SORTED;
-    if (in_smem) {
-        __shared__ uint32_t s_keys[MAX_SORTED];
-        __shared__ uint32_t s_kept;
-        if (tid == 0) s_kept = 0;
-        for (uint32_t i = tid; i < n; i += 64) s_keys[i] = b.prims[begin + i].key;
-        __syncthreads();
-        for (uint32_t i = tid; i < n; i += 64) {
-            const uint32_t key = s_keys[i];
-            if ((int)key >= z) {
-                uint32_t rank = 0;
-                for (uint32_t j = 0; j < n; j++) rank += (s_keys[j] < key && (int)s_keys[j] >= z) ? 1u : 0u;
-                s_prims[rank] = b.prims[begin + i];
-                atomicAdd(&s_kept, 1u);
-            }
-        }
-        __syncthreads();
-        n_sorted = s_kept;
-    }
-
-    const int row = tid >> 2, x0 = (tid & 3) * 4;
+    const int row = (int)(lane >> 1), x0 = (int)(lane & 1) * 8;
     const int gx0 = tile_x * TILE + x0, gy = tile_y * TILE + row;
     const bool row_ok = gy < tg.height;
     uint32_t *dst = reinterpret_cast<uint32_t *>(tg.pixels + (size_t)gy * tg.pitch) + gx0;
-    float4 dest[4];
+    float4 dest[8];
+    if (clear) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        if (clear) dest[k] = clear_color;
-        else dest[k] = (row_ok && gx0 + k < tg.width) ? unpack_rgba8(dst[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 8; k++) dest[k] = clear_color;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            dest[k] = (row_ok && gx0 + k < tg.width) ? unpack_rgba8(dst[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+
+    // Sort by paint order and z-cull on chip (sort.comp:49-83). Keys (dense tile indices) are unique.
+    uint32_t n_sorted = 0;
+    const bool in_smem = n <= MAX_SORTED;
+    if (in_smem && n) {
+        uint4 e0 = make_uint4(0xffffffffu, 0, 0, 0), e1 = e0;
+        if (lane < n) e0 = __ldg(reinterpret_cast<const uint4 *>(&b.prims[begin + lane]));
+        if (lane + 32 < n) e1 = __ldg(reinterpret_cast<const uint4 *>(&b.prims[begin + lane + 32]));
+        const bool keep0 = lane < n && (int)e0.x >= z, keep1 = lane + 32 < n && (int)e1.x >= z;
+        uint32_t r0 = 0, r1 = 0;
+        const int rounds = n > 32 ? 64 : 32;
+        for (int j = 0; j < rounds; j++) {
+            const uint32_t kj = __shfl_sync(0xffffffffu, j < 32 ? e0.x : e1.x, j & 31);
+            const bool vj = (uint32_t)j < n && (int)kj >= z;
+            r0 += (vj && kj < e0.x) ? 1u : 0u;
+            r1 += (vj && kj < e1.x) ? 1u : 0u;
+        }
+        if (keep0) s_prims[wib][r0] = e0;
+        if (keep1) s_prims[wib][r1] = e1;
+        n_sorted = (uint32_t)(__popc(__ballot_sync(0xffffffffu, keep0)) + __popc(__ballot_sync(0xffffffffu, keep1)));
+        __syncwarp();
+    }
+
     ColorSampler cs;
     cs.px = p.color_px;
     cs.w = p.color_w;
@@ -420,56 +404,74 @@ __global__ void __launch_bounds__(64) k_composite(BatchView b, PaintView p, Targ
     uint32_t last_key = 0;
     bool first_iter = true;
     for (uint32_t layer = 0;; layer++) {
-        TilePrim prim;
+        uint4 prim;
         if (in_smem) {
             if (layer >= n_sorted) break;
-            prim = s_prims[layer];
+            prim = s_prims[wib][layer];
         } else {
             // selection: next smallest key >= z that is greater than the last one processed
-            uint32_t best = 0xffffffffu;
-            for (uint32_t i = tid; i < n; i += 64) {
-                const uint32_t key = b.prims[begin + i].key;
-                if ((int)key >= z && (first_iter || key > last_key) && key < best) best = key;
+            uint32_t best = 0xffffffffu, best_i = 0;
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t key = __ldg(&b.prims[begin + i].key);
+                if ((int)key >= z && (first_iter || key > last_key) && key < best) {
+                    best = key;
+                    best_i = i;
+                }
             }
-            for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-            __syncthreads();
-            if ((tid & 31) == 0) s_min[tid >> 5] = best;
-            __syncthreads();
-            best = min(s_min[0], s_min[1]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                if (ob < best) {
+                    best = ob;
+                    best_i = oi;
+                }
+            }
             if (best == 0xffffffffu) break;
-            prim.key = best;
-            prim.alpha = -1;
-            prim.ctrl_word = 0;
-            for (uint32_t i = 0; i < n; i++)
-                if (b.prims[begin + i].key == best) prim = b.prims[begin + i];
+            prim = __ldg(reinterpret_cast<const uint4 *>(&b.prims[begin + best_i]));
             last_key = best;
             first_iter = false;
         }
         // tile.comp:765-800
-        const int color_entry = (int)(prim.ctrl_word & 0xffffu);
-        int tile_ctrl = (int)((prim.ctrl_word >> 16) & 0xffu);
-        const int backdrop = (int)prim.ctrl_word >> 24;
+        const uint32_t color_entry = prim.z & 0xffffu;
+        int tile_ctrl = (int)((prim.z >> 16) & 0xffu);
+        const int backdrop = (int)prim.z >> 24;
+        const int alpha = (int)prim.y;
         const uint8_t *mask = nullptr;
-        if (prim.alpha >= 0) {
-            if ((uint32_t)prim.alpha < b.mask_capacity) mask = b.masks + (size_t)prim.alpha * 256;
+        if (alpha >= 0) {
+            if ((uint32_t)alpha < b.mask_capacity) mask = b.masks + (size_t)alpha * 256;
         } else {
             if (backdrop != 0 && (tile_ctrl & 0x2) && (abs(backdrop) & 1) == 0) continue;  // tile.comp:786-792
             tile_ctrl &= ~0x3;
         }
         const int mask_ctrl = tile_ctrl & 0x3;
-        uint32_t mask4 = 0xffffffffu;
-        if (mask_ctrl != 0 && mask) mask4 = __ldg(reinterpret_cast<const uint32_t *>(mask + row * 16 + x0));
-        const PaintConsts pc = load_paint(p, color_entry);
+        uint2 mask8 = make_uint2(0xffffffffu, 0xffffffffu);
+        if (mask_ctrl != 0 && mask) mask8 = __ldg(reinterpret_cast<const uint2 *>(mask + row * 16 + x0));
+        Paint pc;
+        if (color_entry < p.n_paints) {
+            pc.base = __ldg(&p.paints[color_entry].base);
+            if (!SOLID) {
+                pc.m0 = __ldg(&p.paints[color_entry].m0);
+                pc.m1 = __ldg(&p.paints[color_entry].m1);
+                pc.fp0 = __ldg(&p.paints[color_entry].fp0);
+                pc.fp1 = __ldg(&p.paints[color_entry].fp1);
+                pc.ctrl = __ldg(&p.paints[color_entry].ctrl);
+            }
+        } else {
+            pc.base = pc.m0 = pc.m1 = pc.fp0 = pc.fp1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            pc.ctrl = 0;
+        }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 8; k++) {
             float mask_alpha = 1.0f;
             if (mask_ctrl != 0) {  // sampleMask, tile.comp:586-607 (backdrop is 0 for alpha tiles)
-                float cov = (float)((mask4 >> (8 * k)) & 0xffu) * (1.0f / 255.0f);
+                const uint32_t m = k < 4 ? mask8.x : mask8.y;
+                float cov = (float)((m >> (8 * (k & 3))) & 0xffu) * (1.0f / 255.0f);
                 if (mask_ctrl & 0x1) cov = fabsf(cov);
                 else cov = 1.0f - fabsf(1.0f - glsl_mod(cov, 2.0f));
                 mask_alpha = fminf(mask_alpha, cov);
             }
-            const float4 src = shade(pc, cs, (float)(gx0 + k) + 0.5f, fragy, mask_alpha, (float)tg.width, (float)tg.height);
+            const float4 src = shade<SOLID>(pc, cs, (float)(gx0 + k) + 0.5f, fragy, mask_alpha, (float)tg.width,
+                                            (float)tg.height);
             const float ia = 1.0f - src.w;  // tile.comp:841
             dest[k].x = dest[k].x * ia + src.x;
             dest[k].y = dest[k].y * ia + src.y;
@@ -478,12 +480,14 @@ __global__ void __launch_bounds__(64) k_composite(BatchView b, PaintView p, Targ
         }
     }
     if (!row_ok) return;
-    if (gx0 + 3 < tg.width) {
-        const uint4 out = make_uint4(pack_rgba8(dest[0]), pack_rgba8(dest[1]), pack_rgba8(dest[2]), pack_rgba8(dest[3]));
-        *reinterpret_cast<uint4 *>(dst) = out;  // 16-byte store
+    if (gx0 + 7 < tg.width) {
+        reinterpret_cast<uint4 *>(dst)[0] =
+            make_uint4(pack_rgba8(dest[0]), pack_rgba8(dest[1]), pack_rgba8(dest[2]), pack_rgba8(dest[3]));
+        reinterpret_cast<uint4 *>(dst)[1] =
+            make_uint4(pack_rgba8(dest[4]), pack_rgba8(dest[5]), pack_rgba8(dest[6]), pack_rgba8(dest[7]));
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; k++)
+        for (int k = 0; k < 8; k++)
             if (gx0 + k < tg.width) dst[k] = pack_rgba8(dest[k]);
     }
 }
@@ -491,9 +495,11 @@ __global__ void __launch_bounds__(64) k_composite(BatchView b, PaintView p, Targ
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
                              const float clear_color[4], cudaStream_t s) {
     if (b.fb_tw <= 0 || b.fb_th <= 0) return cudaSuccess;
-    dim3 grid((unsigned)b.fb_tw, (unsigned)b.fb_th);
+    const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
+    const unsigned grid = (n_fb + COMPOSITE_WARPS - 1) / COMPOSITE_WARPS;
     const float4 cc = make_float4(clear_color[0], clear_color[1], clear_color[2], clear_color[3]);
-    k_composite<<<grid, 64, 0, s>>>(b, p, t, clear, cc);
+    if (p.all_solid) k_composite<true><<<grid, COMPOSITE_WARPS * 32, 0, s>>>(b, p, t, clear, cc);
+    else k_composite<false><<<grid, COMPOSITE_WARPS * 32, 0, s>>>(b, p, t, clear, cc);
     return cudaGetLastError();
 }
 

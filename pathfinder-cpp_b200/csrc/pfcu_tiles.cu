@@ -8,12 +8,16 @@
 //   scan           : single-pass decoupled look-back exclusive scan (Merrill & Garland 2016). It replaces the
 //                    reference's atomic bump allocation + CPU read-back + retry (renderer.cpp:559-577,832-845):
 //                    fill offsets per dense tile, list offsets per framebuffer tile.
+//   fill scatter   : one thread per staged fill moves it to its tile's contiguous range (CSR).
 //   propagate      : pathfinder/shaders/d3d11/propagate.comp:95-216 (== Tiler::prepare_tiles,
-//                    core/d3d9/tiler.cpp:369-439): column prefix sum of backdrops, clip resolution, alpha-tile
-//                    allocation, z-buffer, list membership.
+//                    core/d3d9/tiler.cpp:369-439). The reference walks each tile column serially in one thread;
+//                    here a WARP owns a column, lanes are 32 consecutive rows, and the backdrop is a warp-shuffle
+//                    prefix sum carried across 32-row chunks. Each lane then resolves its own tile: clip cases,
+//                    alpha-tile allocation (one atomic per warp), z-buffer, list membership.
 //   list scatter   : replaces the per-framebuffer-tile linked list (propagate.comp:209-212) + the global-memory
-//                    insertion sort (sort.comp:49-83) with contiguous (CSR) lists; ordering and z-culling happen
-//                    on chip in the composite kernel.
+//                    insertion sort (sort.comp:49-83) with contiguous (CSR) lists: propagate takes a rank per
+//                    listed tile, the scan turns counts into offsets, one thread per listed tile writes its entry.
+//                    Ordering and z-culling happen on chip in the composite kernel.
 #include "pfcu_device.h"
 
 namespace pfcu {
@@ -43,10 +47,7 @@ __global__ void __launch_bounds__(256) k_init(BatchView b) {
     const uint32_t fbt = (uint32_t)(b.fb_tw * b.fb_th);
     for (uint32_t i = tid; i < b.tile_count; i += stride) b.tile_word[i] = 0u;
     for (uint32_t i = tid; i < b.column_count; i += stride) b.col_backdrop[i] = __ldg(&b.backdrops[i].initial_backdrop);
-    for (uint32_t i = tid; i < fbt; i += stride) {
-        b.fb_count[i] = 0u;
-        b.z[i] = 0;
-    }
+    for (uint32_t i = tid; i < fbt; i += stride) *reinterpret_cast<uint4 *>(&b.fb[i]) = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t i = tid; i < scan_tiles_for(b.tile_count); i += stride) b.scan_desc[0][i] = 0ull;
     for (uint32_t i = tid; i < scan_tiles_for(fbt); i += stride) b.scan_desc[1][i] = 0ull;
     if (tid == 0) {
@@ -72,12 +73,11 @@ cudaError_t launch_init(const BatchView &b, cudaStream_t s) {
 
 constexpr unsigned long long FLAG_AGGREGATE = 1ull << 62, FLAG_PREFIX = 2ull << 62, FLAG_MASK = 3ull << 62;
 
-// WHICH 0: fills per dense tile (tile_word & 0xffffff -> fill_cursor), 1: list entries per framebuffer tile.
+// WHICH 0: fills per dense tile (tile_word & 0xffffff -> fill_cursor), 1: list entries per framebuffer tile
+// (fb[t].count -> fb[t].begin).
 template <int WHICH>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
     const uint32_t n = WHICH == 0 ? b.tile_count : (uint32_t)(b.fb_tw * b.fb_th);
-    const uint32_t *in = WHICH == 0 ? b.tile_word : b.fb_count;
-    uint32_t *out = WHICH == 0 ? b.fill_cursor : b.fb_cursor;
     unsigned long long *desc = b.scan_desc[WHICH];
     __shared__ uint32_t s_tile, s_warp[SCAN_THREADS / 32], s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(&b.counters->scan_ticket[WHICH], 1u);  // forward progress: tiles start in order
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
     uint32_t sum = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        uint32_t x = base + k < n ? in[base + k] : 0u;
-        if (WHICH == 0) x &= 0x00ffffffu;
+        uint32_t x = 0;
+        if (base + k < n) x = WHICH == 0 ? (b.tile_word[base + k] & 0x00ffffffu) : b.fb[base + k].count;
         v[k] = sum;  // exclusive within the thread
         sum += x;
     }
@@ -143,8 +143,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
     __syncthreads();
     const uint32_t off = s_prefix + warp_off + (incl - sum);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++)
-        if (base + k < n) out[base + k] = off + v[k];
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (base + k < n) {
+            if (WHICH == 0) b.fill_cursor[base + k] = off + v[k];
+            else b.fb[base + k].begin = off + v[k];
+        }
+    }
     // the last tile owns the grand total
     if (tile == scan_tiles_for(n) - 1 && threadIdx.x == 0) {
         const uint32_t total = s_prefix + block_total;
@@ -171,13 +175,30 @@ cudaError_t launch_scan_fb(const BatchView &b, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ fill scatter
+
+__global__ void __launch_bounds__(256) k_fill_scatter(BatchView b) {
+    const uint32_t n = min(b.counters->n_staging, b.staging_capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 f = *reinterpret_cast<const uint4 *>(&b.staging[i]);
+        if (f.x >= b.tile_count) continue;  // unused slot
+        const uint32_t pos = atomicAdd(&b.fill_cursor[f.x], 1u);
+        if (pos < b.fill_capacity) b.fills[pos] = make_uint2(f.y, f.z);
+    }
+}
+
+cudaError_t launch_fill_scatter(const BatchView &b, cudaStream_t s) {
+    if (!b.segment_count || !b.tile_count) return cudaSuccess;
+    k_fill_scatter<<<sm_count() * 8, 256, 0, s>>>(b);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ propagate
 
-// SCATTER == false: propagate.comp:95-216. SCATTER == true: second walk that writes the list entries at the
-// offsets the scan produced (same visiting order, so both passes agree on membership).
-template <bool SCATTER>
+// One warp per tile column; lanes are 32 consecutive rows (propagate.comp:95-216, tiler.cpp:369-439).
 __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
-    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
     if (col >= b.column_count) return;
     const uint32_t path = __ldg(&b.backdrops[col].path_index);
     const int tx = __ldg(&b.backdrops[col].tile_x_offset);
@@ -188,26 +209,6 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
     const pfcu_tile_path_info info = b.tpi[path];
     const uint32_t ctrl_base = (uint32_t)info.color | ((uint32_t)info.ctrl << 16);
     const int gx = tx + rect.x;
-
-    if (SCATTER) {
-        for (int ty = 0; ty < h; ty++) {
-            const uint32_t ti = tile_offset + (uint32_t)tx + (uint32_t)w * (uint32_t)ty;
-            const TileState st = b.tile_state[ti];
-            if (!(st.packed & (1u << 24))) continue;
-            const uint32_t map = (uint32_t)(ty + rect.y) * (uint32_t)b.fb_tw + (uint32_t)gx;
-            const uint32_t pos = atomicAdd(&b.fb_cursor[map], 1u);
-            if (pos < b.prim_capacity) {
-                TilePrim p;
-                p.key = ti;
-                p.alpha = st.alpha;
-                p.ctrl_word = ctrl_base | ((st.packed & 0xffu) << 24);
-                p.pad = 0;
-                b.prims[pos] = p;
-            }
-        }
-        return;
-    }
-
     const uint32_t z_write_path = __ldg(&b.meta[path].z_write);
     const uint32_t clip_index = __ldg(&b.meta[path].clip_path_index);
     const bool has_clip = (int32_t)clip_index >= 0;
@@ -220,19 +221,31 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
     }
     const bool even_odd = (info.ctrl & 0x2) != 0;
     const uint32_t first_alpha = b.counters->first_alpha;
-    int cur = b.col_backdrop[col];
+    int carry = b.col_backdrop[col];
 
-    for (int ty = 0; ty < h; ty++) {
-        const uint32_t ti = tile_offset + (uint32_t)tx + (uint32_t)w * (uint32_t)ty;
-        const uint32_t word = b.tile_word[ti];
+    for (int ty0 = 0; ty0 < h; ty0 += 32) {
+        const int ty = ty0 + (int)lane;
+        const bool valid = ty < h;
+        const uint32_t ti = tile_offset + (uint32_t)tx + (uint32_t)w * (uint32_t)(valid ? ty : 0);
+        const uint32_t word = valid ? b.tile_word[ti] : 0u;
         const int delta = (int)(int8_t)(word >> 24);
+        // exclusive prefix of the deltas down the column (tiler.cpp:394,437)
+        int incl = delta;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const int cur = carry + incl - delta;
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+
         const bool have_mask = (word & 0x00ffffffu) != 0;
         int backdrop = (int)(int8_t)cur;  // int8_t(backdrops[column]), tiler.cpp:394
         int backdrop9 = backdrop;
-        bool need_new = have_mask;
+        bool need_new = valid && have_mask;
         int alpha = -1, clip_alpha = -1;
         const int gy = ty + rect.y;
-        if (has_clip) {
+        if (has_clip && valid) {
             const bool inside = clip_ok && gx >= crect.x && gx < crect.z && gy >= crect.y && gy < crect.w;
             if (inside) {
                 const TileState ct = b.clip_tile_state[ctile_offset + (uint32_t)(gx - crect.x) +
@@ -259,46 +272,86 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
                 need_new = false;
             }
         }
-        if (need_new) {  // propagate.comp:178-183
-            const uint32_t id = atomicAdd(b.frame_alpha_counter, 1u);
-            const uint32_t local = id - first_alpha;
-            if (id < b.mask_capacity && local < b.alpha_capacity) {
-                AlphaTile at;
-                at.tile_index = ti;
-                at.clip_alpha = clip_alpha;
-                b.alpha_tiles[local] = at;
-                alpha = (int)id;
-            } else {
-                atomicOr(&b.counters->overflow, (uint32_t)OVF_ALPHA);
-                need_new = false;
+        // alpha tile allocation (propagate.comp:178-183): one atomic per warp
+        const unsigned need_mask = __ballot_sync(0xffffffffu, need_new);
+        if (need_mask) {
+            uint32_t base = 0;
+            const int leader = __ffs(need_mask) - 1;
+            if ((int)lane == leader) base = atomicAdd(b.frame_alpha_counter, (uint32_t)__popc(need_mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (need_new) {
+                const uint32_t id = base + (uint32_t)__popc(need_mask & ((1u << lane) - 1u));
+                const uint32_t local = id - first_alpha;
+                if (id < b.mask_capacity && local < b.alpha_capacity) {
+                    AlphaTile at;
+                    at.tile_index = ti;
+                    at.clip_alpha = clip_alpha;
+                    at.packed = ((uint32_t)backdrop & 0xffu) | ((info.ctrl & 0x1) ? 0x100u : 0u);
+                    at.fill_count = word & 0x00ffffffu;
+                    *reinterpret_cast<uint4 *>(&b.alpha_tiles[local]) = *reinterpret_cast<const uint4 *>(&at);
+                    alpha = (int)id;
+                } else {
+                    atomicOr(&b.counters->overflow, (uint32_t)OVF_ALPHA);
+                    need_new = false;
+                }
             }
         }
-        const bool in_fb = gx >= 0 && gx < b.fb_tw && gy >= 0 && gy < b.fb_th;
+        const bool in_fb = valid && gx >= 0 && gx < b.fb_tw && gy >= 0 && gy < b.fb_th;
         const uint32_t map = in_fb ? (uint32_t)gy * (uint32_t)b.fb_tw + (uint32_t)gx : 0u;
         const bool listed = (backdrop != 0 || alpha >= 0) && in_fb;
-        TileState st;
-        st.alpha = alpha;
-        st.packed = ((uint32_t)backdrop & 0xffu) | (((uint32_t)delta & 0xffu) << 8) | (((uint32_t)backdrop9 & 0xffu) << 16) |
-                    (listed ? 1u << 24 : 0u) | (need_new ? 1u << 25 : 0u) | (((uint32_t)info.ctrl & 0x3u) << 26);
-        b.tile_state[ti] = st;
+        if (valid) {
+            TileState st;
+            st.alpha = alpha;
+            st.packed = ((uint32_t)backdrop & 0xffu) | (((uint32_t)delta & 0xffu) << 8) |
+                        (((uint32_t)backdrop9 & 0xffu) << 16) | (listed ? 1u << 24 : 0u) | (need_new ? 1u << 25 : 0u) |
+                        (((uint32_t)info.ctrl & 0x3u) << 26);
+            b.tile_state[ti] = st;
+        }
         // z-buffer: propagate.comp:190-206 (even-odd tiles with an even backdrop are invisible, not occluders)
         bool z_write = z_write_path != 0;
         if (backdrop != 0 && even_odd && (abs(backdrop) & 1) == 0) z_write = false;
-        if (in_fb && z_write && backdrop != 0 && alpha < 0) atomicMax(&b.z[map], (int)ti);
-        if (listed) atomicAdd(&b.fb_count[map], 1u);
-        cur += delta;  // tiler.cpp:437
+        if (in_fb && z_write && backdrop != 0 && alpha < 0) atomicMax(&b.fb[map].z, (int)ti);
+        // list membership (propagate.comp:209-212): rank inside the framebuffer tile + a compact record
+        const unsigned listed_mask = __ballot_sync(0xffffffffu, listed);
+        if (listed_mask) {
+            uint32_t base = 0;
+            const int leader = __ffs(listed_mask) - 1;
+            if ((int)lane == leader) base = atomicAdd(&b.counters->n_listed, (uint32_t)__popc(listed_mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (listed) {
+                const uint32_t at = base + (uint32_t)__popc(listed_mask & ((1u << lane) - 1u));
+                const uint32_t rank = atomicAdd(&b.fb[map].count, 1u);
+                if (at < b.prim_capacity) {
+                    *reinterpret_cast<uint4 *>(&b.listed[at]) =
+                        make_uint4(ti, (uint32_t)alpha, ctrl_base | (((uint32_t)backdrop & 0xffu) << 24), map);
+                    b.listed_rank[at] = rank;
+                }
+            }
+        }
     }
 }
 
 cudaError_t launch_propagate(const BatchView &b, cudaStream_t s) {
     if (!b.column_count) return cudaSuccess;
-    k_propagate<false><<<(b.column_count + 127) / 128, 128, 0, s>>>(b);
+    const uint32_t warps_per_block = 4;
+    k_propagate<<<(b.column_count + warps_per_block - 1) / warps_per_block, 128, 0, s>>>(b);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ list scatter
+
+__global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
+    const uint32_t n = min(b.counters->n_listed, b.prim_capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(&b.listed[i]);
+        const uint32_t pos = b.fb[r.w].begin + b.listed_rank[i];
+        if (pos < b.prim_capacity) *reinterpret_cast<uint4 *>(&b.prims[pos]) = make_uint4(r.x, r.y, r.z, 0u);
+    }
 }
 
 cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s) {
     if (!b.column_count) return cudaSuccess;
-    k_propagate<true><<<(b.column_count + 127) / 128, 128, 0, s>>>(b);
+    k_list_scatter<<<sm_count() * 8, 256, 0, s>>>(b);
     return cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ EXPORTS = [
     "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
     "pfcu_get_stage_times", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
 ]
-STAGES = ["init", "dice", "bin_count", "scan_tiles", "bin_scatter", "propagate", "scan_fb", "list_scatter", "fill",
+STAGES = ["init", "dice", "bin", "scan_tiles", "fill_scatter", "propagate", "scan_fb", "list_scatter", "fill",
           "composite"]
 
 LINE_DT = np.dtype([("from_x", "<f4"), ("from_y", "<f4"), ("to_x", "<f4"), ("to_y", "<f4"), ("path_index", "<u4")])

@@ -71,8 +71,8 @@ def test_taps_bit_exact_vs_oracle(renderer, area_lut, name):
                 continue
             bid = int(b["info"][0])
             slot = fr.slots[bid]
-            # dice: same multiset of flattened lines, bit for bit (compare the raw 20-byte records)
-            lo, lc = fr.lines(slot), renderer.lines(bid)
+            # dice: same multiset of flattened + view-box-clipped lines, bit for bit (raw 20-byte records)
+            lo, lc = fr.clipped_lines(slot), renderer.lines(bid)
             assert len(lo) == len(lc), "line count %d != %d" % (len(lc), len(lo))
             ro, rc = raw_sorted(lo), raw_sorted(lc)
             assert np.array_equal(ro, rc), "flattened lines differ"
