@@ -147,6 +147,16 @@ int pfcu_draw_batch(pfcu_ctx *ctx, uint32_t batch_id, int target_page, int color
  * read-backs). stats may be NULL. */
 int pfcu_end_frame(pfcu_ctx *ctx, pfcu_frame_stats *stats);
 
+/* ---- options */
+enum {
+    /* 0 (default): fill writes every mask, tile reads them back, as fill.comp / tile.comp do. 1: the tile kernel
+     * computes the coverage of a draw batch's alpha tiles from their fills itself, so a draw batch's masks never
+     * reach memory (one kernel, SURVEY.md section 8d B_fused; pfcu_read_mask then only sees clip batches).
+     * Clip batches always write their masks. */
+    PFCU_OPT_FUSED_FILL = 1
+};
+int pfcu_set_option(pfcu_ctx *ctx, int option, int value);
+
 /* ---- measurement */
 enum {
     PFCU_STAGE_INIT = 0, /* "bound" */

@@ -101,8 +101,8 @@ struct BatchSlot {
     pfcu_batch_desc desc{};
     PinnedBuf host_meta;  // the four metadata vectors, packed, kept for replay
     size_t off_backdrops = 0, off_meta = 0, off_dice = 0, off_tpi = 0, meta_bytes = 0;
-    DevBuf dev_meta, tile_word, fill_cursor, col_backdrop, tile_state, lines, line_meta, staging, fills, fb, listed,
-        listed_rank, prims, alpha_tiles, scan_desc0, scan_desc1;
+    DevBuf dev_meta, tile_word, fill_cursor, alpha_rank, col_backdrop, tile_state, lines, line_meta, staging, fills, fb,
+        prims, alpha_tiles, scan_desc0, scan_desc1;
     uint32_t line_cap = 0, fill_cap = 0, staging_cap = 0;
     BatchView view{};
     bool prepared = false;
@@ -126,6 +126,10 @@ struct pfcu_ctx {
     // static resources
     DevBuf lut;
     int lut_w = 0, lut_h = 0;
+    cudaArray_t lut_array = nullptr;
+    cudaTextureObject_t lut_tex = 0;
+    int lut_band = 0;
+    int fused = 0;  // PFCU_OPT_FUSED_FILL
     DevBuf dummy_px;
     // target
     DevBuf own_target;
@@ -223,9 +227,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     CUDA_TRY(s.line_meta.ensure((size_t)s.line_cap * sizeof(uint2)));
     CUDA_TRY(s.staging.ensure((size_t)s.staging_cap * sizeof(StagedFill)));
     CUDA_TRY(s.fills.ensure((size_t)s.fill_cap * sizeof(uint2)));
+    CUDA_TRY(s.alpha_rank.ensure(D * 4));
     CUDA_TRY(s.fb.ensure(T * sizeof(FbTile)));
-    CUDA_TRY(s.listed.ensure(D * sizeof(ListedRec)));
-    CUDA_TRY(s.listed_rank.ensure(D * 4));
     CUDA_TRY(s.prims.ensure(D * sizeof(TilePrim)));
     CUDA_TRY(s.alpha_tiles.ensure(D * sizeof(AlphaTile)));
     CUDA_TRY(s.scan_desc0.ensure((D / 2048 + 2) * 8));
@@ -266,9 +269,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.staging_capacity = s.staging_cap;
     v.fills = s.fills.as<uint2>();
     v.fill_capacity = s.fill_cap;
+    v.alpha_rank = s.alpha_rank.as<uint32_t>();
     v.fb = s.fb.as<FbTile>();
-    v.listed = s.listed.as<ListedRec>();
-    v.listed_rank = s.listed_rank.as<uint32_t>();
     v.prims = s.prims.as<TilePrim>();
     v.prim_capacity = d.tile_count;
     v.alpha_tiles = s.alpha_tiles.as<AlphaTile>();
@@ -296,6 +298,11 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     pv.area_lut = c->lut.as<uint8_t>();
     pv.lut_w = c->lut_w;
     pv.lut_h = c->lut_h;
+    pv.lut_tex = c->lut_tex;
+    pv.lut_band = c->lut_band;
+    // Fused mode: a draw batch's coverage is computed inside the composite kernel. Clip batches (never composited)
+    // still need their masks in memory for the batches they clip.
+    const bool run_fill = !c->fused || d.path_source != 0;
 
     {
         int r = prof_mark(c, -1);
@@ -309,8 +316,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     LAUNCH_STAGE(PFCU_STAGE_PROPAGATE, launch_propagate(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_SCAN_FB, launch_scan_fb(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_LIST_SCATTER, launch_list_scatter(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, c->stream));
-    c->launches += 9;
+    if (run_fill) LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, c->stream));
+    c->launches += run_fill ? 9 : 8;
     c->in_flight = true;
     return PFCU_OK;
 }
@@ -346,6 +353,9 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
     pv.area_lut = c->lut.as<uint8_t>();
     pv.lut_w = c->lut_w;
     pv.lut_h = c->lut_h;
+    pv.lut_tex = c->lut_tex;
+    pv.lut_band = c->lut_band;
+    pv.fused = c->fused && s.desc.path_source == 0;
     // masks may have been reallocated since the batch was prepared (growth happens only between attempts)
     s.view.masks = c->masks.as<uint8_t>();
     s.view.mask_capacity = c->mask_cap;
@@ -398,7 +408,7 @@ void pfcu_destroy(pfcu_ctx *c) {
     for (auto &s : c->slots) {
         s.host_meta.release();
         for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
-                          &s.line_meta, &s.staging, &s.fills, &s.fb, &s.listed, &s.listed_rank, &s.prims,
+                          &s.line_meta, &s.staging, &s.fills, &s.fb, &s.alpha_rank, &s.prims,
                           &s.alpha_tiles, &s.scan_desc0, &s.scan_desc1})
             b->release();
     }
@@ -409,6 +419,8 @@ void pfcu_destroy(pfcu_ctx *c) {
         c->stage_scene[i].release();
     }
     c->lut.release();
+    if (c->lut_tex) cudaDestroyTextureObject(c->lut_tex);
+    if (c->lut_array) cudaFreeArray(c->lut_array);
     c->dummy_px.release();
     c->own_target.release();
     c->paints.release();
@@ -445,6 +457,38 @@ int pfcu_set_area_lut(pfcu_ctx *c, const uint8_t *rgba, int width, int height) {
     CUDA_TRY(cudaMemcpy(c->lut.p, rgba, (size_t)width * height * 4, cudaMemcpyHostToDevice));
     c->lut_w = width;
     c->lut_h = height;
+    // The fill stage fetches LUT texels through the texture unit (clamp-to-edge, unorm8 -> float) and applies the
+    // bilinear weights of fill.comp:70's sampler (core/renderer.cpp:117-165) in fp32.
+    if (c->lut_tex) cudaDestroyTextureObject(c->lut_tex);
+    if (c->lut_array) cudaFreeArray(c->lut_array);
+    c->lut_tex = 0;
+    c->lut_array = nullptr;
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    CUDA_TRY(cudaMallocArray(&c->lut_array, &fmt, (size_t)width, (size_t)height));
+    CUDA_TRY(cudaMemcpy2DToArray(c->lut_array, 0, 0, rgba, (size_t)width * 4, (size_t)width * 4, (size_t)height,
+                                 cudaMemcpyHostToDevice));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = c->lut_array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModePoint;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 0;
+    CUDA_TRY(cudaCreateTextureObject(&c->lut_tex, &rd, &td, nullptr));
+    // Saturation band of the LUT (add_group in pfcu_raster.cu): left of 120 - row / 2 every channel must be 255, right of
+    // 184 + row / 2 every channel must be 0. True for the reference's area_lut.png; checked, not assumed.
+    c->lut_band = width == 256 && height == 256;
+    for (int y = 0; y < height && c->lut_band; y++)
+        for (int x = 0; x < width; x++) {
+            const uint8_t *t = rgba + ((size_t)y * width + x) * 4;
+            const bool full = t[0] == 255 && t[1] == 255 && t[2] == 255 && t[3] == 255;
+            const bool zero = !t[0] && !t[1] && !t[2] && !t[3];
+            if (((float)x < 120.0f - 0.5f * (float)y && !full) || ((float)x > 184.0f + 0.5f * (float)y && !zero)) {
+                c->lut_band = 0;
+                break;
+            }
+        }
     return PFCU_OK;
 }
 
@@ -759,6 +803,18 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
     return PFCU_OK;
 }
 
+int pfcu_set_option(pfcu_ctx *c, int option, int value) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    if (c->frame_open) return fail(PFCU_ERR_STATE, "options cannot change inside a frame");
+    switch (option) {
+        case PFCU_OPT_FUSED_FILL:
+            c->fused = value != 0;
+            return PFCU_OK;
+        default:
+            return fail(PFCU_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
 int pfcu_set_profiling(pfcu_ctx *c, int enabled) {
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     c->profiling = enabled != 0;
@@ -965,20 +1021,14 @@ int64_t pfcu_read_tiles(pfcu_ctx *c, uint32_t batch_id, pfcu_tile *out) {
     TAP_TRY(cudaMemcpy(&bc, s.view.counters, sizeof(bc), cudaMemcpyDeviceToHost));
     std::vector<uint32_t> word(D);
     std::vector<TileState> st(D);
-    std::vector<AlphaTile> at(D);
     if (D) {
         TAP_TRY(cudaMemcpy(word.data(), s.view.tile_word, (size_t)D * 4, cudaMemcpyDeviceToHost));
         TAP_TRY(cudaMemcpy(st.data(), s.view.tile_state, (size_t)D * sizeof(TileState), cudaMemcpyDeviceToHost));
-        TAP_TRY(cudaMemcpy(at.data(), s.view.alpha_tiles, (size_t)D * sizeof(AlphaTile), cudaMemcpyDeviceToHost));
     }
     for (uint32_t t = 0; t < D; t++) {
         pfcu_tile q{};
         q.alpha_tile_id = st[t].alpha;
-        q.clip_alpha_tile_id = -1;
-        if ((st[t].packed & (1u << 25)) && st[t].alpha >= 0) {
-            const uint32_t local = (uint32_t)st[t].alpha - bc.first_alpha;
-            if (local < D && at[local].tile_index == t) q.clip_alpha_tile_id = at[local].clip_alpha;
-        }
+        q.clip_alpha_tile_id = (st[t].packed & (1u << 25)) ? st[t].clip_alpha : -1;
         q.fill_count = (int32_t)(word[t] & 0x00ffffffu);
         q.backdrop = (int8_t)(st[t].packed & 0xff);
         q.backdrop_delta = (int8_t)((st[t].packed >> 8) & 0xff);
@@ -1036,7 +1086,11 @@ int pfcu_read_mask(pfcu_ctx *c, uint32_t alpha_tile_id, uint8_t out[256]) {
     if (alpha_tile_id >= c->mask_cap) return fail(PFCU_ERR_INVALID, "alpha tile id out of range");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    CUDA_TRY(cudaMemcpy(out, c->masks.as<uint8_t>() + (size_t)alpha_tile_id * 256, 256, cudaMemcpyDeviceToHost));
+    uint8_t raw[256];
+    CUDA_TRY(cudaMemcpy(raw, c->masks.as<uint8_t>() + (size_t)alpha_tile_id * 256, 256, cudaMemcpyDeviceToHost));
+    // device layout is lane-major (pfcu_device.h): byte lane * 8 + q = pixel (lane & 15, (lane >> 4) * 4 + q + (q & 4))
+    for (int lane = 0; lane < 32; lane++)
+        for (int q = 0; q < 8; q++) out[((lane >> 4) * 4 + q + (q & 4)) * 16 + (lane & 15)] = raw[lane * 8 + q];
     return PFCU_OK;
 }
 

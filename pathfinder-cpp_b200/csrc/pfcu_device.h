@@ -24,8 +24,8 @@ struct BatchCounters {
     uint32_t n_lines;         // clipped lines emitted by dice (may exceed capacity: overflow)
     uint32_t n_fills;         // total fills (from the scan)
     uint32_t n_staging;       // staging slots reserved by dice (upper bound of fills per line, summed)
-    uint32_t first_alpha;     // frame-global id of this batch's first alpha tile
-    uint32_t n_listed;        // tiles stitched into framebuffer-tile lists (before z-cull)
+    uint32_t first_alpha;     // frame-global id of this batch's first mask slot
+    uint32_t n_alpha;         // mask slots of this batch = dense tiles with at least one fill (from the scan)
     uint32_t overflow;        // OverflowBits
     uint32_t scan_ticket[2];  // dynamic tile ids for the two look-back scans
     uint32_t n_list_entries;  // total list entries (from the scan over framebuffer tiles)
@@ -35,13 +35,17 @@ static_assert(sizeof(BatchCounters) == 64, "BatchCounters");
 
 enum OverflowBits { OVF_LINES = 1, OVF_FILLS = 2, OVF_ALPHA = 4, OVF_LIST = 8, OVF_STAGING = 16, OVF_DDA = 32 };
 
-// Packed per-dense-tile state written by propagate.
-//   alpha : alpha tile id (int32, -1 none)
-//   packed: bits 0-7 backdrop, 8-15 backdrop delta, 16-23 hybrid-equivalent backdrop, 24 listed, 25 owns a mask,
-//           26-27 mask ctrl bits of the path (winding / even-odd)
+// Per-dense-tile state written by propagate (one 16-byte store).
+//   alpha     : mask slot (frame-global; the clip's slot for solid-draw x alpha-clip) or -1
+//   packed    : bits 0-7 backdrop, 8-15 backdrop delta, 16-23 hybrid-equivalent backdrop, 24 listed, 25 owns a mask,
+//               26-27 mask ctrl bits of the path (winding / even-odd)
+//   path      : batch-local path index (what bound.comp:41-53 finds by binary search)
+//   clip_alpha: mask slot min()-ed into this tile's coverage, or -1
 struct TileState {
     int32_t alpha;
     uint32_t packed;
+    uint32_t path;
+    int32_t clip_alpha;
 };
 
 // One fill waiting for its final position (bin -> scan -> scatter). tile == ~0u marks an unused slot.
@@ -49,28 +53,26 @@ struct StagedFill {
     uint32_t tile, from, to, pad;
 };
 
-// One entry of a framebuffer tile's list (what tile.comp reads per layer, tile.comp:765-768).
+// One entry of a framebuffer tile's list: everything tile.comp reads per layer (tile.comp:765-768) plus, for the
+// fused fill+tile kernel, where the tile's fills are (two 16-byte loads).
 struct TilePrim {
-    uint32_t key;        // dense tile index: sort key == paint order
-    int32_t alpha;       // mask slot or -1
-    uint32_t ctrl_word;  // paint | ctrl << 16 | backdrop << 24
+    uint32_t key;         // dense tile index: sort key == paint order
+    int32_t alpha;        // mask slot or -1
+    uint32_t ctrl_word;   // paint | ctrl << 16 | backdrop << 24
+    uint32_t fill_begin;  // CSR range of the tile's fills (valid when PRIM_OWNS_MASK)
+    uint32_t fill_count;
+    int32_t clip_alpha;   // mask slot min()-ed into the coverage, or -1
+    uint32_t flags;       // PrimFlags
     uint32_t pad;
 };
-
-// A listed tile on its way into a framebuffer tile's list (propagate -> scan -> list scatter).
-struct ListedRec {
-    uint32_t key;
-    int32_t alpha;
-    uint32_t ctrl_word;
-    uint32_t map;  // framebuffer tile index
-};
+enum PrimFlags { PRIM_OWNS_MASK = 1 };
 
 // Per framebuffer tile: list range + z (one 16-byte load in the composite kernel).
 struct FbTile {
-    uint32_t begin;  // from the scan
-    uint32_t count;  // entries before z-cull (atomic rank counter in propagate)
-    int32_t z;       // largest dense tile index of an occluding solid tile (propagate.comp:204-206)
-    uint32_t pad;
+    uint32_t begin;   // from the scan
+    uint32_t count;   // entries before z-cull (counted by propagate)
+    int32_t z;        // largest dense tile index of an occluding solid tile (propagate.comp:204-206)
+    uint32_t cursor;  // entries placed so far (list scatter)
 };
 
 struct AlphaTile {
@@ -119,9 +121,8 @@ struct BatchView {
     uint32_t staging_capacity;
     uint2 *fills;           // [fill_capacity] x = from_x | from_y << 16, y = to_x | to_y << 16
     uint32_t fill_capacity;
+    uint32_t *alpha_rank;   // [tile_count] exclusive count of tiles with fills (mask slot = first_alpha + rank)
     FbTile *fb;             // [fb tiles]
-    ListedRec *listed;      // [tile_count]
-    uint32_t *listed_rank;  // [tile_count]
     TilePrim *prims;        // [prim_capacity]
     uint32_t prim_capacity;
     AlphaTile *alpha_tiles; // [alpha_capacity] batch-local
@@ -133,7 +134,9 @@ struct BatchView {
     uint32_t clip_path_count;
     // frame-global
     uint32_t *frame_alpha_counter;  // next free mask slot
-    uint8_t *masks;                 // 256 B per slot
+    uint8_t *masks;                 // 256 B per slot, lane-major: byte lane * 8 + q = pixel (column lane & 15,
+                                    // row (lane >> 4) * 4 + q + (q & 4)), so a warp stores / loads a mask with one
+                                    // 8-byte access per lane
     uint32_t mask_capacity;         // slots
 };
 
@@ -152,6 +155,9 @@ struct PaintView {
     uint32_t sampling_flags;
     const uint8_t *area_lut;   // 256 x 256 RGBA8
     int lut_w, lut_h;
+    cudaTextureObject_t lut_tex;  // the same LUT behind the texture unit: texel fetch, clamp-to-edge, unorm8 -> float
+    int lut_band;              // the LUT saturates outside |x - 152| <= 32 + y / 2 (checked at upload)
+    int fused;                 // composite computes the coverage of draw tiles itself (no mask round trip)
 };
 
 // ---- launchers (each enqueues exactly one kernel on `s` and returns the CUDA status) --------------------------

@@ -11,11 +11,20 @@
 //           core/d3d9/tiler.cpp:155-279 (tile walk) and core/d3d9/object_builder.cpp:19-114
 //           (fill conversion: clamp [0,4095], round-to-nearest-even; backdrop bookkeeping).
 //
-// B200 mapping. No linked lists, no overflow-and-retry read-backs, and the tile walk runs ONCE: dice reserves, per
-// clipped line, an upper bound of staging slots (2 fills per visited tile) with one atomic per warp; bin writes its
-// fills there and counts them per tile with fire-and-forget reductions; a device-wide scan then gives every tile a
-// contiguous range and a fully parallel scatter (pfcu_tiles.cu) moves the staged fills into it (CSR), so the fill
-// kernel reads each tile's fills with coalesced loads.
+// B200 mapping. No linked lists, no overflow-and-retry read-backs, and the tile walk runs ONCE.
+//   dice: the reference flattens a curve by recursion (one thread per segment would serialise up to ~100 leaves).
+//         Here a CTA owns a chunk of segments and walks all their subdivision trees breadth-first through a
+//         shared-memory node queue: every thread tests / splits one node per level, so a level of any curve is
+//         processed in parallel; each node's control points come from the same sequence of de Casteljau halvings as
+//         the recursion, so the leaves are bit-identical. Lines are collected in shared memory and flushed with one
+//         global atomic per level and CTA.
+//   bin : one thread per line for short walks; a line that crosses many tiles is walked by the whole warp: all lanes
+//         replay the cheap part of the DDA (the t_max chain, which must stay a chain of float additions to be
+//         bit-exact) and each lane does the expensive part (fill conversion, atomics, stores) of every 32nd step.
+//         Every line owns an upper bound of staging slots (2 fills per visited tile, one warp-aggregated atomic);
+//         fills are counted per tile with fire-and-forget reductions; a device-wide scan then gives every tile a
+//         contiguous range and a fully parallel scatter (pfcu_tiles.cu) moves the staged fills into it (CSR), so the
+//         fill stage reads each tile's fills with coalesced loads.
 #include "pfcu_device.h"
 
 namespace pfcu {
@@ -60,16 +69,6 @@ __device__ __forceinline__ bool clip_to_view_box(float &l0, float &l1, float &l2
     return false;
 }
 
-// Upper bound of the fills one clipped line can emit: the tile walk (tiler.cpp:191-278) visits
-// |dx| + |dy| + 1 tiles and adds at most two fills per tile.
-__device__ __forceinline__ uint32_t fill_bound(float l0, float l1, float l2, float l3) {
-    const long long tx0 = (int)floorf(l0 * 0.0625f), ty0 = (int)floorf(l1 * 0.0625f);
-    const long long tx1 = (int)floorf(l2 * 0.0625f), ty1 = (int)floorf(l3 * 0.0625f);
-    long long d = llabs(tx1 - tx0) + llabs(ty1 - ty0) + 1;
-    if (d > MAX_DDA_STEPS) d = MAX_DDA_STEPS;
-    return (uint32_t)(2 * d);
-}
-
 // ------------------------------------------------------------------------------------------------ dice
 
 struct Cubic {
@@ -102,45 +101,6 @@ __device__ __forceinline__ float2 lerp_half(float2 a, float2 b) {  // a + 0.5 * 
     return make_float2(a.x + 0.5f * (b.x - a.x), a.y + 0.5f * (b.y - a.y));
 }
 
-// Walks the subdivision tree of one curve depth-first with an explicit stack of right siblings
-// (tiler.cpp:284-315 recursion). `emit(from, to)` is called once per leaf, left to right.
-template <bool CUBIC, typename Emit>
-__device__ __forceinline__ void flatten(Cubic cur, Emit &&emit) {
-    Cubic stack[MAX_FLATTEN_DEPTH];
-    unsigned char stack_depth[MAX_FLATTEN_DEPTH];
-    int sp = 0, depth = 0;
-    while (true) {
-        bool flat = depth >= MAX_FLATTEN_DEPTH || (CUBIC ? is_flat_cubic(cur) : is_flat_quadratic(cur));
-        if (flat) {
-            emit(cur.p0, cur.p3);
-            if (sp == 0) break;
-            sp--;
-            cur = stack[sp];
-            depth = stack_depth[sp];
-        } else {
-            Cubic left, right;
-            if (CUBIC) {  // Segment::split_cubic(0.5), segment.cpp:43-108
-                float2 p01 = lerp_half(cur.p0, cur.p1), p12 = lerp_half(cur.p1, cur.p2), p23 = lerp_half(cur.p2, cur.p3);
-                float2 p012 = lerp_half(p01, p12), p123 = lerp_half(p12, p23);
-                float2 p0123 = lerp_half(p012, p123);
-                left = {cur.p0, p01, p012, p0123};
-                right = {p0123, p123, p23, cur.p3};
-            } else {  // Segment::split_quadratic(0.5), segment.cpp:110-135: a = p0 + (p1 - p0) * t ...
-                float2 a = make_float2(cur.p0.x + (cur.p1.x - cur.p0.x) * 0.5f, cur.p0.y + (cur.p1.y - cur.p0.y) * 0.5f);
-                float2 b = make_float2(cur.p1.x + (cur.p3.x - cur.p1.x) * 0.5f, cur.p1.y + (cur.p3.y - cur.p1.y) * 0.5f);
-                float2 c = make_float2(a.x + (b.x - a.x) * 0.5f, a.y + (b.y - a.y) * 0.5f);
-                left = {cur.p0, a, a, c};
-                right = {c, b, b, cur.p3};
-            }
-            depth++;
-            stack[sp] = right;
-            stack_depth[sp] = (unsigned char)depth;
-            sp++;
-            cur = left;
-        }
-    }
-}
-
 __device__ __forceinline__ bool finite2(float2 p) { return isfinite(p.x) && isfinite(p.y); }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, unsigned lane) {
@@ -152,112 +112,221 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, unsigned lane) {
     return v;
 }
 
-__global__ void __launch_bounds__(128) k_dice(BatchView b) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    const unsigned lane = threadIdx.x & 31;
-    const float left = b.view_box[0], right = b.view_box[2], bottom = b.view_box[3];
-    uint32_t path = 0, npt = 0;
-    Cubic c;
-    bool active = false;
-    if (s < b.segment_count) {
-        // Owner path: last p with first_batch_segment_index <= s (dice.comp:134-149 binary search).
-        uint32_t lo = 0, hi = b.path_count;
-        while (lo + 1 < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(&b.dice[mid].first_batch_segment_index) <= s) lo = mid; else hi = mid;
+constexpr int DICE_THREADS = 256;
+constexpr int DICE_CHUNK = 32;    // segments a CTA takes at a time
+constexpr int DICE_QUEUE = 1024;  // nodes per level held in shared memory; wider levels fall back to a private stack
+constexpr int DICE_OUT = 1024;    // lines collected between flushes
+
+struct DiceShared {
+    float4 qa[2][DICE_QUEUE];    // p0, p1
+    float4 qb[2][DICE_QUEUE];    // p2, p3
+    uint32_t qm[2][DICE_QUEUE];  // path | depth << 24 | cubic << 31
+    float4 out_line[DICE_OUT];
+    uint32_t out_path[DICE_OUT];
+    uint32_t q_count[2];
+    uint32_t out_count, out_base;
+};
+
+// One flattened line: view-box clip, then into the CTA's output buffer (or straight to global memory when full).
+__device__ __forceinline__ void dice_emit(const BatchView &b, DiceShared &sh, float2 from, float2 to, uint32_t path) {
+    float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
+    if (!clip_to_view_box(l0, l1, l2, l3, b.view_box[0], b.view_box[2], b.view_box[3])) return;
+    const uint32_t at = atomicAdd(&sh.out_count, 1u);
+    if (at < DICE_OUT) {
+        sh.out_line[at] = make_float4(l0, l1, l2, l3);
+        sh.out_path[at] = path;
+    } else {
+        const uint32_t g = atomicAdd(&b.counters->n_lines, 1u);
+        if (g < b.line_capacity) {
+            b.lines[g] = make_float4(l0, l1, l2, l3);
+            b.line_meta[g] = make_uint2(path, 0u);
+        } else {
+            atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
         }
-        path = lo;
-        const uint32_t g = __ldg(&b.dice[path].first_global_segment_index) +
-                           (s - __ldg(&b.dice[path].first_batch_segment_index));
-        if (g < b.n_segments_total) {
-            const uint2 ix = __ldg(&b.indices[g]);
-            const uint32_t fp = ix.x, flag = ix.y;
-            const uint32_t next_fp = g + 1 < b.n_segments_total ? __ldg(&b.indices[g + 1]).x : b.n_points;
-            npt = (flag & CURVE_IS_CUBIC) ? 4u : (flag & CURVE_IS_QUADRATIC) ? 3u : 2u;
-            if (fp + npt <= b.n_points) {
-                float2 q[4];
+    }
+}
+
+__device__ __forceinline__ void split_node(const Cubic &cur, bool cubic, Cubic &left, Cubic &right) {
+    if (cubic) {  // Segment::split_cubic(0.5), segment.cpp:43-108
+        const float2 p01 = lerp_half(cur.p0, cur.p1), p12 = lerp_half(cur.p1, cur.p2), p23 = lerp_half(cur.p2, cur.p3);
+        const float2 p012 = lerp_half(p01, p12), p123 = lerp_half(p12, p23);
+        const float2 p0123 = lerp_half(p012, p123);
+        left = {cur.p0, p01, p012, p0123};
+        right = {p0123, p123, p23, cur.p3};
+    } else {  // Segment::split_quadratic(0.5), segment.cpp:110-135: a = p0 + (p1 - p0) * t ...
+        const float2 a = make_float2(cur.p0.x + (cur.p1.x - cur.p0.x) * 0.5f, cur.p0.y + (cur.p1.y - cur.p0.y) * 0.5f);
+        const float2 bq = make_float2(cur.p1.x + (cur.p3.x - cur.p1.x) * 0.5f, cur.p1.y + (cur.p3.y - cur.p1.y) * 0.5f);
+        const float2 c = make_float2(a.x + (bq.x - a.x) * 0.5f, a.y + (bq.y - a.y) * 0.5f);
+        left = {cur.p0, a, a, c};
+        right = {c, bq, bq, cur.p3};
+    }
+}
+
+__device__ __forceinline__ bool node_is_flat(const Cubic &c, bool cubic, int depth) {
+    return depth >= MAX_FLATTEN_DEPTH || (cubic ? is_flat_cubic(c) : is_flat_quadratic(c));
+}
+
+// Depth-first walk of one subtree with a private stack: only used when a level does not fit the shared queue.
+__device__ __noinline__ void dice_subtree_serial(const BatchView &b, DiceShared &sh, Cubic cur, bool cubic, int depth,
+                                                 uint32_t path) {
+    Cubic stack[MAX_FLATTEN_DEPTH];
+    unsigned char stack_depth[MAX_FLATTEN_DEPTH];
+    int sp = 0;
+    while (true) {
+        if (node_is_flat(cur, cubic, depth)) {
+            dice_emit(b, sh, cur.p0, cur.p3, path);
+            if (sp == 0) break;
+            sp--;
+            cur = stack[sp];
+            depth = stack_depth[sp];
+        } else {
+            Cubic left, right;
+            split_node(cur, cubic, left, right);
+            depth++;
+            stack[sp] = right;
+            stack_depth[sp] = (unsigned char)depth;
+            sp++;
+            cur = left;
+        }
+    }
+}
+
+__device__ __forceinline__ void dice_push(const BatchView &b, DiceShared &sh, int buf, const Cubic &c, bool cubic,
+                                          int depth, uint32_t path) {
+    const uint32_t at = atomicAdd(&sh.q_count[buf], 1u);
+    if (at < DICE_QUEUE) {
+        sh.qa[buf][at] = make_float4(c.p0.x, c.p0.y, c.p1.x, c.p1.y);
+        sh.qb[buf][at] = make_float4(c.p2.x, c.p2.y, c.p3.x, c.p3.y);
+        sh.qm[buf][at] = path | ((uint32_t)depth << 24) | (cubic ? 0x80000000u : 0u);
+    } else {
+        dice_subtree_serial(b, sh, c, cubic, depth, path);
+    }
+}
+
+__global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b) {
+    extern __shared__ __align__(16) unsigned char dice_smem[];
+    DiceShared &sh = *reinterpret_cast<DiceShared *>(dice_smem);
+    const uint32_t n_chunks = (b.segment_count + DICE_CHUNK - 1) / DICE_CHUNK;
+    if (threadIdx.x == 0) {
+        sh.q_count[0] = sh.q_count[1] = 0;
+        sh.out_count = 0;
+    }
+    __syncthreads();
+    for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        // ---- roots: one thread per segment of the chunk
+        if (threadIdx.x < DICE_CHUNK) {
+            const uint32_t s = chunk * DICE_CHUNK + threadIdx.x;
+            if (s < b.segment_count) {
+                // Owner path: last p with first_batch_segment_index <= s (dice.comp:134-149 binary search).
+                uint32_t lo = 0, hi = b.path_count;
+                while (lo + 1 < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(&b.dice[mid].first_batch_segment_index) <= s) lo = mid; else hi = mid;
+                }
+                const uint32_t path = lo;
+                const uint32_t g = __ldg(&b.dice[path].first_global_segment_index) +
+                                   (s - __ldg(&b.dice[path].first_batch_segment_index));
+                if (g < b.n_segments_total) {
+                    const uint2 ix = __ldg(&b.indices[g]);
+                    const uint32_t fp = ix.x, flag = ix.y;
+                    const uint32_t next_fp = g + 1 < b.n_segments_total ? __ldg(&b.indices[g + 1]).x : b.n_points;
+                    const uint32_t npt = (flag & CURVE_IS_CUBIC) ? 4u : (flag & CURVE_IS_QUADRATIC) ? 3u : 2u;
+                    if (fp + npt <= b.n_points) {
+                        float2 q[4];
+                        bool ok = true;
 #pragma unroll
-                for (uint32_t k = 0; k < 4; k++) {
-                    if (k < npt) {
-                        float2 p = __ldg(&b.points[fp + k]);
-                        if (!b.identity_transform) {  // Transform2::operator*(Vec2F), common/math/transform2.h:89-91
-                            float tx = b.transform[0] * p.x + b.transform[2] * p.y + b.transform[4];
-                            float ty = b.transform[1] * p.x + b.transform[3] * p.y + b.transform[5];
-                            p = make_float2(tx, ty);
+                        for (uint32_t k = 0; k < 4; k++) {
+                            q[k] = make_float2(0.f, 0.f);
+                            if (k < npt) {
+                                float2 p = __ldg(&b.points[fp + k]);
+                                if (!b.identity_transform) {  // Transform2::operator*(Vec2F), common/math/transform2.h:89-91
+                                    const float tx = b.transform[0] * p.x + b.transform[2] * p.y + b.transform[4];
+                                    const float ty = b.transform[1] * p.x + b.transform[3] * p.y + b.transform[5];
+                                    p = make_float2(tx, ty);
+                                }
+                                q[k] = p;
+                                ok = ok && finite2(p);  // line_segment.cpp:97-104
+                            }
                         }
-                        q[k] = p;
-                    } else {
-                        q[k] = make_float2(0.f, 0.f);
+                        // SegmentsD3D11::add_path appends points[0] after each contour (gpu_data.cpp:109): a line whose
+                        // successor starts two points later is the closing line, which the hybrid tiler only emits when
+                        // the contour is not already closed (contour.cpp:157-166).
+                        if (npt == 2 && next_fp == fp + 2) {
+                            const float dx = q[1].x - q[0].x, dy = q[1].y - q[0].y;
+                            if (sqrtf(dx * dx + dy * dy) <= FLOAT_EPSILON) ok = false;
+                        }
+                        if (ok) {
+                            if (npt == 2) {
+                                dice_emit(b, sh, q[0], q[1], path);
+                            } else {
+                                const Cubic c = npt == 3 ? Cubic{q[0], q[1], q[1], q[2]} : Cubic{q[0], q[1], q[2], q[3]};
+                                dice_push(b, sh, 0, c, npt == 4, 0, path);
+                            }
+                        }
                     }
                 }
-                active = true;
-                for (uint32_t k = 0; k < npt; k++) active = active && finite2(q[k]);  // line_segment.cpp:97-104
-                // SegmentsD3D11::add_path appends points[0] after each contour (gpu_data.cpp:109): a line whose
-                // successor starts two points later is the closing line, which the hybrid tiler only emits when the
-                // contour is not already closed (contour.cpp:157-166).
-                if (npt == 2 && next_fp == fp + 2) {
-                    float dx = q[1].x - q[0].x, dy = q[1].y - q[0].y;
-                    if (sqrtf(dx * dx + dy * dy) <= FLOAT_EPSILON) active = false;
-                }
-                if (npt == 2) c = {q[0], q[1], q[1], q[1]};
-                else if (npt == 3) c = {q[0], q[1], q[1], q[2]};
-                else c = {q[0], q[1], q[2], q[3]};
             }
         }
-    }
-
-    // Pass 1: count this segment's surviving lines and the staging slots they may need.
-    uint32_t n = 0, slots = 0;
-    auto count = [&](float2 from, float2 to) {
-        float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
-        if (clip_to_view_box(l0, l1, l2, l3, left, right, bottom)) {
-            n++;
-            slots += fill_bound(l0, l1, l2, l3);
+        __syncthreads();
+        // ---- breadth-first over the subdivision trees (tiler.cpp:284-315): one node per thread per level
+        int cur = 0;
+        while (true) {
+            const uint32_t count = min(sh.q_count[cur], (uint32_t)DICE_QUEUE);
+            for (uint32_t i = threadIdx.x; i < count; i += DICE_THREADS) {
+                const float4 a = sh.qa[cur][i], bq = sh.qb[cur][i];
+                const uint32_t m = sh.qm[cur][i];
+                const Cubic c = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(bq.x, bq.y), make_float2(bq.z, bq.w)};
+                const bool cubic = (m & 0x80000000u) != 0;
+                const int depth = (int)((m >> 24) & 0x7fu);
+                const uint32_t path = m & 0x00ffffffu;
+                if (node_is_flat(c, cubic, depth)) {
+                    dice_emit(b, sh, c.p0, c.p3, path);
+                } else {
+                    Cubic left, right;
+                    split_node(c, cubic, left, right);
+                    dice_push(b, sh, cur ^ 1, left, cubic, depth + 1, path);
+                    dice_push(b, sh, cur ^ 1, right, cubic, depth + 1, path);
+                }
+            }
+            __syncthreads();
+            // ---- flush the lines of this level: one global atomic per CTA
+            const uint32_t n_out = min(sh.out_count, (uint32_t)DICE_OUT);
+            if (threadIdx.x == 0) {
+                sh.out_base = n_out ? atomicAdd(&b.counters->n_lines, n_out) : 0u;
+                sh.q_count[cur] = 0;
+            }
+            __syncthreads();
+            const uint32_t base = sh.out_base;
+            if (base + n_out > b.line_capacity) {
+                if (threadIdx.x == 0 && n_out) atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
+            } else {
+                for (uint32_t i = threadIdx.x; i < n_out; i += DICE_THREADS) {
+                    b.lines[base + i] = sh.out_line[i];
+                    b.line_meta[base + i] = make_uint2(sh.out_path[i], 0u);
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) sh.out_count = 0;
+            const bool more = sh.q_count[cur ^ 1] != 0;
+            __syncthreads();
+            cur ^= 1;
+            if (!more) break;
         }
-    };
-    if (active) {
-        if (npt == 2) count(c.p0, c.p3);
-        else if (npt == 3) flatten<false>(c, count);
-        else flatten<true>(c, count);
+        __syncthreads();
     }
-    // Warp-aggregated reservation: one atomic per warp and per counter.
-    const uint32_t incl_n = warp_incl_scan(n, lane), incl_s = warp_incl_scan(slots, lane);
-    const uint32_t total_n = __shfl_sync(0xffffffffu, incl_n, 31), total_s = __shfl_sync(0xffffffffu, incl_s, 31);
-    uint32_t base_n = 0, base_s = 0;
-    if (lane == 31 && total_n) {
-        base_n = atomicAdd(&b.counters->n_lines, total_n);
-        base_s = atomicAdd(&b.counters->n_staging, total_s);
-    }
-    base_n = __shfl_sync(0xffffffffu, base_n, 31);
-    base_s = __shfl_sync(0xffffffffu, base_s, 31);
-    if (!n) return;
-    uint32_t at = base_n + incl_n - n, slot = base_s + incl_s - slots;
-    if (at + n > b.line_capacity) {
-        atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
-        return;
-    }
-    if (slot + slots > b.staging_capacity) {
-        atomicOr(&b.counters->overflow, (uint32_t)OVF_STAGING);
-        return;
-    }
-    // Pass 2: emit the clipped lines.
-    auto emit = [&](float2 from, float2 to) {
-        float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
-        if (clip_to_view_box(l0, l1, l2, l3, left, right, bottom)) {
-            b.lines[at] = make_float4(l0, l1, l2, l3);
-            b.line_meta[at] = make_uint2(path, slot);
-            at++;
-            slot += fill_bound(l0, l1, l2, l3);
-        }
-    };
-    if (npt == 2) emit(c.p0, c.p3);
-    else if (npt == 3) flatten<false>(c, emit);
-    else flatten<true>(c, emit);
 }
 
 cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
     if (!b.segment_count) return cudaSuccess;
-    k_dice<<<(b.segment_count + 127) / 128, 128, 0, s>>>(b);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_dice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiceShared));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const uint32_t n_chunks = (b.segment_count + DICE_CHUNK - 1) / DICE_CHUNK;
+    const uint32_t grid = min(n_chunks, (uint32_t)sm_count() * 2u);
+    k_dice<<<grid, DICE_THREADS, sizeof(DiceShared), s>>>(b);
     return cudaGetLastError();
 }
 
@@ -301,64 +370,182 @@ __device__ __forceinline__ void adjust_backdrop(const BatchView &b, const PathTi
     atomicAdd(&b.tile_word[pt.tile_offset + (uint32_t)ox + (uint32_t)w * (uint32_t)oy], (uint32_t)delta << 24);
 }
 
-__global__ void __launch_bounds__(128) k_bin(BatchView b) {
-    const uint32_t n_lines = min(b.counters->n_lines, b.line_capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_lines; i += gridDim.x * blockDim.x) {
-        const float4 ln = b.lines[i];
-        const uint2 lm = b.line_meta[i];
-        const uint32_t path = lm.x;
-        const float l0 = ln.x, l1 = ln.y, l2 = ln.z, l3 = ln.w;
-        uint32_t slot = lm.y;
-        const uint32_t slot_end = slot + fill_bound(l0, l1, l2, l3);
-        if (slot_end > b.staging_capacity) continue;  // dice flagged the overflow; the frame will be replayed
-        PathTiles pt;
-        {
-            const int4 r = __ldg(reinterpret_cast<const int4 *>(&b.meta[path].tile_rect[0]));
-            pt.min_x = r.x; pt.min_y = r.y; pt.max_x = r.z; pt.max_y = r.w;
-            pt.tile_offset = __ldg(&b.meta[path].tile_offset);
-            pt.backdrop_offset = __ldg(&b.meta[path].backdrop_offset);
-        }
-        // process_line_segment, tiler.cpp:155-278
+__device__ __forceinline__ PathTiles load_path_tiles(const BatchView &b, uint32_t path) {
+    PathTiles pt;
+    const int4 r = __ldg(reinterpret_cast<const int4 *>(&b.meta[path].tile_rect[0]));
+    pt.min_x = r.x; pt.min_y = r.y; pt.max_x = r.z; pt.max_y = r.w;
+    pt.tile_offset = __ldg(&b.meta[path].tile_offset);
+    pt.backdrop_offset = __ldg(&b.meta[path].backdrop_offset);
+    return pt;
+}
+
+// The set-up of the tile walk (process_line_segment, tiler.cpp:155-190).
+struct Walk {
+    float l0, l1, vx, vy;
+    float t_max_x, t_max_y, t_delta_x, t_delta_y;
+    int tcx, tcy, to_tx, to_ty, step_x, step_y;
+    __device__ __forceinline__ void init(float a0, float a1, float a2, float a3) {
         const float ts = 16.0f;
-        int tcx = (int)floorf(l0 * 0.0625f), tcy = (int)floorf(l1 * 0.0625f);
-        const int to_tx = (int)floorf(l2 * 0.0625f), to_ty = (int)floorf(l3 * 0.0625f);
-        const float vx = l2 - l0, vy = l3 - l1;
-        const int step_x = vx < 0 ? -1 : 1, step_y = vy < 0 ? -1 : 1;
+        l0 = a0; l1 = a1;
+        tcx = (int)floorf(a0 * 0.0625f); tcy = (int)floorf(a1 * 0.0625f);
+        to_tx = (int)floorf(a2 * 0.0625f); to_ty = (int)floorf(a3 * 0.0625f);
+        vx = a2 - a0; vy = a3 - a1;
+        step_x = vx < 0 ? -1 : 1; step_y = vy < 0 ? -1 : 1;
         const float fcx = ((float)tcx + (vx >= 0 ? 1.0f : 0.0f)) * ts;
         const float fcy = ((float)tcy + (vy >= 0 ? 1.0f : 0.0f)) * ts;
-        float t_max_x = (fcx - l0) / vx, t_max_y = (fcy - l1) / vy;
-        const float t_delta_x = fabsf(ts / vx), t_delta_y = fabsf(ts / vy);
-        float cur_x = l0, cur_y = l1;
-        int last_dir = 0;  // 0 none, 1 X, 2 Y
-        for (int iter = 0; iter < MAX_DDA_STEPS; iter++) {
-            int next_dir;
-            if (t_max_x < t_max_y) next_dir = 1;
-            else if (t_max_x > t_max_y) next_dir = 2;
-            else next_dir = step_x > 0 ? 1 : 2;
-            float next_t = next_dir == 1 ? t_max_x : t_max_y;
-            next_t = next_t < 1.0f ? next_t : 1.0f;
-            if (tcx == to_tx && tcy == to_ty) next_dir = 0;
-            const float nx = l0 + vx * next_t, ny = l1 + vy * next_t;  // LineSegmentF::sample
-            if (slot + 2 > slot_end) {  // the walk left the |dx|+|dy|+1 envelope (only with non-finite arithmetic)
-                atomicOr(&b.counters->overflow, (uint32_t)OVF_DDA);
-                break;
-            }
-            if (add_fill(b, pt, cur_x, cur_y, nx, ny, tcx, tcy, slot)) slot++;
-            if (step_y < 0 && next_dir == 2) {
-                if (add_fill(b, pt, nx, ny, (float)tcx * ts, (float)tcy * ts, tcx, tcy, slot)) slot++;
-            } else if (step_y > 0 && last_dir == 2) {
-                if (add_fill(b, pt, (float)tcx * ts, (float)tcy * ts, cur_x, cur_y, tcx, tcy, slot)) slot++;
-            }
-            if (step_x < 0 && last_dir == 1) adjust_backdrop(b, pt, tcx, tcy, 1);
-            else if (step_x > 0 && next_dir == 1) adjust_backdrop(b, pt, tcx, tcy, -1);
-            if (next_dir == 1) { t_max_x += t_delta_x; tcx += step_x; }
-            else if (next_dir == 2) { t_max_y += t_delta_y; tcy += step_y; }
-            else break;
-            cur_x = nx;
-            cur_y = ny;
-            last_dir = next_dir;
+        t_max_x = (fcx - a0) / vx; t_max_y = (fcy - a1) / vy;
+        t_delta_x = fabsf(ts / vx); t_delta_y = fabsf(ts / vy);
+    }
+    // Decision of one step (tiler.cpp:191-215): direction of the next tile crossing and its clamped t.
+    __device__ __forceinline__ void decide(int &next_dir, float &next_t) const {
+        if (t_max_x < t_max_y) next_dir = 1;
+        else if (t_max_x > t_max_y) next_dir = 2;
+        else next_dir = step_x > 0 ? 1 : 2;
+        next_t = next_dir == 1 ? t_max_x : t_max_y;
+        next_t = next_t < 1.0f ? next_t : 1.0f;
+        if (tcx == to_tx && tcy == to_ty) next_dir = 0;
+    }
+    __device__ __forceinline__ void advance(int next_dir) {
+        if (next_dir == 1) { t_max_x += t_delta_x; tcx += step_x; }
+        else if (next_dir == 2) { t_max_y += t_delta_y; tcy += step_y; }
+    }
+};
+
+// The expensive part of one step (tiler.cpp:216-270): up to two fills into this step's two staging slots, backdrop
+// bookkeeping. cur = where the line enters the tile, (nx, ny) = where it leaves it.
+__device__ __forceinline__ uint32_t walk_step_emit(const BatchView &b, const PathTiles &pt, const Walk &w, float cur_x,
+                                                   float cur_y, float nx, float ny, int tcx, int tcy, int last_dir,
+                                                   int next_dir, uint32_t slot) {
+    const float ts = 16.0f;
+    uint32_t used = 0;
+    if (add_fill(b, pt, cur_x, cur_y, nx, ny, tcx, tcy, slot + used)) used++;
+    if (w.step_y < 0 && next_dir == 2) {
+        if (add_fill(b, pt, nx, ny, (float)tcx * ts, (float)tcy * ts, tcx, tcy, slot + used)) used++;
+    } else if (w.step_y > 0 && last_dir == 2) {
+        if (add_fill(b, pt, (float)tcx * ts, (float)tcy * ts, cur_x, cur_y, tcx, tcy, slot + used)) used++;
+    }
+    if (w.step_x < 0 && last_dir == 1) adjust_backdrop(b, pt, tcx, tcy, 1);
+    else if (w.step_x > 0 && next_dir == 1) adjust_backdrop(b, pt, tcx, tcy, -1);
+    return used;
+}
+
+constexpr uint32_t BIN_LONG_STEPS = 12;  // walks longer than this are shared by the warp
+
+__global__ void __launch_bounds__(128) k_bin(BatchView b) {
+    const uint32_t n_lines = min(b.counters->n_lines, b.line_capacity);
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp0 * 32; base < n_lines; base += n_warps * 32) {
+        const uint32_t i = base + lane;
+        bool active = i < n_lines;
+        float4 ln = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t path = 0, steps = 0;
+        if (active) {
+            ln = b.lines[i];
+            path = b.line_meta[i].x;
+            // the walk visits |dx| + |dy| + 1 tiles (tiler.cpp:191-278) and adds at most two fills per tile
+            const long long tx0 = (int)floorf(ln.x * 0.0625f), ty0 = (int)floorf(ln.y * 0.0625f);
+            const long long tx1 = (int)floorf(ln.z * 0.0625f), ty1 = (int)floorf(ln.w * 0.0625f);
+            long long d = llabs(tx1 - tx0) + llabs(ty1 - ty0) + 1;
+            if (d > MAX_DDA_STEPS) d = MAX_DDA_STEPS;
+            steps = (uint32_t)d;
         }
-        for (; slot < slot_end; slot++) b.staging[slot].tile = 0xffffffffu;  // unused slots
+        // staging slots for the whole warp: one atomic
+        const uint32_t slots = 2u * steps;
+        const uint32_t incl = warp_incl_scan(slots, lane);
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t sbase = 0;
+        if (lane == 31 && total) sbase = atomicAdd(&b.counters->n_staging, total);
+        sbase = __shfl_sync(0xffffffffu, sbase, 31);
+        const uint32_t slot0 = sbase + incl - slots;
+        if (active && slot0 + slots > b.staging_capacity) {
+            atomicOr(&b.counters->overflow, (uint32_t)OVF_STAGING);
+            active = false;
+        }
+        const bool is_long = active && steps > BIN_LONG_STEPS;
+        if (active && !is_long) {
+            const PathTiles pt = load_path_tiles(b, path);
+            Walk w;
+            w.init(ln.x, ln.y, ln.z, ln.w);
+            float cur_x = ln.x, cur_y = ln.y;
+            int last_dir = 0;  // 0 none, 1 X, 2 Y
+            uint32_t slot = slot0;
+            const uint32_t slot_end = slot0 + slots;
+            for (uint32_t s = 0;; s++) {
+                int next_dir;
+                float next_t;
+                w.decide(next_dir, next_t);
+                if (s >= steps) {  // the walk left the |dx|+|dy|+1 envelope (only with non-finite arithmetic)
+                    atomicOr(&b.counters->overflow, (uint32_t)OVF_DDA);
+                    break;
+                }
+                const float nx = w.l0 + w.vx * next_t, ny = w.l1 + w.vy * next_t;  // LineSegmentF::sample
+                slot += walk_step_emit(b, pt, w, cur_x, cur_y, nx, ny, w.tcx, w.tcy, last_dir, next_dir, slot);
+                if (next_dir == 0) break;
+                w.advance(next_dir);
+                cur_x = nx;
+                cur_y = ny;
+                last_dir = next_dir;
+            }
+            for (; slot < slot_end; slot++) b.staging[slot].tile = 0xffffffffu;  // unused slots
+        }
+        // long walks: one at a time, all 32 lanes
+        unsigned long_mask = __ballot_sync(0xffffffffu, is_long);
+        while (long_mask) {
+            const int src = __ffs(long_mask) - 1;
+            long_mask &= long_mask - 1;
+            const float a0 = __shfl_sync(0xffffffffu, ln.x, src), a1 = __shfl_sync(0xffffffffu, ln.y, src);
+            const float a2 = __shfl_sync(0xffffffffu, ln.z, src), a3 = __shfl_sync(0xffffffffu, ln.w, src);
+            const uint32_t lpath = __shfl_sync(0xffffffffu, path, src);
+            const uint32_t lslot0 = __shfl_sync(0xffffffffu, slot0, src), lsteps = __shfl_sync(0xffffffffu, steps, src);
+            const PathTiles pt = load_path_tiles(b, lpath);
+            Walk w;
+            w.init(a0, a1, a2, a3);
+            int last_dir = 0;
+            float prev_t = 0.0f;
+            uint32_t s = 0;
+            bool done = false;
+            while (!done) {
+                // cheap part, replayed by every lane: 32 steps of the t_max chain; lane k keeps step s0 + k
+                int my_dir = -1, my_last = 0, my_tcx = 0, my_tcy = 0;
+                float my_t = 0.0f, my_prev_t = 0.0f;
+                const uint32_t s0 = s;
+#pragma unroll 4
+                for (int k = 0; k < 32; k++) {
+                    int next_dir;
+                    float next_t;
+                    w.decide(next_dir, next_t);
+                    if (s >= lsteps) {
+                        if (lane == 0) atomicOr(&b.counters->overflow, (uint32_t)OVF_DDA);
+                        done = true;
+                        break;
+                    }
+                    if ((int)lane == k) {
+                        my_dir = next_dir; my_last = last_dir; my_tcx = w.tcx; my_tcy = w.tcy;
+                        my_t = next_t; my_prev_t = prev_t;
+                    }
+                    s++;
+                    if (next_dir == 0) {
+                        done = true;
+                        break;
+                    }
+                    w.advance(next_dir);
+                    prev_t = next_t;
+                    last_dir = next_dir;
+                }
+                // expensive part: one step per lane
+                if (my_dir >= 0) {
+                    const uint32_t my_s = s0 + lane;
+                    const float nx = w.l0 + w.vx * my_t, ny = w.l1 + w.vy * my_t;
+                    const float cx = my_s == 0 ? a0 : w.l0 + w.vx * my_prev_t, cy = my_s == 0 ? a1 : w.l1 + w.vy * my_prev_t;
+                    const uint32_t slot = lslot0 + 2u * my_s;
+                    const uint32_t used = walk_step_emit(b, pt, w, cx, cy, nx, ny, my_tcx, my_tcy, my_last, my_dir, slot);
+                    for (uint32_t u = used; u < 2; u++) b.staging[slot + u].tile = 0xffffffffu;
+                }
+            }
+            // steps the walk never reached
+            for (uint32_t u = lslot0 + 2u * s + lane; u < lslot0 + 2u * lsteps; u += 32) b.staging[u].tile = 0xffffffffu;
+        }
     }
 }
 

@@ -1,15 +1,26 @@
-// fill + tile ("composite"): the two rasterizing kernels, the HBM-bound end of the path.
+// fill + tile ("composite"): the two rasterizing stages, the HBM-bound end of the path.
 //
-//   fill : pathfinder/shaders/d3d11/fill.comp:51-154. One warp per alpha tile; a lane owns one pixel column of two
-//          4-row groups (the LUT's four channels are four consecutive rows). The tile's fills are contiguous
-//          (CSR from the scatter), read once with coalesced 8-byte loads and broadcast by shuffle; coverage is
-//          accumulated in registers; the 16 x 16 mask is written once, 1 byte per pixel.
+// Pixel ownership is the same in both kernels so that they can be fused: a WARP owns one 16 x 16 tile, lane
+// (c = lane & 15, h = lane >> 4) owns pixel column c, rows h*4 .. h*4+3 and 8+h*4 .. 8+h*4+3, i.e. two of the area
+// LUT's 4-row groups, one in the top half of the tile and one in the bottom half (a short fill touches one half, so
+// the other half's LUT fetches are skipped by the whole warp).
+//
+//   fill : pathfinder/shaders/d3d11/fill.comp:51-154. The tile's fills are contiguous (CSR from the scatter), read
+//          once with coalesced 8-byte loads and broadcast by shuffle. The 256 x 256 area LUT sits behind the
+//          texture unit (texel fetch + unorm conversion; the bilinear weights are applied in fp32); lanes whose
+//          column a fill does not overlap (dX == 0, contribution exactly 0) skip it, and 4-row groups outside the
+//          LUT's transition band take the saturated value without fetching. Coverage stays in registers; the mask
+//          is stored once, lane-major, one 8-byte store per lane.
 //   tile : pathfinder/shaders/d3d11/tile.comp:737-850 with the shading functions of tile.comp:126-134 (combine),
 //          :319-347 (radial gradient), :354-392 (blur), :459-582 (composite), :586-607 (mask), :694-726 (paint
-//          metadata, decoded once per upload into a float table). One WARP per framebuffer tile (no block barriers):
-//          one 16-byte load gives the tile's list range and z; the list is sorted by paint order and z-culled on
-//          chip (sort.comp:49-83); a lane blends 8 pixels of one row in fp32 registers and stores them with two
-//          16-byte stores. Scenes whose paints are all solid take a specialised instantiation.
+//          metadata, decoded once per upload into a float table). One 16-byte load gives the tile's list range and
+//          z; the list (<= 32 entries: registers + shuffles, longer: selection from global memory) is ordered by
+//          paint order and z-culled on chip (sort.comp:49-83). While every layer so far covered the whole tile with
+//          one colour, the warp blends ONE pixel instead of 256 and stores the tile with 16-byte stores; the first
+//          masked / textured layer expands it to per-pixel registers.
+//   fused: in the fused instantiation the composite kernel computes the coverage of a draw tile from its fills
+//          right where it is blended -- the mask never leaves the SM (B_fused). Clip masks
+//          (written by the clip batch's fill kernel) are still read from memory and min()-ed in.
 #include <cuda_fp16.h>
 
 #include "pfcu_device.h"
@@ -72,83 +83,136 @@ __device__ __forceinline__ float glsl_mod(float x, float y) { return x - y * flo
 
 // ------------------------------------------------------------------------------------------------ fill
 
-// computeCoverage, fill.comp:51-71: coverage of the 4 rows (fragy .. fragy + 3) in one pixel column.
-__device__ __forceinline__ float4 compute_coverage(const PaintView &p, float fx, float fy, float tx, float ty) {
-    const bool from_left = fx < tx;
-    const float lx = from_left ? fx : tx, ly = from_left ? fy : ty;
-    const float rx = from_left ? tx : fx, ry = from_left ? ty : fy;
-    const float wx = clampf(fx, -0.5f, 0.5f), wy = clampf(tx, -0.5f, 0.5f);
-    const float offset = mixf(wx, wy, 0.5f) - lx;
-    const float t = offset / (rx - lx);
-    const float y = mixf(ly, ry, t);
-    const float d = (ry - ly) / (rx - lx);
-    const float dX = wx - wy;
-    const float4 s = sample_rgba8(p.area_lut, p.lut_w, p.lut_h, (y + 8.0f) / 16.0f, fabsf(d * dX) / 16.0f, false,
-                                  false, false);
-    return make_float4(s.x * dX, s.y * dX, s.z * dX, s.w * dX);
+// One 4-row group of one pixel column (computeCoverage's LUT fetch, fill.comp:70, times dX, into cov[0..3]).
+// texture(uAreaLUT, uv) is spelled out in fp32: the texture unit fetches the four texels (point sampling,
+// clamp-to-edge, unorm8 -> float) and the bilinear weights k** (already multiplied by dX) are applied here. The unit's
+// own bilinear mode keeps only 8 fraction bits of the weights, which moves about 1 % of the mask bytes by one step --
+// too coarse for a 1/255 bound on pixels under several translucent layers.
+// Outside the LUT's transition band all four channels are exactly 1 (rows below the line) or exactly 0 (above it);
+// `band` says the uploaded LUT has been checked for that (pfcu_set_area_lut), so when the whole warp is outside the
+// band the group costs two compares instead of four fetches.
+__device__ __forceinline__ void add_group(cudaTextureObject_t lut, bool band, float x, float fx0, float fy0, float half,
+                                          float k00, float k10, float k01, float k11, float dX, float *cov) {
+    int kind = 0;  // 0: sample, 1: all rows fully covered, 2: no row covered
+    if (band) {
+        if (x + 2.0f < 120.0f - half) kind = 1;
+        else if (x - 1.0f > 184.0f + half) kind = 2;
+    }
+    if (__any_sync(__activemask(), kind == 0)) {
+        const float4 t00 = tex2D<float4>(lut, fx0 + 0.5f, fy0 + 0.5f), t10 = tex2D<float4>(lut, fx0 + 1.5f, fy0 + 0.5f);
+        const float4 t01 = tex2D<float4>(lut, fx0 + 0.5f, fy0 + 1.5f), t11 = tex2D<float4>(lut, fx0 + 1.5f, fy0 + 1.5f);
+        cov[0] = fmaf(t11.x, k11, fmaf(t01.x, k01, fmaf(t10.x, k10, fmaf(t00.x, k00, cov[0]))));
+        cov[1] = fmaf(t11.y, k11, fmaf(t01.y, k01, fmaf(t10.y, k10, fmaf(t00.y, k00, cov[1]))));
+        cov[2] = fmaf(t11.z, k11, fmaf(t01.z, k01, fmaf(t10.z, k10, fmaf(t00.z, k00, cov[2]))));
+        cov[3] = fmaf(t11.w, k11, fmaf(t01.w, k01, fmaf(t10.w, k10, fmaf(t00.w, k00, cov[3]))));
+    } else if (kind == 1) {
+        cov[0] += dX; cov[1] += dX; cov[2] += dX; cov[3] += dX;
+    }
 }
 
-__device__ __forceinline__ float apply_fill_rule(float cv, bool winding) {  // fill.comp:133-140
-    if (winding) return clampf(fabsf(cv), 0.0f, 1.0f);
-    return clampf(1.0f - fabsf(1.0f - glsl_mod(cv, 2.0f)), 0.0f, 1.0f);
-}
-
-__global__ void __launch_bounds__(256) k_fill(BatchView b, PaintView p) {
-    const unsigned lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t first_alpha = b.counters->first_alpha;
-    uint32_t n_alpha = *b.frame_alpha_counter - first_alpha;
-    if (n_alpha > b.alpha_capacity) n_alpha = b.alpha_capacity;
-    const int lx = (int)(lane & 15), g0 = (int)(lane >> 4);
-    const float fragx = (float)lx + 0.5f;
-    for (uint32_t a = warp; a < n_alpha; a += n_warps) {
-        const uint32_t id = first_alpha + a;
-        if (id >= b.mask_capacity) break;
-        AlphaTile at;
-        *reinterpret_cast<uint4 *>(&at) = *reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]);
-        const uint32_t ti = at.tile_index;
-        if (ti >= b.tile_count) continue;
-        const uint32_t count = at.fill_count;
-        uint32_t end = b.fill_cursor[ti];
-        if (end > b.fill_capacity) end = b.fill_capacity;
-        const uint32_t begin = end >= count ? end - count : 0u;
-        const float backdrop = (float)(int8_t)(at.packed & 0xffu);
-        const bool winding = (at.packed & 0x100u) != 0;
-        float4 cov0 = make_float4(backdrop, backdrop, backdrop, backdrop), cov1 = cov0;
-        const float fragy0 = (float)(g0 * 4) + 0.5f, fragy1 = (float)((g0 + 2) * 4) + 0.5f;
-        for (uint32_t c = begin; c < end; c += 32) {
-            uint2 mine = make_uint2(0, 0);
-            if (c + lane < end) mine = b.fills[c + lane];
-            const int m = (int)min(32u, end - c);
-            for (int k = 0; k < m; k++) {
-                const uint32_t f = __shfl_sync(0xffffffffu, mine.x, k), t = __shfl_sync(0xffffffffu, mine.y, k);
-                // vec4(from.x, from.y, to.x, to.y) / 256.0 - tileFragCoord.xyxy (fill.comp:87-90)
-                const float fx = (float)(f & 0xffffu) / 256.0f - fragx, tx = (float)(t & 0xffffu) / 256.0f - fragx;
-                const float fyq = (float)(f >> 16) / 256.0f, tyq = (float)(t >> 16) / 256.0f;
-                const float4 c0 = compute_coverage(p, fx, fyq - fragy0, tx, tyq - fragy0);
-                const float4 c1 = compute_coverage(p, fx, fyq - fragy1, tx, tyq - fragy1);
-                cov0.x += c0.x; cov0.y += c0.y; cov0.z += c0.z; cov0.w += c0.w;
-                cov1.x += c1.x; cov1.y += c1.y; cov1.z += c1.z; cov1.w += c1.w;
-            }
+// Adds the signed area coverage of fills [begin, end) to the lane's 8 pixels (computeCoverage, fill.comp:51-71,
+// for the lane's two 4-row groups: rows h*4 .. h*4+3 and 8+h*4 .. 8+h*4+3, column c). What only depends on the fill
+// (left end point, slope) is computed once by the lane that loaded it and broadcast by shuffle.
+__device__ __forceinline__ void accumulate_fills(const uint2 *__restrict__ fills, uint32_t begin, uint32_t end,
+                                                 unsigned lane, cudaTextureObject_t lut, bool band, float cov[8]) {
+    const float col = (float)(lane & 15u);  // left edge of the pixel column; tileFragCoord.x = col + 0.5
+    const float fragy0 = (float)((lane >> 4) * 4u) + 0.5f;
+    for (uint32_t at = begin; at < end; at += 32) {
+        float x_from = 0.f, x_to = 0.f, ly = 0.f, d = 0.f;
+        if (at + lane < end) {
+            const uint2 f = __ldg(&fills[at + lane]);
+            x_from = (float)(f.x & 0xffffu) * (1.0f / 256.0f);
+            x_to = (float)(f.y & 0xffffu) * (1.0f / 256.0f);
+            const float y_from = (float)(f.x >> 16) * (1.0f / 256.0f), y_to = (float)(f.y >> 16) * (1.0f / 256.0f);
+            const bool from_left = x_from < x_to;  // fill.comp:53-55
+            ly = from_left ? y_from : y_to;
+            const float ry = from_left ? y_to : y_from;
+            d = (ry - ly) * __fdividef(1.0f, fabsf(x_to - x_from));  // fill.comp:64 (bin never emits x_from == x_to)
         }
-        float cv[8] = {cov0.x, cov0.y, cov0.z, cov0.w, cov1.x, cov1.y, cov1.z, cov1.w};
-        uint8_t *mask = b.masks + (size_t)id * 256;
-        const uint8_t *clip = at.clip_alpha >= 0 && (uint32_t)at.clip_alpha < b.mask_capacity
-                                  ? b.masks + (size_t)at.clip_alpha * 256 : nullptr;
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int row = (q < 4 ? g0 * 4 : (g0 + 2) * 4) + (q & 3);
-            float v = apply_fill_rule(cv[q], winding);
-            if (clip) v = fminf(v, (float)clip[row * 16 + lx] * (1.0f / 255.0f));  // fill.comp:147-150
-            mask[row * 16 + lx] = (uint8_t)__float2int_rn(v * 255.0f);
+        const int m = (int)min(32u, end - at);
+        for (int k = 0; k < m; k++) {
+            const float xf = __shfl_sync(0xffffffffu, x_from, k), xt = __shfl_sync(0xffffffffu, x_to, k);
+            // window = clamp(vec2(from.x, to.x), -0.5, 0.5) in fragment-centred coordinates (fill.comp:58) == saturate
+            // in column-edge coordinates; the differences are exact (multiples of 1/256 below 16)
+            const float wx = __saturatef(xf - col), wy = __saturatef(xt - col);
+            const float lyk = __shfl_sync(0xffffffffu, ly, k), dk = __shfl_sync(0xffffffffu, d, k);
+            const float dX = wx - wy;
+            if (dX == 0.0f) continue;  // the fill does not overlap this pixel column: contributes exactly 0
+            // y of the line at the middle of the window (fill.comp:59-63), relative to the group's first pixel centre
+            const float offset = fmaf(0.5f, wx + wy, col - fminf(xf, xt));
+            const float y = fmaf(dk, offset, lyk) - fragy0;
+            // LUT texel coordinates: u = (y + 8) / 16, v = |d * dX| / 16 on 256 x 256 texels, minus the half texel
+            const float lut_x = fmaf(y, 16.0f, 127.5f), lut_y = fmaf(fabsf(dk * dX), 16.0f, -0.5f);
+            const float fx0 = floorf(lut_x), fy0 = floorf(lut_y);
+            const float ax = lut_x - fx0, ay = lut_y - fy0;
+            const float w11 = ax * ay, w10 = ax - w11, w01 = ay - w11, w00 = (1.0f - ax) - w01;
+            const float half = fmaf(0.5f, lut_y, 1.0f);
+            add_group(lut, band, lut_x, fx0, fy0, half, w00 * dX, w10 * dX, w01 * dX, w11 * dX, dX, cov);
+            add_group(lut, band, lut_x - 128.0f, fx0 - 128.0f, fy0, half, w00 * dX, w10 * dX, w01 * dX, w11 * dX, dX,
+                      cov + 4);  // 8 rows further down
         }
     }
 }
 
+// round(v * 255) for v in [0, 1] in the low byte (adding 1.5 * 2^23 leaves the integer, nearest-even, in the mantissa)
+__device__ __forceinline__ uint32_t unorm8_bits(float v) { return __float_as_uint(fmaf(v, 255.0f, 12582912.0f)); }
+
+// Coverage -> the 8 mask bytes of the lane (fill.comp:131-153): fill rule, optional min() with the clip mask,
+// RGBA8-unorm quantisation.
+__device__ __forceinline__ uint2 quantise_mask(const float cov[8], bool winding, const uint8_t *masks, int clip_alpha,
+                                               unsigned lane) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; q++) {  // fill.comp:133-140
+        if (winding) v[q] = fminf(fabsf(cov[q]), 1.0f);
+        else v[q] = __saturatef(1.0f - fabsf(1.0f - glsl_mod(cov[q], 2.0f)));
+    }
+    if (clip_alpha >= 0) {  // fill.comp:147-150
+        const uint2 clip = __ldg(reinterpret_cast<const uint2 *>(masks + (size_t)clip_alpha * 256) + lane);
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            v[q] = fminf(v[q], (float)(((q < 4 ? clip.x : clip.y) >> (8 * (q & 3))) & 0xffu) * (1.0f / 255.0f));
+    }
+    uint2 out;
+    out.x = __byte_perm(__byte_perm(unorm8_bits(v[0]), unorm8_bits(v[1]), 0x0040),
+                        __byte_perm(unorm8_bits(v[2]), unorm8_bits(v[3]), 0x0040), 0x5410);
+    out.y = __byte_perm(__byte_perm(unorm8_bits(v[4]), unorm8_bits(v[5]), 0x0040),
+                        __byte_perm(unorm8_bits(v[6]), unorm8_bits(v[7]), 0x0040), 0x5410);
+    return out;
+}
+
+constexpr int FILL_WARPS = 8;
+
+__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView p) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t first_alpha = b.counters->first_alpha;
+    uint32_t n_alpha = b.counters->n_alpha;
+    if (n_alpha > b.alpha_capacity) n_alpha = b.alpha_capacity;
+    for (uint32_t a = warp; a < n_alpha; a += n_warps) {
+        const uint32_t id = first_alpha + a;
+        if (id >= b.mask_capacity) break;
+        const uint4 at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]));  // tile, clip, packed, fill count
+        const uint32_t ti = at.x;
+        if (ti >= b.tile_count) continue;  // a tile with fills that the clip made invisible: no mask needed
+        uint32_t end = b.fill_cursor[ti];
+        if (end > b.fill_capacity) end = b.fill_capacity;
+        const uint32_t begin = end >= at.w ? end - at.w : 0u;
+        const float backdrop = (float)(int8_t)(at.z & 0xffu);
+        float cov[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) cov[q] = backdrop;
+        accumulate_fills(b.fills, begin, end, lane, p.lut_tex, p.lut_band != 0, cov);
+        const int clip_alpha = (int)at.y >= 0 && at.y < b.mask_capacity ? (int)at.y : -1;
+        const uint2 m = quantise_mask(cov, (at.z & 0x100u) != 0, b.masks, clip_alpha, lane);
+        reinterpret_cast<uint2 *>(b.masks + (size_t)id * 256)[lane] = m;
+    }
+}
+
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s) {
-    if (!b.tile_count || !p.area_lut) return cudaSuccess;
-    k_fill<<<sm_count() * 16, 256, 0, s>>>(b, p);
+    if (!b.tile_count || !p.lut_tex) return cudaSuccess;
+    k_fill<<<sm_count() * 8, FILL_WARPS * 32, 0, s>>>(b, p);
     return cudaGetLastError();
 }
 
@@ -323,15 +387,16 @@ __device__ __forceinline__ float4 shade(const Paint &pc, const ColorSampler &cs,
     return color;
 }
 
-constexpr int MAX_SORTED = 64;      // list entries sorted in shared memory per warp; longer lists use selection
-constexpr int COMPOSITE_WARPS = 4;  // framebuffer tiles per CTA
+constexpr int CT_WARPS = 8;    // warps per CTA
+#ifndef CT_MIN_CTAS
+#define CT_MIN_CTAS 3
+#endif
+constexpr int CT_TILES = 32;   // consecutive framebuffer tiles a CTA stages and renders
+constexpr int CT_PRIMS = 160;  // list entries staged in shared memory (longer batches read their lists from global)
 
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
-    const uint32_t r = (uint32_t)__float2int_rn(clampf(c.x, 0.f, 1.f) * 255.0f);
-    const uint32_t g = (uint32_t)__float2int_rn(clampf(c.y, 0.f, 1.f) * 255.0f);
-    const uint32_t bl = (uint32_t)__float2int_rn(clampf(c.z, 0.f, 1.f) * 255.0f);
-    const uint32_t a = (uint32_t)__float2int_rn(clampf(c.w, 0.f, 1.f) * 255.0f);
-    return r | (g << 8) | (bl << 16) | (a << 24);
+    return __byte_perm(__byte_perm(unorm8_bits(__saturatef(c.x)), unorm8_bits(__saturatef(c.y)), 0x0040),
+                       __byte_perm(unorm8_bits(__saturatef(c.z)), unorm8_bits(__saturatef(c.w)), 0x0040), 0x5410);
 }
 
 __device__ __forceinline__ float4 unpack_rgba8(uint32_t v) {
@@ -340,56 +405,125 @@ __device__ __forceinline__ float4 unpack_rgba8(uint32_t v) {
                        (float)(v >> 24) * k);
 }
 
-template <bool SOLID>
-__global__ void __launch_bounds__(COMPOSITE_WARPS * 32) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
-                                                                    float4 clear_color) {
-    __shared__ uint4 s_prims[COMPOSITE_WARPS][MAX_SORTED];
+__device__ __forceinline__ void blend_over(float4 &dest, const float4 &src) {  // tile.comp:841
+    const float ia = 1.0f - src.w;
+    dest.x = fmaf(dest.x, ia, src.x);
+    dest.y = fmaf(dest.y, ia, src.y);
+    dest.z = fmaf(dest.z, ia, src.z);
+    dest.w = fmaf(dest.w, ia, src.w);
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+constexpr int CT_SLOTS = 4;  // coverage masks a warp keeps in shared memory between its two phases
+
+struct CompositeShared {
+    uint4 fb[CT_TILES];                     // begin, count, z, cursor of the CTA's tiles
+    uint4 prims[CT_PRIMS][2];               // their lists (contiguous in memory because the list offsets come from a scan)
+    uint2 cover[CT_WARPS][CT_SLOTS][32];    // fused: mask bytes of the layers being blended, lane-major
+    uint32_t next;                          // dynamic tile distribution inside the CTA
+};
+
+// Walks a tile's list in paint order. Lists of up to 32 entries live in registers (one entry per lane, ranked by
+// key); longer ones are walked by repeated selection of the next larger key from the list itself.
+struct ListCursor {
+    uint32_t layer, last_key;
+    bool first;
+};
+
+template <bool FUSED>
+__device__ __forceinline__ bool next_entry(ListCursor &cur, bool in_regs, uint32_t n, uint32_t n_sorted, int z,
+                                           const uint4 *list, const uint4 &e0, const uint4 &e1, uint32_t rank,
+                                           unsigned lane, uint4 &q0, uint4 &q1) {
+    q1 = make_uint4(0u, 0xffffffffu, 0u, 0u);
+    if (in_regs) {
+        if (cur.layer >= n_sorted) return false;
+        const int src = __ffs(__ballot_sync(0xffffffffu, rank == cur.layer)) - 1;
+        q0.x = __shfl_sync(0xffffffffu, e0.x, src);
+        q0.y = __shfl_sync(0xffffffffu, e0.y, src);
+        q0.z = __shfl_sync(0xffffffffu, e0.z, src);
+        q0.w = 0u;
+        if (FUSED) {
+            q0.w = __shfl_sync(0xffffffffu, e0.w, src);
+            q1.x = __shfl_sync(0xffffffffu, e1.x, src);
+            q1.y = __shfl_sync(0xffffffffu, e1.y, src);
+            q1.z = __shfl_sync(0xffffffffu, e1.z, src);
+        }
+        cur.layer++;
+        return true;
+    }
+    // selection: next smallest key >= z that is greater than the last one processed
+    uint32_t best = 0xffffffffu, best_i = 0;
+    for (uint32_t i = lane; i < n; i += 32) {
+        const uint32_t key = list[i * 2].x;
+        if ((int)key >= z && (cur.first || key > cur.last_key) && key < best) {
+            best = key;
+            best_i = i;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+        if (ob < best) {
+            best = ob;
+            best_i = oi;
+        }
+    }
+    if (best == 0xffffffffu) return false;
+    q0 = list[best_i * 2];
+    if (FUSED) q1 = list[best_i * 2 + 1];
+    cur.last_key = best;
+    cur.first = false;
+    cur.layer++;
+    return true;
+}
+
+// One CTA renders CT_TILES consecutive framebuffer tiles. The three dependent loads of a tile (its list header, its
+// list, the fills / masks the list points to) are issued for ALL of the CTA's tiles at once -- header and lists with
+// coalesced loads into shared memory, fills / masks as L1 prefetches -- so their latency is paid once per CTA instead
+// of once per tile; warps then pull tiles from a shared counter, which balances tiles with deep lists against empty
+// ones. A tile is rendered in two phases so that the registers of the coverage computation and of the 8 x RGBA
+// destination pixels are never live together: first the masks of its layers (fused mode), then the blend.
+template <bool SOLID, bool FUSED>
+__global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchView b, PaintView p, TargetView tg,
+                                                                          int clear, float4 clear_color) {
+    __shared__ CompositeShared sh;
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
-    const uint32_t map = blockIdx.x * COMPOSITE_WARPS + wib;
-    if (map >= n_fb) return;
-    const int tile_x = (int)(map % (uint32_t)b.fb_tw), tile_y = (int)(map / (uint32_t)b.fb_tw);
-    const uint4 fbt = __ldg(reinterpret_cast<const uint4 *>(&b.fb[map]));  // begin, count, z
-    uint32_t n = fbt.y;
-    if (n == 0 && !clear) return;  // tile.comp:743-744
-    const uint32_t begin = fbt.x;
-    if (begin + n > b.prim_capacity) n = begin < b.prim_capacity ? b.prim_capacity - begin : 0u;
-    const int z = (int)fbt.z;
+    const uint32_t map0 = blockIdx.x * CT_TILES;
+    const uint32_t n_tiles = min((uint32_t)CT_TILES, n_fb - map0);
 
-    const int row = (int)(lane >> 1), x0 = (int)(lane & 1) * 8;
-    const int gx0 = tile_x * TILE + x0, gy = tile_y * TILE + row;
-    const bool row_ok = gy < tg.height;
-    uint32_t *dst = reinterpret_cast<uint32_t *>(tg.pixels + (size_t)gy * tg.pitch) + gx0;
-    float4 dest[8];
-    if (clear) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) dest[k] = clear_color;
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            dest[k] = (row_ok && gx0 + k < tg.width) ? unpack_rgba8(dst[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- stage 1: list headers
+    if (threadIdx.x < CT_TILES) {
+        uint4 f = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x < n_tiles) f = __ldg(reinterpret_cast<const uint4 *>(&b.fb[map0 + threadIdx.x]));
+        sh.fb[threadIdx.x] = f;
     }
-
-    // Sort by paint order and z-cull on chip (sort.comp:49-83). Keys (dense tile indices) are unique.
-    uint32_t n_sorted = 0;
-    const bool in_smem = n <= MAX_SORTED;
-    if (in_smem && n) {
-        uint4 e0 = make_uint4(0xffffffffu, 0, 0, 0), e1 = e0;
-        if (lane < n) e0 = __ldg(reinterpret_cast<const uint4 *>(&b.prims[begin + lane]));
-        if (lane + 32 < n) e1 = __ldg(reinterpret_cast<const uint4 *>(&b.prims[begin + lane + 32]));
-        const bool keep0 = lane < n && (int)e0.x >= z, keep1 = lane + 32 < n && (int)e1.x >= z;
-        uint32_t r0 = 0, r1 = 0;
-        const int rounds = n > 32 ? 64 : 32;
-        for (int j = 0; j < rounds; j++) {
-            const uint32_t kj = __shfl_sync(0xffffffffu, j < 32 ? e0.x : e1.x, j & 31);
-            const bool vj = (uint32_t)j < n && (int)kj >= z;
-            r0 += (vj && kj < e0.x) ? 1u : 0u;
-            r1 += (vj && kj < e1.x) ? 1u : 0u;
+    if (threadIdx.x == 0) sh.next = 0;
+    __syncthreads();
+    // ---- stage 2: the lists of all tiles are one contiguous range
+    const uint32_t range0 = sh.fb[0].x;
+    uint32_t range_n = sh.fb[n_tiles - 1].x + sh.fb[n_tiles - 1].y - range0;
+    if (range0 + range_n > b.prim_capacity) range_n = range0 < b.prim_capacity ? b.prim_capacity - range0 : 0u;
+    const bool staged = range_n <= CT_PRIMS;
+    if (staged) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(b.prims + range0);
+        for (uint32_t i = threadIdx.x; i < range_n * 2; i += CT_WARPS * 32) (&sh.prims[0][0])[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    // ---- stage 3: pull the fills (fused) or masks the lists point to towards this SM
+    if (staged) {
+        for (uint32_t i = threadIdx.x; i < range_n; i += CT_WARPS * 32) {
+            const uint4 q0 = sh.prims[i][0], q1 = sh.prims[i][1];
+            if ((int)q0.y < 0) continue;
+            if (FUSED && (q1.z & PRIM_OWNS_MASK)) {
+                if (q1.x && q0.w < b.fill_capacity) prefetch_l1(b.fills + q0.w);
+                if ((int)q1.y >= 0 && q1.y < b.mask_capacity) prefetch_l1(b.masks + (size_t)q1.y * 256);
+            } else if (q0.y < b.mask_capacity) {
+                prefetch_l1(b.masks + (size_t)q0.y * 256);
+                prefetch_l1(b.masks + (size_t)q0.y * 256 + 128);
+            }
         }
-        if (keep0) s_prims[wib][r0] = e0;
-        if (keep1) s_prims[wib][r1] = e1;
-        n_sorted = (uint32_t)(__popc(__ballot_sync(0xffffffffu, keep0)) + __popc(__ballot_sync(0xffffffffu, keep1)));
-        __syncwarp();
     }
 
     ColorSampler cs;
@@ -399,107 +533,219 @@ __global__ void __launch_bounds__(COMPOSITE_WARPS * 32) k_composite(BatchView b,
     cs.repeat_u = (p.sampling_flags & 1u) != 0;
     cs.repeat_v = (p.sampling_flags & 2u) != 0;
     cs.nearest = (p.sampling_flags & 0xcu) != 0;
-    const float fragy = (float)gy + 0.5f;
+    const int c = (int)(lane & 15u), h = (int)(lane >> 4);
 
-    uint32_t last_key = 0;
-    bool first_iter = true;
-    for (uint32_t layer = 0;; layer++) {
-        uint4 prim;
-        if (in_smem) {
-            if (layer >= n_sorted) break;
-            prim = s_prims[wib][layer];
-        } else {
-            // selection: next smallest key >= z that is greater than the last one processed
-            uint32_t best = 0xffffffffu, best_i = 0;
-            for (uint32_t i = lane; i < n; i += 32) {
-                const uint32_t key = __ldg(&b.prims[begin + i].key);
-                if ((int)key >= z && (first_iter || key > last_key) && key < best) {
-                    best = key;
-                    best_i = i;
+    // ---- stage 4: tiles
+    while (true) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&sh.next, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n_tiles) break;
+        const uint32_t map = map0 + t;
+        const uint4 fbt = sh.fb[t];
+        uint32_t n = fbt.y;
+        if (n == 0 && !clear) continue;  // tile.comp:743-744
+        const uint32_t begin = fbt.x;
+        if (begin + n > b.prim_capacity) n = begin < b.prim_capacity ? b.prim_capacity - begin : 0u;
+        const int z = (int)fbt.z;
+        const int tile_y = (int)(map / (uint32_t)b.fb_tw), tile_x = (int)map - tile_y * b.fb_tw;
+        const int gx = tile_x * TILE + c, gy0 = tile_y * TILE + h * 4;  // pixel q of the lane: row gy0 + ROW(q)
+#define ROW(q) ((q) + ((q) & 4))
+        const bool interior = (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
+        uint8_t *const px0 = tg.pixels + (size_t)gy0 * tg.pitch + (size_t)gx * 4;  // the lane's first pixel
+
+        // Order by paint order and z-cull (sort.comp:49-83). Keys (dense tile indices) are unique.
+        const bool in_regs = n <= 32;
+        const uint4 *list = staged ? &sh.prims[begin - range0][0] : reinterpret_cast<const uint4 *>(b.prims + begin);
+        uint4 e0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), e1 = make_uint4(0u, 0xffffffffu, 0u, 0u);
+        uint32_t rank = 0xffffffffu, n_sorted = 0;
+        if (in_regs && n) {
+            if (lane < n) {
+                e0 = list[lane * 2];
+                if (FUSED) e1 = list[lane * 2 + 1];
+            }
+            const bool keep = lane < n && (int)e0.x >= z;
+            const uint32_t kept_mask = __ballot_sync(0xffffffffu, keep);
+            n_sorted = (uint32_t)__popc(kept_mask);
+            if (keep) {
+                rank = 0;
+                if (n_sorted > 1) {
+                    for (uint32_t j = 0; j < n; j++) {  // keys of the other entries straight from the list
+                        const uint32_t kj = list[j * 2].x;
+                        rank += ((kept_mask >> j) & 1u) && kj < e0.x ? 1u : 0u;
+                    }
                 }
             }
+        }
+
+        // dest: one colour for the whole tile while `uniform`, else 8 pixels per lane
+        bool uniform = clear != 0;
+        float4 dest_u = clear_color;
+        float4 dest[8];
+        if (!uniform) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-                if (ob < best) {
-                    best = ob;
-                    best_i = oi;
+            for (int q = 0; q < 8; q++) {
+                const bool ok = gx < tg.width && gy0 + ROW(q) < tg.height;
+                dest[q] = ok ? unpack_rgba8(*reinterpret_cast<const uint32_t *>(px0 + (size_t)ROW(q) * tg.pitch))
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+
+        const float fragx = (float)gx + 0.5f;
+        ListCursor cur = {0u, 0u, true};
+        bool more = n != 0;
+        while (more) {
+            // ---- phase 1 (fused): coverage masks of the next layers that own one, up to CT_SLOTS of them
+            ListCursor ahead = cur;
+            uint32_t n_round = 0xffffffffu;  // layers of this round (all remaining ones unless the slots run out)
+            if (FUSED) {
+                int slot = 0;
+                uint32_t seen = 0;
+                uint4 q0, q1;
+                while (next_entry<FUSED>(ahead, in_regs, n, n_sorted, z, list, e0, e1, rank, lane, q0, q1)) {
+                    seen++;
+                    const int tile_ctrl = (int)((q0.z >> 16) & 0xffu);
+                    if ((int)q0.y < 0 || !(tile_ctrl & 0x3) || !(q1.z & PRIM_OWNS_MASK) || q0.y >= b.mask_capacity) continue;
+                    float cov[8];
+                    const float bd = (float)((int)q0.z >> 24);
+#pragma unroll
+                    for (int q = 0; q < 8; q++) cov[q] = bd;
+                    uint32_t fb_ = q0.w, fe_ = q0.w + q1.x;
+                    if (fe_ > b.fill_capacity) fe_ = b.fill_capacity;
+                    if (fb_ > fe_) fb_ = fe_;
+                    accumulate_fills(b.fills, fb_, fe_, lane, p.lut_tex, p.lut_band != 0, cov);
+                    const int clip_alpha = (int)q1.y >= 0 && q1.y < b.mask_capacity ? (int)q1.y : -1;
+                    sh.cover[wib][slot][lane] = quantise_mask(cov, (tile_ctrl & 0x1) != 0, b.masks, clip_alpha, lane);
+                    if (++slot == CT_SLOTS) {
+                        n_round = seen;
+                        break;
+                    }
+                }
+                __syncwarp();
+            }
+            // ---- phase 2: blend this round's layers
+            int slot = 0;
+            more = false;
+            for (uint32_t i = 0; i < n_round; i++) {
+                uint4 q0, q1;
+                if (!next_entry<FUSED>(cur, in_regs, n, n_sorted, z, list, e0, e1, rank, lane, q0, q1)) break;
+                more = i + 1 == n_round;  // stopped by the slot limit: another round follows
+                // tile.comp:765-800
+                const uint32_t color_entry = q0.z & 0xffffu;
+                int tile_ctrl = (int)((q0.z >> 16) & 0xffu);
+                const int backdrop = (int)q0.z >> 24;
+                const int alpha = (int)q0.y;
+                if (alpha < 0) {
+                    if (backdrop != 0 && (tile_ctrl & 0x2) && (abs(backdrop) & 1) == 0) continue;  // tile.comp:786-792
+                    tile_ctrl &= ~0x3;
+                }
+                const int mask_ctrl = tile_ctrl & 0x3;
+                const bool masked = mask_ctrl != 0 && alpha >= 0 && (uint32_t)alpha < b.mask_capacity;
+
+                Paint pc;
+                if (color_entry < p.n_paints) {
+                    pc.base = __ldg(&p.paints[color_entry].base);
+                    if (!SOLID) {
+                        pc.m0 = __ldg(&p.paints[color_entry].m0);
+                        pc.m1 = __ldg(&p.paints[color_entry].m1);
+                        pc.fp0 = __ldg(&p.paints[color_entry].fp0);
+                        pc.fp1 = __ldg(&p.paints[color_entry].fp1);
+                        pc.ctrl = __ldg(&p.paints[color_entry].ctrl);
+                    }
+                } else {
+                    pc.base = pc.m0 = pc.m1 = pc.fp0 = pc.fp1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    pc.ctrl = 0;
+                }
+                const bool flat_paint = SOLID || pc.ctrl == 0;
+
+                if (!masked && flat_paint) {
+                    // the whole tile gets one premultiplied colour (calculateColor with maskAlpha == 1, tile.comp:611-675)
+                    float4 src = pc.base;
+                    src.x *= src.w;
+                    src.y *= src.w;
+                    src.z *= src.w;
+                    if (uniform) {
+                        blend_over(dest_u, src);
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 8; q++) blend_over(dest[q], src);
+                    }
+                    continue;
+                }
+                if (uniform) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) dest[q] = dest_u;
+                    uniform = false;
+                }
+                // the RGBA8 mask texel values tile.comp:594-598 would fetch for the lane's 8 pixels
+                uint2 mask8 = make_uint2(0xffffffffu, 0xffffffffu);
+                if (masked) {
+                    if (FUSED && (q1.z & PRIM_OWNS_MASK)) mask8 = sh.cover[wib][slot++][lane];
+                    else mask8 = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)alpha * 256) + lane);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    float mask_alpha = 1.0f;
+                    if (masked) {  // sampleMask, tile.comp:586-607 (backdrop is 0 for alpha tiles)
+                        float cov = (float)(((q < 4 ? mask8.x : mask8.y) >> (8 * (q & 3))) & 0xffu) * (1.0f / 255.0f);
+                        if (!(mask_ctrl & 0x1)) cov = 1.0f - fabsf(1.0f - glsl_mod(cov, 2.0f));
+                        mask_alpha = fminf(mask_alpha, cov);
+                    }
+                    float4 src;
+                    if (flat_paint) {
+                        src = pc.base;
+                        src.w *= mask_alpha;
+                        src.x *= src.w;
+                        src.y *= src.w;
+                        src.z *= src.w;
+                    } else {
+                        src = shade<false>(pc, cs, fragx, (float)(gy0 + ROW(q)) + 0.5f, mask_alpha, (float)tg.width,
+                                           (float)tg.height);
+                    }
+                    blend_over(dest[q], src);
                 }
             }
-            if (best == 0xffffffffu) break;
-            prim = __ldg(reinterpret_cast<const uint4 *>(&b.prims[begin + best_i]));
-            last_key = best;
-            first_iter = false;
+            if (FUSED) __syncwarp();  // the slots are rewritten by the next round
         }
-        // tile.comp:765-800
-        const uint32_t color_entry = prim.z & 0xffffu;
-        int tile_ctrl = (int)((prim.z >> 16) & 0xffu);
-        const int backdrop = (int)prim.z >> 24;
-        const int alpha = (int)prim.y;
-        const uint8_t *mask = nullptr;
-        if (alpha >= 0) {
-            if ((uint32_t)alpha < b.mask_capacity) mask = b.masks + (size_t)alpha * 256;
-        } else {
-            if (backdrop != 0 && (tile_ctrl & 0x2) && (abs(backdrop) & 1) == 0) continue;  // tile.comp:786-792
-            tile_ctrl &= ~0x3;
-        }
-        const int mask_ctrl = tile_ctrl & 0x3;
-        uint2 mask8 = make_uint2(0xffffffffu, 0xffffffffu);
-        if (mask_ctrl != 0 && mask) mask8 = __ldg(reinterpret_cast<const uint2 *>(mask + row * 16 + x0));
-        Paint pc;
-        if (color_entry < p.n_paints) {
-            pc.base = __ldg(&p.paints[color_entry].base);
-            if (!SOLID) {
-                pc.m0 = __ldg(&p.paints[color_entry].m0);
-                pc.m1 = __ldg(&p.paints[color_entry].m1);
-                pc.fp0 = __ldg(&p.paints[color_entry].fp0);
-                pc.fp1 = __ldg(&p.paints[color_entry].fp1);
-                pc.ctrl = __ldg(&p.paints[color_entry].ctrl);
+
+        if (uniform) {
+            const uint32_t px = pack_rgba8(dest_u);
+            if (interior) {  // 2 x 16-byte stores per lane: row lane >> 1, pixels (lane & 1) * 8 .. + 7
+                uint4 *d = reinterpret_cast<uint4 *>(tg.pixels + (size_t)(tile_y * TILE + (int)(lane >> 1)) * tg.pitch) +
+                           (tile_x * 4 + (int)(lane & 1u) * 2);
+                d[0] = make_uint4(px, px, px, px);
+                d[1] = make_uint4(px, px, px, px);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; q++)
+                    if (gx < tg.width && gy0 + ROW(q) < tg.height)
+                        *reinterpret_cast<uint32_t *>(px0 + (size_t)ROW(q) * tg.pitch) = px;
             }
-        } else {
-            pc.base = pc.m0 = pc.m1 = pc.fp0 = pc.fp1 = make_float4(0.f, 0.f, 0.f, 0.f);
-            pc.ctrl = 0;
+            continue;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            float mask_alpha = 1.0f;
-            if (mask_ctrl != 0) {  // sampleMask, tile.comp:586-607 (backdrop is 0 for alpha tiles)
-                const uint32_t m = k < 4 ? mask8.x : mask8.y;
-                float cov = (float)((m >> (8 * (k & 3))) & 0xffu) * (1.0f / 255.0f);
-                if (mask_ctrl & 0x1) cov = fabsf(cov);
-                else cov = 1.0f - fabsf(1.0f - glsl_mod(cov, 2.0f));
-                mask_alpha = fminf(mask_alpha, cov);
-            }
-            const float4 src = shade<SOLID>(pc, cs, (float)(gx0 + k) + 0.5f, fragy, mask_alpha, (float)tg.width,
-                                            (float)tg.height);
-            const float ia = 1.0f - src.w;  // tile.comp:841
-            dest[k].x = dest[k].x * ia + src.x;
-            dest[k].y = dest[k].y * ia + src.y;
-            dest[k].z = dest[k].z * ia + src.z;
-            dest[k].w = dest[k].w * ia + src.w;
-        }
-    }
-    if (!row_ok) return;
-    if (gx0 + 7 < tg.width) {
-        reinterpret_cast<uint4 *>(dst)[0] =
-            make_uint4(pack_rgba8(dest[0]), pack_rgba8(dest[1]), pack_rgba8(dest[2]), pack_rgba8(dest[3]));
-        reinterpret_cast<uint4 *>(dst)[1] =
-            make_uint4(pack_rgba8(dest[4]), pack_rgba8(dest[5]), pack_rgba8(dest[6]), pack_rgba8(dest[7]));
-    } else {
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (gx0 + k < tg.width) dst[k] = pack_rgba8(dest[k]);
+        for (int q = 0; q < 8; q++)
+            if (interior || (gx < tg.width && gy0 + ROW(q) < tg.height))
+                *reinterpret_cast<uint32_t *>(px0 + (size_t)ROW(q) * tg.pitch) = pack_rgba8(dest[q]);
     }
 }
+
+#undef ROW
 
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
                              const float clear_color[4], cudaStream_t s) {
     if (b.fb_tw <= 0 || b.fb_th <= 0) return cudaSuccess;
     const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
-    const unsigned grid = (n_fb + COMPOSITE_WARPS - 1) / COMPOSITE_WARPS;
+    const unsigned grid = (n_fb + CT_TILES - 1) / CT_TILES;
     const float4 cc = make_float4(clear_color[0], clear_color[1], clear_color[2], clear_color[3]);
-    if (p.all_solid) k_composite<true><<<grid, COMPOSITE_WARPS * 32, 0, s>>>(b, p, t, clear, cc);
-    else k_composite<false><<<grid, COMPOSITE_WARPS * 32, 0, s>>>(b, p, t, clear, cc);
+    const int threads = CT_WARPS * 32;
+    if (p.fused) {
+        if (p.all_solid) k_composite<true, true><<<grid, threads, 0, s>>>(b, p, t, clear, cc);
+        else k_composite<false, true><<<grid, threads, 0, s>>>(b, p, t, clear, cc);
+    } else {
+        if (p.all_solid) k_composite<true, false><<<grid, threads, 0, s>>>(b, p, t, clear, cc);
+        else k_composite<false, false><<<grid, threads, 0, s>>>(b, p, t, clear, cc);
+    }
     return cudaGetLastError();
 }
 

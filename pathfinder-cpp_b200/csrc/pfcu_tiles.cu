@@ -72,38 +72,58 @@ cudaError_t launch_init(const BatchView &b, cudaStream_t s) {
 // ------------------------------------------------------------------------------------------------ scan
 
 constexpr unsigned long long FLAG_AGGREGATE = 1ull << 62, FLAG_PREFIX = 2ull << 62, FLAG_MASK = 3ull << 62;
+constexpr unsigned long long VALUE_MASK = ~FLAG_MASK;
 
-// WHICH 0: fills per dense tile (tile_word & 0xffffff -> fill_cursor), 1: list entries per framebuffer tile
-// (fb[t].count -> fb[t].begin).
+// WHICH 0: per dense tile, fills (tile_word & 0xffffff -> fill_cursor) and, in the same pass, tiles that have fills
+//          (-> alpha_rank: the tile's mask slot is first_alpha + rank, so propagate needs no allocation atomics).
+//          The scanned value packs both: fills in bits 0-31, tiles in bits 32-55.
+// WHICH 1: list entries per framebuffer tile (fb[t].count -> fb[t].begin).
 template <int WHICH>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
     const uint32_t n = WHICH == 0 ? b.tile_count : (uint32_t)(b.fb_tw * b.fb_th);
     unsigned long long *desc = b.scan_desc[WHICH];
-    __shared__ uint32_t s_tile, s_warp[SCAN_THREADS / 32], s_prefix;
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_warp[SCAN_THREADS / 32], s_prefix;
     if (threadIdx.x == 0) s_tile = atomicAdd(&b.counters->scan_ticket[WHICH], 1u);  // forward progress: tiles start in order
     __syncthreads();
     const uint32_t tile = s_tile;
     const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t v[SCAN_ITEMS];
-    uint32_t sum = 0;
+    unsigned long long v[SCAN_ITEMS];
+    unsigned long long sum = 0;
+    uint32_t raw[SCAN_ITEMS];
+    if (WHICH == 0 && base + SCAN_ITEMS <= n) {  // 2 x 16-byte loads (SCAN_ITEMS == 8, base is a multiple of 8)
+        const uint4 r0 = *reinterpret_cast<const uint4 *>(&b.tile_word[base]);
+        const uint4 r1 = *reinterpret_cast<const uint4 *>(&b.tile_word[base + 4]);
+        raw[0] = r0.x; raw[1] = r0.y; raw[2] = r0.z; raw[3] = r0.w;
+        raw[4] = r1.x; raw[5] = r1.y; raw[6] = r1.z; raw[7] = r1.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            raw[k] = 0;
+            if (base + k < n) raw[k] = WHICH == 0 ? b.tile_word[base + k] : b.fb[base + k].count;
+        }
+    }
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
-        uint32_t x = 0;
-        if (base + k < n) x = WHICH == 0 ? (b.tile_word[base + k] & 0x00ffffffu) : b.fb[base + k].count;
+        unsigned long long x = raw[k];
+        if (WHICH == 0) {
+            x &= 0x00ffffffull;
+            if (x) x |= 1ull << 32;
+        }
         v[k] = sum;  // exclusive within the thread
         sum += x;
     }
     // block exclusive scan of the per-thread sums
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t incl = sum;
+    unsigned long long incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= (unsigned)d) incl += t;
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    uint32_t warp_off = 0, block_total = 0;
+    unsigned long long warp_off = 0, block_total = 0;
 #pragma unroll
     for (int w = 0; w < SCAN_THREADS / 32; w++) {
         if (w < (int)warp) warp_off += s_warp[w];
@@ -115,7 +135,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
             const unsigned long long d = (tile == 0 ? FLAG_PREFIX : FLAG_AGGREGATE) | block_total;
             atomicExch(&desc[tile], d);
         }
-        uint32_t prefix = 0;
+        unsigned long long prefix = 0;
         if (tile > 0) {
             int look = (int)tile - 1;
             while (true) {
@@ -129,35 +149,62 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
                 const unsigned is_prefix = __ballot_sync(0xffffffffu, (d & FLAG_MASK) == FLAG_PREFIX);
                 // add everything up to and including the closest PREFIX descriptor (lane 0 is the closest tile)
                 const int first = __ffs(is_prefix) - 1;  // -1: all 32 predecessors only published aggregates
-                uint32_t contrib = (idx >= 0 && (first < 0 || (int)lane <= first)) ? (uint32_t)(d & 0xffffffffull) : 0u;
+                unsigned long long contrib = (idx >= 0 && (first < 0 || (int)lane <= first)) ? (d & VALUE_MASK) : 0ull;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
                 prefix += contrib;
                 if (first >= 0) break;
                 look -= 32;
             }
-            if (lane == 0) atomicExch(&desc[tile], FLAG_PREFIX | (unsigned long long)(prefix + block_total));
+            if (lane == 0) atomicExch(&desc[tile], FLAG_PREFIX | (prefix + block_total));
         }
         if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
-    const uint32_t off = s_prefix + warp_off + (incl - sum);
+    const unsigned long long off = s_prefix + warp_off + (incl - sum);
+    if (WHICH == 0 && base + SCAN_ITEMS <= n) {
+        uint32_t f[SCAN_ITEMS], a[SCAN_ITEMS];
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        if (base + k < n) {
-            if (WHICH == 0) b.fill_cursor[base + k] = off + v[k];
-            else b.fb[base + k].begin = off + v[k];
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            const unsigned long long o = off + v[k];
+            f[k] = (uint32_t)o;
+            a[k] = (uint32_t)(o >> 32);
+        }
+        *reinterpret_cast<uint4 *>(&b.fill_cursor[base]) = make_uint4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<uint4 *>(&b.fill_cursor[base + 4]) = make_uint4(f[4], f[5], f[6], f[7]);
+        *reinterpret_cast<uint4 *>(&b.alpha_rank[base]) = make_uint4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<uint4 *>(&b.alpha_rank[base + 4]) = make_uint4(a[4], a[5], a[6], a[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            if (base + k < n) {
+                const unsigned long long o = off + v[k];
+                if (WHICH == 0) {
+                    b.fill_cursor[base + k] = (uint32_t)o;
+                    b.alpha_rank[base + k] = (uint32_t)(o >> 32);
+                } else {
+                    b.fb[base + k].begin = (uint32_t)o;
+                }
+            }
         }
     }
     // the last tile owns the grand total
     if (tile == scan_tiles_for(n) - 1 && threadIdx.x == 0) {
-        const uint32_t total = s_prefix + block_total;
+        const unsigned long long total = s_prefix + block_total;
         if (WHICH == 0) {
-            b.counters->n_fills = total;
-            if (total > b.fill_capacity) atomicOr(&b.counters->overflow, (uint32_t)OVF_FILLS);
+            const uint32_t fills = (uint32_t)total, alphas = (uint32_t)(total >> 32);
+            b.counters->n_fills = fills;
+            b.counters->n_alpha = alphas;
+            // batches of a frame are stream-ordered: plain read-modify-write of the frame-global mask slot counter
+            const uint32_t first = b.counters->first_alpha;
+            *b.frame_alpha_counter = first + alphas;
+            uint32_t ovf = 0;
+            if (fills > b.fill_capacity) ovf |= OVF_FILLS;
+            if (first + alphas > b.mask_capacity || alphas > b.alpha_capacity) ovf |= OVF_ALPHA;
+            if (ovf) atomicOr(&b.counters->overflow, ovf);
         } else {
-            b.counters->n_list_entries = total;
-            if (total > b.prim_capacity) atomicOr(&b.counters->overflow, (uint32_t)OVF_LIST);
+            b.counters->n_list_entries = (uint32_t)total;
+            if ((uint32_t)total > b.prim_capacity) atomicOr(&b.counters->overflow, (uint32_t)OVF_LIST);
         }
     }
 }
@@ -195,7 +242,8 @@ cudaError_t launch_fill_scatter(const BatchView &b, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------ propagate
 
-// One warp per tile column; lanes are 32 consecutive rows (propagate.comp:95-216, tiler.cpp:369-439).
+// One warp per tile column; lanes are 32 consecutive rows (propagate.comp:95-216, tiler.cpp:369-439). No atomic
+// returns a value: mask slots come from the scan, list positions are taken later by the list scatter.
 __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
     const uint32_t col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31;
@@ -207,7 +255,6 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
     const int w = rect.z - rect.x, h = rect.w - rect.y;
     if (w <= 0 || h <= 0 || tx >= w) return;
     const pfcu_tile_path_info info = b.tpi[path];
-    const uint32_t ctrl_base = (uint32_t)info.color | ((uint32_t)info.ctrl << 16);
     const int gx = tx + rect.x;
     const uint32_t z_write_path = __ldg(&b.meta[path].z_write);
     const uint32_t clip_index = __ldg(&b.meta[path].clip_path_index);
@@ -238,30 +285,33 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
         }
         const int cur = carry + incl - delta;
         carry += __shfl_sync(0xffffffffu, incl, 31);
+        if (!valid) continue;
 
-        const bool have_mask = (word & 0x00ffffffu) != 0;
+        const uint32_t fill_count = word & 0x00ffffffu;
+        const bool have_mask = fill_count != 0;
         int backdrop = (int)(int8_t)cur;  // int8_t(backdrops[column]), tiler.cpp:394
         int backdrop9 = backdrop;
-        bool need_new = valid && have_mask;
+        bool need_new = have_mask;
         int alpha = -1, clip_alpha = -1;
         const int gy = ty + rect.y;
-        if (has_clip && valid) {
+        if (has_clip) {
             const bool inside = clip_ok && gx >= crect.x && gx < crect.z && gy >= crect.y && gy < crect.w;
             if (inside) {
-                const TileState ct = b.clip_tile_state[ctile_offset + (uint32_t)(gx - crect.x) +
-                                                       (uint32_t)(crect.z - crect.x) * (uint32_t)(gy - crect.y)];
-                if (ct.alpha >= 0) {
+                const uint4 ct = *reinterpret_cast<const uint4 *>(
+                    &b.clip_tile_state[ctile_offset + (uint32_t)(gx - crect.x) +
+                                       (uint32_t)(crect.z - crect.x) * (uint32_t)(gy - crect.y)]);
+                if ((int)ct.x >= 0) {
                     if (have_mask) {  // tiler.cpp:403-414 / propagate.comp:144-147
-                        clip_alpha = ct.alpha;
+                        clip_alpha = (int)ct.x;
                         backdrop9 = 0;
                     } else if (backdrop != 0) {  // tiler.cpp:415-420 / propagate.comp:149-154
-                        alpha = ct.alpha;
+                        alpha = (int)ct.x;
                         need_new = false;
-                        backdrop9 = (int)(int8_t)((ct.packed >> 16) & 0xffu);
+                        backdrop9 = (int)(int8_t)((ct.y >> 16) & 0xffu);
                     } else {
                         need_new = false;
                     }
-                } else if ((int8_t)(ct.packed & 0xffu) == 0) {  // blank clip tile: tiler.cpp:421-425
+                } else if ((int8_t)(ct.y & 0xffu) == 0) {  // blank clip tile: tiler.cpp:421-425
                     backdrop = 0;
                     backdrop9 = 0;
                     need_new = false;
@@ -272,62 +322,33 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
                 need_new = false;
             }
         }
-        // alpha tile allocation (propagate.comp:178-183): one atomic per warp
-        const unsigned need_mask = __ballot_sync(0xffffffffu, need_new);
-        if (need_mask) {
-            uint32_t base = 0;
-            const int leader = __ffs(need_mask) - 1;
-            if ((int)lane == leader) base = atomicAdd(b.frame_alpha_counter, (uint32_t)__popc(need_mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (need_new) {
-                const uint32_t id = base + (uint32_t)__popc(need_mask & ((1u << lane) - 1u));
-                const uint32_t local = id - first_alpha;
-                if (id < b.mask_capacity && local < b.alpha_capacity) {
-                    AlphaTile at;
-                    at.tile_index = ti;
-                    at.clip_alpha = clip_alpha;
-                    at.packed = ((uint32_t)backdrop & 0xffu) | ((info.ctrl & 0x1) ? 0x100u : 0u);
-                    at.fill_count = word & 0x00ffffffu;
-                    *reinterpret_cast<uint4 *>(&b.alpha_tiles[local]) = *reinterpret_cast<const uint4 *>(&at);
-                    alpha = (int)id;
-                } else {
-                    atomicOr(&b.counters->overflow, (uint32_t)OVF_ALPHA);
-                    need_new = false;
-                }
+        // alpha tile allocation (propagate.comp:178-183): the slot was fixed by the scan over tiles with fills
+        if (have_mask) {
+            const uint32_t local = b.alpha_rank[ti];
+            const uint32_t id = first_alpha + local;
+            if (id < b.mask_capacity && local < b.alpha_capacity) {
+                // a tile whose fills the clip made invisible keeps its slot but is marked so that fill skips it
+                *reinterpret_cast<uint4 *>(&b.alpha_tiles[local]) =
+                    make_uint4(need_new ? ti : 0xffffffffu, (uint32_t)clip_alpha,
+                               ((uint32_t)backdrop & 0xffu) | ((info.ctrl & 0x1) ? 0x100u : 0u), fill_count);
+                if (need_new) alpha = (int)id;
+            } else {
+                need_new = false;  // the scan flagged OVF_ALPHA: the frame is replayed with more slots
             }
         }
-        const bool in_fb = valid && gx >= 0 && gx < b.fb_tw && gy >= 0 && gy < b.fb_th;
+        const bool in_fb = gx >= 0 && gx < b.fb_tw && gy >= 0 && gy < b.fb_th;
         const uint32_t map = in_fb ? (uint32_t)gy * (uint32_t)b.fb_tw + (uint32_t)gx : 0u;
         const bool listed = (backdrop != 0 || alpha >= 0) && in_fb;
-        if (valid) {
-            TileState st;
-            st.alpha = alpha;
-            st.packed = ((uint32_t)backdrop & 0xffu) | (((uint32_t)delta & 0xffu) << 8) |
-                        (((uint32_t)backdrop9 & 0xffu) << 16) | (listed ? 1u << 24 : 0u) | (need_new ? 1u << 25 : 0u) |
-                        (((uint32_t)info.ctrl & 0x3u) << 26);
-            b.tile_state[ti] = st;
-        }
+        const uint32_t packed = ((uint32_t)backdrop & 0xffu) | (((uint32_t)delta & 0xffu) << 8) |
+                                (((uint32_t)backdrop9 & 0xffu) << 16) | (listed ? 1u << 24 : 0u) |
+                                (need_new ? 1u << 25 : 0u) | (((uint32_t)info.ctrl & 0x3u) << 26);
+        *reinterpret_cast<uint4 *>(&b.tile_state[ti]) = make_uint4((uint32_t)alpha, packed, path, (uint32_t)clip_alpha);
         // z-buffer: propagate.comp:190-206 (even-odd tiles with an even backdrop are invisible, not occluders)
         bool z_write = z_write_path != 0;
         if (backdrop != 0 && even_odd && (abs(backdrop) & 1) == 0) z_write = false;
         if (in_fb && z_write && backdrop != 0 && alpha < 0) atomicMax(&b.fb[map].z, (int)ti);
-        // list membership (propagate.comp:209-212): rank inside the framebuffer tile + a compact record
-        const unsigned listed_mask = __ballot_sync(0xffffffffu, listed);
-        if (listed_mask) {
-            uint32_t base = 0;
-            const int leader = __ffs(listed_mask) - 1;
-            if ((int)lane == leader) base = atomicAdd(&b.counters->n_listed, (uint32_t)__popc(listed_mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (listed) {
-                const uint32_t at = base + (uint32_t)__popc(listed_mask & ((1u << lane) - 1u));
-                const uint32_t rank = atomicAdd(&b.fb[map].count, 1u);
-                if (at < b.prim_capacity) {
-                    *reinterpret_cast<uint4 *>(&b.listed[at]) =
-                        make_uint4(ti, (uint32_t)alpha, ctrl_base | (((uint32_t)backdrop & 0xffu) << 24), map);
-                    b.listed_rank[at] = rank;
-                }
-            }
-        }
+        // list membership (propagate.comp:209-212): count now, place after the scan (fire-and-forget reduction)
+        if (listed) atomicAdd(&b.fb[map].count, 1u);
     }
 }
 
@@ -340,18 +361,41 @@ cudaError_t launch_propagate(const BatchView &b, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------ list scatter
 
+// One thread per dense tile (coalesced 16-byte state loads): a listed tile takes the next free position of its
+// framebuffer tile's range and writes everything the composite kernel needs about it as one 32-byte record.
 __global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
-    const uint32_t n = min(b.counters->n_listed, b.prim_capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint4 r = *reinterpret_cast<const uint4 *>(&b.listed[i]);
-        const uint32_t pos = b.fb[r.w].begin + b.listed_rank[i];
-        if (pos < b.prim_capacity) *reinterpret_cast<uint4 *>(&b.prims[pos]) = make_uint4(r.x, r.y, r.z, 0u);
+    for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < b.tile_count; ti += gridDim.x * blockDim.x) {
+        const uint4 st = *reinterpret_cast<const uint4 *>(&b.tile_state[ti]);
+        if (!(st.y & (1u << 24))) continue;
+        const uint32_t path = st.z;
+        const int4 rect = __ldg(reinterpret_cast<const int4 *>(&b.meta[path].tile_rect[0]));
+        const uint32_t local = ti - __ldg(&b.meta[path].tile_offset);
+        const uint32_t w = (uint32_t)(rect.z - rect.x);
+        const int gx = rect.x + (int)(local % w), gy = rect.y + (int)(local / w);
+        const uint32_t map = (uint32_t)gy * (uint32_t)b.fb_tw + (uint32_t)gx;
+        const uint2 pi = __ldg(reinterpret_cast<const uint2 *>(&b.tpi[path]) + 1);  // first_tile | color, ctrl, backdrop
+        const uint32_t ctrl_word = (pi.y & 0x00ffffffu) | ((st.y & 0xffu) << 24);
+        const uint32_t pos = __ldg(&b.fb[map].begin) + atomicAdd(&b.fb[map].cursor, 1u);
+        if (pos >= b.prim_capacity) continue;
+        const bool owns = (st.y & (1u << 25)) != 0;
+        uint32_t fill_begin = 0, fill_count = 0;
+        if (owns) {
+            fill_count = b.tile_word[ti] & 0x00ffffffu;
+            const uint32_t end = b.fill_cursor[ti];
+            fill_begin = end >= fill_count ? end - fill_count : 0u;
+        }
+        uint4 *out = reinterpret_cast<uint4 *>(&b.prims[pos]);
+        out[0] = make_uint4(ti, st.x, ctrl_word, fill_begin);
+        out[1] = make_uint4(fill_count, st.w, owns ? (uint32_t)PRIM_OWNS_MASK : 0u, 0u);
     }
 }
 
 cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s) {
-    if (!b.column_count) return cudaSuccess;
-    k_list_scatter<<<sm_count() * 8, 256, 0, s>>>(b);
+    if (!b.column_count || !b.tile_count) return cudaSuccess;
+    int grid = (int)((b.tile_count + 255) / 256);
+    const int cap = sm_count() * 8;
+    if (grid > cap) grid = cap;
+    k_list_scatter<<<grid, 256, 0, s>>>(b);
     return cudaGetLastError();
 }
 

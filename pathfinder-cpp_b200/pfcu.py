@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpfcu.so")
+# PFCU_LIB selects an experimental build of the same sources (tools/variants.sh); the default is the product library
+LIB_PATH = os.environ.get("PFCU_LIB") or os.path.join(_HERE, "lib", "libpfcu.so")
 NONE = 0xFFFFFFFF
 
 EXPORTS = [
@@ -19,7 +20,7 @@ EXPORTS = [
     "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
     "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
     "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
-    "pfcu_get_stage_times", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
+    "pfcu_get_stage_times", "pfcu_set_option", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
 ]
 STAGES = ["init", "dice", "bin", "scan_tiles", "fill_scatter", "propagate", "scan_fb", "list_scatter", "fill",
           "composite"]
@@ -90,6 +91,7 @@ def lib():
         L.pfcu_read_tile_lists.argtypes = [vp, u32, vp, vp]
         L.pfcu_read_tile_lists.restype = C.c_int64
         L.pfcu_read_mask.argtypes = [vp, u32, vp]
+        L.pfcu_set_option.argtypes = [vp, i32, i32]
         L.pfcu_set_profiling.argtypes = [vp, i32]
         L.pfcu_get_stage_times.argtypes = [vp, vp, i32]
         L.pfcu_graph_capture.argtypes = [vp]
@@ -213,7 +215,11 @@ class Renderer:
         _check(L.pfcu_end_frame(self.h, C.byref(st)))
         return st.as_dict()
 
-    # -- measurement
+    # -- options / measurement
+    def set_fused(self, enabled):
+        """PFCU_OPT_FUSED_FILL: draw-batch coverage computed inside the tile kernel (default) or by a separate fill."""
+        _check(self.L.pfcu_set_option(self.h, 1, int(bool(enabled))))
+
     def set_profiling(self, enabled):
         _check(self.L.pfcu_set_profiling(self.h, int(bool(enabled))))
 
