@@ -101,7 +101,7 @@ struct BatchSlot {
     pfcu_batch_desc desc{};
     PinnedBuf host_meta;  // the four metadata vectors, packed, kept for replay
     size_t off_backdrops = 0, off_meta = 0, off_dice = 0, off_tpi = 0, meta_bytes = 0;
-    DevBuf dev_meta, tile_word, fill_cursor, alpha_rank, col_backdrop, tile_state, lines, line_meta, staging, fills, fb,
+    DevBuf dev_meta, tile_word, fill_cursor, alpha_rank, col_backdrop, tile_state, lines, line_meta, staging, fills, fb, long_lines,
         prims, alpha_tiles, scan_desc0, scan_desc1;
     uint32_t line_cap = 0, fill_cap = 0, staging_cap = 0;
     BatchView view{};
@@ -225,6 +225,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     CUDA_TRY(s.tile_state.ensure(D * sizeof(TileState)));
     CUDA_TRY(s.lines.ensure((size_t)s.line_cap * sizeof(float4)));
     CUDA_TRY(s.line_meta.ensure((size_t)s.line_cap * sizeof(uint2)));
+    CUDA_TRY(s.long_lines.ensure((size_t)s.line_cap * 4));
     CUDA_TRY(s.staging.ensure((size_t)s.staging_cap * sizeof(StagedFill)));
     CUDA_TRY(s.fills.ensure((size_t)s.fill_cap * sizeof(uint2)));
     CUDA_TRY(s.alpha_rank.ensure(D * 4));
@@ -264,6 +265,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.tile_state = s.tile_state.as<TileState>();
     v.lines = s.lines.as<float4>();
     v.line_meta = s.line_meta.as<uint2>();
+    v.long_lines = s.long_lines.as<uint32_t>();
     v.line_capacity = s.line_cap;
     v.staging = s.staging.as<StagedFill>();
     v.staging_capacity = s.staging_cap;
@@ -317,7 +319,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     LAUNCH_STAGE(PFCU_STAGE_SCAN_FB, launch_scan_fb(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_LIST_SCATTER, launch_list_scatter(v, c->stream));
     if (run_fill) LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, c->stream));
-    c->launches += run_fill ? 9 : 8;
+    c->launches += run_fill ? 10 : 9;
     c->in_flight = true;
     return PFCU_OK;
 }
@@ -408,7 +410,7 @@ void pfcu_destroy(pfcu_ctx *c) {
     for (auto &s : c->slots) {
         s.host_meta.release();
         for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
-                          &s.line_meta, &s.staging, &s.fills, &s.fb, &s.alpha_rank, &s.prims,
+                          &s.line_meta, &s.long_lines, &s.staging, &s.fills, &s.fb, &s.alpha_rank, &s.prims,
                           &s.alpha_tiles, &s.scan_desc0, &s.scan_desc1})
             b->release();
     }

@@ -29,7 +29,8 @@ struct BatchCounters {
     uint32_t overflow;        // OverflowBits
     uint32_t scan_ticket[2];  // dynamic tile ids for the two look-back scans
     uint32_t n_list_entries;  // total list entries (from the scan over framebuffer tiles)
-    uint32_t pad[7];
+    uint32_t n_long;          // lines queued for the long-line bin kernel
+    uint32_t pad[6];
 };
 static_assert(sizeof(BatchCounters) == 64, "BatchCounters");
 
@@ -115,7 +116,8 @@ struct BatchView {
     int32_t *col_backdrop;  // [column_count]
     TileState *tile_state;  // [tile_count]
     float4 *lines;          // [line_capacity] clipped lines
-    uint2 *line_meta;       // [line_capacity] x: path index, y: first staging slot
+    uint2 *line_meta;       // [line_capacity] x: path index, y: first staging slot (long lines only)
+    uint32_t *long_lines;   // [line_capacity] indices of the lines whose tile walk is shared by a warp
     uint32_t line_capacity;
     StagedFill *staging;    // [staging_capacity]
     uint32_t staging_capacity;

@@ -429,7 +429,18 @@ __device__ __forceinline__ uint32_t walk_step_emit(const BatchView &b, const Pat
     return used;
 }
 
-constexpr uint32_t BIN_LONG_STEPS = 12;  // walks longer than this are shared by the warp
+constexpr uint32_t BIN_LONG_STEPS = 12;  // walks longer than this go to the long-line kernel, one warp per line
+constexpr int BIN_CHAIN = 1032;          // crossings per axis the long-line kernel keeps in shared memory (16 K pixels)
+constexpr int BIN_LONG_WARPS = 4;
+
+__device__ __forceinline__ uint32_t walk_steps(const float4 &ln) {
+    // the walk visits |dx| + |dy| + 1 tiles (tiler.cpp:191-278) and adds at most two fills per tile
+    const long long tx0 = (int)floorf(ln.x * 0.0625f), ty0 = (int)floorf(ln.y * 0.0625f);
+    const long long tx1 = (int)floorf(ln.z * 0.0625f), ty1 = (int)floorf(ln.w * 0.0625f);
+    long long d = llabs(tx1 - tx0) + llabs(ty1 - ty0) + 1;
+    if (d > MAX_DDA_STEPS) d = MAX_DDA_STEPS;
+    return (uint32_t)d;
+}
 
 __global__ void __launch_bounds__(128) k_bin(BatchView b) {
     const uint32_t n_lines = min(b.counters->n_lines, b.line_capacity);
@@ -443,12 +454,7 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
         if (active) {
             ln = b.lines[i];
             path = b.line_meta[i].x;
-            // the walk visits |dx| + |dy| + 1 tiles (tiler.cpp:191-278) and adds at most two fills per tile
-            const long long tx0 = (int)floorf(ln.x * 0.0625f), ty0 = (int)floorf(ln.y * 0.0625f);
-            const long long tx1 = (int)floorf(ln.z * 0.0625f), ty1 = (int)floorf(ln.w * 0.0625f);
-            long long d = llabs(tx1 - tx0) + llabs(ty1 - ty0) + 1;
-            if (d > MAX_DDA_STEPS) d = MAX_DDA_STEPS;
-            steps = (uint32_t)d;
+            steps = walk_steps(ln);
         }
         // staging slots for the whole warp: one atomic
         const uint32_t slots = 2u * steps;
@@ -462,89 +468,180 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
             atomicOr(&b.counters->overflow, (uint32_t)OVF_STAGING);
             active = false;
         }
+        // long walks are queued for k_bin_long (their slots are already reserved)
         const bool is_long = active && steps > BIN_LONG_STEPS;
-        if (active && !is_long) {
-            const PathTiles pt = load_path_tiles(b, path);
-            Walk w;
-            w.init(ln.x, ln.y, ln.z, ln.w);
-            float cur_x = ln.x, cur_y = ln.y;
-            int last_dir = 0;  // 0 none, 1 X, 2 Y
-            uint32_t slot = slot0;
-            const uint32_t slot_end = slot0 + slots;
-            for (uint32_t s = 0;; s++) {
-                int next_dir;
-                float next_t;
-                w.decide(next_dir, next_t);
-                if (s >= steps) {  // the walk left the |dx|+|dy|+1 envelope (only with non-finite arithmetic)
-                    atomicOr(&b.counters->overflow, (uint32_t)OVF_DDA);
-                    break;
-                }
-                const float nx = w.l0 + w.vx * next_t, ny = w.l1 + w.vy * next_t;  // LineSegmentF::sample
-                slot += walk_step_emit(b, pt, w, cur_x, cur_y, nx, ny, w.tcx, w.tcy, last_dir, next_dir, slot);
-                if (next_dir == 0) break;
-                w.advance(next_dir);
-                cur_x = nx;
-                cur_y = ny;
-                last_dir = next_dir;
+        const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);
+        if (long_mask) {
+            uint32_t lbase = 0;
+            const int leader = __ffs(long_mask) - 1;
+            if ((int)lane == leader) lbase = atomicAdd(&b.counters->n_long, (uint32_t)__popc(long_mask));
+            lbase = __shfl_sync(0xffffffffu, lbase, leader);
+            if (is_long) {
+                b.line_meta[i].y = slot0;
+                b.long_lines[lbase + (uint32_t)__popc(long_mask & ((1u << lane) - 1u))] = i;  // capacity == line capacity
             }
-            for (; slot < slot_end; slot++) b.staging[slot].tile = 0xffffffffu;  // unused slots
         }
-        // long walks: one at a time, all 32 lanes
-        unsigned long_mask = __ballot_sync(0xffffffffu, is_long);
-        while (long_mask) {
-            const int src = __ffs(long_mask) - 1;
-            long_mask &= long_mask - 1;
-            const float a0 = __shfl_sync(0xffffffffu, ln.x, src), a1 = __shfl_sync(0xffffffffu, ln.y, src);
-            const float a2 = __shfl_sync(0xffffffffu, ln.z, src), a3 = __shfl_sync(0xffffffffu, ln.w, src);
-            const uint32_t lpath = __shfl_sync(0xffffffffu, path, src);
-            const uint32_t lslot0 = __shfl_sync(0xffffffffu, slot0, src), lsteps = __shfl_sync(0xffffffffu, steps, src);
-            const PathTiles pt = load_path_tiles(b, lpath);
-            Walk w;
-            w.init(a0, a1, a2, a3);
-            int last_dir = 0;
-            float prev_t = 0.0f;
-            uint32_t s = 0;
-            bool done = false;
-            while (!done) {
-                // cheap part, replayed by every lane: 32 steps of the t_max chain; lane k keeps step s0 + k
-                int my_dir = -1, my_last = 0, my_tcx = 0, my_tcy = 0;
-                float my_t = 0.0f, my_prev_t = 0.0f;
-                const uint32_t s0 = s;
-#pragma unroll 4
-                for (int k = 0; k < 32; k++) {
-                    int next_dir;
-                    float next_t;
-                    w.decide(next_dir, next_t);
-                    if (s >= lsteps) {
-                        if (lane == 0) atomicOr(&b.counters->overflow, (uint32_t)OVF_DDA);
-                        done = true;
-                        break;
-                    }
-                    if ((int)lane == k) {
-                        my_dir = next_dir; my_last = last_dir; my_tcx = w.tcx; my_tcy = w.tcy;
-                        my_t = next_t; my_prev_t = prev_t;
-                    }
-                    s++;
-                    if (next_dir == 0) {
-                        done = true;
-                        break;
-                    }
-                    w.advance(next_dir);
-                    prev_t = next_t;
-                    last_dir = next_dir;
-                }
-                // expensive part: one step per lane
-                if (my_dir >= 0) {
-                    const uint32_t my_s = s0 + lane;
-                    const float nx = w.l0 + w.vx * my_t, ny = w.l1 + w.vy * my_t;
-                    const float cx = my_s == 0 ? a0 : w.l0 + w.vx * my_prev_t, cy = my_s == 0 ? a1 : w.l1 + w.vy * my_prev_t;
-                    const uint32_t slot = lslot0 + 2u * my_s;
-                    const uint32_t used = walk_step_emit(b, pt, w, cx, cy, nx, ny, my_tcx, my_tcy, my_last, my_dir, slot);
-                    for (uint32_t u = used; u < 2; u++) b.staging[slot + u].tile = 0xffffffffu;
-                }
+        if (!active || is_long) continue;
+        const PathTiles pt = load_path_tiles(b, path);
+        Walk w;
+        w.init(ln.x, ln.y, ln.z, ln.w);
+        float cur_x = ln.x, cur_y = ln.y;
+        int last_dir = 0;  // 0 none, 1 X, 2 Y
+        uint32_t slot = slot0;
+        const uint32_t slot_end = slot0 + slots;
+        for (uint32_t s = 0;; s++) {
+            int next_dir;
+            float next_t;
+            w.decide(next_dir, next_t);
+            if (s >= steps) {  // the walk left the |dx|+|dy|+1 envelope (only with non-finite arithmetic)
+                atomicOr(&b.counters->overflow, (uint32_t)OVF_DDA);
+                break;
             }
-            // steps the walk never reached
-            for (uint32_t u = lslot0 + 2u * s + lane; u < lslot0 + 2u * lsteps; u += 32) b.staging[u].tile = 0xffffffffu;
+            const float nx = w.l0 + w.vx * next_t, ny = w.l1 + w.vy * next_t;  // LineSegmentF::sample
+            slot += walk_step_emit(b, pt, w, cur_x, cur_y, nx, ny, w.tcx, w.tcy, last_dir, next_dir, slot);
+            if (next_dir == 0) break;
+            w.advance(next_dir);
+            cur_x = nx;
+            cur_y = ny;
+            last_dir = next_dir;
+        }
+        for (; slot < slot_end; slot++) b.staging[slot].tile = 0xffffffffu;  // unused slots
+    }
+}
+
+// Exact replay of the serial walk by a whole warp: all lanes run the cheap part (the t_max chain and the direction
+// decisions) and lane k does the expensive part of every 32nd step. Used when the crossings of a line do not fit the
+// shared-memory chains or when the merge below cannot be proven to equal the serial walk.
+__device__ __noinline__ void walk_replay(const BatchView &b, const PathTiles &pt, float a0, float a1, float a2, float a3,
+                                         uint32_t lslot0, uint32_t lsteps, unsigned lane) {
+    Walk w;
+    w.init(a0, a1, a2, a3);
+    int last_dir = 0;
+    float prev_t = 0.0f;
+    uint32_t s = 0;
+    bool done = false;
+    while (!done) {
+        int my_dir = -1, my_last = 0, my_tcx = 0, my_tcy = 0;
+        float my_t = 0.0f, my_prev_t = 0.0f;
+        const uint32_t s0 = s;
+#pragma unroll 4
+        for (int k = 0; k < 32; k++) {
+            int next_dir;
+            float next_t;
+            w.decide(next_dir, next_t);
+            if (s >= lsteps) {
+                if (lane == 0) atomicOr(&b.counters->overflow, (uint32_t)OVF_DDA);
+                done = true;
+                break;
+            }
+            if ((int)lane == k) {
+                my_dir = next_dir; my_last = last_dir; my_tcx = w.tcx; my_tcy = w.tcy;
+                my_t = next_t; my_prev_t = prev_t;
+            }
+            s++;
+            if (next_dir == 0) {
+                done = true;
+                break;
+            }
+            w.advance(next_dir);
+            prev_t = next_t;
+            last_dir = next_dir;
+        }
+        if (my_dir >= 0) {
+            const uint32_t my_s = s0 + lane;
+            const float nx = w.l0 + w.vx * my_t, ny = w.l1 + w.vy * my_t;
+            const float cx = my_s == 0 ? a0 : w.l0 + w.vx * my_prev_t, cy = my_s == 0 ? a1 : w.l1 + w.vy * my_prev_t;
+            const uint32_t slot = lslot0 + 2u * my_s;
+            const uint32_t used = walk_step_emit(b, pt, w, cx, cy, nx, ny, my_tcx, my_tcy, my_last, my_dir, slot);
+            for (uint32_t u = used; u < 2; u++) b.staging[slot + u].tile = 0xffffffffu;
+        }
+    }
+    for (uint32_t u = lslot0 + 2u * s + lane; u < lslot0 + 2u * lsteps; u += 32) b.staging[u].tile = 0xffffffffu;
+}
+
+// The order in which the serial walk consumes tile crossings: an X crossing at time a goes before a Y crossing at
+// time b_ exactly when the walk, comparing the two, steps in X (tiler.cpp:193-205).
+__device__ __forceinline__ bool x_first(float a, float b_, bool tie_x) { return a < b_ || (!(a > b_) && tie_x); }
+
+// One warp per long line. The serial walk is a merge of two monotone sequences -- the times at which the line crosses
+// vertical and horizontal tile boundaries, each built by REPEATED float addition (which is why it cannot be jumped
+// into) -- so two lanes build the sequences once (one dependent add per crossing), and then every step of the walk is
+// independent: a lane finds how many X crossings precede its step with a merge-path binary search and does the step's
+// fill conversion, atomics and stores. 32 steps of the walk per pass instead of one.
+__global__ void __launch_bounds__(BIN_LONG_WARPS * 32) k_bin_long(BatchView b) {
+    __shared__ float chain[BIN_LONG_WARPS][2][BIN_CHAIN];
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t n_long = min(b.counters->n_long, b.line_capacity);
+    const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    float *sx = chain[wib][0], *sy = chain[wib][1];
+    for (uint32_t at = warp0; at < n_long; at += n_warps) {
+        const uint32_t i = b.long_lines[at];
+        const float4 ln = b.lines[i];
+        const uint2 lm = b.line_meta[i];
+        const uint32_t steps = walk_steps(ln), slot0 = lm.y;
+        const PathTiles pt = load_path_tiles(b, lm.x);
+        Walk w;
+        w.init(ln.x, ln.y, ln.z, ln.w);
+        const uint32_t nx = (uint32_t)abs(w.to_tx - w.tcx), ny = (uint32_t)abs(w.to_ty - w.tcy);
+        if (nx + 1 > BIN_CHAIN || ny + 1 > BIN_CHAIN || nx + ny + 1 != steps) {
+            walk_replay(b, pt, ln.x, ln.y, ln.z, ln.w, slot0, steps, lane);
+            continue;
+        }
+        __syncwarp();
+        if (lane < 2) {  // sx[k] / sy[k]: t_max_x / t_max_y after k steps in that axis (tiler.cpp:271-277)
+            float t = lane ? w.t_max_y : w.t_max_x;
+            const float dt = lane ? w.t_delta_y : w.t_delta_x;
+            const uint32_t n = lane ? ny : nx;
+            float *dst = lane ? sy : sx;
+            for (uint32_t k = 0; k <= n; k++) {
+                dst[k] = t;
+                t += dt;
+            }
+        }
+        __syncwarp();
+        const bool tie_x = w.step_x > 0;
+        // The merge equals the serial walk iff the walk never steps past the last tile column / row before reaching
+        // the last tile: once in the last column it must keep stepping in Y (and vice versa).
+        const bool ok = (ny == 0 || !x_first(sx[nx], sy[ny - 1], tie_x)) && (nx == 0 || x_first(sx[nx - 1], sy[ny], tie_x));
+        if (!ok) {
+            walk_replay(b, pt, ln.x, ln.y, ln.z, ln.w, slot0, steps, lane);
+            continue;
+        }
+        const uint32_t last = nx + ny;
+        for (uint32_t s0 = 0; s0 <= last; s0 += 32) {
+            const uint32_t s = s0 + lane;
+            if (s > last) break;
+            // state before step s: ix X crossings and s - ix Y crossings consumed
+            uint32_t lo = s > ny ? s - ny : 0u, hi = min(s, nx);
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (x_first(sx[mid], sy[s - 1 - mid], tie_x)) lo = mid + 1; else hi = mid;
+            }
+            const uint32_t ix = lo, iy = s - lo;
+            const float a = sx[ix], c = sy[iy];
+            int next_dir = x_first(a, c, tie_x) ? 1 : 2;
+            float next_t = next_dir == 1 ? a : c;
+            next_t = next_t < 1.0f ? next_t : 1.0f;
+            if (s == last) next_dir = 0;
+            int last_dir = 0;
+            float cur_x = ln.x, cur_y = ln.y;
+            if (s > 0) {  // the crossing consumed last: the later of sx[ix - 1], sy[iy - 1]
+                float prev_t;
+                if (ix == 0) { last_dir = 2; prev_t = sy[iy - 1]; }
+                else if (iy == 0) { last_dir = 1; prev_t = sx[ix - 1]; }
+                else {
+                    const float pa = sx[ix - 1], pc = sy[iy - 1];
+                    if (x_first(pa, pc, tie_x)) { last_dir = 2; prev_t = pc; } else { last_dir = 1; prev_t = pa; }
+                }
+                prev_t = prev_t < 1.0f ? prev_t : 1.0f;
+                cur_x = w.l0 + w.vx * prev_t;
+                cur_y = w.l1 + w.vy * prev_t;
+            }
+            const float px = w.l0 + w.vx * next_t, py = w.l1 + w.vy * next_t;  // LineSegmentF::sample
+            const int tcx = w.tcx + (int)ix * w.step_x, tcy = w.tcy + (int)iy * w.step_y;
+            const uint32_t slot = slot0 + 2u * s;
+            const uint32_t used = walk_step_emit(b, pt, w, cur_x, cur_y, px, py, tcx, tcy, last_dir, next_dir, slot);
+            for (uint32_t u = used; u < 2; u++) b.staging[slot + u].tile = 0xffffffffu;
         }
     }
 }
@@ -552,6 +649,9 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
 cudaError_t launch_bin(const BatchView &b, cudaStream_t s) {
     if (!b.segment_count) return cudaSuccess;
     k_bin<<<sm_count() * 8, 128, 0, s>>>(b);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_bin_long<<<sm_count() * 2, BIN_LONG_WARPS * 32, 0, s>>>(b);
     return cudaGetLastError();
 }
 

@@ -132,6 +132,58 @@ def test_masks_match_oracle(renderer, area_lut):
     fr.close()
 
 
+def compare_with_oracle(renderer, area_lut, scene, what):
+    """Geometry taps bit-exact + pixels within tolerance for a scene that has no reference fixture."""
+    renderer.set_scene(scene)
+    st = renderer.draw(clear=True)
+    fr, want = oracle_frame(scene, area_lut)
+    for b in scene["draw_batches"]:
+        bid = int(b["info"][0])
+        slot = fr.slots[bid]
+        assert np.array_equal(raw_sorted(fr.clipped_lines(slot)), raw_sorted(renderer.lines(bid))), what + ": lines"
+        assert np.array_equal(fr.fills(slot), renderer.fills(bid)), what + ": fills"
+        to, tc = fr.tiles(slot), renderer.tiles(bid)
+        for f in ("fill_count", "backdrop", "backdrop_delta", "backdrop_d3d9", "listed"):
+            assert np.array_equal(to[f], tc[f]), what + ": " + f
+        oo, ot = fr.tile_lists(slot)
+        co, ct = renderer.tile_lists(bid)
+        assert np.array_equal(oo, co) and np.array_equal(ot, ct), what + ": tile lists"
+    diff = np.abs(renderer.pixels().astype(int) - want.astype(int))
+    assert diff.max() <= PIXEL_TOL, what + ": pixels off by %d" % diff.max()
+    fr.close()
+    return st
+
+
+def test_long_lines_bit_exact_vs_oracle(renderer, area_lut):
+    """Lines that cross hundreds of tiles take the warp-per-line path of bin (merge of the two crossing sequences):
+    axis-aligned, diagonal, nearly-horizontal, nearly-vertical, reversed, starting above / left of the view box."""
+    def poly(pts, paint, rule=0):
+        pts = np.array(pts, "<f4")
+        return {"contours": [(pts, np.zeros(len(pts), "u1"))], "paint": paint, "fill_rule": rule, "opaque": False}
+
+    W = 3000
+    paths = [
+        poly([[0, 0], [W, 0], [W, W], [0, W]], 0),                                  # full-canvas rectangle
+        poly([[3.25, 7.5], [2990.75, 2801.125], [2989.5, 2810.0], [1.0, 19.0]], 1),  # thin diagonal sliver
+        poly([[10, 1500.3], [2995, 1503.9], [2995, 1504.4], [10, 1500.9]], 2),       # nearly horizontal
+        poly([[1501.3, 5], [1504.2, 2996], [1504.9, 2996], [1501.8, 5]], 3),         # nearly vertical
+        poly([[2999, 2999], [0.5, 0.5], [40.0, 0.5]], 1, rule=1),                   # reversed diagonal, even-odd
+        poly([[-500, -800], [2500, 2900], [2400, 2950]], 2),                         # starts above and left of the view
+        poly([[16, 16], [2992, 16], [2992, 2992], [16, 2992]], 3),                   # edges exactly on tile boundaries
+        poly([[100, 3500], [2900, -300], [2950, -250]], 0),                          # crosses top and bottom
+    ]
+    colors = np.array([[255, 255, 255, 255], [255, 0, 0, 128], [0, 255, 0, 200], [0, 0, 255, 77]], "u1")
+    scene = scenes.build_scene_from_outlines(W, W, paths, colors)
+    st = compare_with_oracle(renderer, area_lut, scene, "long lines")
+    assert st["overflow_flags"] == 0
+
+
+def test_synthetic_blobs_bit_exact_vs_oracle(renderer, area_lut):
+    """BASELINE.json config 4 in miniature: 1500 random cubic blobs at 1024 x 1024 (many tiny paths, deep lists)."""
+    scene = scenes.synthetic_scene(1500, 1024)
+    compare_with_oracle(renderer, area_lut, scene, "synthetic blobs")
+
+
 def test_repeat_frames_are_identical_and_reuse_buffers(renderer):
     scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
     renderer.set_scene(scene)
