@@ -12,6 +12,12 @@ A step is one whole frame (every batch of the scene: bound, dice, bin, propagate
   roofline: the composite ("tile") kernel, algorithmic bytes of SURVEY.md section 8d / measured HBM copy bandwidth.
 N > 1 (torchrun): the scene-sharded configuration -- every rank renders its own frames, no data-path collective
 (SURVEY.md section 8e), weak scaling.
+
+Other workloads (not what the driver runs; evidence for BASELINE.json configs 4 and 5, see profiles/):
+  --workload synthetic --paths 200000 --size 8192   config 4: one large canvas, horizontal strips, one per rank, assembled
+                                                    by one NCCL all-gather (--gather nccl) or by the tile kernel storing
+                                                    straight into rank 0's framebuffer over NVLink (--gather p2p); strong
+  --workload tiger512 --frames 4096                 config 5: a batch of independent frames, scene-sharded; frames/s
 """
 import argparse
 import json
@@ -327,19 +333,189 @@ def run_ours(args, rank, world):
         dist.destroy_process_group()
 
 
+def run_strips(args, rank, world):
+    """BASELINE.json config 4: synthetic cubic blobs on one size x size canvas, strip k on rank k (sharding.py)."""
+    import torch
+    import torch.distributed as dist
+
+    import pfcu
+    import sharding
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    size = args.size
+    paths, colors = scenes.synthetic_paths(args.paths, size)
+    y0, y1 = sharding.strip_bounds(size, world, rank)
+    rows = sharding.strip_rows(size, world)
+    scene = scenes.build_scene_from_outlines(size, size, paths, colors, strip=(y0, y1))
+    # every on-curve point starts one segment (SegmentsD3D11::add_path closes each contour, gpu_data.cpp:109)
+    segs_total = int(sum(int((c[1] == 0).sum()) for p_ in paths for c in p_["contours"]))
+    lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
+    stream = torch.cuda.Stream()
+    dev = torch.device("cuda", local)
+    peer = None
+    if args.gather == "p2p" and world > 1:
+        peer = sharding.PeerFramebuffer(size, size, world, rank, dev)
+        target_ptr, full = peer.strip_ptr(), None
+    else:
+        full = torch.zeros((rows * world, size, 4), dtype=torch.uint8, device=dev)
+        target_ptr = full[rank * rows:].data_ptr()
+    r = pfcu.Renderer(local, lut)
+    r.set_stream(stream.cuda_stream)
+    r.set_scene(scene, target_ptr, size * 4)
+    first = r.draw(clear=True)
+    steady = r.draw(clear=True)
+    assert steady["retries"] == 0, steady
+    r.set_profiling(True)
+    r.draw(clear=True)
+    stage_ms = r.stage_times()
+    r.set_profiling(False)
+    r.draw(clear=True)
+    r.graph_capture()
+
+    def step():
+        r.graph_launch()
+        if world > 1:
+            if peer is not None:
+                with torch.cuda.stream(stream):
+                    peer.barrier()
+            else:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(full.view(-1), full[rank * rows:(rank + 1) * rows].view(-1))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    gstats = r.graph_finish()
+    t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
+    units = torch.tensor([gstats[k] for k in ("segments", "lines", "fills", "alpha_tiles", "dense_tiles")],
+                         device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ms = float(t[0]) / args.steps
+        line = {
+            "metric": "segments/s (dice->composite), %d synthetic cubic paths at %dx%d, strip-sharded" % (args.paths, size, size),
+            "value": segs_total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (PCG32 seed 0x5EED5EED, SURVEY.md section 8d config 4)",
+            "config": {"workload": "synthetic%d@%dx%d" % (args.paths, size, size), "sharding": "horizontal strips, one per rank",
+                       "gather": ("tile-kernel stores into rank 0's framebuffer over NVLink (peer mapping) + barrier"
+                                  if peer is not None else "one NCCL all-gather of %d-row blocks" % rows) if world > 1 else "none",
+                       "l2": "framebuffer (%d MiB) larger than L2" % (size * size * 4 >> 20),
+                       "units_all_ranks": dict(zip(("segments", "lines", "fills", "alpha_tiles", "dense_tiles"),
+                                                   (int(x) for x in units.tolist()))),
+                       "rank0_stage_ms": stage_ms, "frame_ms_per_rank0": first["gpu_ms"]},
+            "gpu_launches": int(gstats["kernel_launches"]) * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_batch(args, rank, world):
+    """BASELINE.json config 5: a batch of independent frames (the same small scene), scene-sharded, frames/s."""
+    import torch
+    import torch.distributed as dist
+
+    import pfcu
+    import sharding
+
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scene, asset, size, native = load_workload(args.workload)
+    lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
+    mine = sharding.scene_share(args.frames, world, rank)
+    stream = torch.cuda.Stream()
+    r = pfcu.Renderer(local, lut)
+    r.set_stream(stream.cuda_stream)
+    r.set_scene(scene)
+    r.draw(clear=True)
+    r.draw(clear=True)
+    r.graph_capture()
+    for _ in range(max(args.warmup, 3)):
+        r.graph_launch()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        for _f in mine:
+            r.graph_launch()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop()
+    gstats = r.graph_finish()
+    if rank == 0:
+        ms = float(t[0]) / args.steps
+        print(json.dumps({
+            "metric": "frames/s, batch of %d independent %s renders at %dx%d, scene-sharded" % (args.frames, asset, size, size),
+            "value": args.frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "reference asset %s, scene fixture built by the reference front end" % asset,
+            "config": {"workload": "%d x %s@%dx%d" % (args.frames, asset, size, size),
+                       "sharding": "contiguous share of the batch per rank, no collective",
+                       "l2": "working set of one frame < L2 (frames are back to back, as in a batch)",
+                       "segments_per_s": args.frames * n_segments(scene) / (ms / 1e3)},
+            "gpu_launches": int(gstats["kernel_launches"]) * args.steps * len(mine), "clocks": clocks}))
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="tiger4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="tiger4096", choices=sorted(WORKLOADS) + ["synthetic"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--paths", type=int, default=200000, help="--workload synthetic: number of paths")
+    ap.add_argument("--size", type=int, default=8192, help="--workload synthetic: canvas size")
+    ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="--workload synthetic: strip assembly")
+    ap.add_argument("--frames", type=int, default=0, help="batch mode: render this many independent frames per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
+        if args.workload == "synthetic":
+            args.workload = "tiger4096"
         run_reference(args, rank)
+    elif args.workload == "synthetic":
+        run_strips(args, rank, world)
+    elif args.frames > 0:
+        run_batch(args, rank, world)
     else:
         run_ours(args, rank, world)
 

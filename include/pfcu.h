@@ -121,6 +121,13 @@ int pfcu_set_area_lut(pfcu_ctx *ctx, const uint8_t *rgba, int width, int height)
 int pfcu_set_target(pfcu_ctx *ctx, int width, int height, void *rgba8_dev, size_t pitch_bytes,
                     const float view_box[4]);
 
+/* The destination shows the scene from pixel (origin_x, origin_y) on (multiples of 16; reset to 0 by pfcu_set_target):
+ * one horizontal strip of a larger canvas per GPU. The view box passed to pfcu_set_target stays in scene coordinates
+ * ([0, origin_y, W, origin_y + height]) and the batch metadata is built against it, so every float operation is the
+ * one the full-canvas frame performs: the strip is bit-identical to its rows of the full frame. (The reference has no
+ * equivalent; its tile kernel maps scene tile (x, y) to framebuffer pixel (16 x, 16 y), tile.comp:739-741.) */
+int pfcu_set_target_origin(pfcu_ctx *ctx, int origin_x, int origin_y);
+
 /* ---- per-scene uploads */
 /* RendererD3D11::upload_scene (d3d11/renderer.cpp:346-350): which 0 = draw, 1 = clip.
  * points: xy float pairs; indices: SegmentIndicesD3D11 {first_point_index, flag} pairs. */

@@ -59,6 +59,7 @@ typedef struct {
 
 struct pfo_frame {
     int fb_w, fb_h, fb_tw, fb_th;
+    int org_tx, org_ty; /* scene tile that maps to framebuffer tile (0, 0): horizontal strips of a large canvas */
     float view_box[4]; /* left top right bottom */
     uint8_t *lut;
     int lut_w, lut_h;
@@ -556,7 +557,7 @@ static void propagate_batch(pfo_frame *f, batch_t *b) {
                 t->backdrop_d3d9 = (int8_t)backdrop9;
                 (void)has_alpha9;
 
-                int gx = tx + m->rect[0], gy = ty + m->rect[1];
+                int gx = tx + m->rect[0] - f->org_tx, gy = ty + m->rect[1] - f->org_ty;
                 int in_fb = gx >= 0 && gx < f->fb_tw && gy >= 0 && gy < f->fb_th;
                 size_t map = (size_t)gy * f->fb_tw + gx;
                 /* z: propagate.comp:190-206 */
@@ -600,7 +601,7 @@ static void propagate_batch(pfo_frame *f, batch_t *b) {
             for (int tx = 0; tx < w; tx++) {
                 uint32_t ti = m->tile_offset + (uint32_t)tx + (uint32_t)w * (uint32_t)ty;
                 if (!b->tiles[ti].listed) continue;
-                size_t map = (size_t)(ty + m->rect[1]) * f->fb_tw + (tx + m->rect[0]);
+                size_t map = (size_t)(ty + m->rect[1] - f->org_ty) * f->fb_tw + (tx + m->rect[0] - f->org_tx);
                 if ((int32_t)ti >= b->z11[map]) list_count[map]++;
             }
     }
@@ -620,7 +621,7 @@ static void propagate_batch(pfo_frame *f, batch_t *b) {
             for (int tx = 0; tx < w; tx++) {
                 uint32_t ti = m->tile_offset + (uint32_t)tx + (uint32_t)w * (uint32_t)ty;
                 if (!b->tiles[ti].listed) continue;
-                size_t map = (size_t)(ty + m->rect[1]) * f->fb_tw + (tx + m->rect[0]);
+                size_t map = (size_t)(ty + m->rect[1] - f->org_ty) * f->fb_tw + (tx + m->rect[0] - f->org_tx);
                 if ((int32_t)ti >= b->z11[map]) b->list_tiles[b->list_offsets[map] + cursor[map]++] = ti;
             }
     }
@@ -1045,6 +1046,10 @@ int pfo_frame_draw_batch(pfo_frame *f, int slot, int target_page, int color_page
                     if (clear) memcpy(dest, cc, 16);
                     else for (int c = 0; c < 4; c++) dest[c] = (float)dp[c] * (1.0f / 255.0f);
                     float fragx = (float)gx + 0.5f, fragy = (float)gy + 0.5f;
+                    if (target_page < 0) { /* gl_FragCoord of the full canvas (strip origin) */
+                        fragx = (float)(gx + f->org_tx * TILE) + 0.5f;
+                        fragy = (float)(gy + f->org_ty * TILE) + 0.5f;
+                    }
                     for (uint32_t k = lo; k < hi; k++) {
                         uint32_t ti = b->list_tiles[k];
                         const pfo_tile *t = &b->tiles[ti];
@@ -1120,6 +1125,11 @@ int pfo_frame_draw_batch(pfo_frame *f, int slot, int target_page, int color_page
         }
     }
     return 0;
+}
+
+void pfo_frame_set_origin(pfo_frame *f, int tile_x0, int tile_y0) {
+    f->org_tx = tile_x0;
+    f->org_ty = tile_y0;
 }
 
 void pfo_frame_pixels(const pfo_frame *f, uint8_t *out) { memcpy(out, f->dest, (size_t)f->fb_w * f->fb_h * 4); }

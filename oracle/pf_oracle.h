@@ -89,6 +89,10 @@ typedef struct {
 pfo_frame *pfo_frame_create(int fb_width, int fb_height, const float view_box[4], const uint8_t *area_lut_rgba,
                             int lut_w, int lut_h);
 void pfo_frame_destroy(pfo_frame *f);
+/* The framebuffer shows the scene from tile (tile_x0, tile_y0) on: one horizontal strip of a larger canvas. The view
+ * box stays in scene coordinates ([0, 16 * tile_y0, W, 16 * tile_y0 + fb_height]), so every float operation is the one
+ * the full-canvas frame performs. Default (0, 0). */
+void pfo_frame_set_origin(pfo_frame *f, int tile_x0, int tile_y0);
 
 /* which: 0 draw, 1 clip. points = xy pairs; indices = (first_point_index, flag) pairs. */
 void pfo_frame_set_segments(pfo_frame *f, int which, const float *points, uint32_t n_points,

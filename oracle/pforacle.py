@@ -43,6 +43,7 @@ def lib():
         vp, sz = C.c_void_p, C.c_size_t
         L.pfo_frame_create.restype = vp
         L.pfo_frame_create.argtypes = [C.c_int, C.c_int, vp, vp, C.c_int, C.c_int]
+        L.pfo_frame_set_origin.argtypes = [vp, C.c_int, C.c_int]
         L.pfo_frame_destroy.argtypes = [vp]
         L.pfo_frame_reset.argtypes = [vp]
         L.pfo_frame_set_segments.argtypes = [vp, C.c_int, vp, C.c_uint32, vp, C.c_uint32]
@@ -99,6 +100,8 @@ class Frame:
         lut = np.ascontiguousarray(area_lut, "u1") if area_lut is not None else None
         lw, lh = (lut.shape[1], lut.shape[0]) if lut is not None else (0, 0)
         self.h = lib().pfo_frame_create(int(scene["width"]), int(scene["height"]), _p(vb), _p(lut), lw, lh)
+        org = scene.get("origin_tiles", (0, 0))
+        lib().pfo_frame_set_origin(self.h, int(org[0]), int(org[1]))
         self.fb_tiles = ((int(scene["width"]) + 15) // 16) * ((int(scene["height"]) + 15) // 16)
         for which, name in ((0, "draw"), (1, "clip")):
             pts = np.ascontiguousarray(scene[name + "_points"], "<f4")

@@ -135,6 +135,7 @@ struct pfcu_ctx {
     DevBuf own_target;
     TargetView target{};
     float view_box[4] = {0, 0, 0, 0};
+    int origin_tx = 0, origin_ty = 0;
     // scene
     DevBuf points[2], indices[2];
     uint32_t n_points[2] = {0, 0}, n_segments[2] = {0, 0};
@@ -258,6 +259,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     memcpy(v.view_box, c->view_box, sizeof(v.view_box));
     v.fb_tw = (c->target.width + TILE - 1) / TILE;
     v.fb_th = (c->target.height + TILE - 1) / TILE;
+    v.fb_tx0 = c->origin_tx;
+    v.fb_ty0 = c->origin_ty;
     v.counters = c->counters.as<BatchCounters>() + slot_index;
     v.tile_word = s.tile_word.as<uint32_t>();
     v.fill_cursor = s.fill_cursor.as<uint32_t>();
@@ -365,7 +368,7 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
         int r = prof_mark(c, -1);
         if (r) return r;
     }
-    LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, cmd.target_page < 0, c->stream));
     c->launches += 1;
     c->in_flight = true;
     return PFCU_OK;
@@ -514,6 +517,16 @@ int pfcu_set_target(pfcu_ctx *c, int width, int height, void *rgba8_dev, size_t 
     c->target.width = width;
     c->target.height = height;
     memcpy(c->view_box, view_box, sizeof(c->view_box));
+    c->origin_tx = c->origin_ty = 0;
+    return PFCU_OK;
+}
+
+int pfcu_set_target_origin(pfcu_ctx *c, int origin_x, int origin_y) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    if ((origin_x % TILE) || (origin_y % TILE)) return fail(PFCU_ERR_INVALID, "the origin must be a multiple of the tile size");
+    if (c->frame_open) return fail(PFCU_ERR_STATE, "the origin cannot change inside a frame");
+    c->origin_tx = origin_x / TILE;
+    c->origin_ty = origin_y / TILE;
     return PFCU_OK;
 }
 

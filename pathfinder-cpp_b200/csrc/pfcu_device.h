@@ -109,6 +109,7 @@ struct BatchView {
     int identity_transform;
     float view_box[4];
     int fb_tw, fb_th;
+    int fb_tx0, fb_ty0;  // scene tile shown at framebuffer tile (0, 0) (pfcu_set_target_origin: strips of a large canvas)
     // working set
     BatchCounters *counters;
     uint32_t *tile_word;    // [tile_count] low 24 bits: fill count; high 8 bits: backdrop delta
@@ -172,8 +173,9 @@ cudaError_t launch_propagate(const BatchView &b, cudaStream_t s);
 cudaError_t launch_scan_fb(const BatchView &b, cudaStream_t s);
 cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s);
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s);
+// origin != 0: the target is the destination framebuffer, whose tile (0, 0) is scene tile (fb_tx0, fb_ty0)
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
-                             const float clear_color[4], cudaStream_t s);
+                             const float clear_color[4], int origin, cudaStream_t s);
 
 int sm_count();
 

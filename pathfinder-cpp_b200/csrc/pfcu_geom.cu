@@ -113,9 +113,10 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, unsigned lane) {
 }
 
 constexpr int DICE_THREADS = 256;
-constexpr int DICE_CHUNK = 32;    // segments a CTA takes at a time
+constexpr int DICE_CHUNK = 32;    // fewest segments a CTA takes at a time (launch_dice picks 32 .. DICE_THREADS)
 constexpr int DICE_QUEUE = 1024;  // nodes per level held in shared memory; wider levels fall back to a private stack
 constexpr int DICE_OUT = 1024;    // lines collected between flushes
+constexpr int DICE_PATHS = 512;   // dice metadata entries staged per chunk (more: the search stays in global memory)
 
 struct DiceShared {
     float4 qa[2][DICE_QUEUE];    // p0, p1
@@ -125,6 +126,8 @@ struct DiceShared {
     uint32_t out_path[DICE_OUT];
     uint32_t q_count[2];
     uint32_t out_count, out_base;
+    uint32_t path_lo, path_hi;         // paths that own the chunk's first / last segment
+    uint2 path_seg[DICE_PATHS];        // their (first_batch_segment_index, first_global_segment_index)
 };
 
 // One flattened line: view-box clip, then into the CTA's output buffer (or straight to global memory when full).
@@ -203,29 +206,148 @@ __device__ __forceinline__ void dice_push(const BatchView &b, DiceShared &sh, in
     }
 }
 
-__global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b) {
+// Warp-aggregated versions of dice_emit / dice_push (one shared-memory atomic per warp instead of one per lane: 256
+// lanes bumping the same counter serialise). Must be called by all 32 lanes of a warp.
+__device__ __forceinline__ void dice_emit_warp(const BatchView &b, DiceShared &sh, bool want, float2 from, float2 to,
+                                               uint32_t path, unsigned lane) {
+    float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
+    const bool em = want && clip_to_view_box(l0, l1, l2, l3, b.view_box[0], b.view_box[2], b.view_box[3]);
+    const unsigned mask = __ballot_sync(0xffffffffu, em);
+    if (!mask) return;
+    uint32_t base = 0;
+    const int leader = __ffs(mask) - 1;
+    if ((int)lane == leader) base = atomicAdd(&sh.out_count, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!em) return;
+    const uint32_t at = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    if (at < DICE_OUT) {
+        sh.out_line[at] = make_float4(l0, l1, l2, l3);
+        sh.out_path[at] = path;
+    } else {
+        const uint32_t g = atomicAdd(&b.counters->n_lines, 1u);
+        if (g < b.line_capacity) {
+            b.lines[g] = make_float4(l0, l1, l2, l3);
+            b.line_meta[g] = make_uint2(path, 0u);
+        } else {
+            atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
+        }
+    }
+}
+
+// Queues `n_nodes` (1 or 2) nodes per wanting lane; nodes that do not fit are flattened on the spot.
+__device__ __forceinline__ void dice_push_warp(const BatchView &b, DiceShared &sh, int buf, bool want, int n_nodes,
+                                               const Cubic &c0, const Cubic &c1, bool cubic, int depth, uint32_t path,
+                                               unsigned lane) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (!mask) return;
+    uint32_t base = 0;
+    const int leader = __ffs(mask) - 1;
+    if ((int)lane == leader) base = atomicAdd(&sh.q_count[buf], (uint32_t)(n_nodes * __popc(mask)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!want) return;
+    const uint32_t at = base + (uint32_t)(n_nodes * __popc(mask & ((1u << lane) - 1u)));
+    const uint32_t meta = path | ((uint32_t)depth << 24) | (cubic ? 0x80000000u : 0u);
+    for (int k = 0; k < n_nodes; k++) {
+        const Cubic &c = k ? c1 : c0;
+        if (at + k < DICE_QUEUE) {
+            sh.qa[buf][at + k] = make_float4(c.p0.x, c.p0.y, c.p1.x, c.p1.y);
+            sh.qb[buf][at + k] = make_float4(c.p2.x, c.p2.y, c.p3.x, c.p3.y);
+            sh.qm[buf][at + k] = meta;
+        } else {
+            dice_subtree_serial(b, sh, c, cubic, depth, path);
+        }
+    }
+}
+
+// Last path p in [0, n) with first_batch_segment_index[p] <= key, found by one warp with a 32-ary search: 2 dependent
+// loads for 300 paths, 4 for 200 000 (dice.comp:134-149 does a binary search per thread: 9 and 18).
+__device__ __forceinline__ uint32_t warp_find_path(const pfcu_dice_metadata *dice, uint32_t n, uint32_t key, unsigned lane) {
+    uint32_t lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const uint32_t step = (hi - lo + 31) / 32;
+        const uint32_t idx = lo + lane * step;
+        const bool ok = idx < hi && (idx == lo || __ldg(&dice[idx].first_batch_segment_index) <= key);
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);  // monotone: a prefix of the lanes (lane 0 always)
+        const uint32_t j = 31u - (uint32_t)__clz((int)mask);
+        const uint32_t nlo = lo + j * step;
+        hi = min(nlo + step, hi);
+        lo = nlo;
+    }
+    return lo;
+}
+
+// Copies the CTA's collected lines to global memory: one atomic per flush.
+__device__ __forceinline__ void dice_flush(const BatchView &b, DiceShared &sh) {
+    // (called by all threads, between two __syncthreads() of the caller's making: out_count is stable)
+    const uint32_t n_out = min(sh.out_count, (uint32_t)DICE_OUT);
+    if (threadIdx.x == 0) sh.out_base = n_out ? atomicAdd(&b.counters->n_lines, n_out) : 0u;
+    __syncthreads();
+    const uint32_t base = sh.out_base;
+    if (base + n_out > b.line_capacity) {
+        if (threadIdx.x == 0 && n_out) atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
+    } else {
+        for (uint32_t i = threadIdx.x; i < n_out; i += DICE_THREADS) {
+            b.lines[base + i] = sh.out_line[i];
+            b.line_meta[base + i] = make_uint2(sh.out_path[i], 0u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sh.out_count = 0;
+}
+
+__global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chunk_size) {
     extern __shared__ __align__(16) unsigned char dice_smem[];
     DiceShared &sh = *reinterpret_cast<DiceShared *>(dice_smem);
-    const uint32_t n_chunks = (b.segment_count + DICE_CHUNK - 1) / DICE_CHUNK;
+    const uint32_t n_chunks = (b.segment_count + chunk_size - 1) / chunk_size;
     if (threadIdx.x == 0) {
         sh.q_count[0] = sh.q_count[1] = 0;
         sh.out_count = 0;
     }
     __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
     for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-        // ---- roots: one thread per segment of the chunk
-        if (threadIdx.x < DICE_CHUNK) {
-            const uint32_t s = chunk * DICE_CHUNK + threadIdx.x;
+        // ---- which paths own this chunk's segments: warps 0 and 1 search, everybody stages that slice of the metadata
+        const uint32_t seg0 = chunk * chunk_size, seg1 = min(seg0 + chunk_size, b.segment_count) - 1;
+        if (threadIdx.x < 64) {
+            const uint32_t p = warp_find_path(b.dice, b.path_count, threadIdx.x < 32 ? seg0 : seg1, lane);
+            if (lane == 0) (threadIdx.x < 32 ? sh.path_lo : sh.path_hi) = p;
+        }
+        __syncthreads();
+        const uint32_t path_lo = sh.path_lo, n_staged = sh.path_hi - sh.path_lo + 1;
+        const bool paths_staged = n_staged <= DICE_PATHS;
+        if (paths_staged)
+            for (uint32_t i = threadIdx.x; i < n_staged; i += DICE_THREADS) {
+                const uint4 d = __ldg(reinterpret_cast<const uint4 *>(&b.dice[path_lo + i]));
+                sh.path_seg[i] = make_uint2(d.z, d.y);
+            }
+        __syncthreads();
+        // ---- roots: one thread per segment of the chunk (chunk_size is a multiple of 32: whole warps)
+        if (threadIdx.x < chunk_size) {
+            const uint32_t s = chunk * chunk_size + threadIdx.x;
+            bool root_line = false, root_curve = false, root_cubic = false;
+            Cubic root = {};
+            uint32_t root_path = 0;
             if (s < b.segment_count) {
                 // Owner path: last p with first_batch_segment_index <= s (dice.comp:134-149 binary search).
-                uint32_t lo = 0, hi = b.path_count;
-                while (lo + 1 < hi) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (__ldg(&b.dice[mid].first_batch_segment_index) <= s) lo = mid; else hi = mid;
+                uint32_t lo = 0, hi = n_staged, path, g;
+                if (paths_staged) {
+                    while (lo + 1 < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (sh.path_seg[mid].x <= s) lo = mid; else hi = mid;
+                    }
+                    path = path_lo + lo;
+                    g = sh.path_seg[lo].y + (s - sh.path_seg[lo].x);
+                } else {
+                    lo = path_lo;
+                    hi = path_lo + n_staged;
+                    while (lo + 1 < hi) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldg(&b.dice[mid].first_batch_segment_index) <= s) lo = mid; else hi = mid;
+                    }
+                    path = lo;
+                    g = __ldg(&b.dice[path].first_global_segment_index) +
+                        (s - __ldg(&b.dice[path].first_batch_segment_index));
                 }
-                const uint32_t path = lo;
-                const uint32_t g = __ldg(&b.dice[path].first_global_segment_index) +
-                                   (s - __ldg(&b.dice[path].first_batch_segment_index));
                 if (g < b.n_segments_total) {
                     const uint2 ix = __ldg(&b.indices[g]);
                     const uint32_t fp = ix.x, flag = ix.y;
@@ -256,64 +378,62 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b) {
                             if (sqrtf(dx * dx + dy * dy) <= FLOAT_EPSILON) ok = false;
                         }
                         if (ok) {
-                            if (npt == 2) {
-                                dice_emit(b, sh, q[0], q[1], path);
-                            } else {
-                                const Cubic c = npt == 3 ? Cubic{q[0], q[1], q[1], q[2]} : Cubic{q[0], q[1], q[2], q[3]};
-                                dice_push(b, sh, 0, c, npt == 4, 0, path);
-                            }
+                            root_path = path;
+                            root_line = npt == 2;
+                            root_curve = npt != 2;
+                            root_cubic = npt == 4;
+                            root = npt == 2 ? Cubic{q[0], q[1], q[1], q[1]}
+                                            : npt == 3 ? Cubic{q[0], q[1], q[1], q[2]} : Cubic{q[0], q[1], q[2], q[3]};
                         }
                     }
                 }
             }
+            dice_emit_warp(b, sh, root_line, root.p0, root.p3, root_path, lane);
+            // (a quadratic and a cubic root may share a warp: two passes keep the kind warp-uniform per call)
+            dice_push_warp(b, sh, 0, root_curve && root_cubic, 1, root, root, true, 0, root_path, lane);
+            dice_push_warp(b, sh, 0, root_curve && !root_cubic, 1, root, root, false, 0, root_path, lane);
         }
         __syncthreads();
         // ---- breadth-first over the subdivision trees (tiler.cpp:284-315): one node per thread per level
         int cur = 0;
         while (true) {
             const uint32_t count = min(sh.q_count[cur], (uint32_t)DICE_QUEUE);
-            for (uint32_t i = threadIdx.x; i < count; i += DICE_THREADS) {
-                const float4 a = sh.qa[cur][i], bq = sh.qb[cur][i];
-                const uint32_t m = sh.qm[cur][i];
-                const Cubic c = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(bq.x, bq.y), make_float2(bq.z, bq.w)};
+            // a level emits at most one line per node: flush first if they might not fit
+            if (sh.out_count + count > DICE_OUT) {
+                __syncthreads();
+                dice_flush(b, sh);
+                __syncthreads();
+            }
+            if (count == 0) break;
+            for (uint32_t base = 0; base < count; base += DICE_THREADS) {
+                const uint32_t i = base + threadIdx.x;
+                const bool active = i < count;
+                Cubic c = {};
+                uint32_t m = 0;
+                if (active) {
+                    const float4 a = sh.qa[cur][i], bq = sh.qb[cur][i];
+                    m = sh.qm[cur][i];
+                    c = {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(bq.x, bq.y), make_float2(bq.z, bq.w)};
+                }
                 const bool cubic = (m & 0x80000000u) != 0;
                 const int depth = (int)((m >> 24) & 0x7fu);
                 const uint32_t path = m & 0x00ffffffu;
-                if (node_is_flat(c, cubic, depth)) {
-                    dice_emit(b, sh, c.p0, c.p3, path);
-                } else {
-                    Cubic left, right;
-                    split_node(c, cubic, left, right);
-                    dice_push(b, sh, cur ^ 1, left, cubic, depth + 1, path);
-                    dice_push(b, sh, cur ^ 1, right, cubic, depth + 1, path);
-                }
+                const bool flat = active && node_is_flat(c, cubic, depth);
+                dice_emit_warp(b, sh, flat, c.p0, c.p3, path, lane);
+                Cubic left = {}, right = {};
+                if (active && !flat) split_node(c, cubic, left, right);
+                dice_push_warp(b, sh, cur ^ 1, active && !flat && cubic, 2, left, right, true, depth + 1, path, lane);
+                dice_push_warp(b, sh, cur ^ 1, active && !flat && !cubic, 2, left, right, false, depth + 1, path, lane);
             }
             __syncthreads();
-            // ---- flush the lines of this level: one global atomic per CTA
-            const uint32_t n_out = min(sh.out_count, (uint32_t)DICE_OUT);
-            if (threadIdx.x == 0) {
-                sh.out_base = n_out ? atomicAdd(&b.counters->n_lines, n_out) : 0u;
-                sh.q_count[cur] = 0;
-            }
-            __syncthreads();
-            const uint32_t base = sh.out_base;
-            if (base + n_out > b.line_capacity) {
-                if (threadIdx.x == 0 && n_out) atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
-            } else {
-                for (uint32_t i = threadIdx.x; i < n_out; i += DICE_THREADS) {
-                    b.lines[base + i] = sh.out_line[i];
-                    b.line_meta[base + i] = make_uint2(sh.out_path[i], 0u);
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) sh.out_count = 0;
-            const bool more = sh.q_count[cur ^ 1] != 0;
-            __syncthreads();
+            if (threadIdx.x == 0) sh.q_count[cur] = 0;
             cur ^= 1;
-            if (!more) break;
+            __syncthreads();
         }
-        __syncthreads();
+        // (both queues are empty here; the lines stay in the buffer until it fills up or the CTA is done)
     }
+    __syncthreads();
+    dice_flush(b, sh);
 }
 
 cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
@@ -324,9 +444,14 @@ cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    const uint32_t n_chunks = (b.segment_count + DICE_CHUNK - 1) / DICE_CHUNK;
-    const uint32_t grid = min(n_chunks, (uint32_t)sm_count() * 2u);
-    k_dice<<<grid, DICE_THREADS, sizeof(DiceShared), s>>>(b);
+    // Segments per CTA and pass: few segments -> small chunks (every SM gets one, deep trees fit the queue);
+    // many segments -> large chunks (fewer block-wide barriers per segment).
+    const uint32_t ctas = (uint32_t)sm_count() * 2u;
+    uint32_t chunk = (b.segment_count / (ctas * 4u) + 31u) & ~31u;
+    chunk = chunk < DICE_CHUNK ? DICE_CHUNK : (chunk > DICE_THREADS ? DICE_THREADS : chunk);
+    const uint32_t n_chunks = (b.segment_count + chunk - 1) / chunk;
+    const uint32_t grid = min(n_chunks, ctas);
+    k_dice<<<grid, DICE_THREADS, sizeof(DiceShared), s>>>(b, chunk);
     return cudaGetLastError();
 }
 

@@ -486,7 +486,7 @@ __device__ __forceinline__ bool next_entry(ListCursor &cur, bool in_regs, uint32
 // destination pixels are never live together: first the masks of its layers (fused mode), then the blend.
 template <bool SOLID, bool FUSED>
 __global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchView b, PaintView p, TargetView tg,
-                                                                          int clear, float4 clear_color) {
+                                                                          int clear, float4 clear_color, int origin) {
     __shared__ CompositeShared sh;
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
@@ -591,7 +591,9 @@ __global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchV
             }
         }
 
-        const float fragx = (float)gx + 0.5f;
+        // gl_FragCoord of the full canvas (only textured paints look at it); render-target pages have no origin
+        const float org_x = (float)(origin ? b.fb_tx0 * TILE : 0), org_y = (float)(origin ? b.fb_ty0 * TILE : 0);
+        const float fragx = (float)gx + org_x + 0.5f;
         ListCursor cur = {0u, 0u, true};
         bool more = n != 0;
         while (more) {
@@ -699,7 +701,7 @@ __global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchV
                         src.y *= src.w;
                         src.z *= src.w;
                     } else {
-                        src = shade<false>(pc, cs, fragx, (float)(gy0 + ROW(q)) + 0.5f, mask_alpha, (float)tg.width,
+                        src = shade<false>(pc, cs, fragx, (float)(gy0 + ROW(q)) + org_y + 0.5f, mask_alpha, (float)tg.width,
                                            (float)tg.height);
                     }
                     blend_over(dest[q], src);
@@ -733,18 +735,18 @@ __global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchV
 #undef ROW
 
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
-                             const float clear_color[4], cudaStream_t s) {
+                             const float clear_color[4], int origin, cudaStream_t s) {
     if (b.fb_tw <= 0 || b.fb_th <= 0) return cudaSuccess;
     const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
     const unsigned grid = (n_fb + CT_TILES - 1) / CT_TILES;
     const float4 cc = make_float4(clear_color[0], clear_color[1], clear_color[2], clear_color[3]);
     const int threads = CT_WARPS * 32;
     if (p.fused) {
-        if (p.all_solid) k_composite<true, true><<<grid, threads, 0, s>>>(b, p, t, clear, cc);
-        else k_composite<false, true><<<grid, threads, 0, s>>>(b, p, t, clear, cc);
+        if (p.all_solid) k_composite<true, true><<<grid, threads, 0, s>>>(b, p, t, clear, cc, origin);
+        else k_composite<false, true><<<grid, threads, 0, s>>>(b, p, t, clear, cc, origin);
     } else {
-        if (p.all_solid) k_composite<true, false><<<grid, threads, 0, s>>>(b, p, t, clear, cc);
-        else k_composite<false, false><<<grid, threads, 0, s>>>(b, p, t, clear, cc);
+        if (p.all_solid) k_composite<true, false><<<grid, threads, 0, s>>>(b, p, t, clear, cc, origin);
+        else k_composite<false, false><<<grid, threads, 0, s>>>(b, p, t, clear, cc, origin);
     }
     return cudaGetLastError();
 }

@@ -336,8 +336,9 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
                 need_new = false;  // the scan flagged OVF_ALPHA: the frame is replayed with more slots
             }
         }
-        const bool in_fb = gx >= 0 && gx < b.fb_tw && gy >= 0 && gy < b.fb_th;
-        const uint32_t map = in_fb ? (uint32_t)gy * (uint32_t)b.fb_tw + (uint32_t)gx : 0u;
+        const int fx = gx - b.fb_tx0, fy = gy - b.fb_ty0;  // framebuffer tile
+        const bool in_fb = fx >= 0 && fx < b.fb_tw && fy >= 0 && fy < b.fb_th;
+        const uint32_t map = in_fb ? (uint32_t)fy * (uint32_t)b.fb_tw + (uint32_t)fx : 0u;
         const bool listed = (backdrop != 0 || alpha >= 0) && in_fb;
         const uint32_t packed = ((uint32_t)backdrop & 0xffu) | (((uint32_t)delta & 0xffu) << 8) |
                                 (((uint32_t)backdrop9 & 0xffu) << 16) | (listed ? 1u << 24 : 0u) |
@@ -371,8 +372,8 @@ __global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
         const int4 rect = __ldg(reinterpret_cast<const int4 *>(&b.meta[path].tile_rect[0]));
         const uint32_t local = ti - __ldg(&b.meta[path].tile_offset);
         const uint32_t w = (uint32_t)(rect.z - rect.x);
-        const int gx = rect.x + (int)(local % w), gy = rect.y + (int)(local / w);
-        const uint32_t map = (uint32_t)gy * (uint32_t)b.fb_tw + (uint32_t)gx;
+        const int fx = rect.x + (int)(local % w) - b.fb_tx0, fy = rect.y + (int)(local / w) - b.fb_ty0;
+        const uint32_t map = (uint32_t)fy * (uint32_t)b.fb_tw + (uint32_t)fx;
         const uint2 pi = __ldg(reinterpret_cast<const uint2 *>(&b.tpi[path]) + 1);  // first_tile | color, ctrl, backdrop
         const uint32_t ctrl_word = (pi.y & 0x00ffffffu) | ((st.y & 0xffu) << 24);
         const uint32_t pos = __ldg(&b.fb[map].begin) + atomicAdd(&b.fb[map].cursor, 1u);

@@ -16,7 +16,7 @@ NONE = 0xFFFFFFFF
 
 EXPORTS = [
     "pfcu_abi_version", "pfcu_last_error", "pfcu_create", "pfcu_destroy", "pfcu_set_stream", "pfcu_get_stream",
-    "pfcu_set_area_lut", "pfcu_set_target", "pfcu_upload_scene", "pfcu_upload_paint_metadata", "pfcu_alloc_page",
+    "pfcu_set_area_lut", "pfcu_set_target", "pfcu_set_target_origin", "pfcu_upload_scene", "pfcu_upload_paint_metadata", "pfcu_alloc_page",
     "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
     "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
     "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
@@ -73,6 +73,7 @@ def lib():
         L.pfcu_get_stream.restype = vp
         L.pfcu_set_area_lut.argtypes = [vp, vp, i32, i32]
         L.pfcu_set_target.argtypes = [vp, i32, i32, vp, sz, vp]
+        L.pfcu_set_target_origin.argtypes = [vp, i32, i32]
         L.pfcu_upload_scene.argtypes = [vp, i32, vp, u32, vp, u32]
         L.pfcu_upload_paint_metadata.argtypes = [vp, vp, u32]
         L.pfcu_alloc_page.argtypes = [vp, u32, i32, i32]
@@ -180,6 +181,8 @@ class Renderer:
     def set_scene(self, scene, target_ptr=None, pitch=0):
         self.scene = scene
         self.set_target(scene["width"], scene["height"], scene["view_box"], target_ptr, pitch)
+        org = scene.get("origin_tiles", (0, 0))
+        _check(self.L.pfcu_set_target_origin(self.h, int(org[0]) * 16, int(org[1]) * 16))
         self.upload_segments(scene)
         self.upload_paints(scene)
         self._keep = []

@@ -239,6 +239,8 @@ def digest(*arrays):
 class PCG32:
     """PCG-XSH-RR 64/32 (O'Neill 2014), the generator SURVEY.md section 8d names for config 4."""
 
+    MULT = 6364136223846793005
+
     def __init__(self, seed, seq=0xda3e39cb94b95bdb):
         self.mask = (1 << 64) - 1
         self.state = 0
@@ -249,10 +251,24 @@ class PCG32:
 
     def next(self):
         old = self.state
-        self.state = (old * 6364136223846793005 + self.inc) & self.mask
+        self.state = (old * self.MULT + self.inc) & self.mask
         xorshifted = (((old >> 18) ^ old) >> 27) & 0xFFFFFFFF
         rot = old >> 59
         return ((xorshifted >> rot) | (xorshifted << ((-rot) & 31))) & 0xFFFFFFFF
+
+    def block(self, n):
+        """The next n outputs at once (same values as n calls of next()): the LCG is jumped ahead in closed form,
+        state_k = a^k * s + inc * (1 + a + ... + a^(k-1)), all in wrapping uint64 arithmetic."""
+        with np.errstate(over="ignore"):
+            a_pow = np.cumprod(np.concatenate(([np.uint64(1)], np.full(n, self.MULT, np.uint64))), dtype=np.uint64)
+            geo = np.concatenate(([np.uint64(0)], np.cumsum(a_pow[:-1], dtype=np.uint64)))
+            states = a_pow * np.uint64(self.state) + np.uint64(self.inc) * geo
+        old = states[:-1]
+        self.state = int(states[-1])
+        xorshifted = (((old >> np.uint64(18)) ^ old) >> np.uint64(27)) & np.uint64(0xFFFFFFFF)
+        rot = old >> np.uint64(59)
+        out = (xorshifted >> rot) | (xorshifted << ((np.uint64(32) - rot) & np.uint64(31)))
+        return (out & np.uint64(0xFFFFFFFF)).astype(np.uint32)
 
 
 def _half_bits(x):
@@ -276,7 +292,7 @@ def solid_metadata(colors_rgba8):
     return md
 
 
-def build_scene_from_outlines(width, height, paths, colors_rgba8, strip=None):
+def build_scene_from_outlines(width, height, paths, colors_rgba8, strip=None, drop_invisible=True):
     """Host-side mirror of SceneBuilderD3D11::build for pre-flattened outlines (one draw batch, no clips).
 
     paths: list of dicts {contours: [ (points (k,2) f32, flags (k,) u8 [0 on-curve, 1 ctrl0, 2 ctrl1]) ],
@@ -284,15 +300,20 @@ def build_scene_from_outlines(width, height, paths, colors_rgba8, strip=None):
     Restates SegmentsD3D11::add_path (core/d3d11/gpu_data.cpp:79-115), prepare_draw_path_for_gpu_binning
     (core/d3d11/scene_builder.cpp:26-58), BuiltPath tile bounds (core/data/built_path.cpp:8-34,
     core/data/data.h:53-55) and TileBatchDataD3D11::push (core/d3d11/gpu_data.cpp:24-77).
-    strip = (y0, y1): render only that horizontal strip: geometry is translated by -y0 and the
-    view box / framebuffer become width x (y1 - y0).
+    strip = (y0, y1), y0 a multiple of 16: render only that horizontal strip. The geometry is NOT
+    moved: the view box becomes [0, y0, W, y1] and the framebuffer (width x (y1 - y0)) starts at scene tile row y0 / 16
+    ("origin_tiles"), so every float operation is the one the full-canvas frame performs and the strip is bit-identical
+    to rows [y0, y1) of it.
     """
-    y_off = 0.0
+    y_top = 0.0
+    origin_tiles = (0, 0)
     if strip is not None:
-        y_off = float(strip[0])
+        assert int(strip[0]) % 16 == 0
+        y_top = float(strip[0])
+        origin_tiles = (0, int(strip[0]) // 16)
         height = int(strip[1] - strip[0])
     vb_right = float(int(np.ceil(width / 16.0)) * 16)  # Scene::set_view_box (core/scene.cpp:170-179)
-    view_box = np.array([0.0, 0.0, vb_right, float(height)], "<f4")
+    view_box = np.array([0.0, y_top, vb_right, y_top + float(height)], "<f4")
     points, indices = [], []
     n_points = 0
     backdrops, meta, dice, tpi = [], [], [], []
@@ -302,16 +323,14 @@ def build_scene_from_outlines(width, height, paths, colors_rgba8, strip=None):
         lo = np.array([np.inf, np.inf], "<f4")
         hi = np.array([-np.inf, -np.inf], "<f4")
         for pts, flags in p["contours"]:
-            pts = np.asarray(pts, "<f4").copy()
-            if y_off:
-                pts[:, 1] = pts[:, 1] - np.float32(y_off)
+            pts = np.asarray(pts, "<f4")
             k = len(pts)
-            for i in range(k):
-                if flags[i] == 0:
-                    flag = 0
-                    if i + 1 < k and flags[i + 1] == 1:
-                        flag = CURVE_IS_CUBIC if (i + 2 < k and flags[i + 2] == 2) else CURVE_IS_QUADRATIC
-                    indices.append((n_points + i, flag))
+            fl = np.asarray(flags, "u1")
+            nxt1 = np.append(fl[1:], 0)
+            nxt2 = np.append(fl[2:], [0, 0])[:k]
+            on_curve = np.nonzero(fl == 0)[0]
+            seg_flag = np.where(nxt1[on_curve] == 1, np.where(nxt2[on_curve] == 2, CURVE_IS_CUBIC, CURVE_IS_QUADRATIC), 0)
+            indices.extend(zip((n_points + on_curve).tolist(), seg_flag.tolist()))
             points.append(pts)
             points.append(pts[:1])
             n_points += k + 1
@@ -323,6 +342,10 @@ def build_scene_from_outlines(width, height, paths, colors_rgba8, strip=None):
         # outline.bounds ∩ view box (Rect::intersection, common/math/rect.h:160-173); {} when disjoint
         if not np.isfinite(lo).all() or lo[0] > view_box[2] or hi[0] < view_box[0] or lo[1] > view_box[3] or \
                 hi[1] < view_box[1]:
+            if drop_invisible:
+                # prepare_draw_path_for_gpu_binning returns nullptr (core/d3d11/scene_builder.cpp:36-42): the path is
+                # not part of the batch; its segments stay in the scene's point / index arrays, unreferenced
+                continue
             bounds = np.zeros(4, "<f4")
         else:
             bounds = np.array([max(lo[0], view_box[0]), max(lo[1], view_box[1]), min(hi[0], view_box[2]),
@@ -334,7 +357,7 @@ def build_scene_from_outlines(width, height, paths, colors_rgba8, strip=None):
         ctrl = 0x2 if p.get("fill_rule", 0) == 1 else 0x1
         meta.append((rect, tile_count, path_index, 1 if p.get("opaque", True) else 0, NONE, len(backdrops), (0, 0, 0)))
         backdrops.extend((0, x, path_index) for x in range(w))
-        dice.append((gid, first_seg, seg_count, 0))
+        dice.append((gid, first_seg, seg_count, 0))  # first_seg: global (scene) index, seg_count: batch-local
         tpi.append((rect[0], rect[1], rect[2], rect[3], tile_count, p["paint"], ctrl, 0))
         tile_count += w * h
         seg_count += n_seg
@@ -353,44 +376,41 @@ def build_scene_from_outlines(width, height, paths, colors_rgba8, strip=None):
         "clip_points": np.zeros((0, 2), "<f4"), "clip_indices": np.zeros((0, 2), "<u4"),
         "draw_batches": [batch], "clip_batches": [],
         "metadata": solid_metadata(colors_rgba8), "pages": {},
+        "origin_tiles": origin_tiles,
     }
 
 
 def synthetic_paths(n_paths, size, seed=0x5EED5EED, n_colors=4096):
-    """closed blobs of K~U{8..16} cubic segments, radius U[6,20] px."""
+    """closed blobs of K~U{8..16} cubic segments, radius U[6,20] px.
+    Draw order per path: K; centre x, y; radius; K radial jitters; then per segment two control points, each two
+    Box-Muller normals (u1, u2 per normal). The stream is generated in blocks and consumed with a cursor."""
     rng = PCG32(seed)
-
-    def uni():
-        return rng.next() / 4294967296.0
-
-    def normal():
-        u1, u2 = max(uni(), 1e-12), uni()
-        return float(np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2))
-
+    draws = rng.block(n_paths * (4 + 9 * 16))
+    pos = 0
     paths = []
+    two_pi = 2.0 * np.pi
     for i in range(n_paths):
-        k = 8 + rng.next() % 9
-        cx, cy = 32.0 + uni() * (size - 64.0), 32.0 + uni() * (size - 64.0)
-        r = 6.0 + uni() * 14.0
-        on = []
-        for j in range(k):
-            a = 2.0 * np.pi * j / k
-            rr = r * (0.6 + 0.8 * uni())
-            on.append((cx + rr * np.cos(a), cy + rr * np.sin(a)))
-        pts, flags = [], []
-        for j in range(k):
-            p0, p3 = on[j], on[(j + 1) % k]
-            c1 = (p0[0] + (p3[0] - p0[0]) / 3.0 + normal() * 0.25 * r, p0[1] + (p3[1] - p0[1]) / 3.0 + normal() * 0.25 * r)
-            c2 = (p0[0] + (p3[0] - p0[0]) * 2.0 / 3.0 + normal() * 0.25 * r,
-                  p0[1] + (p3[1] - p0[1]) * 2.0 / 3.0 + normal() * 0.25 * r)
-            pts += [p0, c1, c2]
-            flags += [0, 1, 2]
-        pts.append(on[0])
-        flags.append(0)
-        paths.append({"contours": [(np.array(pts, "<f4"), np.array(flags, "u1"))], "paint": i % n_colors,
-                      "fill_rule": 0, "opaque": True})
+        k = 8 + int(draws[pos]) % 9
+        u = draws[pos + 1:pos + 4 + 9 * k].astype(np.float64) / 4294967296.0
+        pos += 4 + 9 * k
+        cx, cy = 32.0 + u[0] * (size - 64.0), 32.0 + u[1] * (size - 64.0)
+        r = 6.0 + u[2] * 14.0
+        ang = two_pi * np.arange(k) / k
+        rr = r * (0.6 + 0.8 * u[3:3 + k])
+        on = np.stack([cx + rr * np.cos(ang), cy + rr * np.sin(ang)], axis=1)
+        nrm = u[3 + k:].reshape(k, 4, 2)  # per segment: (c1.x, c1.y, c2.x, c2.y) x (u1, u2)
+        g = np.sqrt(-2.0 * np.log(np.maximum(nrm[..., 0], 1e-12))) * np.cos(two_pi * nrm[..., 1]) * (0.25 * r)
+        p0, p3 = on, np.roll(on, -1, axis=0)
+        c1 = p0 + (p3 - p0) / 3.0 + g[:, 0:2]
+        c2 = p0 + (p3 - p0) * 2.0 / 3.0 + g[:, 2:4]
+        pts = np.empty((3 * k + 1, 2), "<f4")
+        pts[0:3 * k:3], pts[1:3 * k:3], pts[2:3 * k:3], pts[3 * k] = p0, c1, c2, on[0]
+        flags = np.zeros(3 * k + 1, "u1")
+        flags[1:3 * k:3], flags[2:3 * k:3] = 1, 2
+        paths.append({"contours": [(pts, flags)], "paint": i % n_colors, "fill_rule": 0, "opaque": True})
     crng = PCG32(seed ^ 0xC0105)
-    colors = np.array([[crng.next() & 255, crng.next() & 255, crng.next() & 255, 255] for _ in range(n_colors)], "u1")
+    colors = np.concatenate([crng.block(3 * n_colors).reshape(n_colors, 3) & 255,
+                             np.full((n_colors, 1), 255, np.uint32)], axis=1).astype("u1")
     return paths, colors
 
 

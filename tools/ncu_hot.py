@@ -2,6 +2,11 @@
 """Top stall-sample SASS lines of one kernel from `ncu -i rep --page source --csv -k <kernel>` output."""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
+heads = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0  # n-th kernel section of the file
+print("kernel:", rows[heads[which] - 1][1][:80])
+end = heads[which + 1] - 1 if which + 1 < len(heads) else len(rows)
+rows = [None, rows[heads[which]]] + [r for r in rows[heads[which] + 1:end] if len(r) == len(rows[heads[which]])]
 hdr = rows[1]
 i_src, i_s, i_ex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
 stalls = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
