@@ -77,10 +77,10 @@ struct FbTile {
 };
 
 struct AlphaTile {
-    uint32_t tile_index;  // dense tile that owns the mask
+    uint32_t tile_index;  // dense tile that owns the mask (0x7fffffff: skip) | winding rule << 31
     int32_t clip_alpha;   // mask slot to min() with, or -1
-    uint32_t packed;      // bits 0-7 backdrop, bit 8 winding rule
-    uint32_t fill_count;
+    uint32_t fill_begin;  // CSR range of its fills
+    uint32_t packed;      // bits 0-7 backdrop, 8-31 fill count
 };
 
 // Per-paint constants decoded once per metadata upload from the RGBA16F texels (tile.comp:694-726).

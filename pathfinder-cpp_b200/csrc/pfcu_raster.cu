@@ -83,6 +83,15 @@ __device__ __forceinline__ float glsl_mod(float x, float y) { return x - y * flo
 
 // ------------------------------------------------------------------------------------------------ fill
 
+__device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, unsigned lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= (unsigned)d) v += t;
+    }
+    return v;
+}
+
 // One 4-row group of one pixel column (computeCoverage's LUT fetch, fill.comp:70, times dX, into cov[0..3]).
 // texture(uAreaLUT, uv) is spelled out in fp32: the texture unit fetches the four texels (point sampling,
 // clamp-to-edge, unorm8 -> float) and the bilinear weights k** (already multiplied by dX) are applied here. The unit's
@@ -182,31 +191,163 @@ __device__ __forceinline__ uint2 quantise_mask(const float cov[8], bool winding,
 }
 
 constexpr int FILL_WARPS = 8;
+constexpr float FILL_SCALE = 1048576.0f;  // coverage is accumulated in 12.20 fixed point (order-independent sums)
+constexpr int FILL_ONE = 1 << 20;
+
+// Standalone fill kernel: one warp per alpha tile, and inside the tile one lane per (fill, pixel column) PAIR.
+//
+// A fill only touches the pixel columns it spans (5 of 16 on tiger 4096^2) and, in each of them, the few rows around the
+// line; below those rows its contribution is the constant dX, above them 0 (the area LUT saturates there, which
+// pfcu_set_area_lut verifies for the uploaded LUT). So the work of a tile is enumerated as pairs -- a prefix sum over
+// the fills' column spans, lane p takes pair p -- instead of giving every lane a fixed pixel column and every fill to
+// every lane (30 % useful lanes). A pair samples only the 4-row groups its line passes through (one or two unless the
+// line is steep) and adds what it finds to a 16 x 16 accumulator in shared memory as DIFFERENCES down
+// its column: the tile's coverage is then one prefix sum per column, and "every row below gets dX" is a single add.
+// Sums are fixed point, so the result does not depend on the order in which pairs or atomics land.
+struct FillShared {
+    int acc[FILL_WARPS][17][16];  // [row][column]; row 16 is a sink for differences that fall below the tile
+};
 
 __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView p) {
-    const unsigned lane = threadIdx.x & 31;
+    __shared__ FillShared sh;
+    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t first_alpha = b.counters->first_alpha;
     uint32_t n_alpha = b.counters->n_alpha;
     if (n_alpha > b.alpha_capacity) n_alpha = b.alpha_capacity;
+    int *const acc = &sh.acc[wib][0][0];
+    for (int i = (int)lane; i < 17 * 16; i += 32) acc[i] = 0;
+    __syncwarp();
+    const bool band = p.lut_band != 0;
+    const int c_own = (int)(lane & 15u), h_own = (int)(lane >> 4);
+
     for (uint32_t a = warp; a < n_alpha; a += n_warps) {
         const uint32_t id = first_alpha + a;
         if (id >= b.mask_capacity) break;
-        const uint4 at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]));  // tile, clip, packed, fill count
-        const uint32_t ti = at.x;
-        if (ti >= b.tile_count) continue;  // a tile with fills that the clip made invisible: no mask needed
-        uint32_t end = b.fill_cursor[ti];
-        if (end > b.fill_capacity) end = b.fill_capacity;
-        const uint32_t begin = end >= at.w ? end - at.w : 0u;
-        const float backdrop = (float)(int8_t)(at.z & 0xffu);
-        float cov[8];
+        // tile | winding << 31, clip mask slot, first fill, backdrop | fill count << 8
+        const uint4 at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]));
+        if ((at.x & 0x7fffffffu) >= b.tile_count) continue;  // fills that the clip made invisible: no mask needed
+        const uint32_t count = at.w >> 8;
+        uint32_t begin = at.z;
+        if (begin > b.fill_capacity) begin = b.fill_capacity;
+        const uint32_t end = min(begin + count, b.fill_capacity);
+
+        for (uint32_t chunk = begin; chunk < end; chunk += 32) {
+            // ---- one fill per lane: what only depends on the fill (fill.comp:53-64)
+            const bool vf = chunk + lane < end;
+            float x_from = 0.f, x_to = 0.f, ly = 0.f, d = 0.f;
+            int c0 = 0, len = 0;
+            if (vf) {
+                const uint2 f = __ldg(&b.fills[chunk + lane]);
+                x_from = (float)(f.x & 0xffffu) * (1.0f / 256.0f);
+                x_to = (float)(f.y & 0xffffu) * (1.0f / 256.0f);
+                const float y_from = (float)(f.x >> 16) * (1.0f / 256.0f), y_to = (float)(f.y >> 16) * (1.0f / 256.0f);
+                const bool from_left = x_from < x_to;
+                ly = from_left ? y_from : y_to;
+                const float ry = from_left ? y_to : y_from;
+                d = (ry - ly) * __fdividef(1.0f, fabsf(x_to - x_from));  // bin never emits x_from == x_to
+                // pixel columns whose window [c, c + 1] the fill overlaps with positive length
+                const float xmin = fminf(x_from, x_to), xmax = fmaxf(x_from, x_to);
+                c0 = min((int)xmin, 15);
+                const int c1 = min((int)ceilf(xmax) - 1, 15);
+                len = max(c1 - c0 + 1, 1);
+            }
+            const int incl = (int)warp_incl_scan_u32((uint32_t)len, lane);
+            const int excl = incl - len;
+            const int n_pairs = __shfl_sync(0xffffffffu, incl, 31);
+            const int pair_base = excl - c0;  // column of pair p of this fill = p - pair_base
+
+            for (int p0 = 0; p0 < n_pairs; p0 += 32) {
+                // ---- which fill does pair p0 + lane belong to: the number of fills that start at or before it, minus one
+                // (every fill owns at least one pair, so fill k is lane k)
+                const unsigned starts = __reduce_or_sync(0xffffffffu, (vf && excl >= p0 && excl < p0 + 32) ? 1u << (excl - p0) : 0u);
+                const int before = __popc(__ballot_sync(0xffffffffu, vf && excl < p0));
+                const int k = before - 1 + __popc(starts & (0xffffffffu >> (31 - lane)));
+                const int srcl = k < 0 ? 0 : (k > 31 ? 31 : k);
+                const float xf = __shfl_sync(0xffffffffu, x_from, srcl), xt = __shfl_sync(0xffffffffu, x_to, srcl);
+                const float lyk = __shfl_sync(0xffffffffu, ly, srcl), dk = __shfl_sync(0xffffffffu, d, srcl);
+                const int pb = __shfl_sync(0xffffffffu, pair_base, srcl);
+                const int pidx = p0 + (int)lane;
+                if (pidx >= n_pairs) continue;
+                const int c = pidx - pb;
+                const float col = (float)c;
+                // window = clamp(vec2(from.x, to.x), -0.5, 0.5) in fragment-centred coordinates (fill.comp:58)
+                const float wx = __saturatef(xf - col), wy = __saturatef(xt - col);
+                const float dX = wx - wy;
+                if (dX == 0.0f) continue;
+                // y of the line at the middle of the window (fill.comp:59-63), tile space
+                const float y_line = fmaf(dk, fmaf(0.5f, wx + wy, col - fminf(xf, xt)), lyk);
+                const float lut_y = fmaf(fabsf(dk * dX), 16.0f, -0.5f);  // v * 256 - 0.5
+                const float fy0 = floorf(lut_y), ay = lut_y - fy0;
+                // rows whose LUT value is not saturated: above r_lo the coverage is 0, below r_hi it is 1
+                int r_lo = 0, r_hi = 15;
+                if (band) {
+                    const float hw = (lut_y + 1.0f) * (1.0f / 32.0f);
+                    r_lo = (int)ceilf(y_line - hw - (17.0f / 16.0f + 1.0f / 64.0f));
+                    r_hi = (int)floorf(y_line + hw + 1.0f / 64.0f);
+                }
+                // windows are the LUT's own 4-row groups (rows 0-3, 4-7, ...): its channels are NOT exact one-row shifts of
+                // each other for steep lines, so a row must be read from the channel fill.comp reads it from
+                const int r_start = max(r_lo, 0) & ~3, r_end = min(r_hi, 15);
+                const float ks = dX * FILL_SCALE;
+                const int v_full = __float2int_rn(ks);
+                int prev = 0;
+                int *const colp = acc + c;
+                int r0 = r_start;
+                for (; r0 <= r_end; r0 += 4) {
+                    // texture(uAreaLUT, vec2((y + 8) / 16, v)) for the 4 rows r0 .. r0 + 3 (fill.comp:66-70), fp32 weights
+                    const float lut_x = fmaf(y_line - (float)r0, 16.0f, 119.5f);
+                    const float fx0 = floorf(lut_x), ax = lut_x - fx0;
+                    const float w11 = ax * ay, w10 = ax - w11, w01 = ay - w11, w00 = (1.0f - ax) - w01;
+                    const float k00 = w00 * ks, k10 = w10 * ks, k01 = w01 * ks, k11 = w11 * ks;
+                    const float4 t00 = tex2D<float4>(p.lut_tex, fx0 + 0.5f, fy0 + 0.5f), t10 = tex2D<float4>(p.lut_tex, fx0 + 1.5f, fy0 + 0.5f);
+                    const float4 t01 = tex2D<float4>(p.lut_tex, fx0 + 0.5f, fy0 + 1.5f), t11 = tex2D<float4>(p.lut_tex, fx0 + 1.5f, fy0 + 1.5f);
+                    const int v0 = __float2int_rn(fmaf(t11.x, k11, fmaf(t01.x, k01, fmaf(t10.x, k10, t00.x * k00))));
+                    const int v1 = __float2int_rn(fmaf(t11.y, k11, fmaf(t01.y, k01, fmaf(t10.y, k10, t00.y * k00))));
+                    const int v2 = __float2int_rn(fmaf(t11.z, k11, fmaf(t01.z, k01, fmaf(t10.z, k10, t00.z * k00))));
+                    const int v3 = __float2int_rn(fmaf(t11.w, k11, fmaf(t01.w, k01, fmaf(t10.w, k10, t00.w * k00))));
+                    atomicAdd(colp + r0 * 16, v0 - prev);  // rows past 15 land in the sink row or beyond? no: r0 <= 15
+                    atomicAdd(colp + min(r0 + 1, 16) * 16, v1 - v0);
+                    atomicAdd(colp + min(r0 + 2, 16) * 16, v2 - v1);
+                    atomicAdd(colp + min(r0 + 3, 16) * 16, v3 - v2);
+                    prev = v3;
+                }
+                // every row below the sampled ones is fully covered by the window: one add (telescopes with `prev`)
+                const int tail = r0 > r_start ? r0 : max(r_hi + 1, 0);
+                if (tail <= 15) atomicAdd(colp + tail * 16, v_full - prev);
+            }
+        }
+        __syncwarp();
+        // ---- coverage = prefix sum down each column (+ backdrop), fill rule, clip, RGBA8-unorm quantisation
+        // (fill.comp:131-153); lane (c, h) owns rows h*4 .. h*4+3 and 8+h*4 .. 8+h*4+3 of column c
+        int run = (int)(int8_t)(at.w & 0xffu) * FILL_ONE;
+        int cv[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) cov[q] = backdrop;
-        accumulate_fills(b.fills, begin, end, lane, p.lut_tex, p.lut_band != 0, cov);
-        const int clip_alpha = (int)at.y >= 0 && at.y < b.mask_capacity ? (int)at.y : -1;
-        const uint2 m = quantise_mask(cov, (at.z & 0x100u) != 0, b.masks, clip_alpha, lane);
+        for (int r = 0; r < 16; r++) {
+            run += acc[r * 16 + c_own];
+            const int q = (r & 3) + ((r >> 3) << 2);         // slot of row r for the lane that owns it
+            if (((r >> 2) & 1) == h_own) cv[q] = run;        // rows 0-3, 8-11 -> h 0; rows 4-7, 12-15 -> h 1
+        }
+        __syncwarp();
+        for (int i = (int)lane; i < 17 * 16; i += 32) acc[i] = 0;
+        const bool winding = (at.x >> 31) != 0;
+        uint2 clip = make_uint2(0xffffffffu, 0xffffffffu);
+        if ((int)at.y >= 0 && at.y < b.mask_capacity) clip = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)at.y * 256) + lane);
+        uint32_t bytes[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            int v = cv[q];
+            if (winding) v = min(abs(v), FILL_ONE);
+            else { v &= 2 * FILL_ONE - 1; v = FILL_ONE - abs(FILL_ONE - v); }  // 1 - |1 - mod(cv, 2)|
+            const uint32_t byte = ((uint32_t)v * 255u + (1u << 19)) >> 20;     // round(v * 255)
+            bytes[q] = min(byte, ((q < 4 ? clip.x : clip.y) >> (8 * (q & 3))) & 0xffu);  // fill.comp:147-150
+        }
+        uint2 m;
+        m.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
+        m.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
         reinterpret_cast<uint2 *>(b.masks + (size_t)id * 256)[lane] = m;
+        __syncwarp();
     }
 }
 
@@ -421,6 +562,9 @@ struct CompositeShared {
     uint4 fb[CT_TILES];                     // begin, count, z, cursor of the CTA's tiles
     uint4 prims[CT_PRIMS][2];               // their lists (contiguous in memory because the list offsets come from a scan)
     uint2 cover[CT_WARPS][CT_SLOTS][32];    // fused: mask bytes of the layers being blended, lane-major
+    uint32_t flat_color[CT_TILES];          // packed RGBA8 of the tiles that are one colour
+    uint8_t work[CT_TILES];                 // the other tiles (indices), compacted
+    uint32_t n_work;
     uint32_t next;                          // dynamic tile distribution inside the CTA
 };
 
@@ -511,17 +655,110 @@ __global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchV
         for (uint32_t i = threadIdx.x; i < range_n * 2; i += CT_WARPS * 32) (&sh.prims[0][0])[i] = __ldg(src + i);
     }
     __syncthreads();
-    // ---- stage 3: pull the fills (fused) or masks the lists point to towards this SM
-    if (staged) {
-        for (uint32_t i = threadIdx.x; i < range_n; i += CT_WARPS * 32) {
-            const uint4 q0 = sh.prims[i][0], q1 = sh.prims[i][1];
-            if ((int)q0.y < 0) continue;
-            if (FUSED && (q1.z & PRIM_OWNS_MASK)) {
-                if (q1.x && q0.w < b.fill_capacity) prefetch_l1(b.fills + q0.w);
-                if ((int)q1.y >= 0 && q1.y < b.mask_capacity) prefetch_l1(b.masks + (size_t)q1.y * 256);
-            } else if (q0.y < b.mask_capacity) {
-                prefetch_l1(b.masks + (size_t)q0.y * 256);
-                prefetch_l1(b.masks + (size_t)q0.y * 256 + 128);
+    // ---- stage 3: pull the fills (fused) or masks the lists point to towards this SM (warps 1..), while warp 0 sorts the
+    // CTA's tiles into flat ones -- every surviving layer covers the whole tile with one colour, the common case for
+    // interior and empty tiles: ONE THREAD blends them, as a single pixel -- and the rest.
+    if (threadIdx.x >= 32) {
+        if (staged) {
+            for (uint32_t i = threadIdx.x - 32; i < range_n; i += (CT_WARPS - 1) * 32) {
+                const uint4 q0 = sh.prims[i][0], q1 = sh.prims[i][1];
+                if ((int)q0.y < 0) continue;
+                if (FUSED && (q1.z & PRIM_OWNS_MASK)) {
+                    if (q1.x && q0.w < b.fill_capacity) prefetch_l1(b.fills + q0.w);
+                    if ((int)q1.y >= 0 && q1.y < b.mask_capacity) prefetch_l1(b.masks + (size_t)q1.y * 256);
+                } else if (q0.y < b.mask_capacity) {
+                    prefetch_l1(b.masks + (size_t)q0.y * 256);
+                    prefetch_l1(b.masks + (size_t)q0.y * 256 + 128);
+                }
+            }
+        }
+    } else {
+        const uint32_t t = threadIdx.x;
+        bool is_flat = false, is_work = false;
+        if (t < n_tiles) {
+            const uint4 fbt = sh.fb[t];
+            const uint32_t n = fbt.y;
+            const int z = (int)fbt.z;
+            if (n == 0) {
+                is_flat = clear != 0;  // LOAD_ACTION_LOAD leaves an empty tile alone (tile.comp:743-744)
+            } else if (!clear || !staged || n > 12) {
+                is_work = true;
+            } else {
+                const uint4 *list = &sh.prims[fbt.x - range0][0];
+                float4 dest = clear_color;
+                uint32_t last_key = 0;
+                bool first = true;
+                is_flat = true;
+                while (true) {  // next key in paint order (sort.comp:49-83), z-culled
+                    uint32_t best = 0xffffffffu, best_i = 0;
+                    for (uint32_t i = 0; i < n; i++) {
+                        const uint32_t key = list[i * 2].x;
+                        if ((int)key >= z && (first || key > last_key) && key < best) {
+                            best = key;
+                            best_i = i;
+                        }
+                    }
+                    if (best == 0xffffffffu) break;
+                    last_key = best;
+                    first = false;
+                    const uint4 q0 = list[best_i * 2];
+                    const int tile_ctrl = (int)((q0.z >> 16) & 0xffu), backdrop = (int)q0.z >> 24;
+                    if ((int)q0.y >= 0) {
+                        if (tile_ctrl & 0x3) {  // a mask: per-pixel work
+                            is_flat = false;
+                            break;
+                        }
+                    } else if (backdrop != 0 && (tile_ctrl & 0x2) && (abs(backdrop) & 1) == 0) {
+                        continue;  // tile.comp:786-792
+                    }
+                    const uint32_t color_entry = q0.z & 0xffffu;
+                    float4 src = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (color_entry < p.n_paints) {
+                        if (!SOLID && __ldg(&p.paints[color_entry].ctrl) != 0) {  // textured paint: per-pixel work
+                            is_flat = false;
+                            break;
+                        }
+                        src = __ldg(&p.paints[color_entry].base);
+                    }
+                    src.x *= src.w;
+                    src.y *= src.w;
+                    src.z *= src.w;
+                    blend_over(dest, src);
+                }
+                is_work = !is_flat;
+                if (is_flat) sh.flat_color[t] = pack_rgba8(dest);
+            }
+            if (n == 0 && is_flat) sh.flat_color[t] = pack_rgba8(clear_color);
+        }
+        const unsigned work_mask = __ballot_sync(0xffffffffu, is_work), flat_mask = __ballot_sync(0xffffffffu, is_flat);
+        if (is_work) sh.work[__popc(work_mask & ((1u << t) - 1u))] = (uint8_t)t;
+        if (t == 0) {
+            sh.n_work = (uint32_t)__popc(work_mask);
+            sh.fb[0].w = flat_mask;  // (the cursor word of the header is not needed any more)
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 4a: flat tiles, stored by the whole CTA with 16-byte stores: consecutive threads write consecutive
+    // 16-byte pieces of one pixel row across the CTA's tiles (2 KiB contiguous when the tiles share a tile row)
+    {
+        const uint32_t flat_mask = sh.fb[0].w;
+        if (flat_mask) {
+            for (uint32_t j = threadIdx.x; j < CT_TILES * TILE * 4; j += CT_WARPS * 32) {
+                const uint32_t t = (j >> 2) & (CT_TILES - 1), row = j >> 7, quarter = j & 3u;
+                if (!((flat_mask >> t) & 1u)) continue;
+                const uint32_t map = map0 + t;
+                const int tile_y = (int)(map / (uint32_t)b.fb_tw), tile_x = (int)map - tile_y * b.fb_tw;
+                const int gy = tile_y * TILE + (int)row, gx = tile_x * TILE + (int)quarter * 4;
+                if (gy >= tg.height) continue;
+                const uint32_t px = sh.flat_color[t];
+                uint8_t *dst = tg.pixels + (size_t)gy * tg.pitch + (size_t)gx * 4;
+                if (gx + 3 < tg.width) {
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(px, px, px, px);
+                } else {
+                    for (int k = 0; k < 4; k++)
+                        if (gx + k < tg.width) reinterpret_cast<uint32_t *>(dst)[k] = px;
+                }
             }
         }
     }
@@ -535,12 +772,14 @@ __global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchV
     cs.nearest = (p.sampling_flags & 0xcu) != 0;
     const int c = (int)(lane & 15u), h = (int)(lane >> 4);
 
-    // ---- stage 4: tiles
+    // ---- stage 4b: the other tiles, one warp per tile
+    const uint32_t n_work = sh.n_work;
     while (true) {
-        uint32_t t = 0;
-        if (lane == 0) t = atomicAdd(&sh.next, 1u);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n_tiles) break;
+        uint32_t wi = 0;
+        if (lane == 0) wi = atomicAdd(&sh.next, 1u);
+        wi = __shfl_sync(0xffffffffu, wi, 0);
+        if (wi >= n_work) break;
+        const uint32_t t = sh.work[wi];
         const uint32_t map = map0 + t;
         const uint4 fbt = sh.fb[t];
         uint32_t n = fbt.y;

@@ -327,10 +327,14 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
             const uint32_t local = b.alpha_rank[ti];
             const uint32_t id = first_alpha + local;
             if (id < b.mask_capacity && local < b.alpha_capacity) {
-                // a tile whose fills the clip made invisible keeps its slot but is marked so that fill skips it
+                // a tile whose fills the clip made invisible keeps its slot but is marked so that fill skips it.
+                // Record: tile | winding << 31, clip mask slot, first fill (the scatter left the END of the tile's
+                // range in fill_cursor), backdrop | fill count << 8
+                const uint32_t fill_end = b.fill_cursor[ti];
                 *reinterpret_cast<uint4 *>(&b.alpha_tiles[local]) =
-                    make_uint4(need_new ? ti : 0xffffffffu, (uint32_t)clip_alpha,
-                               ((uint32_t)backdrop & 0xffu) | ((info.ctrl & 0x1) ? 0x100u : 0u), fill_count);
+                    make_uint4((need_new ? ti : 0x7fffffffu) | ((info.ctrl & 0x1) ? 0x80000000u : 0u), (uint32_t)clip_alpha,
+                               fill_end >= fill_count ? fill_end - fill_count : 0u,
+                               ((uint32_t)backdrop & 0xffu) | (fill_count << 8));
                 if (need_new) alpha = (int)id;
             } else {
                 need_new = false;  // the scan flagged OVF_ALPHA: the frame is replayed with more slots
