@@ -156,11 +156,9 @@ int pfcu_end_frame(pfcu_ctx *ctx, pfcu_frame_stats *stats);
 
 /* ---- options */
 enum {
-    /* 0 (default): fill writes every mask, tile reads them back, as fill.comp / tile.comp do. 1: the tile kernel
-     * computes the coverage of a draw batch's alpha tiles from their fills itself, so a draw batch's masks never
-     * reach memory (one kernel, SURVEY.md section 8d B_fused; pfcu_read_mask then only sees clip batches).
-     * Clip batches always write their masks. */
-    PFCU_OPT_FUSED_FILL = 1
+    /* No tunable is defined in this ABI version (a fused fill+tile kernel existed in early builds and lost to the
+     * split pair on every workload); the entry point stays so that options can be added without an ABI bump. */
+    PFCU_OPT_RESERVED = 0
 };
 int pfcu_set_option(pfcu_ctx *ctx, int option, int value);
 

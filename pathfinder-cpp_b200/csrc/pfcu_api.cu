@@ -129,7 +129,6 @@ struct pfcu_ctx {
     cudaArray_t lut_array = nullptr;
     cudaTextureObject_t lut_tex = 0;
     int lut_band = 0;
-    int fused = 0;  // PFCU_OPT_FUSED_FILL
     DevBuf dummy_px;
     // target
     DevBuf own_target;
@@ -142,7 +141,7 @@ struct pfcu_ctx {
     PinnedBuf stage_scene[2];
     DevBuf paints;  // Paint table decoded from the RGBA16F metadata texels
     uint32_t n_paints = 0;
-    int all_solid = 1;
+    int all_solid = 1, unit_range = 1;
     PinnedBuf stage_metadata;
     Page pages[MAX_PAGES];
     PinnedBuf stage_page;
@@ -305,9 +304,6 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     pv.lut_h = c->lut_h;
     pv.lut_tex = c->lut_tex;
     pv.lut_band = c->lut_band;
-    // Fused mode: a draw batch's coverage is computed inside the composite kernel. Clip batches (never composited)
-    // still need their masks in memory for the batches they clip.
-    const bool run_fill = !c->fused || d.path_source != 0;
 
     {
         int r = prof_mark(c, -1);
@@ -321,8 +317,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     LAUNCH_STAGE(PFCU_STAGE_PROPAGATE, launch_propagate(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_SCAN_FB, launch_scan_fb(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_LIST_SCATTER, launch_list_scatter(v, c->stream));
-    if (run_fill) LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, c->stream));
-    c->launches += run_fill ? 10 : 9;
+    LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, c->stream));
+    c->launches += 10;
     c->in_flight = true;
     return PFCU_OK;
 }
@@ -345,6 +341,7 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
     pv.paints = c->paints.as<Paint>();
     pv.n_paints = c->n_paints;
     pv.all_solid = c->all_solid;
+    pv.unit_range = c->unit_range;
     pv.color_px = c->dummy_px.as<uint8_t>();
     pv.color_w = pv.color_h = 1;
     pv.sampling_flags = 0;
@@ -360,7 +357,6 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
     pv.lut_h = c->lut_h;
     pv.lut_tex = c->lut_tex;
     pv.lut_band = c->lut_band;
-    pv.fused = c->fused && s.desc.path_source == 0;
     // masks may have been reallocated since the batch was prepared (growth happens only between attempts)
     s.view.masks = c->masks.as<uint8_t>();
     s.view.mask_capacity = c->mask_cap;
@@ -592,7 +588,7 @@ int pfcu_upload_paint_metadata(pfcu_ctx *c, const uint16_t *half_texels, uint32_
     CUDA_TRY(c->paints.ensure(bytes));
     CUDA_TRY(c->stage_metadata.ensure(bytes));
     Paint *table = static_cast<Paint *>(c->stage_metadata.p);
-    int all_solid = 1;
+    int all_solid = 1, unit_range = 1;
     for (uint32_t i = 0; i < n_paints; i++) {
         const uint16_t *t = half_texels + ((size_t)(i / 128) * 1280 + (size_t)(i % 128) * 10) * 4;
         auto texel = [&](int e) {
@@ -607,6 +603,8 @@ int pfcu_upload_paint_metadata(pfcu_ctx *c, const uint16_t *half_texels, uint32_
         p.fp1 = texel(4);
         p.ctrl = (int32_t)texel(8).x;  // int(extra.x), tile.comp:725
         if (p.ctrl != 0) all_solid = 0;
+        for (float v : {p.base.x, p.base.y, p.base.z, p.base.w})
+            if (!(v >= 0.0f && v <= 1.0f)) unit_range = 0;
         table[i] = p;
     }
     if (n_paints) {
@@ -615,6 +613,7 @@ int pfcu_upload_paint_metadata(pfcu_ctx *c, const uint16_t *half_texels, uint32_
     }
     c->n_paints = n_paints;
     c->all_solid = all_solid;
+    c->unit_range = unit_range;
     return PFCU_OK;
 }
 
@@ -822,8 +821,8 @@ int pfcu_set_option(pfcu_ctx *c, int option, int value) {
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     if (c->frame_open) return fail(PFCU_ERR_STATE, "options cannot change inside a frame");
     switch (option) {
-        case PFCU_OPT_FUSED_FILL:
-            c->fused = value != 0;
+        case PFCU_OPT_RESERVED:
+            (void)value;
             return PFCU_OK;
         default:
             return fail(PFCU_ERR_INVALID, "unknown option %d", option);
@@ -1084,10 +1083,10 @@ int64_t pfcu_read_tile_lists(pfcu_ctx *c, uint32_t batch_id, uint32_t *offsets, 
     std::vector<uint32_t> keys;
     for (uint32_t t = 0; t < T; t++) {
         if (offsets) offsets[t] = (uint32_t)total;
-        const uint32_t begin = std::min(fb[t].begin, D), end = std::min(fb[t].begin + fb[t].count, D);
+        // the scatter only places what the z-buffer does not cull: `cursor` entries of the `count` slots are in use
+        const uint32_t begin = std::min(fb[t].begin, D), end = std::min(fb[t].begin + std::min(fb[t].cursor, fb[t].count), D);
         keys.clear();
-        for (uint32_t k = begin; k < end; k++)
-            if ((int32_t)prims[k].key >= fb[t].z) keys.push_back(prims[k].key);
+        for (uint32_t k = begin; k < end; k++) keys.push_back(prims[k].key);
         std::sort(keys.begin(), keys.end());
         if (tiles) memcpy(tiles + total, keys.data(), keys.size() * 4);
         total += (int64_t)keys.size();
@@ -1103,9 +1102,10 @@ int pfcu_read_mask(pfcu_ctx *c, uint32_t alpha_tile_id, uint8_t out[256]) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     uint8_t raw[256];
     CUDA_TRY(cudaMemcpy(raw, c->masks.as<uint8_t>() + (size_t)alpha_tile_id * 256, 256, cudaMemcpyDeviceToHost));
-    // device layout is lane-major (pfcu_device.h): byte lane * 8 + q = pixel (lane & 15, (lane >> 4) * 4 + q + (q & 4))
+    // device layout is lane-major (pfcu_device.h): byte lane * 8 + q = pixel (column (lane & 3) * 4 + (q & 3),
+    // row (lane >> 2) * 2 + (q >> 2))
     for (int lane = 0; lane < 32; lane++)
-        for (int q = 0; q < 8; q++) out[((lane >> 4) * 4 + q + (q & 4)) * 16 + (lane & 15)] = raw[lane * 8 + q];
+        for (int q = 0; q < 8; q++) out[((lane >> 2) * 2 + (q >> 2)) * 16 + (lane & 3) * 4 + (q & 3)] = raw[lane * 8 + q];
     return PFCU_OK;
 }
 

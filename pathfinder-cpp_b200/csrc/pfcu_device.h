@@ -54,26 +54,20 @@ struct StagedFill {
     uint32_t tile, from, to, pad;
 };
 
-// One entry of a framebuffer tile's list: everything tile.comp reads per layer (tile.comp:765-768) plus, for the
-// fused fill+tile kernel, where the tile's fills are (two 16-byte loads).
+// One entry of a framebuffer tile's list: everything tile.comp reads per layer (tile.comp:765-768), one 16-byte load.
 struct TilePrim {
-    uint32_t key;         // dense tile index: sort key == paint order
-    int32_t alpha;        // mask slot or -1
-    uint32_t ctrl_word;   // paint | ctrl << 16 | backdrop << 24
-    uint32_t fill_begin;  // CSR range of the tile's fills (valid when PRIM_OWNS_MASK)
-    uint32_t fill_count;
-    int32_t clip_alpha;   // mask slot min()-ed into the coverage, or -1
-    uint32_t flags;       // PrimFlags
+    uint32_t key;        // dense tile index: sort key == paint order
+    int32_t alpha;       // mask slot or -1
+    uint32_t ctrl_word;  // paint | ctrl << 16 | backdrop << 24
     uint32_t pad;
 };
-enum PrimFlags { PRIM_OWNS_MASK = 1 };
 
 // Per framebuffer tile: list range + z (one 16-byte load in the composite kernel).
 struct FbTile {
     uint32_t begin;   // from the scan
-    uint32_t count;   // entries before z-cull (counted by propagate)
+    uint32_t count;   // slots: entries before z-cull (counted by propagate)
     int32_t z;        // largest dense tile index of an occluding solid tile (propagate.comp:204-206)
-    uint32_t cursor;  // entries placed so far (list scatter)
+    uint32_t cursor;  // entries actually placed by the list scatter (it leaves out what z culls, sort.comp:62)
 };
 
 struct AlphaTile {
@@ -137,9 +131,9 @@ struct BatchView {
     uint32_t clip_path_count;
     // frame-global
     uint32_t *frame_alpha_counter;  // next free mask slot
-    uint8_t *masks;                 // 256 B per slot, lane-major: byte lane * 8 + q = pixel (column lane & 15,
-                                    // row (lane >> 4) * 4 + q + (q & 4)), so a warp stores / loads a mask with one
-                                    // 8-byte access per lane
+    uint8_t *masks;                 // 256 B per slot, lane-major: byte lane * 8 + q = pixel (column (lane & 3) * 4 +
+                                    // (q & 3), row (lane >> 2) * 2 + (q >> 2)), so a warp stores / loads a mask with
+                                    // one 8-byte access per lane and owns the same pixels as 16-byte framebuffer pieces
     uint32_t mask_capacity;         // slots
 };
 
@@ -160,7 +154,7 @@ struct PaintView {
     int lut_w, lut_h;
     cudaTextureObject_t lut_tex;  // the same LUT behind the texture unit: texel fetch, clamp-to-edge, unorm8 -> float
     int lut_band;              // the LUT saturates outside |x - 152| <= 32 + y / 2 (checked at upload)
-    int fused;                 // composite computes the coverage of draw tiles itself (no mask round trip)
+    int unit_range;            // every base colour component is in [0, 1]
 };
 
 // ---- launchers (each enqueues exactly one kernel on `s` and returns the CUDA status) --------------------------

@@ -1,26 +1,20 @@
 // fill + tile ("composite"): the two rasterizing stages, the HBM-bound end of the path.
 //
-// Pixel ownership is the same in both kernels so that they can be fused: a WARP owns one 16 x 16 tile, lane
-// (c = lane & 15, h = lane >> 4) owns pixel column c, rows h*4 .. h*4+3 and 8+h*4 .. 8+h*4+3, i.e. two of the area
-// LUT's 4-row groups, one in the top half of the tile and one in the bottom half (a short fill touches one half, so
-// the other half's LUT fetches are skipped by the whole warp).
+// Pixel ownership is the same in both kernels: a WARP owns one 16 x 16 tile, lane (k = lane & 3, s = lane >> 2) owns
+// pixel columns 4k .. 4k+3 of rows 2s and 2s+1 -- two 16-byte pieces of the framebuffer, one 8-byte piece of a mask.
 //
 //   fill : pathfinder/shaders/d3d11/fill.comp:51-154. The tile's fills are contiguous (CSR from the scatter), read
-//          once with coalesced 8-byte loads and broadcast by shuffle. The 256 x 256 area LUT sits behind the
-//          texture unit (texel fetch + unorm conversion; the bilinear weights are applied in fp32); lanes whose
-//          column a fill does not overlap (dX == 0, contribution exactly 0) skip it, and 4-row groups outside the
-//          LUT's transition band take the saturated value without fetching. Coverage stays in registers; the mask
-//          is stored once, lane-major, one 8-byte store per lane.
+//          once with coalesced 8-byte loads. The work of a tile is enumerated as (fill, pixel column) pairs, one per
+//          lane; a pair samples the 256 x 256 area LUT (behind the texture unit: texel fetch + unorm conversion, the
+//          bilinear weights are applied in fp32) only for the 4-row groups its line passes through and adds the
+//          result to a 16 x 16 fixed-point accumulator in shared memory as differences down its column.
 //   tile : pathfinder/shaders/d3d11/tile.comp:737-850 with the shading functions of tile.comp:126-134 (combine),
 //          :319-347 (radial gradient), :354-392 (blur), :459-582 (composite), :586-607 (mask), :694-726 (paint
-//          metadata, decoded once per upload into a float table). One 16-byte load gives the tile's list range and
-//          z; the list (<= 32 entries: registers + shuffles, longer: selection from global memory) is ordered by
-//          paint order and z-culled on chip (sort.comp:49-83). While every layer so far covered the whole tile with
-//          one colour, the warp blends ONE pixel instead of 256 and stores the tile with 16-byte stores; the first
-//          masked / textured layer expands it to per-pixel registers.
-//   fused: in the fused instantiation the composite kernel computes the coverage of a draw tile from its fills
-//          right where it is blended -- the mask never leaves the SM (B_fused). Clip masks
-//          (written by the clip batch's fill kernel) are still read from memory and min()-ed in.
+//          metadata, decoded once per upload into a float table). A CTA stages the (z-culled) lists of 32 consecutive
+//          framebuffer tiles in shared memory, orders them by paint order with 8 threads per tile (sort.comp:49-83)
+//          and blends the leading whole-tile layers of every tile as ONE pixel. Tiles that end there are stored by
+//          the whole CTA with 16-byte stores; the others go to one warp each, which blends the remaining layers in
+//          registers with packed f32x2 arithmetic and stores 16 bytes per lane and row.
 #include <cuda_fp16.h>
 
 #include "pfcu_device.h"
@@ -92,103 +86,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, unsigned lane
     return v;
 }
 
-// One 4-row group of one pixel column (computeCoverage's LUT fetch, fill.comp:70, times dX, into cov[0..3]).
-// texture(uAreaLUT, uv) is spelled out in fp32: the texture unit fetches the four texels (point sampling,
-// clamp-to-edge, unorm8 -> float) and the bilinear weights k** (already multiplied by dX) are applied here. The unit's
-// own bilinear mode keeps only 8 fraction bits of the weights, which moves about 1 % of the mask bytes by one step --
-// too coarse for a 1/255 bound on pixels under several translucent layers.
-// Outside the LUT's transition band all four channels are exactly 1 (rows below the line) or exactly 0 (above it);
-// `band` says the uploaded LUT has been checked for that (pfcu_set_area_lut), so when the whole warp is outside the
-// band the group costs two compares instead of four fetches.
-__device__ __forceinline__ void add_group(cudaTextureObject_t lut, bool band, float x, float fx0, float fy0, float half,
-                                          float k00, float k10, float k01, float k11, float dX, float *cov) {
-    int kind = 0;  // 0: sample, 1: all rows fully covered, 2: no row covered
-    if (band) {
-        if (x + 2.0f < 120.0f - half) kind = 1;
-        else if (x - 1.0f > 184.0f + half) kind = 2;
-    }
-    if (__any_sync(__activemask(), kind == 0)) {
-        const float4 t00 = tex2D<float4>(lut, fx0 + 0.5f, fy0 + 0.5f), t10 = tex2D<float4>(lut, fx0 + 1.5f, fy0 + 0.5f);
-        const float4 t01 = tex2D<float4>(lut, fx0 + 0.5f, fy0 + 1.5f), t11 = tex2D<float4>(lut, fx0 + 1.5f, fy0 + 1.5f);
-        cov[0] = fmaf(t11.x, k11, fmaf(t01.x, k01, fmaf(t10.x, k10, fmaf(t00.x, k00, cov[0]))));
-        cov[1] = fmaf(t11.y, k11, fmaf(t01.y, k01, fmaf(t10.y, k10, fmaf(t00.y, k00, cov[1]))));
-        cov[2] = fmaf(t11.z, k11, fmaf(t01.z, k01, fmaf(t10.z, k10, fmaf(t00.z, k00, cov[2]))));
-        cov[3] = fmaf(t11.w, k11, fmaf(t01.w, k01, fmaf(t10.w, k10, fmaf(t00.w, k00, cov[3]))));
-    } else if (kind == 1) {
-        cov[0] += dX; cov[1] += dX; cov[2] += dX; cov[3] += dX;
-    }
-}
-
-// Adds the signed area coverage of fills [begin, end) to the lane's 8 pixels (computeCoverage, fill.comp:51-71,
-// for the lane's two 4-row groups: rows h*4 .. h*4+3 and 8+h*4 .. 8+h*4+3, column c). What only depends on the fill
-// (left end point, slope) is computed once by the lane that loaded it and broadcast by shuffle.
-__device__ __forceinline__ void accumulate_fills(const uint2 *__restrict__ fills, uint32_t begin, uint32_t end,
-                                                 unsigned lane, cudaTextureObject_t lut, bool band, float cov[8]) {
-    const float col = (float)(lane & 15u);  // left edge of the pixel column; tileFragCoord.x = col + 0.5
-    const float fragy0 = (float)((lane >> 4) * 4u) + 0.5f;
-    for (uint32_t at = begin; at < end; at += 32) {
-        float x_from = 0.f, x_to = 0.f, ly = 0.f, d = 0.f;
-        if (at + lane < end) {
-            const uint2 f = __ldg(&fills[at + lane]);
-            x_from = (float)(f.x & 0xffffu) * (1.0f / 256.0f);
-            x_to = (float)(f.y & 0xffffu) * (1.0f / 256.0f);
-            const float y_from = (float)(f.x >> 16) * (1.0f / 256.0f), y_to = (float)(f.y >> 16) * (1.0f / 256.0f);
-            const bool from_left = x_from < x_to;  // fill.comp:53-55
-            ly = from_left ? y_from : y_to;
-            const float ry = from_left ? y_to : y_from;
-            d = (ry - ly) * __fdividef(1.0f, fabsf(x_to - x_from));  // fill.comp:64 (bin never emits x_from == x_to)
-        }
-        const int m = (int)min(32u, end - at);
-        for (int k = 0; k < m; k++) {
-            const float xf = __shfl_sync(0xffffffffu, x_from, k), xt = __shfl_sync(0xffffffffu, x_to, k);
-            // window = clamp(vec2(from.x, to.x), -0.5, 0.5) in fragment-centred coordinates (fill.comp:58) == saturate
-            // in column-edge coordinates; the differences are exact (multiples of 1/256 below 16)
-            const float wx = __saturatef(xf - col), wy = __saturatef(xt - col);
-            const float lyk = __shfl_sync(0xffffffffu, ly, k), dk = __shfl_sync(0xffffffffu, d, k);
-            const float dX = wx - wy;
-            if (dX == 0.0f) continue;  // the fill does not overlap this pixel column: contributes exactly 0
-            // y of the line at the middle of the window (fill.comp:59-63), relative to the group's first pixel centre
-            const float offset = fmaf(0.5f, wx + wy, col - fminf(xf, xt));
-            const float y = fmaf(dk, offset, lyk) - fragy0;
-            // LUT texel coordinates: u = (y + 8) / 16, v = |d * dX| / 16 on 256 x 256 texels, minus the half texel
-            const float lut_x = fmaf(y, 16.0f, 127.5f), lut_y = fmaf(fabsf(dk * dX), 16.0f, -0.5f);
-            const float fx0 = floorf(lut_x), fy0 = floorf(lut_y);
-            const float ax = lut_x - fx0, ay = lut_y - fy0;
-            const float w11 = ax * ay, w10 = ax - w11, w01 = ay - w11, w00 = (1.0f - ax) - w01;
-            const float half = fmaf(0.5f, lut_y, 1.0f);
-            add_group(lut, band, lut_x, fx0, fy0, half, w00 * dX, w10 * dX, w01 * dX, w11 * dX, dX, cov);
-            add_group(lut, band, lut_x - 128.0f, fx0 - 128.0f, fy0, half, w00 * dX, w10 * dX, w01 * dX, w11 * dX, dX,
-                      cov + 4);  // 8 rows further down
-        }
-    }
-}
-
 // round(v * 255) for v in [0, 1] in the low byte (adding 1.5 * 2^23 leaves the integer, nearest-even, in the mantissa)
 __device__ __forceinline__ uint32_t unorm8_bits(float v) { return __float_as_uint(fmaf(v, 255.0f, 12582912.0f)); }
-
-// Coverage -> the 8 mask bytes of the lane (fill.comp:131-153): fill rule, optional min() with the clip mask,
-// RGBA8-unorm quantisation.
-__device__ __forceinline__ uint2 quantise_mask(const float cov[8], bool winding, const uint8_t *masks, int clip_alpha,
-                                               unsigned lane) {
-    float v[8];
-#pragma unroll
-    for (int q = 0; q < 8; q++) {  // fill.comp:133-140
-        if (winding) v[q] = fminf(fabsf(cov[q]), 1.0f);
-        else v[q] = __saturatef(1.0f - fabsf(1.0f - glsl_mod(cov[q], 2.0f)));
-    }
-    if (clip_alpha >= 0) {  // fill.comp:147-150
-        const uint2 clip = __ldg(reinterpret_cast<const uint2 *>(masks + (size_t)clip_alpha * 256) + lane);
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            v[q] = fminf(v[q], (float)(((q < 4 ? clip.x : clip.y) >> (8 * (q & 3))) & 0xffu) * (1.0f / 255.0f));
-    }
-    uint2 out;
-    out.x = __byte_perm(__byte_perm(unorm8_bits(v[0]), unorm8_bits(v[1]), 0x0040),
-                        __byte_perm(unorm8_bits(v[2]), unorm8_bits(v[3]), 0x0040), 0x5410);
-    out.y = __byte_perm(__byte_perm(unorm8_bits(v[4]), unorm8_bits(v[5]), 0x0040),
-                        __byte_perm(unorm8_bits(v[6]), unorm8_bits(v[7]), 0x0040), 0x5410);
-    return out;
-}
 
 constexpr int FILL_WARPS = 8;
 constexpr float FILL_SCALE = 1048576.0f;  // coverage is accumulated in 12.20 fixed point (order-independent sums)
@@ -204,7 +103,7 @@ constexpr int FILL_ONE = 1 << 20;
 // line is steep) and adds what it finds to a 16 x 16 accumulator in shared memory as DIFFERENCES down
 // its column: the tile's coverage is then one prefix sum per column, and "every row below gets dX" is a single add.
 // Sums are fixed point, so the result does not depend on the order in which pairs or atomics land.
-struct FillShared {
+struct __align__(16) FillShared {
     int acc[FILL_WARPS][17][16];  // [row][column]; row 16 is a sink for differences that fall below the tile
 };
 
@@ -220,7 +119,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
     for (int i = (int)lane; i < 17 * 16; i += 32) acc[i] = 0;
     __syncwarp();
     const bool band = p.lut_band != 0;
-    const int c_own = (int)(lane & 15u), h_own = (int)(lane >> 4);
+    const int k_own = (int)(lane & 3u), s_own = (int)(lane >> 2);
 
     for (uint32_t a = warp; a < n_alpha; a += n_warps) {
         const uint32_t id = first_alpha + a;
@@ -320,32 +219,42 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
         }
         __syncwarp();
         // ---- coverage = prefix sum down each column (+ backdrop), fill rule, clip, RGBA8-unorm quantisation
-        // (fill.comp:131-153); lane (c, h) owns rows h*4 .. h*4+3 and 8+h*4 .. 8+h*4+3 of column c
-        int run = (int)(int8_t)(at.w & 0xffu) * FILL_ONE;
-        int cv[8];
+        // (fill.comp:131-153). Lane (k, s) owns columns 4k .. 4k+3 of rows 2s and 2s+1: it reads its two 16-byte pieces
+        // of the accumulator (and zeroes them for the next tile: nobody else reads them), and the sums of the rows
+        // above come from a scan over the lanes of the same column group (stride 4).
+        int4 *const own = reinterpret_cast<int4 *>(acc) + (s_own * 8 + k_own);  // row 2s; row 2s+1 is own[4]
+        const int4 r0 = own[0], r1 = own[4];
+        own[0] = make_int4(0, 0, 0, 0);
+        own[4] = make_int4(0, 0, 0, 0);
+        if (lane < 4) reinterpret_cast<int4 *>(acc)[64 + lane] = make_int4(0, 0, 0, 0);  // the sink row
+        int4 t = make_int4(r0.x + r1.x, r0.y + r1.y, r0.z + r1.z, r0.w + r1.w);
 #pragma unroll
-        for (int r = 0; r < 16; r++) {
-            run += acc[r * 16 + c_own];
-            const int q = (r & 3) + ((r >> 3) << 2);         // slot of row r for the lane that owns it
-            if (((r >> 2) & 1) == h_own) cv[q] = run;        // rows 0-3, 8-11 -> h 0; rows 4-7, 12-15 -> h 1
+        for (int d = 4; d < 32; d <<= 1) {
+            const int ux = __shfl_up_sync(0xffffffffu, t.x, d), uy = __shfl_up_sync(0xffffffffu, t.y, d);
+            const int uz = __shfl_up_sync(0xffffffffu, t.z, d), uw = __shfl_up_sync(0xffffffffu, t.w, d);
+            if (lane >= (unsigned)d) { t.x += ux; t.y += uy; t.z += uz; t.w += uw; }
         }
-        __syncwarp();
-        for (int i = (int)lane; i < 17 * 16; i += 32) acc[i] = 0;
+        const int bd = (int)(int8_t)(at.w & 0xffu) * FILL_ONE;
+        int cv[8];
+        cv[4] = bd + t.x; cv[5] = bd + t.y; cv[6] = bd + t.z; cv[7] = bd + t.w;          // row 2s+1: everything so far
+        cv[0] = cv[4] - r1.x; cv[1] = cv[5] - r1.y; cv[2] = cv[6] - r1.z; cv[3] = cv[7] - r1.w;  // row 2s
         const bool winding = (at.x >> 31) != 0;
-        uint2 clip = make_uint2(0xffffffffu, 0xffffffffu);
-        if ((int)at.y >= 0 && at.y < b.mask_capacity) clip = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)at.y * 256) + lane);
         uint32_t bytes[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
             int v = cv[q];
             if (winding) v = min(abs(v), FILL_ONE);
             else { v &= 2 * FILL_ONE - 1; v = FILL_ONE - abs(FILL_ONE - v); }  // 1 - |1 - mod(cv, 2)|
-            const uint32_t byte = ((uint32_t)v * 255u + (1u << 19)) >> 20;     // round(v * 255)
-            bytes[q] = min(byte, ((q < 4 ? clip.x : clip.y) >> (8 * (q & 3))) & 0xffu);  // fill.comp:147-150
+            bytes[q] = ((uint32_t)v * 255u + (1u << 19)) >> 20;                // round(v * 255)
         }
         uint2 m;
         m.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
         m.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
+        if ((int)at.y >= 0 && at.y < b.mask_capacity) {  // fill.comp:147-150: min() with the clip mask, bytewise
+            const uint2 clip = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)at.y * 256) + lane);
+            m.x = __vminu4(m.x, clip.x);
+            m.y = __vminu4(m.y, clip.y);
+        }
         reinterpret_cast<uint2 *>(b.masks + (size_t)id * 256)[lane] = m;
         __syncwarp();
     }
@@ -528,12 +437,56 @@ __device__ __forceinline__ float4 shade(const Paint &pc, const ColorSampler &cs,
     return color;
 }
 
-constexpr int CT_WARPS = 8;    // warps per CTA
-#ifndef CT_MIN_CTAS
-#define CT_MIN_CTAS 3
+// ---- packed f32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot, each half
+// rounded exactly like the scalar instruction)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
+#ifndef CT_WARPS_N
+#define CT_WARPS_N 8
 #endif
-constexpr int CT_TILES = 32;   // consecutive framebuffer tiles a CTA stages and renders
-constexpr int CT_PRIMS = 160;  // list entries staged in shared memory (longer batches read their lists from global)
+#ifndef CT_MIN_CTAS
+#define CT_MIN_CTAS 4
+#endif
+constexpr int CT_WARPS = CT_WARPS_N;   // warps per CTA
+constexpr int CT_THREADS = CT_WARPS * 32;
+constexpr int CT_TILES = CT_WARPS * 4; // consecutive framebuffer tiles a CTA renders (8 threads order one tile's list)
+constexpr int CT_PRIMS = 256;          // list entries staged at a time (more: the CTA takes its tiles in several rounds)
+
+enum LayerFlags : uint32_t {
+    LF_TEXTURED = 1,  // the paint is not a plain colour (gradient, image, blur, blend mode): per-pixel shading
+    LF_MASKED = 2,    // coverage comes from a mask
+    LF_SKIP = 4       // solid tile of an even-odd path with an even backdrop: invisible (tile.comp:786-792)
+};
 
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
     return __byte_perm(__byte_perm(unorm8_bits(__saturatef(c.x)), unorm8_bits(__saturatef(c.y)), 0x0040),
@@ -556,212 +509,210 @@ __device__ __forceinline__ void blend_over(float4 &dest, const float4 &src) {  /
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-constexpr int CT_SLOTS = 4;  // coverage masks a warp keeps in shared memory between its two phases
-
-struct CompositeShared {
-    uint4 fb[CT_TILES];                     // begin, count, z, cursor of the CTA's tiles
-    uint4 prims[CT_PRIMS][2];               // their lists (contiguous in memory because the list offsets come from a scan)
-    uint2 cover[CT_WARPS][CT_SLOTS][32];    // fused: mask bytes of the layers being blended, lane-major
-    uint32_t flat_color[CT_TILES];          // packed RGBA8 of the tiles that are one colour
-    uint8_t work[CT_TILES];                 // the other tiles (indices), compacted
-    uint32_t n_work;
-    uint32_t next;                          // dynamic tile distribution inside the CTA
-};
-
-// Walks a tile's list in paint order. Lists of up to 32 entries live in registers (one entry per lane, ranked by
-// key); longer ones are walked by repeated selection of the next larger key from the list itself.
-struct ListCursor {
-    uint32_t layer, last_key;
-    bool first;
-};
-
-template <bool FUSED>
-__device__ __forceinline__ bool next_entry(ListCursor &cur, bool in_regs, uint32_t n, uint32_t n_sorted, int z,
-                                           const uint4 *list, const uint4 &e0, const uint4 &e1, uint32_t rank,
-                                           unsigned lane, uint4 &q0, uint4 &q1) {
-    q1 = make_uint4(0u, 0xffffffffu, 0u, 0u);
-    if (in_regs) {
-        if (cur.layer >= n_sorted) return false;
-        const int src = __ffs(__ballot_sync(0xffffffffu, rank == cur.layer)) - 1;
-        q0.x = __shfl_sync(0xffffffffu, e0.x, src);
-        q0.y = __shfl_sync(0xffffffffu, e0.y, src);
-        q0.z = __shfl_sync(0xffffffffu, e0.z, src);
-        q0.w = 0u;
-        if (FUSED) {
-            q0.w = __shfl_sync(0xffffffffu, e0.w, src);
-            q1.x = __shfl_sync(0xffffffffu, e1.x, src);
-            q1.y = __shfl_sync(0xffffffffu, e1.y, src);
-            q1.z = __shfl_sync(0xffffffffu, e1.z, src);
-        }
-        cur.layer++;
-        return true;
-    }
-    // selection: next smallest key >= z that is greater than the last one processed
-    uint32_t best = 0xffffffffu, best_i = 0;
-    for (uint32_t i = lane; i < n; i += 32) {
-        const uint32_t key = list[i * 2].x;
-        if ((int)key >= z && (cur.first || key > cur.last_key) && key < best) {
-            best = key;
-            best_i = i;
-        }
-    }
+// The lane's 8 pixels, channel-major in pairs: pair j holds pixels 2j and 2j+1 (pixel q = column 4k + (q & 3) of row
+// 2s + (q >> 2)), so every blend is a packed f32x2 operation with a per-layer constant or a per-pixel alpha.
+struct PixelBlock {
+    float2 x[4], y[4], z[4], w[4];
+    __device__ __forceinline__ void set_all(float4 c) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
-        if (ob < best) {
-            best = ob;
-            best_i = oi;
+        for (int j = 0; j < 4; j++) {
+            x[j] = splat(c.x);
+            y[j] = splat(c.y);
+            z[j] = splat(c.z);
+            w[j] = splat(c.w);
         }
     }
-    if (best == 0xffffffffu) return false;
-    q0 = list[best_i * 2];
-    if (FUSED) q1 = list[best_i * 2 + 1];
-    cur.last_key = best;
-    cur.first = false;
-    cur.layer++;
-    return true;
+    __device__ __forceinline__ void set(int q, float4 c) {
+        if (q & 1) { x[q >> 1].y = c.x; y[q >> 1].y = c.y; z[q >> 1].y = c.z; w[q >> 1].y = c.w; }
+        else { x[q >> 1].x = c.x; y[q >> 1].x = c.y; z[q >> 1].x = c.z; w[q >> 1].x = c.w; }
+    }
+    // dest = dest * (1 - src.a) + src for one premultiplied colour over all 8 pixels
+    __device__ __forceinline__ void over_all(float4 src) {
+        const float2 ia = splat(1.0f - src.w), sx = splat(src.x), sy = splat(src.y), sz = splat(src.z), sw = splat(src.w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            x[j] = fma2(x[j], ia, sx);
+            y[j] = fma2(y[j], ia, sy);
+            z[j] = fma2(z[j], ia, sz);
+            w[j] = fma2(w[j], ia, sw);
+        }
+    }
+    // pair j: premultiplied sources (sx, sy, sz, sw) of the two pixels
+    __device__ __forceinline__ void over_pair(int j, float2 sx, float2 sy, float2 sz, float2 sw) {
+        const float2 ia = fma2(sw, splat(-1.0f), splat(1.0f));  // 1 - a, one rounding like the scalar subtraction
+        x[j] = fma2(x[j], ia, sx);
+        y[j] = fma2(y[j], ia, sy);
+        z[j] = fma2(z[j], ia, sz);
+        w[j] = fma2(w[j], ia, sw);
+    }
+    // RGBA8 of pixels 4r .. 4r+3 (one 16-byte row piece)
+    template <bool SAT>
+    __device__ __forceinline__ uint4 pack_row(int r) const {
+        uint32_t wd[4];
+#pragma unroll
+        for (int jj = 0; jj < 2; jj++) {
+            const int j = r * 2 + jj;
+            float2 vx = x[j], vy = y[j], vz = z[j], vw = w[j];
+            if (SAT) {
+                vx = make_float2(__saturatef(vx.x), __saturatef(vx.y));
+                vy = make_float2(__saturatef(vy.x), __saturatef(vy.y));
+                vz = make_float2(__saturatef(vz.x), __saturatef(vz.y));
+                vw = make_float2(__saturatef(vw.x), __saturatef(vw.y));
+            }
+            const float2 k = splat(255.0f), m = splat(12582912.0f);  // round to nearest even into the mantissa
+            const float2 bx = fma2(vx, k, m), by = fma2(vy, k, m), bz = fma2(vz, k, m), bw = fma2(vw, k, m);
+            wd[jj * 2 + 0] = __byte_perm(__byte_perm(__float_as_uint(bx.x), __float_as_uint(by.x), 0x0040),
+                                         __byte_perm(__float_as_uint(bz.x), __float_as_uint(bw.x), 0x0040), 0x5410);
+            wd[jj * 2 + 1] = __byte_perm(__byte_perm(__float_as_uint(bx.y), __float_as_uint(by.y), 0x0040),
+                                         __byte_perm(__float_as_uint(bz.y), __float_as_uint(bw.y), 0x0040), 0x5410);
+        }
+        return make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+};
+
+// coverage of pixels 2j, 2j+1 from the lane's 8 mask bytes: float(byte) / 255 like the RGBA8-unorm fetch of
+// tile.comp:594-598 (the byte lands in the mantissa of 2^23, the subtraction is exact)
+__device__ __forceinline__ float2 mask_pair(uint2 mask8, int j, bool even_odd) {
+    const uint32_t m = j < 2 ? mask8.x : mask8.y;
+    const int i0 = (j & 1) * 2;
+    float2 c = make_float2(__uint_as_float(__byte_perm(m, 0x4b000000u, 0x7540 | i0)),
+                           __uint_as_float(__byte_perm(m, 0x4b000000u, 0x7540 | (i0 + 1))));
+    c = mul2(add2(c, splat(-8388608.0f)), splat(1.0f / 255.0f));
+    // sampleMask's even-odd fold, tile.comp:601-602: 1 - |1 - mod(c, 2)| with c in [0, 1]
+    if (even_odd) c = fma2(fma2(c, splat(-1.0f), splat(1.0f)), splat(-1.0f), splat(1.0f));
+    return c;
 }
 
-// One CTA renders CT_TILES consecutive framebuffer tiles. The three dependent loads of a tile (its list header, its
-// list, the fills / masks the list points to) are issued for ALL of the CTA's tiles at once -- header and lists with
-// coalesced loads into shared memory, fills / masks as L1 prefetches -- so their latency is paid once per CTA instead
-// of once per tile; warps then pull tiles from a shared counter, which balances tiles with deep lists against empty
-// ones. A tile is rendered in two phases so that the registers of the coverage computation and of the 8 x RGBA
-// destination pixels are never live together: first the masks of its layers (fused mode), then the blend.
-template <bool SOLID, bool FUSED>
-__global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchView b, PaintView p, TargetView tg,
-                                                                          int clear, float4 clear_color, int origin) {
+struct __align__(16) CompositeShared {
+    uint4 fb[CT_TILES];             // list begin, slots (count before z-cull), z, entries
+    uint4 raw[CT_PRIMS];            // the lists as the scatter left them
+    uint4 sorted[CT_PRIMS];         // in paint order: key, mask slot, paint | ctrl << 16 | backdrop << 24, LayerFlags
+    float4 color[CT_PRIMS];         // base colour of the layer's paint
+    float4 start_color[CT_TILES];   // the tile's colour after its leading whole-tile layers
+    uint32_t start_layer[CT_TILES]; // first layer that needs per-pixel work
+    uint32_t packed_color[CT_TILES];
+    uint32_t txy[CT_TILES];         // tile x | tile y << 16
+    uint8_t work[CT_TILES];         // tiles with per-pixel work
+    uint32_t n_work, next, flat_mask;
+};
+
+struct TileGeom {
+    int gx0, gy0;       // the lane's first pixel
+    bool interior;      // the whole tile is inside the target
+    uint8_t *px0;       // address of the lane's first pixel
+    float fragx, fragy; // gl_FragCoord of the lane's first pixel on the full canvas
+};
+
+// One layer over the lane's 8 pixels (tile.comp:765-842 for one list entry).
+template <bool SOLID>
+__device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 q, const float4 base, const BatchView &b,
+                                            const PaintView &p, const ColorSampler &cs, const TileGeom &g,
+                                            const TargetView &tg, unsigned lane) {
+    const uint32_t fl = q.w;
+    if (fl & LF_SKIP) return;
+    const bool masked = (fl & LF_MASKED) != 0, textured = !SOLID && (fl & LF_TEXTURED) != 0;
+    if (!masked && !textured) {  // one premultiplied colour over the whole tile (calculateColor with maskAlpha == 1)
+        px.over_all(make_float4(base.x * base.w, base.y * base.w, base.z * base.w, base.w));
+        return;
+    }
+    uint2 mask8 = make_uint2(0xffffffffu, 0xffffffffu);
+    if (masked) mask8 = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)q.y * 256) + lane);
+    const bool even_odd = masked && !((q.z >> 16) & 0x1u);
+    if (!textured) {
+        const float2 bx = splat(base.x), by = splat(base.y), bz = splat(base.z), bw = splat(base.w);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 a = mul2(mask_pair(mask8, j, even_odd), bw);  // color.a *= maskAlpha, tile.comp:672
+            px.over_pair(j, mul2(bx, a), mul2(by, a), mul2(bz, a), a);
+        }
+        return;
+    }
+    if (!SOLID) {
+        Paint pc;
+        const uint32_t color_entry = q.z & 0xffffu;
+        pc.base = base;
+        pc.m0 = __ldg(&p.paints[color_entry].m0);
+        pc.m1 = __ldg(&p.paints[color_entry].m1);
+        pc.fp0 = __ldg(&p.paints[color_entry].fp0);
+        pc.fp1 = __ldg(&p.paints[color_entry].fp1);
+        pc.ctrl = __ldg(&p.paints[color_entry].ctrl);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 cov = mask_pair(mask8, j, even_odd);
+            const float fy = g.fragy + (float)(j >> 1), fx = g.fragx + (float)((j & 1) * 2);
+            const float4 s0 = shade<false>(pc, cs, fx, fy, cov.x, (float)tg.width, (float)tg.height);
+            const float4 s1 = shade<false>(pc, cs, fx + 1.0f, fy, cov.y, (float)tg.width, (float)tg.height);
+            px.over_pair(j, make_float2(s0.x, s1.x), make_float2(s0.y, s1.y), make_float2(s0.z, s1.z),
+                         make_float2(s0.w, s1.w));
+        }
+    }
+}
+
+template <bool SOLID>
+__device__ __forceinline__ void store_block(const PixelBlock &px, const TileGeom &g, const TargetView &tg) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint4 v = px.pack_row<!SOLID>(r);
+        uint8_t *dst = g.px0 + (size_t)r * tg.pitch;
+        if (g.interior) {
+            *reinterpret_cast<uint4 *>(dst) = v;
+        } else if (g.gy0 + r < tg.height) {
+            const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (g.gx0 + i < tg.width) reinterpret_cast<uint32_t *>(dst)[i] = wd[i];
+        }
+    }
+}
+
+__device__ __forceinline__ void load_block(PixelBlock &px, const TileGeom &g, const TargetView &tg) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint8_t *src = g.px0 + (size_t)r * tg.pitch;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const bool ok = g.interior || (g.gx0 + i < tg.width && g.gy0 + r < tg.height);
+            px.set(r * 4 + i, ok ? unpack_rgba8(reinterpret_cast<const uint32_t *>(src)[i]) : make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t layer_flags(const uint4 q, uint32_t mask_capacity) {
+    const int alpha = (int)q.y, backdrop = (int)q.z >> 24;
+    const uint32_t ctrl = (q.z >> 16) & 0xffu;
+    if (alpha >= 0) return ((ctrl & 0x3u) && (uint32_t)alpha < mask_capacity) ? (uint32_t)LF_MASKED : 0u;
+    return (backdrop != 0 && (ctrl & 0x2u) && (abs(backdrop) & 1) == 0) ? (uint32_t)LF_SKIP : 0u;  // tile.comp:786-792
+}
+
+// One CTA renders CT_TILES consecutive framebuffer tiles. The dependent loads of a tile (list header -> list -> paints
+// and masks) are issued for all of the CTA's tiles at once, so their latency is paid once per CTA; the lists are
+// ordered and classified by all threads (8 per tile); then the whole CTA stores the one-colour tiles and the warps
+// pull the remaining tiles from a shared counter, which balances deep lists against shallow ones.
+template <bool SOLID>
+__global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : 2) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
+                                                                      float4 clear_color, int origin) {
     __shared__ CompositeShared sh;
-    const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned tid = threadIdx.x, lane = tid & 31;
     const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
     const uint32_t map0 = blockIdx.x * CT_TILES;
     const uint32_t n_tiles = min((uint32_t)CT_TILES, n_fb - map0);
 
     // ---- stage 1: list headers
-    if (threadIdx.x < CT_TILES) {
+    if (tid < CT_TILES) {
         uint4 f = make_uint4(0u, 0u, 0u, 0u);
-        if (threadIdx.x < n_tiles) f = __ldg(reinterpret_cast<const uint4 *>(&b.fb[map0 + threadIdx.x]));
-        sh.fb[threadIdx.x] = f;
-    }
-    if (threadIdx.x == 0) sh.next = 0;
-    __syncthreads();
-    // ---- stage 2: the lists of all tiles are one contiguous range
-    const uint32_t range0 = sh.fb[0].x;
-    uint32_t range_n = sh.fb[n_tiles - 1].x + sh.fb[n_tiles - 1].y - range0;
-    if (range0 + range_n > b.prim_capacity) range_n = range0 < b.prim_capacity ? b.prim_capacity - range0 : 0u;
-    const bool staged = range_n <= CT_PRIMS;
-    if (staged) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(b.prims + range0);
-        for (uint32_t i = threadIdx.x; i < range_n * 2; i += CT_WARPS * 32) (&sh.prims[0][0])[i] = __ldg(src + i);
+        uint32_t xy = 0;
+        if (tid < n_tiles) {
+            f = __ldg(reinterpret_cast<const uint4 *>(&b.fb[map0 + tid]));
+            if (f.x > b.prim_capacity) f.x = b.prim_capacity;
+            if (f.x + f.y > b.prim_capacity) f.y = b.prim_capacity - f.x;
+            f.w = min(f.w, f.y);  // entries the scatter wrote (it leaves out what the z-buffer culls)
+            const uint32_t map = map0 + tid, ty = map / (uint32_t)b.fb_tw;
+            xy = (map - ty * (uint32_t)b.fb_tw) | (ty << 16);
+        }
+        sh.fb[tid] = f;
+        sh.txy[tid] = xy;
     }
     __syncthreads();
-    // ---- stage 3: pull the fills (fused) or masks the lists point to towards this SM (warps 1..), while warp 0 sorts the
-    // CTA's tiles into flat ones -- every surviving layer covers the whole tile with one colour, the common case for
-    // interior and empty tiles: ONE THREAD blends them, as a single pixel -- and the rest.
-    if (threadIdx.x >= 32) {
-        if (staged) {
-            for (uint32_t i = threadIdx.x - 32; i < range_n; i += (CT_WARPS - 1) * 32) {
-                const uint4 q0 = sh.prims[i][0], q1 = sh.prims[i][1];
-                if ((int)q0.y < 0) continue;
-                if (FUSED && (q1.z & PRIM_OWNS_MASK)) {
-                    if (q1.x && q0.w < b.fill_capacity) prefetch_l1(b.fills + q0.w);
-                    if ((int)q1.y >= 0 && q1.y < b.mask_capacity) prefetch_l1(b.masks + (size_t)q1.y * 256);
-                } else if (q0.y < b.mask_capacity) {
-                    prefetch_l1(b.masks + (size_t)q0.y * 256);
-                    prefetch_l1(b.masks + (size_t)q0.y * 256 + 128);
-                }
-            }
-        }
-    } else {
-        const uint32_t t = threadIdx.x;
-        bool is_flat = false, is_work = false;
-        if (t < n_tiles) {
-            const uint4 fbt = sh.fb[t];
-            const uint32_t n = fbt.y;
-            const int z = (int)fbt.z;
-            if (n == 0) {
-                is_flat = clear != 0;  // LOAD_ACTION_LOAD leaves an empty tile alone (tile.comp:743-744)
-            } else if (!clear || !staged || n > 12) {
-                is_work = true;
-            } else {
-                const uint4 *list = &sh.prims[fbt.x - range0][0];
-                float4 dest = clear_color;
-                uint32_t last_key = 0;
-                bool first = true;
-                is_flat = true;
-                while (true) {  // next key in paint order (sort.comp:49-83), z-culled
-                    uint32_t best = 0xffffffffu, best_i = 0;
-                    for (uint32_t i = 0; i < n; i++) {
-                        const uint32_t key = list[i * 2].x;
-                        if ((int)key >= z && (first || key > last_key) && key < best) {
-                            best = key;
-                            best_i = i;
-                        }
-                    }
-                    if (best == 0xffffffffu) break;
-                    last_key = best;
-                    first = false;
-                    const uint4 q0 = list[best_i * 2];
-                    const int tile_ctrl = (int)((q0.z >> 16) & 0xffu), backdrop = (int)q0.z >> 24;
-                    if ((int)q0.y >= 0) {
-                        if (tile_ctrl & 0x3) {  // a mask: per-pixel work
-                            is_flat = false;
-                            break;
-                        }
-                    } else if (backdrop != 0 && (tile_ctrl & 0x2) && (abs(backdrop) & 1) == 0) {
-                        continue;  // tile.comp:786-792
-                    }
-                    const uint32_t color_entry = q0.z & 0xffffu;
-                    float4 src = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (color_entry < p.n_paints) {
-                        if (!SOLID && __ldg(&p.paints[color_entry].ctrl) != 0) {  // textured paint: per-pixel work
-                            is_flat = false;
-                            break;
-                        }
-                        src = __ldg(&p.paints[color_entry].base);
-                    }
-                    src.x *= src.w;
-                    src.y *= src.w;
-                    src.z *= src.w;
-                    blend_over(dest, src);
-                }
-                is_work = !is_flat;
-                if (is_flat) sh.flat_color[t] = pack_rgba8(dest);
-            }
-            if (n == 0 && is_flat) sh.flat_color[t] = pack_rgba8(clear_color);
-        }
-        const unsigned work_mask = __ballot_sync(0xffffffffu, is_work), flat_mask = __ballot_sync(0xffffffffu, is_flat);
-        if (is_work) sh.work[__popc(work_mask & ((1u << t) - 1u))] = (uint8_t)t;
-        if (t == 0) {
-            sh.n_work = (uint32_t)__popc(work_mask);
-            sh.fb[0].w = flat_mask;  // (the cursor word of the header is not needed any more)
-        }
-    }
-    __syncthreads();
-
-    // ---- stage 4a: flat tiles, stored by the whole CTA with 16-byte stores: consecutive threads write consecutive
-    // 16-byte pieces of one pixel row across the CTA's tiles (2 KiB contiguous when the tiles share a tile row)
-    {
-        const uint32_t flat_mask = sh.fb[0].w;
-        if (flat_mask) {
-            for (uint32_t j = threadIdx.x; j < CT_TILES * TILE * 4; j += CT_WARPS * 32) {
-                const uint32_t t = (j >> 2) & (CT_TILES - 1), row = j >> 7, quarter = j & 3u;
-                if (!((flat_mask >> t) & 1u)) continue;
-                const uint32_t map = map0 + t;
-                const int tile_y = (int)(map / (uint32_t)b.fb_tw), tile_x = (int)map - tile_y * b.fb_tw;
-                const int gy = tile_y * TILE + (int)row, gx = tile_x * TILE + (int)quarter * 4;
-                if (gy >= tg.height) continue;
-                const uint32_t px = sh.flat_color[t];
-                uint8_t *dst = tg.pixels + (size_t)gy * tg.pitch + (size_t)gx * 4;
-                if (gx + 3 < tg.width) {
-                    *reinterpret_cast<uint4 *>(dst) = make_uint4(px, px, px, px);
-                } else {
-                    for (int k = 0; k < 4; k++)
-                        if (gx + k < tg.width) reinterpret_cast<uint32_t *>(dst)[k] = px;
-                }
-            }
-        }
-    }
 
     ColorSampler cs;
     cs.px = p.color_px;
@@ -770,208 +721,211 @@ __global__ void __launch_bounds__(CT_WARPS * 32, CT_MIN_CTAS) k_composite(BatchV
     cs.repeat_u = (p.sampling_flags & 1u) != 0;
     cs.repeat_v = (p.sampling_flags & 2u) != 0;
     cs.nearest = (p.sampling_flags & 0xcu) != 0;
-    const int c = (int)(lane & 15u), h = (int)(lane >> 4);
+    const int k_own = (int)(lane & 3u), s_own = (int)(lane >> 2);
+    // gl_FragCoord of the full canvas (only textured paints look at it); render-target pages have no origin
+    const float org_x = (float)(origin ? b.fb_tx0 * TILE : 0) + 0.5f, org_y = (float)(origin ? b.fb_ty0 * TILE : 0) + 0.5f;
 
-    // ---- stage 4b: the other tiles, one warp per tile
-    const uint32_t n_work = sh.n_work;
-    while (true) {
-        uint32_t wi = 0;
-        if (lane == 0) wi = atomicAdd(&sh.next, 1u);
-        wi = __shfl_sync(0xffffffffu, wi, 0);
-        if (wi >= n_work) break;
-        const uint32_t t = sh.work[wi];
-        const uint32_t map = map0 + t;
-        const uint4 fbt = sh.fb[t];
-        uint32_t n = fbt.y;
-        if (n == 0 && !clear) continue;  // tile.comp:743-744
-        const uint32_t begin = fbt.x;
-        if (begin + n > b.prim_capacity) n = begin < b.prim_capacity ? b.prim_capacity - begin : 0u;
-        const int z = (int)fbt.z;
-        const int tile_y = (int)(map / (uint32_t)b.fb_tw), tile_x = (int)map - tile_y * b.fb_tw;
-        const int gx = tile_x * TILE + c, gy0 = tile_y * TILE + h * 4;  // pixel q of the lane: row gy0 + ROW(q)
-#define ROW(q) ((q) + ((q) & 4))
-        const bool interior = (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
-        uint8_t *const px0 = tg.pixels + (size_t)gy0 * tg.pitch + (size_t)gx * 4;  // the lane's first pixel
-
-        // Order by paint order and z-cull (sort.comp:49-83). Keys (dense tile indices) are unique.
-        const bool in_regs = n <= 32;
-        const uint4 *list = staged ? &sh.prims[begin - range0][0] : reinterpret_cast<const uint4 *>(b.prims + begin);
-        uint4 e0 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u), e1 = make_uint4(0u, 0xffffffffu, 0u, 0u);
-        uint32_t rank = 0xffffffffu, n_sorted = 0;
-        if (in_regs && n) {
-            if (lane < n) {
-                e0 = list[lane * 2];
-                if (FUSED) e1 = list[lane * 2 + 1];
-            }
-            const bool keep = lane < n && (int)e0.x >= z;
-            const uint32_t kept_mask = __ballot_sync(0xffffffffu, keep);
-            n_sorted = (uint32_t)__popc(kept_mask);
-            if (keep) {
-                rank = 0;
-                if (n_sorted > 1) {
-                    for (uint32_t j = 0; j < n; j++) {  // keys of the other entries straight from the list
-                        const uint32_t kj = list[j * 2].x;
-                        rank += ((kept_mask >> j) & 1u) && kj < e0.x ? 1u : 0u;
+    uint32_t tb = 0;
+    while (tb < n_tiles) {
+        // ---- the tiles of this round: [tb, te), as many as the staging buffers hold (normally all of them)
+        const uint32_t range0 = sh.fb[tb].x;
+        uint32_t te = n_tiles;
+        if (sh.fb[n_tiles - 1].x + sh.fb[n_tiles - 1].y - range0 > CT_PRIMS) {
+            te = tb + 1;
+            while (te < n_tiles && sh.fb[te].x + sh.fb[te].y - range0 <= CT_PRIMS) te++;
+        }
+        const uint32_t range_n = sh.fb[te - 1].x + sh.fb[te - 1].y - range0;
+        if (tid == 0) {
+            sh.n_work = 0;
+            sh.next = 0;
+            sh.flat_mask = 0;
+        }
+        if (range_n > CT_PRIMS) {
+            // ---- a single tile whose list does not fit (te == tb + 1): one warp walks it by repeated selection of the
+            // next key from global memory
+            __syncthreads();
+            if (tid < 32) {
+                const uint32_t t = tb, xy = sh.txy[t];
+                const uint4 hdr = sh.fb[t];
+                TileGeom g;
+                const int tile_x = (int)(xy & 0xffffu), tile_y = (int)(xy >> 16);
+                g.gx0 = tile_x * TILE + k_own * 4;
+                g.gy0 = tile_y * TILE + s_own * 2;
+                g.interior = (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
+                g.px0 = tg.pixels + (size_t)g.gy0 * tg.pitch + (size_t)g.gx0 * 4;
+                g.fragx = (float)g.gx0 + org_x;
+                g.fragy = (float)g.gy0 + org_y;
+                PixelBlock px;
+                if (clear) px.set_all(clear_color);
+                else load_block(px, g, tg);
+                const uint4 *list = reinterpret_cast<const uint4 *>(b.prims) + hdr.x;
+                uint32_t last_key = 0;
+                bool first = true;
+                while (true) {
+                    uint32_t best = 0xffffffffu, best_i = 0;
+                    for (uint32_t i = lane; i < hdr.w; i += 32) {
+                        const uint32_t key = __ldg(&list[i].x);
+                        if ((first || key > last_key) && key < best) {
+                            best = key;
+                            best_i = i;
+                        }
                     }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const uint32_t ob = __shfl_xor_sync(0xffffffffu, best, o), oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                        if (ob < best) {
+                            best = ob;
+                            best_i = oi;
+                        }
+                    }
+                    if (best == 0xffffffffu) break;
+                    last_key = best;
+                    first = false;
+                    uint4 q = __ldg(&list[best_i]);
+                    q.w = layer_flags(q, b.mask_capacity);
+                    const uint32_t ce = q.z & 0xffffu;
+                    float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ce < p.n_paints) {
+                        base = __ldg(&p.paints[ce].base);
+                        if (!SOLID && __ldg(&p.paints[ce].ctrl) != 0) q.w |= LF_TEXTURED;
+                    }
+                    blend_layer<SOLID>(px, q, base, b, p, cs, g, tg, lane);
                 }
+                if (clear || hdr.w) store_block<SOLID>(px, g, tg);
             }
+            tb = te;
+            __syncthreads();
+            continue;
         }
 
-        // dest: one colour for the whole tile while `uniform`, else 8 pixels per lane
-        bool uniform = clear != 0;
-        float4 dest_u = clear_color;
-        float4 dest[8];
-        if (!uniform) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const bool ok = gx < tg.width && gy0 + ROW(q) < tg.height;
-                dest[q] = ok ? unpack_rgba8(*reinterpret_cast<const uint32_t *>(px0 + (size_t)ROW(q) * tg.pitch))
-                             : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+        // ---- stage 2: the lists of the round's tiles are one contiguous range
+        {
+            const uint4 *src = reinterpret_cast<const uint4 *>(b.prims) + range0;
+            for (uint32_t i = tid; i < range_n; i += CT_THREADS) sh.raw[i] = __ldg(src + i);
         }
+        __syncthreads();
 
-        // gl_FragCoord of the full canvas (only textured paints look at it); render-target pages have no origin
-        const float org_x = (float)(origin ? b.fb_tx0 * TILE : 0), org_y = (float)(origin ? b.fb_ty0 * TILE : 0);
-        const float fragx = (float)gx + org_x + 0.5f;
-        ListCursor cur = {0u, 0u, true};
-        bool more = n != 0;
-        while (more) {
-            // ---- phase 1 (fused): coverage masks of the next layers that own one, up to CT_SLOTS of them
-            ListCursor ahead = cur;
-            uint32_t n_round = 0xffffffffu;  // layers of this round (all remaining ones unless the slots run out)
-            if (FUSED) {
-                int slot = 0;
-                uint32_t seen = 0;
-                uint4 q0, q1;
-                while (next_entry<FUSED>(ahead, in_regs, n, n_sorted, z, list, e0, e1, rank, lane, q0, q1)) {
-                    seen++;
-                    const int tile_ctrl = (int)((q0.z >> 16) & 0xffu);
-                    if ((int)q0.y < 0 || !(tile_ctrl & 0x3) || !(q1.z & PRIM_OWNS_MASK) || q0.y >= b.mask_capacity) continue;
-                    float cov[8];
-                    const float bd = (float)((int)q0.z >> 24);
-#pragma unroll
-                    for (int q = 0; q < 8; q++) cov[q] = bd;
-                    uint32_t fb_ = q0.w, fe_ = q0.w + q1.x;
-                    if (fe_ > b.fill_capacity) fe_ = b.fill_capacity;
-                    if (fb_ > fe_) fb_ = fe_;
-                    accumulate_fills(b.fills, fb_, fe_, lane, p.lut_tex, p.lut_band != 0, cov);
-                    const int clip_alpha = (int)q1.y >= 0 && q1.y < b.mask_capacity ? (int)q1.y : -1;
-                    sh.cover[wib][slot][lane] = quantise_mask(cov, (tile_ctrl & 0x1) != 0, b.masks, clip_alpha, lane);
-                    if (++slot == CT_SLOTS) {
-                        n_round = seen;
-                        break;
+        // ---- stage 3: 8 threads per tile put its list in paint order (keys are unique: rank = number of smaller keys),
+        // look up the layers' colours and start the mask loads; then one of them blends the leading whole-tile layers
+        {
+            const uint32_t t = tb + (tid >> 3), sub = tid & 7u;
+            uint32_t n = 0, off = 0;
+            if (t < te) {
+                const uint4 hdr = sh.fb[t];
+                n = hdr.w;
+                off = hdr.x - range0;
+                for (uint32_t e = sub; e < n; e += 8) {
+                    uint4 q = sh.raw[off + e];
+                    uint32_t rank = 0;
+                    for (uint32_t j = 0; j < n; j++) rank += sh.raw[off + j].x < q.x ? 1u : 0u;
+                    q.w = layer_flags(q, b.mask_capacity);
+                    const uint32_t ce = q.z & 0xffffu;
+                    float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ce < p.n_paints) {
+                        base = __ldg(&p.paints[ce].base);
+                        if (!SOLID && __ldg(&p.paints[ce].ctrl) != 0) q.w |= LF_TEXTURED;
                     }
+                    if (q.w & LF_MASKED) {
+                        prefetch_l1(b.masks + (size_t)q.y * 256);
+                        prefetch_l1(b.masks + (size_t)q.y * 256 + 128);
+                    }
+                    sh.sorted[off + rank] = q;
+                    sh.color[off + rank] = base;
                 }
-                __syncwarp();
             }
-            // ---- phase 2: blend this round's layers
-            int slot = 0;
-            more = false;
-            for (uint32_t i = 0; i < n_round; i++) {
-                uint4 q0, q1;
-                if (!next_entry<FUSED>(cur, in_regs, n, n_sorted, z, list, e0, e1, rank, lane, q0, q1)) break;
-                more = i + 1 == n_round;  // stopped by the slot limit: another round follows
-                // tile.comp:765-800
-                const uint32_t color_entry = q0.z & 0xffffu;
-                int tile_ctrl = (int)((q0.z >> 16) & 0xffu);
-                const int backdrop = (int)q0.z >> 24;
-                const int alpha = (int)q0.y;
-                if (alpha < 0) {
-                    if (backdrop != 0 && (tile_ctrl & 0x2) && (abs(backdrop) & 1) == 0) continue;  // tile.comp:786-792
-                    tile_ctrl &= ~0x3;
-                }
-                const int mask_ctrl = tile_ctrl & 0x3;
-                const bool masked = mask_ctrl != 0 && alpha >= 0 && (uint32_t)alpha < b.mask_capacity;
-
-                Paint pc;
-                if (color_entry < p.n_paints) {
-                    pc.base = __ldg(&p.paints[color_entry].base);
-                    if (!SOLID) {
-                        pc.m0 = __ldg(&p.paints[color_entry].m0);
-                        pc.m1 = __ldg(&p.paints[color_entry].m1);
-                        pc.fp0 = __ldg(&p.paints[color_entry].fp0);
-                        pc.fp1 = __ldg(&p.paints[color_entry].fp1);
-                        pc.ctrl = __ldg(&p.paints[color_entry].ctrl);
-                    }
+            __syncwarp();
+            if (t < te && sub == 0) {
+                bool is_flat = false, is_work = false;
+                float4 dest = clear_color;
+                uint32_t i = 0;
+                if (n == 0) {
+                    is_flat = clear != 0;  // LOAD_ACTION_LOAD leaves an empty tile alone (tile.comp:743-744)
+                } else if (!clear) {
+                    is_work = true;
                 } else {
-                    pc.base = pc.m0 = pc.m1 = pc.fp0 = pc.fp1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    pc.ctrl = 0;
-                }
-                const bool flat_paint = SOLID || pc.ctrl == 0;
-
-                if (!masked && flat_paint) {
-                    // the whole tile gets one premultiplied colour (calculateColor with maskAlpha == 1, tile.comp:611-675)
-                    float4 src = pc.base;
-                    src.x *= src.w;
-                    src.y *= src.w;
-                    src.z *= src.w;
-                    if (uniform) {
-                        blend_over(dest_u, src);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 8; q++) blend_over(dest[q], src);
-                    }
-                    continue;
-                }
-                if (uniform) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) dest[q] = dest_u;
-                    uniform = false;
-                }
-                // the RGBA8 mask texel values tile.comp:594-598 would fetch for the lane's 8 pixels
-                uint2 mask8 = make_uint2(0xffffffffu, 0xffffffffu);
-                if (masked) {
-                    if (FUSED && (q1.z & PRIM_OWNS_MASK)) mask8 = sh.cover[wib][slot++][lane];
-                    else mask8 = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)alpha * 256) + lane);
-                }
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    float mask_alpha = 1.0f;
-                    if (masked) {  // sampleMask, tile.comp:586-607 (backdrop is 0 for alpha tiles)
-                        float cov = (float)(((q < 4 ? mask8.x : mask8.y) >> (8 * (q & 3))) & 0xffu) * (1.0f / 255.0f);
-                        if (!(mask_ctrl & 0x1)) cov = 1.0f - fabsf(1.0f - glsl_mod(cov, 2.0f));
-                        mask_alpha = fminf(mask_alpha, cov);
-                    }
-                    float4 src;
-                    if (flat_paint) {
-                        src = pc.base;
-                        src.w *= mask_alpha;
+                    for (; i < n; i++) {
+                        const uint32_t fl = sh.sorted[off + i].w;
+                        if (fl & LF_SKIP) continue;
+                        if (fl & (LF_MASKED | LF_TEXTURED)) break;
+                        float4 src = sh.color[off + i];
                         src.x *= src.w;
                         src.y *= src.w;
                         src.z *= src.w;
-                    } else {
-                        src = shade<false>(pc, cs, fragx, (float)(gy0 + ROW(q)) + org_y + 0.5f, mask_alpha, (float)tg.width,
-                                           (float)tg.height);
+                        blend_over(dest, src);
                     }
-                    blend_over(dest[q], src);
+                    is_flat = i == n;
+                    is_work = !is_flat;
+                }
+                if (is_flat) {
+                    sh.packed_color[t] = pack_rgba8(dest);
+                    atomicOr(&sh.flat_mask, 1u << (t - tb));
+                } else if (is_work) {
+                    sh.start_color[t] = dest;
+                    sh.start_layer[t] = i;
+                    sh.work[atomicAdd(&sh.n_work, 1u)] = (uint8_t)t;
                 }
             }
-            if (FUSED) __syncwarp();  // the slots are rewritten by the next round
+        }
+        __syncthreads();
+
+        // ---- stage 4a: one-colour tiles, stored by the whole CTA with 16-byte stores: consecutive threads write
+        // consecutive 16-byte pieces of one pixel row across the tiles (contiguous when the tiles share a tile row)
+        {
+            const uint32_t flat_mask = sh.flat_mask;
+            if (flat_mask) {
+                for (uint32_t j = tid; j < CT_TILES * TILE * 4; j += CT_THREADS) {
+                    const uint32_t tt = (j >> 2) % CT_TILES, row = j / (4 * CT_TILES), quarter = j & 3u;
+                    if (!((flat_mask >> tt) & 1u)) continue;
+                    const uint32_t t = tb + tt, xy = sh.txy[t];
+                    const int gy = (int)(xy >> 16) * TILE + (int)row, gx = (int)(xy & 0xffffu) * TILE + (int)quarter * 4;
+                    if (gy >= tg.height) continue;
+                    const uint32_t c = sh.packed_color[t];
+                    uint8_t *dst = tg.pixels + (size_t)gy * tg.pitch + (size_t)gx * 4;
+                    if (gx + 3 < tg.width) {
+                        *reinterpret_cast<uint4 *>(dst) = make_uint4(c, c, c, c);
+                    } else {
+                        for (int i = 0; i < 4; i++)
+                            if (gx + i < tg.width) reinterpret_cast<uint32_t *>(dst)[i] = c;
+                    }
+                }
+            }
         }
 
-        if (uniform) {
-            const uint32_t px = pack_rgba8(dest_u);
-            if (interior) {  // 2 x 16-byte stores per lane: row lane >> 1, pixels (lane & 1) * 8 .. + 7
-                uint4 *d = reinterpret_cast<uint4 *>(tg.pixels + (size_t)(tile_y * TILE + (int)(lane >> 1)) * tg.pitch) +
-                           (tile_x * 4 + (int)(lane & 1u) * 2);
-                d[0] = make_uint4(px, px, px, px);
-                d[1] = make_uint4(px, px, px, px);
-            } else {
-#pragma unroll
-                for (int q = 0; q < 8; q++)
-                    if (gx < tg.width && gy0 + ROW(q) < tg.height)
-                        *reinterpret_cast<uint32_t *>(px0 + (size_t)ROW(q) * tg.pitch) = px;
+        // ---- stage 4b: the other tiles, one warp per tile
+        {
+            const uint32_t n_work = sh.n_work;
+            while (true) {
+                uint32_t wi = 0;
+                if (lane == 0) wi = atomicAdd(&sh.next, 1u);
+                wi = __shfl_sync(0xffffffffu, wi, 0);
+                if (wi >= n_work) break;
+                const uint32_t t = sh.work[wi], xy = sh.txy[t];
+                const uint4 hdr = sh.fb[t];
+                const uint32_t n = hdr.w, off = hdr.x - range0;
+                TileGeom g;
+                const int tile_x = (int)(xy & 0xffffu), tile_y = (int)(xy >> 16);
+                g.gx0 = tile_x * TILE + k_own * 4;
+                g.gy0 = tile_y * TILE + s_own * 2;
+                g.interior = (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
+                g.px0 = tg.pixels + (size_t)g.gy0 * tg.pitch + (size_t)g.gx0 * 4;
+                g.fragx = (float)g.gx0 + org_x;
+                g.fragy = (float)g.gy0 + org_y;
+                PixelBlock px;
+                uint32_t i = 0;
+                if (clear) {
+                    px.set_all(sh.start_color[t]);
+                    i = sh.start_layer[t];
+                } else {
+                    load_block(px, g, tg);
+                }
+                for (; i < n; i++) blend_layer<SOLID>(px, sh.sorted[off + i], sh.color[off + i], b, p, cs, g, tg, lane);
+                store_block<SOLID>(px, g, tg);
             }
-            continue;
         }
-#pragma unroll
-        for (int q = 0; q < 8; q++)
-            if (interior || (gx < tg.width && gy0 + ROW(q) < tg.height))
-                *reinterpret_cast<uint32_t *>(px0 + (size_t)ROW(q) * tg.pitch) = pack_rgba8(dest[q]);
+        tb = te;
+        if (tb < n_tiles) __syncthreads();  // the next round reuses the staging buffers
     }
 }
-
-#undef ROW
 
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
                              const float clear_color[4], int origin, cudaStream_t s) {
@@ -979,14 +933,12 @@ cudaError_t launch_composite(const BatchView &b, const PaintView &p, const Targe
     const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
     const unsigned grid = (n_fb + CT_TILES - 1) / CT_TILES;
     const float4 cc = make_float4(clear_color[0], clear_color[1], clear_color[2], clear_color[3]);
-    const int threads = CT_WARPS * 32;
-    if (p.fused) {
-        if (p.all_solid) k_composite<true, true><<<grid, threads, 0, s>>>(b, p, t, clear, cc, origin);
-        else k_composite<false, true><<<grid, threads, 0, s>>>(b, p, t, clear, cc, origin);
-    } else {
-        if (p.all_solid) k_composite<true, false><<<grid, threads, 0, s>>>(b, p, t, clear, cc, origin);
-        else k_composite<false, false><<<grid, threads, 0, s>>>(b, p, t, clear, cc, origin);
-    }
+    // the plain-colour instantiation skips the saturation before the RGBA8 conversion: src-over of premultiplied colours
+    // in [0, 1] stays in [0, 1]
+    bool unit = p.all_solid && p.unit_range;
+    for (int i = 0; i < 4; i++) unit = unit && clear_color[i] >= 0.0f && clear_color[i] <= 1.0f;
+    if (unit) k_composite<true><<<grid, CT_THREADS, 0, s>>>(b, p, t, clear, cc, origin);
+    else k_composite<false><<<grid, CT_THREADS, 0, s>>>(b, p, t, clear, cc, origin);
     return cudaGetLastError();
 }
 

@@ -366,8 +366,10 @@ cudaError_t launch_propagate(const BatchView &b, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------ list scatter
 
-// One thread per dense tile (coalesced 16-byte state loads): a listed tile takes the next free position of its
-// framebuffer tile's range and writes everything the composite kernel needs about it as one 32-byte record.
+// One thread per dense tile (coalesced 16-byte state loads): a listed tile that the z-buffer does not cull
+// (sort.comp:62: tiles below the top-most occluder of their framebuffer tile) takes the next free position of its
+// framebuffer tile's range and writes what the composite kernel needs about it as one 16-byte record. Culled tiles
+// leave their slot unused: fb[].cursor ends up as the list length, fb[].count stays the slot count.
 __global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
     for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < b.tile_count; ti += gridDim.x * blockDim.x) {
         const uint4 st = *reinterpret_cast<const uint4 *>(&b.tile_state[ti]);
@@ -378,20 +380,13 @@ __global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
         const uint32_t w = (uint32_t)(rect.z - rect.x);
         const int fx = rect.x + (int)(local % w) - b.fb_tx0, fy = rect.y + (int)(local / w) - b.fb_ty0;
         const uint32_t map = (uint32_t)fy * (uint32_t)b.fb_tw + (uint32_t)fx;
-        const uint2 pi = __ldg(reinterpret_cast<const uint2 *>(&b.tpi[path]) + 1);  // first_tile | color, ctrl, backdrop
-        const uint32_t ctrl_word = (pi.y & 0x00ffffffu) | ((st.y & 0xffu) << 24);
-        const uint32_t pos = __ldg(&b.fb[map].begin) + atomicAdd(&b.fb[map].cursor, 1u);
+        const uint4 hdr = *reinterpret_cast<const uint4 *>(&b.fb[map]);  // begin and z are final; cursor is moving
+        if ((int)ti < (int)hdr.z) continue;
+        const uint32_t pi = __ldg(reinterpret_cast<const uint32_t *>(&b.tpi[path]) + 3);  // color, ctrl, backdrop
+        const uint32_t ctrl_word = (pi & 0x00ffffffu) | ((st.y & 0xffu) << 24);
+        const uint32_t pos = hdr.x + atomicAdd(&b.fb[map].cursor, 1u);
         if (pos >= b.prim_capacity) continue;
-        const bool owns = (st.y & (1u << 25)) != 0;
-        uint32_t fill_begin = 0, fill_count = 0;
-        if (owns) {
-            fill_count = b.tile_word[ti] & 0x00ffffffu;
-            const uint32_t end = b.fill_cursor[ti];
-            fill_begin = end >= fill_count ? end - fill_count : 0u;
-        }
-        uint4 *out = reinterpret_cast<uint4 *>(&b.prims[pos]);
-        out[0] = make_uint4(ti, st.x, ctrl_word, fill_begin);
-        out[1] = make_uint4(fill_count, st.w, owns ? (uint32_t)PRIM_OWNS_MASK : 0u, 0u);
+        *reinterpret_cast<uint4 *>(&b.prims[pos]) = make_uint4(ti, st.x, ctrl_word, 0u);
     }
 }
 

@@ -219,10 +219,6 @@ class Renderer:
         return st.as_dict()
 
     # -- options / measurement
-    def set_fused(self, enabled):
-        """PFCU_OPT_FUSED_FILL: draw-batch coverage computed inside the tile kernel (default) or by a separate fill."""
-        _check(self.L.pfcu_set_option(self.h, 1, int(bool(enabled))))
-
     def set_profiling(self, enabled):
         _check(self.L.pfcu_set_profiling(self.h, int(bool(enabled))))
 

@@ -92,23 +92,16 @@ def test_taps_bit_exact_vs_oracle(renderer, area_lut, name):
     fr.close()
 
 
-@pytest.mark.parametrize("fused", [True, False], ids=["fused", "fill+tile"])
 @pytest.mark.parametrize("name", GOLDEN)
-def test_pixels_within_tolerance_of_oracle(renderer, area_lut, name, fused):
-    """Both instantiations of the rasterizing end: the fill.comp / tile.comp split with the mask round trip through memory
-    (the default) and coverage computed inside the tile kernel (fused)."""
+def test_pixels_within_tolerance_of_oracle(renderer, area_lut, name):
+    """The rasterizing end (fill + tile kernels) against the restatement of fill.comp / tile.comp."""
     scene, _ = scenes.load_scene(scenes.golden_path(name))
-    renderer.set_fused(fused)
-    try:
-        renderer.set_scene(scene)
-        renderer.draw(clear=True)
-        got = renderer.pixels()
-    finally:
-        renderer.set_fused(False)
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    got = renderer.pixels()
     fr, want = oracle_frame(scene, area_lut)
     diff = np.abs(got.astype(int) - want.astype(int))
-    print("%s fused=%s: pixels off by one: %d of %d" % (name, fused, int((diff.max(axis=2) > 0).sum()),
-                                                        diff.shape[0] * diff.shape[1]))
+    print("%s: pixels off by one: %d of %d" % (name, int((diff.max(axis=2) > 0).sum()), diff.shape[0] * diff.shape[1]))
     assert diff.max() <= PIXEL_TOL, "max diff %d at %s" % (diff.max(), np.unravel_index(diff.argmax(), diff.shape))
     fr.close()
 
@@ -116,7 +109,6 @@ def test_pixels_within_tolerance_of_oracle(renderer, area_lut, name, fused):
 def test_masks_match_oracle(renderer, area_lut):
     """fill stage alone: every sampled 16 x 16 coverage mask within 1/255 of fill.comp's restatement."""
     scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
-    renderer.set_fused(False)  # masks of draw batches only reach memory in the unfused (default) mode
     renderer.set_scene(scene)
     renderer.draw(clear=True)
     fr, _ = oracle_frame(scene, area_lut)

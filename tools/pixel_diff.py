@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Histogram of |CUDA - oracle| per channel for every golden scene, fused and unfused (tolerance evidence)."""
+"""Histogram of |CUDA - oracle| per channel for every golden scene, (tolerance evidence)."""
 import os
 import sys
 
@@ -18,8 +18,7 @@ for name in sys.argv[1:] or ["tiger_512", "tiger_1024", "features_2048", "demo_c
     scene, _ = scenes.load_scene(scenes.golden_path(name))
     fr = pforacle.Frame(scene, lut)
     want = fr.render().astype(int)
-    for fused in (True, False):
-        r.set_fused(fused)
+    for fused in (False,):
         r.set_scene(scene)
         r.draw(clear=True)
         d = np.abs(r.pixels().astype(int) - want)

@@ -16,12 +16,11 @@ import scenes  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--fixture", default="tiger_4096_scene")
 ap.add_argument("--frames", type=int, default=4)
-ap.add_argument("--split", action="store_true", help="separate fill + tile kernels instead of the fused one")
+ap.add_argument("--split", action="store_true", help="(ignored: fill and tile are always separate kernels)")
 args = ap.parse_args()
 scene, _ = scenes.load_scene(scenes.golden_path(args.fixture))
 lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
 r = pfcu.Renderer(0, lut)
-r.set_fused(not args.split)
 r.set_scene(scene)
 for i in range(args.frames):
     st = r.draw(clear=True)

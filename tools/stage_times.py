@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Per-stage CUDA-event times (median of N frames, L2 flushed between frames) + whole-frame graph time, fused and split.
+"""Per-stage CUDA-event times (median of N frames, L2 flushed between frames) + whole-frame graph time, per library variant.
 Quick A/B tool for kernel variants: PFCU_LIB=... python tools/stage_times.py [fixture]"""
 import os
 import sys
@@ -18,10 +18,9 @@ scene, _ = scenes.load_scene(scenes.golden_path(fixture))
 lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
 stream = torch.cuda.Stream()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for fused in (True, False):
+for fused in (False,):
     r = pfcu.Renderer(0, lut)
     r.set_stream(stream.cuda_stream)
-    r.set_fused(fused)
     r.set_scene(scene)
     r.draw(clear=True)
     r.draw(clear=True)
