@@ -171,7 +171,8 @@ enum {
     PFCU_STAGE_FILL_SCATTER,
     PFCU_STAGE_PROPAGATE,
     PFCU_STAGE_SCAN_FB,
-    PFCU_STAGE_LIST_SCATTER, /* "sort" (ordering itself happens on chip in the tile kernel) */
+    PFCU_STAGE_LIST_SCATTER, /* "sort", first half: contiguous z-culled list per framebuffer tile (paint order is
+                                established on chip by the tile kernel) */
     PFCU_STAGE_FILL,
     PFCU_STAGE_COMPOSITE, /* "tile" */
     PFCU_NUM_STAGES

@@ -101,11 +101,12 @@ struct BatchSlot {
     pfcu_batch_desc desc{};
     PinnedBuf host_meta;  // the four metadata vectors, packed, kept for replay
     size_t off_backdrops = 0, off_meta = 0, off_dice = 0, off_tpi = 0, meta_bytes = 0;
-    DevBuf dev_meta, tile_word, fill_cursor, alpha_rank, col_backdrop, tile_state, lines, line_meta, staging, fills, fb, long_lines,
+    DevBuf dev_meta, tile_word, fill_begin, fill_cursor, alpha_rank, col_backdrop, tile_state, lines, line_meta, staging, fills, fb, long_lines,
         prims, alpha_tiles, scan_desc0, scan_desc1;
     uint32_t line_cap = 0, fill_cap = 0, staging_cap = 0;
     BatchView view{};
     bool prepared = false;
+    cudaEvent_t fill_done = nullptr;  // recorded on the aux stream after this batch's fill kernel
 };
 
 enum CmdKind { CMD_PREPARE, CMD_DRAW };
@@ -122,6 +123,12 @@ struct Cmd {
 struct pfcu_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // second stream of the frame: fill scatter + fill run beside propagate + list building (they only meet again in
+    // the tile kernel), forked and joined with events so that the same code captures into a graph with two branches
+    cudaStream_t aux_stream = nullptr;
+    std::vector<cudaEvent_t> sync_events;
+    size_t sync_used = 0;
+    cudaEvent_t aux_pending = nullptr;  // last event recorded on the aux stream that the main stream has not waited for
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // static resources
     DevBuf lut;
@@ -183,6 +190,7 @@ int find_slot(pfcu_ctx *c, uint32_t batch_id) {
 
 int sync_if_in_flight(pfcu_ctx *c) {
     if (c->in_flight) {
+        if (c->aux_pending) CUDA_TRY(cudaStreamSynchronize(c->aux_stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->in_flight = false;
     }
@@ -204,6 +212,35 @@ int prof_mark(pfcu_ctx *c, int stage) {
     return PFCU_OK;
 }
 
+// Fork / join between the frame's two streams. Events are reused frame after frame.
+int next_sync_event(pfcu_ctx *c, cudaEvent_t *out) {
+    if (c->sync_used == c->sync_events.size()) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->sync_events.push_back(e);
+    }
+    *out = c->sync_events[c->sync_used++];
+    return PFCU_OK;
+}
+
+int order_after(pfcu_ctx *c, cudaStream_t later, cudaStream_t earlier, cudaEvent_t *recorded = nullptr) {
+    cudaEvent_t e;
+    int r = next_sync_event(c, &e);
+    if (r) return r;
+    CUDA_TRY(cudaEventRecord(e, earlier));
+    if (later) CUDA_TRY(cudaStreamWaitEvent(later, e, 0));
+    if (recorded) *recorded = e;
+    return PFCU_OK;
+}
+
+int join_aux(pfcu_ctx *c) {
+    if (c->aux_pending) {
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->aux_pending, 0));
+        c->aux_pending = nullptr;
+    }
+    return PFCU_OK;
+}
+
 #define LAUNCH_STAGE(stage, expr)        \
     do {                                 \
         CUDA_TRY(expr);                  \
@@ -220,6 +257,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     const size_t T = std::max<uint32_t>(fbt, 1);
     CUDA_TRY(s.dev_meta.ensure(s.meta_bytes));
     CUDA_TRY(s.tile_word.ensure(D * 4));
+    CUDA_TRY(s.fill_begin.ensure(D * 4));
     CUDA_TRY(s.fill_cursor.ensure(D * 4));
     CUDA_TRY(s.col_backdrop.ensure(C * 4));
     CUDA_TRY(s.tile_state.ensure(D * sizeof(TileState)));
@@ -262,6 +300,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.fb_ty0 = c->origin_ty;
     v.counters = c->counters.as<BatchCounters>() + slot_index;
     v.tile_word = s.tile_word.as<uint32_t>();
+    v.fill_begin = s.fill_begin.as<uint32_t>();
     v.fill_cursor = s.fill_cursor.as<uint32_t>();
     v.col_backdrop = s.col_backdrop.as<int32_t>();
     v.tile_state = s.tile_state.as<TileState>();
@@ -313,11 +352,30 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     LAUNCH_STAGE(PFCU_STAGE_DICE, launch_dice(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_BIN, launch_bin(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_SCAN_TILES, launch_scan_tiles(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_FILL_SCATTER, launch_fill_scatter(v, c->stream));
+    // Two branches from here: {fill scatter, fill} on the aux stream, {propagate, list building} on the main stream.
+    // fill needs propagate's alpha-tile records; the tile kernel (enqueue_draw) needs both branches. Per-stage
+    // profiling keeps everything on one stream so that the event pairs bracket one kernel each.
+    const bool two_streams = !c->profiling || c->capturing;
+    cudaStream_t aux = two_streams ? c->aux_stream : c->stream;
+    if (two_streams) {
+        int r = order_after(c, aux, c->stream);
+        if (r) return r;
+    }
+    LAUNCH_STAGE(PFCU_STAGE_FILL_SCATTER, launch_fill_scatter(v, aux));
     LAUNCH_STAGE(PFCU_STAGE_PROPAGATE, launch_propagate(v, c->stream));
+    if (two_streams) {
+        int r = order_after(c, aux, c->stream);
+        if (r) return r;
+    }
     LAUNCH_STAGE(PFCU_STAGE_SCAN_FB, launch_scan_fb(v, c->stream));
     LAUNCH_STAGE(PFCU_STAGE_LIST_SCATTER, launch_list_scatter(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, aux));
+    s.fill_done = nullptr;
+    if (two_streams) {
+        int r = order_after(c, nullptr, aux, &s.fill_done);
+        if (r) return r;
+        c->aux_pending = s.fill_done;
+    }
     c->launches += 10;
     c->in_flight = true;
     return PFCU_OK;
@@ -364,6 +422,11 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
         int r = prof_mark(c, -1);
         if (r) return r;
     }
+    if (s.fill_done) {  // join: the masks of this batch (and, the aux stream being in order, of every earlier one)
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, s.fill_done, 0));
+        if (c->aux_pending == s.fill_done) c->aux_pending = nullptr;
+        s.fill_done = nullptr;
+    }
     LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, cmd.target_page < 0, c->stream));
     c->launches += 1;
     c->in_flight = true;
@@ -389,6 +452,7 @@ int pfcu_create(int device_ordinal, pfcu_ctx **out) {
     pfcu_ctx *c = new pfcu_ctx;
     c->device = device_ordinal;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     CUDA_TRY(cudaEventCreate(&c->ev_begin));
     CUDA_TRY(cudaEventCreate(&c->ev_end));
@@ -405,10 +469,11 @@ int pfcu_create(int device_ordinal, pfcu_ctx **out) {
 void pfcu_destroy(pfcu_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->aux_stream);
     cudaStreamSynchronize(c->stream);
     for (auto &s : c->slots) {
         s.host_meta.release();
-        for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
+        for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_begin, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
                           &s.line_meta, &s.long_lines, &s.staging, &s.fills, &s.fb, &s.alpha_rank, &s.prims,
                           &s.alpha_tiles, &s.scan_desc0, &s.scan_desc1})
             b->release();
@@ -435,6 +500,8 @@ void pfcu_destroy(pfcu_ctx *c) {
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_begin);
     cudaEventDestroy(c->ev_end);
+    for (cudaEvent_t e : c->sync_events) cudaEventDestroy(e);
+    cudaStreamDestroy(c->aux_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -655,6 +722,8 @@ int pfcu_begin_frame(pfcu_ctx *c) {
     c->frame_open = true;
     c->event_begin_recorded = false;
     c->prof_used = 0;
+    c->sync_used = 0;
+    c->aux_pending = nullptr;
     return PFCU_OK;
 }
 
@@ -737,6 +806,10 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
     BatchCounters *hc = static_cast<BatchCounters *>(c->host_counters.p);
     const size_t cbytes = sizeof(BatchCounters) * (MAX_SLOTS + 1);
     for (int attempt = 0;; attempt++) {
+        {
+            int r = join_aux(c);  // batches that were prepared but not drawn (clip batches)
+            if (r) return r;
+        }
         if (c->event_begin_recorded) CUDA_TRY(cudaEventRecord(c->ev_end, c->stream));
         // the one read-back of the frame: counters of every batch + the frame alpha counter
         const size_t used = sizeof(BatchCounters) * (size_t)std::max(c->slots_used, 1);
@@ -773,6 +846,7 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
         // grow and replay the recorded frame
         c->retries++;
         c->prof_used = 0;
+        c->sync_used = 0;
         for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
         CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
         CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
@@ -859,6 +933,8 @@ int pfcu_graph_capture(pfcu_ctx *c) {
     for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
     const uint32_t launches_before = c->launches;
     c->capturing = true;
+    c->sync_used = 0;
+    c->aux_pending = nullptr;
     cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
     if (e != cudaSuccess) {
         c->capturing = false;
@@ -870,6 +946,7 @@ int pfcu_graph_capture(pfcu_ctx *c) {
         if (rc) break;
         rc = cmd.kind == CMD_PREPARE ? enqueue_prepare(c, cmd.slot, false) : enqueue_draw(c, cmd);
     }
+    if (!rc) rc = join_aux(c);
     e = cudaStreamEndCapture(c->stream, &c->graph);
     c->capturing = false;
     c->in_flight = false;

@@ -107,7 +107,8 @@ struct BatchView {
     // working set
     BatchCounters *counters;
     uint32_t *tile_word;    // [tile_count] low 24 bits: fill count; high 8 bits: backdrop delta
-    uint32_t *fill_cursor;  // [tile_count] exclusive fill offsets -> end offsets after the scatter
+    uint32_t *fill_begin;   // [tile_count] exclusive fill offsets (CSR; final after the scan)
+    uint32_t *fill_cursor;  // [tile_count] the same offsets, advanced to the end offsets by the fill scatter
     int32_t *col_backdrop;  // [column_count]
     TileState *tile_state;  // [tile_count]
     float4 *lines;          // [line_capacity] clipped lines

@@ -398,9 +398,11 @@ __device__ void composite_rgb(const float d[3], const float s[3], int op, float 
 }
 
 // calculateColor, tile.comp:611-675: premultiplied source colour of one layer at one pixel.
+// (not inlined: one copy of the gradient / blur / blend-mode code per kernel instead of one per pixel and call site --
+// inlining it made the textured instantiation of the tile kernel 1 MB of SASS, an instruction-cache disaster)
 template <bool SOLID>
-__device__ __forceinline__ float4 shade(const Paint &pc, const ColorSampler &cs, float fragx, float fragy,
-                                        float mask_alpha, float fb_w, float fb_h) {
+__device__ __noinline__ float4 shade(const Paint &pc, const ColorSampler &cs, float fragx, float fragy,
+                                     float mask_alpha, float fb_w, float fb_h) {
     float4 color = pc.base;
     if (!SOLID) {
         const int combine = (pc.ctrl >> 8) & 0x3;
@@ -472,11 +474,12 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 
 #ifndef CT_WARPS_N
-#define CT_WARPS_N 8
+#define CT_WARPS_N 4
 #endif
 #ifndef CT_MIN_CTAS
-#define CT_MIN_CTAS 4
+#define CT_MIN_CTAS (32 / CT_WARPS_N)  // 64 registers per thread
 #endif
+#define CT_MIN_CTAS_TEX (CT_MIN_CTAS / 2)  // gradients / images / blend modes: 128 registers
 constexpr int CT_WARPS = CT_WARPS_N;   // warps per CTA
 constexpr int CT_THREADS = CT_WARPS * 32;
 constexpr int CT_TILES = CT_WARPS * 4; // consecutive framebuffer tiles a CTA renders (8 threads order one tile's list)
@@ -688,8 +691,11 @@ __device__ __forceinline__ uint32_t layer_flags(const uint4 q, uint32_t mask_cap
 // and masks) are issued for all of the CTA's tiles at once, so their latency is paid once per CTA; the lists are
 // ordered and classified by all threads (8 per tile); then the whole CTA stores the one-colour tiles and the warps
 // pull the remaining tiles from a shared counter, which balances deep lists against shallow ones.
+// Measured alternatives that lost on tiger 4096^2 (profiles/r01_tile_kernel_experiments.md): a persistent grid with a
+// device-wide ticket counter (39 us vs 31 us); a separate sort kernel that also stores the one-colour tiles and
+// compacts the others into a work list for a warp-per-tile blend kernel (21 + 24 us vs 33 us for this kernel alone).
 template <bool SOLID>
-__global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : 2) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
+__global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_TEX) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
                                                                       float4 clear_color, int origin) {
     __shared__ CompositeShared sh;
     const unsigned tid = threadIdx.x, lane = tid & 31;
@@ -868,22 +874,25 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : 2) k_composi
         }
         __syncthreads();
 
-        // ---- stage 4a: one-colour tiles, stored by the whole CTA with 16-byte stores: consecutive threads write
-        // consecutive 16-byte pieces of one pixel row across the tiles (contiguous when the tiles share a tile row)
+        // ---- stage 4a: one-colour tiles, stored by the whole CTA with 16-byte stores. A thread keeps one tile and one
+        // 16-byte column of it and walks down the rows; consecutive threads write consecutive 16-byte pieces of a pixel
+        // row across the tiles (contiguous when the tiles share a tile row)
         {
-            const uint32_t flat_mask = sh.flat_mask;
-            if (flat_mask) {
-                for (uint32_t j = tid; j < CT_TILES * TILE * 4; j += CT_THREADS) {
-                    const uint32_t tt = (j >> 2) % CT_TILES, row = j / (4 * CT_TILES), quarter = j & 3u;
-                    if (!((flat_mask >> tt) & 1u)) continue;
-                    const uint32_t t = tb + tt, xy = sh.txy[t];
-                    const int gy = (int)(xy >> 16) * TILE + (int)row, gx = (int)(xy & 0xffffu) * TILE + (int)quarter * 4;
-                    if (gy >= tg.height) continue;
-                    const uint32_t c = sh.packed_color[t];
-                    uint8_t *dst = tg.pixels + (size_t)gy * tg.pitch + (size_t)gx * 4;
-                    if (gx + 3 < tg.width) {
-                        *reinterpret_cast<uint4 *>(dst) = make_uint4(c, c, c, c);
-                    } else {
+            constexpr uint32_t ROW_STEP = CT_THREADS / (4 * CT_TILES);
+            const uint32_t tt = (tid >> 2) % CT_TILES, quarter = tid & 3u;
+            if ((sh.flat_mask >> tt) & 1u) {
+                const uint32_t t = tb + tt, xy = sh.txy[t], c = sh.packed_color[t];
+                const int tile_x = (int)(xy & 0xffffu), tile_y = (int)(xy >> 16);
+                const int gx = tile_x * TILE + (int)quarter * 4;
+                int gy = tile_y * TILE + (int)(tid / (4 * CT_TILES));
+                uint8_t *dst = tg.pixels + (size_t)gy * tg.pitch + (size_t)gx * 4;
+                const uint4 v = make_uint4(c, c, c, c);
+                if ((tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height) {
+#pragma unroll
+                    for (uint32_t r = 0; r < TILE / ROW_STEP; r++, dst += ROW_STEP * tg.pitch) *reinterpret_cast<uint4 *>(dst) = v;
+                } else {
+                    for (uint32_t r = 0; r < TILE / ROW_STEP; r++, dst += ROW_STEP * tg.pitch, gy += ROW_STEP) {
+                        if (gy >= tg.height) break;
                         for (int i = 0; i < 4; i++)
                             if (gx + i < tg.width) reinterpret_cast<uint32_t *>(dst)[i] = c;
                     }

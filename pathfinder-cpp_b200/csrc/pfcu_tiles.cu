@@ -170,6 +170,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
             f[k] = (uint32_t)o;
             a[k] = (uint32_t)(o >> 32);
         }
+        *reinterpret_cast<uint4 *>(&b.fill_begin[base]) = make_uint4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<uint4 *>(&b.fill_begin[base + 4]) = make_uint4(f[4], f[5], f[6], f[7]);
         *reinterpret_cast<uint4 *>(&b.fill_cursor[base]) = make_uint4(f[0], f[1], f[2], f[3]);
         *reinterpret_cast<uint4 *>(&b.fill_cursor[base + 4]) = make_uint4(f[4], f[5], f[6], f[7]);
         *reinterpret_cast<uint4 *>(&b.alpha_rank[base]) = make_uint4(a[0], a[1], a[2], a[3]);
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
             if (base + k < n) {
                 const unsigned long long o = off + v[k];
                 if (WHICH == 0) {
+                    b.fill_begin[base + k] = (uint32_t)o;
                     b.fill_cursor[base + k] = (uint32_t)o;
                     b.alpha_rank[base + k] = (uint32_t)(o >> 32);
                 } else {
@@ -328,13 +331,10 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
             const uint32_t id = first_alpha + local;
             if (id < b.mask_capacity && local < b.alpha_capacity) {
                 // a tile whose fills the clip made invisible keeps its slot but is marked so that fill skips it.
-                // Record: tile | winding << 31, clip mask slot, first fill (the scatter left the END of the tile's
-                // range in fill_cursor), backdrop | fill count << 8
-                const uint32_t fill_end = b.fill_cursor[ti];
+                // Record: tile | winding << 31, clip mask slot, first fill, backdrop | fill count << 8
                 *reinterpret_cast<uint4 *>(&b.alpha_tiles[local]) =
                     make_uint4((need_new ? ti : 0x7fffffffu) | ((info.ctrl & 0x1) ? 0x80000000u : 0u), (uint32_t)clip_alpha,
-                               fill_end >= fill_count ? fill_end - fill_count : 0u,
-                               ((uint32_t)backdrop & 0xffu) | (fill_count << 8));
+                               b.fill_begin[ti], ((uint32_t)backdrop & 0xffu) | (fill_count << 8));
                 if (need_new) alpha = (int)id;
             } else {
                 need_new = false;  // the scan flagged OVF_ALPHA: the frame is replayed with more slots

@@ -210,7 +210,8 @@ class Renderer:
             color_page = -1 if int(info[7]) == NONE else int(info[7])
             flags = 0 if int(info[8]) == NONE else int(info[8])
             if int(info[10]) == NONE:
-                _check(L.pfcu_draw_batch(self.h, d.batch_id, -1, color_page, flags, int(first), _p(cc)))
+                for _ in range(int(os.environ.get("PFCU_EXP_DRAWS", "1"))):  # kernel experiments: the tile pass repeated
+                    _check(L.pfcu_draw_batch(self.h, d.batch_id, -1, color_page, flags, int(first), _p(cc)))
                 first = False
             else:
                 _check(L.pfcu_draw_batch(self.h, d.batch_id, int(info[11]), color_page, flags, 1, _p(zero)))
