@@ -348,15 +348,34 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
         int r = prof_mark(c, -1);
         if (r) return r;
     }
-    LAUNCH_STAGE(PFCU_STAGE_INIT, launch_init(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_DICE, launch_dice(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_BIN, launch_bin(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_SCAN_TILES, launch_scan_tiles(v, c->stream));
-    // Two branches from here: {fill scatter, fill} on the aux stream, {propagate, list building} on the main stream.
-    // fill needs propagate's alpha-tile records; the tile kernel (enqueue_draw) needs both branches. Per-stage
-    // profiling keeps everything on one stream so that the event pairs bracket one kernel each.
+    // The frame forks and joins between two streams (graph branches when captured); per-stage profiling keeps
+    // everything on one stream so that the event pairs bracket one kernel each.
+    //   main: counters = 0, dice ........ bin (short walks) ..... scan, propagate, list building ......... tile
+    //   aux :  init (zeroing) ........... bin (long walks) ...... fill scatter ........ fill ............../
     const bool two_streams = !c->profiling || c->capturing;
     cudaStream_t aux = two_streams ? c->aux_stream : c->stream;
+    if (two_streams) {
+        int r = order_after(c, aux, c->stream);  // (also orders this batch's aux work after the previous batch's)
+        if (r) return r;
+    }
+    CUDA_TRY(cudaMemsetAsync(v.counters, 0, sizeof(BatchCounters), c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_INIT, launch_init(v, aux));
+    LAUNCH_STAGE(PFCU_STAGE_DICE, launch_dice(v, c->stream));
+    if (two_streams) {  // bin needs the zeroed tile words; the long-walk kernel needs dice's lines
+        int r = order_after(c, c->stream, aux);
+        if (r) return r;
+        r = order_after(c, aux, c->stream);
+        if (r) return r;
+    }
+    LAUNCH_STAGE(PFCU_STAGE_BIN, launch_bin(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_BIN, launch_bin_long(v, aux));
+    if (two_streams) {
+        int r = order_after(c, c->stream, aux);
+        if (r) return r;
+    }
+    LAUNCH_STAGE(PFCU_STAGE_SCAN_TILES, launch_scan_tiles(v, c->stream));
+    // {fill scatter, fill} on the aux stream, {propagate, list building} on the main stream. fill needs propagate's
+    // alpha-tile records; the tile kernel (enqueue_draw) needs both branches.
     if (two_streams) {
         int r = order_after(c, aux, c->stream);
         if (r) return r;
@@ -376,7 +395,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
         if (r) return r;
         c->aux_pending = s.fill_done;
     }
-    c->launches += 10;
+    c->launches += 11;
     c->in_flight = true;
     return PFCU_OK;
 }

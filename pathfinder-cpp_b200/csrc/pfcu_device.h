@@ -161,7 +161,8 @@ struct PaintView {
 // ---- launchers (each enqueues exactly one kernel on `s` and returns the CUDA status) --------------------------
 cudaError_t launch_init(const BatchView &b, cudaStream_t s);
 cudaError_t launch_dice(const BatchView &b, cudaStream_t s);
-cudaError_t launch_bin(const BatchView &b, cudaStream_t s);
+cudaError_t launch_bin(const BatchView &b, cudaStream_t s);       // walks of up to 12 tiles: a thread per line
+cudaError_t launch_bin_long(const BatchView &b, cudaStream_t s);  // longer walks: a warp per line (independent of launch_bin)
 cudaError_t launch_scan_tiles(const BatchView &b, cudaStream_t s);
 cudaError_t launch_fill_scatter(const BatchView &b, cudaStream_t s);
 cudaError_t launch_propagate(const BatchView &b, cudaStream_t s);
@@ -173,5 +174,35 @@ cudaError_t launch_composite(const BatchView &b, const PaintView &p, const Targe
                              const float clear_color[4], int origin, cudaStream_t s);
 
 int sm_count();
+
+// Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while the previous kernel of its
+// stream is still draining (its CTAs are placed and run up to pdl_wait(), which returns once that kernel has completed
+// and its writes are visible), so the launch latency between the small kernels of a frame overlaps the previous kernel's
+// tail. Every kernel calls pdl_wait() before it touches anything another kernel produced. PFCU_NO_PDL builds use plain
+// launches (the wait is then a no-op).
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+#ifndef PFCU_NO_PDL
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#else
+    (void)attr;
+#endif
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 }  // namespace pfcu

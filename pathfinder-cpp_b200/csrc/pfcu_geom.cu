@@ -69,6 +69,31 @@ __device__ __forceinline__ bool clip_to_view_box(float &l0, float &l1, float &l2
     return false;
 }
 
+constexpr uint32_t BIN_LONG_STEPS = 12;  // walks longer than this go to the long-line kernel, one warp per line
+
+__device__ __forceinline__ uint32_t walk_steps(const float4 &ln) {
+    // the walk visits |dx| + |dy| + 1 tiles (tiler.cpp:191-278) and adds at most two fills per tile
+    const long long tx0 = (int)floorf(ln.x * 0.0625f), ty0 = (int)floorf(ln.y * 0.0625f);
+    const long long tx1 = (int)floorf(ln.z * 0.0625f), ty1 = (int)floorf(ln.w * 0.0625f);
+    long long d = llabs(tx1 - tx0) + llabs(ty1 - ty0) + 1;
+    if (d > MAX_DDA_STEPS) d = MAX_DDA_STEPS;
+    return (uint32_t)d;
+}
+
+// Where a line's fills will be staged, decided as soon as the line exists (dice): 2 slots per tile of its walk. Lines
+// with long walks are queued for k_bin_long at the same time, so that the two bin kernels need nothing from each other
+// and run side by side. One line per thread, per-thread atomics (the rare paths of dice).
+__device__ __forceinline__ uint32_t reserve_line_slots(const BatchView &b, const float4 &ln, uint32_t g) {
+    const uint32_t steps = walk_steps(ln), slots = 2u * steps;
+    const uint32_t slot0 = atomicAdd(&b.counters->n_staging, slots);
+    if (slot0 + slots > b.staging_capacity) {
+        atomicOr(&b.counters->overflow, (uint32_t)OVF_STAGING);
+        return 0xffffffffu;
+    }
+    if (steps > BIN_LONG_STEPS) b.long_lines[atomicAdd(&b.counters->n_long, 1u)] = g;  // capacity == line capacity
+    return slot0;
+}
+
 // ------------------------------------------------------------------------------------------------ dice
 
 struct Cubic {
@@ -141,8 +166,9 @@ __device__ __forceinline__ void dice_emit(const BatchView &b, DiceShared &sh, fl
     } else {
         const uint32_t g = atomicAdd(&b.counters->n_lines, 1u);
         if (g < b.line_capacity) {
-            b.lines[g] = make_float4(l0, l1, l2, l3);
-            b.line_meta[g] = make_uint2(path, 0u);
+            const float4 ln = make_float4(l0, l1, l2, l3);
+            b.lines[g] = ln;
+            b.line_meta[g] = make_uint2(path, reserve_line_slots(b, ln, g));
         } else {
             atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
         }
@@ -226,8 +252,9 @@ __device__ __forceinline__ void dice_emit_warp(const BatchView &b, DiceShared &s
     } else {
         const uint32_t g = atomicAdd(&b.counters->n_lines, 1u);
         if (g < b.line_capacity) {
-            b.lines[g] = make_float4(l0, l1, l2, l3);
-            b.line_meta[g] = make_uint2(path, 0u);
+            const float4 ln = make_float4(l0, l1, l2, l3);
+            b.lines[g] = ln;
+            b.line_meta[g] = make_uint2(path, reserve_line_slots(b, ln, g));
         } else {
             atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
         }
@@ -286,9 +313,47 @@ __device__ __forceinline__ void dice_flush(const BatchView &b, DiceShared &sh) {
     if (base + n_out > b.line_capacity) {
         if (threadIdx.x == 0 && n_out) atomicOr(&b.counters->overflow, (uint32_t)OVF_LINES);
     } else {
-        for (uint32_t i = threadIdx.x; i < n_out; i += DICE_THREADS) {
-            b.lines[base + i] = sh.out_line[i];
-            b.line_meta[base + i] = make_uint2(sh.out_path[i], 0u);
+        // every line also gets its staging slots here (2 per tile of its walk; one atomic per warp) and long walks are
+        // queued for k_bin_long, so the two bin kernels are independent of each other
+        const unsigned lane = threadIdx.x & 31;
+        for (uint32_t i0 = 0; i0 < n_out; i0 += DICE_THREADS) {  // whole warps: the scan below needs all lanes
+            const uint32_t i = i0 + threadIdx.x;
+            bool active = i < n_out;
+            float4 ln = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t steps = 0;
+            if (active) {
+                ln = sh.out_line[i];
+                steps = walk_steps(ln);
+            }
+            const uint32_t slots = 2u * steps;
+            uint32_t incl = slots;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= (unsigned)d) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t sbase = 0;
+            if (lane == 31 && total) sbase = atomicAdd(&b.counters->n_staging, total);
+            sbase = __shfl_sync(0xffffffffu, sbase, 31);
+            uint32_t slot0 = sbase + incl - slots;
+            if (active && slot0 + slots > b.staging_capacity) {
+                atomicOr(&b.counters->overflow, (uint32_t)OVF_STAGING);
+                slot0 = 0xffffffffu;
+            }
+            const bool is_long = active && slot0 != 0xffffffffu && steps > BIN_LONG_STEPS;
+            const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);
+            if (long_mask) {
+                uint32_t lbase = 0;
+                const int leader = __ffs(long_mask) - 1;
+                if ((int)lane == leader) lbase = atomicAdd(&b.counters->n_long, (uint32_t)__popc(long_mask));
+                lbase = __shfl_sync(0xffffffffu, lbase, leader);
+                if (is_long) b.long_lines[lbase + (uint32_t)__popc(long_mask & ((1u << lane) - 1u))] = base + i;
+            }
+            if (active) {
+                b.lines[base + i] = ln;
+                b.line_meta[base + i] = make_uint2(sh.out_path[i], slot0);
+            }
         }
     }
     __syncthreads();
@@ -298,6 +363,7 @@ __device__ __forceinline__ void dice_flush(const BatchView &b, DiceShared &sh) {
 __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chunk_size) {
     extern __shared__ __align__(16) unsigned char dice_smem[];
     DiceShared &sh = *reinterpret_cast<DiceShared *>(dice_smem);
+    pdl_wait();
     const uint32_t n_chunks = (b.segment_count + chunk_size - 1) / chunk_size;
     if (threadIdx.x == 0) {
         sh.q_count[0] = sh.q_count[1] = 0;
@@ -451,8 +517,7 @@ cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
     chunk = chunk < DICE_CHUNK ? DICE_CHUNK : (chunk > DICE_THREADS ? DICE_THREADS : chunk);
     const uint32_t n_chunks = (b.segment_count + chunk - 1) / chunk;
     const uint32_t grid = min(n_chunks, ctas);
-    k_dice<<<grid, DICE_THREADS, sizeof(DiceShared), s>>>(b, chunk);
-    return cudaGetLastError();
+    return launch_pdl(k_dice, grid, DICE_THREADS, sizeof(DiceShared), s, b, chunk);
 }
 
 // ------------------------------------------------------------------------------------------------ bin
@@ -554,20 +619,11 @@ __device__ __forceinline__ uint32_t walk_step_emit(const BatchView &b, const Pat
     return used;
 }
 
-constexpr uint32_t BIN_LONG_STEPS = 12;  // walks longer than this go to the long-line kernel, one warp per line
 constexpr int BIN_CHAIN = 1032;          // crossings per axis the long-line kernel keeps in shared memory (16 K pixels)
 constexpr int BIN_LONG_WARPS = 4;
 
-__device__ __forceinline__ uint32_t walk_steps(const float4 &ln) {
-    // the walk visits |dx| + |dy| + 1 tiles (tiler.cpp:191-278) and adds at most two fills per tile
-    const long long tx0 = (int)floorf(ln.x * 0.0625f), ty0 = (int)floorf(ln.y * 0.0625f);
-    const long long tx1 = (int)floorf(ln.z * 0.0625f), ty1 = (int)floorf(ln.w * 0.0625f);
-    long long d = llabs(tx1 - tx0) + llabs(ty1 - ty0) + 1;
-    if (d > MAX_DDA_STEPS) d = MAX_DDA_STEPS;
-    return (uint32_t)d;
-}
-
 __global__ void __launch_bounds__(128) k_bin(BatchView b) {
+    pdl_wait();
     const uint32_t n_lines = min(b.counters->n_lines, b.line_capacity);
     const unsigned lane = threadIdx.x & 31;
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -576,36 +632,19 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
         bool active = i < n_lines;
         float4 ln = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t path = 0, steps = 0;
+        uint32_t slot0 = 0xffffffffu;
         if (active) {
             ln = b.lines[i];
-            path = b.line_meta[i].x;
+            const uint2 lm = b.line_meta[i];
+            path = lm.x;
+            slot0 = lm.y;
             steps = walk_steps(ln);
         }
-        // staging slots for the whole warp: one atomic
+        // the staging slots were reserved by dice (line_meta.y; ~0: no room, the frame is replayed with more); long
+        // walks are k_bin_long's
         const uint32_t slots = 2u * steps;
-        const uint32_t incl = warp_incl_scan(slots, lane);
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t sbase = 0;
-        if (lane == 31 && total) sbase = atomicAdd(&b.counters->n_staging, total);
-        sbase = __shfl_sync(0xffffffffu, sbase, 31);
-        const uint32_t slot0 = sbase + incl - slots;
-        if (active && slot0 + slots > b.staging_capacity) {
-            atomicOr(&b.counters->overflow, (uint32_t)OVF_STAGING);
-            active = false;
-        }
-        // long walks are queued for k_bin_long (their slots are already reserved)
-        const bool is_long = active && steps > BIN_LONG_STEPS;
-        const unsigned long_mask = __ballot_sync(0xffffffffu, is_long);
-        if (long_mask) {
-            uint32_t lbase = 0;
-            const int leader = __ffs(long_mask) - 1;
-            if ((int)lane == leader) lbase = atomicAdd(&b.counters->n_long, (uint32_t)__popc(long_mask));
-            lbase = __shfl_sync(0xffffffffu, lbase, leader);
-            if (is_long) {
-                b.line_meta[i].y = slot0;
-                b.long_lines[lbase + (uint32_t)__popc(long_mask & ((1u << lane) - 1u))] = i;  // capacity == line capacity
-            }
-        }
+        const bool is_long = steps > BIN_LONG_STEPS;
+        if (slot0 == 0xffffffffu) active = false;
         if (!active || is_long) continue;
         const PathTiles pt = load_path_tiles(b, path);
         Walk w;
@@ -695,6 +734,7 @@ __device__ __forceinline__ bool x_first(float a, float b_, bool tie_x) { return 
 // fill conversion, atomics and stores. 32 steps of the walk per pass instead of one.
 __global__ void __launch_bounds__(BIN_LONG_WARPS * 32) k_bin_long(BatchView b) {
     __shared__ float chain[BIN_LONG_WARPS][2][BIN_CHAIN];
+    pdl_wait();
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t n_long = min(b.counters->n_long, b.line_capacity);
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -773,11 +813,12 @@ __global__ void __launch_bounds__(BIN_LONG_WARPS * 32) k_bin_long(BatchView b) {
 
 cudaError_t launch_bin(const BatchView &b, cudaStream_t s) {
     if (!b.segment_count) return cudaSuccess;
-    k_bin<<<sm_count() * 8, 128, 0, s>>>(b);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    k_bin_long<<<sm_count() * 2, BIN_LONG_WARPS * 32, 0, s>>>(b);
-    return cudaGetLastError();
+    return launch_pdl(k_bin, sm_count() * 8, 128, 0, s, b);
+}
+
+cudaError_t launch_bin_long(const BatchView &b, cudaStream_t s) {
+    if (!b.segment_count) return cudaSuccess;
+    return launch_pdl(k_bin_long, sm_count() * 2, BIN_LONG_WARPS * 32, 0, s, b);
 }
 
 }  // namespace pfcu

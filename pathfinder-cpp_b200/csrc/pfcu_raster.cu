@@ -109,6 +109,7 @@ struct __align__(16) FillShared {
 
 __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView p) {
     __shared__ FillShared sh;
+    pdl_wait();
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -262,8 +263,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
 
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s) {
     if (!b.tile_count || !p.lut_tex) return cudaSuccess;
-    k_fill<<<sm_count() * 8, FILL_WARPS * 32, 0, s>>>(b, p);
-    return cudaGetLastError();
+    return launch_pdl(k_fill, sm_count() * 8, FILL_WARPS * 32, 0, s, b, p);
 }
 
 // ------------------------------------------------------------------------------------------------ tile
@@ -698,6 +698,7 @@ template <bool SOLID>
 __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_TEX) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
                                                                       float4 clear_color, int origin) {
     __shared__ CompositeShared sh;
+    pdl_wait();
     const unsigned tid = threadIdx.x, lane = tid & 31;
     const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
     const uint32_t map0 = blockIdx.x * CT_TILES;
@@ -946,9 +947,8 @@ cudaError_t launch_composite(const BatchView &b, const PaintView &p, const Targe
     // in [0, 1] stays in [0, 1]
     bool unit = p.all_solid && p.unit_range;
     for (int i = 0; i < 4; i++) unit = unit && clear_color[i] >= 0.0f && clear_color[i] <= 1.0f;
-    if (unit) k_composite<true><<<grid, CT_THREADS, 0, s>>>(b, p, t, clear, cc, origin);
-    else k_composite<false><<<grid, CT_THREADS, 0, s>>>(b, p, t, clear, cc, origin);
-    return cudaGetLastError();
+    if (unit) return launch_pdl(k_composite<true>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin);
+    return launch_pdl(k_composite<false>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin);
 }
 
 }  // namespace pfcu

@@ -4,7 +4,7 @@
 //                    search per tile; here a tile is one 32-bit word (fill count | backdrop delta << 24) that only
 //                    needs zeroing, the per-path control word is looked up where it is used. The same kernel
 //                    resets the column backdrops, z-buffer, list counters and scan descriptors that the reference
-//                    uploads from the CPU every batch (d3d11/renderer.cpp:565,868-883).
+//                    uploads from the CPU every batch (d3d11/renderer.cpp:565,868-883). It runs beside dice.
 //   scan           : single-pass decoupled look-back exclusive scan (Merrill & Garland 2016). It replaces the
 //                    reference's atomic bump allocation + CPU read-back + retry (renderer.cpp:559-577,832-845):
 //                    fill offsets per dense tile, list offsets per framebuffer tile.
@@ -42,6 +42,7 @@ __host__ __device__ static inline uint32_t scan_tiles_for(uint32_t n) { return (
 // ------------------------------------------------------------------------------------------------ init
 
 __global__ void __launch_bounds__(256) k_init(BatchView b) {
+    pdl_wait();
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t fbt = (uint32_t)(b.fb_tw * b.fb_th);
@@ -50,11 +51,7 @@ __global__ void __launch_bounds__(256) k_init(BatchView b) {
     for (uint32_t i = tid; i < fbt; i += stride) *reinterpret_cast<uint4 *>(&b.fb[i]) = make_uint4(0u, 0u, 0u, 0u);
     for (uint32_t i = tid; i < scan_tiles_for(b.tile_count); i += stride) b.scan_desc[0][i] = 0ull;
     for (uint32_t i = tid; i < scan_tiles_for(fbt); i += stride) b.scan_desc[1][i] = 0ull;
-    if (tid == 0) {
-        BatchCounters c = {};
-        c.first_alpha = *b.frame_alpha_counter;  // batches of a frame are stream-ordered
-        *b.counters = c;
-    }
+    // (the batch counters are zeroed by a memset node ahead of dice, which runs beside this kernel)
 }
 
 cudaError_t launch_init(const BatchView &b, cudaStream_t s) {
@@ -65,8 +62,7 @@ cudaError_t launch_init(const BatchView &b, cudaStream_t s) {
     const int cap = sm_count() * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    k_init<<<grid, 256, 0, s>>>(b);
-    return cudaGetLastError();
+    return launch_pdl(k_init, (unsigned)grid, 256, 0, s, b);
 }
 
 // ------------------------------------------------------------------------------------------------ scan
@@ -84,6 +80,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
     unsigned long long *desc = b.scan_desc[WHICH];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_warp[SCAN_THREADS / 32], s_prefix;
+    pdl_wait();
     if (threadIdx.x == 0) s_tile = atomicAdd(&b.counters->scan_ticket[WHICH], 1u);  // forward progress: tiles start in order
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -199,7 +196,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
             b.counters->n_fills = fills;
             b.counters->n_alpha = alphas;
             // batches of a frame are stream-ordered: plain read-modify-write of the frame-global mask slot counter
-            const uint32_t first = b.counters->first_alpha;
+            const uint32_t first = *b.frame_alpha_counter;
+            b.counters->first_alpha = first;  // read by propagate and fill, which run after this kernel
             *b.frame_alpha_counter = first + alphas;
             uint32_t ovf = 0;
             if (fills > b.fill_capacity) ovf |= OVF_FILLS;
@@ -214,20 +212,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
 
 cudaError_t launch_scan_tiles(const BatchView &b, cudaStream_t s) {
     if (!b.tile_count) return cudaSuccess;
-    k_scan<0><<<scan_tiles_for(b.tile_count), SCAN_THREADS, 0, s>>>(b);
-    return cudaGetLastError();
+    return launch_pdl(k_scan<0>, scan_tiles_for(b.tile_count), SCAN_THREADS, 0, s, b);
 }
 
 cudaError_t launch_scan_fb(const BatchView &b, cudaStream_t s) {
     const uint32_t fbt = (uint32_t)(b.fb_tw * b.fb_th);
     if (!fbt) return cudaSuccess;
-    k_scan<1><<<scan_tiles_for(fbt), SCAN_THREADS, 0, s>>>(b);
-    return cudaGetLastError();
+    return launch_pdl(k_scan<1>, scan_tiles_for(fbt), SCAN_THREADS, 0, s, b);
 }
 
 // ------------------------------------------------------------------------------------------------ fill scatter
 
 __global__ void __launch_bounds__(256) k_fill_scatter(BatchView b) {
+    pdl_wait();
     const uint32_t n = min(b.counters->n_staging, b.staging_capacity);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint4 f = *reinterpret_cast<const uint4 *>(&b.staging[i]);
@@ -239,8 +236,7 @@ __global__ void __launch_bounds__(256) k_fill_scatter(BatchView b) {
 
 cudaError_t launch_fill_scatter(const BatchView &b, cudaStream_t s) {
     if (!b.segment_count || !b.tile_count) return cudaSuccess;
-    k_fill_scatter<<<sm_count() * 8, 256, 0, s>>>(b);
-    return cudaGetLastError();
+    return launch_pdl(k_fill_scatter, sm_count() * 8, 256, 0, s, b);
 }
 
 // ------------------------------------------------------------------------------------------------ propagate
@@ -248,6 +244,7 @@ cudaError_t launch_fill_scatter(const BatchView &b, cudaStream_t s) {
 // One warp per tile column; lanes are 32 consecutive rows (propagate.comp:95-216, tiler.cpp:369-439). No atomic
 // returns a value: mask slots come from the scan, list positions are taken later by the list scatter.
 __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
+    pdl_wait();
     const uint32_t col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31;
     if (col >= b.column_count) return;
@@ -360,8 +357,7 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
 cudaError_t launch_propagate(const BatchView &b, cudaStream_t s) {
     if (!b.column_count) return cudaSuccess;
     const uint32_t warps_per_block = 4;
-    k_propagate<<<(b.column_count + warps_per_block - 1) / warps_per_block, 128, 0, s>>>(b);
-    return cudaGetLastError();
+    return launch_pdl(k_propagate, (b.column_count + warps_per_block - 1) / warps_per_block, 128, 0, s, b);
 }
 
 // ------------------------------------------------------------------------------------------------ list scatter
@@ -371,6 +367,7 @@ cudaError_t launch_propagate(const BatchView &b, cudaStream_t s) {
 // framebuffer tile's range and writes what the composite kernel needs about it as one 16-byte record. Culled tiles
 // leave their slot unused: fb[].cursor ends up as the list length, fb[].count stays the slot count.
 __global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
+    pdl_wait();
     for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < b.tile_count; ti += gridDim.x * blockDim.x) {
         const uint4 st = *reinterpret_cast<const uint4 *>(&b.tile_state[ti]);
         if (!(st.y & (1u << 24))) continue;
@@ -395,8 +392,7 @@ cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s) {
     int grid = (int)((b.tile_count + 255) / 256);
     const int cap = sm_count() * 8;
     if (grid > cap) grid = cap;
-    k_list_scatter<<<grid, 256, 0, s>>>(b);
-    return cudaGetLastError();
+    return launch_pdl(k_list_scatter, (unsigned)grid, 256, 0, s, b);
 }
 
 }  // namespace pfcu
