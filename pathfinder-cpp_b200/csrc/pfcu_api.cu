@@ -395,7 +395,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
         if (r) return r;
         c->aux_pending = s.fill_done;
     }
-    c->launches += 11;
+    c->launches += 10;
     c->in_flight = true;
     return PFCU_OK;
 }

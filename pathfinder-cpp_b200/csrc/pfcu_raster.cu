@@ -90,21 +90,32 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, unsigned lane
 __device__ __forceinline__ uint32_t unorm8_bits(float v) { return __float_as_uint(fmaf(v, 255.0f, 12582912.0f)); }
 
 constexpr int FILL_WARPS = 8;
+#ifndef FILL_CTAS_PER_SM
+#define FILL_CTAS_PER_SM 4  // 64 registers x 256 threads: one wave
+#endif
+#ifndef FILL_GROUP_N
+#define FILL_GROUP_N 4
+#endif
+constexpr int FILL_GROUP = FILL_GROUP_N;  // alpha tiles a warp rasterizes together (2 or 4)
 constexpr float FILL_SCALE = 1048576.0f;  // coverage is accumulated in 12.20 fixed point (order-independent sums)
 constexpr int FILL_ONE = 1 << 20;
+constexpr int FILL_ACC = 17 * 16;         // accumulator of one tile: [row][column]; row 16 is a sink
 
-// Standalone fill kernel: one warp per alpha tile, and inside the tile one lane per (fill, pixel column) PAIR.
+// Standalone fill kernel: a warp takes FILL_GROUP consecutive alpha tiles, and inside them one lane per
+// (fill, pixel column) PAIR.
 //
 // A fill only touches the pixel columns it spans (5 of 16 on tiger 4096^2) and, in each of them, the few rows around the
 // line; below those rows its contribution is the constant dX, above them 0 (the area LUT saturates there, which
-// pfcu_set_area_lut verifies for the uploaded LUT). So the work of a tile is enumerated as pairs -- a prefix sum over
-// the fills' column spans, lane p takes pair p -- instead of giving every lane a fixed pixel column and every fill to
-// every lane (30 % useful lanes). A pair samples only the 4-row groups its line passes through (one or two unless the
-// line is steep) and adds what it finds to a 16 x 16 accumulator in shared memory as DIFFERENCES down
-// its column: the tile's coverage is then one prefix sum per column, and "every row below gets dX" is a single add.
-// Sums are fixed point, so the result does not depend on the order in which pairs or atomics land.
+// pfcu_set_area_lut verifies for the uploaded LUT). So the work is enumerated as pairs -- a prefix sum over the fills'
+// column spans, lane p takes pair p -- instead of giving every lane a fixed pixel column and every fill to every lane
+// (30 % useful lanes). A tile has 3 fills and 16 pairs on average, so the fills of a few consecutive tiles (contiguous:
+// CSR) are taken together: 32 fills per load, full warps of pairs. A pair samples only the 4-row groups its line passes
+// through (one or two unless the line is steep) and adds what it finds to its tile's 16 x 16 accumulator in shared
+// memory as DIFFERENCES down its column: the tile's coverage is then one prefix sum per column, and "every row below
+// gets dX" is a single add. Sums are fixed point, so the result does not depend on the order in which pairs or atomics
+// land.
 struct __align__(16) FillShared {
-    int acc[FILL_WARPS][17][16];  // [row][column]; row 16 is a sink for differences that fall below the tile
+    int acc[FILL_WARPS][FILL_GROUP][FILL_ACC];
 };
 
 __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView p) {
@@ -117,29 +128,50 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
     uint32_t n_alpha = b.counters->n_alpha;
     if (n_alpha > b.alpha_capacity) n_alpha = b.alpha_capacity;
     int *const acc = &sh.acc[wib][0][0];
-    for (int i = (int)lane; i < 17 * 16; i += 32) acc[i] = 0;
+    for (int i = (int)lane; i < FILL_GROUP * FILL_ACC; i += 32) acc[i] = 0;
     __syncwarp();
     const bool band = p.lut_band != 0;
     const int k_own = (int)(lane & 3u), s_own = (int)(lane >> 2);
 
-    for (uint32_t a = warp; a < n_alpha; a += n_warps) {
-        const uint32_t id = first_alpha + a;
-        if (id >= b.mask_capacity) break;
-        // tile | winding << 31, clip mask slot, first fill, backdrop | fill count << 8
-        const uint4 at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]));
-        if ((at.x & 0x7fffffffu) >= b.tile_count) continue;  // fills that the clip made invisible: no mask needed
-        const uint32_t count = at.w >> 8;
-        uint32_t begin = at.z;
-        if (begin > b.fill_capacity) begin = b.fill_capacity;
-        const uint32_t end = min(begin + count, b.fill_capacity);
+    for (uint32_t a0 = warp * FILL_GROUP; a0 < n_alpha; a0 += n_warps * FILL_GROUP) {
+        // ---- the group's alpha tile records, one per lane: tile | winding << 31, clip mask slot, first fill,
+        // backdrop | fill count << 8
+        uint4 at = make_uint4(0x7fffffffu, 0xffffffffu, 0u, 0u);
+        if (lane < FILL_GROUP && a0 + lane < n_alpha && first_alpha + a0 + lane < b.mask_capacity)
+            at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a0 + lane]));
+        const bool visible = (at.x & 0x7fffffffu) < b.tile_count;  // else: fills that the clip made invisible, no mask
+        const uint32_t begin = min(at.z, b.fill_capacity);
+        const uint32_t count = visible ? min(at.w >> 8, b.fill_capacity - begin) : 0u;
+        // the fills of the group as one sequence: tile g owns [pre_g, pre_g + count_g)
+        uint32_t incl = count;
+#pragma unroll
+        for (int d = 1; d < FILL_GROUP; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, FILL_GROUP - 1);
+        uint32_t pre[FILL_GROUP], rel[FILL_GROUP];  // rel_g: address of the tile's fill j = rel_g + j
+#pragma unroll
+        for (int g = 0; g < FILL_GROUP; g++) {
+            pre[g] = __shfl_sync(0xffffffffu, incl - count, g);
+            rel[g] = __shfl_sync(0xffffffffu, begin, g) - pre[g];
+        }
 
-        for (uint32_t chunk = begin; chunk < end; chunk += 32) {
+        for (uint32_t chunk = 0; chunk < total; chunk += 32) {
             // ---- one fill per lane: what only depends on the fill (fill.comp:53-64)
-            const bool vf = chunk + lane < end;
+            const uint32_t j = chunk + lane;
+            const bool vf = j < total;
             float x_from = 0.f, x_to = 0.f, ly = 0.f, d = 0.f;
-            int c0 = 0, len = 0;
+            int c0 = 0, len = 0, g_own = 0;
             if (vf) {
-                const uint2 f = __ldg(&b.fills[chunk + lane]);
+                uint32_t r = rel[0];
+#pragma unroll
+                for (int g = 1; g < FILL_GROUP; g++)
+                    if (j >= pre[g]) {
+                        g_own = g;
+                        r = rel[g];
+                    }
+                const uint2 f = __ldg(&b.fills[r + j]);
                 x_from = (float)(f.x & 0xffffu) * (1.0f / 256.0f);
                 x_to = (float)(f.y & 0xffffu) * (1.0f / 256.0f);
                 const float y_from = (float)(f.x >> 16) * (1.0f / 256.0f), y_to = (float)(f.y >> 16) * (1.0f / 256.0f);
@@ -153,10 +185,11 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
                 const int c1 = min((int)ceilf(xmax) - 1, 15);
                 len = max(c1 - c0 + 1, 1);
             }
-            const int incl = (int)warp_incl_scan_u32((uint32_t)len, lane);
-            const int excl = incl - len;
-            const int n_pairs = __shfl_sync(0xffffffffu, incl, 31);
-            const int pair_base = excl - c0;  // column of pair p of this fill = p - pair_base
+            const int incl_p = (int)warp_incl_scan_u32((uint32_t)len, lane);
+            const int excl = incl_p - len;
+            const int n_pairs = __shfl_sync(0xffffffffu, incl_p, 31);
+            // column of pair p of this fill = p - pair_base; the fill's tile rides along in the low bits
+            const int pair_base_g = ((excl - c0) << 2) | g_own;
 
             for (int p0 = 0; p0 < n_pairs; p0 += 32) {
                 // ---- which fill does pair p0 + lane belong to: the number of fills that start at or before it, minus one
@@ -167,10 +200,10 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
                 const int srcl = k < 0 ? 0 : (k > 31 ? 31 : k);
                 const float xf = __shfl_sync(0xffffffffu, x_from, srcl), xt = __shfl_sync(0xffffffffu, x_to, srcl);
                 const float lyk = __shfl_sync(0xffffffffu, ly, srcl), dk = __shfl_sync(0xffffffffu, d, srcl);
-                const int pb = __shfl_sync(0xffffffffu, pair_base, srcl);
+                const int pbg = __shfl_sync(0xffffffffu, pair_base_g, srcl);
                 const int pidx = p0 + (int)lane;
                 if (pidx >= n_pairs) continue;
-                const int c = pidx - pb;
+                const int c = pidx - (pbg >> 2);
                 const float col = (float)c;
                 // window = clamp(vec2(from.x, to.x), -0.5, 0.5) in fragment-centred coordinates (fill.comp:58)
                 const float wx = __saturatef(xf - col), wy = __saturatef(xt - col);
@@ -193,7 +226,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
                 const float ks = dX * FILL_SCALE;
                 const int v_full = __float2int_rn(ks);
                 int prev = 0;
-                int *const colp = acc + c;
+                int *const colp = acc + (pbg & 3) * FILL_ACC + c;
                 int r0 = r_start;
                 for (; r0 <= r_end; r0 += 4) {
                     // texture(uAreaLUT, vec2((y + 8) / 16, v)) for the 4 rows r0 .. r0 + 3 (fill.comp:66-70), fp32 weights
@@ -207,7 +240,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
                     const int v1 = __float2int_rn(fmaf(t11.y, k11, fmaf(t01.y, k01, fmaf(t10.y, k10, t00.y * k00))));
                     const int v2 = __float2int_rn(fmaf(t11.z, k11, fmaf(t01.z, k01, fmaf(t10.z, k10, t00.z * k00))));
                     const int v3 = __float2int_rn(fmaf(t11.w, k11, fmaf(t01.w, k01, fmaf(t10.w, k10, t00.w * k00))));
-                    atomicAdd(colp + r0 * 16, v0 - prev);  // rows past 15 land in the sink row or beyond? no: r0 <= 15
+                    atomicAdd(colp + r0 * 16, v0 - prev);  // r0 <= 15; the rows after it may be the sink row
                     atomicAdd(colp + min(r0 + 1, 16) * 16, v1 - v0);
                     atomicAdd(colp + min(r0 + 2, 16) * 16, v2 - v1);
                     atomicAdd(colp + min(r0 + 3, 16) * 16, v3 - v2);
@@ -219,51 +252,59 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
             }
         }
         __syncwarp();
-        // ---- coverage = prefix sum down each column (+ backdrop), fill rule, clip, RGBA8-unorm quantisation
+        // ---- per tile: coverage = prefix sum down each column (+ backdrop), fill rule, clip, RGBA8-unorm quantisation
         // (fill.comp:131-153). Lane (k, s) owns columns 4k .. 4k+3 of rows 2s and 2s+1: it reads its two 16-byte pieces
-        // of the accumulator (and zeroes them for the next tile: nobody else reads them), and the sums of the rows
+        // of the accumulator (and zeroes them for the next group: nobody else reads them), and the sums of the rows
         // above come from a scan over the lanes of the same column group (stride 4).
-        int4 *const own = reinterpret_cast<int4 *>(acc) + (s_own * 8 + k_own);  // row 2s; row 2s+1 is own[4]
-        const int4 r0 = own[0], r1 = own[4];
-        own[0] = make_int4(0, 0, 0, 0);
-        own[4] = make_int4(0, 0, 0, 0);
-        if (lane < 4) reinterpret_cast<int4 *>(acc)[64 + lane] = make_int4(0, 0, 0, 0);  // the sink row
-        int4 t = make_int4(r0.x + r1.x, r0.y + r1.y, r0.z + r1.z, r0.w + r1.w);
 #pragma unroll
-        for (int d = 4; d < 32; d <<= 1) {
-            const int ux = __shfl_up_sync(0xffffffffu, t.x, d), uy = __shfl_up_sync(0xffffffffu, t.y, d);
-            const int uz = __shfl_up_sync(0xffffffffu, t.z, d), uw = __shfl_up_sync(0xffffffffu, t.w, d);
-            if (lane >= (unsigned)d) { t.x += ux; t.y += uy; t.z += uz; t.w += uw; }
-        }
-        const int bd = (int)(int8_t)(at.w & 0xffu) * FILL_ONE;
-        int cv[8];
-        cv[4] = bd + t.x; cv[5] = bd + t.y; cv[6] = bd + t.z; cv[7] = bd + t.w;          // row 2s+1: everything so far
-        cv[0] = cv[4] - r1.x; cv[1] = cv[5] - r1.y; cv[2] = cv[6] - r1.z; cv[3] = cv[7] - r1.w;  // row 2s
-        const bool winding = (at.x >> 31) != 0;
-        uint32_t bytes[8];
+        for (int g = 0; g < FILL_GROUP; g++) {
+            const uint32_t at_x = __shfl_sync(0xffffffffu, at.x, g), at_y = __shfl_sync(0xffffffffu, at.y, g);
+            const uint32_t at_w = __shfl_sync(0xffffffffu, at.w, g);
+            if ((at_x & 0x7fffffffu) >= b.tile_count) continue;  // (warp-uniform)
+            int4 *const own = reinterpret_cast<int4 *>(acc + g * FILL_ACC) + (s_own * 8 + k_own);  // row 2s; row 2s+1 is own[4]
+            const int4 r0 = own[0], r1 = own[4];
+            own[0] = make_int4(0, 0, 0, 0);
+            own[4] = make_int4(0, 0, 0, 0);
+            if (lane < 4) reinterpret_cast<int4 *>(acc + g * FILL_ACC)[64 + lane] = make_int4(0, 0, 0, 0);  // the sink row
+            int4 t = make_int4(r0.x + r1.x, r0.y + r1.y, r0.z + r1.z, r0.w + r1.w);
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            int v = cv[q];
-            if (winding) v = min(abs(v), FILL_ONE);
-            else { v &= 2 * FILL_ONE - 1; v = FILL_ONE - abs(FILL_ONE - v); }  // 1 - |1 - mod(cv, 2)|
-            bytes[q] = ((uint32_t)v * 255u + (1u << 19)) >> 20;                // round(v * 255)
+            for (int d = 4; d < 32; d <<= 1) {
+                const int ux = __shfl_up_sync(0xffffffffu, t.x, d), uy = __shfl_up_sync(0xffffffffu, t.y, d);
+                const int uz = __shfl_up_sync(0xffffffffu, t.z, d), uw = __shfl_up_sync(0xffffffffu, t.w, d);
+                if (lane >= (unsigned)d) { t.x += ux; t.y += uy; t.z += uz; t.w += uw; }
+            }
+            const int bd = (int)(int8_t)(at_w & 0xffu) * FILL_ONE;
+            int cv[8];
+            cv[4] = bd + t.x; cv[5] = bd + t.y; cv[6] = bd + t.z; cv[7] = bd + t.w;          // row 2s+1: everything so far
+            cv[0] = cv[4] - r1.x; cv[1] = cv[5] - r1.y; cv[2] = cv[6] - r1.z; cv[3] = cv[7] - r1.w;  // row 2s
+            uint32_t bytes[8];
+            if (at_x >> 31) {  // winding: min(|cv|, 1)
+#pragma unroll
+                for (int q = 0; q < 8; q++) bytes[q] = ((uint32_t)min(abs(cv[q]), FILL_ONE) * 255u + (1u << 19)) >> 20;
+            } else {           // even-odd: 1 - |1 - mod(cv, 2)|
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const int v = FILL_ONE - abs(FILL_ONE - (cv[q] & (2 * FILL_ONE - 1)));
+                    bytes[q] = ((uint32_t)v * 255u + (1u << 19)) >> 20;
+                }
+            }
+            uint2 m;
+            m.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
+            m.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
+            if ((int)at_y >= 0 && at_y < b.mask_capacity) {  // fill.comp:147-150: min() with the clip mask, bytewise
+                const uint2 clip = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)at_y * 256) + lane);
+                m.x = __vminu4(m.x, clip.x);
+                m.y = __vminu4(m.y, clip.y);
+            }
+            reinterpret_cast<uint2 *>(b.masks + (size_t)(first_alpha + a0 + g) * 256)[lane] = m;
         }
-        uint2 m;
-        m.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
-        m.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
-        if ((int)at.y >= 0 && at.y < b.mask_capacity) {  // fill.comp:147-150: min() with the clip mask, bytewise
-            const uint2 clip = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)at.y * 256) + lane);
-            m.x = __vminu4(m.x, clip.x);
-            m.y = __vminu4(m.y, clip.y);
-        }
-        reinterpret_cast<uint2 *>(b.masks + (size_t)id * 256)[lane] = m;
         __syncwarp();
     }
 }
 
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s) {
     if (!b.tile_count || !p.lut_tex) return cudaSuccess;
-    return launch_pdl(k_fill, sm_count() * 8, FILL_WARPS * 32, 0, s, b, p);
+    return launch_pdl(k_fill, sm_count() * FILL_CTAS_PER_SM, FILL_WARPS * 32, 0, s, b, p);
 }
 
 // ------------------------------------------------------------------------------------------------ tile
