@@ -447,15 +447,22 @@ def run_batch(args, rank, world):
     scene, asset, size, native = load_workload(args.workload)
     lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
     mine = sharding.scene_share(args.frames, world, rank)
-    stream = torch.cuda.Stream()
-    r = pfcu.Renderer(local, lut)
-    r.set_stream(stream.cuda_stream)
-    r.set_scene(scene)
-    r.draw(clear=True)
-    r.draw(clear=True)
-    r.graph_capture()
-    for _ in range(max(args.warmup, 3)):
-        r.graph_launch()
+    # Independent frames do not wait for each other: K renderer contexts (own stream, own framebuffer, own captured
+    # frame graph) take the frames round-robin, so the small kernels of several 512 x 512 frames share the GPU.
+    n_ctx = max(1, min(args.contexts, len(mine) or 1))
+    master = torch.cuda.Stream()
+    streams = [torch.cuda.Stream() for _ in range(n_ctx)]
+    rs = []
+    for st in streams:
+        r = pfcu.Renderer(local, lut)
+        r.set_stream(st.cuda_stream)
+        r.set_scene(scene)
+        r.draw(clear=True)
+        r.draw(clear=True)
+        r.graph_capture()
+        for _ in range(max(args.warmup, 3)):
+            r.graph_launch()
+        rs.append(r)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -463,11 +470,17 @@ def run_batch(args, rank, world):
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0.record(master)
+    for st in streams:
+        st.wait_event(e0)
     for _ in range(args.steps):
-        for _f in mine:
-            r.graph_launch()
-    e1.record(stream)
+        for i, _f in enumerate(mine):
+            rs[i % n_ctx].graph_launch()
+    for st in streams:
+        done = torch.cuda.Event()
+        done.record(st)
+        master.wait_event(done)
+    e1.record(master)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -475,7 +488,9 @@ def run_batch(args, rank, world):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     clocks = sampler.stop()
-    gstats = r.graph_finish()
+    gstats = rs[0].graph_finish()
+    for r in rs[1:]:
+        r.graph_finish()
     if rank == 0:
         ms = float(t[0]) / args.steps
         print(json.dumps({
@@ -485,10 +500,12 @@ def run_batch(args, rank, world):
             "dtype": "f32", "data": "reference asset %s, scene fixture built by the reference front end" % asset,
             "config": {"workload": "%d x %s@%dx%d" % (args.frames, asset, size, size),
                        "sharding": "contiguous share of the batch per rank, no collective",
+                       "contexts_per_gpu": n_ctx,
                        "l2": "working set of one frame < L2 (frames are back to back, as in a batch)",
                        "segments_per_s": args.frames * n_segments(scene) / (ms / 1e3)},
             "gpu_launches": int(gstats["kernel_launches"]) * args.steps * len(mine), "clocks": clocks}))
-    r.close()
+    for r in rs:
+        r.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -505,6 +522,7 @@ def main():
     ap.add_argument("--size", type=int, default=8192, help="--workload synthetic: canvas size")
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="--workload synthetic: strip assembly")
     ap.add_argument("--frames", type=int, default=0, help="batch mode: render this many independent frames per step")
+    ap.add_argument("--contexts", type=int, default=16, help="batch mode: renderer contexts (streams) per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -514,7 +514,10 @@ cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
     // many segments -> large chunks (fewer block-wide barriers per segment).
     const uint32_t ctas = (uint32_t)sm_count() * 2u;
     uint32_t chunk = (b.segment_count / (ctas * 4u) + 31u) & ~31u;
-    chunk = chunk < DICE_CHUNK ? DICE_CHUNK : (chunk > DICE_THREADS ? DICE_THREADS : chunk);
+#ifndef DICE_MAX_CHUNK
+#define DICE_MAX_CHUNK DICE_THREADS
+#endif
+    chunk = chunk < DICE_CHUNK ? DICE_CHUNK : (chunk > DICE_MAX_CHUNK ? DICE_MAX_CHUNK : chunk);
     const uint32_t n_chunks = (b.segment_count + chunk - 1) / chunk;
     const uint32_t grid = min(n_chunks, ctas);
     return launch_pdl(k_dice, grid, DICE_THREADS, sizeof(DiceShared), s, b, chunk);
