@@ -58,6 +58,14 @@ def canonical_digest(ref):
     return scenes.digest(*parts)
 
 
+def geometry_digest(ref):
+    """The same without the z-buffers (the GPU-driven path keeps z in dense-tile terms: parity.py maps tiles, not z)."""
+    parts = [ref["group_hashes"]]
+    for b in ref["batches"]:
+        parts += [b["tiles"], b["fills"], b["clips"]]
+    return scenes.digest(*parts)
+
+
 def main():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
     digests = {}
@@ -68,7 +76,8 @@ def main():
         ref = scenes.canonical_from_reference(s.build_d3d9())
         if lut is None:
             lut = s.area_lut()
-        digests[name] = {"canonical_sha256": canonical_digest(ref), "counts": s.counts(),
+        digests[name] = {"canonical_sha256": canonical_digest(ref), "geometry_sha256": geometry_digest(ref),
+                         "counts": s.counts(),
                          "fills": int(sum(len(b["fills"]) for b in ref["batches"])),
                          "tiles": int(sum(len(b["tiles"]) for b in ref["batches"])),
                          "alpha_tiles": int(len(ref["group_hashes"]))}

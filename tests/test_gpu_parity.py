@@ -208,3 +208,85 @@ def test_empty_and_degenerate_scenes(renderer):
     renderer.set_scene(empty)
     st = renderer.draw(clear=True)
     assert st["fills"] == 0 and renderer.pixels().max() == 0
+
+
+def test_tiger_4096_geometry_digest(renderer):
+    """BASELINE.json configs[2] at full size: fills / tiles / backdrops of tiger.svg @ 4096 x 4096 hash to the digest of
+    the REFERENCE's own output (tests/golden/digests.json, written by make_golden.py from SceneBuilderD3D9::build)."""
+    import json
+    import os
+
+    with open(os.path.join(scenes.GOLDEN, "digests.json")) as fp:
+        want = json.load(fp)["tiger_4096"]
+    scene, _ = scenes.load_scene(scenes.golden_path("tiger_4096_scene"))
+    renderer.set_scene(scene)
+    st = renderer.draw(clear=True)
+    mine = parity.canonical_scene(scene, cuda_taps(renderer, scene))
+    parts = [mine["group_hashes"]]
+    for b in mine["batches"]:
+        parts += [b["tiles"], b["fills"], b["clips"]]
+    assert scenes.digest(*parts) == want["geometry_sha256"]
+    assert st["fills"] == want["fills"] and len(mine["group_hashes"]) == want["alpha_tiles"]
+
+
+def stacked_scene(n_layers, size=96):
+    """n_layers translucent rectangles (a few even-odd, a few with a hole) over the same tiles: lists far deeper than the
+    tile kernel's shared-memory staging (256 entries per 16 tiles), nothing for the z-buffer to cull."""
+    rng = np.random.RandomState(7)
+    paths = []
+    for i in range(n_layers):
+        x0, y0 = rng.uniform(2, 30, 2)
+        x1, y1 = rng.uniform(50, size - 2, 2)
+        pts = np.array([[x0, y0], [x1, y0 + rng.uniform(-1, 1)], [x1, y1], [x0 + rng.uniform(-1, 1), y1]], "<f4")
+        contours = [(pts, np.zeros(4, "u1"))]
+        if i % 7 == 3:  # a hole (opposite winding) inside
+            hole = np.array([[36, 36], [36, 44], [44, 44], [44, 36]], "<f4")
+            contours.append((hole, np.zeros(4, "u1")))
+        paths.append({"contours": contours, "paint": i % 5, "fill_rule": 1 if i % 11 == 5 else 0, "opaque": False})
+    colors = np.array([[255, 40, 40, 9], [40, 255, 40, 14], [40, 40, 255, 5], [250, 250, 30, 11], [20, 20, 20, 7]], "u1")
+    return scenes.build_scene_from_outlines(size, size, paths, colors)
+
+
+@pytest.mark.parametrize("n_layers", [40, 300, 700])
+def test_deep_lists_match_oracle(renderer, area_lut, n_layers):
+    """Framebuffer tiles with 40 / 300 / 700 surviving layers: lists in one staging round, in several rounds, and a
+    single tile whose list exceeds the staging (walked by selection from global memory)."""
+    compare_with_oracle(renderer, area_lut, stacked_scene(n_layers), "%d stacked layers" % n_layers)
+
+
+def test_clear_colour_and_load_action(renderer, area_lut):
+    """LOAD_ACTION_CLEAR with a non-zero clear colour, then the same batch again with LOAD_ACTION_LOAD over the result
+    (tile.comp:743-749): empty tiles keep the destination, the others blend over it."""
+    import pforacle
+
+    scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    cc = (0.25, 0.5, 0.75, 1.0)
+    renderer.set_scene(scene)
+    renderer.draw(clear=True, clear_color=cc)
+    first = renderer.pixels()
+    fr = pforacle.Frame(scene, area_lut)
+    want = fr.render(clear=True, clear_color=cc)
+    assert np.abs(first.astype(int) - want.astype(int)).max() <= PIXEL_TOL
+    assert tuple(first[0, 0]) == (64, 128, 191, 255)
+    # second pass without clearing: the oracle draws over its own first result as well
+    renderer.draw(clear=False)
+    second = renderer.pixels()
+    want2 = fr.render(clear=False)
+    # the destination is re-read as RGBA8: one more quantisation step on both sides
+    assert np.abs(second.astype(int) - want2.astype(int)).max() <= PIXEL_TOL + 1
+    assert tuple(second[0, 0]) == (64, 128, 191, 255)
+    fr.close()
+
+
+def test_strips_of_the_full_size_canvas_are_bit_identical(renderer):
+    """Size-independent property at a BASELINE size: a horizontal strip of the synthetic canvas rendered
+    with the framebuffer-origin mechanism equals the same rows of the full frame, byte for byte."""
+    full_scene = scenes.synthetic_scene(20000, 4096)
+    renderer.set_scene(full_scene)
+    renderer.draw(clear=True)
+    full = renderer.pixels()
+    for y0, y1 in ((0, 1024), (1536, 2560), (3072, 4096)):
+        strip_scene = scenes.synthetic_scene(20000, 4096, strip=(y0, y1))
+        renderer.set_scene(strip_scene)
+        renderer.draw(clear=True)
+        assert np.array_equal(renderer.pixels(), full[y0:y1]), "strip %d..%d differs" % (y0, y1)
