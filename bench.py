@@ -172,6 +172,19 @@ def run_reference(args, rank):
 
 # ---------------------------------------------------------------------------------------------- our arm
 
+def measured_traffic(kernel, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch from the committed ncu --set full capture (tiger 4096
+    only: that is the workload the capture was taken on), or None."""
+    if workload != "tiger4096":
+        return None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as fp:
+            t = json.load(fp)[kernel]
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def algorithmic_bytes(r, scene):
     """B_fill and B_tile from the frame's own unit counts (read through the parity taps)."""
     F = A = Ac = L = La = 0
@@ -308,7 +321,8 @@ def run_ours(args, rank, world):
                    "units": {k: gstats[k] for k in ("segments", "lines", "fills", "alpha_tiles", "dense_tiles",
                                                     "listed_tiles", "fb_tiles")}},
         "roofline": {"bound": "hbm", "kernel": "k_composite (tile)", "achieved": achieved, "peak": peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": measured_traffic("k_composite", args.workload),
                      "algorithmic_bytes": bytes_["B_tile"], "kernel_ms": comp_ms,
                      "fill": {"achieved": fill_gbs, "frac": fill_gbs / peak, "algorithmic_bytes": bytes_["B_fill"],
                               "kernel_ms": stage_ms["fill"]},
