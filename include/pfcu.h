@@ -156,9 +156,12 @@ int pfcu_end_frame(pfcu_ctx *ctx, pfcu_frame_stats *stats);
 
 /* ---- options */
 enum {
-    /* No tunable is defined in this ABI version (a fused fill+tile kernel existed in early builds and lost to the
-     * split pair on every workload); the entry point stays so that options can be added without an ABI bump. */
-    PFCU_OPT_RESERVED = 0
+    /* 1 (default): when two consecutive frames enqueue identical work (same batches, counts, buffers, paints, target),
+     * the frame is captured as a CUDA graph and every following identical frame is ONE graph launch issued by
+     * pfcu_end_frame (pfcu_prepare_batch / pfcu_draw_batch then only record). The reference has the matching notion in
+     * its scene epochs (core/scene.h:32-49). A frame that differs is enqueued kernel by kernel and the graph dropped.
+     * 0: always enqueue kernel by kernel. */
+    PFCU_OPT_RETAIN_FRAME_GRAPH = 0
 };
 int pfcu_set_option(pfcu_ctx *ctx, int option, int value);
 

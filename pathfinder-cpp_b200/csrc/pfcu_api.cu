@@ -169,6 +169,17 @@ struct pfcu_ctx {
     std::vector<int> prof_stage;  // stage of the kernel that ends at event i + 1 (-1: frame start marker)
     size_t prof_used = 0;
     float stage_ms[PFCU_NUM_STAGES] = {};
+    // Retained frame graph: when two consecutive frames enqueue byte-identical work (same kernels, same parameter
+    // blocks, same copies -- the signature below), the frame is captured once and later identical frames are ONE graph
+    // launch at pfcu_end_frame instead of a dozen kernel launches and as many event operations. While a retained graph
+    // exists, pfcu_prepare_batch / pfcu_draw_batch only record; a frame that turns out different is enqueued the
+    // ordinary way at pfcu_end_frame and the graph is dropped.
+    bool auto_graph = true;
+    uint64_t frame_sig = 0, prev_sig = 0, retained_sig = 0;
+    cudaGraph_t retained_graph = nullptr;
+    cudaGraphExec_t retained_exec = nullptr;
+    uint32_t retained_launches = 0;
+    bool dry = false;  // this frame is only being recorded (a retained graph may serve it)
     // whole-frame CUDA graph (pfcu_graph_capture)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
@@ -248,7 +259,22 @@ int join_aux(pfcu_ctx *c) {
         if (_r) return _r;               \
     } while (0)
 
-// (Re)build the device view of a slot and enqueue prepare_tiles for it.
+void sig_mix(pfcu_ctx *c, const void *data, size_t n) {  // FNV-1a
+    const unsigned char *p = static_cast<const unsigned char *>(data);
+    uint64_t h = c->frame_sig ? c->frame_sig : 1469598103934665603ull;
+    for (size_t i = 0; i < n; i++) h = (h ^ p[i]) * 1099511628211ull;
+    c->frame_sig = h;
+}
+
+void drop_retained(pfcu_ctx *c) {
+    if (c->retained_exec) cudaGraphExecDestroy(c->retained_exec);
+    if (c->retained_graph) cudaGraphDestroy(c->retained_graph);
+    c->retained_exec = nullptr;
+    c->retained_graph = nullptr;
+    c->retained_sig = 0;
+}
+
+// (Re)build the device view of a slot and enqueue prepare_tiles for it (c->dry: build + sign only).
 int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     BatchSlot &s = c->slots[slot_index];
     const pfcu_batch_desc &d = s.desc;
@@ -272,10 +298,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     CUDA_TRY(s.alpha_tiles.ensure(D * sizeof(AlphaTile)));
     CUDA_TRY(s.scan_desc0.ensure((D / 2048 + 2) * 8));
     CUDA_TRY(s.scan_desc1.ensure((T / 2048 + 2) * 8));
-    if (s.meta_bytes && upload_meta)
-        CUDA_TRY(cudaMemcpyAsync(s.dev_meta.p, s.host_meta.p, s.meta_bytes, cudaMemcpyHostToDevice, c->stream));
-
-    BatchView v{};
+    BatchView v;
+    memset(&v, 0, sizeof(v));  // (padding included: the view is part of the frame signature)
     const char *m = s.dev_meta.as<char>();
     v.backdrops = reinterpret_cast<const pfcu_backdrop_info *>(m + s.off_backdrops);
     v.meta = reinterpret_cast<const pfcu_propagate_metadata *>(m + s.off_meta);
@@ -337,12 +361,24 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     s.view = v;
     s.prepared = true;
 
-    PaintView pv{};
+    PaintView pv;
+    memset(&pv, 0, sizeof(pv));
     pv.area_lut = c->lut.as<uint8_t>();
     pv.lut_w = c->lut_w;
     pv.lut_h = c->lut_h;
     pv.lut_tex = c->lut_tex;
     pv.lut_band = c->lut_band;
+    {
+        const void *host = s.host_meta.p;
+        const size_t bytes = s.meta_bytes;
+        sig_mix(c, &v, sizeof(v));
+        sig_mix(c, &pv, sizeof(pv));
+        sig_mix(c, &host, sizeof(host));
+        sig_mix(c, &bytes, sizeof(bytes));
+    }
+    if (c->dry) return PFCU_OK;
+    if (s.meta_bytes && upload_meta)
+        CUDA_TRY(cudaMemcpyAsync(s.dev_meta.p, s.host_meta.p, s.meta_bytes, cudaMemcpyHostToDevice, c->stream));
 
     {
         int r = prof_mark(c, -1);
@@ -414,7 +450,8 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
         t.height = pg.h;
         clear = 1;  // d3d11/renderer.cpp:382-386
     }
-    PaintView pv{};
+    PaintView pv;
+    memset(&pv, 0, sizeof(pv));
     pv.paints = c->paints.as<Paint>();
     pv.n_paints = c->n_paints;
     pv.all_solid = c->all_solid;
@@ -438,6 +475,19 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
     s.view.masks = c->masks.as<uint8_t>();
     s.view.mask_capacity = c->mask_cap;
     {
+        const int origin = cmd.target_page < 0;
+        sig_mix(c, &s.view, sizeof(s.view));
+        sig_mix(c, &pv, sizeof(pv));
+        sig_mix(c, &t.pixels, sizeof(t.pixels));
+        sig_mix(c, &t.pitch, sizeof(t.pitch));
+        sig_mix(c, &t.width, sizeof(t.width));
+        sig_mix(c, &t.height, sizeof(t.height));
+        sig_mix(c, &clear, sizeof(clear));
+        sig_mix(c, cmd.clear_color, sizeof(cmd.clear_color));
+        sig_mix(c, &origin, sizeof(origin));
+    }
+    if (c->dry) return PFCU_OK;
+    {
         int r = prof_mark(c, -1);
         if (r) return r;
     }
@@ -449,6 +499,42 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
     LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, cmd.target_page < 0, c->stream));
     c->launches += 1;
     c->in_flight = true;
+    return PFCU_OK;
+}
+
+// Replays the recorded frame under stream capture. All buffers are already sized by the frame that was just completed,
+// so the replay performs no allocation. upload_meta: the graph also copies every batch's metadata from its pinned
+// staging buffer (the retained graph, which serves whole frames); otherwise the metadata is taken as resident.
+int capture_frame(pfcu_ctx *c, bool upload_meta, cudaGraph_t *graph, cudaGraphExec_t *exec, uint32_t *launches) {
+    for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
+    const uint32_t launches_before = c->launches;
+    const bool was_dry = c->dry;
+    c->dry = false;
+    c->capturing = true;
+    c->sync_used = 0;
+    c->aux_pending = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) {
+        c->capturing = false;
+        c->dry = was_dry;
+        return fail(PFCU_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
+    }
+    int rc = PFCU_OK;
+    if (cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream) != cudaSuccess) rc = PFCU_ERR_CUDA;
+    for (const Cmd &cmd : c->cmds) {
+        if (rc) break;
+        rc = cmd.kind == CMD_PREPARE ? enqueue_prepare(c, cmd.slot, upload_meta) : enqueue_draw(c, cmd);
+    }
+    if (!rc) rc = join_aux(c);
+    e = cudaStreamEndCapture(c->stream, graph);
+    c->capturing = false;
+    c->dry = was_dry;
+    c->in_flight = false;
+    *launches = c->launches - launches_before;
+    c->launches = launches_before;
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(PFCU_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    CUDA_TRY(cudaGraphInstantiate(exec, *graph, 0));
     return PFCU_OK;
 }
 
@@ -519,6 +605,7 @@ void pfcu_destroy(pfcu_ctx *c) {
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_begin);
     cudaEventDestroy(c->ev_end);
+    drop_retained(c);
     for (cudaEvent_t e : c->sync_events) cudaEventDestroy(e);
     cudaStreamDestroy(c->aux_stream);
     cudaStreamDestroy(c->own_stream);
@@ -743,6 +830,8 @@ int pfcu_begin_frame(pfcu_ctx *c) {
     c->prof_used = 0;
     c->sync_used = 0;
     c->aux_pending = nullptr;
+    c->frame_sig = 0;
+    c->dry = c->auto_graph && !c->profiling && c->retained_exec != nullptr;
     return PFCU_OK;
 }
 
@@ -757,15 +846,15 @@ int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
     CUDA_TRY(cudaSetDevice(c->device));
     const int slot_index = c->slots_used;
     BatchSlot &s = c->slots[slot_index];
-    if (!c->event_begin_recorded) {
+    if (!c->mask_cap) {
+        c->mask_cap = 16384;
+        CUDA_TRY(c->masks.ensure((size_t)c->mask_cap * 256));
+    }
+    if (!c->event_begin_recorded && !c->dry) {
         CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
         c->event_begin_recorded = true;
         // first batch of the frame: reset the frame-global alpha tile counter
         CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
-        if (!c->mask_cap) {
-            c->mask_cap = 16384;
-            CUDA_TRY(c->masks.ensure((size_t)c->mask_cap * 256));
-        }
     }
     s.desc = *d;
     // pack the metadata vectors into pinned memory (stable for the async copy and for replay)
@@ -824,20 +913,45 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
     CUDA_TRY(cudaSetDevice(c->device));
     BatchCounters *hc = static_cast<BatchCounters *>(c->host_counters.p);
     const size_t cbytes = sizeof(BatchCounters) * (MAX_SLOTS + 1);
+    const uint64_t sig = c->frame_sig;
+    bool served_by_graph = false;
+    if (c->dry) {  // nothing has been enqueued yet: the retained graph serves the frame if it is the same frame
+        c->dry = false;
+        if (!c->cmds.empty()) {
+            CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
+            c->event_begin_recorded = true;
+            if (c->retained_exec && sig == c->retained_sig) {
+                CUDA_TRY(cudaGraphLaunch(c->retained_exec, c->stream));
+                c->launches = c->retained_launches;
+                c->in_flight = true;
+                served_by_graph = true;
+            } else {
+                drop_retained(c);
+                CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
+                for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
+                for (const Cmd &cmd : c->cmds) {
+                    const int r = cmd.kind == CMD_PREPARE ? enqueue_prepare(c, cmd.slot) : enqueue_draw(c, cmd);
+                    if (r) {
+                        c->frame_open = false;
+                        return r;
+                    }
+                }
+            }
+        }
+    }
+    int attempts_used = 0;
     for (int attempt = 0;; attempt++) {
+        attempts_used = attempt;
         {
             int r = join_aux(c);  // batches that were prepared but not drawn (clip batches)
             if (r) return r;
         }
         if (c->event_begin_recorded) CUDA_TRY(cudaEventRecord(c->ev_end, c->stream));
         // the one read-back of the frame: counters of every batch + the frame alpha counter
-        const size_t used = sizeof(BatchCounters) * (size_t)std::max(c->slots_used, 1);
-        CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, used, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(hc + MAX_SLOTS, frame_alpha_counter(c), sizeof(BatchCounters), cudaMemcpyDeviceToHost,
-                                 c->stream));
+        // (one copy of the whole 16 KB block -- batch counters + frame alpha counter -- is cheaper than two small ones)
+        CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, cbytes, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->in_flight = false;
-        (void)cbytes;
         uint32_t overflow = 0, dda_anomaly = 0;
         const uint32_t frame_alpha = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
         for (int i = 0; i < c->slots_used; i++) {
@@ -863,6 +977,7 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
             return fail(PFCU_ERR_OVERFLOW, "ran out of space after %d attempts (flags 0x%x)", attempt + 1, overflow);
         }
         // grow and replay the recorded frame
+        drop_retained(c);  // (its parameter blocks point into the buffers that are about to move)
         c->retries++;
         c->prof_used = 0;
         c->sync_used = 0;
@@ -877,6 +992,14 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
             }
         }
     }
+    // Retain the frame: the second of two identical frames is captured, identical frames after it are one graph launch.
+    if (c->auto_graph && !c->profiling && !served_by_graph && !c->retained_exec && attempts_used == 0 && sig &&
+        sig == c->prev_sig && !c->cmds.empty()) {
+        const int r = capture_frame(c, true, &c->retained_graph, &c->retained_exec, &c->retained_launches);
+        if (r == PFCU_OK) c->retained_sig = sig;
+        else drop_retained(c);
+    }
+    c->prev_sig = sig;
     pfcu_frame_stats st{};
     st.batches = (uint32_t)c->slots_used;
     for (int i = 0; i < c->slots_used; i++) {
@@ -914,8 +1037,9 @@ int pfcu_set_option(pfcu_ctx *c, int option, int value) {
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     if (c->frame_open) return fail(PFCU_ERR_STATE, "options cannot change inside a frame");
     switch (option) {
-        case PFCU_OPT_RESERVED:
-            (void)value;
+        case PFCU_OPT_RETAIN_FRAME_GRAPH:
+            c->auto_graph = value != 0;
+            if (!c->auto_graph) drop_retained(c);
             return PFCU_OK;
         default:
             return fail(PFCU_ERR_INVALID, "unknown option %d", option);
@@ -947,34 +1071,8 @@ int pfcu_graph_capture(pfcu_ctx *c) {
     if (c->graph) cudaGraphDestroy(c->graph);
     c->graph_exec = nullptr;
     c->graph = nullptr;
-    // All buffers are already sized by the frame that was just completed, so replaying the command list performs
-    // no allocation; the batch metadata is resident, so no host memory is touched by the graph.
-    for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
-    const uint32_t launches_before = c->launches;
-    c->capturing = true;
-    c->sync_used = 0;
-    c->aux_pending = nullptr;
-    cudaError_t e = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) {
-        c->capturing = false;
-        return fail(PFCU_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
-    }
-    int rc = PFCU_OK;
-    if (cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream) != cudaSuccess) rc = PFCU_ERR_CUDA;
-    for (const Cmd &cmd : c->cmds) {
-        if (rc) break;
-        rc = cmd.kind == CMD_PREPARE ? enqueue_prepare(c, cmd.slot, false) : enqueue_draw(c, cmd);
-    }
-    if (!rc) rc = join_aux(c);
-    e = cudaStreamEndCapture(c->stream, &c->graph);
-    c->capturing = false;
-    c->in_flight = false;
-    c->graph_launches_per_frame = c->launches - launches_before;
-    c->launches = launches_before;
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(PFCU_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
-    CUDA_TRY(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
-    return PFCU_OK;
+    // (the batch metadata is resident, so no host memory is touched by this graph)
+    return capture_frame(c, false, &c->graph, &c->graph_exec, &c->graph_launches_per_frame);
 }
 
 int pfcu_graph_launch(pfcu_ctx *c) {

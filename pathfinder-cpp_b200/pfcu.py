@@ -220,6 +220,10 @@ class Renderer:
         return st.as_dict()
 
     # -- options / measurement
+    def set_retain_frame_graph(self, enabled):
+        """PFCU_OPT_RETAIN_FRAME_GRAPH (default on): identical consecutive frames become one graph launch."""
+        _check(self.L.pfcu_set_option(self.h, 0, int(bool(enabled))))
+
     def set_profiling(self, enabled):
         _check(self.L.pfcu_set_profiling(self.h, int(bool(enabled))))
 

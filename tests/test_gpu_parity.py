@@ -290,3 +290,38 @@ def test_strips_of_the_full_size_canvas_are_bit_identical(renderer):
         renderer.set_scene(strip_scene)
         renderer.draw(clear=True)
         assert np.array_equal(renderer.pixels(), full[y0:y1]), "strip %d..%d differs" % (y0, y1)
+
+
+def test_retained_frame_graph_serves_identical_frames_only(renderer, area_lut):
+    """PFCU_OPT_RETAIN_FRAME_GRAPH: the third identical frame onwards is one graph launch issued by pfcu_end_frame. It
+    must render the same bytes as the kernel-by-kernel path, pick up re-uploaded inputs, and step aside (and come back)
+    when the frame changes."""
+    tiger, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    clip, _ = scenes.load_scene(scenes.golden_path("demo_clip_512"))
+    renderer.set_retain_frame_graph(False)
+    renderer.set_scene(tiger)
+    renderer.draw(clear=True)
+    want_tiger = renderer.pixels()
+    renderer.set_scene(clip)
+    renderer.draw(clear=True)
+    want_clip = renderer.pixels()
+    renderer.set_retain_frame_graph(True)
+    try:
+        renderer.set_scene(tiger)
+        for i in range(5):  # frames 0, 1 enqueue kernels (1 also captures), 2.. are graph launches
+            st = renderer.draw(clear=True, upload=(i == 3))
+            assert st["retries"] == 0 and st["fills"] == 27200
+            assert np.array_equal(renderer.pixels(), want_tiger), "frame %d" % i
+        bid = int(tiger["draw_batches"][0]["info"][0])
+        assert len(renderer.fills(bid)) == 27200  # the taps see the graph-launched frame's buffers
+        renderer.set_scene(clip)  # a different frame: the retained graph must not be used
+        for i in range(4):
+            renderer.draw(clear=True)
+            assert np.array_equal(renderer.pixels(), want_clip), "clip frame %d" % i
+        renderer.set_scene(tiger)
+        renderer.draw(clear=True, clear_color=(0.0, 0.0, 0.0, 1.0))  # same batches, other clear colour: other frame
+        assert renderer.pixels()[0, 0, 3] == 255
+        renderer.draw(clear=True)
+        assert np.array_equal(renderer.pixels(), want_tiger)
+    finally:
+        renderer.set_retain_frame_graph(True)
