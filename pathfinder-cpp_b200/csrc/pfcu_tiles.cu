@@ -241,116 +241,168 @@ cudaError_t launch_fill_scatter(const BatchView &b, cudaStream_t s) {
 
 // ------------------------------------------------------------------------------------------------ propagate
 
-// One warp per tile column; lanes are 32 consecutive rows (propagate.comp:95-216, tiler.cpp:369-439). No atomic
-// returns a value: mask slots come from the scan, list positions are taken later by the list scatter.
-__global__ void __launch_bounds__(128) k_propagate(BatchView b) {
-    pdl_wait();
-    const uint32_t col = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned lane = threadIdx.x & 31;
-    if (col >= b.column_count) return;
-    const uint32_t path = __ldg(&b.backdrops[col].path_index);
-    const int tx = __ldg(&b.backdrops[col].tile_x_offset);
-    const int4 rect = __ldg(reinterpret_cast<const int4 *>(&b.meta[path].tile_rect[0]));
-    const uint32_t tile_offset = __ldg(&b.meta[path].tile_offset);
-    const int w = rect.z - rect.x, h = rect.w - rect.y;
-    if (w <= 0 || h <= 0 || tx >= w) return;
-    const pfcu_tile_path_info info = b.tpi[path];
-    const int gx = tx + rect.x;
-    const uint32_t z_write_path = __ldg(&b.meta[path].z_write);
-    const uint32_t clip_index = __ldg(&b.meta[path].clip_path_index);
-    const bool has_clip = (int32_t)clip_index >= 0;
-    int4 crect = make_int4(0, 0, 0, 0);
-    uint32_t ctile_offset = 0;
-    const bool clip_ok = has_clip && b.clip_meta && clip_index < b.clip_path_count;
-    if (clip_ok) {
-        crect = __ldg(reinterpret_cast<const int4 *>(&b.clip_meta[clip_index].tile_rect[0]));
-        ctile_offset = __ldg(&b.clip_meta[clip_index].tile_offset);
+// What propagate needs to know about a tile column (everything but the running backdrop).
+struct ColumnInfo {
+    uint32_t path, tile_offset, z_write_path, clip_index, ctile_offset;
+    int tx, w, h, gx, rect_y;
+    int4 crect;
+    uint32_t ctrl;  // TilePathInfo::ctrl
+    bool has_clip, clip_ok;
+};
+
+__device__ __forceinline__ bool load_column(const BatchView &b, uint32_t col, ColumnInfo &ci) {
+    ci.path = __ldg(&b.backdrops[col].path_index);
+    ci.tx = __ldg(&b.backdrops[col].tile_x_offset);
+    const int4 rect = __ldg(reinterpret_cast<const int4 *>(&b.meta[ci.path].tile_rect[0]));
+    ci.tile_offset = __ldg(&b.meta[ci.path].tile_offset);
+    ci.w = rect.z - rect.x;
+    ci.h = rect.w - rect.y;
+    ci.gx = ci.tx + rect.x;
+    ci.rect_y = rect.y;
+    if (ci.w <= 0 || ci.h <= 0 || ci.tx >= ci.w) return false;
+    ci.ctrl = b.tpi[ci.path].ctrl;
+    ci.z_write_path = __ldg(&b.meta[ci.path].z_write);
+    ci.clip_index = __ldg(&b.meta[ci.path].clip_path_index);
+    ci.has_clip = (int32_t)ci.clip_index >= 0;
+    ci.crect = make_int4(0, 0, 0, 0);
+    ci.ctile_offset = 0;
+    ci.clip_ok = ci.has_clip && b.clip_meta && ci.clip_index < b.clip_path_count;
+    if (ci.clip_ok) {
+        ci.crect = __ldg(reinterpret_cast<const int4 *>(&b.clip_meta[ci.clip_index].tile_rect[0]));
+        ci.ctile_offset = __ldg(&b.clip_meta[ci.clip_index].tile_offset);
     }
-    const bool even_odd = (info.ctrl & 0x2) != 0;
-    const uint32_t first_alpha = b.counters->first_alpha;
-    int carry = b.col_backdrop[col];
+    return true;
+}
 
-    for (int ty0 = 0; ty0 < h; ty0 += 32) {
-        const int ty = ty0 + (int)lane;
-        const bool valid = ty < h;
-        const uint32_t ti = tile_offset + (uint32_t)tx + (uint32_t)w * (uint32_t)(valid ? ty : 0);
-        const uint32_t word = valid ? b.tile_word[ti] : 0u;
-        const int delta = (int)(int8_t)(word >> 24);
-        // exclusive prefix of the deltas down the column (tiler.cpp:394,437)
-        int incl = delta;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (unsigned)d) incl += t;
-        }
-        const int cur = carry + incl - delta;
-        carry += __shfl_sync(0xffffffffu, incl, 31);
-        if (!valid) continue;
-
-        const uint32_t fill_count = word & 0x00ffffffu;
-        const bool have_mask = fill_count != 0;
-        int backdrop = (int)(int8_t)cur;  // int8_t(backdrops[column]), tiler.cpp:394
-        int backdrop9 = backdrop;
-        bool need_new = have_mask;
-        int alpha = -1, clip_alpha = -1;
-        const int gy = ty + rect.y;
-        if (has_clip) {
-            const bool inside = clip_ok && gx >= crect.x && gx < crect.z && gy >= crect.y && gy < crect.w;
-            if (inside) {
-                const uint4 ct = *reinterpret_cast<const uint4 *>(
-                    &b.clip_tile_state[ctile_offset + (uint32_t)(gx - crect.x) +
-                                       (uint32_t)(crect.z - crect.x) * (uint32_t)(gy - crect.y)]);
-                if ((int)ct.x >= 0) {
-                    if (have_mask) {  // tiler.cpp:403-414 / propagate.comp:144-147
-                        clip_alpha = (int)ct.x;
-                        backdrop9 = 0;
-                    } else if (backdrop != 0) {  // tiler.cpp:415-420 / propagate.comp:149-154
-                        alpha = (int)ct.x;
-                        need_new = false;
-                        backdrop9 = (int)(int8_t)((ct.y >> 16) & 0xffu);
-                    } else {
-                        need_new = false;
-                    }
-                } else if ((int8_t)(ct.y & 0xffu) == 0) {  // blank clip tile: tiler.cpp:421-425
-                    backdrop = 0;
+// One tile of a column (propagate.comp:118-213, tiler.cpp:391-437): `cur` is the column's backdrop BEFORE this tile's
+// delta. No atomic returns a value: mask slots come from the scan, list positions are taken later by the list scatter.
+__device__ __forceinline__ void resolve_tile(const BatchView &b, const ColumnInfo &ci, uint32_t first_alpha, int ty, int cur,
+                                             uint32_t word) {
+    const uint32_t ti = ci.tile_offset + (uint32_t)ci.tx + (uint32_t)ci.w * (uint32_t)ty;
+    const int delta = (int)(int8_t)(word >> 24);
+    const bool even_odd = (ci.ctrl & 0x2) != 0;
+    const uint32_t fill_count = word & 0x00ffffffu;
+    const bool have_mask = fill_count != 0;
+    int backdrop = (int)(int8_t)cur;  // int8_t(backdrops[column]), tiler.cpp:394
+    int backdrop9 = backdrop;
+    bool need_new = have_mask;
+    int alpha = -1, clip_alpha = -1;
+    const int gx = ci.gx, gy = ty + ci.rect_y;
+    if (ci.has_clip) {
+        const int4 crect = ci.crect;
+        const bool inside = ci.clip_ok && gx >= crect.x && gx < crect.z && gy >= crect.y && gy < crect.w;
+        if (inside) {
+            const uint4 ct = *reinterpret_cast<const uint4 *>(
+                &b.clip_tile_state[ci.ctile_offset + (uint32_t)(gx - crect.x) +
+                                   (uint32_t)(crect.z - crect.x) * (uint32_t)(gy - crect.y)]);
+            if ((int)ct.x >= 0) {
+                if (have_mask) {  // tiler.cpp:403-414 / propagate.comp:144-147
+                    clip_alpha = (int)ct.x;
                     backdrop9 = 0;
+                } else if (backdrop != 0) {  // tiler.cpp:415-420 / propagate.comp:149-154
+                    alpha = (int)ct.x;
+                    need_new = false;
+                    backdrop9 = (int)(int8_t)((ct.y >> 16) & 0xffu);
+                } else {
                     need_new = false;
                 }
-            } else {  // outside the clip rect: tiler.cpp:426-430
+            } else if ((int8_t)(ct.y & 0xffu) == 0) {  // blank clip tile: tiler.cpp:421-425
                 backdrop = 0;
                 backdrop9 = 0;
                 need_new = false;
             }
+        } else {  // outside the clip rect: tiler.cpp:426-430
+            backdrop = 0;
+            backdrop9 = 0;
+            need_new = false;
         }
-        // alpha tile allocation (propagate.comp:178-183): the slot was fixed by the scan over tiles with fills
-        if (have_mask) {
-            const uint32_t local = b.alpha_rank[ti];
-            const uint32_t id = first_alpha + local;
-            if (id < b.mask_capacity && local < b.alpha_capacity) {
-                // a tile whose fills the clip made invisible keeps its slot but is marked so that fill skips it.
-                // Record: tile | winding << 31, clip mask slot, first fill, backdrop | fill count << 8
-                *reinterpret_cast<uint4 *>(&b.alpha_tiles[local]) =
-                    make_uint4((need_new ? ti : 0x7fffffffu) | ((info.ctrl & 0x1) ? 0x80000000u : 0u), (uint32_t)clip_alpha,
-                               b.fill_begin[ti], ((uint32_t)backdrop & 0xffu) | (fill_count << 8));
-                if (need_new) alpha = (int)id;
-            } else {
-                need_new = false;  // the scan flagged OVF_ALPHA: the frame is replayed with more slots
+    }
+    // alpha tile allocation (propagate.comp:178-183): the slot was fixed by the scan over tiles with fills
+    if (have_mask) {
+        const uint32_t local = b.alpha_rank[ti];
+        const uint32_t id = first_alpha + local;
+        if (id < b.mask_capacity && local < b.alpha_capacity) {
+            // a tile whose fills the clip made invisible keeps its slot but is marked so that fill skips it.
+            // Record: tile | winding << 31, clip mask slot, first fill, backdrop | fill count << 8
+            *reinterpret_cast<uint4 *>(&b.alpha_tiles[local]) =
+                make_uint4((need_new ? ti : 0x7fffffffu) | ((ci.ctrl & 0x1) ? 0x80000000u : 0u), (uint32_t)clip_alpha,
+                           b.fill_begin[ti], ((uint32_t)backdrop & 0xffu) | (fill_count << 8));
+            if (need_new) alpha = (int)id;
+        } else {
+            need_new = false;  // the scan flagged OVF_ALPHA: the frame is replayed with more slots
+        }
+    }
+    const int fx = gx - b.fb_tx0, fy = gy - b.fb_ty0;  // framebuffer tile
+    const bool in_fb = fx >= 0 && fx < b.fb_tw && fy >= 0 && fy < b.fb_th;
+    const uint32_t map = in_fb ? (uint32_t)fy * (uint32_t)b.fb_tw + (uint32_t)fx : 0u;
+    const bool listed = (backdrop != 0 || alpha >= 0) && in_fb;
+    const uint32_t packed = ((uint32_t)backdrop & 0xffu) | (((uint32_t)delta & 0xffu) << 8) |
+                            (((uint32_t)backdrop9 & 0xffu) << 16) | (listed ? 1u << 24 : 0u) |
+                            (need_new ? 1u << 25 : 0u) | ((ci.ctrl & 0x3u) << 26);
+    *reinterpret_cast<uint4 *>(&b.tile_state[ti]) = make_uint4((uint32_t)alpha, packed, ci.path, (uint32_t)clip_alpha);
+    // z-buffer: propagate.comp:190-206 (even-odd tiles with an even backdrop are invisible, not occluders)
+    bool z_write = ci.z_write_path != 0;
+    if (backdrop != 0 && even_odd && (abs(backdrop) & 1) == 0) z_write = false;
+    if (in_fb && z_write && backdrop != 0 && alpha < 0) atomicMax(&b.fb[map].z, (int)ti);
+    // list membership (propagate.comp:209-212): count now, place after the scan (fire-and-forget reduction)
+    if (listed) atomicAdd(&b.fb[map].count, 1u);
+}
+
+#ifndef PROPAGATE_SHORT_N
+#define PROPAGATE_SHORT_N 4
+#endif
+constexpr int PROPAGATE_SHORT = PROPAGATE_SHORT_N;  // columns of up to this many tiles are walked by one thread
+
+// propagate.comp:95-216 (== Tiler::prepare_tiles, tiler.cpp:369-439). One warp per tile column, in groups of 32
+// consecutive columns:
+//   * a TALL column is walked by its own warp: lanes are 32 consecutive rows and the backdrop is a warp-shuffle prefix
+//     sum carried across 32-row chunks (the reference walks up to 256 tiles serially in one thread);
+//   * the SHORT columns of a group (glyph-sized paths: the bulk of a text-density scene) are all walked by the group's
+//     first warp, ONE LANE per column, serially, as the reference does -- neighbouring lanes are neighbouring columns of
+//     the same path, so every row is one coalesced access and no lane idles below a 3-tile column. The other warps of
+//     the group find their column short and leave.
+__global__ void __launch_bounds__(128) k_propagate(BatchView b) {
+    pdl_wait();
+    const uint32_t wcol = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // this warp's column
+    const unsigned lane = threadIdx.x & 31;
+    if (wcol >= b.column_count) return;
+    const uint32_t first_alpha = b.counters->first_alpha;
+    {
+        ColumnInfo cw = {};
+        if (load_column(b, wcol, cw) && cw.h > PROPAGATE_SHORT) {  // (warp-uniform: every lane loaded the same column)
+            int wcarry = b.col_backdrop[wcol];
+            for (int ty0 = 0; ty0 < cw.h; ty0 += 32) {
+                const int ty = ty0 + (int)lane;
+                const bool in = ty < cw.h;
+                const uint32_t word = in ? b.tile_word[cw.tile_offset + (uint32_t)cw.tx + (uint32_t)cw.w * (uint32_t)ty] : 0u;
+                const int delta = (int)(int8_t)(word >> 24);
+                // exclusive prefix of the deltas down the column (tiler.cpp:394,437)
+                int incl = delta;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= (unsigned)d) incl += t;
+                }
+                const int cur = wcarry + incl - delta;
+                wcarry += __shfl_sync(0xffffffffu, incl, 31);
+                if (in) resolve_tile(b, cw, first_alpha, ty, cur, word);
             }
         }
-        const int fx = gx - b.fb_tx0, fy = gy - b.fb_ty0;  // framebuffer tile
-        const bool in_fb = fx >= 0 && fx < b.fb_tw && fy >= 0 && fy < b.fb_th;
-        const uint32_t map = in_fb ? (uint32_t)fy * (uint32_t)b.fb_tw + (uint32_t)fx : 0u;
-        const bool listed = (backdrop != 0 || alpha >= 0) && in_fb;
-        const uint32_t packed = ((uint32_t)backdrop & 0xffu) | (((uint32_t)delta & 0xffu) << 8) |
-                                (((uint32_t)backdrop9 & 0xffu) << 16) | (listed ? 1u << 24 : 0u) |
-                                (need_new ? 1u << 25 : 0u) | (((uint32_t)info.ctrl & 0x3u) << 26);
-        *reinterpret_cast<uint4 *>(&b.tile_state[ti]) = make_uint4((uint32_t)alpha, packed, path, (uint32_t)clip_alpha);
-        // z-buffer: propagate.comp:190-206 (even-odd tiles with an even backdrop are invisible, not occluders)
-        bool z_write = z_write_path != 0;
-        if (backdrop != 0 && even_odd && (abs(backdrop) & 1) == 0) z_write = false;
-        if (in_fb && z_write && backdrop != 0 && alpha < 0) atomicMax(&b.fb[map].z, (int)ti);
-        // list membership (propagate.comp:209-212): count now, place after the scan (fire-and-forget reduction)
-        if (listed) atomicAdd(&b.fb[map].count, 1u);
+    }
+    if (wcol & 31u) return;
+    // the group's short columns, one per lane
+    const uint32_t col = wcol + lane;
+    ColumnInfo ci = {};
+    if (col >= b.column_count || !load_column(b, col, ci) || ci.h > PROPAGATE_SHORT) return;
+    int carry = b.col_backdrop[col];
+    uint32_t words[PROPAGATE_SHORT];  // all loads first: the rows only depend on each other through the running backdrop
+#pragma unroll
+    for (int ty = 0; ty < PROPAGATE_SHORT; ty++)
+        words[ty] = ty < ci.h ? b.tile_word[ci.tile_offset + (uint32_t)ci.tx + (uint32_t)ci.w * (uint32_t)ty] : 0u;
+#pragma unroll
+    for (int ty = 0; ty < PROPAGATE_SHORT; ty++) {
+        if (ty < ci.h) resolve_tile(b, ci, first_alpha, ty, carry, words[ty]);
+        carry += (int)(int8_t)(words[ty] >> 24);
     }
 }
 
