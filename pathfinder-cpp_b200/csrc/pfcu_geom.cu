@@ -139,16 +139,19 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, unsigned lane) {
 
 constexpr int DICE_THREADS = 256;
 constexpr int DICE_CHUNK = 32;    // fewest segments a CTA takes at a time (launch_dice picks 32 .. DICE_THREADS)
-constexpr int DICE_QUEUE = 1024;  // nodes per level held in shared memory; wider levels fall back to a private stack
-constexpr int DICE_OUT = 1024;    // lines collected between flushes
+// Two shared-memory configurations (template parameters Q = nodes per level held in shared memory -- wider levels fall
+// back to a private stack --, O = lines collected between flushes): few segments with deep trees (an SVG at 4096^2)
+// take <1024, 1024>, 98 KB, 2 CTAs per SM; many segments with shallow trees (text density) take <512, 512>, 50 KB,
+// 4 CTAs per SM, so that twice as many chunks overlap their barriers and dependent loads.
 constexpr int DICE_PATHS = 512;   // dice metadata entries staged per chunk (more: the search stays in global memory)
 
-struct DiceShared {
-    float4 qa[2][DICE_QUEUE];    // p0, p1
-    float4 qb[2][DICE_QUEUE];    // p2, p3
-    uint32_t qm[2][DICE_QUEUE];  // path | depth << 24 | cubic << 31
-    float4 out_line[DICE_OUT];
-    uint32_t out_path[DICE_OUT];
+template <int Q, int O>
+struct DiceSharedT {
+    float4 qa[2][Q];    // p0, p1
+    float4 qb[2][Q];    // p2, p3
+    uint32_t qm[2][Q];  // path | depth << 24 | cubic << 31
+    float4 out_line[O];
+    uint32_t out_path[O];
     uint32_t q_count[2];
     uint32_t out_count, out_base;
     uint32_t path_lo, path_hi;         // paths that own the chunk's first / last segment
@@ -156,11 +159,12 @@ struct DiceShared {
 };
 
 // One flattened line: view-box clip, then into the CTA's output buffer (or straight to global memory when full).
-__device__ __forceinline__ void dice_emit(const BatchView &b, DiceShared &sh, float2 from, float2 to, uint32_t path) {
+template <int Q, int O>
+__device__ __forceinline__ void dice_emit(const BatchView &b, DiceSharedT<Q, O> &sh, float2 from, float2 to, uint32_t path) {
     float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
     if (!clip_to_view_box(l0, l1, l2, l3, b.view_box[0], b.view_box[2], b.view_box[3])) return;
     const uint32_t at = atomicAdd(&sh.out_count, 1u);
-    if (at < DICE_OUT) {
+    if (at < O) {
         sh.out_line[at] = make_float4(l0, l1, l2, l3);
         sh.out_path[at] = path;
     } else {
@@ -196,7 +200,8 @@ __device__ __forceinline__ bool node_is_flat(const Cubic &c, bool cubic, int dep
 }
 
 // Depth-first walk of one subtree with a private stack: only used when a level does not fit the shared queue.
-__device__ __noinline__ void dice_subtree_serial(const BatchView &b, DiceShared &sh, Cubic cur, bool cubic, int depth,
+template <int Q, int O>
+__device__ __noinline__ void dice_subtree_serial(const BatchView &b, DiceSharedT<Q, O> &sh, Cubic cur, bool cubic, int depth,
                                                  uint32_t path) {
     Cubic stack[MAX_FLATTEN_DEPTH];
     unsigned char stack_depth[MAX_FLATTEN_DEPTH];
@@ -220,10 +225,11 @@ __device__ __noinline__ void dice_subtree_serial(const BatchView &b, DiceShared 
     }
 }
 
-__device__ __forceinline__ void dice_push(const BatchView &b, DiceShared &sh, int buf, const Cubic &c, bool cubic,
+template <int Q, int O>
+__device__ __forceinline__ void dice_push(const BatchView &b, DiceSharedT<Q, O> &sh, int buf, const Cubic &c, bool cubic,
                                           int depth, uint32_t path) {
     const uint32_t at = atomicAdd(&sh.q_count[buf], 1u);
-    if (at < DICE_QUEUE) {
+    if (at < Q) {
         sh.qa[buf][at] = make_float4(c.p0.x, c.p0.y, c.p1.x, c.p1.y);
         sh.qb[buf][at] = make_float4(c.p2.x, c.p2.y, c.p3.x, c.p3.y);
         sh.qm[buf][at] = path | ((uint32_t)depth << 24) | (cubic ? 0x80000000u : 0u);
@@ -234,7 +240,8 @@ __device__ __forceinline__ void dice_push(const BatchView &b, DiceShared &sh, in
 
 // Warp-aggregated versions of dice_emit / dice_push (one shared-memory atomic per warp instead of one per lane: 256
 // lanes bumping the same counter serialise). Must be called by all 32 lanes of a warp.
-__device__ __forceinline__ void dice_emit_warp(const BatchView &b, DiceShared &sh, bool want, float2 from, float2 to,
+template <int Q, int O>
+__device__ __forceinline__ void dice_emit_warp(const BatchView &b, DiceSharedT<Q, O> &sh, bool want, float2 from, float2 to,
                                                uint32_t path, unsigned lane) {
     float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
     const bool em = want && clip_to_view_box(l0, l1, l2, l3, b.view_box[0], b.view_box[2], b.view_box[3]);
@@ -246,7 +253,7 @@ __device__ __forceinline__ void dice_emit_warp(const BatchView &b, DiceShared &s
     base = __shfl_sync(0xffffffffu, base, leader);
     if (!em) return;
     const uint32_t at = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-    if (at < DICE_OUT) {
+    if (at < O) {
         sh.out_line[at] = make_float4(l0, l1, l2, l3);
         sh.out_path[at] = path;
     } else {
@@ -262,7 +269,8 @@ __device__ __forceinline__ void dice_emit_warp(const BatchView &b, DiceShared &s
 }
 
 // Queues `n_nodes` (1 or 2) nodes per wanting lane; nodes that do not fit are flattened on the spot.
-__device__ __forceinline__ void dice_push_warp(const BatchView &b, DiceShared &sh, int buf, bool want, int n_nodes,
+template <int Q, int O>
+__device__ __forceinline__ void dice_push_warp(const BatchView &b, DiceSharedT<Q, O> &sh, int buf, bool want, int n_nodes,
                                                const Cubic &c0, const Cubic &c1, bool cubic, int depth, uint32_t path,
                                                unsigned lane) {
     const unsigned mask = __ballot_sync(0xffffffffu, want);
@@ -276,7 +284,7 @@ __device__ __forceinline__ void dice_push_warp(const BatchView &b, DiceShared &s
     const uint32_t meta = path | ((uint32_t)depth << 24) | (cubic ? 0x80000000u : 0u);
     for (int k = 0; k < n_nodes; k++) {
         const Cubic &c = k ? c1 : c0;
-        if (at + k < DICE_QUEUE) {
+        if (at + k < Q) {
             sh.qa[buf][at + k] = make_float4(c.p0.x, c.p0.y, c.p1.x, c.p1.y);
             sh.qb[buf][at + k] = make_float4(c.p2.x, c.p2.y, c.p3.x, c.p3.y);
             sh.qm[buf][at + k] = meta;
@@ -304,9 +312,10 @@ __device__ __forceinline__ uint32_t warp_find_path(const pfcu_dice_metadata *dic
 }
 
 // Copies the CTA's collected lines to global memory: one atomic per flush.
-__device__ __forceinline__ void dice_flush(const BatchView &b, DiceShared &sh) {
+template <int Q, int O>
+__device__ __forceinline__ void dice_flush(const BatchView &b, DiceSharedT<Q, O> &sh) {
     // (called by all threads, between two __syncthreads() of the caller's making: out_count is stable)
-    const uint32_t n_out = min(sh.out_count, (uint32_t)DICE_OUT);
+    const uint32_t n_out = min(sh.out_count, (uint32_t)O);
     if (threadIdx.x == 0) sh.out_base = n_out ? atomicAdd(&b.counters->n_lines, n_out) : 0u;
     __syncthreads();
     const uint32_t base = sh.out_base;
@@ -360,9 +369,10 @@ __device__ __forceinline__ void dice_flush(const BatchView &b, DiceShared &sh) {
     if (threadIdx.x == 0) sh.out_count = 0;
 }
 
+template <int Q, int O>
 __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chunk_size) {
     extern __shared__ __align__(16) unsigned char dice_smem[];
-    DiceShared &sh = *reinterpret_cast<DiceShared *>(dice_smem);
+    DiceSharedT<Q, O> &sh = *reinterpret_cast<DiceSharedT<Q, O> *>(dice_smem);
     pdl_wait();
     const uint32_t n_chunks = (b.segment_count + chunk_size - 1) / chunk_size;
     if (threadIdx.x == 0) {
@@ -463,9 +473,9 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chu
         // ---- breadth-first over the subdivision trees (tiler.cpp:284-315): one node per thread per level
         int cur = 0;
         while (true) {
-            const uint32_t count = min(sh.q_count[cur], (uint32_t)DICE_QUEUE);
+            const uint32_t count = min(sh.q_count[cur], (uint32_t)Q);
             // a level emits at most one line per node: flush first if they might not fit
-            if (sh.out_count + count > DICE_OUT) {
+            if (sh.out_count + count > O) {
                 __syncthreads();
                 dice_flush(b, sh);
                 __syncthreads();
@@ -502,25 +512,40 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chu
     dice_flush(b, sh);
 }
 
-cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
-    if (!b.segment_count) return cudaSuccess;
-    static bool configured = false;
+#ifndef DICE_WIDE_SEGMENTS
+#define DICE_WIDE_SEGMENTS 65536  // batches with more segments than this take the 4-CTAs-per-SM configuration
+#endif
+#ifndef DICE_WIDE_CHUNK
+#define DICE_WIDE_CHUNK 128
+#endif
+
+template <int Q, int O>
+static cudaError_t launch_dice_cfg(const BatchView &b, cudaStream_t s, uint32_t ctas_per_sm, uint32_t max_chunk) {
+    static bool configured = false;  // (one per instantiation)
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_dice, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiceShared));
+        cudaError_t e = cudaFuncSetAttribute(k_dice<Q, O>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(DiceSharedT<Q, O>));
         if (e != cudaSuccess) return e;
         configured = true;
     }
     // Segments per CTA and pass: few segments -> small chunks (every SM gets one, deep trees fit the queue);
     // many segments -> large chunks (fewer block-wide barriers per segment).
-    const uint32_t ctas = (uint32_t)sm_count() * 2u;
+    const uint32_t ctas = (uint32_t)sm_count() * ctas_per_sm;
     uint32_t chunk = (b.segment_count / (ctas * 4u) + 31u) & ~31u;
-#ifndef DICE_MAX_CHUNK
-#define DICE_MAX_CHUNK DICE_THREADS
-#endif
-    chunk = chunk < DICE_CHUNK ? DICE_CHUNK : (chunk > DICE_MAX_CHUNK ? DICE_MAX_CHUNK : chunk);
+    chunk = chunk < DICE_CHUNK ? DICE_CHUNK : (chunk > max_chunk ? max_chunk : chunk);
     const uint32_t n_chunks = (b.segment_count + chunk - 1) / chunk;
     const uint32_t grid = min(n_chunks, ctas);
-    return launch_pdl(k_dice, grid, DICE_THREADS, sizeof(DiceShared), s, b, chunk);
+    return launch_pdl(k_dice<Q, O>, grid, DICE_THREADS, sizeof(DiceSharedT<Q, O>), s, b, chunk);
+}
+
+cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
+    if (!b.segment_count) return cudaSuccess;
+#ifndef DICE_WIDE_Q
+#define DICE_WIDE_Q 512
+#define DICE_WIDE_CTAS 4
+#endif
+    if (b.segment_count > DICE_WIDE_SEGMENTS) return launch_dice_cfg<DICE_WIDE_Q, DICE_WIDE_Q>(b, s, DICE_WIDE_CTAS, DICE_WIDE_CHUNK);
+    return launch_dice_cfg<1024, 1024>(b, s, 2u, DICE_THREADS);
 }
 
 // ------------------------------------------------------------------------------------------------ bin

@@ -325,3 +325,11 @@ def test_retained_frame_graph_serves_identical_frames_only(renderer, area_lut):
         assert np.array_equal(renderer.pixels(), want_tiger)
     finally:
         renderer.set_retain_frame_graph(True)
+
+
+def test_many_small_paths_bit_exact_vs_oracle(renderer, area_lut):
+    """More than 65 536 segments in one batch: dice takes its 4-CTAs-per-SM configuration and propagate its
+    lane-per-column walk for glyph-sized paths (BASELINE.json config 4 at a size the oracle finishes in seconds)."""
+    scene = scenes.synthetic_scene(8000, 2048)
+    assert sum(int(b["info"][3]) for b in scene["draw_batches"]) > 65536
+    compare_with_oracle(renderer, area_lut, scene, "8000 blobs")
