@@ -33,7 +33,10 @@ int sm_count() {
     return g_sm_count;
 }
 
-constexpr int SCAN_THREADS = 256;
+#ifndef SCAN_THREADS_N
+#define SCAN_THREADS_N 256
+#endif
+constexpr int SCAN_THREADS = SCAN_THREADS_N;  // (>= 256: the descriptor arrays are sized for 2048 items per tile)
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
