@@ -36,10 +36,13 @@ SVG_SCENES = {
 DIGEST_ONLY = {
     "tiger_4096": ("tiger.svg", 4096, 900.0),      # BASELINE.json configs[2]
 }
-# demo/common/app.cpp:21-101 blocks: 1 rect, 2 clip circle, 16 gradient stroke (4 shadow, 8 image, 32 render target
-# need render-target passes: SURVEY.md section 8 row f3)
+# demo/common/app.cpp:21-101 blocks: 1 rect, 2 clip circle, 4 blurred shadow, 8 image, 16 gradient stroke, 32 render
+# target pattern. 0x3f = the whole primitives scene of the demo (shadow = two blur passes through render targets).
+# name -> (size, scale, feature mask)
 DEMO_SCENES = {
     "demo_clip_512": (512, 1.0, 1 | 2 | 16),
+    "demo_full_512": (512, 1.0, 0x3f),
+    "demo_full_2048": (2048, 2048 / 720.0, 0x3f),  # BASELINE.json configs[1], demo-primitives half
 }
 
 

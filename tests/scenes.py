@@ -201,7 +201,14 @@ def canonical_from_taps(scene, batch, tiles, fills, clip_batch=None, clip_tiles=
     ti, quad = ti[order], quad[order]
     utile, starts = np.unique(ti, return_index=True)
     ends = np.append(starts[1:], len(ti))
-    hashes = np.array([_group_hash(quad[s:e]) for s, e in zip(starts, ends)], "<u8")
+    # the GPU-driven builder does not clip a clip path's tile rect to the view box (d3d11/scene_builder.cpp:80 "TODO"),
+    # the hybrid tiler does (tiler.cpp:327): tiles outside the view box exist only on the GPU-driven side (they feed the
+    # column backdrops, which ARE compared) and are left out of the fill-group comparison
+    vb = np.asarray(scene["view_box"], "f4")
+    vx0, vy0 = int(np.floor(vb[0] / 16)), int(np.floor(vb[1] / 16))
+    vx1, vy1 = int(np.ceil(vb[2] / 16)), int(np.ceil(vb[3] / 16))
+    hashes = np.array([_group_hash(quad[s:e]) for t, s, e in zip(utile, starts, ends)
+                       if vx0 <= tx[t] < vx1 and vy0 <= ty[t] < vy1], "<u8")
     # keyed fills: tiles that own a mask of their own and are listed
     first_own = None
     own = (tiles["alpha_tile_id"] >= 0) & (tiles["fill_count"] > 0) & listed
@@ -224,6 +231,26 @@ def canonical_from_taps(scene, batch, tiles, fills, clip_batch=None, clip_tiles=
             c = cidx[int(tiles["clip_alpha_tile_id"][i])]
             clips[j]["src_backdrop"] = clip_tiles["backdrop_d3d9"][c]
             clips[j]["src_group"] = _group_hash(cq[cti == c])
+        # solid draw tile x alpha clip tile: the draw tile points straight at the clip's mask (tiler.cpp:417-422), so
+        # the reference form keys the clip tile's fills by the draw tile when that mask has exactly one such user and
+        # is not also the source of a mask combine in this batch
+        borrowed = np.nonzero((tiles["alpha_tile_id"] >= 0) & (tiles["fill_count"] == 0) & listed)[0]
+        if len(borrowed):
+            ids, cnt = np.unique(tiles["alpha_tile_id"][listed & (tiles["alpha_tile_id"] >= 0)], return_counts=True)
+            users = dict(zip(ids.tolist(), cnt.tolist()))
+            combine_src = set(tiles["clip_alpha_tile_id"][has_clip].tolist())
+            extra = []
+            for i in borrowed:
+                a = int(tiles["alpha_tile_id"][i])
+                if users.get(a, 0) != 1 or a in combine_src or a not in cidx:
+                    continue
+                q = cq[cti == cidx[a]]
+                e = np.zeros(len(q), CANON_FILL_DT)
+                e["path"], e["tile_x"], e["tile_y"] = gid[i], tx[i], ty[i]
+                e["from_x"], e["from_y"], e["to_x"], e["to_y"] = q.T
+                extra.append(e)
+            if extra:
+                k = np.concatenate([k] + extra)
     return dict(tiles=_sorted(ct), fills=_sorted(k), clips=_sorted(clips), group_hashes=np.sort(hashes))
 
 

@@ -12,7 +12,7 @@ import scenes
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = ["tiger_512", "tiger_1024", "features_2048", "demo_clip_512"]
+GOLDEN = ["tiger_512", "tiger_1024", "features_2048", "demo_clip_512", "demo_full_512", "demo_full_2048"]
 PIXEL_TOL = 1  # 1/255 per channel, BASELINE.json north_star
 
 
