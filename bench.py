@@ -8,7 +8,9 @@ A step is one whole frame (every batch of the scene: bound, dice, bin, propagate
   value   : segments/s with all inputs resident in HBM, frame replayed as one CUDA graph, CUDA-event time per step on
             the launching stream, L2 flushed between steps (not timed), max over ranks.
   e2e     : the same metric through the public C-ABI with HOST buffers: every step uploads the scene's segments and
-            batch metadata (pinned staging -> H2D), runs the frame, and reads the frame counters back (D2H).
+            batch metadata (pinned staging -> H2D), runs the frame, and reads the frame counters back (D2H); wall clock
+            over all steps with --e2e-contexts frames in flight (pfcu_submit_frame / pfcu_wait_frame, one context per
+            frame in flight); e2e.serial_ms_per_step is the blocking one-context figure (pfcu_end_frame every frame).
   roofline: the composite ("tile") kernel, algorithmic bytes of SURVEY.md section 8d / measured HBM copy bandwidth.
 N > 1 (torchrun): the scene-sharded configuration -- every rank renders its own frames, no data-path collective
 (SURVEY.md section 8e), weak scaling.
@@ -42,8 +44,11 @@ WORKLOADS = {
     "tiger1024": ("tiger_1024", "tiger.svg", 1024, 900.0),
     "tiger512": ("tiger_512", "tiger.svg", 512, 900.0),
     "features2048": ("features_2048", "features.svg", 2048, 720.0),
+    # the primitives scene of the reference demo (clip, blurred shadow, image, gradient, render-target pattern): the
+    # other half of BASELINE.json configs[1]; 9 prepared batches, 11 tile passes, 4 of them into render targets
+    "demo2048": ("demo_full_2048", "demo:sea.png", 2048, 720.0),
 }
-METRIC = "segments/s (dice->composite), tiger.svg at 4096x4096"
+METRIC = "segments/s (dice->composite), %s at %dx%d"  # default workload: tiger.svg at 4096x4096
 UNIT = "segments/s"
 
 
@@ -124,7 +129,10 @@ def reference_cpu(asset, size, native, steps, warmup, budget_s=20.0):
     import pfref
 
     if pfref.available():
-        s = pfref.RefScene.from_svg(pfref.asset(asset), size, size, size / native)
+        if asset.startswith("demo:"):
+            s = pfref.RefScene.demo(size, size, size / native, pfref.asset(asset[5:]), 0x3f)
+        else:
+            s = pfref.RefScene.from_svg(pfref.asset(asset), size, size, size / native)
         s.time_d3d9_build(max(warmup, 1))
         probe = float(np.median(s.time_d3d9_build(3)))
         n = int(max(1, min(steps, budget_s * 1000.0 / max(probe, 1e-3))))
@@ -158,7 +166,7 @@ def run_reference(args, rank):
     ms = float(np.mean(r["ms"]))
     value = segs / (ms / 1e3)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+        "impl": "reference", "metric": METRIC % (asset, size, size), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "reference asset %s parsed by the reference front end" % asset,
         "config": {"workload": "%s@%dx%d" % (asset, size, size), "threads": r["cores"],
@@ -280,7 +288,35 @@ def run_ours(args, rank, world):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         st = r.draw(clear=True, upload=True)  # pfcu_end_frame synchronises and reads the counters back
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_serial_ms = (time.perf_counter() - t0) * 1e3
+    # ... and streamed: the same per-frame work (H2D of the frame's inputs, the frame, D2H of its counters) with
+    # args.e2e_contexts frames in flight, one renderer context (own stream, own framebuffer) each -- double buffering
+    # as an application that renders a sequence of frames does it (pfcu_submit_frame / pfcu_wait_frame)
+    n_ctx = max(1, args.e2e_contexts)
+    if n_ctx > 1:
+        rs = [pfcu.Renderer(local, lut) for _ in range(n_ctx)]
+        for q in rs:
+            q.set_scene(scene)
+            for _ in range(4):
+                q.draw(clear=True, upload=True)
+        torch.cuda.synchronize()
+        pending = [False] * n_ctx
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            k = i % n_ctx
+            if pending[k]:
+                rs[k].wait()
+            rs[k].draw(clear=True, upload=True, wait=False)
+            pending[k] = True
+        for k in range(n_ctx):
+            if pending[k]:
+                st = rs[k].wait()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        assert st["retries"] == 0 and st["fills"] == steady["fills"], st
+        for q in rs:
+            q.close()
+    else:
+        e2e_ms = e2e_serial_ms
     clocks = sampler.stop()
     h2d = int(sum(scene[k].nbytes for k in ("draw_points", "draw_indices", "clip_points", "clip_indices")))
     for b in scene["draw_batches"] + scene["clip_batches"]:
@@ -295,9 +331,9 @@ def run_ours(args, rank, world):
         px_ms.append((time.perf_counter() - t0) * 1e3)
 
     if world > 1:
-        t = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([total_ms, e2e_ms, e2e_serial_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_ms = float(t[0]), float(t[1])
+        total_ms, e2e_ms, e2e_serial_ms = float(t[0]), float(t[1]), float(t[2])
     if rank != 0:
         r.close()
         if world > 1:
@@ -311,7 +347,8 @@ def run_ours(args, rank, world):
     fill_gbs = bytes_["B_fill"] / (stage_ms["fill"] * 1e-3) / 1e9 if stage_ms["fill"] > 0 else 0.0
     both = (bytes_["B_fill"] + bytes_["B_tile"]) / ((stage_ms["fill"] + comp_ms) * 1e-3) / 1e9
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC % (asset, size, size), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup,
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic-free: reference asset %s, scene fixture built by the reference front end"
                                 % asset,
@@ -329,7 +366,8 @@ def run_ours(args, rank, world):
                      "fill_plus_tile": {"achieved": both, "frac": both / peak},
                      "stage_ms": stage_ms, "counts": bytes_},
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h,
+                "d2h_bytes_per_step": d2h, "frames_in_flight": n_ctx,
+                "serial_ms_per_step": e2e_serial_ms / args.steps,  # one context, pfcu_end_frame blocks every frame
                 "with_frame_readback_ms": float(np.median(px_ms)),
                 "frame_readback_bytes": int(scene["width"]) * int(scene["height"]) * 4},
         "gpu_launches": int(gstats["kernel_launches"]) * args.steps,
@@ -537,6 +575,7 @@ def main():
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="--workload synthetic: strip assembly")
     ap.add_argument("--frames", type=int, default=0, help="batch mode: render this many independent frames per step")
     ap.add_argument("--contexts", type=int, default=16, help="batch mode: renderer contexts (streams) per GPU")
+    ap.add_argument("--e2e-contexts", type=int, default=4, help="e2e leg: frames in flight (1 = blocking pfcu_end_frame)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

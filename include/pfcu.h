@@ -153,6 +153,13 @@ int pfcu_draw_batch(pfcu_ctx *ctx, uint32_t batch_id, int target_page, int color
  * and replays the recorded frame (the reference's retry loops, renderer.cpp:537-577, without the mid-frame
  * read-backs). stats may be NULL. */
 int pfcu_end_frame(pfcu_ctx *ctx, pfcu_frame_stats *stats);
+/* pfcu_end_frame in two halves, for callers that keep several frames in flight (one context per frame in flight,
+ * e.g. double buffering): pfcu_submit_frame enqueues the rest of the frame and its read-back and returns without
+ * waiting; pfcu_wait_frame blocks until that frame is done and does the overflow check / replay / stats of
+ * pfcu_end_frame. Between the two calls the context accepts no other frame or upload call (PFCU_ERR_STATE). The
+ * reference submits and blocks on its one fence in the same step (Queue::submit, gpu/queue.h:17; core/renderer.cpp:30). */
+int pfcu_submit_frame(pfcu_ctx *ctx);
+int pfcu_wait_frame(pfcu_ctx *ctx, pfcu_frame_stats *stats);
 
 /* ---- options */
 enum {

@@ -143,7 +143,12 @@ struct pfcu_ctx {
     float view_box[4] = {0, 0, 0, 0};
     int origin_tx = 0, origin_ty = 0;
     // scene
-    DevBuf points[2], indices[2];
+    DevBuf scene_dev[2];  // points, then (16-byte aligned) indices: one H2D copy per upload
+    size_t indices_off[2] = {0, 0};
+    bool stage_busy[2] = {false, false};  // an H2D copy out of stage_scene[i] may still be running
+    bool frame_pending = false;           // pfcu_submit_frame without its pfcu_wait_frame yet
+    bool pending_served_by_graph = false;
+    uint64_t pending_sig = 0;
     uint32_t n_points[2] = {0, 0}, n_segments[2] = {0, 0};
     PinnedBuf stage_scene[2];
     DevBuf paints;  // Paint table decoded from the RGBA16F metadata texels
@@ -204,6 +209,7 @@ int sync_if_in_flight(pfcu_ctx *c) {
         if (c->aux_pending) CUDA_TRY(cudaStreamSynchronize(c->aux_stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->in_flight = false;
+        c->stage_busy[0] = c->stage_busy[1] = false;
     }
     return PFCU_OK;
 }
@@ -306,8 +312,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.dice = reinterpret_cast<const pfcu_dice_metadata *>(m + s.off_dice);
     v.tpi = reinterpret_cast<const pfcu_tile_path_info *>(m + s.off_tpi);
     const int which = d.path_source ? 1 : 0;
-    v.points = c->points[which].as<float2>();
-    v.indices = c->indices[which].as<uint2>();
+    v.points = c->scene_dev[which].as<float2>();
+    v.indices = reinterpret_cast<uint2 *>(c->scene_dev[which].as<char>() + c->indices_off[which]);
     v.n_points = c->n_points[which];
     v.n_segments_total = c->n_segments[which];
     v.path_count = d.path_count;
@@ -585,8 +591,7 @@ void pfcu_destroy(pfcu_ctx *c) {
     }
     for (auto &p : c->pages) p.px.release();
     for (int i = 0; i < 2; i++) {
-        c->points[i].release();
-        c->indices[i].release();
+        c->scene_dev[i].release();
         c->stage_scene[i].release();
     }
     c->lut.release();
@@ -704,21 +709,21 @@ int pfcu_upload_scene(pfcu_ctx *c, int which, const float *points, uint32_t n_po
     if (!c || which < 0 || which > 1 || (n_points && !points) || (n_segments && !indices))
         return fail(PFCU_ERR_INVALID, "bad scene upload");
     CUDA_TRY(cudaSetDevice(c->device));
-    int r = sync_if_in_flight(c);
-    if (r) return r;
+    if (c->frame_pending) return fail(PFCU_ERR_STATE, "a submitted frame has not been waited for");
     const size_t pb = (size_t)n_points * 8, ib = (size_t)n_segments * 8;
-    CUDA_TRY(c->points[which].ensure(std::max<size_t>(pb, 8)));
-    CUDA_TRY(c->indices[which].ensure(std::max<size_t>(ib, 8)));
-    CUDA_TRY(c->stage_scene[which].ensure(pb + ib + 16));
+    const size_t ioff = (pb + 15) & ~(size_t)15;
+    if (c->stage_busy[which] || ioff + ib > c->scene_dev[which].cap || ioff + ib + 16 > c->stage_scene[which].cap) {
+        int r = sync_if_in_flight(c);
+        if (r) return r;
+    }
+    CUDA_TRY(c->scene_dev[which].ensure(std::max<size_t>(ioff + ib, 16)));
+    CUDA_TRY(c->stage_scene[which].ensure(ioff + ib + 16));
     char *st = static_cast<char *>(c->stage_scene[which].p);
-    if (pb) {
-        memcpy(st, points, pb);
-        CUDA_TRY(cudaMemcpyAsync(c->points[which].p, st, pb, cudaMemcpyHostToDevice, c->stream));
-    }
-    if (ib) {
-        memcpy(st + pb, indices, ib);
-        CUDA_TRY(cudaMemcpyAsync(c->indices[which].p, st + pb, ib, cudaMemcpyHostToDevice, c->stream));
-    }
+    if (pb) memcpy(st, points, pb);
+    if (ib) memcpy(st + ioff, indices, ib);
+    if (pb + ib) CUDA_TRY(cudaMemcpyAsync(c->scene_dev[which].p, st, ioff + ib, cudaMemcpyHostToDevice, c->stream));
+    c->indices_off[which] = ioff;
+    c->stage_busy[which] = (pb + ib) != 0;
     c->n_points[which] = n_points;
     c->n_segments[which] = n_segments;
     c->in_flight = true;
@@ -819,6 +824,7 @@ int pfcu_upload_page_region(pfcu_ctx *c, uint32_t page, int x, int y, int width,
 int pfcu_begin_frame(pfcu_ctx *c) {
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     if (!c->target.pixels) return fail(PFCU_ERR_STATE, "pfcu_set_target has not been called");
+    if (c->frame_pending) return fail(PFCU_ERR_STATE, "a submitted frame has not been waited for");
     CUDA_TRY(cudaSetDevice(c->device));
     for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
     c->slots_used = 0;
@@ -907,12 +913,22 @@ int pfcu_draw_batch(pfcu_ctx *c, uint32_t batch_id, int target_page, int color_p
     return enqueue_draw(c, cmd);
 }
 
-int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
+// The tail of every attempt: join the second stream, close the frame's event pair, start the one read-back of the frame
+// (counters of every batch + the frame alpha counter: one copy of the whole block is cheaper than two small ones).
+static int enqueue_frame_tail(pfcu_ctx *c) {
+    int r = join_aux(c);  // batches that were prepared but not drawn (clip batches)
+    if (r) return r;
+    if (c->event_begin_recorded) CUDA_TRY(cudaEventRecord(c->ev_end, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->host_counters.p, c->counters.p, sizeof(BatchCounters) * (MAX_SLOTS + 1), cudaMemcpyDeviceToHost,
+                             c->stream));
+    return PFCU_OK;
+}
+
+int pfcu_submit_frame(pfcu_ctx *c) {
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     if (!c->frame_open) return fail(PFCU_ERR_STATE, "no frame is open");
+    if (c->frame_pending) return fail(PFCU_ERR_STATE, "the frame has already been submitted");
     CUDA_TRY(cudaSetDevice(c->device));
-    BatchCounters *hc = static_cast<BatchCounters *>(c->host_counters.p);
-    const size_t cbytes = sizeof(BatchCounters) * (MAX_SLOTS + 1);
     const uint64_t sig = c->frame_sig;
     bool served_by_graph = false;
     if (c->dry) {  // nothing has been enqueued yet: the retained graph serves the frame if it is the same frame
@@ -939,19 +955,40 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
             }
         }
     }
+    {
+        const int r = enqueue_frame_tail(c);
+        if (r) {
+            c->frame_open = false;
+            return r;
+        }
+    }
+    c->pending_served_by_graph = served_by_graph;
+    c->pending_sig = sig;
+    c->frame_pending = true;
+    return PFCU_OK;
+}
+
+int pfcu_wait_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    if (!c->frame_pending) return fail(PFCU_ERR_STATE, "no frame has been submitted");
+    CUDA_TRY(cudaSetDevice(c->device));
+    c->frame_pending = false;
+    BatchCounters *hc = static_cast<BatchCounters *>(c->host_counters.p);
+    const uint64_t sig = c->pending_sig;
+    const bool served_by_graph = c->pending_served_by_graph;
     int attempts_used = 0;
     for (int attempt = 0;; attempt++) {
         attempts_used = attempt;
-        {
-            int r = join_aux(c);  // batches that were prepared but not drawn (clip batches)
-            if (r) return r;
+        if (attempt > 0) {
+            const int r = enqueue_frame_tail(c);
+            if (r) {
+                c->frame_open = false;
+                return r;
+            }
         }
-        if (c->event_begin_recorded) CUDA_TRY(cudaEventRecord(c->ev_end, c->stream));
-        // the one read-back of the frame: counters of every batch + the frame alpha counter
-        // (one copy of the whole 16 KB block -- batch counters + frame alpha counter -- is cheaper than two small ones)
-        CUDA_TRY(cudaMemcpyAsync(hc, c->counters.p, cbytes, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->in_flight = false;
+        c->stage_busy[0] = c->stage_busy[1] = false;
         uint32_t overflow = 0, dda_anomaly = 0;
         const uint32_t frame_alpha = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
         for (int i = 0; i < c->slots_used; i++) {
@@ -1031,6 +1068,11 @@ int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
     if (stats) *stats = st;
     c->frame_open = false;
     return PFCU_OK;
+}
+
+int pfcu_end_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
+    const int r = pfcu_submit_frame(c);
+    return r ? r : pfcu_wait_frame(c, stats);
 }
 
 int pfcu_set_option(pfcu_ctx *c, int option, int value) {

@@ -18,6 +18,7 @@ EXPORTS = [
     "pfcu_abi_version", "pfcu_last_error", "pfcu_create", "pfcu_destroy", "pfcu_set_stream", "pfcu_get_stream",
     "pfcu_set_area_lut", "pfcu_set_target", "pfcu_set_target_origin", "pfcu_upload_scene", "pfcu_upload_paint_metadata", "pfcu_alloc_page",
     "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
+    "pfcu_submit_frame", "pfcu_wait_frame",
     "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
     "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
     "pfcu_get_stage_times", "pfcu_set_option", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
@@ -82,6 +83,8 @@ def lib():
         L.pfcu_prepare_batch.argtypes = [vp, C.POINTER(BatchDesc)]
         L.pfcu_draw_batch.argtypes = [vp, u32, i32, i32, u32, i32, vp]
         L.pfcu_end_frame.argtypes = [vp, C.POINTER(FrameStats)]
+        L.pfcu_submit_frame.argtypes = [vp]
+        L.pfcu_wait_frame.argtypes = [vp, C.POINTER(FrameStats)]
         L.pfcu_read_target.argtypes = [vp, vp]
         L.pfcu_read_page.argtypes = [vp, u32, vp]
         L.pfcu_target_device_ptr.argtypes = [vp, C.POINTER(sz)]
@@ -190,9 +193,10 @@ class Renderer:
                        "draw": [make_desc(b, self._keep) for b in scene["draw_batches"]]}
 
     # -- frame
-    def draw(self, clear=True, clear_color=(0.0, 0.0, 0.0, 0.0), upload=False):
+    def draw(self, clear=True, clear_color=(0.0, 0.0, 0.0, 0.0), upload=False, wait=True):
         """RendererD3D11::draw: clip batches in reverse, then prepare + composite every draw batch.
-        upload=True re-uploads the segments first (what the reference does every frame, renderer.cpp:314)."""
+        upload=True re-uploads the segments first (what the reference does every frame, renderer.cpp:314).
+        wait=False submits the frame (pfcu_submit_frame) and returns; wait() collects it."""
         scene = self.scene
         if upload:
             self.upload_segments(scene)
@@ -215,8 +219,17 @@ class Renderer:
                 first = False
             else:
                 _check(L.pfcu_draw_batch(self.h, d.batch_id, int(info[11]), color_page, flags, 1, _p(zero)))
+        if not wait:
+            _check(L.pfcu_submit_frame(self.h))
+            return None
         st = FrameStats()
         _check(L.pfcu_end_frame(self.h, C.byref(st)))
+        return st.as_dict()
+
+    def wait(self):
+        """Second half of draw(wait=False): pfcu_wait_frame."""
+        st = FrameStats()
+        _check(self.L.pfcu_wait_frame(self.h, C.byref(st)))
         return st.as_dict()
 
     # -- options / measurement

@@ -333,3 +333,38 @@ def test_many_small_paths_bit_exact_vs_oracle(renderer, area_lut):
     scene = scenes.synthetic_scene(8000, 2048)
     assert sum(int(b["info"][3]) for b in scene["draw_batches"]) > 65536
     compare_with_oracle(renderer, area_lut, scene, "8000 blobs")
+
+
+def test_frames_in_flight_on_two_contexts(renderer, area_lut):
+    """pfcu_submit_frame / pfcu_wait_frame: two contexts each keep a frame in flight (uploads included); every frame is
+    byte-identical to the blocking pfcu_end_frame render, and the call-sequence rules are enforced."""
+    import pfcu
+
+    tiger, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    demo, _ = scenes.load_scene(scenes.golden_path("demo_full_512"))
+    want = {}
+    for name, scene in (("tiger", tiger), ("demo", demo)):
+        renderer.set_scene(scene)
+        renderer.draw(clear=True)
+        want[name] = renderer.pixels()
+    a, b = pfcu.Renderer(0, area_lut), pfcu.Renderer(0, area_lut)
+    try:
+        a.set_scene(tiger)
+        b.set_scene(demo)
+        for i in range(6):
+            assert a.draw(clear=True, upload=True, wait=False) is None
+            assert b.draw(clear=True, upload=True, wait=False) is None
+            if i == 2:  # nothing but pfcu_wait_frame is accepted while the frame is pending
+                with pytest.raises(RuntimeError):
+                    a.draw(clear=True, wait=False)
+                with pytest.raises(RuntimeError):
+                    a.upload_segments(tiger)
+            sa, sb = a.wait(), b.wait()
+            assert sa["fills"] == 27200 and sa["retries"] == 0 or i == 0
+            assert np.array_equal(a.pixels(), want["tiger"]), "tiger frame %d" % i
+            assert np.array_equal(b.pixels(), want["demo"]), "demo frame %d" % i
+        with pytest.raises(RuntimeError):
+            a.wait()  # no frame submitted
+    finally:
+        a.close()
+        b.close()
