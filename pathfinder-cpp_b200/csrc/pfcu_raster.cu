@@ -772,6 +772,8 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
     cs.repeat_v = (p.sampling_flags & 2u) != 0;
     cs.nearest = (p.sampling_flags & 0xcu) != 0;
     const int k_own = (int)(lane & 3u), s_own = (int)(lane >> 2);
+    // 16-byte stores need 16-byte rows (a render-target page of odd width has none: 4-byte stores there)
+    const bool vec_ok = ((reinterpret_cast<size_t>(tg.pixels) | tg.pitch) & 15) == 0;
     // gl_FragCoord of the full canvas (only textured paints look at it); render-target pages have no origin
     const float org_x = (float)(origin ? b.fb_tx0 * TILE : 0) + 0.5f, org_y = (float)(origin ? b.fb_ty0 * TILE : 0) + 0.5f;
 
@@ -801,7 +803,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 const int tile_x = (int)(xy & 0xffffu), tile_y = (int)(xy >> 16);
                 g.gx0 = tile_x * TILE + k_own * 4;
                 g.gy0 = tile_y * TILE + s_own * 2;
-                g.interior = (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
+                g.interior = vec_ok && (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
                 g.px0 = tg.pixels + (size_t)g.gy0 * tg.pitch + (size_t)g.gx0 * 4;
                 g.fragx = (float)g.gx0 + org_x;
                 g.fragy = (float)g.gy0 + org_y;
@@ -931,7 +933,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 int gy = tile_y * TILE + (int)(tid / (4 * CT_TILES));
                 uint8_t *dst = tg.pixels + (size_t)gy * tg.pitch + (size_t)gx * 4;
                 const uint4 v = make_uint4(c, c, c, c);
-                if ((tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height) {
+                if (vec_ok && (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height) {
 #pragma unroll
                     for (uint32_t r = 0; r < TILE / ROW_STEP; r++, dst += ROW_STEP * tg.pitch) *reinterpret_cast<uint4 *>(dst) = v;
                 } else {
@@ -959,7 +961,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 const int tile_x = (int)(xy & 0xffffu), tile_y = (int)(xy >> 16);
                 g.gx0 = tile_x * TILE + k_own * 4;
                 g.gy0 = tile_y * TILE + s_own * 2;
-                g.interior = (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
+                g.interior = vec_ok && (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
                 g.px0 = tg.pixels + (size_t)g.gy0 * tg.pitch + (size_t)g.gx0 * 4;
                 g.fragx = (float)g.gx0 + org_x;
                 g.fragy = (float)g.gy0 + org_y;
