@@ -201,6 +201,9 @@ int pfcu_graph_finish(pfcu_ctx *ctx, pfcu_frame_stats *stats); /* waits, reads t
 
 /* ---- results */
 int pfcu_read_target(pfcu_ctx *ctx, uint8_t *host_rgba8);                    /* width*height*4, tightly packed */
+/* CommandEncoder::read_texture(texture, region, data) (gpu/command_encoder.cpp:317-355): width*height*4 bytes, tightly
+ * packed; a region that is empty or not inside the target is PFCU_ERR_INVALID (the reference logs and returns). */
+int pfcu_read_target_region(pfcu_ctx *ctx, int x, int y, int width, int height, uint8_t *host_rgba8);
 int pfcu_read_page(pfcu_ctx *ctx, uint32_t page, uint8_t *host_rgba8);
 void *pfcu_target_device_ptr(pfcu_ctx *ctx, size_t *pitch_bytes);            /* zero-copy consumers */
 

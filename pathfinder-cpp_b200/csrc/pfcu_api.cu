@@ -1161,6 +1161,19 @@ int pfcu_read_target(pfcu_ctx *c, uint8_t *host) {
     return PFCU_OK;
 }
 
+int pfcu_read_target_region(pfcu_ctx *c, int x, int y, int width, int height, uint8_t *host) {
+    if (!c || !host || !c->target.pixels) return fail(PFCU_ERR_INVALID, "no target");
+    // CommandEncoder::read_texture (gpu/command_encoder.cpp:317-325): an invalid or empty region is an error
+    if (x < 0 || y < 0 || width <= 0 || height <= 0 || x + width > c->target.width || y + height > c->target.height)
+        return fail(PFCU_ERR_INVALID, "region %d,%d %dx%d is outside the %dx%d target", x, y, width, height,
+                    c->target.width, c->target.height);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaMemcpy2D(host, (size_t)width * 4, c->target.pixels + (size_t)y * c->target.pitch + (size_t)x * 4,
+                          c->target.pitch, (size_t)width * 4, height, cudaMemcpyDeviceToHost));
+    return PFCU_OK;
+}
+
 int pfcu_read_page(pfcu_ctx *c, uint32_t page, uint8_t *host) {
     if (!c || !host || page >= MAX_PAGES || !c->pages[page].px.p) return fail(PFCU_ERR_INVALID, "texture page not allocated");
     CUDA_TRY(cudaSetDevice(c->device));

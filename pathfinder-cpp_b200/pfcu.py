@@ -18,7 +18,7 @@ EXPORTS = [
     "pfcu_abi_version", "pfcu_last_error", "pfcu_create", "pfcu_destroy", "pfcu_set_stream", "pfcu_get_stream",
     "pfcu_set_area_lut", "pfcu_set_target", "pfcu_set_target_origin", "pfcu_upload_scene", "pfcu_upload_paint_metadata", "pfcu_alloc_page",
     "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
-    "pfcu_submit_frame", "pfcu_wait_frame",
+    "pfcu_submit_frame", "pfcu_wait_frame", "pfcu_read_target_region",
     "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
     "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
     "pfcu_get_stage_times", "pfcu_set_option", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
@@ -86,6 +86,7 @@ def lib():
         L.pfcu_submit_frame.argtypes = [vp]
         L.pfcu_wait_frame.argtypes = [vp, C.POINTER(FrameStats)]
         L.pfcu_read_target.argtypes = [vp, vp]
+        L.pfcu_read_target_region.argtypes = [vp, i32, i32, i32, i32, vp]
         L.pfcu_read_page.argtypes = [vp, u32, vp]
         L.pfcu_target_device_ptr.argtypes = [vp, C.POINTER(sz)]
         L.pfcu_target_device_ptr.restype = vp
@@ -259,6 +260,11 @@ class Renderer:
     def pixels(self):
         px = np.zeros((self.height, self.width, 4), "u1")
         _check(self.L.pfcu_read_target(self.h, _p(px)))
+        return px
+
+    def pixels_region(self, x, y, width, height):
+        px = np.zeros((height, width, 4), "u1")
+        _check(self.L.pfcu_read_target_region(self.h, int(x), int(y), int(width), int(height), _p(px)))
         return px
 
     # -- parity taps

@@ -368,3 +368,16 @@ def test_frames_in_flight_on_two_contexts(renderer, area_lut):
     finally:
         a.close()
         b.close()
+
+
+def test_region_readback_matches_the_full_frame(renderer):
+    """pfcu_read_target_region = CommandEncoder::read_texture with a region (gpu/command_encoder.cpp:317-355)."""
+    scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    full = renderer.pixels()
+    for x, y, w, h in ((0, 0, 512, 512), (17, 33, 100, 7), (500, 500, 12, 12), (3, 0, 1, 512)):
+        assert np.array_equal(renderer.pixels_region(x, y, w, h), full[y:y + h, x:x + w])
+    for bad in ((-1, 0, 4, 4), (0, 0, 0, 4), (510, 0, 4, 4), (0, 510, 4, 4)):
+        with pytest.raises(RuntimeError):
+            renderer.pixels_region(*bad)
