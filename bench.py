@@ -203,8 +203,11 @@ def algorithmic_bytes(r, scene):
         bid = int(b["info"][0])
         tiles = r.tiles(bid)
         off, lst = r.tile_lists(bid)
-        F += int(tiles["fill_count"][tiles["alpha_tile_id"] >= 0].sum())
-        own = (tiles["alpha_tile_id"] >= 0) & (tiles["fill_count"] > 0)
+        # masks the fill stage rasterizes: tiles with fills whose tile survives the z-cull (PFCU_OPT_FILL_CULLED_TILES = 0)
+        kept = np.zeros(len(tiles), bool)
+        kept[lst] = True
+        own = (tiles["alpha_tile_id"] >= 0) & (tiles["fill_count"] > 0) & kept
+        F += int(tiles["fill_count"][own].sum())
         A += int(own.sum())
         Ac += int((tiles["clip_alpha_tile_id"] >= 0).sum())
         L += len(lst)

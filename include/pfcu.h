@@ -168,7 +168,11 @@ enum {
      * pfcu_end_frame (pfcu_prepare_batch / pfcu_draw_batch then only record). The reference has the matching notion in
      * its scene epochs (core/scene.h:32-49). A frame that differs is enqueued kernel by kernel and the graph dropped.
      * 0: always enqueue kernel by kernel. */
-    PFCU_OPT_RETAIN_FRAME_GRAPH = 0
+    PFCU_OPT_RETAIN_FRAME_GRAPH = 0,
+    /* 0 (default): the fill stage skips the masks of draw tiles that the z-buffer culls (tiles under an opaque whole-tile
+     * layer of a later path, sort.comp:62): nothing ever reads them (19 % of tiger.svg's masks at 4096^2). 1: every mask
+     * is rasterized, as fill.comp:109-154 does (pfcu_read_mask then returns a valid mask for culled tiles too). */
+    PFCU_OPT_FILL_CULLED_TILES = 1
 };
 int pfcu_set_option(pfcu_ctx *ctx, int option, int value);
 

@@ -102,7 +102,7 @@ struct BatchSlot {
     PinnedBuf host_meta;  // the four metadata vectors, packed, kept for replay
     size_t off_backdrops = 0, off_meta = 0, off_dice = 0, off_tpi = 0, meta_bytes = 0;
     DevBuf dev_meta, tile_word, fill_begin, fill_cursor, alpha_rank, col_backdrop, tile_state, lines, line_meta, staging, fills, fb, long_lines,
-        prims, alpha_tiles, scan_desc0, scan_desc1;
+        prims, alpha_tiles, alpha_map, scan_desc0, scan_desc1;
     uint32_t line_cap = 0, fill_cap = 0, staging_cap = 0;
     BatchView view{};
     bool prepared = false;
@@ -180,6 +180,7 @@ struct pfcu_ctx {
     // exists, pfcu_prepare_batch / pfcu_draw_batch only record; a frame that turns out different is enqueued the
     // ordinary way at pfcu_end_frame and the graph is dropped.
     bool auto_graph = true;
+    bool fill_culled_tiles = false;  // PFCU_OPT_FILL_CULLED_TILES
     uint64_t frame_sig = 0, prev_sig = 0, retained_sig = 0;
     cudaGraph_t retained_graph = nullptr;
     cudaGraphExec_t retained_exec = nullptr;
@@ -302,6 +303,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     CUDA_TRY(s.fb.ensure(T * sizeof(FbTile)));
     CUDA_TRY(s.prims.ensure(D * sizeof(TilePrim)));
     CUDA_TRY(s.alpha_tiles.ensure(D * sizeof(AlphaTile)));
+    CUDA_TRY(s.alpha_map.ensure(D * 4));
     CUDA_TRY(s.scan_desc0.ensure((D / 2048 + 2) * 8));
     CUDA_TRY(s.scan_desc1.ensure((T / 2048 + 2) * 8));
     BatchView v;
@@ -347,6 +349,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.prims = s.prims.as<TilePrim>();
     v.prim_capacity = d.tile_count;
     v.alpha_tiles = s.alpha_tiles.as<AlphaTile>();
+    v.alpha_map = s.alpha_map.as<uint32_t>();
+    v.cull_fill = d.path_source == 0 && !c->fill_culled_tiles;
     v.alpha_capacity = d.tile_count;
     v.scan_desc[0] = s.scan_desc0.as<unsigned long long>();
     v.scan_desc[1] = s.scan_desc1.as<unsigned long long>();
@@ -586,7 +590,7 @@ void pfcu_destroy(pfcu_ctx *c) {
         s.host_meta.release();
         for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_begin, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
                           &s.line_meta, &s.long_lines, &s.staging, &s.fills, &s.fb, &s.alpha_rank, &s.prims,
-                          &s.alpha_tiles, &s.scan_desc0, &s.scan_desc1})
+                          &s.alpha_tiles, &s.alpha_map, &s.scan_desc0, &s.scan_desc1})
             b->release();
     }
     for (auto &p : c->pages) p.px.release();
@@ -1082,6 +1086,9 @@ int pfcu_set_option(pfcu_ctx *c, int option, int value) {
         case PFCU_OPT_RETAIN_FRAME_GRAPH:
             c->auto_graph = value != 0;
             if (!c->auto_graph) drop_retained(c);
+            return PFCU_OK;
+        case PFCU_OPT_FILL_CULLED_TILES:
+            c->fill_culled_tiles = value != 0;
             return PFCU_OK;
         default:
             return fail(PFCU_ERR_INVALID, "unknown option %d", option);

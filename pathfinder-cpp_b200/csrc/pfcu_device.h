@@ -30,7 +30,8 @@ struct BatchCounters {
     uint32_t scan_ticket[2];  // dynamic tile ids for the two look-back scans
     uint32_t n_list_entries;  // total list entries (from the scan over framebuffer tiles)
     uint32_t n_long;          // lines queued for the long-line bin kernel
-    uint32_t pad[6];
+    uint32_t fill_ticket;     // next group of alpha tiles to rasterize (fill takes its work dynamically)
+    uint32_t pad[5];
 };
 static_assert(sizeof(BatchCounters) == 64, "BatchCounters");
 
@@ -124,6 +125,8 @@ struct BatchView {
     TilePrim *prims;        // [prim_capacity]
     uint32_t prim_capacity;
     AlphaTile *alpha_tiles; // [alpha_capacity] batch-local
+    uint32_t *alpha_map;    // [alpha_capacity] framebuffer tile of the mask's owner (~0: none), for fill's z-cull
+    int cull_fill;          // fill skips masks whose tile the z-buffer culls (draw batches; fill.comp rasterizes them all)
     uint32_t alpha_capacity;
     unsigned long long *scan_desc[2];  // look-back descriptors (tile_count / fb tiles)
     // clip batch (may be null)

@@ -647,6 +647,9 @@ __device__ __forceinline__ uint32_t walk_step_emit(const BatchView &b, const Pat
     return used;
 }
 
+#ifndef BIN_PERMUTE
+#define BIN_PERMUTE 1
+#endif
 constexpr int BIN_CHAIN = 1032;          // crossings per axis the long-line kernel keeps in shared memory (16 K pixels)
 constexpr int BIN_LONG_WARPS = 4;
 
@@ -654,7 +657,14 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
     pdl_wait();
     const uint32_t n_lines = min(b.counters->n_lines, b.line_capacity);
     const unsigned lane = threadIdx.x & 31;
+    // consecutive 32-line chunks go to consecutive CTAs: the grid is one wave sized for the largest batches, and with
+    // CTA-major numbering a small batch would keep the first few hundred CTAs (two or three per SM on some SMs, none on
+    // others) busy and leave the rest idle
+#if BIN_PERMUTE
+    const uint32_t warp0 = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, n_warps = (gridDim.x * blockDim.x) >> 5;
+#else
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+#endif
     for (uint32_t base = warp0 * 32; base < n_lines; base += n_warps * 32) {
         const uint32_t i = base + lane;
         bool active = i < n_lines;
@@ -765,7 +775,11 @@ __global__ void __launch_bounds__(BIN_LONG_WARPS * 32) k_bin_long(BatchView b) {
     pdl_wait();
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t n_long = min(b.counters->n_long, b.line_capacity);
+#if BIN_PERMUTE
+    const uint32_t warp0 = wib * gridDim.x + blockIdx.x, n_warps = (gridDim.x * blockDim.x) >> 5;  // (as in k_bin)
+#else
     const uint32_t warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+#endif
     float *sx = chain[wib][0], *sy = chain[wib][1];
     for (uint32_t at = warp0; at < n_long; at += n_warps) {
         const uint32_t i = b.long_lines[at];

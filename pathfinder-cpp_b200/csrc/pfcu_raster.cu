@@ -90,6 +90,12 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, unsigned lane
 __device__ __forceinline__ uint32_t unorm8_bits(float v) { return __float_as_uint(fmaf(v, 255.0f, 12582912.0f)); }
 
 constexpr int FILL_WARPS = 8;
+#ifndef FILL_DYNAMIC
+#define FILL_DYNAMIC 0
+#endif
+#ifndef FILL_PERMUTE
+#define FILL_PERMUTE 1
+#endif
 #ifndef FILL_CTAS_PER_SM
 #define FILL_CTAS_PER_SM 4  // 64 registers x 256 threads: one wave
 #endif
@@ -122,7 +128,13 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
     __shared__ FillShared sh;
     pdl_wait();
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+#if FILL_PERMUTE
+    // consecutive groups go to consecutive CTAs (different SMs): the groups of one path -- similar fill counts -- are
+    // spread over the whole GPU instead of landing on the 8 warps of one CTA
+    const uint32_t warp = wib * gridDim.x + blockIdx.x;
+#else
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#endif
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t first_alpha = b.counters->first_alpha;
     uint32_t n_alpha = b.counters->n_alpha;
@@ -133,13 +145,28 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
     const bool band = p.lut_band != 0;
     const int k_own = (int)(lane & 3u), s_own = (int)(lane >> 2);
 
-    for (uint32_t a0 = warp * FILL_GROUP; a0 < n_alpha; a0 += n_warps * FILL_GROUP) {
+    // Groups are handed out dynamically: fills per group vary from 0 to 60+ (tiger 4096^2: mean 13), and with a fixed
+    // stride the slowest warp gets 3.2 x the mean. The first group of a warp is its own index (no atomic on the way in);
+    // the ticket for the next one is taken before the current one is rasterized, so its latency is hidden.
+    uint32_t a0 = warp * FILL_GROUP, next_ticket = 0;
+#if FILL_DYNAMIC
+    if (lane == 0) next_ticket = atomicAdd(&b.counters->fill_ticket, 1u);
+#endif
+    for (; a0 < n_alpha;) {
         // ---- the group's alpha tile records, one per lane: tile | winding << 31, clip mask slot, first fill,
         // backdrop | fill count << 8
         uint4 at = make_uint4(0x7fffffffu, 0xffffffffu, 0u, 0u);
         if (lane < FILL_GROUP && a0 + lane < n_alpha && first_alpha + a0 + lane < b.mask_capacity)
             at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a0 + lane]));
-        const bool visible = (at.x & 0x7fffffffu) < b.tile_count;  // else: fills that the clip made invisible, no mask
+        uint32_t fbt = 0xffffffffu;
+        if (b.cull_fill && lane < FILL_GROUP && a0 + lane < n_alpha) fbt = __ldg(&b.alpha_map[a0 + lane]);
+        bool visible = (at.x & 0x7fffffffu) < b.tile_count;  // else: fills that the clip made invisible, no mask
+        // a mask under an opaque whole-tile layer of a later path is never read (the list scatter leaves its tile out,
+        // sort.comp:62): do not rasterize it. The z-buffer is final: propagate has finished.
+        if (fbt != 0xffffffffu && (int)(at.x & 0x7fffffffu) < b.fb[fbt].z) {
+            visible = false;
+            at.x = 0x7fffffffu;
+        }
         const uint32_t begin = min(at.z, b.fill_capacity);
         const uint32_t count = visible ? min(at.w >> 8, b.fill_capacity - begin) : 0u;
         // the fills of the group as one sequence: tile g owns [pre_g, pre_g + count_g)
@@ -301,6 +328,12 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
             reinterpret_cast<uint2 *>(b.masks + (size_t)(first_alpha + a0 + g) * 256)[lane] = m;
         }
         __syncwarp();
+#if FILL_DYNAMIC
+        a0 = (n_warps + __shfl_sync(0xffffffffu, next_ticket, 0)) * FILL_GROUP;
+        if (lane == 0 && a0 < n_alpha) next_ticket = atomicAdd(&b.counters->fill_ticket, 1u);
+#else
+        a0 += n_warps * FILL_GROUP;
+#endif
     }
 }
 

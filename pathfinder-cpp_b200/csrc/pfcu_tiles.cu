@@ -321,6 +321,7 @@ __device__ __forceinline__ void resolve_tile(const BatchView &b, const ColumnInf
         }
     }
     // alpha tile allocation (propagate.comp:178-183): the slot was fixed by the scan over tiles with fills
+    uint32_t own_slot = 0xffffffffu;
     if (have_mask) {
         const uint32_t local = b.alpha_rank[ti];
         const uint32_t id = first_alpha + local;
@@ -330,6 +331,7 @@ __device__ __forceinline__ void resolve_tile(const BatchView &b, const ColumnInf
             *reinterpret_cast<uint4 *>(&b.alpha_tiles[local]) =
                 make_uint4((need_new ? ti : 0x7fffffffu) | ((ci.ctrl & 0x1) ? 0x80000000u : 0u), (uint32_t)clip_alpha,
                            b.fill_begin[ti], ((uint32_t)backdrop & 0xffu) | (fill_count << 8));
+            own_slot = local;
             if (need_new) alpha = (int)id;
         } else {
             need_new = false;  // the scan flagged OVF_ALPHA: the frame is replayed with more slots
@@ -338,6 +340,7 @@ __device__ __forceinline__ void resolve_tile(const BatchView &b, const ColumnInf
     const int fx = gx - b.fb_tx0, fy = gy - b.fb_ty0;  // framebuffer tile
     const bool in_fb = fx >= 0 && fx < b.fb_tw && fy >= 0 && fy < b.fb_th;
     const uint32_t map = in_fb ? (uint32_t)fy * (uint32_t)b.fb_tw + (uint32_t)fx : 0u;
+    if (own_slot != 0xffffffffu) b.alpha_map[own_slot] = in_fb ? map : 0xffffffffu;  // for fill's z-cull
     const bool listed = (backdrop != 0 || alpha >= 0) && in_fb;
     const uint32_t packed = ((uint32_t)backdrop & 0xffu) | (((uint32_t)delta & 0xffu) << 8) |
                             (((uint32_t)backdrop9 & 0xffu) << 16) | (listed ? 1u << 24 : 0u) |

@@ -143,6 +143,8 @@ class Renderer:
         self._descs = None
         if area_lut is not None:
             self.set_area_lut(area_lut)
+        if os.environ.get("PFCU_EXP_FILL_CULLED"):  # kernel experiments: rasterize z-culled masks too
+            self.set_fill_culled_tiles(True)
 
     def close(self):
         if getattr(self, "h", None):
@@ -237,6 +239,10 @@ class Renderer:
     def set_retain_frame_graph(self, enabled):
         """PFCU_OPT_RETAIN_FRAME_GRAPH (default on): identical consecutive frames become one graph launch."""
         _check(self.L.pfcu_set_option(self.h, 0, int(bool(enabled))))
+
+    def set_fill_culled_tiles(self, enabled):
+        """PFCU_OPT_FILL_CULLED_TILES (default off): rasterize the masks of z-culled tiles too, like fill.comp."""
+        _check(self.L.pfcu_set_option(self.h, 1, int(bool(enabled))))
 
     def set_profiling(self, enabled):
         _check(self.L.pfcu_set_profiling(self.h, int(bool(enabled))))

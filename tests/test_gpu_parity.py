@@ -109,18 +109,32 @@ def test_pixels_within_tolerance_of_oracle(renderer, area_lut, name):
 def test_masks_match_oracle(renderer, area_lut):
     """fill stage alone: every sampled 16 x 16 coverage mask within 1/255 of fill.comp's restatement."""
     scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
-    renderer.set_scene(scene)
-    renderer.draw(clear=True)
     fr, _ = oracle_frame(scene, area_lut)
     bid = int(scene["draw_batches"][0]["info"][0])
-    to, tc = fr.tiles(fr.slots[bid]), renderer.tiles(bid)
+    to = fr.tiles(fr.slots[bid])
     own = np.nonzero((to["alpha_tile_id"] >= 0) & (to["fill_count"] > 0))[0]
-    worst = 0
-    for i in own[:: max(1, len(own) // 400)]:
-        a = fr.mask(int(to["alpha_tile_id"][i])).astype(int)
-        b = renderer.mask(int(tc["alpha_tile_id"][i])).astype(int)
-        worst = max(worst, np.abs(a - b).max())
-    assert worst <= 1
+    try:
+        # every mask, as fill.comp rasterizes them; then the default: masks of z-culled tiles are skipped, so only tiles
+        # that made it into the sorted lists are compared (and some tile must actually have been culled)
+        for fill_culled in (True, False):
+            renderer.set_fill_culled_tiles(fill_culled)
+            renderer.set_scene(scene)
+            renderer.draw(clear=True)
+            tc = renderer.tiles(bid)
+            sel = own
+            if not fill_culled:
+                kept = np.zeros(len(tc), bool)
+                kept[renderer.tile_lists(bid)[1]] = True
+                assert (~kept[own]).any()
+                sel = own[kept[own]]
+            worst = 0
+            for i in sel[:: max(1, len(sel) // 400)]:
+                a = fr.mask(int(to["alpha_tile_id"][i])).astype(int)
+                b = renderer.mask(int(tc["alpha_tile_id"][i])).astype(int)
+                worst = max(worst, np.abs(a - b).max())
+            assert worst <= 1
+    finally:
+        renderer.set_fill_culled_tiles(False)
     fr.close()
 
 
