@@ -106,6 +106,7 @@ struct BatchSlot {
     uint32_t line_cap = 0, fill_cap = 0, staging_cap = 0;
     BatchView view{};
     bool prepared = false;
+    bool heavy_paints = false;  // a path of the batch paints with a blur filter (tile.comp:354-392)
     cudaEvent_t fill_done = nullptr;  // recorded on the aux stream after this batch's fill kernel
 };
 
@@ -495,6 +496,8 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
         sig_mix(c, &clear, sizeof(clear));
         sig_mix(c, cmd.clear_color, sizeof(cmd.clear_color));
         sig_mix(c, &origin, sizeof(origin));
+        const int heavy = s.heavy_paints;
+        sig_mix(c, &heavy, sizeof(heavy));
     }
     if (c->dry) return PFCU_OK;
     {
@@ -506,7 +509,7 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
         if (c->aux_pending == s.fill_done) c->aux_pending = nullptr;
         s.fill_done = nullptr;
     }
-    LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, cmd.target_page < 0, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, cmd.target_page < 0, s.heavy_paints, c->stream));
     c->launches += 1;
     c->in_flight = true;
     return PFCU_OK;
@@ -881,6 +884,17 @@ int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
         memcpy(hm + s.off_meta, d->propagate_metadata, (size_t)d->path_count * sizeof(pfcu_propagate_metadata));
         memcpy(hm + s.off_dice, d->dice_metadata, (size_t)d->path_count * sizeof(pfcu_dice_metadata));
         memcpy(hm + s.off_tpi, d->tile_path_info, (size_t)d->path_count * sizeof(pfcu_tile_path_info));
+    }
+    s.heavy_paints = false;
+    if (!c->all_solid && c->stage_metadata.p) {
+        const Paint *table = static_cast<const Paint *>(c->stage_metadata.p);
+        for (uint32_t i = 0; i < d->path_count && !s.heavy_paints; i++) {
+            const uint32_t paint = d->tile_path_info[i].color;
+            if (paint < c->n_paints) {
+                const int ctrl = table[paint].ctrl;
+                s.heavy_paints = ((ctrl >> 8) & 0x3) != 0 && ((ctrl >> 4) & 0xf) == 0x3;
+            }
+        }
     }
     s.desc.backdrops = nullptr;  // the caller's vectors are not retained
     s.desc.propagate_metadata = nullptr;

@@ -174,7 +174,7 @@ cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s);
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s);
 // origin != 0: the target is the destination framebuffer, whose tile (0, 0) is scene tile (fb_tx0, fb_ty0)
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
-                             const float clear_color[4], int origin, cudaStream_t s);
+                             const float clear_color[4], int origin, int heavy_paints, cudaStream_t s);
 
 int sm_count();
 

@@ -23,9 +23,13 @@ namespace pfcu {
 
 __device__ __forceinline__ float4 ld_rgba8(const uint8_t *px, int w, int x, int y) {
     const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(px) + (size_t)y * w + x);
-    const float k = 1.0f / 255.0f;
-    return make_float4((float)(v & 0xffu) * k, (float)((v >> 8) & 0xffu) * k, (float)((v >> 16) & 0xffu) * k,
-                       (float)(v >> 24) * k);
+    // float(byte) without the conversion pipe (a quarter-rate I2F per channel is what a blur tap would spend most of its
+    // time on): the byte lands in the mantissa of 2^23 and the subtraction is exact, so the value is the same
+    const float k = 1.0f / 255.0f, m = 8388608.0f;
+    return make_float4((__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7540)) - m) * k,
+                       (__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7541)) - m) * k,
+                       (__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7542)) - m) * k,
+                       (__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7543)) - m) * k);
 }
 
 __device__ __forceinline__ int wrap_or_clamp(int i, int n, bool repeat) {
@@ -128,17 +132,19 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
     __shared__ FillShared sh;
     pdl_wait();
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-#if FILL_PERMUTE
-    // consecutive groups go to consecutive CTAs (different SMs): the groups of one path -- similar fill counts -- are
-    // spread over the whole GPU instead of landing on the 8 warps of one CTA
-    const uint32_t warp = wib * gridDim.x + blockIdx.x;
-#else
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-#endif
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t first_alpha = b.counters->first_alpha;
     uint32_t n_alpha = b.counters->n_alpha;
     if (n_alpha > b.alpha_capacity) n_alpha = b.alpha_capacity;
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#if FILL_PERMUTE
+    // With work for every warp, consecutive groups go to consecutive CTAs (different SMs): the groups of one path --
+    // similar fill counts -- are spread over the whole GPU instead of landing on the 8 warps of one CTA (tiger 4096^2:
+    // SM-active time 21k .. 42k cycles before). A small frame keeps the CTA-major order, so that most CTAs of the
+    // (one-wave) grid exit at once and leave their SMs to the other frames in flight (batch of 512^2 frames: 74k vs
+    // 64k frames/s).
+    if (n_alpha >= n_warps * FILL_GROUP) warp = wib * gridDim.x + blockIdx.x;
+#endif
     int *const acc = &sh.acc[wib][0][0];
     for (int i = (int)lane; i < FILL_GROUP * FILL_ACC; i += 32) acc[i] = 0;
     __syncwarp();
@@ -564,7 +570,8 @@ constexpr int CT_PRIMS = 256;          // list entries staged at a time (more: t
 enum LayerFlags : uint32_t {
     LF_TEXTURED = 1,  // the paint is not a plain colour (gradient, image, blur, blend mode): per-pixel shading
     LF_MASKED = 2,    // coverage comes from a mask
-    LF_SKIP = 4       // solid tile of an even-odd path with an even backdrop: invisible (tile.comp:786-792)
+    LF_SKIP = 4,      // solid tile of an even-odd path with an even backdrop: invisible (tile.comp:786-792)
+    LF_HEAVY = 8      // blur filter: thousands of instructions per pixel -- the tile is split over the CTA's warps
 };
 
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
@@ -671,7 +678,7 @@ struct __align__(16) CompositeShared {
     uint32_t start_layer[CT_TILES]; // first layer that needs per-pixel work
     uint32_t packed_color[CT_TILES];
     uint32_t txy[CT_TILES];         // tile x | tile y << 16
-    uint8_t work[CT_TILES];         // tiles with per-pixel work
+    uint16_t work[CT_TILES * 4];    // per-pixel work items: tile | pixel pairs (bit j = pair j of every lane) << 8
     uint32_t n_work, next, flat_mask;
 };
 
@@ -686,7 +693,7 @@ struct TileGeom {
 template <bool SOLID>
 __device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 q, const float4 base, const BatchView &b,
                                             const PaintView &p, const ColorSampler &cs, const TileGeom &g,
-                                            const TargetView &tg, unsigned lane) {
+                                            const TargetView &tg, unsigned lane, uint32_t pairs = 0xfu) {
     const uint32_t fl = q.w;
     if (fl & LF_SKIP) return;
     const bool masked = (fl & LF_MASKED) != 0, textured = !SOLID && (fl & LF_TEXTURED) != 0;
@@ -717,6 +724,7 @@ __device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 q, const
         pc.ctrl = __ldg(&p.paints[color_entry].ctrl);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+            if (!((pairs >> j) & 1u)) continue;  // (a tile split over several warps: the other pairs are theirs)
             const float2 cov = mask_pair(mask8, j, even_odd);
             const float fy = g.fragy + (float)(j >> 1), fx = g.fragx + (float)((j & 1) * 2);
             const float4 s0 = shade<false>(pc, cs, fx, fy, cov.x, (float)tg.width, (float)tg.height);
@@ -728,12 +736,19 @@ __device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 q, const
 }
 
 template <bool SOLID>
-__device__ __forceinline__ void store_block(const PixelBlock &px, const TileGeom &g, const TargetView &tg) {
+__device__ __forceinline__ void store_block(const PixelBlock &px, const TileGeom &g, const TargetView &tg,
+                                            uint32_t pairs = 0xfu) {
 #pragma unroll
     for (int r = 0; r < 2; r++) {
         const uint4 v = px.pack_row<!SOLID>(r);
         uint8_t *dst = g.px0 + (size_t)r * tg.pitch;
-        if (g.interior) {
+        if (!SOLID && pairs != 0xfu) {  // this warp owns some of the lane's pixel pairs only
+            const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (((pairs >> (r * 2 + (i >> 1))) & 1u) && g.gx0 + i < tg.width && g.gy0 + r < tg.height)
+                    reinterpret_cast<uint32_t *>(dst)[i] = wd[i];
+        } else if (g.interior) {
             *reinterpret_cast<uint4 *>(dst) = v;
         } else if (g.gy0 + r < tg.height) {
             const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
@@ -772,25 +787,27 @@ __device__ __forceinline__ uint32_t layer_flags(const uint4 q, uint32_t mask_cap
 // compacts the others into a work list for a warp-per-tile blend kernel (21 + 24 us vs 33 us for this kernel alone).
 template <bool SOLID>
 __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_TEX) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
-                                                                      float4 clear_color, int origin) {
+                                                                      float4 clear_color, int origin, uint32_t tiles_per_cta,
+                                                                      uint32_t sub_tw, uint32_t sub_n) {
     __shared__ CompositeShared sh;
     pdl_wait();
     const unsigned tid = threadIdx.x, lane = tid & 31;
-    const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
-    const uint32_t map0 = blockIdx.x * CT_TILES;
-    const uint32_t n_tiles = min((uint32_t)CT_TILES, n_fb - map0);
+    // the CTA's tiles: tiles_per_cta consecutive tiles of the sub_tw-wide rectangle of the tile grid that the target
+    // covers (the whole grid for the destination; a render-target page is smaller than the scene's grid)
+    const uint32_t map0 = blockIdx.x * tiles_per_cta;
+    const uint32_t n_tiles = min(tiles_per_cta, sub_n - map0);
 
     // ---- stage 1: list headers
     if (tid < CT_TILES) {
         uint4 f = make_uint4(0u, 0u, 0u, 0u);
         uint32_t xy = 0;
         if (tid < n_tiles) {
-            f = __ldg(reinterpret_cast<const uint4 *>(&b.fb[map0 + tid]));
+            const uint32_t at = map0 + tid, ty = at / sub_tw, tx = at - ty * sub_tw;
+            f = __ldg(reinterpret_cast<const uint4 *>(&b.fb[ty * (uint32_t)b.fb_tw + tx]));
             if (f.x > b.prim_capacity) f.x = b.prim_capacity;
             if (f.x + f.y > b.prim_capacity) f.y = b.prim_capacity - f.x;
             f.w = min(f.w, f.y);  // entries the scatter wrote (it leaves out what the z-buffer culls)
-            const uint32_t map = map0 + tid, ty = map / (uint32_t)b.fb_tw;
-            xy = (map - ty * (uint32_t)b.fb_tw) | (ty << 16);
+            xy = tx | (ty << 16);
         }
         sh.fb[tid] = f;
         sh.txy[tid] = xy;
@@ -908,7 +925,11 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                     float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (ce < p.n_paints) {
                         base = __ldg(&p.paints[ce].base);
-                        if (!SOLID && __ldg(&p.paints[ce].ctrl) != 0) q.w |= LF_TEXTURED;
+                        if (!SOLID) {
+                            const int ctrl = __ldg(&p.paints[ce].ctrl);
+                            if (ctrl != 0) q.w |= LF_TEXTURED;
+                            if (((ctrl >> 8) & 0x3) != 0 && ((ctrl >> 4) & 0xf) == 0x3) q.w |= LF_HEAVY;
+                        }
                     }
                     if (q.w & LF_MASKED) {
                         prefetch_l1(b.masks + (size_t)q.y * 256);
@@ -947,7 +968,15 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 } else if (is_work) {
                     sh.start_color[t] = dest;
                     sh.start_layer[t] = i;
-                    sh.work[atomicAdd(&sh.n_work, 1u)] = (uint8_t)t;
+                    bool heavy = false;
+                    if (!SOLID)
+                        for (uint32_t k = clear ? i : 0u; k < n; k++) heavy = heavy || (sh.sorted[off + k].w & LF_HEAVY) != 0;
+                    if (heavy) {  // four work items, one pixel pair of every lane each
+                        const uint32_t at = atomicAdd(&sh.n_work, 4u);
+                        for (uint32_t k = 0; k < 4; k++) sh.work[at + k] = (uint16_t)(t | ((1u << k) << 8));
+                    } else {
+                        sh.work[atomicAdd(&sh.n_work, 1u)] = (uint16_t)(t | (0xfu << 8));
+                    }
                 }
             }
         }
@@ -987,7 +1016,8 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 if (lane == 0) wi = atomicAdd(&sh.next, 1u);
                 wi = __shfl_sync(0xffffffffu, wi, 0);
                 if (wi >= n_work) break;
-                const uint32_t t = sh.work[wi], xy = sh.txy[t];
+                const uint32_t item = sh.work[wi], t = item & 0xffu, xy = sh.txy[t];
+                const uint32_t pairs = SOLID ? 0xfu : item >> 8;
                 const uint4 hdr = sh.fb[t];
                 const uint32_t n = hdr.w, off = hdr.x - range0;
                 TileGeom g;
@@ -1006,8 +1036,8 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 } else {
                     load_block(px, g, tg);
                 }
-                for (; i < n; i++) blend_layer<SOLID>(px, sh.sorted[off + i], sh.color[off + i], b, p, cs, g, tg, lane);
-                store_block<SOLID>(px, g, tg);
+                for (; i < n; i++) blend_layer<SOLID>(px, sh.sorted[off + i], sh.color[off + i], b, p, cs, g, tg, lane, pairs);
+                store_block<SOLID>(px, g, tg, pairs);
             }
         }
         tb = te;
@@ -1016,17 +1046,32 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
 }
 
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
-                             const float clear_color[4], int origin, cudaStream_t s) {
+                             const float clear_color[4], int origin, int heavy_paints, cudaStream_t s) {
     if (b.fb_tw <= 0 || b.fb_th <= 0) return cudaSuccess;
-    const uint32_t n_fb = (uint32_t)(b.fb_tw * b.fb_th);
-    const unsigned grid = (n_fb + CT_TILES - 1) / CT_TILES;
+    // tiles of the scene's grid that the target covers (its top-left corner is the grid's: pages have no origin)
+    const uint32_t sub_tw = (uint32_t)min(b.fb_tw, (t.width + TILE - 1) / TILE);
+    const uint32_t sub_th = (uint32_t)min(b.fb_th, (t.height + TILE - 1) / TILE);
+    const uint32_t n_fb = sub_tw * sub_th;
+    if (!n_fb) return cudaSuccess;
+    unsigned grid = (n_fb + CT_TILES - 1) / CT_TILES;
     const float4 cc = make_float4(clear_color[0], clear_color[1], clear_color[2], clear_color[3]);
     // the plain-colour instantiation skips the saturation before the RGBA8 conversion: src-over of premultiplied colours
     // in [0, 1] stays in [0, 1]
     bool unit = p.all_solid && p.unit_range;
     for (int i = 0; i < 4; i++) unit = unit && clear_color[i] >= 0.0f && clear_color[i] <= 1.0f;
-    if (unit) return launch_pdl(k_composite<true>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin);
-    return launch_pdl(k_composite<false>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin);
+    if (unit) return launch_pdl(k_composite<true>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin, (uint32_t)CT_TILES, sub_tw, n_fb);
+    // Textured passes on small targets (the blur passes of a shadow run on a render target of a few hundred tiles, and
+    // a blurred pixel costs thousands of instructions): fewer tiles per CTA, so that the pass covers every SM instead of
+    // n_fb / 16 of them
+    uint32_t tpc = CT_TILES;
+    const uint32_t wave = (uint32_t)sm_count() * CT_MIN_CTAS_TEX * 2;
+    if (n_fb < wave * CT_TILES) tpc = (n_fb + wave - 1) / wave;
+    // a batch that paints with a blur filter: its blurred tiles sit side by side (the shadow's rectangle) -- one tile per
+    // CTA, so that the hardware spreads them over all SMs (each is split over the CTA's four warps)
+    if (heavy_paints) tpc = 1;
+    if (tpc < 1) tpc = 1;
+    grid = (n_fb + tpc - 1) / tpc;
+    return launch_pdl(k_composite<false>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin, tpc, sub_tw, n_fb);
 }
 
 }  // namespace pfcu
