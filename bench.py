@@ -461,37 +461,63 @@ def run_strips(args, rank, world):
     # every on-curve point starts one segment (SegmentsD3D11::add_path closes each contour, gpu_data.cpp:109)
     segs_total = int(sum(int((c[1] == 0).sum()) for p_ in paths for c in p_["contours"]))
     lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
-    stream = torch.cuda.Stream()
     dev = torch.device("cuda", local)
-    peer = None
-    if args.gather == "p2p" and world > 1:
-        peer = sharding.PeerFramebuffer(size, size, world, rank, dev)
-        target_ptr, full = peer.strip_ptr(), None
-    else:
-        full = torch.zeros((rows * world, size, 4), dtype=torch.uint8, device=dev)
-        target_ptr = full[rank * rows:].data_ptr()
-    r = pfcu.Renderer(local, lut)
-    r.set_stream(stream.cuda_stream)
-    r.set_scene(scene, target_ptr, size * 4)
-    first = r.draw(clear=True)
-    steady = r.draw(clear=True)
-    assert steady["retries"] == 0, steady
-    r.set_profiling(True)
-    r.draw(clear=True)
-    stage_ms = r.stage_times()
-    r.set_profiling(False)
-    r.draw(clear=True)
-    r.graph_capture()
+    # frames in flight (p2p gather only): frame k + 1 is computed while frame k's strips are still arriving at rank 0
+    # (7/8 of the canvas through one GPU's NVLink ingress); every frame in flight has its own context, stream and
+    # presenting framebuffer
+    n_fly = max(1, args.strip_frames_in_flight) if (args.gather == "p2p" and world > 1) else 1
+    lanes = []
+    full = None
+    for k in range(n_fly):
+        stream = torch.cuda.Stream()
+        peer = None
+        if args.gather == "p2p" and world > 1:
+            peer = sharding.PeerFramebuffer(size, size, world, rank, dev)
+            target_ptr = peer.strip_ptr()
+        else:
+            full = torch.zeros((rows * world, size, 4), dtype=torch.uint8, device=dev)
+            target_ptr = full[rank * rows:].data_ptr()
+        r = pfcu.Renderer(local, lut)
+        r.set_stream(stream.cuda_stream)
+        r.set_scene(scene, target_ptr, size * 4)
+        first = r.draw(clear=True)
+        steady = r.draw(clear=True)
+        assert steady["retries"] == 0, steady
+        if k == 0:
+            r.set_profiling(True)
+            r.draw(clear=True)
+            stage_ms = r.stage_times()
+            r.set_profiling(False)
+            r.draw(clear=True)
+        r.graph_capture()
+        lanes.append((r, stream, peer))
+    r, stream, peer = lanes[0]
+    main = torch.cuda.Stream()
+    counter = [0]
 
     def step():
-        r.graph_launch()
+        q, qs, qp = lanes[counter[0] % n_fly]
+        counter[0] += 1
+        q.graph_launch()
         if world > 1:
-            if peer is not None:
-                with torch.cuda.stream(stream):
-                    peer.barrier()
+            if qp is not None:
+                with torch.cuda.stream(qs):
+                    qp.barrier()
             else:
-                with torch.cuda.stream(stream):
+                with torch.cuda.stream(qs):
                     dist.all_gather_into_tensor(full.view(-1), full[rank * rows:(rank + 1) * rows].view(-1))
+
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(main)
+        for _, qs, _ in lanes:
+            qs.wait_event(ev)
+
+    def join():
+        for _, qs, _ in lanes:
+            ev = torch.cuda.Event()
+            ev.record(qs)
+            main.wait_event(ev)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -502,16 +528,19 @@ def run_strips(args, rank, world):
     sampler = ClockSampler(local)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    e0.record(main)
+    fork()
     for _ in range(args.steps):
         step()
-    e1.record(stream)
+    join()
+    e1.record(main)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    gstats = r.graph_finish()
+    for q, _, _ in lanes:
+        gstats = q.graph_finish()
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
     units = torch.tensor([gstats[k] for k in ("segments", "lines", "fills", "alpha_tiles", "dense_tiles")],
                          device="cuda", dtype=torch.float64)
@@ -529,13 +558,15 @@ def run_strips(args, rank, world):
                        "gather": ("tile-kernel stores into rank 0's framebuffer over NVLink (peer mapping) + barrier"
                                   if peer is not None else "one NCCL all-gather of %d-row blocks" % rows) if world > 1 else "none",
                        "l2": "framebuffer (%d MiB) larger than L2" % (size * size * 4 >> 20),
+                       "frames_in_flight": n_fly,
                        "units_all_ranks": dict(zip(("segments", "lines", "fills", "alpha_tiles", "dense_tiles"),
                                                    (int(x) for x in units.tolist()))),
                        "rank0_stage_ms": stage_ms, "frame_ms_per_rank0": first["gpu_ms"]},
             "gpu_launches": int(gstats["kernel_launches"]) * args.steps, "clocks": clocks,
         }
         print(json.dumps(line))
-    r.close()
+    for q, _, _ in lanes:
+        q.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -631,6 +662,7 @@ def main():
     ap.add_argument("--gather", default="nccl", choices=["nccl", "p2p"], help="--workload synthetic: strip assembly")
     ap.add_argument("--frames", type=int, default=0, help="batch mode: render this many independent frames per step")
     ap.add_argument("--contexts", type=int, default=16, help="batch mode: renderer contexts (streams) per GPU")
+    ap.add_argument("--strip-frames-in-flight", type=int, default=2, help="--workload synthetic --gather p2p: frames in flight")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="value leg: contexts replaying their frame graph side by side")
     ap.add_argument("--e2e-contexts", type=int, default=4, help="e2e leg: frames in flight (1 = blocking pfcu_end_frame)")
     args = ap.parse_args()

@@ -17,6 +17,8 @@
 //          registers with packed f32x2 arithmetic and stores 16 bytes per lane and row.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "pfcu_device.h"
 
 namespace pfcu {
@@ -1059,7 +1061,17 @@ cudaError_t launch_composite(const BatchView &b, const PaintView &p, const Targe
     // in [0, 1] stays in [0, 1]
     bool unit = p.all_solid && p.unit_range;
     for (int i = 0; i < 4; i++) unit = unit && clear_color[i] >= 0.0f && clear_color[i] <= 1.0f;
-    if (unit) return launch_pdl(k_composite<true>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin, (uint32_t)CT_TILES, sub_tw, n_fb);
+    if (unit) {
+        static int exp_tpc = -1;  // kernel experiments: PFCU_EXP_TPC = tiles per CTA of the plain-colour instantiation
+        if (exp_tpc < 0) {
+            const char *e = getenv("PFCU_EXP_TPC");
+            exp_tpc = e ? atoi(e) : 0;
+            if (exp_tpc < 0 || exp_tpc > CT_TILES) exp_tpc = 0;
+        }
+        const uint32_t tpc_solid = exp_tpc ? (uint32_t)exp_tpc : (uint32_t)CT_TILES;
+        grid = (n_fb + tpc_solid - 1) / tpc_solid;
+        return launch_pdl(k_composite<true>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin, tpc_solid, sub_tw, n_fb);
+    }
     // Textured passes on small targets (the blur passes of a shadow run on a render target of a few hundred tiles, and
     // a blurred pixel costs thousands of instructions): fewer tiles per CTA, so that the pass covers every SM instead of
     // n_fb / 16 of them
