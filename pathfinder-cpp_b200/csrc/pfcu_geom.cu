@@ -143,6 +143,9 @@ constexpr int DICE_CHUNK = 32;    // fewest segments a CTA takes at a time (laun
 // back to a private stack --, O = lines collected between flushes): few segments with deep trees (an SVG at 4096^2)
 // take <1024, 1024>, 98 KB, 2 CTAs per SM; many segments with shallow trees (text density) take <512, 512>, 50 KB,
 // 4 CTAs per SM, so that twice as many chunks overlap their barriers and dependent loads.
+#ifndef DICE_INTERLEAVE
+#define DICE_INTERLEAVE 1
+#endif
 constexpr int DICE_PATHS = 512;   // dice metadata entries staged per chunk (more: the search stays in global memory)
 
 template <int Q, int O>
@@ -383,8 +386,19 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chu
     const unsigned lane = threadIdx.x & 31;
     for (uint32_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
         // ---- which paths own this chunk's segments: warps 0 and 1 search, everybody stages that slice of the metadata
+        // A batch whose whole path table fits the staging buffer deals its segments to the chunks round-robin (segment
+        // s -> chunk s mod n_chunks): the segments of one path -- similar sizes, so similar subdivision depths -- spread
+        // over all CTAs instead of making one CTA walk 32 deep trees (tiger 4096^2: SM-active time 22 k cycles on average,
+        // 35 k on the slowest SM with contiguous chunks). Larger batches (text-density scenes: uniform small paths) keep
+        // contiguous chunks and stage only the paths of their range.
+        const bool interleave = DICE_INTERLEAVE && b.path_count <= (uint32_t)DICE_PATHS && n_chunks > 1;
         const uint32_t seg0 = chunk * chunk_size, seg1 = min(seg0 + chunk_size, b.segment_count) - 1;
-        if (threadIdx.x < 64) {
+        if (interleave) {
+            if (threadIdx.x == 0) {
+                sh.path_lo = 0;
+                sh.path_hi = b.path_count - 1;
+            }
+        } else if (threadIdx.x < 64) {
             const uint32_t p = warp_find_path(b.dice, b.path_count, threadIdx.x < 32 ? seg0 : seg1, lane);
             if (lane == 0) (threadIdx.x < 32 ? sh.path_lo : sh.path_hi) = p;
         }
@@ -399,7 +413,7 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chu
         __syncthreads();
         // ---- roots: one thread per segment of the chunk (chunk_size is a multiple of 32: whole warps)
         if (threadIdx.x < chunk_size) {
-            const uint32_t s = chunk * chunk_size + threadIdx.x;
+            const uint32_t s = interleave ? threadIdx.x * n_chunks + chunk : chunk * chunk_size + threadIdx.x;
             bool root_line = false, root_curve = false, root_cubic = false;
             Cubic root = {};
             uint32_t root_path = 0;

@@ -354,6 +354,9 @@ __device__ __forceinline__ void resolve_tile(const BatchView &b, const ColumnInf
     if (listed) atomicAdd(&b.fb[map].count, 1u);
 }
 
+#ifndef PROPAGATE_PERMUTE
+#define PROPAGATE_PERMUTE 0  // measured: no change on tiger 4096^2 (16.4 us either way)
+#endif
 #ifndef PROPAGATE_SHORT_N
 #define PROPAGATE_SHORT_N 4
 #endif
@@ -369,7 +372,13 @@ constexpr int PROPAGATE_SHORT = PROPAGATE_SHORT_N;  // columns of up to this man
 //     the group find their column short and leave.
 __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
     pdl_wait();
-    const uint32_t wcol = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // this warp's column
+    // this warp's column: consecutive columns go to consecutive CTAs, so that the tall columns of one large path (tiger
+    // 4096^2: 256 columns of 256 tiles under the background) spread over all SMs instead of sitting four to a CTA
+#if PROPAGATE_PERMUTE
+    const uint32_t wcol = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+#else
+    const uint32_t wcol = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#endif
     const unsigned lane = threadIdx.x & 31;
     if (wcol >= b.column_count) return;
     const uint32_t first_alpha = b.counters->first_alpha;
