@@ -664,7 +664,7 @@ def main():
     ap.add_argument("--contexts", type=int, default=16, help="batch mode: renderer contexts (streams) per GPU")
     ap.add_argument("--strip-frames-in-flight", type=int, default=2, help="--workload synthetic --gather p2p: frames in flight")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="value leg: contexts replaying their frame graph side by side")
-    ap.add_argument("--e2e-contexts", type=int, default=4, help="e2e leg: frames in flight (1 = blocking pfcu_end_frame)")
+    ap.add_argument("--e2e-contexts", type=int, default=6, help="e2e leg: frames in flight (1 = blocking pfcu_end_frame)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -30,8 +30,7 @@ struct BatchCounters {
     uint32_t scan_ticket[2];  // dynamic tile ids for the two look-back scans
     uint32_t n_list_entries;  // total list entries (from the scan over framebuffer tiles)
     uint32_t n_long;          // lines queued for the long-line bin kernel
-    uint32_t fill_ticket;     // next group of alpha tiles to rasterize (fill takes its work dynamically)
-    uint32_t pad[5];
+    uint32_t pad[6];
 };
 static_assert(sizeof(BatchCounters) == 64, "BatchCounters");
 

@@ -96,9 +96,6 @@ __device__ __forceinline__ uint32_t warp_incl_scan_u32(uint32_t v, unsigned lane
 __device__ __forceinline__ uint32_t unorm8_bits(float v) { return __float_as_uint(fmaf(v, 255.0f, 12582912.0f)); }
 
 constexpr int FILL_WARPS = 8;
-#ifndef FILL_DYNAMIC
-#define FILL_DYNAMIC 0
-#endif
 #ifndef FILL_PERMUTE
 #define FILL_PERMUTE 1
 #endif
@@ -153,13 +150,9 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
     const bool band = p.lut_band != 0;
     const int k_own = (int)(lane & 3u), s_own = (int)(lane >> 2);
 
-    // Groups are handed out dynamically: fills per group vary from 0 to 60+ (tiger 4096^2: mean 13), and with a fixed
-    // stride the slowest warp gets 3.2 x the mean. The first group of a warp is its own index (no atomic on the way in);
-    // the ticket for the next one is taken before the current one is rasterized, so its latency is hidden.
-    uint32_t a0 = warp * FILL_GROUP, next_ticket = 0;
-#if FILL_DYNAMIC
-    if (lane == 0) next_ticket = atomicAdd(&b.counters->fill_ticket, 1u);
-#endif
+    // (Handing the groups out through a global ticket counter instead -- one atomic per group, next ticket prefetched --
+    // measured slower: 28.7 us against 24.6 us on tiger 4096^2, profiles/r01_tile_kernel_experiments.md.)
+    uint32_t a0 = warp * FILL_GROUP;
     for (; a0 < n_alpha;) {
         // ---- the group's alpha tile records, one per lane: tile | winding << 31, clip mask slot, first fill,
         // backdrop | fill count << 8
@@ -336,12 +329,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
             reinterpret_cast<uint2 *>(b.masks + (size_t)(first_alpha + a0 + g) * 256)[lane] = m;
         }
         __syncwarp();
-#if FILL_DYNAMIC
-        a0 = (n_warps + __shfl_sync(0xffffffffu, next_ticket, 0)) * FILL_GROUP;
-        if (lane == 0 && a0 < n_alpha) next_ticket = atomicAdd(&b.counters->fill_ticket, 1u);
-#else
         a0 += n_warps * FILL_GROUP;
-#endif
     }
 }
 
