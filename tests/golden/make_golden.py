@@ -9,6 +9,9 @@ into oracle/_ref/libpfref.so; this script drives it through oracle/pfref.py and 
                           in the order- and id-independent canonical form of tests/scenes.py
   area_lut.npz  the 256 x 256 RGBA8 area LUT as decoded by the reference (core/renderer.cpp:17-21)
   digests.json  sha256 of the canonical outputs of the configurations too large to commit (tiger 4096)
+  shader_frames.npz  RGBA8 frames of the 512^2 fixtures as the reference's OWN compute shaders render them: fill.comp and
+                tile.comp, read where they lie, compiled by g++ through oracle/ref_harness/glsl_shim.h and run on the CPU
+                (oracle/_ref/libpfshader.so, oracle/pfshader.py)
 
 Usage: python tests/golden/make_golden.py
 """
@@ -44,6 +47,10 @@ DEMO_SCENES = {
     "demo_full_512": (512, 1.0, 0x3f),
     "demo_full_2048": (2048, 2048 / 720.0, 0x3f),  # BASELINE.json configs[1], demo-primitives half
 }
+
+
+# scenes whose frame, rendered by the reference's own fill.comp + tile.comp on the CPU, is committed (shader_frames.npz)
+SHADER_FRAMES = ["tiger_512", "demo_clip_512", "demo_full_512"]
 
 
 def canonical_extra(ref):
@@ -100,6 +107,22 @@ def main():
         s.close()
         print(name, digests[name])
     np.savez_compressed(os.path.join(HERE, "area_lut.npz"), lut=lut)
+    # The pixel half: the reference's OWN compute shaders (fill.comp, tile.comp) run on the CPU through
+    # oracle/_ref/libpfshader.so on the (pinned) geometry of every 512^2 fixture: what the GPU-driven mode renders
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "shaders", "port"])
+    import pforacle
+    import pfshader
+    frames = {}
+    for name in SHADER_FRAMES:
+        scene, _ = scenes.load_scene(scenes.golden_path(name))
+        fr = pforacle.Frame(scene, lut)
+        fr.render()
+        dest, pages, _ = pfshader.render_frame(scene, fr, lut)
+        fr.close()
+        frames[name] = dest
+        digests[name]["shader_frame_sha256"] = scenes.digest(dest)
+        print(name, "shader frame", digests[name]["shader_frame_sha256"])
+    np.savez_compressed(os.path.join(HERE, "shader_frames.npz"), **frames)
     with open(os.path.join(HERE, "digests.json"), "w") as fp:
         json.dump(digests, fp, indent=1, sort_keys=True)
 

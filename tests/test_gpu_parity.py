@@ -395,3 +395,19 @@ def test_region_readback_matches_the_full_frame(renderer):
     for bad in ((-1, 0, 4, 4), (0, 0, 0, 4), (510, 0, 4, 4), (0, 510, 4, 4)):
         with pytest.raises(RuntimeError):
             renderer.pixels_region(*bad)
+
+
+@pytest.mark.parametrize("name", ["tiger_512", "demo_clip_512", "demo_full_512"])
+def test_pixels_against_reference_shader_frames(renderer, name):
+    """CUDA pixels against the frames the reference's OWN fill.comp + tile.comp render (tests/golden/shader_frames.npz,
+    produced by running the shader text on the CPU: oracle/pfshader.py). The north star's bound: 1/255 per channel."""
+    import os
+
+    want = np.load(os.path.join(scenes.GOLDEN, "shader_frames.npz"))[name]
+    scene, _ = scenes.load_scene(scenes.golden_path(name))
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    d = np.abs(renderer.pixels().astype(int) - want.astype(int))
+    print("%s: %d pixels differ from the reference shaders' frame, %d by more than 1" %
+          (name, int((d.max(axis=2) > 0).sum()), int((d.max(axis=2) > 1).sum())))
+    assert d.max() <= PIXEL_TOL, "max diff %d at %s" % (d.max(), np.unravel_index(d.argmax(), d.shape))
