@@ -12,9 +12,13 @@
  *
  * PINNING. The geometry + tile-resolution half is pinned against the reference itself
  * (oracle/_ref/libpfref.so, tests/test_oracle_vs_reference.py and the fixtures in tests/golden/ it
- * generated). The pixel half is "parity unpinned": the reference has no CPU rasteriser, no test
- * vectors, and neither of its GPU back ends can run headless here, so the pixel
- * restatement follows the shader text and cannot be checked against reference output.
+ * generated). The pixel half is pinned against the reference's OWN compute shaders: fill.comp and tile.comp, read
+ * where they lie under /root/reference, rewritten to C++ syntax (oracle/ref_harness/make_shader_cpp.py) and compiled by
+ * g++ over a GLSL vocabulary header (oracle/ref_harness/glsl_shim.h) into oracle/_ref/libpfshader.so, then run on the CPU
+ * on this oracle's geometry (oracle/pfshader.py): masks and frames agree within 1/255 on every fixture
+ * (tests/test_oracle_golden.py; tests/golden/shader_frames.npz holds the shader-rendered frames). What that does NOT pin
+ * is a particular GPU's arithmetic: the shaders are evaluated in IEEE fp32 with exact bilinear weights (a GPU filters
+ * with 8 fraction bits), neither of the reference's GPU back ends can run headless here.
  *
  * Inputs are exactly what the reference's SceneBuilderD3D11 hands to its renderer
  * (core/d3d11/gpu_data.h:54-205), so the same buffers feed this oracle and the CUDA path.
