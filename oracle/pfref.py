@@ -49,6 +49,8 @@ def lib():
         L.pfref_scene_from_svg.argtypes = [C.c_char_p, sz, C.c_int, C.c_int, C.c_float]
         L.pfref_scene_demo.restype = vp
         L.pfref_scene_demo.argtypes = [C.c_int, C.c_int, C.c_float, C.c_char_p, sz, C.c_int]
+        L.pfref_scene_paints.restype = vp
+        L.pfref_scene_paints.argtypes = [C.c_int, C.c_int, C.c_float, C.c_char_p, sz]
         L.pfref_scene_free.argtypes = [vp]
         L.pfref_scene_counts.argtypes = [vp, u32p]
         L.pfref_view_box.argtypes = [vp, C.POINTER(C.c_float)]
@@ -118,6 +120,11 @@ class RefScene:
     def demo(cls, width, height, scale, image_bytes=b"", features=0x3f):
         return cls(lib().pfref_scene_demo(width, height, scale, image_bytes, len(image_bytes), features), width,
                    height)
+
+    @classmethod
+    def paints(cls, width, height, scale, image_bytes=b""):
+        """Every blend mode, radial gradients, a repeating unsmoothed image pattern (ref_harness.cpp)."""
+        return cls(lib().pfref_scene_paints(width, height, scale, image_bytes, len(image_bytes)), width, height)
 
     def close(self):
         if self.h:

@@ -199,6 +199,71 @@ void *pfref_scene_demo(int width, int height, float scale, const char *img, size
     return h;
 }
 
+/// Paint coverage the SVG / demo scenes lack: a linear-gradient background, one translucent rectangle per BlendMode
+/// (effects.h:56-122; the separable and HSL modes go through tile.comp's composite(), :459-582), two radial gradients
+/// (filterRadialGradient, :319-347) and a small image used as a repeating, unsmoothed pattern (REPEAT + NEAREST sampler
+/// flags). `scale` multiplies every coordinate.
+void *pfref_scene_paints(int width, int height, float scale, const char *img, size_t img_len) {
+    auto *h = new_handle(width, height);
+    auto &canvas = h->canvas;
+    const float s = scale;
+    {
+        Path2d path;
+        path.add_rect(RectF(Vec2F(0, 0), Vec2F(512 * s, 512 * s)));
+        auto gradient = Gradient::linear(LineSegmentF({0, 0}, {512.0f * s, 512.0f * s}));
+        gradient.add_color_stop(ColorU(230, 40, 60, 255), 0);
+        gradient.add_color_stop(ColorU(40, 200, 90, 255), 0.5f);
+        gradient.add_color_stop(ColorU(30, 60, 220, 255), 1);
+        canvas->set_fill_paint(Paint::from_gradient(gradient));
+        canvas->fill_path(path, FillRule::Winding);
+    }
+    const BlendMode modes[] = {BlendMode::SrcOver, BlendMode::Multiply, BlendMode::Screen, BlendMode::Overlay,
+                               BlendMode::Darken, BlendMode::Lighten, BlendMode::ColorDodge, BlendMode::ColorBurn,
+                               BlendMode::HardLight, BlendMode::SoftLight, BlendMode::Difference, BlendMode::Exclusion,
+                               BlendMode::Hue, BlendMode::Saturation, BlendMode::Color, BlendMode::Luminosity,
+                               BlendMode::Lighter, BlendMode::Xor, BlendMode::DestOver, BlendMode::SrcAtop};
+    int k = 0;
+    for (BlendMode mode : modes) {
+        const float x = (20 + (k % 5) * 96) * s, y = (20 + (k / 5) * 70) * s;
+        Path2d path;
+        path.add_circle(Vec2F(x + 40 * s, y + 28 * s), 30 * s);
+        path.add_rect(RectF(Vec2F(x + 30 * s, y + 10 * s), Vec2F(x + 90 * s, y + 50 * s)));
+        canvas->set_global_composite_operation(mode);
+        canvas->set_fill_paint(Paint::from_color(ColorU((uint8_t)(40 + 37 * k), (uint8_t)(220 - 29 * k), (uint8_t)(90 + 53 * k), (uint8_t)(k % 3 ? 200 : 255))));
+        canvas->fill_path(path, k % 2 ? FillRule::EvenOdd : FillRule::Winding);
+        k++;
+    }
+    canvas->set_global_composite_operation(BlendMode::SrcOver);
+    for (int r = 0; r < 2; r++) {
+        Path2d path;
+        const Vec2F c((120 + 260 * r) * s, 400 * s);
+        path.add_circle(c, 90 * s);
+        auto gradient = Gradient::radial(LineSegmentF(c - Vec2F(20 * s * r, 0), c + Vec2F(30 * s * r, 10 * s * r)), Vec2F(10 * s, 90 * s));
+        gradient.add_color_stop(ColorU(255, 255, 255, 255), 0);
+        gradient.add_color_stop(ColorU(255, 180, 0, 160), 0.6f);
+        gradient.add_color_stop(ColorU(0, 0, 0, 0), 1);
+        canvas->set_fill_paint(Paint::from_gradient(gradient));
+        canvas->fill_path(path, FillRule::Winding);
+    }
+    if (img && img_len) {
+        auto image_buffer = ImageBuffer::from_memory(std::vector<char>(img, img + img_len), false);
+        if (image_buffer) {
+            auto image = std::make_shared<Image>(image_buffer->get_size(), image_buffer->to_rgba_pixels());
+            auto pattern = Pattern::from_image(image);
+            pattern.set_repeat_x(true);
+            pattern.set_repeat_y(true);
+            pattern.set_smoothing_enabled(false);
+            pattern.apply_transform(Transform2::from_scale(Vec2F(0.11f * s, 0.11f * s)));
+            Path2d path;
+            path.add_rect(RectF(Vec2F(300 * s, 300 * s), Vec2F(500 * s, 500 * s)));
+            canvas->set_fill_paint(Paint::from_pattern(pattern));
+            canvas->fill_path(path, FillRule::Winding);
+        }
+    }
+    h->scene = canvas->get_scene();
+    return h;
+}
+
 void pfref_scene_free(void *p) { delete static_cast<Handle *>(p); }
 
 void pfref_scene_counts(void *p, uint32_t out[4]) {

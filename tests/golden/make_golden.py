@@ -49,8 +49,12 @@ DEMO_SCENES = {
 }
 
 
+# every BlendMode over a gradient, radial gradients, a repeating unsmoothed image pattern (ref_harness.cpp
+# pfref_scene_paints): the tile.comp branches no SVG / demo scene reaches. name -> (size, scale)
+PAINT_SCENES = {"paints_512": (512, 1.0)}
+
 # scenes whose frame, rendered by the reference's own fill.comp + tile.comp on the CPU, is committed (shader_frames.npz)
-SHADER_FRAMES = ["tiger_512", "demo_clip_512", "demo_full_512"]
+SHADER_FRAMES = ["tiger_512", "demo_clip_512", "demo_full_512", "paints_512"]
 
 
 def canonical_extra(ref):
@@ -100,6 +104,14 @@ def main():
         print(name, digests[name])
     for name, (size, scale, features) in DEMO_SCENES.items():
         s = pfref.RefScene.demo(size, size, scale, pfref.asset("sea.png"), features)
+        scene = s.build_d3d11()
+        ref = scenes.canonical_from_reference(s.build_d3d9())
+        digests[name] = {"canonical_sha256": canonical_digest(ref), "counts": s.counts()}
+        scenes.save_scene(scenes.golden_path(name), scene, canonical_extra(ref))
+        s.close()
+        print(name, digests[name])
+    for name, (size, scale) in PAINT_SCENES.items():
+        s = pfref.RefScene.paints(size, size, scale, pfref.asset("sea.png"))
         scene = s.build_d3d11()
         ref = scenes.canonical_from_reference(s.build_d3d9())
         digests[name] = {"canonical_sha256": canonical_digest(ref), "counts": s.counts()}

@@ -12,7 +12,7 @@ import scenes
 
 pytestmark = pytest.mark.gpu
 
-GOLDEN = ["tiger_512", "tiger_1024", "features_2048", "demo_clip_512", "demo_full_512", "demo_full_2048"]
+GOLDEN = ["tiger_512", "tiger_1024", "features_2048", "demo_clip_512", "demo_full_512", "demo_full_2048", "paints_512"]
 PIXEL_TOL = 1  # 1/255 per channel, BASELINE.json north_star
 
 
@@ -397,7 +397,7 @@ def test_region_readback_matches_the_full_frame(renderer):
             renderer.pixels_region(*bad)
 
 
-@pytest.mark.parametrize("name", ["tiger_512", "demo_clip_512", "demo_full_512"])
+@pytest.mark.parametrize("name", ["tiger_512", "demo_clip_512", "demo_full_512", "paints_512"])
 def test_pixels_against_reference_shader_frames(renderer, name):
     """CUDA pixels against the frames the reference's OWN fill.comp + tile.comp render (tests/golden/shader_frames.npz,
     produced by running the shader text on the CPU: oracle/pfshader.py). The north star's bound: 1/255 per channel."""
