@@ -5,7 +5,8 @@
 // buffers are device-local, keyed by batch slot, grown geometrically and reused across frames; the whole frame is
 // enqueued on one stream without a single mid-frame host read-back (the reference has three per batch,
 // renderer.cpp:705-724,832-845,943-950). Capacity overflows are detected once, at pfcu_end_frame, and answered by
-// growing the buffer and replaying the recorded frame.
+// growing the buffer and replaying the recorded frame. A context is ONE frame in flight (pfcu_submit_frame /
+// pfcu_wait_frame; pfcu_end_frame = both): applications that stream frames keep a few contexts.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>

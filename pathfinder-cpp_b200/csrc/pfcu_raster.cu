@@ -3,14 +3,15 @@
 // Pixel ownership is the same in both kernels: a WARP owns one 16 x 16 tile, lane (k = lane & 3, s = lane >> 2) owns
 // pixel columns 4k .. 4k+3 of rows 2s and 2s+1 -- two 16-byte pieces of the framebuffer, one 8-byte piece of a mask.
 //
-//   fill : pathfinder/shaders/d3d11/fill.comp:51-154. The tile's fills are contiguous (CSR from the scatter), read
+//   fill : pathfinder/shaders/d3d11/fill.comp:51-154. Masks whose tile the z-buffer culls are skipped (nothing reads
+//          them). The tile's fills are contiguous (CSR from the scatter), read
 //          once with coalesced 8-byte loads. The work of a tile is enumerated as (fill, pixel column) pairs, one per
 //          lane; a pair samples the 256 x 256 area LUT (behind the texture unit: texel fetch + unorm conversion, the
 //          bilinear weights are applied in fp32) only for the 4-row groups its line passes through and adds the
 //          result to a 16 x 16 fixed-point accumulator in shared memory as differences down its column.
 //   tile : pathfinder/shaders/d3d11/tile.comp:737-850 with the shading functions of tile.comp:126-134 (combine),
 //          :319-347 (radial gradient), :354-392 (blur), :459-582 (composite), :586-607 (mask), :694-726 (paint
-//          metadata, decoded once per upload into a float table). A CTA stages the (z-culled) lists of 32 consecutive
+//          metadata, decoded once per upload into a float table). A CTA stages the (z-culled) lists of 16 consecutive
 //          framebuffer tiles in shared memory, orders them by paint order with 8 threads per tile (sort.comp:49-83)
 //          and blends the leading whole-tile layers of every tile as ONE pixel. Tiles that end there are stored by
 //          the whole CTA with 16-byte stores; the others go to one warp each, which blends the remaining layers in
