@@ -550,7 +550,7 @@ __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 #define CT_WARPS_N 4
 #endif
 #ifndef CT_MIN_CTAS
-#define CT_MIN_CTAS (24 / CT_WARPS_N)  // 80 registers per thread: measured best (64: spills, 33 us; 80: 31 us; 128: 39 us)
+#define CT_MIN_CTAS (28 / CT_WARPS_N)  // 7 CTAs per SM = 72 registers per thread, no spills: 31.2 us against 33.2 us at 6 CTAs (78 registers); 64 registers spill
 #endif
 #define CT_MIN_CTAS_TEX (CT_MIN_CTAS / 2)  // gradients / images / blend modes: 128 registers
 constexpr int CT_WARPS = CT_WARPS_N;   // warps per CTA
