@@ -411,3 +411,24 @@ def test_pixels_against_reference_shader_frames(renderer, name):
     print("%s: %d pixels differ from the reference shaders' frame, %d by more than 1" %
           (name, int((d.max(axis=2) > 0).sum()), int((d.max(axis=2) > 1).sum())))
     assert d.max() <= PIXEL_TOL, "max diff %d at %s" % (d.max(), np.unravel_index(d.argmax(), d.shape))
+
+
+def test_tiger_4096_pixels_against_live_reference_shaders(renderer, area_lut):
+    """The headline configuration (BASELINE.json configs[2]) against the reference's own fill.comp + tile.comp, run on the
+    host CPU of this box through the prebuilt oracle/_ref/libpfshader.so (about 10 s; skipped where the library did not
+    travel). 16.7 M pixels within 1/255."""
+    pfshader = pytest.importorskip("pfshader")
+    if not pfshader.available():
+        pytest.skip("oracle/_ref/libpfshader.so not present")
+    import pforacle
+
+    scene, _ = scenes.load_scene(scenes.golden_path("tiger_4096_scene"))
+    fr = pforacle.Frame(scene, area_lut)
+    fr.render()  # geometry taps (pinned bit-exact to the reference's tiler) for the shaders' input buffers
+    want, _, _ = pfshader.render_frame(scene, fr, area_lut)
+    fr.close()
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    d = np.abs(renderer.pixels().astype(np.int16) - want.astype(np.int16)).max(axis=2)
+    print("tiger 4096: %d of %d pixels differ from the reference shaders' frame" % (int((d > 0).sum()), d.size))
+    assert d.max() <= PIXEL_TOL
