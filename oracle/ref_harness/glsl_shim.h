@@ -263,6 +263,7 @@ struct sampler2D {
 inline ivec2 textureSize(const sampler2D &s, int) { return ivec2(s.width, s.height); }
 inline vec4 texelFetch(const sampler2D &s, ivec2 p, int) { return s.fetch(p.x, p.y); }
 inline bool &debug_trace() { static thread_local bool on = false; return on; }
+inline int &subtexel_bits() { static int bits = 0; return bits; }  // 0: exact fp32 weights (default)
 inline vec4 texture(const sampler2D &s, const vec2 &uv) {
     const float x = uv.x * (float)s.width, y = uv.y * (float)s.height;
     if (debug_trace()) fprintf(stderr, "texture %dx%d uv %.9g %.9g -> texel %.6f %.6f\n", s.width, s.height, uv.x, uv.y, x - 0.5f, y - 0.5f);
@@ -278,6 +279,11 @@ inline vec4 texture(const sampler2D &s, const vec2 &uv) {
     const float snap = 1.0f / 512.0f;
     if (ax < snap) ax = 0.0f; else if (ax > 1.0f - snap) ax = 1.0f;
     if (ay < snap) ay = 0.0f; else if (ay > 1.0f - snap) ay = 1.0f;
+    if (subtexel_bits() > 0) {  // diagnostic: ALL weights in fixed point, as a GPU's texture unit computes them
+        const float q = (float)(1 << subtexel_bits());
+        ax = std::nearbyint(ax * q) / q;
+        ay = std::nearbyint(ay * q) / q;
+    }
     const vec4 t00 = s.fetch((int)x0, (int)y0), t10 = s.fetch((int)x0 + 1, (int)y0);
     const vec4 t01 = s.fetch((int)x0, (int)y0 + 1), t11 = s.fetch((int)x0 + 1, (int)y0 + 1);
     return mix(mix(t00, t10, ax), mix(t01, t11, ax), ay);

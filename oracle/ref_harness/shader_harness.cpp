@@ -31,6 +31,9 @@ extern "C" {
 
 int pfshader_abi_version(void) { return 1; }
 
+/// Diagnostic: compute every bilinear weight with `bits` fraction bits (8 = what GPUs do); 0 = exact fp32 (default).
+void pfshader_set_subtexel_bits(int bits) { glsl::subtexel_bits() = bits; }
+
 /// fill.comp over the alpha tiles [first_alpha, first_alpha + n_alpha) of one batch (draw_fills, renderer.cpp:959-1002:
 /// one work group of 16 x 4 invocations per alpha tile; uAlphaTileRange = the batch's range of frame-global indices).
 ///   fills       : 3 x u32 per fill {from, to, next fill index or -1} (bin.comp's linked lists)
