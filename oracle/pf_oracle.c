@@ -42,6 +42,7 @@ typedef struct {
     size_t n_fills, cap_fills;
     pfo_tile *tiles;      /* tile_count */
     int32_t *col_backdrop; /* column_count: crossings above the tile rect (object_builder.cpp:107-110) */
+    int32_t *col_backdrop0; /* the same as bin left them (propagate advances col_backdrop down the columns) */
     int32_t *z11;          /* fb tiles */
     uint32_t *z9;
     uint32_t *list_offsets; /* fb tiles + 1 */
@@ -108,6 +109,7 @@ static void batch_free(batch_t *b) {
     free(b->fills);
     free(b->tiles);
     free(b->col_backdrop);
+    free(b->col_backdrop0);
     free(b->z11);
     free(b->z9);
     free(b->list_offsets);
@@ -495,6 +497,9 @@ static void propagate_batch(pfo_frame *f, batch_t *b) {
     uint32_t *list_count = (uint32_t *)calloc(fbt + 1, sizeof(uint32_t));
     b->first_alpha = (uint32_t)f->n_masks;
     uint32_t next_alpha = b->first_alpha;
+    free(b->col_backdrop0);
+    b->col_backdrop0 = (int32_t *)malloc(sizeof(int32_t) * (b->desc.column_count ? b->desc.column_count : 1));
+    memcpy(b->col_backdrop0, b->col_backdrop, sizeof(int32_t) * b->desc.column_count);
 
     /* Alpha tile ids are allocated in dense tile order (deterministic stand-in for propagate.comp:178-183's
      * atomicAdd); backdrops are a prefix sum down each column. Walk row-major like tiler.cpp:381. */
@@ -821,6 +826,13 @@ size_t pfo_batch_tiles(const pfo_frame *f, int slot, pfo_tile *out) {
     const batch_t *b = &f->batches[slot];
     if (out) memcpy(out, b->tiles, (size_t)b->desc.tile_count * sizeof(pfo_tile));
     return b->desc.tile_count;
+}
+
+size_t pfo_batch_column_backdrops(const pfo_frame *f, int slot, int32_t *out) {
+    if (slot < 0 || slot >= f->n_batches) return 0;
+    const batch_t *b = &f->batches[slot];
+    if (out && b->col_backdrop0) memcpy(out, b->col_backdrop0, sizeof(int32_t) * b->desc.column_count);
+    return b->desc.column_count;
 }
 
 size_t pfo_batch_z(const pfo_frame *f, int slot, int32_t *z11, uint32_t *z9) {

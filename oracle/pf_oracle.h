@@ -122,6 +122,8 @@ size_t pfo_batch_tiles(const pfo_frame *f, int slot, pfo_tile *out);
 /* Per framebuffer tile: propagate.comp's z (max dense tile index of an occluding solid tile, 0 if none) and
  * the hybrid builder's z (max draw path id, core/d3d9/scene_builder.cpp:65-78). Either may be NULL. */
 size_t pfo_batch_z(const pfo_frame *f, int slot, int32_t *z_d3d11, uint32_t *z_d3d9);
+/* Column backdrops as bin left them (crossings above each path's tile rect), i.e. propagate's input. */
+size_t pfo_batch_column_backdrops(const pfo_frame *f, int slot, int32_t *out);
 /* Sorted, z-culled per-framebuffer-tile lists in CSR form (sort.comp:49-83). offsets has fb_tiles + 1 entries. */
 size_t pfo_batch_tile_lists(const pfo_frame *f, int slot, uint32_t *offsets, uint32_t *dense_tile_indices);
 /* 16 x 16 coverage bytes (row-major) of one mask slot. */

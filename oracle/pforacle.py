@@ -55,6 +55,8 @@ def lib():
         for name in ("pfo_batch_lines", "pfo_batch_clipped_lines", "pfo_batch_fills", "pfo_batch_tiles"):
             getattr(L, name).restype = sz
             getattr(L, name).argtypes = [vp, C.c_int, vp]
+        L.pfo_batch_column_backdrops.restype = sz
+        L.pfo_batch_column_backdrops.argtypes = [vp, C.c_int, vp]
         L.pfo_batch_z.restype = sz
         L.pfo_batch_z.argtypes = [vp, C.c_int, vp, vp]
         L.pfo_batch_tile_lists.restype = sz
@@ -163,6 +165,9 @@ class Frame:
 
     def tiles(self, slot):
         return self._get(lib().pfo_batch_tiles, slot, TILE_DT)
+
+    def column_backdrops(self, slot):
+        return self._get(lib().pfo_batch_column_backdrops, slot, "<i4")
 
     def z(self, slot):
         z11 = np.zeros(self.fb_tiles, "<i4")

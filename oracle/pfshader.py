@@ -188,3 +188,53 @@ def render_frame(scene, fr, area_lut, clear_color=(0.0, 0.0, 0.0, 0.0)):
         else:
             run_tile(t, first_map, fb_tw, fb_th, md, color, flags, mask, pages[int(info[11])], True, (0.0, 0.0, 0.0, 0.0))
     return dest, pages, mask
+
+
+# ---------------------------------------------------------------------------------------------- propagate.comp + sort.comp
+
+def run_propagate_sort(scene, fr, kind, index, clip_state=None):
+    """propagate.comp then sort.comp on one batch, fed with what bin left behind according to the oracle frame `fr`
+    (first fill ids, backdrop deltas, column backdrops). Returns a dict: tiles (n x 4 u32 after both shaders), z (per
+    framebuffer tile), first_map (sorted list heads), alpha_tiles (k x 2), lists (CSR offsets, dense tile indices walked
+    from the sorted linked lists). clip_state: the same dict of the batch's clip batch (its tiles are read)."""
+    import scenes
+
+    L = lib()
+    if not getattr(L, "_prop_ready", False):
+        vp, i = C.c_void_p, C.c_int
+        L.pfshader_propagate.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i]
+        L.pfshader_sort.argtypes = [vp, vp, vp, i]
+        L._prop_ready = True
+    b = scene[kind + "_batches"][index]
+    slot = fr.slots[int(b["info"][0])]
+    tiles, fills = fr.tiles(slot), fr.fills(slot)
+    path = scenes.dense_tile_coords(b)[0]
+    i_fills, i_tiles, _, _ = fill_buffers(b, tiles, fills, path)
+    # as bound.comp + bin.comp leave the tiles: no alpha tile yet (-1 in the low 24 bits), backdrop 0 in the control word
+    i_tiles[:, 2] = 0x00FFFFFF | (tiles["backdrop_delta"].astype("<i4").view("<u4") << 24)
+    i_tiles[:, 3] &= 0x00FFFFFF
+    w, h = int(scene["width"]), int(scene["height"])
+    fb_tw, fb_th = (w + 15) // 16, (h + 15) // 16
+    z = np.zeros(8 + fb_tw * fb_th, "<i4")
+    first_map = np.full(fb_tw * fb_th, -1, "<i4")
+    alpha = np.zeros((max(len(tiles), 1), 2), "<u4")
+    md = np.ascontiguousarray(b["propagate_metadata"]).view("<u4").reshape(-1)
+    bd = np.ascontiguousarray(b["backdrops"]).view("<i4").reshape(-1, 3).copy()
+    bd[:, 0] = fr.column_backdrops(slot)
+    first_alpha = fr.counts(slot)["first_alpha"]
+    clip_md = clip_tiles = None
+    if clip_state is not None:
+        clip_md, clip_tiles = clip_state["metadata_words"], clip_state["tiles"]
+    L.pfshader_propagate(_p(md), _p(clip_md) if clip_md is not None else None, _p(bd), _p(i_tiles),
+                         _p(clip_tiles) if clip_tiles is not None else None, _p(z), _p(first_map), _p(alpha), fb_tw, fb_th,
+                         len(bd), first_alpha)
+    L.pfshader_sort(_p(i_tiles), _p(first_map), _p(z), fb_tw * fb_th)
+    offsets, lst = [0], []
+    for m in range(fb_tw * fb_th):
+        t = int(first_map[m])
+        while t >= 0:
+            lst.append(t)
+            t = int(np.int32(i_tiles[t, 0]))
+        offsets.append(len(lst))
+    return dict(tiles=i_tiles, z=z[8:], n_alpha=int(z[4]), first_map=first_map, alpha_tiles=alpha[:int(z[4])],
+                lists=(np.array(offsets, "<u4"), np.array(lst, "<u4")), metadata_words=md, first_alpha=first_alpha)

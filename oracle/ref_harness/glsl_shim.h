@@ -119,6 +119,8 @@ struct ivec2 {
     explicit ivec2(int s) : x(s), y(s) {}
     ivec2(int a, int b) : x(a), y(b) {}
     ivec2(uint a, uint b) : x((int)a), y((int)b) {}
+    ivec2(int a, uint b) : x(a), y((int)b) {}
+    ivec2(uint a, int b) : x((int)a), y(b) {}
     explicit ivec2(const vec2 &v) : x((int)v.x), y((int)v.y) {}
     explicit ivec2(const struct uvec2 &v);
 };
@@ -129,15 +131,28 @@ struct uvec2 {
     explicit uvec2(int s) : x((uint)s), y((uint)s) {}
     uvec2(uint a, uint b) : x(a), y(b) {}
     uvec2(int a, int b) : x((uint)a), y((uint)b) {}
+    uvec2(int a, uint b) : x((uint)a), y(b) {}
+    uvec2(uint a, int b) : x(a), y((uint)b) {}
     explicit uvec2(const vec2 &v) : x((uint)v.x), y((uint)v.y) {}
 };
 inline uvec2 operator*(uvec2 a, uvec2 b) { return uvec2(a.x * b.x, a.y * b.y); }
 inline uvec2 operator+(uvec2 a, uvec2 b) { return uvec2(a.x + b.x, a.y + b.y); }
-struct uvec4 {
-    uint x, y, z, w;
-    uvec4() : x(0), y(0), z(0), w(0) {}
-    uvec4(uint a, uint b, uint c, uint d) : x(a), y(b), z(c), w(d) {}
+template <int A, int B>
+struct USwz2 {
+    uint d[4];
+    operator uvec2() const { return uvec2(d[A], d[B]); }
 };
+struct uvec4 {
+    union {
+        struct { uint x, y, z, w; };
+        USwz2<0, 1> xy;
+        USwz2<2, 3> zw;
+    };
+    uvec4() : x(0), y(0), z(0), w(0) {}
+    explicit uvec4(uint s) : x(s), y(s), z(s), w(s) {}
+    uvec4(uint a, uint b, uint c, uint d_) : x(a), y(b), z(c), w(d_) {}
+};
+inline uvec2 operator-(uvec2 a, uvec2 b) { return uvec2(a.x - b.x, a.y - b.y); }
 struct uvec3 {
     uint x, y, z;
     struct XY { uint x, y; } ;
@@ -223,7 +238,20 @@ inline bvec3 lessThanEqual(const vec3 &a, const vec3 &b) { return bvec3(a.x <= b
 inline bvec3 lessThan(const vec3 &a, const vec3 &b) { return bvec3(a.x < b.x, a.y < b.y, a.z < b.z); }
 inline bvec3 equal(const vec3 &a, const vec3 &b) { return bvec3(a.x == b.x, a.y == b.y, a.z == b.z); }
 inline bvec2 lessThanEqual(const vec2 &a, const vec2 &b) { return bvec2(a.x <= b.x, a.y <= b.y); }
+struct bvec4 {
+    bool x, y, z, w;
+    bvec4(const bvec2 &a, const bvec2 &b) : x(a.x), y(a.y), z(b.x), w(b.y) {}
+};
+inline bvec2 greaterThanEqual(uvec2 a, uvec2 b) { return bvec2(a.x >= b.x, a.y >= b.y); }
+inline bvec2 lessThan(uvec2 a, uvec2 b) { return bvec2(a.x < b.x, a.y < b.y); }
+inline bool all(const bvec4 &v) { return v.x && v.y && v.z && v.w; }
 inline bool all(const bvec2 &v) { return v.x && v.y; }
+// atomics on buffer elements: invocations run one after the other, so plain read-modify-write
+inline int atomicAdd(int &mem, int v) { const int old = mem; mem = old + v; return old; }
+inline uint atomicAdd(uint &mem, uint v) { const uint old = mem; mem = old + v; return old; }
+inline int atomicMax(int &mem, int v) { const int old = mem; if (v > old) mem = v; return old; }
+inline int atomicExchange(int &mem, int v) { const int old = mem; mem = v; return old; }
+inline uint atomicExchange(uint &mem, uint v) { const uint old = mem; mem = v; return old; }
 inline bool all(const bvec3 &v) { return v.x && v.y && v.z; }
 inline bool any(const bvec3 &v) { return v.x || v.y || v.z; }
 

@@ -15,6 +15,8 @@
 
 #include "fill_comp.inc"
 #include "tile_comp.inc"
+#include "propagate_comp.inc"
+#include "sort_comp.inc"
 
 namespace {
 
@@ -126,6 +128,53 @@ int pfshader_tile(const uint32_t *tiles, const int32_t *first_tile_map, int fb_t
         }
     glsl::debug_trace() = false;
     uColorTexture0.texels = uMaskTexture0.texels = uTextureMetadata.texels = nullptr;
+    return 0;
+}
+
+/// propagate.comp over every tile column of one batch (propagate_tiles, renderer.cpp:853-953: one invocation per column).
+///   draw_metadata : PropagateMetadataD3D11 records (3 x uvec4 per path);  backdrops: BackdropInfoD3D11 (3 x i32 per
+///                   column) with the counts bin left in [0];  draw_tiles: 4 x u32 per dense tile, read and written
+///   clip_metadata / clip_tiles: the clip batch's records or NULL. NOTE: the shader indexes clip_metadata with a stride of
+///                   TWO uvec4 (propagate.comp:110-111) while the reference binds the clip batch's 48-byte records
+///                   (renderer.cpp:910-916), so only clip path 0 is read correctly upstream; the caller passes what the
+///                   reference binds.
+///   z_buffer      : 8 + framebuffer tiles i32 ([4] = alpha tile counter), first_tile_map: framebuffer tiles i32 (-1),
+///   alpha_tiles   : 2 x u32 per alpha tile (written).
+int pfshader_propagate(const uint32_t *draw_metadata, const uint32_t *clip_metadata, const int32_t *backdrops,
+                       uint32_t *draw_tiles, uint32_t *clip_tiles, int32_t *z_buffer, int32_t *first_tile_map,
+                       uint32_t *alpha_tiles, int fb_tw, int fb_th, int column_count, int first_alpha) {
+    using namespace propagate_comp;
+    iDrawMetadata = reinterpret_cast<const glsl::uvec4 *>(draw_metadata);
+    iClipMetadata = reinterpret_cast<const glsl::uvec4 *>(clip_metadata);
+    iBackdrops = backdrops;
+    iDrawTiles = draw_tiles;
+    iClipTiles = clip_tiles;
+    iZBuffer = z_buffer;
+    iFirstTileMap = first_tile_map;
+    iAlphaTiles = alpha_tiles;
+    uFramebufferTileSize = glsl::ivec2(fb_tw, fb_th);
+    uColumnCount = column_count;
+    uFirstAlphaTileIndex = first_alpha;
+    for (int c = 0; c < column_count; c++) {
+        gl_GlobalInvocationID.x = (unsigned)c;
+        gl_GlobalInvocationID.y = gl_GlobalInvocationID.z = 0;
+        shader_main();
+    }
+    return 0;
+}
+
+/// sort.comp over every framebuffer tile (sort_tiles, renderer.cpp:1004-1039).
+int pfshader_sort(uint32_t *tiles, int32_t *first_tile_map, const int32_t *z_buffer, int fb_tiles) {
+    using namespace sort_comp;
+    iTiles = tiles;
+    iFirstTileMap = first_tile_map;
+    iZBuffer = z_buffer;
+    uTileCount = fb_tiles;
+    for (int t = 0; t < fb_tiles; t++) {
+        gl_GlobalInvocationID.x = (unsigned)t;
+        gl_GlobalInvocationID.y = gl_GlobalInvocationID.z = 0;
+        shader_main();
+    }
     return 0;
 }
 
