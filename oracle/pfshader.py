@@ -238,3 +238,97 @@ def run_propagate_sort(scene, fr, kind, index, clip_state=None):
         offsets.append(len(lst))
     return dict(tiles=i_tiles, z=z[8:], n_alpha=int(z[4]), first_map=first_map, alpha_tiles=alpha[:int(z[4])],
                 lists=(np.array(offsets, "<u4"), np.array(lst, "<u4")), metadata_words=md, first_alpha=first_alpha)
+
+
+# ---------------------------------------------------------------------------------------------- the whole GPU-driven mode
+
+def render_frame_gpu_driven(scene, area_lut, clear_color=(0.0, 0.0, 0.0, 0.0)):
+    """The reference's GPU-driven mode END TO END on the CPU, from the scene builder's vectors alone: dice.comp, bound.comp,
+    bin.comp, propagate.comp, fill.comp, sort.comp and tile.comp in RendererD3D11::draw's order
+    (core/d3d11/renderer.cpp:302-336, :510-616). No part of oracle/pf_oracle.c is involved. This is the render the
+    reference's own shaders produce -- with THEIR flattening (uniform-t microlines, dice.comp:176-222) and THEIR fixed
+    point (truncation, bin.comp:94), i.e. not the hybrid tiler's geometry that the CUDA path is bit-exact with.
+    Returns (destination pixels, stats)."""
+    L = lib()
+    if not getattr(L, "_geo_ready", False):
+        vp, i = C.c_void_p, C.c_int
+        L.pfshader_dice.argtypes = [vp, vp, vp, i, vp, vp, vp, i, i, i]
+        L.pfshader_bound.argtypes = [vp, vp, i, i]
+        L.pfshader_bin.argtypes = [vp, vp, vp, vp, vp, vp, i, i]
+        L.pfshader_propagate.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i, i, i, i]
+        L.pfshader_sort.argtypes = [vp, vp, vp, i]
+        L._geo_ready = L._prop_ready = True
+    w, h = int(scene["width"]), int(scene["height"])
+    fb_tw, fb_th = (w + 15) // 16, (h + 15) // 16
+    n_fb = fb_tw * fb_th
+    md = metadata_texels(scene)
+    dest = np.zeros((h, w, 4), "u1")
+    pages = {int(k): np.array(v, "u1", copy=True) for k, v in scene.get("pages", {}).items()}
+    dummy = np.zeros((1, 1, 4), "u1")
+    mask = mask_image(1 << 16)
+    state, stats = {}, dict(microlines=0, fills=0, alpha_tiles=0)
+    next_alpha = 0
+    order = [("clip", i) for i in reversed(range(len(scene["clip_batches"])))
+             if int(scene["clip_batches"][i]["info"][1]) > 0] + [("draw", i) for i in range(len(scene["draw_batches"]))]
+    first = True
+    for kind, bi in order:
+        b = scene[kind + "_batches"][bi]
+        info = b["info"]
+        n_paths, n_tiles, n_segs = int(info[1]), int(info[2]), int(info[3])
+        src = "clip" if int(info[5]) else "draw"
+        pts = np.ascontiguousarray(scene[src + "_points"], "<f4")
+        idx = np.ascontiguousarray(scene[src + "_indices"], "<u4")
+        dice_md = np.ascontiguousarray(b["dice_metadata"]).view("<u4").reshape(-1)
+        prop_md = np.ascontiguousarray(b["propagate_metadata"]).view("<u4").reshape(-1)
+        tpi = np.ascontiguousarray(b["tile_path_info"]).view("<u4").reshape(-1)
+        transform = np.ascontiguousarray(b["transform"], "<f4")
+        cap = max(16384, n_segs * 8)
+        while True:  # dice_segments retries with a larger buffer (renderer.cpp:537-556)
+            indirect = np.zeros(8, "<u4")
+            microlines = np.zeros((cap, 4), "<u4")
+            L.pfshader_dice(_p(indirect), _p(dice_md), _p(pts), len(pts), _p(idx), _p(microlines), _p(transform), n_paths,
+                            n_segs, cap)
+            if int(indirect[3]) <= cap:
+                break
+            cap = int(indirect[3])
+        n_micro = int(indirect[3])
+        tiles = np.zeros((max(n_tiles, 1), 4), "<u4")
+        L.pfshader_bound(_p(tpi), _p(tiles), n_paths, n_tiles)
+        backdrops = np.ascontiguousarray(b["backdrops"]).view("<u4").reshape(-1, 3).copy()
+        fcap = max(65536, n_micro * 4)
+        while True:
+            z = np.zeros(8 + n_fb, "<i4")
+            t2, bd2 = tiles.copy(), backdrops.copy()
+            fills = np.zeros((fcap, 3), "<u4")
+            L.pfshader_bin(_p(microlines), _p(prop_md.view("<i4")), _p(z.view("<u4")), _p(fills), _p(t2), _p(bd2), n_micro, fcap)
+            if int(z[1]) <= fcap:
+                break
+            fcap = int(z[1])
+        tiles, backdrops = t2, bd2
+        first_map = np.full(n_fb, -1, "<i4")
+        alpha = np.zeros((max(n_tiles, 1), 2), "<u4")
+        clip_md = clip_tiles = None
+        cb = int(info[6])
+        if cb != NONE and cb in state:
+            clip_md, clip_tiles = state[cb]["metadata"], state[cb]["tiles"]
+        L.pfshader_propagate(_p(prop_md), _p(clip_md) if clip_md is not None else None, _p(backdrops.view("<i4")),
+                             _p(tiles), _p(clip_tiles) if clip_tiles is not None else None, _p(z), _p(first_map), _p(alpha),
+                             fb_tw, fb_th, len(backdrops), next_alpha)
+        n_alpha = int(z[4])
+        run_fill(fills, tiles, alpha[:n_alpha], next_alpha, area_lut, mask)
+        L.pfshader_sort(_p(tiles), _p(first_map), _p(z), n_fb)
+        state[int(info[0])] = dict(metadata=prop_md, tiles=tiles)
+        stats["microlines"] += n_micro
+        stats["fills"] += int(z[1])
+        stats["alpha_tiles"] += n_alpha
+        next_alpha += n_alpha
+        if kind == "clip":
+            continue
+        color = pages[int(info[7])] if int(info[7]) != NONE else dummy
+        flags = 0 if int(info[8]) == NONE else int(info[8])
+        if int(info[10]) == NONE:
+            run_tile(tiles, first_map, fb_tw, fb_th, md, color, flags, mask, dest, first, clear_color)
+            first = False
+        else:
+            run_tile(tiles, first_map, fb_tw, fb_th, md, color, flags, mask, pages[int(info[11])], True, (0.0, 0.0, 0.0, 0.0))
+    return dest, stats

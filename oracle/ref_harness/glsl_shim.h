@@ -88,6 +88,7 @@ struct vec4 {
         float d[4];
         Swz2<0, 1> xy; Swz2<2, 3> zw; Swz2<1, 2> yz; Swz2<0, 1> rg;
         Swz3<0, 1, 2> xyz; Swz3<0, 1, 2> rgb; Swz3<1, 2, 3> yzw; Swz3<2, 1, 0> zyx; Swz3<0, 0, 0> rrr;
+        Swz4<2, 3, 0, 1> zwxy;
     };
     vec4() : x(0), y(0), z(0), w(0) {}
     explicit vec4(float s) : x(s), y(s), z(s), w(s) {}
@@ -96,6 +97,7 @@ struct vec4 {
     vec4(const vec2 &p, const vec2 &q) : x(p.x), y(p.y), z(q.x), w(q.y) {}
     vec4(const vec2 &p, float c, float d_) : x(p.x), y(p.y), z(c), w(d_) {}
     // GLSL constructors convert every scalar argument on their own (uint / int arguments in fill.comp)
+    explicit vec4(const struct ivec4 &v);
     template <class A, class B, class C, class D>
     vec4(A a_, B b_, C c, D d_) : x((float)a_), y((float)b_), z((float)c), w((float)d_) {}
     float &operator[](int i) { return d[i]; }
@@ -113,8 +115,17 @@ template <int A, int B, int C> Swz3<A, B, C> &Swz3<A, B, C>::operator*=(float s)
 template <int A, int B, int C> Swz3<A, B, C> &Swz3<A, B, C>::operator*=(const vec3 &v) { d[A] *= v.x; d[B] *= v.y; d[C] *= v.z; return *this; }
 template <int A, int B, int C, int D> Swz4<A, B, C, D>::operator vec4() const { return vec4(d[A], d[B], d[C], d[D]); }
 
+struct ivec4;
+template <int A, int B, int C_, int D>
+struct ISwz4 {
+    int d[4];
+    operator ivec4() const;
+};
 struct ivec2 {
-    int x, y;
+    union {
+        struct { int x, y; };
+        ISwz4<0, 1, 0, 1> xyxy;
+    };
     ivec2() : x(0), y(0) {}
     explicit ivec2(int s) : x(s), y(s) {}
     ivec2(int a, int b) : x(a), y(b) {}
@@ -151,8 +162,31 @@ struct uvec4 {
     uvec4() : x(0), y(0), z(0), w(0) {}
     explicit uvec4(uint s) : x(s), y(s), z(s), w(s) {}
     uvec4(uint a, uint b, uint c, uint d_) : x(a), y(b), z(c), w(d_) {}
+    explicit uvec4(const struct vec4 &v);
 };
 inline uvec2 operator-(uvec2 a, uvec2 b) { return uvec2(a.x - b.x, a.y - b.y); }
+template <int A, int B>
+struct ISwz2 {
+    int d[4];
+    operator ivec2() const { return ivec2(d[A], d[B]); }
+};
+struct ivec4 {
+    union {
+        struct { int x, y, z, w; };
+        ISwz2<0, 1> xy;
+        ISwz2<2, 3> zw;
+    };
+    ivec4() : x(0), y(0), z(0), w(0) {}
+    explicit ivec4(int s) : x(s), y(s), z(s), w(s) {}
+    ivec4(int a, int b, int c, int d_) : x(a), y(b), z(c), w(d_) {}
+    explicit ivec4(const uvec4 &v) : x((int)v.x), y((int)v.y), z((int)v.z), w((int)v.w) {}
+    explicit ivec4(const vec4 &v);
+};
+template <int A, int B, int C_, int D> ISwz4<A, B, C_, D>::operator ivec4() const { return ivec4(d[A], d[B], d[C_], d[D]); }
+inline ivec4 operator-(ivec4 a, ivec4 b) { return ivec4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+inline ivec4 operator+(ivec4 a, ivec4 b) { return ivec4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+inline ivec4 operator*(ivec4 a, ivec4 b) { return ivec4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+inline ivec4 operator*(ivec4 a, int s) { return ivec4(a.x * s, a.y * s, a.z * s, a.w * s); }
 struct uvec3 {
     uint x, y, z;
     struct XY { uint x, y; } ;
@@ -170,6 +204,8 @@ struct bvec2 {
     bvec2(bool a, bool b_) : x(a), y(b_) {}
 };
 
+inline bool operator==(ivec2 a, ivec2 b) { return a.x == b.x && a.y == b.y; }
+inline bool operator!=(ivec2 a, ivec2 b) { return !(a == b); }
 inline ivec2 operator+(ivec2 a, ivec2 b) { return ivec2(a.x + b.x, a.y + b.y); }
 inline ivec2 operator-(ivec2 a, ivec2 b) { return ivec2(a.x - b.x, a.y - b.y); }
 inline ivec2 operator*(ivec2 a, ivec2 b) { return ivec2(a.x * b.x, a.y * b.y); }
@@ -190,6 +226,9 @@ inline ivec2 operator%(ivec2 a, ivec2 b) { return ivec2(a.x % b.x, a.y % b.y); }
 GLSL_VEC(vec2)
 GLSL_VEC(vec3)
 GLSL_VEC(vec4)
+inline vec4::vec4(const ivec4 &v) : x((float)v.x), y((float)v.y), z((float)v.z), w((float)v.w) {}
+inline ivec4::ivec4(const vec4 &v) : x((int)v.x), y((int)v.y), z((int)v.z), w((int)v.w) {}
+inline uvec4::uvec4(const vec4 &v) : x((uint)v.x), y((uint)v.y), z((uint)v.z), w((uint)v.w) {}
 
 // ---- built-in functions, scalar
 inline float abs(float a) { return std::fabs(a); }
@@ -198,6 +237,7 @@ inline float sign(float a) { return a > 0.0f ? 1.0f : (a < 0.0f ? -1.0f : 0.0f);
 inline float floor(float a) { return std::floor(a); }
 inline float ceil(float a) { return std::ceil(a); }
 inline float fract(float a) { return a - std::floor(a); }
+inline float round(float a) { return std::nearbyint(a); }
 inline float sqrt(float a) { return std::sqrt(a); }
 inline float inversesqrt(float a) { return 1.0f / std::sqrt(a); }
 inline float exp(float a) { return std::exp(a); }
@@ -220,7 +260,7 @@ inline float step(float edge, float v) { return v < edge ? 0.0f : 1.0f; }
     inline V F(const V &a, const V &b) { V r; for (int i = 0; i < (int)(sizeof(a.d) / 4); i++) r.d[i] = F(a.d[i], b.d[i]); return r; } \
     inline V F(const V &a, float s) { V r; for (int i = 0; i < (int)(sizeof(a.d) / 4); i++) r.d[i] = F(a.d[i], s); return r; }
 #define GLSL_FUNCS(V)                                                                                                     \
-    GLSL_MAP1(V, abs) GLSL_MAP1(V, sign) GLSL_MAP1(V, floor) GLSL_MAP1(V, ceil) GLSL_MAP1(V, fract) GLSL_MAP1(V, sqrt)    \
+    GLSL_MAP1(V, round) GLSL_MAP1(V, abs) GLSL_MAP1(V, sign) GLSL_MAP1(V, floor) GLSL_MAP1(V, ceil) GLSL_MAP1(V, fract) GLSL_MAP1(V, sqrt)    \
     GLSL_MAP1(V, exp) GLSL_MAP2(V, min) GLSL_MAP2(V, max) GLSL_MAP2(V, mod) GLSL_MAP2(V, pow)                                    \
     inline V clamp(const V &v, float lo, float hi) { V r; for (int i = 0; i < (int)(sizeof(v.d) / 4); i++) r.d[i] = clamp(v.d[i], lo, hi); return r; } \
     inline V clamp(const V &v, const V &lo, const V &hi) { V r; for (int i = 0; i < (int)(sizeof(v.d) / 4); i++) r.d[i] = clamp(v.d[i], lo.d[i], hi.d[i]); return r; } \
@@ -245,6 +285,9 @@ struct bvec4 {
 inline bvec2 greaterThanEqual(uvec2 a, uvec2 b) { return bvec2(a.x >= b.x, a.y >= b.y); }
 inline bvec2 lessThan(uvec2 a, uvec2 b) { return bvec2(a.x < b.x, a.y < b.y); }
 inline bool all(const bvec4 &v) { return v.x && v.y && v.z && v.w; }
+inline bool any(const bvec4 &v) { return v.x || v.y || v.z || v.w; }
+inline bvec2 lessThan(ivec2 a, ivec2 b) { return bvec2(a.x < b.x, a.y < b.y); }
+inline bvec2 greaterThanEqual(ivec2 a, ivec2 b) { return bvec2(a.x >= b.x, a.y >= b.y); }
 inline bool all(const bvec2 &v) { return v.x && v.y; }
 // atomics on buffer elements: invocations run one after the other, so plain read-modify-write
 inline int atomicAdd(int &mem, int v) { const int old = mem; mem = old + v; return old; }

@@ -17,6 +17,9 @@
 #include "tile_comp.inc"
 #include "propagate_comp.inc"
 #include "sort_comp.inc"
+#include "dice_comp.inc"
+#include "bound_comp.inc"
+#include "bin_comp.inc"
 
 namespace {
 
@@ -173,6 +176,69 @@ int pfshader_sort(uint32_t *tiles, int32_t *first_tile_map, const int32_t *z_buf
     for (int t = 0; t < fb_tiles; t++) {
         gl_GlobalInvocationID.x = (unsigned)t;
         gl_GlobalInvocationID.y = gl_GlobalInvocationID.z = 0;
+        shader_main();
+    }
+    return 0;
+}
+
+/// dice.comp (dice_segments, renderer.cpp:618-731): one invocation per batch segment. transform = m11 m21 m12 m22 m13 m23.
+/// indirect[3] counts the microlines (may exceed max_microlines: the caller retries with more room, as the reference does).
+int pfshader_dice(uint32_t *indirect, const uint32_t *dice_metadata, const float *points, int point_count,
+                  const uint32_t *indices, uint32_t *microlines, const float *transform, int path_count, int segment_count,
+                  int max_microlines) {
+    using namespace dice_comp;
+    iComputeIndirectParams = indirect;
+    iDiceMetadata = reinterpret_cast<const glsl::uvec4 *>(dice_metadata);
+    // (glsl::vec2 carries its swizzle proxies and is wider than two floats: repack the std430 array)
+    std::vector<glsl::vec2> point_array;
+    {
+        point_array.resize((size_t)point_count);
+        for (size_t i = 0; i < (size_t)point_count; i++) point_array[i] = glsl::vec2(points[i * 2], points[i * 2 + 1]);
+    }
+    iPoints = point_array.data();
+    iInputIndices = reinterpret_cast<const glsl::uvec2 *>(indices);
+    iMicrolines = reinterpret_cast<glsl::uvec4 *>(microlines);
+    uTransform = glsl::mat2(transform[0], transform[1], transform[2], transform[3]);
+    uTranslation = glsl::vec2(transform[4], transform[5]);
+    uPathCount = path_count;
+    uLastBatchSegmentIndex = segment_count;
+    uMaxMicrolineCount = max_microlines;
+    for (int i = 0; i < segment_count; i++) {
+        gl_GlobalInvocationID.x = (unsigned)i;
+        shader_main();
+    }
+    return 0;
+}
+
+/// bound.comp (bound, renderer.cpp:733-775): one invocation per dense tile; tile_path_info = TilePathInfoD3D11 records.
+int pfshader_bound(const uint32_t *tile_path_info, uint32_t *tiles, int path_count, int tile_count) {
+    using namespace bound_comp;
+    iTilePathInfo = reinterpret_cast<const glsl::uvec4 *>(tile_path_info);
+    iTiles = tiles;
+    uPathCount = path_count;
+    uTileCount = tile_count;
+    for (int i = 0; i < tile_count; i++) {
+        gl_GlobalInvocationID.x = (unsigned)i;
+        shader_main();
+    }
+    return 0;
+}
+
+/// bin.comp (bin_segments, renderer.cpp:777-851): one invocation per microline. indirect_draw = the z-buffer's 8-word
+/// header ([1] counts the fills; may exceed max_fills: retry with more room). backdrops: 3 x u32 per column, [0] updated.
+int pfshader_bin(const uint32_t *microlines, const int32_t *metadata, uint32_t *indirect_draw, uint32_t *fills,
+                 uint32_t *tiles, uint32_t *backdrops, int microline_count, int max_fills) {
+    using namespace bin_comp;
+    iMicrolines = reinterpret_cast<const glsl::uvec4 *>(microlines);
+    iMetadata = reinterpret_cast<const glsl::ivec4 *>(metadata);
+    iIndirectDrawParams = indirect_draw;
+    iFills = fills;
+    iTiles = tiles;
+    iBackdrops = backdrops;
+    uMicrolineCount = microline_count;
+    uMaxFillCount = max_fills;
+    for (int i = 0; i < microline_count; i++) {
+        gl_GlobalInvocationID.x = (unsigned)i;
         shader_main();
     }
     return 0;
