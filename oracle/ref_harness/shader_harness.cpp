@@ -1,8 +1,8 @@
 // TEST INFRASTRUCTURE (oracle side). Runs the reference's own compute shaders on the CPU.
 //
-// oracle/Makefile generates fill_comp.inc / tile_comp.inc from pathfinder/shaders/d3d11/fill.comp and tile.comp where
-// they lie under /root/reference (make_shader_cpp.py: a syntactic GLSL -> C++ rewrite over glsl_shim.h) and compiles
-// this file into oracle/_ref/libpfshader.so. The entry points bind the shaders' buffers / textures / uniforms to host
+// oracle/Makefile generates <name>_comp.inc from pathfinder/shaders/d3d11/<name>.comp where they lie under
+// /root/reference (make_shader_cpp.py: a syntactic GLSL -> C++ rewrite over glsl_shim.h) into a temporary directory and
+// compiles this file into oracle/_ref/libpfshader.so. The entry points bind the shaders' buffers / textures / uniforms to host
 // memory exactly as RendererD3D11 binds them (core/d3d11/renderer.cpp:365-448 draw_tiles, :959-1002 draw_fills) and
 // run every work group, one invocation after the other. What comes out is the reference's GPU-driven pixel pipeline
 // evaluated in IEEE fp32 -- the thing tests/ pins oracle/pf_oracle.c's fill / tile restatement against.
