@@ -66,6 +66,34 @@ def expected(linear, repeat_u):
     return out
 
 
+def expected_integers():
+    """integerProbe() of tests/glsl/probe.comp in plain Python integers, over two runs of the 8 invocations."""
+    def s16(v):
+        return v - 0x10000 if v & 0x8000 else v
+
+    counters, signed = [0] * 9, [-5, 9]
+    for _ in range(2):
+        for y in range(2):
+            for x in range(4):
+                w = WORDS[x + 4 * y]
+                wi = w - (1 << 32) if w & 0x80000000 else w
+                r = [s16(w & 0xffff), wi >> 16, 7, -3]
+                t = [r[0] + 2, r[1] + 1]
+                u = [int(max(np.float32(np.float32(v * 3) * np.float32(0.5) + np.float32(64.0)), np.float32(0))) for v in (t[0], t[1], t[0], t[1])]
+                outside = [t[0] < r[2], t[1] < r[3], t[0] >= r[2], t[1] >= r[3]]
+                slot = counters[0]
+                counters[0] += 2
+                before = signed[0]
+                signed[0] = max(signed[0], t[0])
+                swapped = signed[1]
+                signed[1] = t[1]
+                d = (u[2] - u[0]) & 0xffffffff
+                val = (slot + (100 if any(outside) else 0) + (1000 if all(outside) else 0) + (before & 0xff) * 10000 +
+                       (swapped & 0xf) * 1000000 + d + u[3]) & 0xffffffff
+                counters[1 + x + 4 * y] = val
+    return counters, signed
+
+
 def test_probe_shader_through_the_shim(tmp_path):
     inc = tmp_path / "probe_comp.inc"
     with open(inc, "w") as fp:
@@ -78,5 +106,11 @@ def test_probe_shader_through_the_shim(tmp_path):
     for variant, (linear, repeat_u) in enumerate(((True, False), (False, True))):
         got = np.array([int(v) for v in lines[variant].split()], np.uint8).reshape(2, 4, 4)
         assert np.array_equal(got, expected(linear, repeat_u)), (variant, got, expected(linear, repeat_u))
+    # integer vectors / atomics: both variants ran, 8 invocations each, on the same counters
+    got_counters = [int(v) for v in lines[2].split()]
+    got_signed = [int(v) for v in lines[3].split()]
+    want_counters, want_signed = expected_integers()
+    assert got_counters == want_counters and got_signed == want_signed, (got_counters, want_counters, got_signed, want_signed)
+    lines = lines[:2] + lines[4:]
     # 1e-7 off the centre of texel (1, 0): exactly that texel
     assert np.array_equal(np.array([float(v) for v in lines[2].split()], f32), TEX[0, 1])
