@@ -46,4 +46,5 @@ def test_product_does_not_touch_oracle():
             for f in files:
                 if f.endswith((".cu", ".h", ".cpp", ".py", "Makefile")):
                     text = open(os.path.join(dirpath, f), errors="ignore").read()
-                    assert "pforacle" not in text and "pfref" not in text and "libpforacle" not in text, f
+                    for word in ("pforacle", "pfref", "libpforacle", "pfshader", "glsl_shim"):
+                        assert word not in text, (f, word)
