@@ -139,7 +139,11 @@ def reference_cpu(asset, size, native, steps, warmup, budget_s=20.0):
         # The reference's builder runs 4 worker threads, hard-coded (core/d3d9/scene_builder.cpp:13). To give it every host
         # core, independent frames are built side by side, one unmodified 4-thread builder per 4 cores -- the CPU
         # counterpart of our frames in flight.
-        builders = max(1, (os.cpu_count() or 4) // 4)
+        try:
+            host_cores = len(os.sched_getaffinity(0))  # the cores this process may run on
+        except AttributeError:
+            host_cores = os.cpu_count() or 4
+        builders = max(1, min(host_cores // 4, 64))
         handles = [make() for _ in range(builders)]
         handles[0].time_d3d9_build(max(warmup, 1))
         probe = float(np.median(handles[0].time_d3d9_build(3)))
