@@ -209,6 +209,15 @@ int pfcu_read_target(pfcu_ctx *ctx, uint8_t *host_rgba8);                    /* 
  * packed; a region that is empty or not inside the target is PFCU_ERR_INVALID (the reference logs and returns). */
 int pfcu_read_target_region(pfcu_ctx *ctx, int x, int y, int width, int height, uint8_t *host_rgba8);
 int pfcu_read_page(pfcu_ctx *ctx, uint32_t page, uint8_t *host_rgba8);
+/* The same read-back without blocking (replaces CommandEncoder::read_texture + the fence wait of Queue::submit_and_wait,
+ * gpu/command_encoder.cpp:317-355, gpu/vk/queue.cpp:29-35): enqueues the device-to-host copy of the whole target behind the
+ * frame in flight, on the context's copy stream, and returns. host_rgba8 should be page-locked (pfcu_host_alloc);
+ * host_pitch_bytes 0 = tightly packed. pfcu_wait_read blocks until the pixels are in host memory. A later frame on the same
+ * context waits (on the device) for the copy before it overwrites the target; other contexts keep rendering. */
+int pfcu_read_target_async(pfcu_ctx *ctx, uint8_t *host_rgba8, size_t host_pitch_bytes);
+int pfcu_wait_read(pfcu_ctx *ctx);
+void *pfcu_host_alloc(size_t bytes); /* page-locked host memory; NULL + pfcu_last_error() on failure */
+void pfcu_host_free(void *p);
 void *pfcu_target_device_ptr(pfcu_ctx *ctx, size_t *pitch_bytes);            /* zero-copy consumers */
 
 /* ---- parity taps: pass NULL to query the element count. Valid after pfcu_end_frame. */

@@ -8,6 +8,7 @@
 #include <memory>
 #include <string>
 
+#include "demo_scene.h"
 #include "host_device.h"
 #include "pathfinder/common/logger.h"
 #include "pathfinder/core/canvas.h"
@@ -54,6 +55,42 @@ int pfref_cuda_render_svg(const char *svg, size_t len, int width, int height, fl
         return 0;
     } catch (const std::exception &e) {
         Logger::error(std::string("pfref_cuda_render_svg: ") + e.what());
+        return -2;
+    }
+}
+
+/// The demo's primitives scene (demo_scene.h: clip circle, blurred shadow through two render-target passes, image pattern,
+/// gradient stroke, render-target pattern) through RendererCuda: clip batches in reverse, pattern pages, color_texture_info.
+/// `frames` frames are drawn; when `load_last` is set, the last one is drawn with clear_dst_texture = false (the reference's
+/// LOAD_ACTION_LOAD: it blends over what the previous frame left in the destination, d3d11/renderer.cpp:382-386).
+int pfref_cuda_render_demo(int width, int height, float scale, int features, int cuda_device, int frames, int load_last,
+                           uint8_t *out, pfcu_frame_stats *stats) {
+    try {
+        Logger::set_global_level(Logger::Level::Error);
+        auto device = std::make_shared<HostDevice>();
+        auto queue = std::make_shared<HostQueue>();
+        auto canvas = std::make_shared<Canvas>(Vec2I(width, height), device, queue, RenderMode::Hybrid);
+        extern const char _binary_sea_png_start[], _binary_sea_png_end[];
+        pfref::draw_demo_scene(canvas, width, height, scale, _binary_sea_png_start,
+                               (size_t)(_binary_sea_png_end - _binary_sea_png_start), features);
+        auto scene = canvas->get_scene();
+        auto renderer = std::make_shared<RendererCuda>(device, queue, cuda_device);
+        auto scene_builder = std::make_shared<SceneBuilderD3D11>();
+        renderer->set_up_pipelines();
+        auto dest = device->create_texture({Vec2I(width, height), TextureFormat::Rgba8Unorm}, "dest texture");
+        renderer->set_dest_texture(dest);
+        const int n = frames > 0 ? frames : 1;
+        for (int f = 0; f < n; f++) {
+            scene_builder->build(scene.get(), renderer.get());
+            renderer->draw(scene_builder, !(load_last && f == n - 1));
+            renderer->reset();
+        }
+        renderer->read_dest_texture();
+        if (out) memcpy(out, static_cast<HostTexture *>(dest.get())->bytes.data(), (size_t)width * height * 4);
+        if (stats) *stats = renderer->last_frame_stats();
+        return 0;
+    } catch (const std::exception &e) {
+        Logger::error(std::string("pfref_cuda_render_demo: ") + e.what());
         return -2;
     }
 }

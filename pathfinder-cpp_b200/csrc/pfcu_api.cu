@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler attaches
+
 #include "pfcu_device.h"
 
 using namespace pfcu;
@@ -132,6 +134,12 @@ struct pfcu_ctx {
     size_t sync_used = 0;
     cudaEvent_t aux_pending = nullptr;  // last event recorded on the aux stream that the main stream has not waited for
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    // asynchronous read-back of the target (pfcu_read_target_async): its own stream, ordered after the frame by an event
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_frame_done = nullptr, ev_copy_done = nullptr;
+    bool read_pending = false;  // a D2H copy of the target may still be running: the next frame's writes wait for it
+    uint8_t *read_host = nullptr;  // ... into this buffer (re-issued if the frame it was enqueued behind is replayed)
+    size_t read_pitch = 0;
     // static resources
     DevBuf lut;
     int lut_w = 0, lut_h = 0;
@@ -261,8 +269,19 @@ int join_aux(pfcu_ctx *c) {
     return PFCU_OK;
 }
 
+const char *const STAGE_NAMES[PFCU_NUM_STAGES] = {"pfcu:init (bound)", "pfcu:dice", "pfcu:bin", "pfcu:scan tiles",
+                                                 "pfcu:fill scatter", "pfcu:propagate", "pfcu:scan fb", "pfcu:list scatter (sort)",
+                                                 "pfcu:fill", "pfcu:tile (composite)"};
+
+// NVTX range over a scope (Nsight Systems / ncu --nvtx show the API call or stage around the kernels it enqueues)
+struct NvtxScope {
+    explicit NvtxScope(const char *name) { nvtxRangePushA(name); }
+    ~NvtxScope() { nvtxRangePop(); }
+};
+
 #define LAUNCH_STAGE(stage, expr)        \
     do {                                 \
+        NvtxScope _nvtx(STAGE_NAMES[stage]); \
         CUDA_TRY(expr);                  \
         int _r = prof_mark(c, stage);    \
         if (_r) return _r;               \
@@ -370,6 +389,9 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.frame_alpha_counter = frame_alpha_counter(c);
     v.masks = c->masks.as<uint8_t>();
     v.mask_capacity = c->mask_cap;
+    v.paints = c->paints.as<Paint>();
+    v.n_paints = c->n_paints;
+    v.solid_prims = c->all_solid;
     s.view = v;
     s.prepared = true;
 
@@ -575,6 +597,9 @@ int pfcu_create(int device_ordinal, pfcu_ctx **out) {
     c->stream = c->own_stream;
     CUDA_TRY(cudaEventCreate(&c->ev_begin));
     CUDA_TRY(cudaEventCreate(&c->ev_end));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_frame_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_copy_done, cudaEventDisableTiming));
     CUDA_TRY(c->counters.ensure(sizeof(BatchCounters) * (MAX_SLOTS + 1)));
     CUDA_TRY(cudaMemset(c->counters.p, 0, sizeof(BatchCounters) * (MAX_SLOTS + 1)));
     CUDA_TRY(c->host_counters.ensure(sizeof(BatchCounters) * (MAX_SLOTS + 1)));
@@ -590,6 +615,7 @@ void pfcu_destroy(pfcu_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->aux_stream);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
     for (auto &s : c->slots) {
         s.host_meta.release();
         for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_begin, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
@@ -618,6 +644,9 @@ void pfcu_destroy(pfcu_ctx *c) {
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     cudaEventDestroy(c->ev_begin);
     cudaEventDestroy(c->ev_end);
+    cudaEventDestroy(c->ev_frame_done);
+    cudaEventDestroy(c->ev_copy_done);
+    cudaStreamDestroy(c->copy_stream);
     drop_retained(c);
     for (cudaEvent_t e : c->sync_events) cudaEventDestroy(e);
     cudaStreamDestroy(c->aux_stream);
@@ -682,17 +711,25 @@ int pfcu_set_area_lut(pfcu_ctx *c, const uint8_t *rgba, int width, int height) {
 int pfcu_set_target(pfcu_ctx *c, int width, int height, void *rgba8_dev, size_t pitch_bytes, const float view_box[4]) {
     if (!c || width <= 0 || height <= 0 || !view_box) return fail(PFCU_ERR_INVALID, "bad target");
     CUDA_TRY(cudaSetDevice(c->device));
-    int r = sync_if_in_flight(c);
-    if (r) return r;
+    if (c->frame_open) return fail(PFCU_ERR_STATE, "the target cannot change inside a frame");
     if (rgba8_dev) {
         if (pitch_bytes < (size_t)width * 4 || (pitch_bytes & 15) || ((uintptr_t)rgba8_dev & 15))
             return fail(PFCU_ERR_INVALID, "target rows must be 16-byte aligned and at least width*4 bytes");
         c->target.pixels = static_cast<uint8_t *>(rgba8_dev);
         c->target.pitch = pitch_bytes;
     } else {
+        // The context's own target keeps its contents from frame to frame (LOAD_ACTION_LOAD draws over the previous
+        // frame, d3d11/renderer.cpp:382-386); it is zeroed only when it is (re)allocated.
         const size_t pitch = ((size_t)width * 4 + 15) & ~(size_t)15;
-        CUDA_TRY(c->own_target.ensure(pitch * height));
-        CUDA_TRY(cudaMemsetAsync(c->own_target.p, 0, pitch * height, c->stream));
+        const bool same = c->target.pixels == c->own_target.as<uint8_t>() && c->own_target.p && c->target.width == width &&
+                          c->target.height == height && c->target.pitch == pitch;
+        if (!same) {
+            int r = sync_if_in_flight(c);  // (frames in flight may still write the old buffer)
+            if (r) return r;
+            CUDA_TRY(c->own_target.ensure(pitch * height));
+            CUDA_TRY(cudaMemsetAsync(c->own_target.p, 0, pitch * height, c->stream));
+            c->in_flight = true;
+        }
         c->target.pixels = c->own_target.as<uint8_t>();
         c->target.pitch = pitch;
     }
@@ -714,6 +751,7 @@ int pfcu_set_target_origin(pfcu_ctx *c, int origin_x, int origin_y) {
 
 int pfcu_upload_scene(pfcu_ctx *c, int which, const float *points, uint32_t n_points, const uint32_t *indices,
                       uint32_t n_segments) {
+    NvtxScope nvtx("pfcu_upload_scene");
     if (!c || which < 0 || which > 1 || (n_points && !points) || (n_segments && !indices))
         return fail(PFCU_ERR_INVALID, "bad scene upload");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -763,6 +801,7 @@ static float half_bits_to_float(uint16_t h) {
 }
 
 int pfcu_upload_paint_metadata(pfcu_ctx *c, const uint16_t *half_texels, uint32_t n_rows) {
+    NvtxScope nvtx("pfcu_upload_paint_metadata");
     if (!c || (n_rows && !half_texels)) return fail(PFCU_ERR_INVALID, "bad metadata upload");
     CUDA_TRY(cudaSetDevice(c->device));
     int r = sync_if_in_flight(c);
@@ -789,6 +828,11 @@ int pfcu_upload_paint_metadata(pfcu_ctx *c, const uint16_t *half_texels, uint32_
         p.fp1 = texel(4);
         p.ctrl = (int32_t)texel(8).x;  // int(extra.x), tile.comp:725
         if (p.ctrl != 0) all_solid = 0;
+        // tile.comp:184-227,394-404 also has a text (0x2) and a colour-matrix (0x4) filter; upstream never emits them
+        // (paint/palette.cpp:65-67) and they are not implemented here: refuse rather than sample the texture unfiltered
+        const int filter = (p.ctrl >> 4) & 0xf;
+        if (((p.ctrl >> 8) & 0x3) != 0 && filter != 0x0 && filter != 0x1 && filter != 0x3)
+            return fail(PFCU_ERR_INVALID, "paint %u uses filter %d: only none / radial gradient / blur are implemented", i, filter);
         for (float v : {p.base.x, p.base.y, p.base.z, p.base.w})
             if (!(v >= 0.0f && v <= 1.0f)) unit_range = 0;
         table[i] = p;
@@ -832,8 +876,13 @@ int pfcu_upload_page_region(pfcu_ctx *c, uint32_t page, int x, int y, int width,
 int pfcu_begin_frame(pfcu_ctx *c) {
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     if (!c->target.pixels) return fail(PFCU_ERR_STATE, "pfcu_set_target has not been called");
+    if (!c->lut_tex) return fail(PFCU_ERR_STATE, "pfcu_set_area_lut has not been called (the fill stage has no coverage table)");
     if (c->frame_pending) return fail(PFCU_ERR_STATE, "a submitted frame has not been waited for");
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->read_pending) {  // the copy engine is still reading the target this frame is about to overwrite
+        CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_copy_done, 0));
+        c->read_pending = false;
+    }
     for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
     c->slots_used = 0;
     c->cmds.clear();
@@ -850,6 +899,7 @@ int pfcu_begin_frame(pfcu_ctx *c) {
 }
 
 int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
+    NvtxScope nvtx("pfcu_prepare_batch");
     if (!c || !d) return fail(PFCU_ERR_INVALID, "null argument");
     if (!c->frame_open) return fail(PFCU_ERR_STATE, "pfcu_begin_frame has not been called");
     if (c->slots_used >= MAX_SLOTS) return fail(PFCU_ERR_INVALID, "too many batches in one frame");
@@ -857,6 +907,22 @@ int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
         (d->column_count && !d->backdrops))
         return fail(PFCU_ERR_INVALID, "batch metadata missing");
     if (d->tile_count >= (1u << 24)) return fail(PFCU_ERR_INVALID, "tile_count exceeds the 24-bit alpha tile id range");
+    if (d->segment_count && !d->path_count) return fail(PFCU_ERR_INVALID, "a batch with segments needs at least one path");
+    // the kernels index the dense tile maps and the column backdrops straight from this metadata: check it once, here
+    for (uint32_t i = 0; i < d->path_count; i++) {
+        const pfcu_propagate_metadata &m = d->propagate_metadata[i];
+        const int64_t w = (int64_t)m.tile_rect[2] - m.tile_rect[0], h = (int64_t)m.tile_rect[3] - m.tile_rect[1];
+        if (w <= 0 || h <= 0) continue;  // an empty rect owns no tiles
+        if ((uint64_t)m.tile_offset + (uint64_t)(w * h) > d->tile_count)
+            return fail(PFCU_ERR_INVALID, "path %u: tile_offset %u + %lld x %lld tiles exceeds tile_count %u", i, m.tile_offset,
+                        (long long)w, (long long)h, d->tile_count);
+        if ((uint64_t)m.backdrop_offset + (uint64_t)w > d->column_count)
+            return fail(PFCU_ERR_INVALID, "path %u: backdrop_offset %u + %lld columns exceeds column_count %u", i,
+                        m.backdrop_offset, (long long)w, d->column_count);
+    }
+    for (uint32_t i = 0; i < d->column_count; i++)
+        if (d->backdrops[i].path_index >= d->path_count)
+            return fail(PFCU_ERR_INVALID, "backdrop column %u names path %u of %u", i, d->backdrops[i].path_index, d->path_count);
     CUDA_TRY(cudaSetDevice(c->device));
     const int slot_index = c->slots_used;
     BatchSlot &s = c->slots[slot_index];
@@ -915,6 +981,7 @@ int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
 
 int pfcu_draw_batch(pfcu_ctx *c, uint32_t batch_id, int target_page, int color_page, uint32_t sampling_flags, int clear,
                     const float clear_color[4]) {
+    NvtxScope nvtx("pfcu_draw_batch");
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     if (!c->frame_open) return fail(PFCU_ERR_STATE, "pfcu_begin_frame has not been called");
     const int slot = find_slot(c, batch_id);
@@ -944,6 +1011,7 @@ static int enqueue_frame_tail(pfcu_ctx *c) {
 }
 
 int pfcu_submit_frame(pfcu_ctx *c) {
+    NvtxScope nvtx("pfcu_submit_frame");
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     if (!c->frame_open) return fail(PFCU_ERR_STATE, "no frame is open");
     if (c->frame_pending) return fail(PFCU_ERR_STATE, "the frame has already been submitted");
@@ -988,6 +1056,7 @@ int pfcu_submit_frame(pfcu_ctx *c) {
 }
 
 int pfcu_wait_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
+    NvtxScope nvtx("pfcu_wait_frame");
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     if (!c->frame_pending) return fail(PFCU_ERR_STATE, "no frame has been submitted");
     CUDA_TRY(cudaSetDevice(c->device));
@@ -1047,6 +1116,14 @@ int pfcu_wait_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
                 return r;
             }
         }
+        if (c->read_pending) {  // a read-back was enqueued behind the attempt that overflowed: read the replayed frame
+            CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+            const int r = pfcu_read_target_async(c, c->read_host, c->read_pitch);
+            if (r) {
+                c->frame_open = false;
+                return r;
+            }
+        }
     }
     // Retain the frame: the second of two identical frames is captured, identical frames after it are one graph launch.
     if (c->auto_graph && !c->profiling && !served_by_graph && !c->retained_exec && attempts_used == 0 && sig &&
@@ -1064,6 +1141,8 @@ int pfcu_wait_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
         st.fills += hc[i].n_fills;
         st.dense_tiles += c->slots[i].desc.tile_count;
         st.listed_tiles += hc[i].n_list_entries;
+        st.listed_after_cull += hc[i].n_listed;
+        st.max_list_len = std::max(st.max_list_len, hc[i].max_list_len);
     }
     st.alpha_tiles = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
     st.fb_tiles = (uint32_t)(((c->target.width + TILE - 1) / TILE) * ((c->target.height + TILE - 1) / TILE));
@@ -1156,13 +1235,15 @@ int pfcu_graph_finish(pfcu_ctx *c, pfcu_frame_stats *stats) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     c->in_flight = false;
     pfcu_frame_stats st = c->last_stats;
-    st.lines = st.fills = st.listed_tiles = 0;
+    st.lines = st.fills = st.listed_tiles = st.listed_after_cull = st.max_list_len = 0;
     uint32_t overflow = 0;
     for (int i = 0; i < c->slots_used; i++) {
         overflow |= hc[i].overflow;
         st.lines += hc[i].n_lines;
         st.fills += hc[i].n_fills;
         st.listed_tiles += hc[i].n_list_entries;
+        st.listed_after_cull += hc[i].n_listed;
+        st.max_list_len = std::max(st.max_list_len, hc[i].max_list_len);
     }
     st.alpha_tiles = *reinterpret_cast<uint32_t *>(hc + MAX_SLOTS);
     if (st.alpha_tiles > c->mask_cap) overflow |= OVF_ALPHA;
@@ -1181,6 +1262,52 @@ int pfcu_read_target(pfcu_ctx *c, uint8_t *host) {
     CUDA_TRY(cudaMemcpy2D(host, (size_t)c->target.width * 4, c->target.pixels, c->target.pitch,
                           (size_t)c->target.width * 4, c->target.height, cudaMemcpyDeviceToHost));
     return PFCU_OK;
+}
+
+// CommandEncoder::read_texture + the fence wait of Queue::submit_and_wait (gpu/command_encoder.cpp:317-355,
+// gpu/vk/queue.cpp:29-35), split in two so that nothing blocks: the copy is enqueued on the context's copy stream behind
+// the frame that is in flight (submitted or not yet waited for) and runs on a copy engine while the SMs render the next
+// frame of ANOTHER context; a new frame on THIS context waits for the copy before it overwrites the target.
+int pfcu_read_target_async(pfcu_ctx *c, uint8_t *host, size_t host_pitch_bytes) {
+    if (!c || !host || !c->target.pixels) return fail(PFCU_ERR_INVALID, "no target");
+    if (c->frame_open && !c->frame_pending) return fail(PFCU_ERR_STATE, "submit or end the frame before reading it back");
+    const size_t row = (size_t)c->target.width * 4;
+    if (!host_pitch_bytes) host_pitch_bytes = row;
+    if (host_pitch_bytes < row) return fail(PFCU_ERR_INVALID, "host pitch smaller than a row");
+    CUDA_TRY(cudaSetDevice(c->device));
+    NvtxScope nvtx("pfcu_read_target_async");
+    CUDA_TRY(cudaEventRecord(c->ev_frame_done, c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->ev_frame_done, 0));
+    CUDA_TRY(cudaMemcpy2DAsync(host, host_pitch_bytes, c->target.pixels, c->target.pitch, row, c->target.height,
+                               cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_TRY(cudaEventRecord(c->ev_copy_done, c->copy_stream));
+    c->read_pending = true;
+    c->read_host = host;
+    c->read_pitch = host_pitch_bytes;
+    return PFCU_OK;
+}
+
+int pfcu_wait_read(pfcu_ctx *c) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventSynchronize(c->ev_copy_done));  // (returns at once when no read was ever enqueued)
+    c->read_pending = false;
+    return PFCU_OK;
+}
+
+// Page-locked host memory for pfcu_read_target_async / the upload calls (a pageable destination makes the copy
+// synchronous and three times slower). Plain C callers need no CUDA headers.
+void *pfcu_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        fail(PFCU_ERR_OOM, "cudaMallocHost(%zu) failed", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void pfcu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 int pfcu_read_target_region(pfcu_ctx *c, int x, int y, int width, int height, uint8_t *host) {
@@ -1357,7 +1484,7 @@ int64_t pfcu_read_tile_lists(pfcu_ctx *c, uint32_t batch_id, uint32_t *offsets, 
         // the scatter only places what the z-buffer does not cull: `cursor` entries of the `count` slots are in use
         const uint32_t begin = std::min(fb[t].begin, D), end = std::min(fb[t].begin + std::min(fb[t].cursor, fb[t].count), D);
         keys.clear();
-        for (uint32_t k = begin; k < end; k++) keys.push_back(prims[k].key);
+        for (uint32_t k = begin; k < end; k++) keys.push_back(prims[k].key & 0x00ffffffu);  // (high byte: LayerFlags)
         std::sort(keys.begin(), keys.end());
         if (tiles) memcpy(tiles + total, keys.data(), keys.size() * 4);
         total += (int64_t)keys.size();

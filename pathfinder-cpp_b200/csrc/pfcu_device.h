@@ -30,7 +30,9 @@ struct BatchCounters {
     uint32_t scan_ticket[2];  // dynamic tile ids for the two look-back scans
     uint32_t n_list_entries;  // total list entries (from the scan over framebuffer tiles)
     uint32_t n_long;          // lines queued for the long-line bin kernel
-    uint32_t pad[6];
+    uint32_t n_listed;        // list entries that survive the z-cull (placed by the list scatter)
+    uint32_t max_list_len;    // longest list after the z-cull
+    uint32_t pad[4];
 };
 static_assert(sizeof(BatchCounters) == 64, "BatchCounters");
 
@@ -55,12 +57,35 @@ struct StagedFill {
 };
 
 // One entry of a framebuffer tile's list: everything tile.comp reads per layer (tile.comp:765-768), one 16-byte load.
+// Two formats, chosen per frame by BatchView::solid_prims:
+//   general  : key, mask slot, paint | ctrl << 16 | backdrop << 24, 0  -- the tile kernel looks the paint up
+//   resolved : key | LayerFlags << 24, mask slot, base colour as four halfs (r | g << 16, b | a << 16) -- every paint of
+//              the frame is a plain colour (ctrl == 0): the list scatter resolves the layer completely, the tile kernel
+//              reads nothing but this record (the metadata texels ARE halfs, core/renderer.cpp:176, so this is lossless)
 struct TilePrim {
-    uint32_t key;        // dense tile index: sort key == paint order
+    uint32_t key;        // dense tile index (< 2^24, pfcu_prepare_batch checks): sort key == paint order
     int32_t alpha;       // mask slot or -1
-    uint32_t ctrl_word;  // paint | ctrl << 16 | backdrop << 24
-    uint32_t pad;
+    uint32_t ctrl_word;  // general: paint | ctrl << 16 | backdrop << 24; resolved: r | g << 16
+    uint32_t pad;        // resolved: b | a << 16
 };
+
+enum LayerFlags : uint32_t {
+    LF_TEXTURED = 1,  // the paint is not a plain colour (gradient, image, blur, blend mode): per-pixel shading
+    LF_MASKED = 2,    // coverage comes from a mask
+    LF_SKIP = 4,      // solid tile of an even-odd path with an even backdrop: invisible (tile.comp:786-792)
+    LF_HEAVY = 8,     // blur filter: thousands of instructions per pixel -- the tile is split over the CTA's warps
+    LF_EVEN_ODD = 16  // the mask is folded 1 - |1 - mod(c, 2)| when it is sampled (tile.comp:601-602)
+};
+
+// tile.comp:765-792 for one list entry: which of the cases above apply (paint-independent part)
+__host__ __device__ __forceinline__ uint32_t layer_flags(int alpha, uint32_t ctrl, int backdrop, uint32_t mask_capacity) {
+    if (alpha >= 0) {
+        if (!(ctrl & 0x3u) || (uint32_t)alpha >= mask_capacity) return 0u;
+        return (uint32_t)LF_MASKED | ((ctrl & 0x1u) ? 0u : (uint32_t)LF_EVEN_ODD);
+    }
+    const int ab = backdrop < 0 ? -backdrop : backdrop;
+    return (backdrop != 0 && (ctrl & 0x2u) && (ab & 1) == 0) ? (uint32_t)LF_SKIP : 0u;
+}
 
 // Per framebuffer tile: list range + z (one 16-byte load in the composite kernel).
 struct FbTile {
@@ -138,6 +163,10 @@ struct BatchView {
                                     // (q & 3), row (lane >> 2) * 2 + (q >> 2)), so a warp stores / loads a mask with
                                     // one 8-byte access per lane and owns the same pixels as 16-byte framebuffer pieces
     uint32_t mask_capacity;         // slots
+    // paints (the list scatter resolves plain colours into the list entries)
+    const struct Paint *paints;
+    uint32_t n_paints;
+    int solid_prims;                // every paint of the frame is a plain colour: list entries carry the colour (TilePrim)
 };
 
 struct TargetView {
@@ -175,7 +204,9 @@ cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s);
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
                              const float clear_color[4], int origin, int heavy_paints, cudaStream_t s);
 
-int sm_count();
+constexpr int MAX_DEVICES = 64;
+int current_device();  // clamped to [0, MAX_DEVICES)
+int sm_count();        // of the current device
 
 // Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while the previous kernel of its
 // stream is still draining (its CTAs are placed and run up to pdl_wait(), which returns once that kernel has completed

@@ -535,12 +535,13 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chu
 
 template <int Q, int O>
 static cudaError_t launch_dice_cfg(const BatchView &b, cudaStream_t s, uint32_t ctas_per_sm, uint32_t max_chunk) {
-    static bool configured = false;  // (one per instantiation)
-    if (!configured) {
+    static bool configured[MAX_DEVICES] = {};  // (one per instantiation and device: function attributes are per device)
+    const int dev = current_device();
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_dice<Q, O>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)sizeof(DiceSharedT<Q, O>));
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     // Segments per CTA and pass: few segments -> small chunks (every SM gets one, deep trees fit the queue);
     // many segments -> large chunks (fewer block-wide barriers per segment).

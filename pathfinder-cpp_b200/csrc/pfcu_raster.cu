@@ -18,8 +18,6 @@
 //          registers with packed f32x2 arithmetic and stores 16 bytes per lane and row.
 #include <cuda_fp16.h>
 
-#include <cstdlib>
-
 #include "pfcu_device.h"
 
 namespace pfcu {
@@ -546,25 +544,19 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 
+
 #ifndef CT_WARPS_N
 #define CT_WARPS_N 4
 #endif
 #ifndef CT_MIN_CTAS
-#define CT_MIN_CTAS (28 / CT_WARPS_N)  // 7 CTAs per SM = 72 registers per thread, no spills: 31.2 us against 33.2 us at 6 CTAs (78 registers); 64 registers spill
+#define CT_MIN_CTAS (28 / CT_WARPS_N)  // 7 CTAs per SM = 72 registers per thread (6: 78 registers measured 2 us slower; 64 registers spill)
 #endif
-#define CT_MIN_CTAS_TEX (CT_MIN_CTAS / 2)  // gradients / images / blend modes: 128 registers
+#define CT_MIN_CTAS_TEX 4  // gradients / images / blend modes: up to 168 registers
 constexpr int CT_WARPS = CT_WARPS_N;   // warps per CTA
 constexpr int CT_THREADS = CT_WARPS * 32;
-constexpr int CT_TILES = CT_WARPS * 4; // consecutive framebuffer tiles a CTA renders (8 threads order one tile's list)
-constexpr int CT_PRIMS = 256;          // list entries staged at a time (more: the CTA takes its tiles in several rounds)
-
-enum LayerFlags : uint32_t {
-    LF_TEXTURED = 1,  // the paint is not a plain colour (gradient, image, blur, blend mode): per-pixel shading
-    LF_MASKED = 2,    // coverage comes from a mask
-    LF_SKIP = 4,      // solid tile of an even-odd path with an even backdrop: invisible (tile.comp:786-792)
-    LF_HEAVY = 8      // blur filter: thousands of instructions per pixel -- the tile is split over the CTA's warps
-};
-
+constexpr int CT_TILES = CT_WARPS * 4; // consecutive framebuffer tiles of one group (8 threads order one tile's list)
+constexpr int CT_PRIMS = 256;          // list entries staged per group (more: the CTA takes the group in several rounds)
+constexpr uint32_t KEY_MASK = 0x00ffffffu;
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
     return __byte_perm(__byte_perm(unorm8_bits(__saturatef(c.x)), unorm8_bits(__saturatef(c.y)), 0x0040),
                        __byte_perm(unorm8_bits(__saturatef(c.z)), unorm8_bits(__saturatef(c.w)), 0x0040), 0x5410);
@@ -585,6 +577,13 @@ __device__ __forceinline__ void blend_over(float4 &dest, const float4 &src) {  /
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// base colour of a resolved list entry (TilePrim): four halfs -> floats, exact
+__device__ __forceinline__ float4 prim_color(const uint4 u) {
+    const float2 rg = __half22float2(*reinterpret_cast<const __half2 *>(&u.z));
+    const float2 ba = __half22float2(*reinterpret_cast<const __half2 *>(&u.w));
+    return make_float4(rg.x, rg.y, ba.x, ba.y);
+}
 
 // The lane's 8 pixels, channel-major in pairs: pair j holds pixels 2j and 2j+1 (pixel q = column 4k + (q & 3) of row
 // 2s + (q >> 2)), so every blend is a packed f32x2 operation with a per-layer constant or a per-pixel alpha.
@@ -660,16 +659,17 @@ __device__ __forceinline__ float2 mask_pair(uint2 mask8, int j, bool even_odd) {
     return c;
 }
 
+template <bool SOLID>
 struct __align__(16) CompositeShared {
-    uint4 fb[CT_TILES];             // list begin, slots (count before z-cull), z, entries
-    uint4 raw[CT_PRIMS];            // the lists as the scatter left them
-    uint4 sorted[CT_PRIMS];         // in paint order: key, mask slot, paint | ctrl << 16 | backdrop << 24, LayerFlags
-    float4 color[CT_PRIMS];         // base colour of the layer's paint
-    float4 start_color[CT_TILES];   // the tile's colour after its leading whole-tile layers
-    uint32_t start_layer[CT_TILES]; // first layer that needs per-pixel work
+    uint4 fb[CT_TILES];                // list begin, slots (count before z-cull), z, entries
+    uint4 raw[CT_PRIMS];               // the lists as the scatter left them
+    uint4 sorted[CT_PRIMS];            // in paint order, resolved: key | LayerFlags << 24, mask slot, colour (4 halfs)
+    float4 start_color[CT_TILES];      // the tile's colour after its leading whole-tile layers
+    uint32_t start_layer[CT_TILES];    // first layer that needs per-pixel work
     uint32_t packed_color[CT_TILES];
-    uint32_t txy[CT_TILES];         // tile x | tile y << 16
-    uint16_t work[CT_TILES * 4];    // per-pixel work items: tile | pixel pairs (bit j = pair j of every lane) << 8
+    uint32_t txy[CT_TILES];            // tile x | tile y << 16
+    uint16_t paint[SOLID ? 8 : CT_PRIMS]; // paint of every layer (textured layers look their constants up at blend time)
+    uint16_t work[CT_TILES * 4];       // per-pixel work items: tile | pixel pairs (bit j = pair j of every lane) << 8
     uint32_t n_work, next, flat_mask;
 };
 
@@ -680,21 +680,48 @@ struct TileGeom {
     float fragx, fragy; // gl_FragCoord of the lane's first pixel on the full canvas
 };
 
-// One layer over the lane's 8 pixels (tile.comp:765-842 for one list entry).
+// A general-format list entry (key, mask slot, paint | ctrl << 16 | backdrop << 24) resolved against the paint table:
+// key | LayerFlags << 24, mask slot, base colour as halfs. Frames whose paints are all plain colours get this from the list
+// scatter already (BatchView::solid_prims).
 template <bool SOLID>
-__device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 q, const float4 base, const BatchView &b,
+__device__ __forceinline__ uint4 resolve_prim(const uint4 q, const BatchView &b, const PaintView &p, uint32_t &paint) {
+    if (SOLID || b.solid_prims) {
+        paint = 0;
+        return q;
+    }
+    paint = q.z & 0xffffu;
+    uint32_t fl = layer_flags((int)q.y, (q.z >> 16) & 0xffu, (int)q.z >> 24, b.mask_capacity);
+    float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (paint < p.n_paints) {
+        base = __ldg(&p.paints[paint].base);
+        const int ctrl = __ldg(&p.paints[paint].ctrl);
+        if (ctrl != 0) fl |= LF_TEXTURED;
+        if (((ctrl >> 8) & 0x3) != 0 && ((ctrl >> 4) & 0xf) == 0x3) fl |= LF_HEAVY;
+    }
+    const __half2 rg = __floats2half2_rn(base.x, base.y), ba = __floats2half2_rn(base.z, base.w);
+    return make_uint4((q.x & KEY_MASK) | (fl << 24), q.y, *reinterpret_cast<const uint32_t *>(&rg), *reinterpret_cast<const uint32_t *>(&ba));
+}
+
+// One layer over the lane's 8 pixels (tile.comp:765-842 for one list entry).
+// the lane's 8 coverage bytes of a layer (all ones for a layer without a mask)
+__device__ __forceinline__ uint2 load_mask(const uint4 u, const BatchView &b, unsigned lane) {
+    if (!(u.x & ((uint32_t)LF_MASKED << 24)) || (u.x & ((uint32_t)LF_SKIP << 24))) return make_uint2(0xffffffffu, 0xffffffffu);
+    return __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)u.y * 256) + lane);
+}
+
+template <bool SOLID>
+__device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 u, const uint2 mask8, uint32_t paint, const BatchView &b,
                                             const PaintView &p, const ColorSampler &cs, const TileGeom &g,
                                             const TargetView &tg, unsigned lane, uint32_t pairs = 0xfu) {
-    const uint32_t fl = q.w;
+    const uint32_t fl = u.x >> 24;
     if (fl & LF_SKIP) return;
     const bool masked = (fl & LF_MASKED) != 0, textured = !SOLID && (fl & LF_TEXTURED) != 0;
+    const float4 base = prim_color(u);
     if (!masked && !textured) {  // one premultiplied colour over the whole tile (calculateColor with maskAlpha == 1)
         px.over_all(make_float4(base.x * base.w, base.y * base.w, base.z * base.w, base.w));
         return;
     }
-    uint2 mask8 = make_uint2(0xffffffffu, 0xffffffffu);
-    if (masked) mask8 = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)q.y * 256) + lane);
-    const bool even_odd = masked && !((q.z >> 16) & 0x1u);
+    const bool even_odd = (fl & LF_EVEN_ODD) != 0;
     if (!textured) {
         const float2 bx = splat(base.x), by = splat(base.y), bz = splat(base.z), bw = splat(base.w);
 #pragma unroll
@@ -706,13 +733,12 @@ __device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 q, const
     }
     if (!SOLID) {
         Paint pc;
-        const uint32_t color_entry = q.z & 0xffffu;
         pc.base = base;
-        pc.m0 = __ldg(&p.paints[color_entry].m0);
-        pc.m1 = __ldg(&p.paints[color_entry].m1);
-        pc.fp0 = __ldg(&p.paints[color_entry].fp0);
-        pc.fp1 = __ldg(&p.paints[color_entry].fp1);
-        pc.ctrl = __ldg(&p.paints[color_entry].ctrl);
+        pc.m0 = __ldg(&p.paints[paint].m0);
+        pc.m1 = __ldg(&p.paints[paint].m1);
+        pc.fp0 = __ldg(&p.paints[paint].fp0);
+        pc.fp1 = __ldg(&p.paints[paint].fp1);
+        pc.ctrl = __ldg(&p.paints[paint].ctrl);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             if (!((pairs >> j) & 1u)) continue;  // (a tile split over several warps: the other pairs are theirs)
@@ -762,25 +788,41 @@ __device__ __forceinline__ void load_block(PixelBlock &px, const TileGeom &g, co
     }
 }
 
-__device__ __forceinline__ uint32_t layer_flags(const uint4 q, uint32_t mask_capacity) {
-    const int alpha = (int)q.y, backdrop = (int)q.z >> 24;
-    const uint32_t ctrl = (q.z >> 16) & 0xffu;
-    if (alpha >= 0) return ((ctrl & 0x3u) && (uint32_t)alpha < mask_capacity) ? (uint32_t)LF_MASKED : 0u;
-    return (backdrop != 0 && (ctrl & 0x2u) && (abs(backdrop) & 1) == 0) ? (uint32_t)LF_SKIP : 0u;  // tile.comp:786-792
+__device__ __forceinline__ TileGeom tile_geom(uint32_t xy, unsigned lane, bool vec_ok, float org_x, float org_y, const TargetView &tg) {
+    TileGeom g;
+    const int tile_x = (int)(xy & 0xffffu), tile_y = (int)(xy >> 16);
+    g.gx0 = tile_x * TILE + (int)(lane & 3u) * 4;
+    g.gy0 = tile_y * TILE + (int)(lane >> 2) * 2;
+    g.interior = vec_ok && (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
+    g.px0 = tg.pixels + (size_t)g.gy0 * tg.pitch + (size_t)g.gx0 * 4;
+    g.fragx = (float)g.gx0 + org_x;
+    g.fragy = (float)g.gy0 + org_y;
+    return g;
 }
 
-// One CTA renders CT_TILES consecutive framebuffer tiles. The dependent loads of a tile (list header -> list -> paints
-// and masks) are issued for all of the CTA's tiles at once, so their latency is paid once per CTA; the lists are
-// ordered and classified by all threads (8 per tile); then the whole CTA stores the one-colour tiles and the warps
-// pull the remaining tiles from a shared counter, which balances deep lists against shallow ones.
-// Measured alternatives that lost on tiger 4096^2 (profiles/r01_tile_kernel_experiments.md): a persistent grid with a
-// device-wide ticket counter (39 us vs 31 us); a separate sort kernel that also stores the one-colour tiles and
-// compacts the others into a work list for a warp-per-tile blend kernel (21 + 24 us vs 33 us for this kernel alone).
+
+__device__ __forceinline__ uint4 clamp_header(uint4 f, uint32_t prim_capacity) {
+    if (f.x > prim_capacity) f.x = prim_capacity;
+    if (f.x + f.y > prim_capacity) f.y = prim_capacity - f.x;
+    f.w = min(f.w, f.y);  // entries the scatter wrote (it leaves out what the z-buffer culls)
+    return f;
+}
+
+// One CTA renders CT_TILES consecutive framebuffer tiles. The dependent loads of a tile (list header -> list -> masks) are
+// issued for all of the CTA's tiles at once, so their latency is paid once per CTA; the lists are ordered and classified by
+// all threads (8 per tile); then the whole CTA stores the one-colour tiles and the warps pull the remaining tiles from a
+// shared counter, which balances deep lists against shallow ones.
+// Measured alternatives that lost on tiger 4096^2 (profiles/r01_tile_kernel_experiments.md, profiles/r02_tile_kernel.md):
+// persistent grids (device-wide ticket; round 2: headers and lists prefetched two groups ahead by bulk copies into a
+// shared-memory ring -- the loads no longer stall anybody, the kernel is still slower, 43 us); 32 / 64 tiles per CTA with
+// headers and lists staged once by bulk copies (39 / 48 us); one warp per 2 / 4 / 8 tiles with no block-wide barrier at all
+// (41 - 50 us); a separate sort kernel + warp-per-tile blend kernel; streaming / evict-first / TMA tensor stores for the
+// framebuffer (no faster than plain 16-byte stores, tools/ubench/store_floor.cu).
 template <bool SOLID>
 __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_TEX) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
                                                                       float4 clear_color, int origin, uint32_t tiles_per_cta,
                                                                       uint32_t sub_tw, uint32_t sub_n) {
-    __shared__ CompositeShared sh;
+    __shared__ CompositeShared<SOLID> sh;
     pdl_wait();
     const unsigned tid = threadIdx.x, lane = tid & 31;
     // the CTA's tiles: tiles_per_cta consecutive tiles of the sub_tw-wide rectangle of the tile grid that the target
@@ -794,10 +836,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
         uint32_t xy = 0;
         if (tid < n_tiles) {
             const uint32_t at = map0 + tid, ty = at / sub_tw, tx = at - ty * sub_tw;
-            f = __ldg(reinterpret_cast<const uint4 *>(&b.fb[ty * (uint32_t)b.fb_tw + tx]));
-            if (f.x > b.prim_capacity) f.x = b.prim_capacity;
-            if (f.x + f.y > b.prim_capacity) f.y = b.prim_capacity - f.x;
-            f.w = min(f.w, f.y);  // entries the scatter wrote (it leaves out what the z-buffer culls)
+            f = clamp_header(__ldg(reinterpret_cast<const uint4 *>(&b.fb[ty * (uint32_t)b.fb_tw + tx])), b.prim_capacity);
             xy = tx | (ty << 16);
         }
         sh.fb[tid] = f;
@@ -812,7 +851,6 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
     cs.repeat_u = (p.sampling_flags & 1u) != 0;
     cs.repeat_v = (p.sampling_flags & 2u) != 0;
     cs.nearest = (p.sampling_flags & 0xcu) != 0;
-    const int k_own = (int)(lane & 3u), s_own = (int)(lane >> 2);
     // 16-byte stores need 16-byte rows (a render-target page of odd width has none: 4-byte stores there)
     const bool vec_ok = ((reinterpret_cast<size_t>(tg.pixels) | tg.pitch) & 15) == 0;
     // gl_FragCoord of the full canvas (only textured paints look at it); render-target pages have no origin
@@ -838,26 +876,14 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
             // next key from global memory
             __syncthreads();
             if (tid < 32) {
-                const uint32_t t = tb, xy = sh.txy[t];
+                const uint32_t t = tb;
                 const uint4 hdr = sh.fb[t];
-                TileGeom g;
-                const int tile_x = (int)(xy & 0xffffu), tile_y = (int)(xy >> 16);
-                g.gx0 = tile_x * TILE + k_own * 4;
-                g.gy0 = tile_y * TILE + s_own * 2;
-                g.interior = vec_ok && (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
-                g.px0 = tg.pixels + (size_t)g.gy0 * tg.pitch + (size_t)g.gx0 * 4;
-                g.fragx = (float)g.gx0 + org_x;
-                g.fragy = (float)g.gy0 + org_y;
-                PixelBlock px;
-                if (clear) px.set_all(clear_color);
-                else load_block(px, g, tg);
+                const TileGeom g = tile_geom(sh.txy[t], lane, vec_ok, org_x, org_y, tg);
                 const uint4 *list = reinterpret_cast<const uint4 *>(b.prims) + hdr.x;
-                uint32_t last_key = 0;
-                bool first = true;
-                while (true) {
+                auto next_layer = [&](uint32_t &last_key, bool &first, uint4 &u, uint32_t &paint) {
                     uint32_t best = 0xffffffffu, best_i = 0;
                     for (uint32_t i = lane; i < hdr.w; i += 32) {
-                        const uint32_t key = __ldg(&list[i].x);
+                        const uint32_t key = __ldg(&list[i].x) & KEY_MASK;
                         if ((first || key > last_key) && key < best) {
                             best = key;
                             best_i = i;
@@ -871,20 +897,22 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                             best_i = oi;
                         }
                     }
-                    if (best == 0xffffffffu) break;
+                    if (best == 0xffffffffu) return false;
                     last_key = best;
                     first = false;
-                    uint4 q = __ldg(&list[best_i]);
-                    q.w = layer_flags(q, b.mask_capacity);
-                    const uint32_t ce = q.z & 0xffffu;
-                    float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ce < p.n_paints) {
-                        base = __ldg(&p.paints[ce].base);
-                        if (!SOLID && __ldg(&p.paints[ce].ctrl) != 0) q.w |= LF_TEXTURED;
-                    }
-                    blend_layer<SOLID>(px, q, base, b, p, cs, g, tg, lane);
+                    u = resolve_prim<SOLID>(__ldg(&list[best_i]), b, p, paint);
+                    return true;
+                };
+                {
+                    PixelBlock px;
+                    if (clear) px.set_all(clear_color);
+                    else load_block(px, g, tg);
+                    uint32_t last_key = 0, paint;
+                    bool first = true;
+                    uint4 u;
+                    while (next_layer(last_key, first, u, paint)) blend_layer<SOLID>(px, u, load_mask(u, b, lane), paint, b, p, cs, g, tg, lane);
+                    if (clear || hdr.w) store_block<SOLID>(px, g, tg);
                 }
-                if (clear || hdr.w) store_block<SOLID>(px, g, tg);
             }
             tb = te;
             __syncthreads();
@@ -899,7 +927,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
         __syncthreads();
 
         // ---- stage 3: 8 threads per tile put its list in paint order (keys are unique: rank = number of smaller keys),
-        // look up the layers' colours and start the mask loads; then one of them blends the leading whole-tile layers
+        // resolve the layers and start the mask loads; then one of them blends the leading whole-tile layers
         {
             const uint32_t t = tb + (tid >> 3), sub = tid & 7u;
             uint32_t n = 0, off = 0;
@@ -908,26 +936,18 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 n = hdr.w;
                 off = hdr.x - range0;
                 for (uint32_t e = sub; e < n; e += 8) {
-                    uint4 q = sh.raw[off + e];
+                    const uint4 q = sh.raw[off + e];
+                    const uint32_t key = q.x & KEY_MASK;
                     uint32_t rank = 0;
-                    for (uint32_t j = 0; j < n; j++) rank += sh.raw[off + j].x < q.x ? 1u : 0u;
-                    q.w = layer_flags(q, b.mask_capacity);
-                    const uint32_t ce = q.z & 0xffffu;
-                    float4 base = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ce < p.n_paints) {
-                        base = __ldg(&p.paints[ce].base);
-                        if (!SOLID) {
-                            const int ctrl = __ldg(&p.paints[ce].ctrl);
-                            if (ctrl != 0) q.w |= LF_TEXTURED;
-                            if (((ctrl >> 8) & 0x3) != 0 && ((ctrl >> 4) & 0xf) == 0x3) q.w |= LF_HEAVY;
-                        }
+                    for (uint32_t j = 0; j < n; j++) rank += (sh.raw[off + j].x & KEY_MASK) < key ? 1u : 0u;
+                    uint32_t paint;
+                    const uint4 u = resolve_prim<SOLID>(q, b, p, paint);
+                    if ((u.x & ((uint32_t)LF_MASKED << 24))) {
+                        prefetch_l1(b.masks + (size_t)u.y * 256);
+                        prefetch_l1(b.masks + (size_t)u.y * 256 + 128);
                     }
-                    if (q.w & LF_MASKED) {
-                        prefetch_l1(b.masks + (size_t)q.y * 256);
-                        prefetch_l1(b.masks + (size_t)q.y * 256 + 128);
-                    }
-                    sh.sorted[off + rank] = q;
-                    sh.color[off + rank] = base;
+                    sh.sorted[off + rank] = u;
+                    if (!SOLID) sh.paint[off + rank] = (uint16_t)paint;
                 }
             }
             __syncwarp();
@@ -941,10 +961,11 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                     is_work = true;
                 } else {
                     for (; i < n; i++) {
-                        const uint32_t fl = sh.sorted[off + i].w;
+                        const uint4 u = sh.sorted[off + i];
+                        const uint32_t fl = u.x >> 24;
                         if (fl & LF_SKIP) continue;
                         if (fl & (LF_MASKED | LF_TEXTURED)) break;
-                        float4 src = sh.color[off + i];
+                        float4 src = prim_color(u);
                         src.x *= src.w;
                         src.y *= src.w;
                         src.z *= src.w;
@@ -961,10 +982,10 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                     sh.start_layer[t] = i;
                     bool heavy = false;
                     if (!SOLID)
-                        for (uint32_t k = clear ? i : 0u; k < n; k++) heavy = heavy || (sh.sorted[off + k].w & LF_HEAVY) != 0;
+                        for (uint32_t j = clear ? i : 0u; j < n; j++) heavy = heavy || ((sh.sorted[off + j].x >> 24) & LF_HEAVY) != 0;
                     if (heavy) {  // four work items, one pixel pair of every lane each
                         const uint32_t at = atomicAdd(&sh.n_work, 4u);
-                        for (uint32_t k = 0; k < 4; k++) sh.work[at + k] = (uint16_t)(t | ((1u << k) << 8));
+                        for (uint32_t j = 0; j < 4; j++) sh.work[at + j] = (uint16_t)(t | ((1u << j) << 8));
                     } else {
                         sh.work[atomicAdd(&sh.n_work, 1u)] = (uint16_t)(t | (0xfu << 8));
                     }
@@ -999,7 +1020,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
             }
         }
 
-        // ---- stage 4b: the other tiles, one warp per tile
+        // ---- stage 4b: the other tiles, one warp per tile; the mask of layer i + 1 is fetched before layer i is blended
         {
             const uint32_t n_work = sh.n_work;
             while (true) {
@@ -1007,27 +1028,30 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 if (lane == 0) wi = atomicAdd(&sh.next, 1u);
                 wi = __shfl_sync(0xffffffffu, wi, 0);
                 if (wi >= n_work) break;
-                const uint32_t item = sh.work[wi], t = item & 0xffu, xy = sh.txy[t];
-                const uint32_t pairs = SOLID ? 0xfu : item >> 8;
+                const uint32_t item = sh.work[wi], t = item & 0xffu;
                 const uint4 hdr = sh.fb[t];
                 const uint32_t n = hdr.w, off = hdr.x - range0;
-                TileGeom g;
-                const int tile_x = (int)(xy & 0xffffu), tile_y = (int)(xy >> 16);
-                g.gx0 = tile_x * TILE + k_own * 4;
-                g.gy0 = tile_y * TILE + s_own * 2;
-                g.interior = vec_ok && (tile_x + 1) * TILE <= tg.width && (tile_y + 1) * TILE <= tg.height;
-                g.px0 = tg.pixels + (size_t)g.gy0 * tg.pitch + (size_t)g.gx0 * 4;
-                g.fragx = (float)g.gx0 + org_x;
-                g.fragy = (float)g.gy0 + org_y;
+                const uint32_t i0 = clear ? sh.start_layer[t] : 0u;  // (a work tile has a layer at i0)
+                const TileGeom g = tile_geom(sh.txy[t], lane, vec_ok, org_x, org_y, tg);
+                const uint32_t pairs = SOLID ? 0xfu : item >> 8;
+                uint32_t i = i0;
+                uint4 u = sh.sorted[off + i];
+                uint2 mask8 = load_mask(u, b, lane);
                 PixelBlock px;
-                uint32_t i = 0;
-                if (clear) {
-                    px.set_all(sh.start_color[t]);
-                    i = sh.start_layer[t];
-                } else {
-                    load_block(px, g, tg);
+                if (clear) px.set_all(sh.start_color[t]);
+                else load_block(px, g, tg);
+                while (true) {
+                    uint4 un = u;
+                    uint2 mn = mask8;
+                    if (i + 1 < n) {
+                        un = sh.sorted[off + i + 1];
+                        mn = load_mask(un, b, lane);
+                    }
+                    blend_layer<SOLID>(px, u, mask8, SOLID ? 0u : (uint32_t)sh.paint[off + i], b, p, cs, g, tg, lane, pairs);
+                    if (++i >= n) break;
+                    u = un;
+                    mask8 = mn;
                 }
-                for (; i < n; i++) blend_layer<SOLID>(px, sh.sorted[off + i], sh.color[off + i], b, p, cs, g, tg, lane, pairs);
                 store_block<SOLID>(px, g, tg, pairs);
             }
         }
@@ -1044,22 +1068,14 @@ cudaError_t launch_composite(const BatchView &b, const PaintView &p, const Targe
     const uint32_t sub_th = (uint32_t)min(b.fb_th, (t.height + TILE - 1) / TILE);
     const uint32_t n_fb = sub_tw * sub_th;
     if (!n_fb) return cudaSuccess;
-    unsigned grid = (n_fb + CT_TILES - 1) / CT_TILES;
     const float4 cc = make_float4(clear_color[0], clear_color[1], clear_color[2], clear_color[3]);
     // the plain-colour instantiation skips the saturation before the RGBA8 conversion: src-over of premultiplied colours
     // in [0, 1] stays in [0, 1]
-    bool unit = p.all_solid && p.unit_range;
+    bool unit = p.all_solid && p.unit_range && b.solid_prims;
     for (int i = 0; i < 4; i++) unit = unit && clear_color[i] >= 0.0f && clear_color[i] <= 1.0f;
     if (unit) {
-        static int exp_tpc = -1;  // kernel experiments: PFCU_EXP_TPC = tiles per CTA of the plain-colour instantiation
-        if (exp_tpc < 0) {
-            const char *e = getenv("PFCU_EXP_TPC");
-            exp_tpc = e ? atoi(e) : 0;
-            if (exp_tpc < 0 || exp_tpc > CT_TILES) exp_tpc = 0;
-        }
-        const uint32_t tpc_solid = exp_tpc ? (uint32_t)exp_tpc : (uint32_t)CT_TILES;
-        grid = (n_fb + tpc_solid - 1) / tpc_solid;
-        return launch_pdl(k_composite<true>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin, tpc_solid, sub_tw, n_fb);
+        const uint32_t tpc = CT_TILES;
+        return launch_pdl(k_composite<true>, (n_fb + tpc - 1) / tpc, CT_THREADS, 0, s, b, p, t, clear, cc, origin, tpc, sub_tw, n_fb);
     }
     // Textured passes on small targets (the blur passes of a shadow run on a render target of a few hundred tiles, and
     // a blurred pixel costs thousands of instructions): fewer tiles per CTA, so that the pass covers every SM instead of
@@ -1071,8 +1087,7 @@ cudaError_t launch_composite(const BatchView &b, const PaintView &p, const Targe
     // CTA, so that the hardware spreads them over all SMs (each is split over the CTA's four warps)
     if (heavy_paints) tpc = 1;
     if (tpc < 1) tpc = 1;
-    grid = (n_fb + tpc - 1) / tpc;
-    return launch_pdl(k_composite<false>, grid, CT_THREADS, 0, s, b, p, t, clear, cc, origin, tpc, sub_tw, n_fb);
+    return launch_pdl(k_composite<false>, (n_fb + tpc - 1) / tpc, CT_THREADS, 0, s, b, p, t, clear, cc, origin, tpc, sub_tw, n_fb);
 }
 
 }  // namespace pfcu

@@ -18,19 +18,28 @@
 //                    insertion sort (sort.comp:49-83) with contiguous (CSR) lists: propagate takes a rank per
 //                    listed tile, the scan turns counts into offsets, one thread per listed tile writes its entry.
 //                    Ordering and z-culling happen on chip in the composite kernel.
+#include <cuda_fp16.h>
+
 #include "pfcu_device.h"
 
 namespace pfcu {
 
-static int g_sm_count = 0;
+// Per DEVICE, not per process: a process may hold contexts on several GPUs (pfcu_create(device_ordinal)).
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 ? 0 : (dev >= MAX_DEVICES ? MAX_DEVICES - 1 : dev);
+}
+
 int sm_count() {
-    if (!g_sm_count) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
+    static int counts[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!counts[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        counts[dev] = n > 0 ? n : 148;
     }
-    return g_sm_count;
+    return counts[dev];
 }
 
 #ifndef SCAN_THREADS_N
@@ -427,7 +436,11 @@ cudaError_t launch_propagate(const BatchView &b, cudaStream_t s) {
 // leave their slot unused: fb[].cursor ends up as the list length, fb[].count stays the slot count.
 __global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
     pdl_wait();
-    for (uint32_t ti = blockIdx.x * blockDim.x + threadIdx.x; ti < b.tile_count; ti += gridDim.x * blockDim.x) {
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t placed = 0, longest = 0;
+    for (uint32_t ti0 = blockIdx.x * blockDim.x; ti0 < b.tile_count; ti0 += gridDim.x * blockDim.x) {
+        const uint32_t ti = ti0 + threadIdx.x;
+        if (ti >= b.tile_count) continue;
         const uint4 st = *reinterpret_cast<const uint4 *>(&b.tile_state[ti]);
         if (!(st.y & (1u << 24))) continue;
         const uint32_t path = st.z;
@@ -439,10 +452,39 @@ __global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
         const uint4 hdr = *reinterpret_cast<const uint4 *>(&b.fb[map]);  // begin and z are final; cursor is moving
         if ((int)ti < (int)hdr.z) continue;
         const uint32_t pi = __ldg(reinterpret_cast<const uint32_t *>(&b.tpi[path]) + 3);  // color, ctrl, backdrop
-        const uint32_t ctrl_word = (pi & 0x00ffffffu) | ((st.y & 0xffu) << 24);
-        const uint32_t pos = hdr.x + atomicAdd(&b.fb[map].cursor, 1u);
+        const uint32_t at = atomicAdd(&b.fb[map].cursor, 1u);
+        const uint32_t pos = hdr.x + at;
+        placed++;
+        longest = max(longest, at + 1u);
         if (pos >= b.prim_capacity) continue;
-        *reinterpret_cast<uint4 *>(&b.prims[pos]) = make_uint4(ti, st.x, ctrl_word, 0u);
+        uint4 rec;
+        if (b.solid_prims) {
+            // the layer, resolved: flags + the paint's base colour (the texels are halfs: nothing is lost)
+            const uint32_t paint = pi & 0xffffu;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (paint < b.n_paints) c = __ldg(&b.paints[paint].base);
+            const uint32_t fl = layer_flags((int)st.x, (pi >> 16) & 0xffu, (int)(int8_t)(st.y & 0xffu), b.mask_capacity);
+            const __half2 rg = __floats2half2_rn(c.x, c.y), ba = __floats2half2_rn(c.z, c.w);
+            rec = make_uint4(ti | (fl << 24), st.x, *reinterpret_cast<const uint32_t *>(&rg), *reinterpret_cast<const uint32_t *>(&ba));
+        } else {
+            rec = make_uint4(ti, st.x, (pi & 0x00ffffffu) | ((st.y & 0xffu) << 24), 0u);
+        }
+        *reinterpret_cast<uint4 *>(&b.prims[pos]) = rec;
+    }
+    // frame statistics (pfcu_frame_stats::listed_after_cull / max_list_len): one pair of atomics per CTA
+    __shared__ uint32_t s_placed, s_longest;
+    if (threadIdx.x == 0) s_placed = s_longest = 0;
+    __syncthreads();
+    placed = __reduce_add_sync(0xffffffffu, placed);
+    longest = __reduce_max_sync(0xffffffffu, longest);
+    if (lane == 0 && placed) {
+        atomicAdd(&s_placed, placed);
+        atomicMax(&s_longest, longest);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_placed) {
+        atomicAdd(&b.counters->n_listed, s_placed);
+        atomicMax(&b.counters->max_list_len, s_longest);
     }
 }
 

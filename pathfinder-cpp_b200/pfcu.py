@@ -19,6 +19,7 @@ EXPORTS = [
     "pfcu_set_area_lut", "pfcu_set_target", "pfcu_set_target_origin", "pfcu_upload_scene", "pfcu_upload_paint_metadata", "pfcu_alloc_page",
     "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
     "pfcu_submit_frame", "pfcu_wait_frame", "pfcu_read_target_region",
+    "pfcu_read_target_async", "pfcu_wait_read", "pfcu_host_alloc", "pfcu_host_free",
     "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
     "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
     "pfcu_get_stage_times", "pfcu_set_option", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
@@ -88,6 +89,12 @@ def lib():
         L.pfcu_read_target.argtypes = [vp, vp]
         L.pfcu_read_target_region.argtypes = [vp, i32, i32, i32, i32, vp]
         L.pfcu_read_page.argtypes = [vp, u32, vp]
+        L.pfcu_read_target_async.argtypes = [vp, vp, sz]
+        L.pfcu_wait_read.argtypes = [vp]
+        L.pfcu_host_alloc.argtypes = [sz]
+        L.pfcu_host_alloc.restype = vp
+        L.pfcu_host_free.argtypes = [vp]
+        L.pfcu_host_free.restype = None
         L.pfcu_target_device_ptr.argtypes = [vp, C.POINTER(sz)]
         L.pfcu_target_device_ptr.restype = vp
         for n in ("pfcu_read_lines", "pfcu_read_fills", "pfcu_read_tiles", "pfcu_read_z"):
@@ -150,6 +157,9 @@ class Renderer:
         if getattr(self, "h", None):
             self.L.pfcu_destroy(self.h)
             self.h = None
+            for ptr in getattr(self, "_pinned", []):
+                self.L.pfcu_host_free(ptr)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -267,6 +277,22 @@ class Renderer:
         px = np.zeros((self.height, self.width, 4), "u1")
         _check(self.L.pfcu_read_target(self.h, _p(px)))
         return px
+
+    def pinned_frame(self):
+        """A page-locked (height, width, 4) u8 array for read_async (pfcu_host_alloc); freed with the renderer."""
+        n = self.height * self.width * 4
+        ptr = self.L.pfcu_host_alloc(n)
+        if not ptr:
+            raise PfcuError(self.L.pfcu_last_error().decode())
+        self._pinned = getattr(self, "_pinned", []) + [ptr]
+        return np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr)).reshape(self.height, self.width, 4)
+
+    def read_async(self, out):
+        """pfcu_read_target_async: enqueue the read-back of the frame in flight into `out` (use pinned_frame())."""
+        _check(self.L.pfcu_read_target_async(self.h, _p(out), out.strides[0]))
+
+    def wait_read(self):
+        _check(self.L.pfcu_wait_read(self.h))
 
     def pixels_region(self, x, y, width, height):
         px = np.zeros((height, width, 4), "u1")

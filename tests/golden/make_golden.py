@@ -9,6 +9,10 @@ into oracle/_ref/libpfref.so; this script drives it through oracle/pfref.py and 
                           in the order- and id-independent canonical form of tests/scenes.py
   area_lut.npz  the 256 x 256 RGBA8 area LUT as decoded by the reference (core/renderer.cpp:17-21)
   digests.json  sha256 of the canonical outputs of the configurations too large to commit (tiger 4096)
+  synthetic_200k_8192.npz  BASELINE.json configs[3] at its STATED size (200,000 cubic blobs at 8192 x 8192): sha256 of every
+                geometry tap of oracle/pf_oracle.c (lines, fills, tiles, z, sorted lists -- the restatement is pinned to the
+                reference's tiler on the fixtures above) + the channel sums of every 16 x 16 tile of the oracle's frame
+                (`python tests/golden/make_golden.py config4` regenerates only this one: 2 minutes of CPU)
   shader_frames.npz  RGBA8 frames of the 512^2 fixtures as the reference's OWN compute shaders render them: fill.comp and
                 tile.comp, read where they lie, compiled by g++ through oracle/ref_harness/glsl_shim.h and run on the CPU
                 (oracle/_ref/libpfshader.so, oracle/pfshader.py)
@@ -80,7 +84,45 @@ def geometry_digest(ref):
     return scenes.digest(*parts)
 
 
+def tap_digests(fr, slot):
+    """sha256 of every geometry tap of one oracle batch, in the canonical forms tests/test_gpu_parity.py compares."""
+    lines = fr.clipped_lines(slot)
+    w = np.frombuffer(lines.tobytes(), "<u4").reshape(len(lines), -1)
+    lines_sorted = w[np.lexsort(w.T[::-1])]
+    tiles = fr.tiles(slot)
+    off, lst = fr.tile_lists(slot)
+    out = {"lines": scenes.digest(lines_sorted), "fills": scenes.digest(fr.fills(slot)),
+           "z": scenes.digest(fr.z(slot)[0]), "tile_lists": scenes.digest(off, lst)}
+    for f in ("fill_count", "backdrop", "backdrop_delta", "backdrop_d3d9", "listed"):
+        out["tiles_" + f] = scenes.digest(tiles[f])
+    out["tiles_has_alpha"] = scenes.digest(tiles["alpha_tile_id"] >= 0)
+    return out
+
+
+def config4():
+    """BASELINE.json configs[3] at full size through the C restatement (no reference front end involved: the scene is
+    built by tests/scenes.py from the PCG32 stream SURVEY.md names)."""
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "port"])
+    import pforacle
+    n_paths, size = scenes.CONFIG4
+    scene = scenes.synthetic_scene(n_paths, size)
+    lut = np.load(os.path.join(HERE, "area_lut.npz"))["lut"]
+    fr = pforacle.Frame(scene, lut)
+    px = fr.render()
+    slot = fr.slots[int(scene["draw_batches"][0]["info"][0])]
+    dig = tap_digests(fr, slot)
+    counts = fr.counts(slot)
+    fr.close()
+    np.savez_compressed(os.path.join(HERE, "synthetic_%dk_%d.npz" % (n_paths // 1000, size)), tile_sums=scenes.tile_sums(px),
+                        digests=np.array(json.dumps(dig)), counts=np.array(json.dumps(counts)),
+                        frame_sha256=np.array(scenes.digest(px)))
+    print("config4", counts, dig)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "config4":
+        config4()
+        return
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
     digests = {}
     lut = None
@@ -137,6 +179,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "shader_frames.npz"), **frames)
     with open(os.path.join(HERE, "digests.json"), "w") as fp:
         json.dump(digests, fp, indent=1, sort_keys=True)
+    config4()
 
 
 if __name__ == "__main__":

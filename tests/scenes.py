@@ -444,3 +444,13 @@ def synthetic_paths(n_paths, size, seed=0x5EED5EED, n_colors=4096):
 def synthetic_scene(n_paths, size, seed=0x5EED5EED, strip=None):
     paths, colors = synthetic_paths(n_paths, size, seed)
     return build_scene_from_outlines(size, size, paths, colors, strip=strip)
+
+
+CONFIG4 = (200000, 8192)  # BASELINE.json configs[3] / SURVEY.md section 8d config 4: paths, canvas size
+
+
+def tile_sums(px):
+    """Channel sums of every 16 x 16 tile of an RGBA8 frame: (tiles_y, tiles_x, 4) u16 (256 * 255 < 65536). The pixel half
+    of the fixtures that are too large to commit as frames (tests/golden/synthetic_200k_8192.npz)."""
+    h, w, _ = px.shape
+    return px.reshape(h // 16, 16, w // 16, 16, 4).astype(np.uint32).sum(axis=(1, 3)).astype("<u2")

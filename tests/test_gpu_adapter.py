@@ -75,3 +75,58 @@ def test_reference_front_end_through_renderer_cuda(lib, area_lut, name, asset, s
     want = fr.render()
     fr.close()
     assert np.abs(out.astype(int) - want.astype(int)).max() <= 1
+
+
+def _demo(lib, size, scale, features, frames, load_last):
+    lib.pfref_cuda_render_demo.argtypes = [C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                           C.POINTER(FrameStats)]
+    out = np.zeros((size, size, 4), "u1")
+    st = FrameStats()
+    rc = lib.pfref_cuda_render_demo(size, size, C.c_float(scale), features, 0, frames, load_last,
+                                    out.ctypes.data_as(C.c_void_p), C.byref(st))
+    assert rc == 0
+    return out, st
+
+
+def test_demo_primitives_through_renderer_cuda(lib, area_lut):
+    """The demo's whole primitives scene (demo/common/app.cpp:21-101) through the C++ adapter: clip batches prepared in
+    reverse, two blur passes through render-target pages, the image pattern's page + color_texture_info, the render-target
+    pattern -- every branch of host/renderer_cuda.cpp that an SVG never takes."""
+    import pfcu
+    import pforacle
+
+    out, st = _demo(lib, 512, 1.0, 0x3f, 2, 0)
+    assert st.retries == 0 and st.kernel_launches > 0
+    scene, _ = scenes.load_scene(scenes.golden_path("demo_full_512"))
+    r = pfcu.Renderer(0, area_lut)
+    r.set_scene(scene)
+    stats = r.draw(clear=True)
+    mine = r.pixels()
+    r.close()
+    for k in ("batches", "segments", "lines", "fills", "alpha_tiles", "dense_tiles"):
+        assert getattr(st, k) == stats[k], k
+    diff = np.abs(out.astype(int) - mine.astype(int))
+    print("demo_full_512: adapter vs harness: %d channel values differ, max %d" % (int((diff > 0).sum()), int(diff.max())))
+    assert diff.max() <= 1 and (diff > 0).sum() <= 1e-3 * diff.size
+    fr = pforacle.Frame(scene, area_lut)
+    want = fr.render()
+    fr.close()
+    assert np.abs(out.astype(int) - want.astype(int)).max() <= 1
+
+
+def test_renderer_cuda_load_action_keeps_the_destination(lib, area_lut):
+    """Renderer::draw(builder, clear_dst_texture = false) (core/renderer.h:83; LOAD_ACTION_LOAD, d3d11/renderer.cpp:382-386):
+    the second frame blends over what the first left in the destination instead of starting from a zeroed target."""
+    import pfcu
+
+    out, _ = _demo(lib, 512, 1.0, 1 | 2 | 16, 2, 1)
+    scene, _ = scenes.load_scene(scenes.golden_path("demo_clip_512"))
+    r = pfcu.Renderer(0, area_lut)
+    r.set_scene(scene)
+    r.draw(clear=True)
+    once = r.pixels()
+    r.draw(clear=False)
+    twice = r.pixels()
+    r.close()
+    assert np.abs(once.astype(int) - twice.astype(int)).max() > 8  # translucent layers: drawing twice must show
+    assert np.abs(out.astype(int) - twice.astype(int)).max() <= 1

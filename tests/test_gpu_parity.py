@@ -432,3 +432,86 @@ def test_tiger_4096_pixels_against_live_reference_shaders(renderer, area_lut):
     d = np.abs(renderer.pixels().astype(np.int16) - want.astype(np.int16)).max(axis=2)
     print("tiger 4096: %d of %d pixels differ from the reference shaders' frame" % (int((d > 0).sum()), d.size))
     assert d.max() <= PIXEL_TOL
+
+
+def test_config4_at_its_stated_size_against_the_oracle_fixture(renderer):
+    """BASELINE.json configs[3] at FULL size -- 200,000 cubic blobs at 8192 x 8192 (16.7 M fills, 1.39 M masks: the
+    only configuration that stresses the 24-bit tile ids and the multi-megabyte scans) -- against
+    tests/golden/synthetic_200k_8192.npz, made by tests/golden/make_golden.py from oracle/pf_oracle.c (99 s of CPU):
+    every geometry tap bit-exact (sha256 of lines, fills, tiles, z, sorted lists), pixels through the channel sums of
+    every 16 x 16 tile (a pixel may differ by 1/255, so a tile's sum may move by a few units, never by a layer)."""
+    import json
+    import os
+
+    fx = np.load(os.path.join(scenes.GOLDEN, "synthetic_200k_8192.npz"))
+    want = json.loads(str(fx["digests"]))
+    counts = json.loads(str(fx["counts"]))
+    n_paths, size = scenes.CONFIG4
+    scene = scenes.synthetic_scene(n_paths, size)
+    renderer.set_scene(scene)
+    st = renderer.draw(clear=True)
+    assert st["overflow_flags"] == 0
+    assert st["lines"] == counts["lines"] and st["fills"] == counts["fills"] and st["alpha_tiles"] == counts["alpha_tiles"]
+    bid = int(scene["draw_batches"][0]["info"][0])
+    tiles = renderer.tiles(bid)
+    got = {"lines": scenes.digest(raw_sorted(renderer.lines(bid))), "fills": scenes.digest(renderer.fills(bid)),
+           "z": scenes.digest(renderer.z(bid)), "tile_lists": scenes.digest(*renderer.tile_lists(bid)),
+           "tiles_has_alpha": scenes.digest(tiles["alpha_tile_id"] >= 0)}
+    for f in ("fill_count", "backdrop", "backdrop_delta", "backdrop_d3d9", "listed"):
+        got["tiles_" + f] = scenes.digest(tiles[f])
+    for k in sorted(want):
+        assert got[k] == want[k], "config 4 @ %d^2: %s differs from the oracle" % (size, k)
+    assert st["listed_after_cull"] == counts["listed_culled"] and st["max_list_len"] == counts["max_list"]
+    px = renderer.pixels()
+    d = np.abs(scenes.tile_sums(px).astype(np.int32) - fx["tile_sums"].astype(np.int32))
+    print("config 4: %d of %d tiles differ in a channel sum, worst by %d" % (int((d.max(axis=2) > 0).sum()), d.shape[0] * d.shape[1], d.max()))
+    # a 16 x 16 tile holds 256 pixels, each within 1/255: the bound is 256 per channel; what is observed is far below it
+    assert d.max() <= 32, "a tile's channel sum is off by %d" % d.max()
+    assert (d.max(axis=2) > 0).mean() < 0.02
+
+
+def test_async_readback_into_pinned_memory(renderer, area_lut):
+    """pfcu_read_target_async / pfcu_wait_read (= CommandEncoder::read_texture without the blocking fence wait,
+    gpu/command_encoder.cpp:317-355): the copy is enqueued behind a SUBMITTED frame and lands in page-locked memory while
+    another context renders; a new frame on the same context does not overwrite the target before the copy has read it."""
+    import pfcu
+
+    tiger, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    demo, _ = scenes.load_scene(scenes.golden_path("demo_full_512"))
+    want = {}
+    for name, scene in (("tiger", tiger), ("demo", demo)):
+        renderer.set_scene(scene)
+        renderer.draw(clear=True)
+        want[name] = renderer.pixels()
+    a, b = pfcu.Renderer(0, area_lut), pfcu.Renderer(0, area_lut)
+    try:
+        a.set_scene(tiger)
+        b.set_scene(demo)
+        bufs = {"a": [a.pinned_frame(), a.pinned_frame()], "b": [b.pinned_frame(), b.pinned_frame()]}
+        for i in range(6):
+            for r, key, name in ((a, "a", "tiger"), (b, "b", "demo")):
+                buf = bufs[key][i & 1]
+                buf[:] = 0x55
+                r.draw(clear=True, clear_color=(1.0, 1.0, 1.0, 1.0) if i == 4 else (0.0, 0.0, 0.0, 0.0), upload=True, wait=False)
+                r.read_async(buf)       # behind the frame that was just submitted
+            for r, key, name in ((a, "a", "tiger"), (b, "b", "demo")):
+                r.wait()
+                r.wait_read()
+                if i != 4:
+                    assert np.array_equal(bufs[key][i & 1], want[name]), "%s frame %d" % (name, i)
+                elif name == "tiger":
+                    assert tuple(bufs[key][i & 1][0, 0]) == (255, 255, 255, 255)
+        # read-back of a finished frame, then a new frame at once: the copy must see the OLD frame
+        a.draw(clear=True)
+        buf = bufs["a"][0]
+        a.read_async(buf)
+        a.draw(clear=True, clear_color=(1.0, 0.0, 0.0, 1.0))
+        a.wait_read()
+        assert np.array_equal(buf, want["tiger"])
+        assert tuple(a.pixels()[0, 0]) == (255, 0, 0, 255)
+        with pytest.raises(RuntimeError):
+            a.L.pfcu_begin_frame(a.h) and None
+            a.read_async(buf)  # a frame is open and not submitted
+    finally:
+        a.close()
+        b.close()
