@@ -96,7 +96,9 @@ typedef struct {
     uint32_t batches, segments, lines, fills, alpha_tiles, dense_tiles, listed_tiles, listed_after_cull;
     uint32_t fb_tiles, max_list_len, overflow_flags, retries;
     uint32_t kernel_launches; /* kernels enqueued for this frame, including retries */
-    uint32_t reserved[3];
+    uint32_t diced_segments; /* segments that went through dice this frame (all of them unless PFCU_OPT_INCREMENTAL_DICE) */
+    uint32_t uploaded_bytes; /* host-to-device bytes of this frame: segments (full or partial uploads) + batch metadata */
+    uint32_t reserved[1];
     float gpu_ms; /* CUDA-event time of the frame on the context's stream (prepare..last draw), last attempt */
 } pfcu_frame_stats;
 
@@ -134,6 +136,14 @@ int pfcu_set_target_origin(pfcu_ctx *ctx, int origin_x, int origin_y);
 int pfcu_upload_scene(pfcu_ctx *ctx, int which, const float *points, uint32_t n_points, const uint32_t *indices,
                       uint32_t n_segments);
 /* Renderer::upload_texture_metadata (core/renderer.cpp:167-251): rows of 1280 RGBA16F texels. */
+/* Incremental scenes (replaces what Scene::epoch / LastSceneInfo::draw_segment_ranges exist for upstream, core/scene.h:32-49,
+ * core/d3d11/scene_builder.cpp:217-218 -- the reference records the ranges and then re-uploads and re-dices everything): the
+ * points [first_point, first_point + n_points) of source `which` changed; they belong to the segments [first_segment,
+ * first_segment + n_segments) (one path's Range of draw_segment_ranges, or several consecutive paths'). Topology -- the
+ * indices -- is unchanged; anything else needs pfcu_upload_scene. Only this range crosses PCIe, and with
+ * PFCU_OPT_INCREMENTAL_DICE only the paths that own those segments are diced again in the next frame. */
+int pfcu_update_scene_range(pfcu_ctx *ctx, int which, uint32_t first_point, const float *points, uint32_t n_points,
+                            uint32_t first_segment, uint32_t n_segments);
 int pfcu_upload_paint_metadata(pfcu_ctx *ctx, const uint16_t *half_texels, uint32_t n_rows);
 /* Renderer::allocate_pattern_texture_page / upload_texel_data (core/renderer.cpp:46-61,95-114). */
 int pfcu_alloc_page(pfcu_ctx *ctx, uint32_t page, int width, int height);
@@ -172,7 +182,12 @@ enum {
     /* 0 (default): the fill stage skips the masks of draw tiles that the z-buffer culls (tiles under an opaque whole-tile
      * layer of a later path, sort.comp:62): nothing ever reads them (19 % of tiger.svg's masks at 4096^2). 1: every mask
      * is rasterized, as fill.comp:109-154 does (pfcu_read_mask then returns a valid mask for culled tiles too). */
-    PFCU_OPT_FILL_CULLED_TILES = 1
+    PFCU_OPT_FILL_CULLED_TILES = 1,
+    /* 1: a batch keeps the lines dice produced (keyed on batch id, path / segment counts, dice metadata, transform, view box
+     * and the scene upload they came from); later frames dice only the paths touched by pfcu_update_scene_range since then
+     * and bin skips the retained lines of those paths. A frame that would re-dice more than half of the batch, or whose key
+     * changed, dices everything and becomes the new base. Default 0: every frame dices every segment, like the reference. */
+    PFCU_OPT_INCREMENTAL_DICE = 2
 };
 int pfcu_set_option(pfcu_ctx *ctx, int option, int value);
 

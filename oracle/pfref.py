@@ -131,6 +131,13 @@ class RefScene:
             lib().pfref_scene_free(self.h)
             self.h = None
 
+    def translate_draw_path(self, index, dx, dy):
+        """Outline::transform(Transform2::from_translation) on one draw path (an animated path)."""
+        L = lib()
+        L.pfref_scene_translate_draw_path.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float]
+        if L.pfref_scene_translate_draw_path(self.h, index, dx, dy) != 0:
+            raise IndexError(index)
+
     def counts(self):
         out = (C.c_uint32 * 4)()
         lib().pfref_scene_counts(self.h, out)

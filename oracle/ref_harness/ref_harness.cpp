@@ -208,6 +208,24 @@ void *pfref_scene_paints(int width, int height, float scale, const char *img, si
 
 void pfref_scene_free(void *p) { delete static_cast<Handle *>(p); }
 
+/// Outline::transform on one draw path of the scene (an animated path: the incremental-frame fixtures).
+/// xform = the six floats of Transform2(float[6]).
+int pfref_scene_transform_draw_path(void *p, uint32_t index, const float xform[6]) {
+    auto *h = static_cast<Handle *>(p);
+    if (!h->scene || index >= h->scene->draw_paths.size()) return -1;
+    float m[6] = {xform[0], xform[1], xform[2], xform[3], xform[4], xform[5]};
+    h->scene->draw_paths[index].outline.transform(Transform2(m));
+    return 0;
+}
+
+/// The same as a translation.
+int pfref_scene_translate_draw_path(void *p, uint32_t index, float dx, float dy) {
+    auto *h = static_cast<Handle *>(p);
+    if (!h->scene || index >= h->scene->draw_paths.size()) return -1;
+    h->scene->draw_paths[index].outline.transform(Transform2::from_translation(Vec2F(dx, dy)));
+    return 0;
+}
+
 void pfref_scene_counts(void *p, uint32_t out[4]) {
     auto *h = static_cast<Handle *>(p);
     out[0] = (uint32_t)h->scene->draw_paths.size();

@@ -110,6 +110,19 @@ struct BatchSlot {
     BatchView view{};
     bool prepared = false;
     bool heavy_paints = false;  // a path of the batch paints with a blur filter (tile.comp:354-392)
+    // Incremental frames (PFCU_OPT_INCREMENTAL_DICE): the dice output of an earlier frame that this slot still holds.
+    struct DiceBase {
+        bool valid = false;
+        uint64_t key = 0;        // everything the retained lines depend on except the segments themselves
+        uint64_t scene_gen = 0;  // full upload the lines were diced from
+        uint64_t seq = 0;        // partial updates up to this one are in the lines
+        uint32_t n_lines = 0, n_staging = 0, n_long = 0;
+    } base;
+    uint64_t frame_key = 0, frame_seq = 0;  // of the frame being recorded
+    bool diced_all = false;                 // this frame dices every segment (it becomes the base when it completes)
+    uint32_t diced_segments = 0;
+    size_t off_dirty = 0, off_ranges = 0, off_counters = 0;  // incremental extras inside host_meta / dev_meta
+    uint32_t n_ranges = 0;
     cudaEvent_t fill_done = nullptr;  // recorded on the aux stream after this batch's fill kernel
 };
 
@@ -191,6 +204,15 @@ struct pfcu_ctx {
     // ordinary way at pfcu_end_frame and the graph is dropped.
     bool auto_graph = true;
     bool fill_culled_tiles = false;  // PFCU_OPT_FILL_CULLED_TILES
+    // PFCU_OPT_INCREMENTAL_DICE: partial scene updates since the last full upload, per path source
+    bool incremental = false;
+    struct DirtyRange {
+        uint32_t lo, hi;  // global segments [lo, hi)
+        uint64_t seq;
+    };
+    std::vector<DirtyRange> dirty[2];
+    uint64_t scene_gen[2] = {1, 1}, update_seq = 0;
+    uint32_t uploaded_bytes = 0;  // H2D bytes of the frame being recorded (segments + metadata)
     uint64_t frame_sig = 0, prev_sig = 0, retained_sig = 0;
     cudaGraph_t retained_graph = nullptr;
     cudaGraphExec_t retained_exec = nullptr;
@@ -392,6 +414,13 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.paints = c->paints.as<Paint>();
     v.n_paints = c->n_paints;
     v.solid_prims = c->all_solid;
+    if (c->incremental && !s.diced_all) {
+        v.dice_ranges = reinterpret_cast<const uint2 *>(m + s.off_ranges);
+        v.n_dice_ranges = s.n_ranges;
+        v.n_dice_segments = s.diced_segments;
+        v.dirty_paths = reinterpret_cast<const uint32_t *>(m + s.off_dirty);
+        v.n_static_lines = s.base.n_lines;
+    }
     s.view = v;
     s.prepared = true;
 
@@ -411,8 +440,10 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
         sig_mix(c, &bytes, sizeof(bytes));
     }
     if (c->dry) return PFCU_OK;
-    if (s.meta_bytes && upload_meta)
+    if (s.meta_bytes && upload_meta) {
         CUDA_TRY(cudaMemcpyAsync(s.dev_meta.p, s.host_meta.p, s.meta_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (!c->capturing) c->uploaded_bytes += (uint32_t)s.meta_bytes;
+    }
 
     {
         int r = prof_mark(c, -1);
@@ -428,7 +459,10 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
         int r = order_after(c, aux, c->stream);  // (also orders this batch's aux work after the previous batch's)
         if (r) return r;
     }
-    CUDA_TRY(cudaMemsetAsync(v.counters, 0, sizeof(BatchCounters), c->stream));
+    if (v.dice_ranges)  // the retained lines, staging slots and long-line queue stay: the counters start where they ended
+        CUDA_TRY(cudaMemcpyAsync(v.counters, m + s.off_counters, sizeof(BatchCounters), cudaMemcpyDeviceToDevice, c->stream));
+    else
+        CUDA_TRY(cudaMemsetAsync(v.counters, 0, sizeof(BatchCounters), c->stream));
     LAUNCH_STAGE(PFCU_STAGE_INIT, launch_init(v, aux));
     LAUNCH_STAGE(PFCU_STAGE_DICE, launch_dice(v, c->stream));
     if (two_streams) {  // bin needs the zeroed tile words; the long-walk kernel needs dice's lines
@@ -773,6 +807,48 @@ int pfcu_upload_scene(pfcu_ctx *c, int which, const float *points, uint32_t n_po
     c->n_points[which] = n_points;
     c->n_segments[which] = n_segments;
     c->in_flight = true;
+    c->scene_gen[which]++;  // retained dice output of this source is stale
+    c->dirty[which].clear();
+    c->uploaded_bytes += (uint32_t)(pb + ib);
+    return PFCU_OK;
+}
+
+// Scene::epoch / LastSceneInfo::draw_segment_ranges (core/scene.h:32-49, d3d11/scene_builder.cpp:217-218): the points of a
+// run of segments changed (a path moved or was reshaped with the same topology); indices and every other segment stay.
+int pfcu_update_scene_range(pfcu_ctx *c, int which, uint32_t first_point, const float *points, uint32_t n_points,
+                            uint32_t first_segment, uint32_t n_segments) {
+    if (!c || which < 0 || which > 1 || !points || !n_points || !n_segments) return fail(PFCU_ERR_INVALID, "bad scene update");
+    if (c->frame_pending) return fail(PFCU_ERR_STATE, "a submitted frame has not been waited for");
+    if (c->frame_open) return fail(PFCU_ERR_STATE, "the scene cannot change inside a frame");
+    if ((uint64_t)first_point + n_points > c->n_points[which] || (uint64_t)first_segment + n_segments > c->n_segments[which])
+        return fail(PFCU_ERR_INVALID, "update range exceeds the uploaded scene (%u points, %u segments)", c->n_points[which],
+                    c->n_segments[which]);
+    CUDA_TRY(cudaSetDevice(c->device));
+    NvtxScope nvtx("pfcu_update_scene_range");
+    if (c->stage_busy[which]) {  // an earlier copy may still be reading the staging buffer
+        int r = sync_if_in_flight(c);
+        if (r) return r;
+    }
+    char *st = static_cast<char *>(c->stage_scene[which].p) + (size_t)first_point * 8;
+    memcpy(st, points, (size_t)n_points * 8);  // (the pinned copy stays a mirror of the device arrays)
+    CUDA_TRY(cudaMemcpyAsync(c->scene_dev[which].as<char>() + (size_t)first_point * 8, st, (size_t)n_points * 8,
+                             cudaMemcpyHostToDevice, c->stream));
+    c->stage_busy[which] = true;
+    c->in_flight = true;
+    c->update_seq++;
+    if (c->dirty[which].size() >= 1024) {  // too many to track: fall back to a full re-dice
+        c->scene_gen[which]++;
+        c->dirty[which].clear();
+    } else {
+        bool known = false;  // (an animation updates the same path every frame: one entry, its sequence number renewed)
+        for (auto &r : c->dirty[which])
+            if (r.lo == first_segment && r.hi == first_segment + n_segments) {
+                r.seq = c->update_seq;
+                known = true;
+            }
+        if (!known) c->dirty[which].push_back({first_segment, first_segment + n_segments, c->update_seq});
+    }
+    c->uploaded_bytes += n_points * 8;
     return PFCU_OK;
 }
 
@@ -944,6 +1020,11 @@ int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
     s.off_dice = align16(s.off_meta + (size_t)d->path_count * sizeof(pfcu_propagate_metadata));
     s.off_tpi = align16(s.off_dice + (size_t)d->path_count * sizeof(pfcu_dice_metadata));
     s.meta_bytes = align16(s.off_tpi + (size_t)d->path_count * sizeof(pfcu_tile_path_info));
+    // incremental extras: dirty-path bitmap, dice ranges (+ sentinel), the seed of the batch counters
+    s.off_dirty = s.meta_bytes;
+    s.off_ranges = align16(s.off_dirty + ((size_t)d->path_count + 31) / 32 * 4);
+    s.off_counters = align16(s.off_ranges + ((size_t)d->path_count + 1) * sizeof(uint2));
+    if (c->incremental) s.meta_bytes = s.off_counters + sizeof(BatchCounters);
     CUDA_TRY(s.host_meta.ensure(std::max<size_t>(s.meta_bytes, 16)));
     char *hm = static_cast<char *>(s.host_meta.p);
     if (d->column_count) memcpy(hm + s.off_backdrops, d->backdrops, (size_t)d->column_count * sizeof(pfcu_backdrop_info));
@@ -960,6 +1041,61 @@ int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
             if (paint < c->n_paints) {
                 const int ctrl = table[paint].ctrl;
                 s.heavy_paints = ((ctrl >> 8) & 0x3) != 0 && ((ctrl >> 4) & 0xf) == 0x3;
+            }
+        }
+    }
+    // ---- incremental frames: which paths changed since the slot's retained dice output was made
+    s.diced_all = true;
+    s.diced_segments = d->segment_count;
+    s.n_ranges = 0;
+    s.frame_seq = c->update_seq;
+    if (c->incremental && d->path_count) {
+        const int which = d->path_source ? 1 : 0;
+        uint64_t key = 1469598103934665603ull;
+        auto mix = [&](const void *p, size_t n) {
+            const unsigned char *q = static_cast<const unsigned char *>(p);
+            for (size_t i = 0; i < n; i++) key = (key ^ q[i]) * 1099511628211ull;
+        };
+        mix(&d->batch_id, 4); mix(&d->path_count, 4); mix(&d->segment_count, 4); mix(&d->path_source, 4);
+        mix(d->transform, sizeof(d->transform)); mix(c->view_box, sizeof(c->view_box));
+        mix(d->dice_metadata, (size_t)d->path_count * sizeof(pfcu_dice_metadata));
+        s.frame_key = key;
+        const bool usable = s.base.valid && s.base.key == key && s.base.scene_gen == c->scene_gen[which];
+        if (usable) {
+            uint32_t *bitmap = reinterpret_cast<uint32_t *>(hm + s.off_dirty);
+            uint2 *ranges = reinterpret_cast<uint2 *>(hm + s.off_ranges);
+            memset(bitmap, 0, ((size_t)d->path_count + 31) / 32 * 4);
+            uint32_t n_ranges = 0, n_seg = 0;
+            for (uint32_t p = 0; p < d->path_count; p++) {
+                const pfcu_dice_metadata &dm = d->dice_metadata[p];
+                const uint32_t cnt = (p + 1 < d->path_count ? d->dice_metadata[p + 1].first_batch_segment_index : d->segment_count) -
+                                     dm.first_batch_segment_index;
+                const uint32_t g0 = dm.first_global_segment_index, g1 = g0 + cnt;
+                bool dirty = false;
+                for (const auto &r : c->dirty[which])
+                    if (r.seq > s.base.seq && r.lo < g1 && g0 < r.hi) {
+                        dirty = true;
+                        break;
+                    }
+                if (!dirty || !cnt) continue;
+                bitmap[p >> 5] |= 1u << (p & 31u);
+                if (n_ranges && ranges[n_ranges - 1].x + (n_seg - ranges[n_ranges - 1].y) == dm.first_batch_segment_index) {
+                    // (extends the previous range)
+                } else {
+                    ranges[n_ranges++] = make_uint2(dm.first_batch_segment_index, n_seg);
+                }
+                n_seg += cnt;
+            }
+            if (n_seg * 2 <= d->segment_count) {  // otherwise a full re-dice is cheaper, and it renews the base
+                ranges[n_ranges] = make_uint2(0xffffffffu, n_seg);
+                s.n_ranges = n_ranges;
+                s.diced_all = false;
+                s.diced_segments = n_seg;
+                BatchCounters seed{};
+                seed.n_lines = s.base.n_lines;
+                seed.n_staging = s.base.n_staging;
+                seed.n_long = s.base.n_long;
+                memcpy(hm + s.off_counters, &seed, sizeof(seed));
             }
         }
     }
@@ -1103,6 +1239,11 @@ int pfcu_wait_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
         }
         // grow and replay the recorded frame
         drop_retained(c);  // (its parameter blocks point into the buffers that are about to move)
+        for (int i = 0; i < c->slots_used; i++) {  // ... and so do the lines an incremental frame would have kept
+            c->slots[i].base.valid = false;
+            c->slots[i].diced_all = true;
+            c->slots[i].diced_segments = c->slots[i].desc.segment_count;
+        }
         c->retries++;
         c->prof_used = 0;
         c->sync_used = 0;
@@ -1134,6 +1275,25 @@ int pfcu_wait_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
     }
     c->prev_sig = sig;
     pfcu_frame_stats st{};
+    if (c->incremental) {
+        for (int i = 0; i < c->slots_used; i++) {
+            BatchSlot &s = c->slots[i];
+            if (s.diced_all) {  // everything this slot holds was diced from the current scene: the new base
+                s.base.valid = true;
+                s.base.key = s.frame_key;
+                s.base.scene_gen = c->scene_gen[s.desc.path_source ? 1 : 0];
+                s.base.seq = s.frame_seq;
+                s.base.n_lines = hc[i].n_lines;
+                s.base.n_staging = hc[i].n_staging;
+                s.base.n_long = hc[i].n_long;
+            }
+            st.diced_segments += s.diced_segments;
+        }
+    } else {
+        for (int i = 0; i < c->slots_used; i++) st.diced_segments += c->slots[i].desc.segment_count;
+    }
+    st.uploaded_bytes = c->uploaded_bytes;
+    c->uploaded_bytes = 0;
     st.batches = (uint32_t)c->slots_used;
     for (int i = 0; i < c->slots_used; i++) {
         st.segments += c->slots[i].desc.segment_count;
@@ -1183,6 +1343,10 @@ int pfcu_set_option(pfcu_ctx *c, int option, int value) {
             return PFCU_OK;
         case PFCU_OPT_FILL_CULLED_TILES:
             c->fill_culled_tiles = value != 0;
+            return PFCU_OK;
+        case PFCU_OPT_INCREMENTAL_DICE:
+            c->incremental = value != 0;
+            for (auto &sl : c->slots) sl.base.valid = false;
             return PFCU_OK;
         default:
             return fail(PFCU_ERR_INVALID, "unknown option %d", option);

@@ -167,6 +167,13 @@ struct BatchView {
     const struct Paint *paints;
     uint32_t n_paints;
     int solid_prims;                // every paint of the frame is a plain colour: list entries carry the colour (TilePrim)
+    // incremental frames (PFCU_OPT_INCREMENTAL_DICE): the first n_static_lines lines are the previous frames' dice output;
+    // those whose path is marked in dirty_paths are skipped by bin, and only the segments of dice_ranges are diced again
+    const uint2 *dice_ranges;       // [n_dice_ranges + 1] x: first batch segment of the range, y: segments before it; the
+                                    // last entry is a sentinel (y = n_dice_segments). null: every segment is diced
+    uint32_t n_dice_ranges, n_dice_segments;
+    const uint32_t *dirty_paths;    // bitmap over the batch's paths, or null
+    uint32_t n_static_lines;
 };
 
 struct TargetView {

@@ -314,6 +314,18 @@ __device__ __forceinline__ uint32_t warp_find_path(const pfcu_dice_metadata *dic
     return lo;
 }
 
+// Batch segment number of the i-th segment to dice (identity unless the frame dices a subset: BatchView::dice_ranges)
+__device__ __forceinline__ uint32_t dice_segment(const BatchView &b, uint32_t i) {
+    if (!b.dice_ranges) return i;
+    uint32_t lo = 0, hi = b.n_dice_ranges;  // last range whose prefix count is <= i
+    while (lo + 1 < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&b.dice_ranges[mid].y) <= i) lo = mid; else hi = mid;
+    }
+    const uint2 r = __ldg(&b.dice_ranges[lo]);
+    return r.x + (i - r.y);
+}
+
 // Copies the CTA's collected lines to global memory: one atomic per flush.
 template <int Q, int O>
 __device__ __forceinline__ void dice_flush(const BatchView &b, DiceSharedT<Q, O> &sh) {
@@ -377,7 +389,9 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chu
     extern __shared__ __align__(16) unsigned char dice_smem[];
     DiceSharedT<Q, O> &sh = *reinterpret_cast<DiceSharedT<Q, O> *>(dice_smem);
     pdl_wait();
-    const uint32_t n_chunks = (b.segment_count + chunk_size - 1) / chunk_size;
+    // segments to dice: all of the batch, or -- incremental frames -- the ranges of the paths that changed
+    const uint32_t n_dice = b.dice_ranges ? b.n_dice_segments : b.segment_count;
+    const uint32_t n_chunks = (n_dice + chunk_size - 1) / chunk_size;
     if (threadIdx.x == 0) {
         sh.q_count[0] = sh.q_count[1] = 0;
         sh.out_count = 0;
@@ -392,7 +406,7 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chu
         // 35 k on the slowest SM with contiguous chunks). Larger batches (text-density scenes: uniform small paths) keep
         // contiguous chunks and stage only the paths of their range.
         const bool interleave = DICE_INTERLEAVE && b.path_count <= (uint32_t)DICE_PATHS && n_chunks > 1;
-        const uint32_t seg0 = chunk * chunk_size, seg1 = min(seg0 + chunk_size, b.segment_count) - 1;
+        const uint32_t seg0 = dice_segment(b, chunk * chunk_size), seg1 = dice_segment(b, min((chunk + 1) * chunk_size, n_dice) - 1);
         if (interleave) {
             if (threadIdx.x == 0) {
                 sh.path_lo = 0;
@@ -413,7 +427,8 @@ __global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chu
         __syncthreads();
         // ---- roots: one thread per segment of the chunk (chunk_size is a multiple of 32: whole warps)
         if (threadIdx.x < chunk_size) {
-            const uint32_t s = interleave ? threadIdx.x * n_chunks + chunk : chunk * chunk_size + threadIdx.x;
+            const uint32_t s_lin = interleave ? threadIdx.x * n_chunks + chunk : chunk * chunk_size + threadIdx.x;
+            const uint32_t s = s_lin < n_dice ? dice_segment(b, s_lin) : 0xffffffffu;
             bool root_line = false, root_curve = false, root_cubic = false;
             Cubic root = {};
             uint32_t root_path = 0;
@@ -546,15 +561,16 @@ static cudaError_t launch_dice_cfg(const BatchView &b, cudaStream_t s, uint32_t 
     // Segments per CTA and pass: few segments -> small chunks (every SM gets one, deep trees fit the queue);
     // many segments -> large chunks (fewer block-wide barriers per segment).
     const uint32_t ctas = (uint32_t)sm_count() * ctas_per_sm;
-    uint32_t chunk = (b.segment_count / (ctas * 4u) + 31u) & ~31u;
+    const uint32_t n_dice = b.dice_ranges ? b.n_dice_segments : b.segment_count;
+    uint32_t chunk = (n_dice / (ctas * 4u) + 31u) & ~31u;
     chunk = chunk < DICE_CHUNK ? DICE_CHUNK : (chunk > max_chunk ? max_chunk : chunk);
-    const uint32_t n_chunks = (b.segment_count + chunk - 1) / chunk;
+    const uint32_t n_chunks = (n_dice + chunk - 1) / chunk;
     const uint32_t grid = min(n_chunks, ctas);
     return launch_pdl(k_dice<Q, O>, grid, DICE_THREADS, sizeof(DiceSharedT<Q, O>), s, b, chunk);
 }
 
 cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
-    if (!b.segment_count) return cudaSuccess;
+    if (!b.segment_count || (b.dice_ranges && !b.n_dice_segments)) return cudaSuccess;
 #ifndef DICE_WIDE_Q
 #define DICE_WIDE_Q 512
 #define DICE_WIDE_CTAS 4
@@ -668,6 +684,11 @@ __device__ __forceinline__ uint32_t walk_step_emit(const BatchView &b, const Pat
 constexpr int BIN_CHAIN = 1032;          // crossings per axis the long-line kernel keeps in shared memory (16 K pixels)
 constexpr int BIN_LONG_WARPS = 4;
 
+// Incremental frames: line i is a retained line (diced in an earlier frame) of a path that has changed since
+__device__ __forceinline__ bool stale_line(const BatchView &b, uint32_t i, uint32_t path) {
+    return i < b.n_static_lines && b.dirty_paths && ((__ldg(&b.dirty_paths[path >> 5]) >> (path & 31u)) & 1u);
+}
+
 __global__ void __launch_bounds__(128) k_bin(BatchView b) {
     pdl_wait();
     const uint32_t n_lines = min(b.counters->n_lines, b.line_capacity);
@@ -699,6 +720,10 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
         const bool is_long = steps > BIN_LONG_STEPS;
         if (slot0 == 0xffffffffu) active = false;
         if (!active || is_long) continue;
+        if (stale_line(b, i, path)) {  // a retained line of a path that changed: its slots stay empty
+            for (uint32_t slot = slot0; slot < slot0 + slots; slot++) b.staging[slot].tile = 0xffffffffu;
+            continue;
+        }
         const PathTiles pt = load_path_tiles(b, path);
         Walk w;
         w.init(ln.x, ln.y, ln.z, ln.w);
@@ -801,6 +826,10 @@ __global__ void __launch_bounds__(BIN_LONG_WARPS * 32) k_bin_long(BatchView b) {
         const float4 ln = b.lines[i];
         const uint2 lm = b.line_meta[i];
         const uint32_t steps = walk_steps(ln), slot0 = lm.y;
+        if (stale_line(b, i, lm.x)) {  // (warp-uniform)
+            for (uint32_t slot = slot0 + lane; slot < slot0 + 2u * steps; slot += 32) b.staging[slot].tile = 0xffffffffu;
+            continue;
+        }
         const PathTiles pt = load_path_tiles(b, lm.x);
         Walk w;
         w.init(ln.x, ln.y, ln.z, ln.w);

@@ -107,7 +107,9 @@ constexpr int FILL_WARPS = 8;
 constexpr int FILL_GROUP = FILL_GROUP_N;  // alpha tiles a warp rasterizes together (2 or 4)
 constexpr float FILL_SCALE = 1048576.0f;  // coverage is accumulated in 12.20 fixed point (order-independent sums)
 constexpr int FILL_ONE = 1 << 20;
-constexpr int FILL_ACC = 17 * 16;         // accumulator of one tile: [row][column]; row 16 is a sink
+constexpr int FILL_CS = 20;               // accumulator of one tile: [column][row], 16 rows padded to 20 words: a lane's
+                                          // 16-byte loads of 8 consecutive rows are conflict free
+constexpr int FILL_ACC = 16 * FILL_CS;
 
 // Standalone fill kernel: a warp takes FILL_GROUP consecutive alpha tiles, and inside them one lane per
 // (fill, pixel column) PAIR.
@@ -126,7 +128,7 @@ struct __align__(16) FillShared {
     int acc[FILL_WARPS][FILL_GROUP][FILL_ACC];
 };
 
-__global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView p) {
+__global__ void __launch_bounds__(FILL_WARPS * 32, FILL_CTAS_PER_SM) k_fill(BatchView b, PaintView p) {
     __shared__ FillShared sh;
     pdl_wait();
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -147,7 +149,6 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
     for (int i = (int)lane; i < FILL_GROUP * FILL_ACC; i += 32) acc[i] = 0;
     __syncwarp();
     const bool band = p.lut_band != 0;
-    const int k_own = (int)(lane & 3u), s_own = (int)(lane >> 2);
 
     // (Handing the groups out through a global ticket counter instead -- one atomic per group, next ticket prefetched --
     // measured slower: 28.7 us against 24.6 us on tiger 4096^2, profiles/r01_tile_kernel_experiments.md.)
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
                 const float ks = dX * FILL_SCALE;
                 const int v_full = __float2int_rn(ks);
                 int prev = 0;
-                int *const colp = acc + (pbg & 3) * FILL_ACC + c;
+                int *const colp = acc + (pbg & 3) * FILL_ACC + c * FILL_CS;
                 int r0 = r_start;
                 for (; r0 <= r_end; r0 += 4) {
                     // texture(uAreaLUT, vec2((y + 8) / 16, v)) for the 4 rows r0 .. r0 + 3 (fill.comp:66-70), fp32 weights
@@ -267,65 +268,77 @@ __global__ void __launch_bounds__(FILL_WARPS * 32) k_fill(BatchView b, PaintView
                     const int v1 = __float2int_rn(fmaf(t11.y, k11, fmaf(t01.y, k01, fmaf(t10.y, k10, t00.y * k00))));
                     const int v2 = __float2int_rn(fmaf(t11.z, k11, fmaf(t01.z, k01, fmaf(t10.z, k10, t00.z * k00))));
                     const int v3 = __float2int_rn(fmaf(t11.w, k11, fmaf(t01.w, k01, fmaf(t10.w, k10, t00.w * k00))));
-                    atomicAdd(colp + r0 * 16, v0 - prev);  // r0 <= 15; the rows after it may be the sink row
-                    atomicAdd(colp + min(r0 + 1, 16) * 16, v1 - v0);
-                    atomicAdd(colp + min(r0 + 2, 16) * 16, v2 - v1);
-                    atomicAdd(colp + min(r0 + 3, 16) * 16, v3 - v2);
+                    atomicAdd(colp + r0, v0 - prev);  // r0 <= 12 (a multiple of 4): rows r0 .. r0 + 3 exist
+                    atomicAdd(colp + r0 + 1, v1 - v0);
+                    atomicAdd(colp + r0 + 2, v2 - v1);
+                    atomicAdd(colp + r0 + 3, v3 - v2);
                     prev = v3;
                 }
                 // every row below the sampled ones is fully covered by the window: one add (telescopes with `prev`)
                 const int tail = r0 > r_start ? r0 : max(r_hi + 1, 0);
-                if (tail <= 15) atomicAdd(colp + tail * 16, v_full - prev);
+                if (tail <= 15) atomicAdd(colp + tail, v_full - prev);
             }
         }
         __syncwarp();
         // ---- per tile: coverage = prefix sum down each column (+ backdrop), fill rule, clip, RGBA8-unorm quantisation
-        // (fill.comp:131-153). Lane (k, s) owns columns 4k .. 4k+3 of rows 2s and 2s+1: it reads its two 16-byte pieces
-        // of the accumulator (and zeroes them for the next group: nobody else reads them), and the sums of the rows
-        // above come from a scan over the lanes of the same column group (stride 4).
+        // (fill.comp:131-153). Lane (c, h) = (lane & 15, lane >> 4) owns rows 8h .. 8h+7 of column c: two 16-byte loads of
+        // the accumulator (zeroed for the next group at once: nobody else reads them), a serial prefix sum in registers and
+        // ONE shuffle for the upper half's total (round 1 kept the mask's lane layout here -- 4 columns x 2 rows -- and paid
+        // a 3-level shuffle scan of 4 values: 135 instructions per tile, 37 % of the kernel). The bytes then go to the
+        // mask's layout by a 4 x 4 byte transpose among the 4 lanes of a column group (2 shuffles + 2 byte permutes per
+        // word) and two 4-byte stores per lane.
+        const int c_own = (int)(lane & 15u), h_own = (int)(lane >> 4), j_own = (int)(lane & 3u);
+        // byte selectors of the two transpose rounds (lane-dependent, tile-independent)
+        const uint32_t sel1 = (j_own & 1) ? 0x3715u : 0x6240u;  // odd: [t1, w1, t3, w3]; even: [w0, t0, w2, t2]
+        const uint32_t sel2 = (j_own & 2) ? 0x3276u : 0x5410u;  // upper: [u2, u3, w2, w3]; lower: [w0, w1, u0, u1]
+        // after the transpose this lane holds pixel row 8h + j (from the first word) and 8h + 4 + j (second word) of columns
+        // 4k .. 4k+3; the mask's layout (pfcu_device.h) puts row y, columns 4k .. 4k+3 at byte ((y >> 1) * 4 + k) * 8 + (y & 1) * 4
+        const int k_grp = c_own >> 2, y_a = h_own * 8 + j_own, y_b = y_a + 4;
+        const uint32_t off_a = (uint32_t)(((y_a >> 1) * 4 + k_grp) * 8 + (y_a & 1) * 4);
+        const uint32_t off_b = (uint32_t)(((y_b >> 1) * 4 + k_grp) * 8 + (y_b & 1) * 4);
 #pragma unroll
         for (int g = 0; g < FILL_GROUP; g++) {
             const uint32_t at_x = __shfl_sync(0xffffffffu, at.x, g), at_y = __shfl_sync(0xffffffffu, at.y, g);
             const uint32_t at_w = __shfl_sync(0xffffffffu, at.w, g);
             if ((at_x & 0x7fffffffu) >= b.tile_count) continue;  // (warp-uniform)
-            int4 *const own = reinterpret_cast<int4 *>(acc + g * FILL_ACC) + (s_own * 8 + k_own);  // row 2s; row 2s+1 is own[4]
-            const int4 r0 = own[0], r1 = own[4];
+            int4 *const own = reinterpret_cast<int4 *>(acc + g * FILL_ACC + c_own * FILL_CS + h_own * 8);
+            const int4 ra = own[0], rb = own[1];
             own[0] = make_int4(0, 0, 0, 0);
-            own[4] = make_int4(0, 0, 0, 0);
-            if (lane < 4) reinterpret_cast<int4 *>(acc + g * FILL_ACC)[64 + lane] = make_int4(0, 0, 0, 0);  // the sink row
-            int4 t = make_int4(r0.x + r1.x, r0.y + r1.y, r0.z + r1.z, r0.w + r1.w);
-#pragma unroll
-            for (int d = 4; d < 32; d <<= 1) {
-                const int ux = __shfl_up_sync(0xffffffffu, t.x, d), uy = __shfl_up_sync(0xffffffffu, t.y, d);
-                const int uz = __shfl_up_sync(0xffffffffu, t.z, d), uw = __shfl_up_sync(0xffffffffu, t.w, d);
-                if (lane >= (unsigned)d) { t.x += ux; t.y += uy; t.z += uz; t.w += uw; }
-            }
-            const int bd = (int)(int8_t)(at_w & 0xffu) * FILL_ONE;
+            own[1] = make_int4(0, 0, 0, 0);
+            const int half_total = (ra.x + ra.y + ra.z) + (ra.w + rb.x + rb.y) + (rb.z + rb.w);
+            const int above = __shfl_xor_sync(0xffffffffu, half_total, 16);
             int cv[8];
-            cv[4] = bd + t.x; cv[5] = bd + t.y; cv[6] = bd + t.z; cv[7] = bd + t.w;          // row 2s+1: everything so far
-            cv[0] = cv[4] - r1.x; cv[1] = cv[5] - r1.y; cv[2] = cv[6] - r1.z; cv[3] = cv[7] - r1.w;  // row 2s
+            cv[0] = (int)(int8_t)(at_w & 0xffu) * FILL_ONE + (h_own ? above : 0) + ra.x;
+            cv[1] = cv[0] + ra.y; cv[2] = cv[1] + ra.z; cv[3] = cv[2] + ra.w;
+            cv[4] = cv[3] + rb.x; cv[5] = cv[4] + rb.y; cv[6] = cv[5] + rb.z; cv[7] = cv[6] + rb.w;
+            // round(v * 255) for v in [0, 1] as 12.20 fixed point = (v * 255 + 2^19) >> 20; scaled by 16 it is the TOP BYTE
+            // of a 32-bit product, which the byte permutes below pick up directly
             uint32_t bytes[8];
-            if (__any_sync(0xffffffffu, (at_x >> 31) != 0)) {  // winding: min(|cv|, 1)
+            if (at_x >> 31) {  // winding: min(|cv|, 1)
 #pragma unroll
-                for (int q = 0; q < 8; q++) bytes[q] = ((uint32_t)min(abs(cv[q]), FILL_ONE) * 255u + (1u << 19)) >> 20;
+                for (int q = 0; q < 8; q++) bytes[q] = (uint32_t)min(abs(cv[q]), FILL_ONE) * (255u << 4) + (1u << 23);
             } else {           // even-odd: 1 - |1 - mod(cv, 2)|
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
                     const int v = FILL_ONE - abs(FILL_ONE - (cv[q] & (2 * FILL_ONE - 1)));
-                    bytes[q] = ((uint32_t)v * 255u + (1u << 19)) >> 20;
+                    bytes[q] = (uint32_t)v * (255u << 4) + (1u << 23);
                 }
             }
-            uint2 m;
-            m.x = bytes[0] | (bytes[1] << 8) | (bytes[2] << 16) | (bytes[3] << 24);
-            m.y = bytes[4] | (bytes[5] << 8) | (bytes[6] << 16) | (bytes[7] << 24);
-            // (the vote makes the branch visibly warp-uniform: without it the byte-wise min is issued predicated-off for
-            // every tile, 6 % of the kernel's instructions on scenes without clips)
-            if (__any_sync(0xffffffffu, (int)at_y >= 0 && at_y < b.mask_capacity)) {  // fill.comp:147-150: min() with the clip mask
-                const uint2 clip = __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)at_y * 256) + lane);
-                m.x = __vminu4(m.x, clip.x);
-                m.y = __vminu4(m.y, clip.y);
+            // this lane's column as two words (rows 8h .. 8h+3, rows 8h+4 .. 8h+7), then the transposes
+            uint32_t wa = __byte_perm(__byte_perm(bytes[0], bytes[1], 0x0073), __byte_perm(bytes[2], bytes[3], 0x0073), 0x5410);
+            uint32_t wb = __byte_perm(__byte_perm(bytes[4], bytes[5], 0x0073), __byte_perm(bytes[6], bytes[7], 0x0073), 0x5410);
+            wa = __byte_perm(wa, __shfl_xor_sync(0xffffffffu, wa, 1), sel1);
+            wb = __byte_perm(wb, __shfl_xor_sync(0xffffffffu, wb, 1), sel1);
+            wa = __byte_perm(wa, __shfl_xor_sync(0xffffffffu, wa, 2), sel2);
+            wb = __byte_perm(wb, __shfl_xor_sync(0xffffffffu, wb, 2), sel2);
+            if ((int)at_y >= 0 && at_y < b.mask_capacity) {  // fill.comp:147-150: min() with the clip mask (warp-uniform)
+                const uint8_t *clip = b.masks + (size_t)at_y * 256;
+                wa = __vminu4(wa, __ldg(reinterpret_cast<const uint32_t *>(clip + off_a)));
+                wb = __vminu4(wb, __ldg(reinterpret_cast<const uint32_t *>(clip + off_b)));
             }
-            reinterpret_cast<uint2 *>(b.masks + (size_t)(first_alpha + a0 + g) * 256)[lane] = m;
+            uint8_t *const dst = b.masks + (size_t)(first_alpha + a0 + g) * 256;
+            *reinterpret_cast<uint32_t *>(dst + off_a) = wa;
+            *reinterpret_cast<uint32_t *>(dst + off_b) = wb;
         }
         __syncwarp();
         a0 += n_warps * FILL_GROUP;

@@ -16,7 +16,8 @@ NONE = 0xFFFFFFFF
 
 EXPORTS = [
     "pfcu_abi_version", "pfcu_last_error", "pfcu_create", "pfcu_destroy", "pfcu_set_stream", "pfcu_get_stream",
-    "pfcu_set_area_lut", "pfcu_set_target", "pfcu_set_target_origin", "pfcu_upload_scene", "pfcu_upload_paint_metadata", "pfcu_alloc_page",
+    "pfcu_set_area_lut", "pfcu_set_target", "pfcu_set_target_origin", "pfcu_upload_scene", "pfcu_update_scene_range",
+    "pfcu_upload_paint_metadata", "pfcu_alloc_page",
     "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
     "pfcu_submit_frame", "pfcu_wait_frame", "pfcu_read_target_region",
     "pfcu_read_target_async", "pfcu_wait_read", "pfcu_host_alloc", "pfcu_host_free",
@@ -43,8 +44,9 @@ class BatchDesc(C.Structure):
 class FrameStats(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("batches", "segments", "lines", "fills", "alpha_tiles", "dense_tiles",
                                           "listed_tiles", "listed_after_cull", "fb_tiles", "max_list_len",
-                                          "overflow_flags", "retries", "kernel_launches")] + \
-               [("reserved", C.c_uint32 * 3), ("gpu_ms", C.c_float)]
+                                          "overflow_flags", "retries", "kernel_launches", "diced_segments",
+                                          "uploaded_bytes")] + \
+               [("reserved", C.c_uint32 * 1), ("gpu_ms", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
@@ -77,6 +79,7 @@ def lib():
         L.pfcu_set_target.argtypes = [vp, i32, i32, vp, sz, vp]
         L.pfcu_set_target_origin.argtypes = [vp, i32, i32]
         L.pfcu_upload_scene.argtypes = [vp, i32, vp, u32, vp, u32]
+        L.pfcu_update_scene_range.argtypes = [vp, i32, u32, vp, u32, u32, u32]
         L.pfcu_upload_paint_metadata.argtypes = [vp, vp, u32]
         L.pfcu_alloc_page.argtypes = [vp, u32, i32, i32]
         L.pfcu_upload_page_region.argtypes = [vp, u32, i32, i32, i32, i32, vp]
@@ -185,6 +188,29 @@ class Renderer:
             pts = np.ascontiguousarray(scene[name + "_points"], "<f4")
             idx = np.ascontiguousarray(scene[name + "_indices"], "<u4")
             _check(self.L.pfcu_upload_scene(self.h, which, _p(pts), len(pts), _p(idx), len(idx)))
+
+    def set_incremental_dice(self, enabled):
+        """PFCU_OPT_INCREMENTAL_DICE (default off): later frames dice only the paths whose segments were updated."""
+        _check(self.L.pfcu_set_option(self.h, 2, int(bool(enabled))))
+
+    def update_scene(self, scene):
+        """Switch to `scene`, which differs from the current one only in the POINTS of some draw segments (same indices,
+        same batch structure: a path moved): uploads the changed point range (pfcu_update_scene_range) and takes the new
+        batch metadata. Returns (first_segment, n_segments) of the update."""
+        old, new = self.scene, scene
+        assert np.array_equal(old["draw_indices"], new["draw_indices"]) and old["draw_points"].shape == new["draw_points"].shape
+        changed = np.nonzero((old["draw_points"] != new["draw_points"]).any(axis=1))[0]
+        first_point, n_points = int(changed[0]), int(changed[-1] - changed[0] + 1)
+        fp = new["draw_indices"][:, 0]
+        first_seg = int(np.searchsorted(fp, first_point, side="right") - 1)
+        end_seg = int(np.searchsorted(fp, first_point + n_points - 1, side="right"))
+        pts = np.ascontiguousarray(new["draw_points"][first_point:first_point + n_points], "<f4")
+        _check(self.L.pfcu_update_scene_range(self.h, 0, first_point, _p(pts), n_points, first_seg, end_seg - first_seg))
+        self.scene = new
+        self._keep = []
+        self._descs = {"clip": [make_desc(b, self._keep) for b in new["clip_batches"]],
+                       "draw": [make_desc(b, self._keep) for b in new["draw_batches"]]}
+        return first_seg, end_seg - first_seg
 
     def upload_paints(self, scene):
         md = np.ascontiguousarray(scene["metadata"], "<u2")

@@ -43,6 +43,11 @@ SVG_SCENES = {
 DIGEST_ONLY = {
     "tiger_4096": ("tiger.svg", 4096, 900.0),      # BASELINE.json configs[2]
 }
+# The incremental-frame fixture: tiger 512 with ONE draw path moved (Outline::transform, core/data/path.h:20-21), built by
+# the reference front end like the others; inputs only (its pixels are compared with a full CUDA render of the same inputs,
+# which the other tests pin). name -> (base scene, draw path index, dx, dy)
+MOVED_SCENES = {"tiger_512_moved": ("tiger_512", 145, 23.25, -17.5)}
+
 # demo/common/app.cpp:21-101 blocks: 1 rect, 2 clip circle, 4 blurred shadow, 8 image, 16 gradient stroke, 32 render
 # target pattern. 0x3f = the whole primitives scene of the demo (shadow = two blur passes through render targets).
 # name -> (size, scale, feature mask)
@@ -119,9 +124,23 @@ def config4():
     print("config4", counts, dig)
 
 
+def moved_scene(name, base, index, dx, dy):
+    asset, size, native = SVG_SCENES[base]
+    s = pfref.RefScene.from_svg(pfref.asset(asset), size, size, size / native)
+    s.translate_draw_path(index, dx, dy)
+    scenes.save_scene(scenes.golden_path(name), s.build_d3d11())
+    s.close()
+    print(name, "path", index, "moved by", (dx, dy))
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "config4":
         config4()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "moved":
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+        for name, (base, index, dx, dy) in MOVED_SCENES.items():
+            moved_scene(name, base, index, dx, dy)
         return
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
     digests = {}
@@ -144,6 +163,8 @@ def main():
             scenes.save_scene(scenes.golden_path(name + "_scene"), scene)
         s.close()
         print(name, digests[name])
+    for name, (base, index, dx, dy) in MOVED_SCENES.items():
+        moved_scene(name, base, index, dx, dy)
     for name, (size, scale, features) in DEMO_SCENES.items():
         s = pfref.RefScene.demo(size, size, scale, pfref.asset("sea.png"), features)
         scene = s.build_d3d11()

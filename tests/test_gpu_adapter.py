@@ -24,8 +24,9 @@ LIB = os.path.join(ROOT, "oracle", "_ref", "libpfref_cuda.so")
 class FrameStats(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("batches", "segments", "lines", "fills", "alpha_tiles", "dense_tiles",
                                           "listed_tiles", "listed_after_cull", "fb_tiles", "max_list_len",
-                                          "overflow_flags", "retries", "kernel_launches")] + \
-               [("reserved", C.c_uint32 * 3), ("gpu_ms", C.c_float)]
+                                          "overflow_flags", "retries", "kernel_launches", "diced_segments",
+                                          "uploaded_bytes")] + \
+               [("reserved", C.c_uint32 * 1), ("gpu_ms", C.c_float)]
 
 
 def _asset(lib, name):

@@ -515,3 +515,53 @@ def test_async_readback_into_pinned_memory(renderer, area_lut):
     finally:
         a.close()
         b.close()
+
+
+def test_incremental_frames_redice_only_the_moved_path(renderer, area_lut):
+    """PFCU_OPT_INCREMENTAL_DICE + pfcu_update_scene_range (what SceneEpoch / LastSceneInfo::draw_segment_ranges are for,
+    core/scene.h:32-49): one tiger path moves (tests/golden/tiger_512_moved.npz, built by the reference front end from the
+    same SVG with Outline::transform on draw path 145). The animated frame uploads and dices that path's 168 segments only,
+    and its pixels, fills and tiles are those of a full render of the moved scene, bit for bit -- in both directions, and
+    again after the path has moved back."""
+    import pfcu
+
+    base, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    moved, _ = scenes.load_scene(scenes.golden_path("tiger_512_moved"))
+    bid = int(base["draw_batches"][0]["info"][0])
+    want = {}
+    for name, scene in (("base", base), ("moved", moved)):
+        renderer.set_scene(scene)
+        st = renderer.draw(clear=True)
+        want[name] = (renderer.pixels(), renderer.fills(bid), renderer.tiles(bid), st)
+    assert not np.array_equal(want["base"][0], want["moved"][0])
+    full = want["base"][3]
+    assert full["diced_segments"] == full["segments"] == 4399
+    r = pfcu.Renderer(0, area_lut)
+    try:
+        r.set_incremental_dice(True)
+        r.set_scene(base)
+        st = r.draw(clear=True)                      # the base frame: everything is diced
+        assert st["diced_segments"] == 4399
+        st = r.draw(clear=True)                      # nothing changed: nothing is diced, nothing but metadata uploaded
+        assert st["diced_segments"] == 0 and st["lines"] == full["lines"] and st["fills"] == full["fills"]
+        assert np.array_equal(r.pixels(), want["base"][0])
+        seq = [("moved", moved), ("base", base), ("moved", moved)]
+        for i, (name, scene) in enumerate(seq):
+            first_seg, n_seg = r.update_scene(scene)
+            assert n_seg == 168
+            st = r.draw(clear=True)
+            assert st["diced_segments"] == 168, st
+            assert st["uploaded_bytes"] < 0.6 * full["uploaded_bytes"]  # 4 KB of points instead of 121 KB of segments
+            assert st["fills"] == want[name][3]["fills"] and st["alpha_tiles"] == want[name][3]["alpha_tiles"]
+            assert np.array_equal(r.fills(bid), want[name][1]), "fills of frame %d" % i
+            got_t, want_t = r.tiles(bid), want[name][2]
+            for f in ("fill_count", "backdrop", "backdrop_delta", "listed"):
+                assert np.array_equal(got_t[f], want_t[f]), f
+            assert np.array_equal(r.pixels(), want[name][0]), "pixels of frame %d (%s)" % (i, name)
+        # a full upload invalidates what was retained: the next frame dices everything again
+        r.upload_segments(moved)
+        st = r.draw(clear=True)
+        assert st["diced_segments"] == 4399
+        assert np.array_equal(r.pixels(), want["moved"][0])
+    finally:
+        r.close()
