@@ -102,6 +102,19 @@ typedef struct {
     float gpu_ms; /* CUDA-event time of the frame on the context's stream (prepare..last draw), last attempt */
 } pfcu_frame_stats;
 
+/* Stroke style, as StrokeStyle (pathfinder/core/stroke.h:14-26). line_cap: 0 butt, 1 square, 2 round (LineCap);
+ * line_join: 0 miter, 1 bevel, 2 round (LineJoin). */
+typedef struct {
+    float line_width;
+    int32_t line_cap;
+    int32_t line_join;
+    float miter_limit;
+    /* Canvas::push_path transforms the finished outline by the canvas state's transform (core/canvas.cpp:190,
+     * Outline::transform, core/data/path.cpp:7-22): m11 m21 m12 m22 m13 m23, applied to every output point; an identity
+     * (1 0 0 1 0 0) leaves the points untouched, as upstream. */
+    float transform[6];
+} pfcu_stroke_style;
+
 /* ---- lifecycle */
 int pfcu_abi_version(void);
 const char *pfcu_last_error(void);

@@ -241,3 +241,50 @@ class RefScene:
         out = (C.c_double * iters)()
         lib().pfref_time_d3d11_build(self.h, iters, out)
         return np.array(list(out))
+
+
+def stroke_outline(points, flags, contour_first, closed, line_width, line_cap=0, line_join=0, miter_limit=10.0):
+    """The reference's OutlineStrokeToFill::offset (core/stroke.cpp:124-167) on an outline given as arrays (the oracle of
+    pfcu_stroke_to_fill). Returns (points (n, 2) f32, flags (n,) u8, contour_first (m + 1,) u32, cpu_ms)."""
+    L = lib()
+    fn = L.pfref_stroke_outline
+    fn.restype = C.c_size_t
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_int, C.c_float,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_double)]
+    pts = np.ascontiguousarray(points, "<f4").reshape(-1, 2)
+    fl = np.ascontiguousarray(flags, "u1")
+    cf = np.ascontiguousarray(contour_first, "<u4")
+    cl = np.ascontiguousarray(closed, "u1")
+    nc = C.c_uint32()
+    args = (pts.ctypes.data, fl.ctypes.data, cf.ctypes.data, cl.ctypes.data, len(cl), line_width, line_cap, line_join,
+            miter_limit)
+    n = fn(*args, None, None, None, C.byref(nc), None)
+    op = np.zeros((n, 2), "<f4")
+    of = np.zeros(n, "u1")
+    oc = np.zeros(nc.value + 1, "<u4")
+    ms = C.c_double()
+    fn(*args, op.ctypes.data, of.ctypes.data, oc.ctypes.data, C.byref(nc), C.byref(ms))
+    return op, of, oc, ms.value
+
+
+def dash_outline(points, flags, contour_first, closed, dashes, offset=0.0):
+    """The reference's OutlineDash (core/dash.cpp) on one outline given as arrays (the oracle of pfcu_dash_outlines).
+    Returns (points, flags, contour_first)."""
+    L = lib()
+    fn = L.pfref_dash_outline
+    fn.restype = C.c_size_t
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_float,
+                   C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+    pts = np.ascontiguousarray(points, "<f4").reshape(-1, 2)
+    fl = np.ascontiguousarray(flags, "u1")
+    cf = np.ascontiguousarray(contour_first, "<u4")
+    cl = np.ascontiguousarray(closed, "u1")
+    da = np.ascontiguousarray(dashes, "<f4")
+    nc = C.c_uint32()
+    args = (pts.ctypes.data, fl.ctypes.data, cf.ctypes.data, cl.ctypes.data, len(cl), da.ctypes.data, len(da), offset)
+    n = fn(*args, None, None, None, C.byref(nc))
+    op = np.zeros((n, 2), "<f4")
+    of = np.zeros(n, "u1")
+    oc = np.zeros(nc.value + 1, "<u4")
+    fn(*args, op.ctypes.data, of.ctypes.data, oc.ctypes.data, C.byref(nc))
+    return op, of, oc

@@ -27,6 +27,8 @@
 #include "pathfinder/core/d3d9/scene_builder.h"
 #include "pathfinder/core/renderer.h"
 #include "pathfinder/core/scene.h"
+#include "pathfinder/core/dash.h"
+#include "pathfinder/core/stroke.h"
 #include "pathfinder/core/svg.h"
 
 using namespace Pathfinder;
@@ -444,6 +446,89 @@ void pfref_time_d3d11_build(void *p, int iters, double *out_ms) {
         auto t1 = std::chrono::steady_clock::now();
         out_ms[i] = std::chrono::duration<double, std::milli>(t1 - t0).count();
     }
+}
+
+// ---------------------------------------------------------------- stroke-to-fill (the oracle of pfcu_stroke_to_fill)
+
+/// OutlineStrokeToFill::offset (core/stroke.cpp:124-167) on an outline given as arrays: points (x, y), flags (PointFlag:
+/// 0 on-curve, 1 control point 0, 2 control point 1), contour i = points [contour_first[i], contour_first[i + 1]), closed[i].
+/// One style for the whole outline. Query the sizes with null outputs: returns the number of output points and stores the
+/// number of output contours; out_contour_first gets n_out_contours + 1 entries. Returns the CPU time in out_ms (optional).
+size_t pfref_stroke_outline(const float *points, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
+                            uint32_t n_contours, float line_width, int line_cap, int line_join, float miter_limit,
+                            float *out_points, uint8_t *out_flags, uint32_t *out_contour_first, uint32_t *n_out_contours,
+                            double *out_ms) {
+    Logger::set_global_level(Logger::Level::Silence);
+    Outline outline;
+    for (uint32_t i = 0; i < n_contours; i++) {
+        Contour contour;
+        for (uint32_t k = contour_first[i]; k < contour_first[i + 1]; k++)
+            contour.push_point(Vec2F(points[2 * k], points[2 * k + 1]), (PointFlag)flags[k], true);
+        contour.closed = closed[i] != 0;
+        outline.contours.push_back(contour);  // (Outline::push_contour drops empty contours; the batch API keeps them)
+    }
+    StrokeStyle style;
+    style.line_width = line_width;
+    style.line_cap = (LineCap)line_cap;
+    style.line_join = (LineJoin)line_join;
+    style.miter_limit = miter_limit;
+    const auto t0 = std::chrono::steady_clock::now();
+    OutlineStrokeToFill stroker(outline, style);
+    stroker.offset();
+    const Outline &result = stroker.output;
+    if (out_ms) *out_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    size_t n = 0;
+    uint32_t c = 0;
+    for (const auto &contour : result.contours) {
+        if (out_contour_first) out_contour_first[c] = (uint32_t)n;
+        for (size_t k = 0; k < contour.points.size(); k++) {
+            if (out_points) {
+                out_points[2 * (n + k)] = contour.points[k].x;
+                out_points[2 * (n + k) + 1] = contour.points[k].y;
+            }
+            if (out_flags) out_flags[n + k] = (uint8_t)contour.flags[k];
+        }
+        n += contour.points.size();
+        c++;
+    }
+    if (out_contour_first) out_contour_first[c] = (uint32_t)n;
+    if (n_out_contours) *n_out_contours = c;
+    return n;
+}
+
+/// OutlineDash::dash + into_outline (core/dash.cpp:49-65) on an outline given as arrays (as pfref_stroke_outline).
+size_t pfref_dash_outline(const float *points, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
+                          uint32_t n_contours, const float *dashes, uint32_t n_dashes, float offset, float *out_points,
+                          uint8_t *out_flags, uint32_t *out_contour_first, uint32_t *n_out_contours) {
+    Logger::set_global_level(Logger::Level::Silence);
+    Outline outline;
+    for (uint32_t i = 0; i < n_contours; i++) {
+        Contour contour;
+        for (uint32_t k = contour_first[i]; k < contour_first[i + 1]; k++)
+            contour.push_point(Vec2F(points[2 * k], points[2 * k + 1]), (PointFlag)flags[k], true);
+        contour.closed = closed[i] != 0;
+        outline.contours.push_back(contour);
+    }
+    OutlineDash dasher(outline, std::vector<float>(dashes, dashes + n_dashes), offset);
+    dasher.dash();
+    const Outline result = dasher.into_outline();
+    size_t n = 0;
+    uint32_t c = 0;
+    for (const auto &contour : result.contours) {
+        if (out_contour_first) out_contour_first[c] = (uint32_t)n;
+        for (size_t k = 0; k < contour.points.size(); k++) {
+            if (out_points) {
+                out_points[2 * (n + k)] = contour.points[k].x;
+                out_points[2 * (n + k) + 1] = contour.points[k].y;
+            }
+            if (out_flags) out_flags[n + k] = (uint8_t)contour.flags[k];
+        }
+        n += contour.points.size();
+        c++;
+    }
+    if (out_contour_first) out_contour_first[c] = (uint32_t)n;
+    if (n_out_contours) *n_out_contours = c;
+    return n;
 }
 
 // ---------------------------------------------------------------- embedded assets (linked from /root/reference/assets)

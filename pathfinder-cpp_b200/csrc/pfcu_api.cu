@@ -20,6 +20,25 @@
 
 using namespace pfcu;
 
+namespace pfcu {
+// pfcu_stroke.cu
+cudaError_t launch_stroke_count(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
+                                const uint32_t *style_index, const pfcu_stroke_style *styles, uint32_t n_contours, uint32_t *counts,
+                                uint32_t *offsets, uint32_t *total, cudaStream_t s);
+cudaError_t launch_stroke_write(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
+                                const uint32_t *style_index, const pfcu_stroke_style *styles, uint32_t n_contours, uint32_t *counts,
+                                const uint32_t *offsets, float2 *out_pts, uint8_t *out_flags, cudaStream_t s);
+cudaError_t launch_dash_count(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
+                              const uint32_t *outline_first, const float *dashes, const uint32_t *dash_first, const float *dash_offset,
+                              uint32_t n_outlines, uint32_t *point_counts, uint32_t *contour_counts, uint32_t *point_offsets,
+                              uint32_t *contour_offsets, uint32_t *totals, cudaStream_t s);
+cudaError_t launch_dash_write(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
+                              const uint32_t *outline_first, const float *dashes, const uint32_t *dash_first, const float *dash_offset,
+                              uint32_t n_outlines, uint32_t *point_counts, uint32_t *contour_counts, const uint32_t *point_offsets,
+                              const uint32_t *contour_offsets, float2 *out_pts, uint8_t *out_flags, uint32_t *out_contour_first,
+                              cudaStream_t s);
+}  // namespace pfcu
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -153,6 +172,17 @@ struct pfcu_ctx {
     bool read_pending = false;  // a D2H copy of the target may still be running: the next frame's writes wait for it
     uint8_t *read_host = nullptr;  // ... into this buffer (re-issued if the frame it was enqueued behind is replayed)
     size_t read_pitch = 0;
+    // stroke-to-fill (pfcu_stroke_to_fill): inputs, counts / offsets, result
+    DevBuf stroke_in, stroke_counts, stroke_out;
+    PinnedBuf stroke_stage;
+    std::vector<uint32_t> stroke_host_counts;
+    std::vector<uint8_t> stroke_closed;
+    // dashing (pfcu_dash_outlines): result layout
+    uint32_t dash_n_outlines = 0, dash_points = 0, dash_contours = 0;
+    size_t dash_off_flags = 0, dash_off_contours = 0, dash_off_outlines = 0;
+    uint32_t stroke_n_contours = 0, stroke_total = 0;
+    size_t stroke_off_flags = 0;
+    float stroke_ms = 0.f;
     // static resources
     DevBuf lut;
     int lut_w = 0, lut_h = 0;
@@ -662,6 +692,10 @@ void pfcu_destroy(pfcu_ctx *c) {
         c->scene_dev[i].release();
         c->stage_scene[i].release();
     }
+    c->stroke_in.release();
+    c->stroke_counts.release();
+    c->stroke_out.release();
+    c->stroke_stage.release();
     c->lut.release();
     if (c->lut_tex) cudaDestroyTextureObject(c->lut_tex);
     if (c->lut_array) cudaFreeArray(c->lut_array);
@@ -948,6 +982,206 @@ int pfcu_upload_page_region(pfcu_ctx *c, uint32_t page, int x, int y, int width,
                           (size_t)width * 4, height, cudaMemcpyHostToDevice));
     return PFCU_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ stroke-to-fill
+
+int pfcu_stroke_to_fill(pfcu_ctx *c, const float *points, const uint8_t *flags, uint32_t n_points, const uint32_t *contour_first,
+                        const uint8_t *closed, const uint32_t *style_index, uint32_t n_contours, const pfcu_stroke_style *styles,
+                        uint32_t n_styles, uint32_t *n_out_contours, uint32_t *n_out_points) {
+    if (!c || (n_points && (!points || !flags)) || (n_contours && (!contour_first || !closed || !style_index || !styles || !n_styles)))
+        return fail(PFCU_ERR_INVALID, "bad stroke input");
+    for (uint32_t i = 0; i < n_contours; i++) {
+        if (contour_first[i] > contour_first[i + 1] || contour_first[i + 1] > n_points)
+            return fail(PFCU_ERR_INVALID, "contour %u: point range [%u, %u) outside the %u points", i, contour_first[i], contour_first[i + 1], n_points);
+        if (style_index[i] >= n_styles) return fail(PFCU_ERR_INVALID, "contour %u: style %u of %u", i, style_index[i], n_styles);
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    NvtxScope nvtx("pfcu_stroke_to_fill");
+    // one staged H2D copy: points | flags | contour_first | closed | style_index | styles (each 16-byte aligned)
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_pts = 0, o_flags = align16(o_pts + (size_t)n_points * 8), o_first = align16(o_flags + n_points);
+    const size_t o_closed = align16(o_first + ((size_t)n_contours + 1) * 4), o_style = align16(o_closed + n_contours);
+    const size_t o_styles = align16(o_style + (size_t)n_contours * 4), bytes = align16(o_styles + (size_t)n_styles * sizeof(pfcu_stroke_style));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));  // (the staging buffer of an earlier call may still be in flight)
+    CUDA_TRY(c->stroke_stage.ensure(bytes + 16));
+    CUDA_TRY(c->stroke_in.ensure(bytes + 16));
+    CUDA_TRY(c->stroke_counts.ensure(((size_t)n_contours * 4 + 4) * 4));
+    char *st = static_cast<char *>(c->stroke_stage.p);
+    if (n_points) {
+        memcpy(st + o_pts, points, (size_t)n_points * 8);
+        memcpy(st + o_flags, flags, n_points);
+    }
+    if (n_contours) {
+        memcpy(st + o_first, contour_first, ((size_t)n_contours + 1) * 4);
+        memcpy(st + o_closed, closed, n_contours);
+        memcpy(st + o_style, style_index, (size_t)n_contours * 4);
+        memcpy(st + o_styles, styles, (size_t)n_styles * sizeof(pfcu_stroke_style));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->stroke_in.p, st, bytes, cudaMemcpyHostToDevice, c->stream));
+    const char *d = c->stroke_in.as<char>();
+    uint32_t *counts = c->stroke_counts.as<uint32_t>(), *offsets = counts + 2 * (size_t)n_contours, *total = offsets + 2 * (size_t)n_contours;
+    c->stroke_n_contours = n_contours;
+    c->stroke_total = 0;
+    c->stroke_host_counts.assign(2 * (size_t)n_contours, 0u);
+    c->stroke_closed.assign(closed, closed + n_contours);
+    if (n_contours) {
+        CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
+        CUDA_TRY(launch_stroke_count(reinterpret_cast<const float2 *>(d + o_pts), reinterpret_cast<const uint8_t *>(d + o_flags),
+                                     reinterpret_cast<const uint32_t *>(d + o_first), reinterpret_cast<const uint8_t *>(d + o_closed),
+                                     reinterpret_cast<const uint32_t *>(d + o_style), reinterpret_cast<const pfcu_stroke_style *>(d + o_styles),
+                                     n_contours, counts, offsets, total, c->stream));
+        // the one mid-way read-back: the point total sizes the output (the counts themselves ride along: the host needs
+        // them to lay the output contours out)
+        CUDA_TRY(cudaMemcpyAsync(c->stroke_host_counts.data(), counts, 2 * (size_t)n_contours * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(&c->stroke_total, total, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->stroke_off_flags = align16((size_t)c->stroke_total * 8);
+        CUDA_TRY(c->stroke_out.ensure(c->stroke_off_flags + c->stroke_total + 16));
+        CUDA_TRY(launch_stroke_write(reinterpret_cast<const float2 *>(d + o_pts), reinterpret_cast<const uint8_t *>(d + o_flags),
+                                     reinterpret_cast<const uint32_t *>(d + o_first), reinterpret_cast<const uint8_t *>(d + o_closed),
+                                     reinterpret_cast<const uint32_t *>(d + o_style), reinterpret_cast<const pfcu_stroke_style *>(d + o_styles),
+                                     n_contours, counts, offsets, c->stroke_out.as<float2>(),
+                                     c->stroke_out.as<uint8_t>() + c->stroke_off_flags, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_end, c->stream));
+    }
+    uint32_t n_out = 0;
+    for (uint32_t i = 0; i < n_contours; i++) n_out += closed[i] ? 2u : 1u;
+    if (n_out_contours) *n_out_contours = n_out;
+    if (n_out_points) *n_out_points = c->stroke_total;
+    c->in_flight = true;
+    return PFCU_OK;
+}
+
+int pfcu_stroke_result(pfcu_ctx *c, float *out_points, uint8_t *out_flags, uint32_t *out_contour_first) {
+    if (!c || !out_contour_first || (c->stroke_total && (!out_points || !out_flags))) return fail(PFCU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->stroke_total) {
+        CUDA_TRY(cudaMemcpyAsync(out_points, c->stroke_out.p, (size_t)c->stroke_total * 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(out_flags, c->stroke_out.as<uint8_t>() + c->stroke_off_flags, c->stroke_total, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->stroke_ms = 0.f;
+    if (c->stroke_n_contours) cudaEventElapsedTime(&c->stroke_ms, c->ev_begin, c->ev_end);
+    // output contours in input order: two per closed input contour (outer, inner), one per open contour
+    uint32_t at = 0, k = 0;
+    const std::vector<uint32_t> &cnt = c->stroke_host_counts;
+    for (uint32_t i = 0; i < c->stroke_n_contours; i++) {
+        out_contour_first[k++] = at;
+        at += cnt[2 * i];
+        if (c->stroke_closed[i]) {
+            out_contour_first[k++] = at;
+            at += cnt[2 * i + 1];
+        }
+    }
+    out_contour_first[k] = at;
+    return PFCU_OK;
+}
+
+float pfcu_stroke_gpu_ms(pfcu_ctx *c) { return c ? c->stroke_ms : 0.f; }
+
+int pfcu_dash_outlines(pfcu_ctx *c, const float *points, const uint8_t *flags, uint32_t n_points, const uint32_t *contour_first,
+                       const uint8_t *closed, uint32_t n_contours, const uint32_t *outline_first, uint32_t n_outlines,
+                       const float *dashes, const uint32_t *dash_first, const float *dash_offset, uint32_t *n_out_contours,
+                       uint32_t *n_out_points) {
+    if (!c || (n_points && (!points || !flags)) || (n_contours && (!contour_first || !closed)) ||
+        (n_outlines && (!outline_first || !dashes || !dash_first || !dash_offset)))
+        return fail(PFCU_ERR_INVALID, "bad dash input");
+    for (uint32_t i = 0; i < n_contours; i++)
+        if (contour_first[i] > contour_first[i + 1] || contour_first[i + 1] > n_points)
+            return fail(PFCU_ERR_INVALID, "contour %u: point range outside the %u points", i, n_points);
+    for (uint32_t o = 0; o < n_outlines; o++)
+        if (outline_first[o] > outline_first[o + 1] || outline_first[o + 1] > n_contours || dash_first[o] > dash_first[o + 1])
+            return fail(PFCU_ERR_INVALID, "outline %u: bad contour or dash range", o);
+    CUDA_TRY(cudaSetDevice(c->device));
+    NvtxScope nvtx("pfcu_dash_outlines");
+    const uint32_t n_dash = n_outlines ? dash_first[n_outlines] : 0u;
+    auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_pts = 0, o_flags = align16((size_t)n_points * 8), o_first = align16(o_flags + n_points);
+    const size_t o_closed = align16(o_first + ((size_t)n_contours + 1) * 4), o_ofirst = align16(o_closed + n_contours);
+    const size_t o_dashes = align16(o_ofirst + ((size_t)n_outlines + 1) * 4), o_dfirst = align16(o_dashes + (size_t)n_dash * 4);
+    const size_t o_doff = align16(o_dfirst + ((size_t)n_outlines + 1) * 4), bytes = align16(o_doff + (size_t)n_outlines * 4);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c->stroke_stage.ensure(bytes + 16));
+    CUDA_TRY(c->stroke_in.ensure(bytes + 16));
+    CUDA_TRY(c->stroke_counts.ensure(((size_t)n_outlines * 4 + 4) * 4));
+    char *st = static_cast<char *>(c->stroke_stage.p);
+    if (n_points) {
+        memcpy(st + o_pts, points, (size_t)n_points * 8);
+        memcpy(st + o_flags, flags, n_points);
+    }
+    if (n_contours) {
+        memcpy(st + o_first, contour_first, ((size_t)n_contours + 1) * 4);
+        memcpy(st + o_closed, closed, n_contours);
+    }
+    if (n_outlines) {
+        memcpy(st + o_ofirst, outline_first, ((size_t)n_outlines + 1) * 4);
+        memcpy(st + o_dashes, dashes, (size_t)n_dash * 4);
+        memcpy(st + o_dfirst, dash_first, ((size_t)n_outlines + 1) * 4);
+        memcpy(st + o_doff, dash_offset, (size_t)n_outlines * 4);
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->stroke_in.p, st, bytes, cudaMemcpyHostToDevice, c->stream));
+    const char *d = c->stroke_in.as<char>();
+    uint32_t *pc = c->stroke_counts.as<uint32_t>(), *cc = pc + n_outlines, *po = cc + n_outlines, *co = po + n_outlines, *totals = co + n_outlines;
+    uint32_t host_totals[2] = {0, 0};
+    c->dash_n_outlines = n_outlines;
+    c->dash_points = c->dash_contours = 0;
+    if (n_outlines) {
+        CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
+        auto P = [&](size_t off) { return d + off; };
+        CUDA_TRY(launch_dash_count(reinterpret_cast<const float2 *>(P(o_pts)), reinterpret_cast<const uint8_t *>(P(o_flags)),
+                                   reinterpret_cast<const uint32_t *>(P(o_first)), reinterpret_cast<const uint8_t *>(P(o_closed)),
+                                   reinterpret_cast<const uint32_t *>(P(o_ofirst)), reinterpret_cast<const float *>(P(o_dashes)),
+                                   reinterpret_cast<const uint32_t *>(P(o_dfirst)), reinterpret_cast<const float *>(P(o_doff)), n_outlines,
+                                   pc, cc, po, co, totals, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(host_totals, totals, 8, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->dash_points = host_totals[0];
+        c->dash_contours = host_totals[1];
+        c->dash_off_flags = align16((size_t)c->dash_points * 8);
+        c->dash_off_contours = align16(c->dash_off_flags + c->dash_points);
+        c->dash_off_outlines = align16(c->dash_off_contours + ((size_t)c->dash_contours + 1) * 4);
+        CUDA_TRY(c->stroke_out.ensure(c->dash_off_outlines + ((size_t)n_outlines + 1) * 4 + 16));
+        char *o = c->stroke_out.as<char>();
+        CUDA_TRY(cudaMemsetAsync(o + c->dash_off_contours, 0, 4, c->stream));
+        CUDA_TRY(launch_dash_write(reinterpret_cast<const float2 *>(P(o_pts)), reinterpret_cast<const uint8_t *>(P(o_flags)),
+                                   reinterpret_cast<const uint32_t *>(P(o_first)), reinterpret_cast<const uint8_t *>(P(o_closed)),
+                                   reinterpret_cast<const uint32_t *>(P(o_ofirst)), reinterpret_cast<const float *>(P(o_dashes)),
+                                   reinterpret_cast<const uint32_t *>(P(o_dfirst)), reinterpret_cast<const float *>(P(o_doff)), n_outlines,
+                                   pc, cc, po, co, reinterpret_cast<float2 *>(o), reinterpret_cast<uint8_t *>(o + c->dash_off_flags),
+                                   reinterpret_cast<uint32_t *>(o + c->dash_off_contours), c->stream));
+        // contour ranges per outline = the exclusive scan of the contour counts (+ the total)
+        CUDA_TRY(cudaMemcpyAsync(o + c->dash_off_outlines, co, (size_t)n_outlines * 4, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(o + c->dash_off_outlines + (size_t)n_outlines * 4, totals + 1, 4, cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaEventRecord(c->ev_end, c->stream));
+    }
+    if (n_out_contours) *n_out_contours = c->dash_contours;
+    if (n_out_points) *n_out_points = c->dash_points;
+    c->in_flight = true;
+    return PFCU_OK;
+}
+
+int pfcu_dash_result(pfcu_ctx *c, float *out_points, uint8_t *out_flags, uint32_t *out_contour_first, uint32_t *out_outline_first) {
+    if (!c || !out_contour_first || !out_outline_first || (c->dash_points && (!out_points || !out_flags)))
+        return fail(PFCU_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    out_contour_first[0] = 0;
+    out_outline_first[0] = 0;
+    if (c->dash_n_outlines) {
+        const char *o = c->stroke_out.as<char>();
+        if (c->dash_points) {
+            CUDA_TRY(cudaMemcpyAsync(out_points, o, (size_t)c->dash_points * 8, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(out_flags, o + c->dash_off_flags, c->dash_points, cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_TRY(cudaMemcpyAsync(out_contour_first, o + c->dash_off_contours, ((size_t)c->dash_contours + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(out_outline_first, o + c->dash_off_outlines, ((size_t)c->dash_n_outlines + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->stroke_ms = 0.f;
+    if (c->dash_n_outlines) cudaEventElapsedTime(&c->stroke_ms, c->ev_begin, c->ev_end);
+    return PFCU_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ frame
 
 int pfcu_begin_frame(pfcu_ctx *c) {
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");

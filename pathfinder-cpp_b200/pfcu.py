@@ -21,6 +21,7 @@ EXPORTS = [
     "pfcu_upload_page_region", "pfcu_begin_frame", "pfcu_prepare_batch", "pfcu_draw_batch", "pfcu_end_frame",
     "pfcu_submit_frame", "pfcu_wait_frame", "pfcu_read_target_region",
     "pfcu_read_target_async", "pfcu_wait_read", "pfcu_host_alloc", "pfcu_host_free",
+    "pfcu_stroke_to_fill", "pfcu_stroke_result", "pfcu_stroke_gpu_ms", "pfcu_dash_outlines", "pfcu_dash_result",
     "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
     "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
     "pfcu_get_stage_times", "pfcu_set_option", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
@@ -92,6 +93,12 @@ def lib():
         L.pfcu_read_target.argtypes = [vp, vp]
         L.pfcu_read_target_region.argtypes = [vp, i32, i32, i32, i32, vp]
         L.pfcu_read_page.argtypes = [vp, u32, vp]
+        L.pfcu_stroke_to_fill.argtypes = [vp, vp, vp, u32, vp, vp, vp, u32, vp, u32, C.POINTER(u32), C.POINTER(u32)]
+        L.pfcu_stroke_result.argtypes = [vp, vp, vp, vp]
+        L.pfcu_dash_outlines.argtypes = [vp, vp, vp, u32, vp, vp, u32, vp, u32, vp, vp, vp, C.POINTER(u32), C.POINTER(u32)]
+        L.pfcu_dash_result.argtypes = [vp, vp, vp, vp, vp]
+        L.pfcu_stroke_gpu_ms.argtypes = [vp]
+        L.pfcu_stroke_gpu_ms.restype = C.c_float
         L.pfcu_read_target_async.argtypes = [vp, vp, sz]
         L.pfcu_wait_read.argtypes = [vp]
         L.pfcu_host_alloc.argtypes = [sz]
@@ -303,6 +310,49 @@ class Renderer:
         px = np.zeros((self.height, self.width, 4), "u1")
         _check(self.L.pfcu_read_target(self.h, _p(px)))
         return px
+
+    def stroke_to_fill(self, points, flags, contour_first, closed, style_index, styles):
+        """pfcu_stroke_to_fill + pfcu_stroke_result: OutlineStrokeToFill::offset for a batch of contours.
+        styles: (k, 4) rows of (line_width, line_cap, line_join, miter_limit). Returns (points (n, 2) f32, flags (n,) u8,
+        contour_first (m + 1,) u32, gpu_ms)."""
+        pts = np.ascontiguousarray(points, "<f4").reshape(-1, 2)
+        fl = np.ascontiguousarray(flags, "u1")
+        cf = np.ascontiguousarray(contour_first, "<u4")
+        cl = np.ascontiguousarray(closed, "u1")
+        si = np.ascontiguousarray(style_index, "<u4")
+        st = np.zeros(len(styles), np.dtype([("w", "<f4"), ("cap", "<i4"), ("join", "<i4"), ("miter", "<f4"),
+                                             ("transform", "<f4", (6,))]))
+        for i, row in enumerate(styles):  # (line_width, cap, join, miter_limit[, (m11, m21, m12, m22, m13, m23)])
+            st[i] = (row[0], int(row[1]), int(row[2]), row[3], row[4] if len(row) > 4 else (1, 0, 0, 1, 0, 0))
+        nc, npts = C.c_uint32(), C.c_uint32()
+        _check(self.L.pfcu_stroke_to_fill(self.h, _p(pts), _p(fl), len(pts), _p(cf), _p(cl), _p(si), len(cl), _p(st), len(st),
+                                          C.byref(nc), C.byref(npts)))
+        op = np.zeros((npts.value, 2), "<f4")
+        of = np.zeros(npts.value, "u1")
+        oc = np.zeros(nc.value + 1, "<u4")
+        _check(self.L.pfcu_stroke_result(self.h, _p(op), _p(of), _p(oc)))
+        return op, of, oc, float(self.L.pfcu_stroke_gpu_ms(self.h))
+
+    def dash_outlines(self, points, flags, contour_first, closed, outline_first, dashes, dash_first, dash_offset):
+        """pfcu_dash_outlines + pfcu_dash_result: OutlineDash for a batch of outlines. Returns (points, flags,
+        contour_first, outline_first, gpu_ms)."""
+        pts = np.ascontiguousarray(points, "<f4").reshape(-1, 2)
+        fl = np.ascontiguousarray(flags, "u1")
+        cf = np.ascontiguousarray(contour_first, "<u4")
+        cl = np.ascontiguousarray(closed, "u1")
+        of_ = np.ascontiguousarray(outline_first, "<u4")
+        da = np.ascontiguousarray(dashes, "<f4")
+        df = np.ascontiguousarray(dash_first, "<u4")
+        do = np.ascontiguousarray(dash_offset, "<f4")
+        nc, npts = C.c_uint32(), C.c_uint32()
+        _check(self.L.pfcu_dash_outlines(self.h, _p(pts), _p(fl), len(pts), _p(cf), _p(cl), len(cl), _p(of_), len(do), _p(da),
+                                         _p(df), _p(do), C.byref(nc), C.byref(npts)))
+        op = np.zeros((npts.value, 2), "<f4")
+        ofl = np.zeros(npts.value, "u1")
+        oc = np.zeros(nc.value + 1, "<u4")
+        oo = np.zeros(len(do) + 1, "<u4")
+        _check(self.L.pfcu_dash_result(self.h, _p(op), _p(ofl), _p(oc), _p(oo)))
+        return op, ofl, oc, oo, float(self.L.pfcu_stroke_gpu_ms(self.h))
 
     def pinned_frame(self):
         """A page-locked (height, width, 4) u8 array for read_async (pfcu_host_alloc); freed with the renderer."""
