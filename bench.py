@@ -545,15 +545,26 @@ def run_strips(args, rank, world, local, steps, warmup, gather):
     # frames in flight (p2p gather only): frame k + 1 is computed while frame k's strips are still arriving at rank 0
     # (7/8 of the canvas through one GPU's NVLink ingress); every frame in flight has its own context, stream and
     # presenting framebuffer
-    n_fly = max(1, args.strip_frames_in_flight) if (gather == "p2p" and world > 1) else 1
+    peer_modes = ("p2p", "copy")
+    sweep = [int(x) for x in str(args.strip_sweep).split(",") if x] if (args.strip_sweep and gather in peer_modes and world > 1) else []
+    n_fly = max([max(1, args.strip_frames_in_flight)] + sweep) if (gather in peer_modes and world > 1) else 1
     lanes = []
     full = None
     for k in range(n_fly):
         stream = torch.cuda.Stream()
         peer = None
+        local_strip = None
         if gather == "p2p" and world > 1:
             peer = sharding.PeerFramebuffer(size, size, world, rank, dev)
             target_ptr = peer.strip_ptr()
+        elif gather == "copy" and world > 1:
+            # render into a local strip; a copy engine pushes it into rank 0's framebuffer (rank 0 renders in place)
+            peer = sharding.PeerFramebuffer(size, size, world, rank, dev)
+            if rank == 0:
+                target_ptr = peer.strip_ptr()
+            else:
+                local_strip = torch.zeros((rows, size, 4), dtype=torch.uint8, device=dev)
+                target_ptr = local_strip.data_ptr()
         else:
             full = torch.zeros((rows * world, size, 4), dtype=torch.uint8, device=dev)
             target_ptr = full[rank * rows:].data_ptr()
@@ -570,17 +581,47 @@ def run_strips(args, rank, world, local, steps, warmup, gather):
             r.set_profiling(False)
             r.draw(clear=True)
         r.graph_capture()
-        lanes.append((r, stream, peer))
-    r, stream, peer = lanes[0]
+        lanes.append((r, stream, peer, local_strip))
+    r, stream, peer, _ = lanes[0]
     main = torch.cuda.Stream()
     counter = [0]
+    all_lanes = lanes
+    n_max = n_fly
+
+    def timed(k_fly):
+        """ms per frame with k_fly frames in flight (the first k_fly lanes)."""
+        nonlocal lanes, n_fly
+        lanes, n_fly = all_lanes[:k_fly], k_fly
+        counter[0] = 0
+        for _ in range(max(warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(main)
+        fork()
+        for _ in range(steps):
+            step()
+        join()
+        b.record(main)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tt = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0]) / steps
 
     def step():
-        q, qs, qp = lanes[counter[0] % n_fly]
+        q, qs, qp, qlocal = lanes[counter[0] % n_fly]
         counter[0] += 1
         q.graph_launch()
         if world > 1:
             if qp is not None:
+                if qlocal is not None:
+                    qp.push_strip(qlocal, qs)
                 with torch.cuda.stream(qs):
                     qp.barrier()
             else:
@@ -590,15 +631,21 @@ def run_strips(args, rank, world, local, steps, warmup, gather):
     def fork():
         ev = torch.cuda.Event()
         ev.record(main)
-        for _, qs, _ in lanes:
+        for _, qs, _, _ in lanes:
             qs.wait_event(ev)
 
     def join():
-        for _, qs, _ in lanes:
+        for _, qs, _, _ in lanes:
             ev = torch.cuda.Event()
             ev.record(qs)
             main.wait_event(ev)
 
+    sweep_ms = {}
+    for k_fly in sweep:  # (diagnostic: the same frames with other numbers of frames in flight)
+        sweep_ms[str(k_fly)] = timed(k_fly)
+    lanes, n_fly = all_lanes[:max(1, args.strip_frames_in_flight) if (gather in peer_modes and world > 1) else 1], \
+        (max(1, args.strip_frames_in_flight) if (gather in peer_modes and world > 1) else 1)
+    counter[0] = 0
     for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
@@ -619,7 +666,8 @@ def run_strips(args, rank, world, local, steps, warmup, gather):
         dist.barrier()
     total_ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    for q, _, _ in lanes:
+    lanes = all_lanes
+    for q, _, _, _ in lanes:
         gstats = q.graph_finish()
     t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
     units = torch.tensor([gstats[k] for k in ("segments", "lines", "fills", "alpha_tiles", "dense_tiles")],
@@ -657,16 +705,18 @@ def run_strips(args, rank, world, local, steps, warmup, gather):
             "verified_how": ("assembled %d-strip frame == 1-GPU render of the whole canvas (torch.equal, %d x %d x 4 bytes)"
                              % (world, size, size)) if world > 1 else "single GPU: nothing to assemble",
             "config": {"workload": "synthetic%d@%dx%d" % (args.paths, size, size), "sharding": "horizontal strips, one per rank",
-                       "gather": ("tile-kernel stores into rank 0's framebuffer over NVLink (peer mapping) + barrier"
-                                  if peer is not None else "one NCCL all-gather of %d-row blocks" % rows) if world > 1 else "none",
+                       "gather": ({"p2p": "tile-kernel stores into rank 0's framebuffer over NVLink (peer mapping) + barrier",
+                                   "copy": "strip rendered locally, pushed into rank 0's framebuffer by a copy engine "
+                                           "(cudaMemcpyAsync over the NVLink peer mapping) + barrier",
+                                   "nccl": "one NCCL all-gather of %d-row blocks" % rows}[gather]) if world > 1 else "none",
                        "l2": "framebuffer (%d MiB) larger than L2" % (size * size * 4 >> 20),
-                       "frames_in_flight": n_fly,
+                       "frames_in_flight": n_fly, "frames_in_flight_sweep_ms": sweep_ms,
                        "units_all_ranks": dict(zip(("segments", "lines", "fills", "alpha_tiles", "dense_tiles"),
                                                    (int(x) for x in units.tolist()))),
                        "rank0_stage_ms": stage_ms, "frame_ms_per_rank0": first["gpu_ms"]},
             "gpu_launches": int(gstats["kernel_launches"]) * steps, "clocks": clocks,
         }
-    for q, _, _ in lanes:
+    for q, _, _, _ in lanes:
         q.close()
     del lanes, full
     torch.cuda.empty_cache()
@@ -775,10 +825,11 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="skip the embedded batch / strip configurations")
     ap.add_argument("--paths", type=int, default=200000, help="synthetic workload: number of paths")
     ap.add_argument("--size", type=int, default=8192, help="synthetic workload: canvas size")
-    ap.add_argument("--gather", default="p2p", choices=["nccl", "p2p"], help="synthetic workload: strip assembly")
+    ap.add_argument("--gather", default="copy", choices=["nccl", "p2p", "copy"], help="synthetic workload: strip assembly")
     ap.add_argument("--frames", type=int, default=0, help="batch mode: render this many independent frames per step")
     ap.add_argument("--contexts", type=int, default=16, help="batch mode: renderer contexts (streams) per GPU")
     ap.add_argument("--strip-frames-in-flight", type=int, default=2, help="synthetic workload, --gather p2p: frames in flight")
+    ap.add_argument("--strip-sweep", default="", help="synthetic workload, --gather p2p: also time these numbers of frames in flight (e.g. 1,3,4)")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="value leg: contexts replaying their frame graph side by side")
     ap.add_argument("--e2e-contexts", type=int, default=6, help="e2e leg: frames in flight (1 = blocking pfcu_end_frame)")
     args = ap.parse_args()
@@ -807,8 +858,9 @@ def main():
         if not args.no_sharded:
             # the configurations that shard (BASELINE.json configs 4 and 5), under the driver's own command and clock
             sharded = {"batch": run_batch(args, rank, world, local, 4096, 3, 1, "tiger512"),
-                       "strips": run_strips(args, rank, world, local, 20, 3, "p2p")}
-            if world > 1:
+                       "strips": run_strips(args, rank, world, local, 20, 3, "copy")}
+            if world > 1:  # the other two ways of assembling the frame, for comparison
+                sharded["strips_kernel_stores"] = run_strips(args, rank, world, local, 20, 3, "p2p")
                 sharded["strips_nccl"] = run_strips(args, rank, world, local, 20, 3, "nccl")
             if line is not None:
                 line["sharded"] = sharded

@@ -288,3 +288,23 @@ def dash_outline(points, flags, contour_first, closed, dashes, offset=0.0):
     oc = np.zeros(nc.value + 1, "<u4")
     fn(*args, op.ctypes.data, of.ctypes.data, oc.ctypes.data, C.byref(nc))
     return op, of, oc
+
+
+def svg_stroke_inputs(svg_bytes):
+    """Every stroked shape of an SVG as SvgScene hands it to Canvas::stroke_path (core/svg.cpp:155-196): outline before
+    dash / stroke / transform + style. Returns dict(points, flags, contour_first, closed, shape_first, styles (n, 5:
+    width, cap, join, miter, dash offset), dashes, dash_first)."""
+    L = lib()
+    fn = L.pfref_svg_stroke_inputs
+    fn.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p] + [C.c_void_p] * 8
+    counts = np.zeros(4, "<u4")
+    if fn(svg_bytes, len(svg_bytes), counts.ctypes.data, *([None] * 8)) != 0:
+        raise RuntimeError("nanosvg could not parse the document")
+    ns, nc, npt, nd = (int(x) for x in counts)
+    out = dict(points=np.zeros((npt, 2), "<f4"), flags=np.zeros(npt, "u1"), contour_first=np.zeros(nc + 1, "<u4"),
+               closed=np.zeros(nc, "u1"), shape_first=np.zeros(ns + 1, "<u4"), styles=np.zeros((ns, 5), "<f4"),
+               dashes=np.zeros(max(nd, 1), "<f4"), dash_first=np.zeros(ns + 1, "<u4"))
+    fn(svg_bytes, len(svg_bytes), counts.ctypes.data, *(out[k].ctypes.data for k in
+       ("points", "flags", "contour_first", "closed", "shape_first", "styles", "dashes", "dash_first")))
+    out["dashes"] = out["dashes"][:nd]
+    return out

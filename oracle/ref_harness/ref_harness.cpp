@@ -18,6 +18,8 @@
 #include <string>
 #include <vector>
 
+#include <nanosvg.h>
+
 #include "demo_scene.h"
 #include "null_device.h"
 #include "pathfinder/common/io.h"
@@ -529,6 +531,70 @@ size_t pfref_dash_outline(const float *points, const uint8_t *flags, const uint3
     if (out_contour_first) out_contour_first[c] = (uint32_t)n;
     if (n_out_contours) *n_out_contours = c;
     return n;
+}
+
+/// What SvgScene hands to Canvas::stroke_path for every shape with a visible stroke (core/svg.cpp:155-196): the shape's
+/// outline BEFORE dashing, stroking and the canvas transform, and its stroke style. Shapes in document order. Two-call
+/// pattern: null outputs to query. counts[4] = {shapes, contours, points, dash values}. style rows: line_width, line_cap,
+/// line_join, miter_limit, dash_offset.
+int pfref_svg_stroke_inputs(const char *svg, size_t len, uint32_t counts[4], float *points, uint8_t *flags, uint32_t *contour_first,
+                            uint8_t *closed, uint32_t *shape_first, float *styles, float *dashes, uint32_t *dash_first) {
+    std::string copy(svg, svg + len);
+    NSVGimage *image = nsvgParse((char *)copy.data(), "px", 96);
+    if (!image) return -1;
+    uint32_t n_shapes = 0, n_contours = 0, n_points = 0, n_dashes = 0;
+    if (contour_first) contour_first[0] = 0;
+    if (shape_first) shape_first[0] = 0;
+    if (dash_first) dash_first[0] = 0;
+    for (NSVGshape *shape = image->shapes; shape != nullptr; shape = shape->next) {
+        // Canvas::stroke_path strokes when the stroke paint is visible and the width positive (canvas.cpp:281)
+        if (shape->stroke.type == NSVG_PAINT_NONE || !(shape->strokeWidth > 0)) continue;
+        if (shape->stroke.type == NSVG_PAINT_COLOR && ColorU(shape->stroke.color).a_ == 0) continue;
+        Path2d path;
+        for (NSVGpath *p = shape->paths; p != nullptr; p = p->next) {
+            path.move_to(p->pts[0], p->pts[1]);
+            for (int i = 0; i < p->npts - 3; i += 3) {
+                float *q = &p->pts[i * 2];
+                path.cubic_to(q[2], q[3], q[4], q[5], q[6], q[7]);
+            }
+            if (p->closed) path.close_path();
+        }
+        const Outline outline = path.into_outline();
+        for (const auto &contour : outline.contours) {
+            for (size_t k = 0; k < contour.points.size(); k++) {
+                if (points) {
+                    points[2 * (n_points + k)] = contour.points[k].x;
+                    points[2 * (n_points + k) + 1] = contour.points[k].y;
+                }
+                if (flags) flags[n_points + k] = (uint8_t)contour.flags[k];
+            }
+            n_points += (uint32_t)contour.points.size();
+            if (closed) closed[n_contours] = contour.closed ? 1 : 0;
+            n_contours++;
+            if (contour_first) contour_first[n_contours] = n_points;
+        }
+        if (styles) {
+            float *st = styles + 5 * n_shapes;
+            st[0] = shape->strokeWidth;
+            st[1] = shape->strokeLineCap == NSVG_CAP_ROUND ? 2.f : shape->strokeLineCap == NSVG_CAP_SQUARE ? 1.f : 0.f;
+            st[2] = shape->strokeLineJoin == NSVG_JOIN_ROUND ? 2.f : shape->strokeLineJoin == NSVG_JOIN_BEVEL ? 1.f : 0.f;
+            st[3] = shape->miterLimit;
+            st[4] = shape->strokeDashOffset;
+        }
+        for (int k = 0; k < shape->strokeDashCount; k++) {
+            if (dashes) dashes[n_dashes] = shape->strokeDashArray[k];
+            n_dashes++;
+        }
+        n_shapes++;
+        if (shape_first) shape_first[n_shapes] = n_contours;
+        if (dash_first) dash_first[n_shapes] = n_dashes;
+    }
+    nsvgDelete(image);
+    counts[0] = n_shapes;
+    counts[1] = n_contours;
+    counts[2] = n_points;
+    counts[3] = n_dashes;
+    return 0;
 }
 
 // ---------------------------------------------------------------- embedded assets (linked from /root/reference/assets)

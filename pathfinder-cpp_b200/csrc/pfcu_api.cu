@@ -596,8 +596,9 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
         if (c->aux_pending == s.fill_done) c->aux_pending = nullptr;
         s.fill_done = nullptr;
     }
-    LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, cmd.target_page < 0, s.heavy_paints, c->stream));
-    c->launches += 1;
+    int n_launched = 0;
+    LAUNCH_STAGE(PFCU_STAGE_COMPOSITE, launch_composite(s.view, pv, t, clear, cmd.clear_color, cmd.target_page < 0, s.heavy_paints, c->stream, &n_launched));
+    c->launches += (uint32_t)n_launched;
     c->in_flight = true;
     return PFCU_OK;
 }

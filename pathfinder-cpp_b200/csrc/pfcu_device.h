@@ -208,8 +208,9 @@ cudaError_t launch_scan_fb(const BatchView &b, cudaStream_t s);
 cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s);
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s);
 // origin != 0: the target is the destination framebuffer, whose tile (0, 0) is scene tile (fb_tx0, fb_ty0)
+// (n_launched: kernels enqueued -- a batch that mixes plain and textured paints on a large target takes two passes)
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
-                             const float clear_color[4], int origin, int heavy_paints, cudaStream_t s);
+                             const float clear_color[4], int origin, int heavy_paints, cudaStream_t s, int *n_launched = nullptr);
 
 constexpr int MAX_DEVICES = 64;
 int current_device();  // clamped to [0, MAX_DEVICES)

@@ -1074,13 +1074,15 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
 }
 
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
-                             const float clear_color[4], int origin, int heavy_paints, cudaStream_t s) {
+                             const float clear_color[4], int origin, int heavy_paints, cudaStream_t s, int *n_launched) {
+    if (n_launched) *n_launched = 0;
     if (b.fb_tw <= 0 || b.fb_th <= 0) return cudaSuccess;
     // tiles of the scene's grid that the target covers (its top-left corner is the grid's: pages have no origin)
     const uint32_t sub_tw = (uint32_t)min(b.fb_tw, (t.width + TILE - 1) / TILE);
     const uint32_t sub_th = (uint32_t)min(b.fb_th, (t.height + TILE - 1) / TILE);
     const uint32_t n_fb = sub_tw * sub_th;
     if (!n_fb) return cudaSuccess;
+    if (n_launched) *n_launched = 1;
     const float4 cc = make_float4(clear_color[0], clear_color[1], clear_color[2], clear_color[3]);
     // the plain-colour instantiation skips the saturation before the RGBA8 conversion: src-over of premultiplied colours
     // in [0, 1] stays in [0, 1]

@@ -75,6 +75,21 @@ class PeerFramebuffer:
     def barrier(self):
         self.handle.barrier()
 
+    def root_strip(self, rank=None):
+        """Rank `rank`'s rows of the presenting rank's framebuffer as a tensor (rows, width, 4) on THIS process: the
+        destination of a copy-engine push (`push_strip`)."""
+        rank = self.rank if rank is None else rank
+        n = self.rows * self.width * 4
+        return self.handle.get_buffer(self.root, (n,), torch.uint8, rank * n).view(self.rows, self.width, 4)
+
+    def push_strip(self, local, stream):
+        """Device-to-device copy of this rank's finished strip into the presenting rank's framebuffer over NVLink, on
+        `stream`. It is a cudaMemcpyAsync between two contiguous buffers: a COPY ENGINE moves the bytes, so the SMs are free
+        for the next frame while 7/8 of the canvas funnels through one GPU's NVLink ingress (when the tile kernel stores
+        across NVLink itself, its CTAs sit on every SM waiting for the link and nothing else can be scheduled)."""
+        with torch.cuda.stream(stream):
+            self.root_strip().copy_(local, non_blocking=True)
+
     def frame(self, height):
         """The assembled frame (valid on the root rank after barrier())."""
         return self.local.view(self.rows * self.world, self.width, 4)[:height]

@@ -181,3 +181,79 @@ def test_dash_matches_the_reference_dasher_bit_for_bit(renderer, pfref):
     g = renderer.stroke_to_fill(got[0], got[1], got[2], np.zeros(n_d, "u1"), np.zeros(n_d, "<u4"), [style])
     w = pfref.stroke_outline(got[0], got[1], got[2], np.zeros(n_d, "u1"), *style)
     assert np.array_equal(g[2], w[2]) and np.array_equal(g[1], w[1]) and _equal_bits(g[0], w[0])
+
+
+def _svg_stroke_chain_gpu(renderer, d, scale):
+    """Canvas::stroke_path for every stroked shape of an SVG, on the GPU: dash (shapes with a dash array), stroke-to-fill,
+    canvas transform. Returns per shape (points, flags, contour_first)."""
+    ns = len(d["styles"])
+    pts, fl, cf, cl, sf = d["points"], d["flags"], d["contour_first"], d["closed"], d["shape_first"]
+    dashed = [s for s in range(ns) if d["dash_first"][s + 1] > d["dash_first"][s]]
+    per_shape = {}
+    if dashed:  # one batch of outlines = the dashed shapes
+        sel_c = np.concatenate([np.arange(sf[s], sf[s + 1]) for s in dashed])
+        lo = [int(cf[c]) for c in sel_c]
+        hi = [int(cf[c + 1]) for c in sel_c]
+        p = np.concatenate([pts[a:b] for a, b in zip(lo, hi)])
+        f = np.concatenate([fl[a:b] for a, b in zip(lo, hi)])
+        c_first = np.concatenate([[0], np.cumsum([b - a for a, b in zip(lo, hi)])]).astype("<u4")
+        o_first = np.concatenate([[0], np.cumsum([sf[s + 1] - sf[s] for s in dashed])]).astype("<u4")
+        dashes = np.concatenate([d["dashes"][d["dash_first"][s]:d["dash_first"][s + 1]] for s in dashed])
+        d_first = np.concatenate([[0], np.cumsum([d["dash_first"][s + 1] - d["dash_first"][s] for s in dashed])]).astype("<u4")
+        got = renderer.dash_outlines(p, f, c_first, cl[sel_c], o_first, dashes, d_first, [float(d["styles"][s][4]) for s in dashed])
+        for k, s in enumerate(dashed):
+            g0, g1 = int(got[3][k]), int(got[3][k + 1])
+            a, b = int(got[2][g0]), int(got[2][g1])
+            per_shape[s] = (got[0][a:b], got[1][a:b], got[2][g0:g1 + 1] - a, np.zeros(g1 - g0, "u1"))
+    for s in range(ns):
+        if s not in per_shape:
+            c0, c1 = int(sf[s]), int(sf[s + 1])
+            a, b = int(cf[c0]), int(cf[c1])
+            per_shape[s] = (pts[a:b], fl[a:b], cf[c0:c1 + 1] - a, cl[c0:c1])
+    # one stroke batch over every shape's contours, a style per shape
+    all_p = np.concatenate([per_shape[s][0] for s in range(ns)])
+    all_f = np.concatenate([per_shape[s][1] for s in range(ns)])
+    counts = [len(per_shape[s][3]) for s in range(ns)]
+    firsts, at = [0], 0
+    for s in range(ns):
+        firsts.extend((per_shape[s][2][1:] + at).tolist())
+        at += len(per_shape[s][0])
+    all_cl = np.concatenate([per_shape[s][3] for s in range(ns)])
+    style_index = np.repeat(np.arange(ns), counts).astype("<u4")
+    styles = [(float(st[0]), int(st[1]), int(st[2]), float(st[3]), (scale, 0, 0, scale, 0, 0)) for st in d["styles"]]
+    g = renderer.stroke_to_fill(all_p, all_f, np.array(firsts, "<u4"), all_cl, style_index, styles)
+    out, k = [], 0
+    for s in range(ns):
+        n_out = int(sum(2 if c else 1 for c in per_shape[s][3]))
+        a, b = int(g[2][k]), int(g[2][k + n_out])
+        out.append((g[0][a:b], g[1][a:b], g[2][k:k + n_out + 1] - a))
+        k += n_out
+    return out, g[3]
+
+
+@pytest.mark.parametrize("asset,scale", [("tiger.svg", 4096 / 900.0), ("features.svg", 2048 / 720.0)])
+def test_svg_strokes_from_unstroked_outlines(renderer, pfref, asset, scale):
+    """Every stroked shape of tiger.svg / features.svg (caps, joins and a dashed path) as SvgScene hands it to
+    Canvas::stroke_path (core/svg.cpp:155-196, oracle/ref_harness pfref_svg_stroke_inputs): the GPU chain dash -> stroke ->
+    canvas transform equals OutlineDash -> OutlineStrokeToFill -> Outline::transform of the reference, bit for bit."""
+    d = pfref.svg_stroke_inputs(pfref.asset(asset))
+    got, gpu_ms = _svg_stroke_chain_gpu(renderer, d, np.float32(scale))
+    s32 = np.float32(scale)
+    n_points = 0
+    for s in range(len(d["styles"])):
+        c0, c1 = int(d["shape_first"][s]), int(d["shape_first"][s + 1])
+        a, b = int(d["contour_first"][c0]), int(d["contour_first"][c1])
+        p, f, cf, cl = d["points"][a:b], d["flags"][a:b], d["contour_first"][c0:c1 + 1] - a, d["closed"][c0:c1]
+        dashes = d["dashes"][d["dash_first"][s]:d["dash_first"][s + 1]]
+        if len(dashes):
+            p, f, cf = pfref.dash_outline(p, f, cf, cl, dashes, float(d["styles"][s][4]))
+            cl = np.zeros(len(cf) - 1, "u1")
+        st = d["styles"][s]
+        wp, wf, wc, _ = pfref.stroke_outline(p, f, cf, cl, float(st[0]), int(st[1]), int(st[2]), float(st[3]))
+        x, y = wp[:, 0], wp[:, 1]
+        wp = np.stack([(s32 * x + np.float32(0) * y) + np.float32(0), (np.float32(0) * x + s32 * y) + np.float32(0)], 1).astype("<f4")
+        assert np.array_equal(got[s][2], wc) and np.array_equal(got[s][1], wf), "shape %d layout" % s
+        assert _equal_bits(got[s][0], wp), "shape %d points" % s
+        n_points += len(wp)
+    print("%s: %d stroked shapes, %d output points, GPU stroke passes %.3f ms" % (asset, len(d["styles"]), n_points, gpu_ms))
+    assert n_points > 1000
