@@ -828,7 +828,7 @@ def main():
     ap.add_argument("--gather", default="copy", choices=["nccl", "p2p", "copy"], help="synthetic workload: strip assembly")
     ap.add_argument("--frames", type=int, default=0, help="batch mode: render this many independent frames per step")
     ap.add_argument("--contexts", type=int, default=16, help="batch mode: renderer contexts (streams) per GPU")
-    ap.add_argument("--strip-frames-in-flight", type=int, default=2, help="synthetic workload, --gather p2p: frames in flight")
+    ap.add_argument("--strip-frames-in-flight", type=int, default=4, help="synthetic workload, --gather p2p: frames in flight")
     ap.add_argument("--strip-sweep", default="", help="synthetic workload, --gather p2p: also time these numbers of frames in flight (e.g. 1,3,4)")
     ap.add_argument("--frames-in-flight", type=int, default=4, help="value leg: contexts replaying their frame graph side by side")
     ap.add_argument("--e2e-contexts", type=int, default=6, help="e2e leg: frames in flight (1 = blocking pfcu_end_frame)")

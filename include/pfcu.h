@@ -162,6 +162,35 @@ int pfcu_upload_paint_metadata(pfcu_ctx *ctx, const uint16_t *half_texels, uint3
 int pfcu_alloc_page(pfcu_ctx *ctx, uint32_t page, int width, int height);
 int pfcu_upload_page_region(pfcu_ctx *ctx, uint32_t page, int x, int y, int width, int height, const uint8_t *rgba);
 
+/* ---- stroke-to-fill (replaces OutlineStrokeToFill::offset, pathfinder/core/stroke.cpp:124-167, which Canvas::stroke_path runs
+ * on the CPU for every stroked path, core/canvas.cpp:272-301) for a batch of contours at once. Input, host memory: the
+ * contours' points (x, y) and point flags (0 on-curve, 1 first / quadratic control point, 2 second control point:
+ * PointFlag, core/data/data.h:42-51) back to back; contour i owns points [contour_first[i], contour_first[i + 1]) and is
+ * closed iff closed[i]; it is stroked with styles[style_index[i]]. pfcu_stroke_to_fill runs the two passes and keeps the result
+ * in the context; its contour / point totals come back through the out parameters, pfcu_stroke_result copies it out:
+ * out_contour_first has n_out_contours + 1 entries. A closed contour yields two output contours (outer and inner offset),
+ * an open one a single contour with its caps, in input order -- the Outline the reference would push_draw_path. Every
+ * output point equals the reference's bit for bit (the kernels are compiled without FMA contraction, like the reference). */
+int pfcu_stroke_to_fill(pfcu_ctx *ctx, const float *points, const uint8_t *flags, uint32_t n_points, const uint32_t *contour_first,
+                        const uint8_t *closed, const uint32_t *style_index, uint32_t n_contours, const pfcu_stroke_style *styles,
+                        uint32_t n_styles, uint32_t *n_out_contours, uint32_t *n_out_points);
+int pfcu_stroke_result(pfcu_ctx *ctx, float *out_points, uint8_t *out_flags, uint32_t *out_contour_first);
+/* Device time (ms, CUDA events) of the two passes of the last pfcu_stroke_to_fill / pfcu_dash_outlines (valid after the
+ * matching _result call). */
+float pfcu_stroke_gpu_ms(pfcu_ctx *ctx);
+/* Dashing (replaces OutlineDash::dash + into_outline, pathfinder/core/dash.cpp:49-65, which Canvas::stroke_path runs before the
+ * stroker when a line dash is set, core/canvas.cpp:286-291) for a batch of outlines. Outline o owns the contours
+ * [outline_first[o], outline_first[o + 1]) of the input (same arrays as pfcu_stroke_to_fill) and is dashed with the pattern
+ * dashes[dash_first[o] .. dash_first[o + 1]) at phase dash_offset[o]; the dash state runs on from one contour of an outline
+ * into the next, as upstream. The result -- open contours, ready for pfcu_stroke_to_fill -- stays in the context;
+ * pfcu_dash_result copies it out: out_contour_first has n_out_contours + 1 entries, out_outline_first n_outlines + 1
+ * (contour ranges per input outline). Bit-identical to the reference's points. */
+int pfcu_dash_outlines(pfcu_ctx *ctx, const float *points, const uint8_t *flags, uint32_t n_points, const uint32_t *contour_first,
+                       const uint8_t *closed, uint32_t n_contours, const uint32_t *outline_first, uint32_t n_outlines,
+                       const float *dashes, const uint32_t *dash_first, const float *dash_offset, uint32_t *n_out_contours,
+                       uint32_t *n_out_points);
+int pfcu_dash_result(pfcu_ctx *ctx, float *out_points, uint8_t *out_flags, uint32_t *out_contour_first, uint32_t *out_outline_first);
+
 /* ---- frame: RendererD3D11::draw (d3d11/renderer.cpp:302-336) */
 int pfcu_begin_frame(pfcu_ctx *ctx);
 /* prepare_tiles (renderer.cpp:510-616): bound + dice + bin + propagate + fill + sort for one batch.

@@ -7,6 +7,6 @@ run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-
 timeout 1500 bash -c "$(declare -f run); n=$n; run --steps 20 --warmup 3" > $out/bench_n$n.json 2> $out/bench_n$n.err
 echo "rc=$?"; tail -3 $out/bench_n$n.err; cut -c1-300 $out/bench_n$n.json
 if [ -n "$sweep" ]; then
-  timeout 900 bash -c "$(declare -f run); n=$n; run --workload synthetic --gather copy --steps 20 --warmup 3 --strip-frames-in-flight 2 --strip-sweep $sweep" > $out/strips_n$n.json 2> $out/strips_n$n.err
+  timeout 900 bash -c "$(declare -f run); n=$n; run --workload synthetic --gather copy --steps 20 --warmup 3 --strip-frames-in-flight 4 --strip-sweep $sweep" > $out/strips_n$n.json 2> $out/strips_n$n.err
   echo "rc=$?"; tail -3 $out/strips_n$n.err; cut -c1-1200 $out/strips_n$n.json
 fi
