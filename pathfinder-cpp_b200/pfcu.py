@@ -200,24 +200,38 @@ class Renderer:
         """PFCU_OPT_INCREMENTAL_DICE (default off): later frames dice only the paths whose segments were updated."""
         _check(self.L.pfcu_set_option(self.h, 2, int(bool(enabled))))
 
-    def update_scene(self, scene):
-        """Switch to `scene`, which differs from the current one only in the POINTS of some draw segments (same indices,
-        same batch structure: a path moved): uploads the changed point range (pfcu_update_scene_range) and takes the new
-        batch metadata. Returns (first_segment, n_segments) of the update."""
-        old, new = self.scene, scene
+    def plan_update(self, old, new):
+        """What update_scene needs to go from scene `old` to `new` (same topology, the points of some draw segments
+        moved): the changed point range, the segments it belongs to, the new batch descriptors. Host-side preparation, kept
+        apart so that a benchmark can time the C-ABI calls alone."""
         assert np.array_equal(old["draw_indices"], new["draw_indices"]) and old["draw_points"].shape == new["draw_points"].shape
         changed = np.nonzero((old["draw_points"] != new["draw_points"]).any(axis=1))[0]
         first_point, n_points = int(changed[0]), int(changed[-1] - changed[0] + 1)
         fp = new["draw_indices"][:, 0]
         first_seg = int(np.searchsorted(fp, first_point, side="right") - 1)
         end_seg = int(np.searchsorted(fp, first_point + n_points - 1, side="right"))
+        keep = []
+        descs = {"clip": [make_desc(b, keep) for b in new["clip_batches"]],
+                 "draw": [make_desc(b, keep) for b in new["draw_batches"]]}
         pts = np.ascontiguousarray(new["draw_points"][first_point:first_point + n_points], "<f4")
-        _check(self.L.pfcu_update_scene_range(self.h, 0, first_point, _p(pts), n_points, first_seg, end_seg - first_seg))
-        self.scene = new
-        self._keep = []
-        self._descs = {"clip": [make_desc(b, self._keep) for b in new["clip_batches"]],
-                       "draw": [make_desc(b, self._keep) for b in new["draw_batches"]]}
-        return first_seg, end_seg - first_seg
+        return dict(scene=new, first_point=first_point, points=pts, first_seg=first_seg, n_seg=end_seg - first_seg,
+                    descs=descs, keep=keep)
+
+    def apply_update(self, plan):
+        """pfcu_update_scene_range with a prepared plan; the next draw() renders plan['scene']."""
+        _check(self.L.pfcu_update_scene_range(self.h, 0, plan["first_point"], _p(plan["points"]), len(plan["points"]),
+                                              plan["first_seg"], plan["n_seg"]))
+        self.scene = plan["scene"]
+        self._keep = plan["keep"]
+        self._descs = plan["descs"]
+
+    def update_scene(self, scene):
+        """Switch to `scene`, which differs from the current one only in the POINTS of some draw segments (same indices,
+        same batch structure: a path moved): uploads the changed point range (pfcu_update_scene_range) and takes the new
+        batch metadata. Returns (first_segment, n_segments) of the update."""
+        plan = self.plan_update(self.scene, scene)
+        self.apply_update(plan)
+        return plan["first_seg"], plan["n_seg"]
 
     def upload_paints(self, scene):
         md = np.ascontiguousarray(scene["metadata"], "<u2")

