@@ -21,17 +21,11 @@
 using namespace pfcu;
 
 namespace pfcu {
-// pfcu_stroke.cu
-cudaError_t launch_stroke_count(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
-                                const uint32_t *style_index, const pfcu_stroke_style *styles, uint32_t n_contours, uint32_t *counts,
-                                uint32_t *offsets, uint32_t *total, cudaStream_t s);
-cudaError_t launch_stroke_write(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
-                                const uint32_t *style_index, const pfcu_stroke_style *styles, uint32_t n_contours, uint32_t *counts,
-                                const uint32_t *offsets, float2 *out_pts, uint8_t *out_flags, cudaStream_t s);
+// pfcu_stroke.cu (the stroke launchers are declared in pfcu_device.h)
 cudaError_t launch_dash_count(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
                               const uint32_t *outline_first, const float *dashes, const uint32_t *dash_first, const float *dash_offset,
                               uint32_t n_outlines, uint32_t *point_counts, uint32_t *contour_counts, uint32_t *point_offsets,
-                              uint32_t *contour_offsets, uint32_t *totals, cudaStream_t s);
+                              uint32_t *contour_offsets, uint32_t *totals, uint32_t *scratch, cudaStream_t s);
 cudaError_t launch_dash_write(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
                               const uint32_t *outline_first, const float *dashes, const uint32_t *dash_first, const float *dash_offset,
                               uint32_t n_outlines, uint32_t *point_counts, uint32_t *contour_counts, const uint32_t *point_offsets,
@@ -173,7 +167,7 @@ struct pfcu_ctx {
     uint8_t *read_host = nullptr;  // ... into this buffer (re-issued if the frame it was enqueued behind is replayed)
     size_t read_pitch = 0;
     // stroke-to-fill (pfcu_stroke_to_fill): inputs, counts / offsets, result
-    DevBuf stroke_in, stroke_counts, stroke_out;
+    DevBuf stroke_in, stroke_counts, stroke_out, stroke_slots, stroke_leaves;
     PinnedBuf stroke_stage;
     std::vector<uint32_t> stroke_host_counts;
     std::vector<uint8_t> stroke_closed;
@@ -696,6 +690,8 @@ void pfcu_destroy(pfcu_ctx *c) {
     c->stroke_in.release();
     c->stroke_counts.release();
     c->stroke_out.release();
+    c->stroke_slots.release();
+    c->stroke_leaves.release();
     c->stroke_stage.release();
     c->lut.release();
     if (c->lut_tex) cudaDestroyTextureObject(c->lut_tex);
@@ -991,22 +987,34 @@ int pfcu_stroke_to_fill(pfcu_ctx *c, const float *points, const uint8_t *flags, 
                         uint32_t n_styles, uint32_t *n_out_contours, uint32_t *n_out_points) {
     if (!c || (n_points && (!points || !flags)) || (n_contours && (!contour_first || !closed || !style_index || !styles || !n_styles)))
         return fail(PFCU_ERR_INVALID, "bad stroke input");
+    // segment slots per contour: a segment starts at an on-curve point, plus the closing line; two sides
+    std::vector<uint32_t> seg_first((size_t)n_contours + 1, 0u);
     for (uint32_t i = 0; i < n_contours; i++) {
         if (contour_first[i] > contour_first[i + 1] || contour_first[i + 1] > n_points)
             return fail(PFCU_ERR_INVALID, "contour %u: point range [%u, %u) outside the %u points", i, contour_first[i], contour_first[i + 1], n_points);
         if (style_index[i] >= n_styles) return fail(PFCU_ERR_INVALID, "contour %u: style %u of %u", i, style_index[i], n_styles);
+        uint32_t on_curve = 0;
+        for (uint32_t k = contour_first[i]; k < contour_first[i + 1]; k++) on_curve += flags[k] == 0;
+        seg_first[i + 1] = seg_first[i] + 2u * (on_curve + 1u);
     }
+    const uint32_t n_slots = n_contours ? seg_first[n_contours] : 0u;
     CUDA_TRY(cudaSetDevice(c->device));
     NvtxScope nvtx("pfcu_stroke_to_fill");
-    // one staged H2D copy: points | flags | contour_first | closed | style_index | styles (each 16-byte aligned)
+    // one staged H2D copy: points | flags | contour_first | closed | style_index | styles | seg_first (each 16-byte aligned)
     auto align16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
     const size_t o_pts = 0, o_flags = align16(o_pts + (size_t)n_points * 8), o_first = align16(o_flags + n_points);
     const size_t o_closed = align16(o_first + ((size_t)n_contours + 1) * 4), o_style = align16(o_closed + n_contours);
-    const size_t o_styles = align16(o_style + (size_t)n_contours * 4), bytes = align16(o_styles + (size_t)n_styles * sizeof(pfcu_stroke_style));
+    const size_t o_styles = align16(o_style + (size_t)n_contours * 4), o_seg = align16(o_styles + (size_t)n_styles * sizeof(pfcu_stroke_style));
+    const size_t bytes = align16(o_seg + ((size_t)n_contours + 1) * 4);
     CUDA_TRY(cudaStreamSynchronize(c->stream));  // (the staging buffer of an earlier call may still be in flight)
     CUDA_TRY(c->stroke_stage.ensure(bytes + 16));
     CUDA_TRY(c->stroke_in.ensure(bytes + 16));
-    CUDA_TRY(c->stroke_counts.ensure(((size_t)n_contours * 4 + 4) * 4));
+    const size_t n_scan = std::max<size_t>(n_slots, 2 * (size_t)n_contours);
+    // counts | offsets (2 per contour) | leaf_count | leaf_offset (per slot) | total | scan scratch
+    const size_t w_counts = 0, w_offsets = 2 * (size_t)n_contours, w_lcount = 4 * (size_t)n_contours, w_loffset = w_lcount + n_slots;
+    const size_t w_total = w_loffset + n_slots, w_scratch = w_total + 4, w_end = w_scratch + n_scan / 4096 + 2;
+    CUDA_TRY(c->stroke_counts.ensure(w_end * 4));
+    CUDA_TRY(c->stroke_slots.ensure(std::max<size_t>((size_t)n_slots * stroke_slot_bytes(), 16)));
     char *st = static_cast<char *>(c->stroke_stage.p);
     if (n_points) {
         memcpy(st + o_pts, points, (size_t)n_points * 8);
@@ -1017,32 +1025,50 @@ int pfcu_stroke_to_fill(pfcu_ctx *c, const float *points, const uint8_t *flags, 
         memcpy(st + o_closed, closed, n_contours);
         memcpy(st + o_style, style_index, (size_t)n_contours * 4);
         memcpy(st + o_styles, styles, (size_t)n_styles * sizeof(pfcu_stroke_style));
+        memcpy(st + o_seg, seg_first.data(), ((size_t)n_contours + 1) * 4);
     }
     CUDA_TRY(cudaMemcpyAsync(c->stroke_in.p, st, bytes, cudaMemcpyHostToDevice, c->stream));
     const char *d = c->stroke_in.as<char>();
-    uint32_t *counts = c->stroke_counts.as<uint32_t>(), *offsets = counts + 2 * (size_t)n_contours, *total = offsets + 2 * (size_t)n_contours;
+    uint32_t *w = c->stroke_counts.as<uint32_t>();
+    StrokeArgs a{};
+    a.pts = reinterpret_cast<const float2 *>(d + o_pts);
+    a.flags = reinterpret_cast<const uint8_t *>(d + o_flags);
+    a.contour_first = reinterpret_cast<const uint32_t *>(d + o_first);
+    a.closed = reinterpret_cast<const uint8_t *>(d + o_closed);
+    a.style_index = reinterpret_cast<const uint32_t *>(d + o_style);
+    a.styles = reinterpret_cast<const pfcu_stroke_style *>(d + o_styles);
+    a.seg_first = reinterpret_cast<const uint32_t *>(d + o_seg);
+    a.n_contours = n_contours;
+    a.n_slots = n_slots;
+    a.slots = c->stroke_slots.p;
+    a.counts = w + w_counts;
+    a.offsets = w + w_offsets;
+    a.leaf_count = w + w_lcount;
+    a.leaf_offset = w + w_loffset;
+    a.total = w + w_total;
+    a.scratch = w + w_scratch;
     c->stroke_n_contours = n_contours;
     c->stroke_total = 0;
     c->stroke_host_counts.assign(2 * (size_t)n_contours, 0u);
     c->stroke_closed.assign(closed, closed + n_contours);
     if (n_contours) {
         CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
-        CUDA_TRY(launch_stroke_count(reinterpret_cast<const float2 *>(d + o_pts), reinterpret_cast<const uint8_t *>(d + o_flags),
-                                     reinterpret_cast<const uint32_t *>(d + o_first), reinterpret_cast<const uint8_t *>(d + o_closed),
-                                     reinterpret_cast<const uint32_t *>(d + o_style), reinterpret_cast<const pfcu_stroke_style *>(d + o_styles),
-                                     n_contours, counts, offsets, total, c->stream));
-        // the one mid-way read-back: the point total sizes the output (the counts themselves ride along: the host needs
-        // them to lay the output contours out)
-        CUDA_TRY(cudaMemcpyAsync(c->stroke_host_counts.data(), counts, 2 * (size_t)n_contours * 4, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(&c->stroke_total, total, 4, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        // level 1 + 2a: segments of every contour side, leaves per segment counted and scanned
+        CUDA_TRY(launch_stroke_segments(a, c->stream));
+        uint32_t total_leaves = 0;
+        CUDA_TRY(cudaMemcpyAsync(&total_leaves, a.total, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // read-back 1: the leaf total sizes the leaf array
+        CUDA_TRY(c->stroke_leaves.ensure(std::max<size_t>((size_t)total_leaves * stroke_leaf_bytes(), 16)));
+        a.leaves = c->stroke_leaves.p;
+        // level 2b + 3a: leaves written, points per output contour counted and scanned
+        CUDA_TRY(launch_stroke_count(a, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->stroke_host_counts.data(), a.counts, 2 * (size_t)n_contours * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(&c->stroke_total, a.total, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));  // read-back 2: the point total sizes the output
         c->stroke_off_flags = align16((size_t)c->stroke_total * 8);
         CUDA_TRY(c->stroke_out.ensure(c->stroke_off_flags + c->stroke_total + 16));
-        CUDA_TRY(launch_stroke_write(reinterpret_cast<const float2 *>(d + o_pts), reinterpret_cast<const uint8_t *>(d + o_flags),
-                                     reinterpret_cast<const uint32_t *>(d + o_first), reinterpret_cast<const uint8_t *>(d + o_closed),
-                                     reinterpret_cast<const uint32_t *>(d + o_style), reinterpret_cast<const pfcu_stroke_style *>(d + o_styles),
-                                     n_contours, counts, offsets, c->stroke_out.as<float2>(),
-                                     c->stroke_out.as<uint8_t>() + c->stroke_off_flags, c->stream));
+        // level 3b: the output contours
+        CUDA_TRY(launch_stroke_write(a, c->stroke_out.as<float2>(), c->stroke_out.as<uint8_t>() + c->stroke_off_flags, c->stream));
         CUDA_TRY(cudaEventRecord(c->ev_end, c->stream));
     }
     uint32_t n_out = 0;
@@ -1104,7 +1130,7 @@ int pfcu_dash_outlines(pfcu_ctx *c, const float *points, const uint8_t *flags, u
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(c->stroke_stage.ensure(bytes + 16));
     CUDA_TRY(c->stroke_in.ensure(bytes + 16));
-    CUDA_TRY(c->stroke_counts.ensure(((size_t)n_outlines * 4 + 4) * 4));
+    CUDA_TRY(c->stroke_counts.ensure(((size_t)n_outlines * 4 + 8 + n_outlines / 4096 + 2) * 4));
     char *st = static_cast<char *>(c->stroke_stage.p);
     if (n_points) {
         memcpy(st + o_pts, points, (size_t)n_points * 8);
@@ -1122,7 +1148,7 @@ int pfcu_dash_outlines(pfcu_ctx *c, const float *points, const uint8_t *flags, u
     }
     CUDA_TRY(cudaMemcpyAsync(c->stroke_in.p, st, bytes, cudaMemcpyHostToDevice, c->stream));
     const char *d = c->stroke_in.as<char>();
-    uint32_t *pc = c->stroke_counts.as<uint32_t>(), *cc = pc + n_outlines, *po = cc + n_outlines, *co = po + n_outlines, *totals = co + n_outlines;
+    uint32_t *pc = c->stroke_counts.as<uint32_t>(), *cc = pc + n_outlines, *po = cc + n_outlines, *co = po + n_outlines, *totals = co + n_outlines, *scratch = totals + 4;
     uint32_t host_totals[2] = {0, 0};
     c->dash_n_outlines = n_outlines;
     c->dash_points = c->dash_contours = 0;
@@ -1133,7 +1159,7 @@ int pfcu_dash_outlines(pfcu_ctx *c, const float *points, const uint8_t *flags, u
                                    reinterpret_cast<const uint32_t *>(P(o_first)), reinterpret_cast<const uint8_t *>(P(o_closed)),
                                    reinterpret_cast<const uint32_t *>(P(o_ofirst)), reinterpret_cast<const float *>(P(o_dashes)),
                                    reinterpret_cast<const uint32_t *>(P(o_dfirst)), reinterpret_cast<const float *>(P(o_doff)), n_outlines,
-                                   pc, cc, po, co, totals, c->stream));
+                                   pc, cc, po, co, totals, scratch, c->stream));
         CUDA_TRY(cudaMemcpyAsync(host_totals, totals, 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->dash_points = host_totals[0];

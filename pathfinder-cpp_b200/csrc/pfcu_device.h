@@ -216,6 +216,29 @@ constexpr int MAX_DEVICES = 64;
 int current_device();  // clamped to [0, MAX_DEVICES)
 int sm_count();        // of the current device
 
+// Device arrays of one pfcu_stroke_to_fill call (pfcu_stroke.cu)
+struct StrokeArgs {
+    const float2 *pts;
+    const uint8_t *flags;
+    const uint32_t *contour_first;
+    const uint8_t *closed;
+    const uint32_t *style_index;
+    const pfcu_stroke_style *styles;
+    const uint32_t *seg_first;  // [n_contours + 1] segment slots of every contour (both sides)
+    uint32_t n_contours, n_slots;
+    void *slots;                // [n_slots] SegSlot
+    uint32_t *leaf_count, *leaf_offset;  // [n_slots]
+    void *leaves;               // [total leaves] Leaf
+    uint32_t *counts, *offsets; // [2 * n_contours] points per output contour
+    uint32_t *total;            // the sum of the last scan
+    uint32_t *scratch;          // scan scratch: max(n_slots, 2 * n_contours) / 4096 + 1 words
+};
+cudaError_t launch_stroke_segments(const StrokeArgs &a, cudaStream_t s);  // segments, leaf counts, leaf offsets (total = leaves)
+cudaError_t launch_stroke_count(const StrokeArgs &a, cudaStream_t s);     // leaves, point counts, point offsets (total = points)
+cudaError_t launch_stroke_write(const StrokeArgs &a, float2 *out_pts, uint8_t *out_flags, cudaStream_t s);
+size_t stroke_slot_bytes();
+size_t stroke_leaf_bytes();
+
 // Programmatic dependent launch: a kernel launched with launch_pdl may be scheduled while the previous kernel of its
 // stream is still draining (its CTAs are placed and run up to pdl_wait(), which returns once that kernel has completed
 // and its writes are visible), so the launch latency between the small kernels of a frame overlaps the previous kernel's

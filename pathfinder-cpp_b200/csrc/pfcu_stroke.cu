@@ -312,9 +312,11 @@ __device__ __forceinline__ void add_to_contour(Out<WRITE> &out, const Seg &s, fl
     out.push_segment(s);
 }
 
-// Segment::offset (stroke.cpp:499-540), the recursion unrolled onto an explicit stack (depth <= 16, one pending sibling per level)
-template <bool WRITE>
-__device__ void offset_segment(Out<WRITE> &out, const Seg &root, float distance, int join, float miter_limit) {
+// Segment::offset (stroke.cpp:499-540), the recursion unrolled onto an explicit stack (depth <= 16, one pending sibling per
+// level). Every accepted piece -- the offset curve, or the segment itself when it is too short or too deep -- goes to
+// `sink(piece, join_point)` in curve order: what Segment::add_to_contour is called with upstream.
+template <typename Sink>
+__device__ void for_each_leaf(const Seg &root, float distance, Sink &&sink) {
     Seg stack[MAX_RECURSION + 1];
     unsigned char depth_of[MAX_RECURSION + 1];
     int sp = 0;
@@ -325,11 +327,11 @@ __device__ void offset_segment(Out<WRITE> &out, const Seg &root, float distance,
         if (seg_valid(cur)) {
             const V2 join_point = cur.p0;
             if (sq_len(cur.p3 - cur.p0) < STROKE_TOL * STROKE_TOL || depth >= MAX_RECURSION) {
-                add_to_contour(out, cur, distance, join, join_point, miter_limit);
+                sink(cur, join_point);
             } else {
                 const Seg candidate = offset_once(cur, distance);
                 if (cur.kind == K_LINE || error_within_tolerance(cur, candidate, distance)) {
-                    add_to_contour(out, candidate, distance, join, join_point, miter_limit);
+                    sink(candidate, join_point);
                 } else {
                     Seg before, after;
                     seg_split(cur, 0.5f, before, after);
@@ -405,30 +407,26 @@ struct SegIter {
     }
 };
 
-template <bool WRITE>
-__device__ void offset_forward(Out<WRITE> &out, const ContourIn &c, float radius, int join, float miter_limit) {  // stroke.cpp:27-51
+// The segments ContourStrokeToFill::offset_forward (stroke.cpp:27-51) offsets, in order: sink(segment)
+template <typename Sink>
+__device__ void forward_segments(const ContourIn &c, Sink &&sink) {
     SegIter it;
-    int index = -1;
     while (it.has_next) {
         const Seg s = it.next(c);
-        index++;
         if (s.kind == K_NONE) break;
-        offset_segment(out, s, -radius, index == 0 ? (int)JOIN_BEVEL : join, miter_limit);
+        sink(s);
     }
 }
 
-template <bool WRITE>
-__device__ void offset_backward(Out<WRITE> &out, const ContourIn &c, float radius, int join, float miter_limit) {  // stroke.cpp:53-122
-    int tail = c.n - 1, index = -1;
-    if (c.closed && c.n > 1 && !approx_eq(c.p(0), c.p(c.n - 1), FLOAT_EPSILON)) {
-        const Seg closing{c.p(0), v2(0.0f, 0.0f), v2(0.0f, 0.0f), c.p(c.n - 1), K_LINE};
-        index++;
-        offset_segment(out, closing, -radius, index == 0 ? (int)JOIN_BEVEL : join, miter_limit);
-    }
+// ... and ContourStrokeToFill::offset_backward (stroke.cpp:53-122): the closing line first, then the contour back to front
+template <typename Sink>
+__device__ void backward_segments(const ContourIn &c, Sink &&sink) {
+    int tail = c.n - 1;
+    if (c.closed && c.n > 1 && !approx_eq(c.p(0), c.p(c.n - 1), FLOAT_EPSILON))
+        sink(Seg{c.p(0), v2(0.0f, 0.0f), v2(0.0f, 0.0f), c.p(c.n - 1), K_LINE});
     while (tail >= 0) {
         if (c.flags[tail] != ON_CURVE) break;
         Seg s;
-        s.c0 = s.c1 = v2(0.0f, 0.0f);
         if (tail >= 3 && c.flags[tail - 1] == CTRL1 && c.flags[tail - 2] == CTRL0 && c.flags[tail - 3] == ON_CURVE) {
             s = Seg{c.p(tail), c.p(tail - 1), c.p(tail - 2), c.p(tail - 3), K_CUBIC};
             tail -= 3;
@@ -441,8 +439,7 @@ __device__ void offset_backward(Out<WRITE> &out, const ContourIn &c, float radiu
         } else {
             break;
         }
-        index++;
-        offset_segment(out, s, -radius, index == 0 ? (int)JOIN_BEVEL : join, miter_limit);
+        sink(s);
     }
 }
 
@@ -625,26 +622,110 @@ __global__ void __launch_bounds__(128) k_dash(const float2 *pts, const uint8_t *
     }
 }
 
+// ---- stroke-to-fill in three levels of parallelism
+//   segments : one thread per input contour lists the segments its two sides offset (forward_segments / backward_segments)
+//   leaves   : one thread per SEGMENT runs Segment::offset's recursion -- offset_once + the 9-sample error check per node,
+//              nine tenths of the stroker's arithmetic -- and records the accepted pieces ("leaves"); count pass, scan,
+//              write pass
+//   contours : one thread per input contour walks its leaves in order and does what is inherently sequential: joins (they
+//              look at the last two points pushed so far), caps, the pushes themselves; count pass, scan, write pass
+// (Round 2's first version ran everything in the per-contour thread: 1.4 ms for tiger.svg's 78 stroked contours, whose
+// longest has 715 segments, against 0.28 ms for the reference on one CPU core.)
+
+struct SegSlot {
+    Seg s;           // kind K_NONE: unused slot (the used ones of a side come first)
+    float distance;  // -radius of the contour's style
+};
+struct Leaf {
+    float4 a, b, c;  // (p0, c0), (c1, p3), (join point, kind, -)
+};
+
+// seg_first[i] .. seg_first[i + 1]: the slots of contour i, first half its forward side, second half its backward side (the
+// host sizes a side as on-curve points + 1: a segment starts at an on-curve point, plus the closing line)
+__global__ void __launch_bounds__(128) k_stroke_segments(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first,
+                                                         const uint8_t *closed, const uint32_t *style_index,
+                                                         const pfcu_stroke_style *styles, const uint32_t *seg_first,
+                                                         uint32_t n_contours, SegSlot *slots) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_contours) return;
+    const uint32_t first = contour_first[i];
+    const ContourIn c{pts + first, flags + first, (int)(contour_first[i + 1] - first), closed[i] != 0};
+    const float distance = -(styles[style_index[i]].line_width * 0.5f);
+    const uint32_t cap = (seg_first[i + 1] - seg_first[i]) / 2;
+    for (int side = 0; side < 2; side++) {
+        SegSlot *out = slots + seg_first[i] + side * cap;
+        uint32_t k = 0;
+        auto sink = [&](const Seg &sg) {
+            if (k < cap) out[k] = SegSlot{sg, distance};
+            k++;
+        };
+        if (side == 0) forward_segments(c, sink);
+        else backward_segments(c, sink);
+        for (; k < cap; k++) out[k].s.kind = K_NONE;
+    }
+}
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128) k_stroke_leaves(const SegSlot *slots, uint32_t n_slots, uint32_t *leaf_count,
+                                                       const uint32_t *leaf_offset, Leaf *leaves) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots) return;
+    const SegSlot sl = slots[i];
+    uint32_t n = 0;
+    if (sl.s.kind != K_NONE) {
+        Leaf *out = WRITE ? leaves + leaf_offset[i] : nullptr;
+        const uint32_t cap = WRITE ? leaf_count[i] : 0u;
+        for_each_leaf(sl.s, sl.distance, [&](const Seg &piece, V2 join_point) {
+            if (WRITE && n < cap)
+                out[n] = Leaf{make_float4(piece.p0.x, piece.p0.y, piece.c0.x, piece.c0.y),
+                              make_float4(piece.c1.x, piece.c1.y, piece.p3.x, piece.p3.y),
+                              make_float4(join_point.x, join_point.y, __int_as_float(piece.kind), 0.0f)};
+            n++;
+        });
+    }
+    if (!WRITE) leaf_count[i] = n;
+}
+
+// One side of a contour: Segment::add_to_contour for every leaf of every segment, in order (the first segment's leaves get
+// a bevel join: stroke.cpp:46, :76, :118)
+template <bool WRITE>
+__device__ void add_side(Out<WRITE> &out, const SegSlot *slots, uint32_t base, uint32_t cap, const uint32_t *leaf_count,
+                         const uint32_t *leaf_offset, const Leaf *leaves, int join, float miter_limit) {
+    for (uint32_t k = 0; k < cap; k++) {
+        if (slots[base + k].s.kind == K_NONE) break;
+        const float distance = slots[base + k].distance;
+        const int jn = k == 0 ? (int)JOIN_BEVEL : join;
+        const uint32_t l0 = leaf_offset[base + k], l1 = l0 + leaf_count[base + k];
+        for (uint32_t l = l0; l < l1; l++) {
+            const Leaf lf = leaves[l];
+            const Seg piece{v2(lf.a.x, lf.a.y), v2(lf.a.z, lf.a.w), v2(lf.b.x, lf.b.y), v2(lf.b.z, lf.b.w), __float_as_int(lf.c.z)};
+            add_to_contour(out, piece, distance, jn, v2(lf.c.x, lf.c.y), miter_limit);
+        }
+    }
+}
+
 // One thread per input contour (OutlineStrokeToFill::offset's loop body, stroke.cpp:130-155). counts[2i], counts[2i+1]:
 // points of the contour's first / second output contour (closed contours produce two, open ones one: the second stays 0).
 // WRITE: offsets[] are the exclusive prefix sums of counts[].
 template <bool WRITE>
 __global__ void __launch_bounds__(128) k_stroke(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
-                                                const uint32_t *style_index, const pfcu_stroke_style *styles, uint32_t n_contours,
-                                                uint32_t *counts, const uint32_t *offsets, float2 *out_pts, uint8_t *out_flags) {
+                                                const uint32_t *style_index, const pfcu_stroke_style *styles, const uint32_t *seg_first,
+                                                const SegSlot *slots, const uint32_t *leaf_count, const uint32_t *leaf_offset,
+                                                const Leaf *leaves, uint32_t n_contours, uint32_t *counts, const uint32_t *offsets,
+                                                float2 *out_pts, uint8_t *out_flags) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_contours) return;
     const uint32_t first = contour_first[i];
     ContourIn c{pts + first, flags + first, (int)(contour_first[i + 1] - first), closed[i] != 0};
     const pfcu_stroke_style st = styles[style_index[i]];
-    const float radius = st.line_width * 0.5f;
+    const uint32_t base = seg_first[i], cap = (seg_first[i + 1] - seg_first[i]) / 2;
     Out<WRITE> out;
     out.xform = T2{M2{{st.transform[0], st.transform[1], st.transform[2], st.transform[3]}}, v2(st.transform[4], st.transform[5])};
     // Outline::transform leaves an identity alone (path.cpp:8-10)
     out.has_xform = !(st.transform[0] == 1.0f && st.transform[1] == 0.0f && st.transform[2] == 0.0f && st.transform[3] == 1.0f &&
                       st.transform[4] == 0.0f && st.transform[5] == 0.0f);
     out.reset(WRITE ? out_pts + offsets[2 * i] : nullptr, WRITE ? out_flags + offsets[2 * i] : nullptr, WRITE ? counts[2 * i] : 0u);
-    offset_forward(out, c, radius, st.line_join, st.miter_limit);
+    add_side(out, slots, base, cap, leaf_count, leaf_offset, leaves, st.line_join, st.miter_limit);
     uint32_t n_first = 0;
     if (c.closed) {
         close_stroked(out, c, st.line_width, st.line_join, st.miter_limit, true);
@@ -653,7 +734,7 @@ __global__ void __launch_bounds__(128) k_stroke(const float2 *pts, const uint8_t
     } else {
         add_cap(out, st.line_width, st.line_cap);
     }
-    offset_backward(out, c, radius, st.line_join, st.miter_limit);
+    add_side(out, slots, base + cap, cap, leaf_count, leaf_offset, leaves, st.line_join, st.miter_limit);
     if (!c.closed) add_cap(out, st.line_width, st.line_cap);
     close_stroked(out, c, st.line_width, st.line_join, st.miter_limit, c.closed);
     if (!WRITE) {
@@ -662,38 +743,67 @@ __global__ void __launch_bounds__(128) k_stroke(const float2 *pts, const uint8_t
     }
 }
 
-// Exclusive scan of the 2 * n_contours counts by one CTA (the counts of a whole scene are a few hundred thousand words);
-// total[0] = sum.
-__global__ void __launch_bounds__(1024) k_stroke_scan(const uint32_t *counts, uint32_t *offsets, uint32_t n, uint32_t *total) {
-    __shared__ uint32_t warp_sums[32];
-    __shared__ uint32_t carry, block_total;
+// ---- exclusive scan of n words in three kernels (CTA-local scan of 4096 words + CTA totals; scan of the totals by one
+// CTA; add): the counts of a glyph-density scene are millions of words. total[0] = sum.
+constexpr int SCAN_BLOCK = 1024, SCAN_PER_THREAD = 4, SCAN_CHUNK = SCAN_BLOCK * SCAN_PER_THREAD;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *warp_sums, uint32_t &block_total) {
     const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += t;
+    }
+    __syncthreads();  // (warp_sums may still be read from an earlier call)
+    if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
-    for (uint32_t base = 0; base < n; base += 1024) {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? counts[i] : 0u;
-        uint32_t incl = v;
+    if (warp == 0) {
+        const uint32_t w = warp_sums[lane];
+        uint32_t wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (unsigned)d) incl += t;
+            const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= (unsigned)d) wi += t;
         }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t w = warp_sums[lane];
-            uint32_t wi = w;
+        warp_sums[lane] = wi - w;
+        if (lane == 31) warp_sums[32] = wi;
+    }
+    __syncthreads();
+    block_total = warp_sums[32];
+    return warp_sums[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_chunks(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *chunk_totals) {
+    __shared__ uint32_t warp_sums[33];
+    const uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD], sum = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
-                if (lane >= (unsigned)d) wi += t;
-            }
-            warp_sums[lane] = wi - w;  // exclusive offset of every warp
-            if (lane == 31) block_total = wi;
-        }
-        __syncthreads();
-        if (i < n) offsets[i] = carry + warp_sums[warp] + incl - v;
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        v[k] = base + k < n ? in[base + k] : 0u;
+        sum += v[k];
+    }
+    uint32_t total;
+    uint32_t off = block_exclusive_scan(sum, warp_sums, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++) {
+        if (base + k < n) out[base + k] = off;
+        off += v[k];
+    }
+    if (threadIdx.x == 0) chunk_totals[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_totals(uint32_t *chunk_totals, uint32_t n_chunks, uint32_t *total) {
+    __shared__ uint32_t warp_sums[33];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_chunks; base += SCAN_BLOCK) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_chunks ? chunk_totals[i] : 0u;
+        uint32_t block_total;
+        const uint32_t off = block_exclusive_scan(v, warp_sums, block_total);
+        if (i < n_chunks) chunk_totals[i] = carry + off;
         __syncthreads();
         if (threadIdx.x == 0) carry += block_total;
         __syncthreads();
@@ -701,35 +811,71 @@ __global__ void __launch_bounds__(1024) k_stroke_scan(const uint32_t *counts, ui
     if (threadIdx.x == 0) *total = carry;
 }
 
-cudaError_t launch_stroke_count(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
-                                const uint32_t *style_index, const pfcu_stroke_style *styles, uint32_t n_contours, uint32_t *counts,
-                                uint32_t *offsets, uint32_t *total, cudaStream_t s) {
-    if (!n_contours) return cudaSuccess;
-    k_stroke<false><<<(n_contours + 127) / 128, 128, 0, s>>>(pts, flags, contour_first, closed, style_index, styles, n_contours, counts,
-                                                             nullptr, nullptr, nullptr);
-    k_stroke_scan<<<1, 1024, 0, s>>>(counts, offsets, 2 * n_contours, total);
+__global__ void __launch_bounds__(SCAN_BLOCK) k_scan_add(uint32_t *out, uint32_t n, const uint32_t *chunk_totals) {
+    const uint32_t add = chunk_totals[blockIdx.x];
+    const uint32_t base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_PER_THREAD;
+#pragma unroll
+    for (int k = 0; k < SCAN_PER_THREAD; k++)
+        if (base + k < n) out[base + k] += add;
+}
+
+// scratch: (n + SCAN_CHUNK - 1) / SCAN_CHUNK words
+cudaError_t launch_scan_u32(const uint32_t *in, uint32_t *out, uint32_t n, uint32_t *total, uint32_t *scratch, cudaStream_t s) {
+    const uint32_t n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    if (!n_chunks) return cudaMemsetAsync(total, 0, 4, s);
+    k_scan_chunks<<<n_chunks, SCAN_BLOCK, 0, s>>>(in, out, n, scratch);
+    k_scan_totals<<<1, SCAN_BLOCK, 0, s>>>(scratch, n_chunks, total);
+    if (n_chunks > 1) k_scan_add<<<n_chunks, SCAN_BLOCK, 0, s>>>(out, n, scratch);
     return cudaGetLastError();
 }
 
-cudaError_t launch_stroke_write(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
-                                const uint32_t *style_index, const pfcu_stroke_style *styles, uint32_t n_contours, uint32_t *counts,
-                                const uint32_t *offsets, float2 *out_pts, uint8_t *out_flags, cudaStream_t s) {
-    if (!n_contours) return cudaSuccess;
-    k_stroke<true><<<(n_contours + 127) / 128, 128, 0, s>>>(pts, flags, contour_first, closed, style_index, styles, n_contours, counts,
-                                                            offsets, out_pts, out_flags);
+cudaError_t launch_stroke_segments(const StrokeArgs &a, cudaStream_t s) {
+    if (!a.n_contours) return cudaSuccess;
+    k_stroke_segments<<<(a.n_contours + 127) / 128, 128, 0, s>>>(a.pts, a.flags, a.contour_first, a.closed, a.style_index, a.styles,
+                                                                 a.seg_first, a.n_contours, static_cast<SegSlot *>(a.slots));
+    if (a.n_slots) {
+        k_stroke_leaves<false><<<(a.n_slots + 127) / 128, 128, 0, s>>>(static_cast<const SegSlot *>(a.slots), a.n_slots, a.leaf_count,
+                                                                      nullptr, nullptr);
+        cudaError_t e = launch_scan_u32(a.leaf_count, a.leaf_offset, a.n_slots, a.total, a.scratch, s);
+        if (e != cudaSuccess) return e;
+    }
     return cudaGetLastError();
 }
+
+cudaError_t launch_stroke_count(const StrokeArgs &a, cudaStream_t s) {
+    if (!a.n_contours) return cudaSuccess;
+    if (a.n_slots)
+        k_stroke_leaves<true><<<(a.n_slots + 127) / 128, 128, 0, s>>>(static_cast<const SegSlot *>(a.slots), a.n_slots, a.leaf_count,
+                                                                     a.leaf_offset, static_cast<Leaf *>(a.leaves));
+    k_stroke<false><<<(a.n_contours + 127) / 128, 128, 0, s>>>(a.pts, a.flags, a.contour_first, a.closed, a.style_index, a.styles,
+                                                             a.seg_first, static_cast<const SegSlot *>(a.slots), a.leaf_count,
+                                                             a.leaf_offset, static_cast<const Leaf *>(a.leaves), a.n_contours, a.counts,
+                                                             nullptr, nullptr, nullptr);
+    return launch_scan_u32(a.counts, a.offsets, 2 * a.n_contours, a.total, a.scratch, s);
+}
+
+cudaError_t launch_stroke_write(const StrokeArgs &a, float2 *out_pts, uint8_t *out_flags, cudaStream_t s) {
+    if (!a.n_contours) return cudaSuccess;
+    k_stroke<true><<<(a.n_contours + 127) / 128, 128, 0, s>>>(a.pts, a.flags, a.contour_first, a.closed, a.style_index, a.styles,
+                                                            a.seg_first, static_cast<const SegSlot *>(a.slots), a.leaf_count,
+                                                            a.leaf_offset, static_cast<const Leaf *>(a.leaves), a.n_contours, a.counts,
+                                                            a.offsets, out_pts, out_flags);
+    return cudaGetLastError();
+}
+
+size_t stroke_slot_bytes() { return sizeof(SegSlot); }
+size_t stroke_leaf_bytes() { return sizeof(Leaf); }
 
 cudaError_t launch_dash_count(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
                               const uint32_t *outline_first, const float *dashes, const uint32_t *dash_first, const float *dash_offset,
                               uint32_t n_outlines, uint32_t *point_counts, uint32_t *contour_counts, uint32_t *point_offsets,
-                              uint32_t *contour_offsets, uint32_t *totals, cudaStream_t s) {
+                              uint32_t *contour_offsets, uint32_t *totals, uint32_t *scratch, cudaStream_t s) {
     if (!n_outlines) return cudaSuccess;
     k_dash<false><<<(n_outlines + 127) / 128, 128, 0, s>>>(pts, flags, contour_first, closed, outline_first, dashes, dash_first, dash_offset,
                                                            n_outlines, point_counts, contour_counts, nullptr, nullptr, nullptr, nullptr, nullptr);
-    k_stroke_scan<<<1, 1024, 0, s>>>(point_counts, point_offsets, n_outlines, totals);
-    k_stroke_scan<<<1, 1024, 0, s>>>(contour_counts, contour_offsets, n_outlines, totals + 1);
-    return cudaGetLastError();
+    cudaError_t e = launch_scan_u32(point_counts, point_offsets, n_outlines, totals, scratch, s);
+    if (e != cudaSuccess) return e;
+    return launch_scan_u32(contour_counts, contour_offsets, n_outlines, totals + 1, scratch, s);
 }
 
 cudaError_t launch_dash_write(const float2 *pts, const uint8_t *flags, const uint32_t *contour_first, const uint8_t *closed,
