@@ -76,6 +76,15 @@ struct pfo_frame {
     uint8_t *masks; /* 256 B per alpha tile id */
     size_t n_masks, cap_masks;
     uint8_t *dest; /* RGBA8 */
+    /* Pixel model: 0 = the GPU-driven shaders (fill.comp + tile.comp: RGBA8 mask with backdrop and fill rule applied, one
+     * float accumulation per pixel, quantised once). 1 = the HYBRID raster shaders on the same geometry (shaders/d3d9/
+     * fill.frag:24-45: raw signed areas blended additively into an RGBA16F mask, d3d9/renderer.cpp:152-158,220-222;
+     * tile.frag sampleMask adds the backdrop and applies the fill rule at composite time; every tile primitive is a draw
+     * into the RGBA8 target through the fixed-function src-over blender, gpu/base.h:83-93: quantised after every layer).
+     * Model 1 exists to MEASURE the distance between the two variants the north star allows; clip combine passes
+     * (tile_clip_combine.frag) are not modelled: scenes without clip paths only. */
+    int pixel_model;
+    float *masks16; /* model 1: raw area sums, every value representable as a half */
 };
 
 /* ------------------------------------------------------------------------------------------ frame plumbing */
@@ -135,6 +144,7 @@ void pfo_frame_destroy(pfo_frame *f) {
     free(f->metadata);
     free(f->lut);
     free(f->masks);
+    free(f->masks16);
     free(f->dest);
     free(f);
 }
@@ -590,6 +600,7 @@ static void propagate_batch(pfo_frame *f, batch_t *b) {
     if (next_alpha > f->cap_masks) {
         f->cap_masks = next_alpha * 2 + 64;
         f->masks = (uint8_t *)realloc(f->masks, f->cap_masks * 256);
+        f->masks16 = (float *)realloc(f->masks16, f->cap_masks * 256 * sizeof(float));
     }
     f->n_masks = next_alpha;
 
@@ -702,6 +713,27 @@ static void compute_coverage(const pfo_frame *f, float fx, float fy, float tx, f
 
 static inline float glsl_mod(float x, float y) { return x - y * floorf(x / y); }
 
+/* float -> nearest half (round to nearest even) -> float: what storing into an RGBA16F render target does */
+static float round_to_half(float v) {
+    union { float f; uint32_t u; } x;
+    x.f = v;
+    const uint32_t sign = x.u & 0x80000000u;
+    x.u &= 0x7fffffffu;
+    if (x.u >= 0x7f800000u) return v;                 /* inf / nan */
+    if (x.f >= 65520.0f) { x.u = 0x7f800000u | sign; return x.f; } /* overflows half */
+    if (x.f < 6.103515625e-05f) {                     /* half subnormal: multiples of 2^-24 */
+        const float q = rintf(x.f * 16777216.0f) / 16777216.0f;
+        x.f = q;
+        x.u |= sign;
+        return x.f;
+    }
+    const uint32_t rem = x.u & 0x1fffu;               /* 13 dropped mantissa bits */
+    x.u &= ~0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (x.u & 0x2000u))) x.u += 0x2000u;
+    x.u |= sign;
+    return x.f;
+}
+
 /* shaders/d3d11/fill.comp:109-154 (main) for every alpha tile this batch allocated */
 static void fill_batch(pfo_frame *f, batch_t *b) {
     for (uint32_t ti = 0; ti < b->desc.tile_count; ti++) {
@@ -730,6 +762,16 @@ static void fill_batch(pfo_frame *f, batch_t *b) {
                     compute_coverage(f, (float)fl[k].from_x / 256.0f - fragx, (float)fl[k].from_y / 256.0f - fragy,
                                      (float)fl[k].to_x / 256.0f - fragx, (float)fl[k].to_y / 256.0f - fragy, c);
                     for (int q = 0; q < 4; q++) cov[q] += c[q];
+                }
+                if (f->pixel_model == 1) { /* additive blending into RGBA16F: the running sum is a half after every fill */
+                    float raw[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                    for (uint32_t k = 0; k < nf; k++) {
+                        float c[4];
+                        compute_coverage(f, (float)fl[k].from_x / 256.0f - fragx, (float)fl[k].from_y / 256.0f - fragy,
+                                         (float)fl[k].to_x / 256.0f - fragx, (float)fl[k].to_y / 256.0f - fragy, c);
+                        for (int q = 0; q < 4; q++) raw[q] = round_to_half(raw[q] + c[q]);
+                    }
+                    for (int q = 0; q < 4; q++) f->masks16[(size_t)t->alpha_tile_id * 256 + (lyq * 4 + q) * 16 + lxq] = raw[q];
                 }
                 for (int q = 0; q < 4; q++) {
                     float cv = cov[q];
@@ -1075,7 +1117,9 @@ int pfo_frame_draw_batch(pfo_frame *f, int slot, int target_page, int color_page
                         int tile_ctrl = b->tpi[plo].ctrl;
                         int backdrop;
                         float mask_alpha = 1.0f;
-                        if (t->alpha_tile_id >= 0) { /* tile.comp:775-777 */
+                        if (t->alpha_tile_id >= 0 && f->pixel_model == 1) { /* d3d9/tile.vert:93-153: the tile's backdrop rides along */
+                            backdrop = t->backdrop_d3d9;
+                        } else if (t->alpha_tile_id >= 0) { /* tile.comp:775-777 */
                             backdrop = 0;
                         } else {
                             backdrop = t->backdrop;
@@ -1084,8 +1128,9 @@ int pfo_frame_draw_batch(pfo_frame *f, int slot, int target_page, int color_page
                         }
                         int mask_ctrl = tile_ctrl & 0x3;
                         if (mask_ctrl != 0) { /* sampleMask, tile.comp:586-607 */
-                            float cov = (float)f->masks[(size_t)t->alpha_tile_id * 256 + py * 16 + pxq] *
-                                            (1.0f / 255.0f) + (float)backdrop;
+                            float cov = (f->pixel_model == 1 ? f->masks16[(size_t)t->alpha_tile_id * 256 + py * 16 + pxq]
+                                                             : (float)f->masks[(size_t)t->alpha_tile_id * 256 + py * 16 + pxq] *
+                                                                   (1.0f / 255.0f)) + (float)backdrop;
                             if (mask_ctrl & 0x1) cov = fabsf(cov);
                             else cov = 1.0f - fabsf(1.0f - glsl_mod(cov, 2.0f));
                             mask_alpha = mask_alpha < cov ? mask_alpha : cov;
@@ -1130,6 +1175,8 @@ int pfo_frame_draw_batch(pfo_frame *f, int slot, int target_page, int color_page
                         color[1] *= color[3];
                         color[2] *= color[3];
                         for (int c = 0; c < 4; c++) dest[c] = dest[c] * (1.0f - color[3]) + color[c]; /* :841 */
+                        if (f->pixel_model == 1) /* the blender writes RGBA8 after every primitive */
+                            for (int c = 0; c < 4; c++) dest[c] = rintf(clampf(dest[c], 0.0f, 1.0f) * 255.0f) * (1.0f / 255.0f);
                     }
                     for (int c = 0; c < 4; c++) dp[c] = (uint8_t)rintf(clampf(dest[c], 0.0f, 1.0f) * 255.0f);
                 }
@@ -1138,6 +1185,8 @@ int pfo_frame_draw_batch(pfo_frame *f, int slot, int target_page, int color_page
     }
     return 0;
 }
+
+void pfo_frame_set_pixel_model(pfo_frame *f, int model) { f->pixel_model = model; }
 
 void pfo_frame_set_origin(pfo_frame *f, int tile_x0, int tile_y0) {
     f->org_tx = tile_x0;

@@ -96,6 +96,8 @@ void pfo_frame_destroy(pfo_frame *f);
 /* The framebuffer shows the scene from tile (tile_x0, tile_y0) on: one horizontal strip of a larger canvas. The view
  * box stays in scene coordinates ([0, 16 * tile_y0, W, 16 * tile_y0 + fb_height]), so every float operation is the one
  * the full-canvas frame performs. Default (0, 0). */
+/* 0: GPU-driven pixel semantics (fill.comp + tile.comp, default); 1: the hybrid raster shaders' (shaders/d3d9): see pf_oracle.c */
+void pfo_frame_set_pixel_model(pfo_frame *f, int model);
 void pfo_frame_set_origin(pfo_frame *f, int tile_x0, int tile_y0);
 
 /* which: 0 draw, 1 clip. points = xy pairs; indices = (first_point_index, flag) pairs. */

@@ -96,7 +96,7 @@ def make_desc(batch, keep):
 class Frame:
     """Oracle state for one frame of one scene."""
 
-    def __init__(self, scene, area_lut=None):
+    def __init__(self, scene, area_lut=None, pixel_model=0):
         self.scene = scene
         vb = np.ascontiguousarray(scene["view_box"], "<f4")
         lut = np.ascontiguousarray(area_lut, "u1") if area_lut is not None else None
@@ -104,6 +104,8 @@ class Frame:
         self.h = lib().pfo_frame_create(int(scene["width"]), int(scene["height"]), _p(vb), _p(lut), lw, lh)
         org = scene.get("origin_tiles", (0, 0))
         lib().pfo_frame_set_origin(self.h, int(org[0]), int(org[1]))
+        if pixel_model:  # 1: the hybrid raster shaders' pixel semantics on the same geometry (pf_oracle.c, pixel_model)
+            lib().pfo_frame_set_pixel_model(self.h, int(pixel_model))
         self.fb_tiles = ((int(scene["width"]) + 15) // 16) * ((int(scene["height"]) + 15) // 16)
         for which, name in ((0, "draw"), (1, "clip")):
             pts = np.ascontiguousarray(scene[name + "_points"], "<f4")
