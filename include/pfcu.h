@@ -229,7 +229,22 @@ enum {
      * and the scene upload they came from); later frames dice only the paths touched by pfcu_update_scene_range since then
      * and bin skips the retained lines of those paths. A frame that would re-dice more than half of the batch, or whose key
      * changed, dices everything and becomes the new base. Default 0: every frame dices every segment, like the reference. */
-    PFCU_OPT_INCREMENTAL_DICE = 2
+    PFCU_OPT_INCREMENTAL_DICE = 2,
+    /* 1: the tile kernel rasterizes the masks of a draw batch itself, in shared memory, right before it blends them
+     * (fill.comp:109-154 inside tile.comp:737-850): no separate fill launch for the batch, no mask written to or read
+     * from device memory, only masks that a tile list references are rasterized. The mask bytes are computed by the
+     * same code as the separate fill kernel, so the frame is byte-identical either way (tested on every fixture). Clip
+     * batches always go through the separate fill kernel (other batches read their masks). 0 (default): separate fill
+     * kernel for every batch -- measured faster on B200 (tiger.svg @ 4096^2: fill 24.6 us beside the list building +
+     * tile 29.1 us, against 64.2 us for the fused tile kernel: the masked tiles of a 16-tile group serialise behind one
+     * CTA, profiles/r02_tile_kernel.md section 7). pfcu_read_mask needs 0. */
+    PFCU_OPT_FUSED_FILL = 3,
+    /* n > 0 (default 4): the tile kernel renders the EXPENSIVE groups of 16 framebuffer tiles first -- propagate counts
+     * the masked tiles of every group, the scan over framebuffer tiles puts the groups with at least n of them first (in
+     * grid order) and the others last, and writes the list headers in that order -- instead of wherever the scene puts
+     * them in the grid (a group costs 1.2 .. 17 us, and expensive groups late in the grid leave most of the GPU idle
+     * at the end of the kernel; tools/timeline.py). Same pixels, same lists. 0: groups in grid order. */
+    PFCU_OPT_ORDER_TILE_GROUPS = 4
 };
 int pfcu_set_option(pfcu_ctx *ctx, int option, int value);
 
@@ -252,6 +267,23 @@ enum {
 int pfcu_set_profiling(pfcu_ctx *ctx, int enabled);
 /* Per-stage device time (ms, summed over batches) of the last frame ended with profiling on. n <= PFCU_NUM_STAGES. */
 int pfcu_get_stage_times(pfcu_ctx *ctx, float *ms, int n);
+
+/* ---- tracing: a device-side timeline of every CTA of every kernel of the frames rendered while it is on. Thread 0 of a
+ * CTA reads %globaltimer (one nanosecond clock for the whole device) when the CTA is placed on an SM, when the kernel it
+ * depends on has finished (programmatic dependent launch: CTAs are placed early and wait) and when it leaves the kernel.
+ * Unlike CUDA events (one stream) and ncu (serialises kernels) this shows which kernels of which frames and contexts share
+ * the GPU at any moment. Costs one predictable branch per CTA when off. */
+typedef struct pfcu_timeline_record {
+    uint32_t stage;  /* PFCU_STAGE_*; | 0x100: the second kernel of the stage (long-walk bin) */
+    uint32_t sm;     /* %smid */
+    uint32_t cta, n_ctas;
+    uint64_t t_placed_ns, t_start_ns, t_end_ns;
+} pfcu_timeline_record;
+/* capacity > 0: (re)allocate a device buffer of that many records and record from the next frame on; 0: off. */
+int pfcu_set_timeline(pfcu_ctx *ctx, uint32_t capacity);
+/* Waits for the context, copies out the records written since the last call (at most max_records; NULL: count only) and
+ * starts over. Returns the number of records written (may exceed the capacity: the excess was dropped), or -1. */
+int64_t pfcu_read_timeline(pfcu_ctx *ctx, pfcu_timeline_record *out, int64_t max_records);
 
 /* ---- whole-frame CUDA graph: replay the last completed frame with device-resident inputs (no host memory is
  * touched, no allocation, no read-back inside the graph). Segment points may be re-uploaded between replays

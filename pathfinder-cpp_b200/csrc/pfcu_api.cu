@@ -118,7 +118,7 @@ struct BatchSlot {
     PinnedBuf host_meta;  // the four metadata vectors, packed, kept for replay
     size_t off_backdrops = 0, off_meta = 0, off_dice = 0, off_tpi = 0, meta_bytes = 0;
     DevBuf dev_meta, tile_word, fill_begin, fill_cursor, alpha_rank, col_backdrop, tile_state, lines, line_meta, staging, fills, fb, long_lines,
-        prims, alpha_tiles, alpha_map, scan_desc0, scan_desc1;
+        prims, alpha_tiles, alpha_map, scan_desc0, scan_desc1, group_of, slot_of, fb_sorted;
     uint32_t line_cap = 0, fill_cap = 0, staging_cap = 0;
     BatchView view{};
     bool prepared = false;
@@ -228,6 +228,10 @@ struct pfcu_ctx {
     // ordinary way at pfcu_end_frame and the graph is dropped.
     bool auto_graph = true;
     bool fill_culled_tiles = false;  // PFCU_OPT_FILL_CULLED_TILES
+    bool fused_fill = false;         // PFCU_OPT_FUSED_FILL
+    int order_groups = 4;            // PFCU_OPT_ORDER_TILE_GROUPS: masked tiles that make a group of 16 tiles expensive
+    DevBuf timeline;                 // pfcu_set_timeline: 64-byte header (word 0 = records claimed) + records
+    uint32_t timeline_cap = 0;       // 0: off
     // PFCU_OPT_INCREMENTAL_DICE: partial scene updates since the last full upload, per path source
     bool incremental = false;
     struct DirtyRange {
@@ -371,6 +375,12 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     CUDA_TRY(s.prims.ensure(D * sizeof(TilePrim)));
     CUDA_TRY(s.alpha_tiles.ensure(D * sizeof(AlphaTile)));
     CUDA_TRY(s.alpha_map.ensure(D * 4));
+    {
+        const size_t groups = (T + GROUP_TILES - 1) / GROUP_TILES;
+        CUDA_TRY(s.group_of.ensure(groups * 4));
+        CUDA_TRY(s.slot_of.ensure(groups * 4));
+        CUDA_TRY(s.fb_sorted.ensure(groups * GROUP_TILES * sizeof(FbTile)));
+    }
     CUDA_TRY(s.scan_desc0.ensure((D / 2048 + 2) * 8));
     CUDA_TRY(s.scan_desc1.ensure((T / 2048 + 2) * 8));
     BatchView v;
@@ -418,6 +428,18 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.alpha_tiles = s.alpha_tiles.as<AlphaTile>();
     v.alpha_map = s.alpha_map.as<uint32_t>();
     v.cull_fill = d.path_source == 0 && !c->fill_culled_tiles;
+    // draw batches only: a clip batch's masks are read by OTHER batches (fill's min() and solid-draw x alpha-clip tiles)
+    v.fused_fill = c->fused_fill && d.path_source == 0 && !c->fill_culled_tiles;
+    v.group_of = v.slot_of = nullptr;
+    v.fb_sorted = nullptr;
+    v.group_cost_min = (uint32_t)c->order_groups;
+    // (clip batches are never drawn; a framebuffer tile's list has at most one entry per path, and its count shares a
+    // word with the count of masked entries)
+    if (c->order_groups > 0 && d.path_source == 0 && d.path_count < (1u << FB_COUNT_BITS)) {
+        v.group_of = s.group_of.as<uint32_t>();
+        v.slot_of = s.slot_of.as<uint32_t>();
+        v.fb_sorted = s.fb_sorted.as<FbTile>();
+    }
     v.alpha_capacity = d.tile_count;
     v.scan_desc[0] = s.scan_desc0.as<unsigned long long>();
     v.scan_desc[1] = s.scan_desc1.as<unsigned long long>();
@@ -438,6 +460,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     v.paints = c->paints.as<Paint>();
     v.n_paints = c->n_paints;
     v.solid_prims = c->all_solid;
+    v.timeline = c->timeline_cap ? c->timeline.as<uint32_t>() : nullptr;
+    v.timeline_capacity = c->timeline_cap;
     if (c->incremental && !s.diced_all) {
         v.dice_ranges = reinterpret_cast<const uint2 *>(m + s.off_ranges);
         v.n_dice_ranges = s.n_ranges;
@@ -483,6 +507,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
         int r = order_after(c, aux, c->stream);  // (also orders this batch's aux work after the previous batch's)
         if (r) return r;
     }
+    // (one 16 KB memset of every batch's counters at the start of the frame instead of a 64-byte one per batch was
+    // measured: 2 us SLOWER per frame -- the small ones do not cost a kernel launch)
     if (v.dice_ranges)  // the retained lines, staging slots and long-line queue stay: the counters start where they ended
         CUDA_TRY(cudaMemcpyAsync(v.counters, m + s.off_counters, sizeof(BatchCounters), cudaMemcpyDeviceToDevice, c->stream));
     else
@@ -523,7 +549,7 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
         if (r) return r;
         c->aux_pending = s.fill_done;
     }
-    c->launches += 10;
+    c->launches += v.fused_fill ? 9 : 10;
     c->in_flight = true;
     return PFCU_OK;
 }
@@ -679,6 +705,7 @@ void pfcu_destroy(pfcu_ctx *c) {
         s.host_meta.release();
         for (DevBuf *b : {&s.dev_meta, &s.tile_word, &s.fill_begin, &s.fill_cursor, &s.col_backdrop, &s.tile_state, &s.lines,
                           &s.line_meta, &s.long_lines, &s.staging, &s.fills, &s.fb, &s.alpha_rank, &s.prims,
+                          &s.group_of, &s.slot_of, &s.fb_sorted,
                           &s.alpha_tiles, &s.alpha_map, &s.scan_desc0, &s.scan_desc1})
             b->release();
     }
@@ -703,6 +730,7 @@ void pfcu_destroy(pfcu_ctx *c) {
     c->stage_page.release();
     c->counters.release();
     c->masks.release();
+    c->timeline.release();
     c->host_counters.release();
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->graph) cudaGraphDestroy(c->graph);
@@ -1612,6 +1640,12 @@ int pfcu_set_option(pfcu_ctx *c, int option, int value) {
         case PFCU_OPT_FILL_CULLED_TILES:
             c->fill_culled_tiles = value != 0;
             return PFCU_OK;
+        case PFCU_OPT_FUSED_FILL:
+            c->fused_fill = value != 0;
+            return PFCU_OK;
+        case PFCU_OPT_ORDER_TILE_GROUPS:
+            c->order_groups = value < 0 ? 0 : value;
+            return PFCU_OK;
         case PFCU_OPT_INCREMENTAL_DICE:
             c->incremental = value != 0;
             for (auto &sl : c->slots) sl.base.valid = false;
@@ -1625,6 +1659,45 @@ int pfcu_set_profiling(pfcu_ctx *c, int enabled) {
     if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
     c->profiling = enabled != 0;
     return PFCU_OK;
+}
+
+int pfcu_set_timeline(pfcu_ctx *c, uint32_t capacity) {
+    if (!c) return fail(PFCU_ERR_INVALID, "ctx is null");
+    if (c->frame_open) return fail(PFCU_ERR_STATE, "the timeline cannot change inside a frame");
+    if (capacity && !timeline_compiled())
+        return fail(PFCU_ERR_STATE, "this library was built without -DPFCU_TIMELINE: load lib/libpfcu_trace.so (make trace)");
+    cudaSetDevice(c->device);
+    int r = sync_if_in_flight(c);
+    if (r) return r;
+    c->timeline_cap = 0;
+    if (capacity) {
+        CUDA_TRY(c->timeline.ensure(64 + (size_t)capacity * sizeof(pfcu_timeline_record)));
+        CUDA_TRY(cudaMemset(c->timeline.p, 0, 64));
+        c->timeline_cap = capacity;
+    }
+    return PFCU_OK;  // (the kernels' parameter blocks change: a retained frame graph is rebuilt by the next frames)
+}
+
+int64_t pfcu_read_timeline(pfcu_ctx *c, pfcu_timeline_record *out, int64_t max_records) {
+    if (!c || !c->timeline_cap) {
+        fail(PFCU_ERR_STATE, "pfcu_set_timeline has not been called");
+        return -1;
+    }
+    cudaSetDevice(c->device);
+    uint32_t n = 0;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaStreamSynchronize(c->aux_stream) != cudaSuccess ||
+        cudaMemcpy(&n, c->timeline.p, 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fail(PFCU_ERR_CUDA, "pfcu_read_timeline: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    if (!out) return n;
+    const int64_t take = std::min<int64_t>(std::min<int64_t>(n, c->timeline_cap), std::max<int64_t>(max_records, 0));
+    if (take > 0 && cudaMemcpy(out, c->timeline.as<char>() + 64, (size_t)take * sizeof(pfcu_timeline_record), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fail(PFCU_ERR_CUDA, "pfcu_read_timeline: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    cudaMemset(c->timeline.p, 0, 64);
+    return n;
 }
 
 int pfcu_get_stage_times(pfcu_ctx *c, float *ms, int n) {
@@ -1907,7 +1980,15 @@ int64_t pfcu_read_tile_lists(pfcu_ctx *c, uint32_t batch_id, uint32_t *offsets, 
     const uint32_t T = (uint32_t)(s.view.fb_tw * s.view.fb_th), D = s.desc.tile_count;
     std::vector<FbTile> fb(T);
     std::vector<TilePrim> prims(D);
-    if (T) TAP_TRY(cudaMemcpy(fb.data(), s.view.fb, (size_t)T * sizeof(FbTile), cudaMemcpyDeviceToHost));
+    if (T && s.view.fb_sorted) {  // the headers are in CTA order (PFCU_OPT_ORDER_TILE_GROUPS): bring them back to tile order
+        const uint32_t groups = (T + GROUP_TILES - 1) / GROUP_TILES;
+        std::vector<FbTile> sorted((size_t)groups * GROUP_TILES);
+        std::vector<uint32_t> slot_of(groups);
+        TAP_TRY(cudaMemcpy(sorted.data(), s.view.fb_sorted, sorted.size() * sizeof(FbTile), cudaMemcpyDeviceToHost));
+        TAP_TRY(cudaMemcpy(slot_of.data(), s.view.slot_of, (size_t)groups * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t t = 0; t < T; t++) fb[t] = sorted[(size_t)slot_of[t / GROUP_TILES] * GROUP_TILES + t % GROUP_TILES];
+    } else if (T)
+        TAP_TRY(cudaMemcpy(fb.data(), s.view.fb, (size_t)T * sizeof(FbTile), cudaMemcpyDeviceToHost));
     if (D) TAP_TRY(cudaMemcpy(prims.data(), s.view.prims, (size_t)D * sizeof(TilePrim), cudaMemcpyDeviceToHost));
     int64_t total = 0;
     std::vector<uint32_t> keys;

@@ -5,12 +5,15 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/pfcu.h"
 
 namespace pfcu {
 
 constexpr int TILE = 16;
+constexpr int GROUP_TILES = 16;  // consecutive framebuffer tiles rendered by one CTA of the tile kernel
+constexpr int FB_COUNT_BITS = 20;  // FbTile::count while propagate runs (ordered tile groups): entries | masked entries << 20
 constexpr uint32_t CURVE_IS_QUADRATIC = 0x80000000u;  // pathfinder/core/data/data.h:19
 constexpr uint32_t CURVE_IS_CUBIC = 0x40000000u;      // pathfinder/core/data/data.h:20
 constexpr float FLATTENING_TOLERANCE = 1.0f;          // pathfinder/core/d3d9/tiler.cpp:15
@@ -151,6 +154,7 @@ struct BatchView {
     AlphaTile *alpha_tiles; // [alpha_capacity] batch-local
     uint32_t *alpha_map;    // [alpha_capacity] framebuffer tile of the mask's owner (~0: none), for fill's z-cull
     int cull_fill;          // fill skips masks whose tile the z-buffer culls (draw batches; fill.comp rasterizes them all)
+    int fused_fill;         // the tile kernel rasterizes this batch's masks itself; k_fill is not launched (PFCU_OPT_FUSED_FILL)
     uint32_t alpha_capacity;
     unsigned long long *scan_desc[2];  // look-back descriptors (tile_count / fb tiles)
     // clip batch (may be null)
@@ -174,7 +178,88 @@ struct BatchView {
     uint32_t n_dice_ranges, n_dice_segments;
     const uint32_t *dirty_paths;    // bitmap over the batch's paths, or null
     uint32_t n_static_lines;
+    // Tile groups in order of cost (PFCU_OPT_ORDER_TILE_GROUPS; fb_sorted == null when off). The tile kernel's CTAs differ 14 x in
+    // duration (a group of one-colour tiles against a group of 16 tiles with deep masked lists) and are placed in grid
+    // order: expensive groups late in the grid leave most of the GPU idle for the last quarter of the kernel. propagate
+    // counts the masked entries of every framebuffer tile (high bits of FbTile::count, FB_COUNT_BITS); the scan over
+    // framebuffer tiles adds them up per group and partitions the groups -- those with at
+    // least group_cost_min masked tiles first, in grid order, the others from the back -- and writes the list headers in
+    // THAT order, so CTA j finds the headers of its group at j * GROUP_TILES (no dependent load).
+    uint32_t group_cost_min;
+    uint32_t *group_of;    // [groups] group rendered by CTA j
+    uint32_t *slot_of;     // [groups] inverse: CTA that renders group g
+    FbTile *fb_sorted;     // [groups * GROUP_TILES] headers in CTA order: begin / count / z from the scan, cursor from the list scatter
+    // device-side timeline (pfcu_set_timeline): word 0 = records claimed so far, records from byte 64 on; null = off
+    uint32_t *timeline;
+    uint32_t timeline_capacity;
+#ifdef PFCU_PAD_VIEW
+    uint32_t pad_experiment[PFCU_PAD_VIEW / 4];
+#endif
 };
+
+// ---- per-kernel argument blocks. BatchView (472 bytes) is what the host keeps; a kernel only gets the fields it reads.
+// Kernel parameters are not free: padding BatchView by 64 / 256 bytes made one tiger 4096^2 frame (11 kernels) 1.0 / 2.5 us
+// slower alone and 0.7 / 2.7 us slower per frame with four frames in flight (profiles/r02_tile_kernel.md section 9), i.e.
+// about 1 us per 700 bytes of parameters launched. Same field names as BatchView, so the kernels read the same; the
+// helpers the kernels share are templates over the block type.
+#define PFCU_ARG_DECL(f) decltype(BatchView::f) f;
+#define PFCU_ARG_COPY(f) memcpy(&f, &v.f, sizeof(f));
+#define PFCU_ARGS(Name, FIELDS)                                           \
+    struct Name {                                                         \
+        FIELDS(PFCU_ARG_DECL)                                             \
+        Name() = default;                                                 \
+        explicit Name(const BatchView &v) { FIELDS(PFCU_ARG_COPY) }       \
+    };
+#ifdef PFCU_TIMELINE
+#define PFCU_TL(X) X(timeline) X(timeline_capacity)
+#else
+#define PFCU_TL(X)
+#endif
+#define PFCU_INIT_FIELDS(X) \
+    X(tile_word) X(col_backdrop) X(backdrops) X(fb) X(scan_desc) X(tile_count) X(column_count) X(fb_tw) X(fb_th) PFCU_TL(X)
+#define PFCU_DICE_FIELDS(X)                                                                                              \
+    X(dice) X(indices) X(points) X(dice_ranges) X(counters) X(line_meta) X(lines) X(long_lines) X(view_box) X(transform)  \
+    X(identity_transform) X(n_dice_segments) X(n_dice_ranges) X(n_points) X(n_segments_total) X(path_count)             \
+    X(segment_count) X(line_capacity) X(staging_capacity) PFCU_TL(X)
+#define PFCU_BIN_FIELDS(X)                                                                                  \
+    X(counters) X(line_meta) X(lines) X(long_lines) X(staging) X(tile_word) X(col_backdrop) X(meta) X(dirty_paths) \
+    X(line_capacity) X(n_static_lines) X(segment_count) PFCU_TL(X)
+#define PFCU_SCAN_FIELDS(X)                                                                                            \
+    X(tile_word) X(fill_begin) X(fill_cursor) X(alpha_rank) X(scan_desc) X(counters) X(frame_alpha_counter) X(fb)        \
+    X(fb_sorted) X(group_of) X(slot_of) X(tile_count) X(fb_tw) X(fb_th) X(fill_capacity) X(mask_capacity) \
+    X(alpha_capacity) X(prim_capacity) X(group_cost_min) PFCU_TL(X)
+#define PFCU_FILL_SCATTER_FIELDS(X) \
+    X(counters) X(staging) X(fill_cursor) X(fills) X(staging_capacity) X(tile_count) X(fill_capacity) PFCU_TL(X)
+#define PFCU_PROPAGATE_FIELDS(X)                                                                                       \
+    X(backdrops) X(clip_meta) X(meta) X(tpi) X(alpha_map) X(alpha_rank) X(alpha_tiles) X(clip_tile_state) X(fb)         \
+    X(fill_begin) X(fb_sorted) X(tile_state) X(col_backdrop) X(counters) X(tile_word) X(clip_path_count)              \
+    X(alpha_capacity) X(fb_th) X(fb_tw) X(fb_tx0) X(fb_ty0) X(mask_capacity) X(column_count) PFCU_TL(X)
+#define PFCU_LIST_FIELDS(X)                                                                                          \
+    X(counters) X(meta) X(paints) X(prims) X(tile_state) X(tpi) X(fb) X(fb_sorted) X(slot_of) X(fb_tw)  \
+    X(fb_tx0) X(fb_ty0) X(mask_capacity) X(n_paints) X(prim_capacity) X(solid_prims) X(tile_count) PFCU_TL(X)
+#define PFCU_FILL_FIELDS(X)                                                                                  \
+    X(alpha_map) X(alpha_tiles) X(counters) X(fb) X(fills) X(masks) X(alpha_capacity) X(cull_fill) X(mask_capacity) \
+    X(fill_capacity) X(tile_count) PFCU_TL(X)
+#define PFCU_COMPOSITE_FIELDS(X)                                                                                      \
+    X(alpha_tiles) X(counters) X(fb_sorted) X(fb) X(slot_of) X(group_of) X(fills) X(masks) X(prims)       \
+    X(alpha_capacity) X(fb_tw) X(fb_tx0) X(fb_ty0) X(fill_capacity) X(mask_capacity) X(prim_capacity) X(solid_prims)   \
+    X(tile_count) PFCU_TL(X)
+PFCU_ARGS(InitArgs, PFCU_INIT_FIELDS)
+PFCU_ARGS(DiceArgs, PFCU_DICE_FIELDS)
+PFCU_ARGS(BinArgs, PFCU_BIN_FIELDS)
+PFCU_ARGS(ScanArgs, PFCU_SCAN_FIELDS)
+PFCU_ARGS(FillScatterArgs, PFCU_FILL_SCATTER_FIELDS)
+PFCU_ARGS(PropagateArgs, PFCU_PROPAGATE_FIELDS)
+PFCU_ARGS(ListArgs, PFCU_LIST_FIELDS)
+PFCU_ARGS(FillArgs, PFCU_FILL_FIELDS)
+PFCU_ARGS(CompositeArgs, PFCU_COMPOSITE_FIELDS)
+
+// Header of framebuffer tile `map`: where the scan put it (in CTA order when the groups are ordered)
+template <class B>
+__device__ __forceinline__ FbTile *fb_header(const B &b, uint32_t map) {
+    if (!b.fb_sorted) return &b.fb[map];
+    return &b.fb_sorted[__ldg(&b.slot_of[map / GROUP_TILES]) * GROUP_TILES + map % GROUP_TILES];
+}
 
 struct TargetView {
     uint8_t *pixels;  // RGBA8
@@ -212,6 +297,7 @@ cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s);
 cudaError_t launch_composite(const BatchView &b, const PaintView &p, const TargetView &t, int clear,
                              const float clear_color[4], int origin, int heavy_paints, cudaStream_t s, int *n_launched = nullptr);
 
+bool timeline_compiled();  // the kernels were built with -DPFCU_TIMELINE
 constexpr int MAX_DEVICES = 64;
 int current_device();  // clamped to [0, MAX_DEVICES)
 int sm_count();        // of the current device
@@ -249,9 +335,75 @@ __device__ __forceinline__ void pdl_wait() {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 #endif
 }
+// griddepcontrol.launch_dependents right after this wait (so that the next kernel's CTAs are placed while this grid runs and
+// sit in their own pdl_wait()) was measured and is NOT used: the gap between the last CTA of a kernel and the first
+// running CTA of the next stays 1.3 - 3.4 us (tools/timeline.py; most edges of the frame graph also carry a cross-stream
+// dependency, which is a full edge), one frame alone takes 100.9 instead of 102.4 us, and the waiting CTAs hold registers
+// and shared memory that the other frames in flight would use: 65.4 instead of 60.9 us per frame with 4 contexts.
+// Device-side timeline: thread 0 of every CTA records when the CTA was placed, when the kernel it depends on had
+// finished (griddepcontrol.wait returned) and when the thread left the kernel, with the SM it ran on -- %globaltimer is
+// one clock for the whole device, so the records of all kernels, streams and contexts line up (what neither CUDA events
+// nor ncu, which serialises kernels, can show: which kernels of which frames actually share the GPU).
+struct CtaStamp {
+    uint32_t *tl;
+    uint32_t cap, stage;
+    unsigned long long *t;  // shared memory: placed, started (keeps the stamps out of the kernel's registers)
+    static __device__ __forceinline__ unsigned long long now() {
+        unsigned long long v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+        return v;
+    }
+    __device__ __forceinline__ void placed() const {
+        if (tl && threadIdx.x == 0) t[0] = now();
+    }
+    __device__ __forceinline__ void go() const {
+        if (tl && threadIdx.x == 0) t[1] = now();
+    }
+    __device__ __forceinline__ ~CtaStamp() {
+        if (tl && threadIdx.x == 0) {
+            const unsigned long long t_end = now();
+            const uint32_t i = atomicAdd(tl, 1u);
+            if (i < cap) {
+                uint32_t sm;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+                pfcu_timeline_record *r = reinterpret_cast<pfcu_timeline_record *>(reinterpret_cast<char *>(tl) + 64) + i;
+                r->stage = stage;
+                r->sm = sm;
+                r->cta = blockIdx.x;
+                r->n_ctas = gridDim.x;
+                r->t_placed_ns = t[0];
+                r->t_start_ns = t[1];
+                r->t_end_ns = t_end;
+            }
+        }
+    }
+};
+// first statement of every kernel of the frame: stamp, wait for the kernel this one depends on, stamp
+// The stamps are compiled in only with -DPFCU_TIMELINE (lib/libpfcu_trace.so): with the timeline off they still cost a
+// frame of eleven kernels 1.8 us alone and 1.3 us per frame in a stream of frames.
+#ifndef PFCU_TIMELINE
+#define PFCU_KERNEL_BEGIN(b, stage_) pdl_wait()
+#else
+#define PFCU_KERNEL_BEGIN(b, stage_)                                                                      \
+    __shared__ unsigned long long cta_stamp_t_[2];                                                        \
+    const CtaStamp cta_stamp_{(b).timeline, (b).timeline_capacity, (uint32_t)(stage_), cta_stamp_t_};     \
+    cta_stamp_.placed();                                                                                  \
+    pdl_wait();                                                                                           \
+    cta_stamp_.go()
+#endif
+
+// One shared-memory carve-out for every kernel of the frame. An SM cannot change its L1 / shared-memory split while CTAs
+// are resident, so a kernel whose preferred split differs from the resident kernel's waits for that SM to drain: the
+// timeline showed fill (4 x 40 KB) getting no CTA on the 32 SMs that held a CTA of the scan kernel (no shared memory to
+// speak of) until it had finished. PFCU_CARVEOUT_PCT < 0: leave the choice to the driver.
+#ifndef PFCU_CARVEOUT_PCT
+#define PFCU_CARVEOUT_PCT -1
+#endif
+void prefer_carveout(const void *kernel);  // once per kernel and device (pfcu_tiles.cu)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
+    if (PFCU_CARVEOUT_PCT >= 0) prefer_carveout(reinterpret_cast<const void *>(kernel));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(block, 1, 1);

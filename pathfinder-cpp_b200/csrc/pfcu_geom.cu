@@ -83,7 +83,8 @@ __device__ __forceinline__ uint32_t walk_steps(const float4 &ln) {
 // Where a line's fills will be staged, decided as soon as the line exists (dice): 2 slots per tile of its walk. Lines
 // with long walks are queued for k_bin_long at the same time, so that the two bin kernels need nothing from each other
 // and run side by side. One line per thread, per-thread atomics (the rare paths of dice).
-__device__ __forceinline__ uint32_t reserve_line_slots(const BatchView &b, const float4 &ln, uint32_t g) {
+template <class B>
+__device__ __forceinline__ uint32_t reserve_line_slots(const B &b, const float4 &ln, uint32_t g) {
     const uint32_t steps = walk_steps(ln), slots = 2u * steps;
     const uint32_t slot0 = atomicAdd(&b.counters->n_staging, slots);
     if (slot0 + slots > b.staging_capacity) {
@@ -162,8 +163,8 @@ struct DiceSharedT {
 };
 
 // One flattened line: view-box clip, then into the CTA's output buffer (or straight to global memory when full).
-template <int Q, int O>
-__device__ __forceinline__ void dice_emit(const BatchView &b, DiceSharedT<Q, O> &sh, float2 from, float2 to, uint32_t path) {
+template <int Q, int O, class B>
+__device__ __forceinline__ void dice_emit(const B &b, DiceSharedT<Q, O> &sh, float2 from, float2 to, uint32_t path) {
     float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
     if (!clip_to_view_box(l0, l1, l2, l3, b.view_box[0], b.view_box[2], b.view_box[3])) return;
     const uint32_t at = atomicAdd(&sh.out_count, 1u);
@@ -203,8 +204,8 @@ __device__ __forceinline__ bool node_is_flat(const Cubic &c, bool cubic, int dep
 }
 
 // Depth-first walk of one subtree with a private stack: only used when a level does not fit the shared queue.
-template <int Q, int O>
-__device__ __noinline__ void dice_subtree_serial(const BatchView &b, DiceSharedT<Q, O> &sh, Cubic cur, bool cubic, int depth,
+template <int Q, int O, class B>
+__device__ __noinline__ void dice_subtree_serial(const B &b, DiceSharedT<Q, O> &sh, Cubic cur, bool cubic, int depth,
                                                  uint32_t path) {
     Cubic stack[MAX_FLATTEN_DEPTH];
     unsigned char stack_depth[MAX_FLATTEN_DEPTH];
@@ -228,8 +229,8 @@ __device__ __noinline__ void dice_subtree_serial(const BatchView &b, DiceSharedT
     }
 }
 
-template <int Q, int O>
-__device__ __forceinline__ void dice_push(const BatchView &b, DiceSharedT<Q, O> &sh, int buf, const Cubic &c, bool cubic,
+template <int Q, int O, class B>
+__device__ __forceinline__ void dice_push(const B &b, DiceSharedT<Q, O> &sh, int buf, const Cubic &c, bool cubic,
                                           int depth, uint32_t path) {
     const uint32_t at = atomicAdd(&sh.q_count[buf], 1u);
     if (at < Q) {
@@ -243,8 +244,8 @@ __device__ __forceinline__ void dice_push(const BatchView &b, DiceSharedT<Q, O> 
 
 // Warp-aggregated versions of dice_emit / dice_push (one shared-memory atomic per warp instead of one per lane: 256
 // lanes bumping the same counter serialise). Must be called by all 32 lanes of a warp.
-template <int Q, int O>
-__device__ __forceinline__ void dice_emit_warp(const BatchView &b, DiceSharedT<Q, O> &sh, bool want, float2 from, float2 to,
+template <int Q, int O, class B>
+__device__ __forceinline__ void dice_emit_warp(const B &b, DiceSharedT<Q, O> &sh, bool want, float2 from, float2 to,
                                                uint32_t path, unsigned lane) {
     float l0 = from.x, l1 = from.y, l2 = to.x, l3 = to.y;
     const bool em = want && clip_to_view_box(l0, l1, l2, l3, b.view_box[0], b.view_box[2], b.view_box[3]);
@@ -272,8 +273,8 @@ __device__ __forceinline__ void dice_emit_warp(const BatchView &b, DiceSharedT<Q
 }
 
 // Queues `n_nodes` (1 or 2) nodes per wanting lane; nodes that do not fit are flattened on the spot.
-template <int Q, int O>
-__device__ __forceinline__ void dice_push_warp(const BatchView &b, DiceSharedT<Q, O> &sh, int buf, bool want, int n_nodes,
+template <int Q, int O, class B>
+__device__ __forceinline__ void dice_push_warp(const B &b, DiceSharedT<Q, O> &sh, int buf, bool want, int n_nodes,
                                                const Cubic &c0, const Cubic &c1, bool cubic, int depth, uint32_t path,
                                                unsigned lane) {
     const unsigned mask = __ballot_sync(0xffffffffu, want);
@@ -315,7 +316,8 @@ __device__ __forceinline__ uint32_t warp_find_path(const pfcu_dice_metadata *dic
 }
 
 // Batch segment number of the i-th segment to dice (identity unless the frame dices a subset: BatchView::dice_ranges)
-__device__ __forceinline__ uint32_t dice_segment(const BatchView &b, uint32_t i) {
+template <class B>
+__device__ __forceinline__ uint32_t dice_segment(const B &b, uint32_t i) {
     if (!b.dice_ranges) return i;
     uint32_t lo = 0, hi = b.n_dice_ranges;  // last range whose prefix count is <= i
     while (lo + 1 < hi) {
@@ -327,8 +329,8 @@ __device__ __forceinline__ uint32_t dice_segment(const BatchView &b, uint32_t i)
 }
 
 // Copies the CTA's collected lines to global memory: one atomic per flush.
-template <int Q, int O>
-__device__ __forceinline__ void dice_flush(const BatchView &b, DiceSharedT<Q, O> &sh) {
+template <int Q, int O, class B>
+__device__ __forceinline__ void dice_flush(const B &b, DiceSharedT<Q, O> &sh) {
     // (called by all threads, between two __syncthreads() of the caller's making: out_count is stable)
     const uint32_t n_out = min(sh.out_count, (uint32_t)O);
     if (threadIdx.x == 0) sh.out_base = n_out ? atomicAdd(&b.counters->n_lines, n_out) : 0u;
@@ -385,10 +387,10 @@ __device__ __forceinline__ void dice_flush(const BatchView &b, DiceSharedT<Q, O>
 }
 
 template <int Q, int O>
-__global__ void __launch_bounds__(DICE_THREADS) k_dice(BatchView b, uint32_t chunk_size) {
+__global__ void __launch_bounds__(DICE_THREADS) k_dice(DiceArgs b, uint32_t chunk_size) {
     extern __shared__ __align__(16) unsigned char dice_smem[];
     DiceSharedT<Q, O> &sh = *reinterpret_cast<DiceSharedT<Q, O> *>(dice_smem);
-    pdl_wait();
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_DICE);
     // segments to dice: all of the batch, or -- incremental frames -- the ranges of the paths that changed
     const uint32_t n_dice = b.dice_ranges ? b.n_dice_segments : b.segment_count;
     const uint32_t n_chunks = (n_dice + chunk_size - 1) / chunk_size;
@@ -566,7 +568,7 @@ static cudaError_t launch_dice_cfg(const BatchView &b, cudaStream_t s, uint32_t 
     chunk = chunk < DICE_CHUNK ? DICE_CHUNK : (chunk > max_chunk ? max_chunk : chunk);
     const uint32_t n_chunks = (n_dice + chunk - 1) / chunk;
     const uint32_t grid = min(n_chunks, ctas);
-    return launch_pdl(k_dice<Q, O>, grid, DICE_THREADS, sizeof(DiceSharedT<Q, O>), s, b, chunk);
+    return launch_pdl(k_dice<Q, O>, grid, DICE_THREADS, sizeof(DiceSharedT<Q, O>), s, DiceArgs(b), chunk);
 }
 
 cudaError_t launch_dice(const BatchView &b, cudaStream_t s) {
@@ -587,7 +589,8 @@ struct PathTiles {
 };
 
 // ObjectBuilder::add_fill, core/d3d9/object_builder.cpp:19-64. Returns true when a fill was staged.
-__device__ __forceinline__ bool add_fill(const BatchView &b, const PathTiles &pt, float fx, float fy, float tx,
+template <class B>
+__device__ __forceinline__ bool add_fill(const B &b, const PathTiles &pt, float fx, float fy, float tx,
                                          float ty, int tcx, int tcy, uint32_t slot) {
     if (!(pt.min_x <= tcx && tcx <= pt.max_x - 1 && pt.min_y <= tcy && tcy <= pt.max_y - 1)) return false;
     const float ulx = (float)tcx * 16.0f, uly = (float)tcy * 16.0f;
@@ -607,7 +610,8 @@ __device__ __forceinline__ bool add_fill(const BatchView &b, const PathTiles &pt
 }
 
 // ObjectBuilder::adjust_alpha_tile_backdrop, core/d3d9/object_builder.cpp:95-114
-__device__ __forceinline__ void adjust_backdrop(const BatchView &b, const PathTiles &pt, int tcx, int tcy, int delta) {
+template <class B>
+__device__ __forceinline__ void adjust_backdrop(const B &b, const PathTiles &pt, int tcx, int tcy, int delta) {
     const int ox = tcx - pt.min_x, oy = tcy - pt.min_y;
     const int w = pt.max_x - pt.min_x, h = pt.max_y - pt.min_y;
     if (ox < 0 || ox >= w || oy >= h) return;
@@ -619,7 +623,8 @@ __device__ __forceinline__ void adjust_backdrop(const BatchView &b, const PathTi
     atomicAdd(&b.tile_word[pt.tile_offset + (uint32_t)ox + (uint32_t)w * (uint32_t)oy], (uint32_t)delta << 24);
 }
 
-__device__ __forceinline__ PathTiles load_path_tiles(const BatchView &b, uint32_t path) {
+template <class B>
+__device__ __forceinline__ PathTiles load_path_tiles(const B &b, uint32_t path) {
     PathTiles pt;
     const int4 r = __ldg(reinterpret_cast<const int4 *>(&b.meta[path].tile_rect[0]));
     pt.min_x = r.x; pt.min_y = r.y; pt.max_x = r.z; pt.max_y = r.w;
@@ -662,7 +667,8 @@ struct Walk {
 
 // The expensive part of one step (tiler.cpp:216-270): up to two fills into this step's two staging slots, backdrop
 // bookkeeping. cur = where the line enters the tile, (nx, ny) = where it leaves it.
-__device__ __forceinline__ uint32_t walk_step_emit(const BatchView &b, const PathTiles &pt, const Walk &w, float cur_x,
+template <class B>
+__device__ __forceinline__ uint32_t walk_step_emit(const B &b, const PathTiles &pt, const Walk &w, float cur_x,
                                                    float cur_y, float nx, float ny, int tcx, int tcy, int last_dir,
                                                    int next_dir, uint32_t slot) {
     const float ts = 16.0f;
@@ -685,12 +691,13 @@ constexpr int BIN_CHAIN = 1032;          // crossings per axis the long-line ker
 constexpr int BIN_LONG_WARPS = 4;
 
 // Incremental frames: line i is a retained line (diced in an earlier frame) of a path that has changed since
-__device__ __forceinline__ bool stale_line(const BatchView &b, uint32_t i, uint32_t path) {
+template <class B>
+__device__ __forceinline__ bool stale_line(const B &b, uint32_t i, uint32_t path) {
     return i < b.n_static_lines && b.dirty_paths && ((__ldg(&b.dirty_paths[path >> 5]) >> (path & 31u)) & 1u);
 }
 
-__global__ void __launch_bounds__(128) k_bin(BatchView b) {
-    pdl_wait();
+__global__ void __launch_bounds__(128) k_bin(BinArgs b) {
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_BIN);
     const uint32_t n_lines = min(b.counters->n_lines, b.line_capacity);
     const unsigned lane = threadIdx.x & 31;
     // consecutive 32-line chunks go to consecutive CTAs: the grid is one wave sized for the largest batches, and with
@@ -754,7 +761,8 @@ __global__ void __launch_bounds__(128) k_bin(BatchView b) {
 // Exact replay of the serial walk by a whole warp: all lanes run the cheap part (the t_max chain and the direction
 // decisions) and lane k does the expensive part of every 32nd step. Used when the crossings of a line do not fit the
 // shared-memory chains or when the merge below cannot be proven to equal the serial walk.
-__device__ __noinline__ void walk_replay(const BatchView &b, const PathTiles &pt, float a0, float a1, float a2, float a3,
+template <class B>
+__device__ __noinline__ void walk_replay(const B &b, const PathTiles &pt, float a0, float a1, float a2, float a3,
                                          uint32_t lslot0, uint32_t lsteps, unsigned lane) {
     Walk w;
     w.init(a0, a1, a2, a3);
@@ -810,9 +818,9 @@ __device__ __forceinline__ bool x_first(float a, float b_, bool tie_x) { return 
 // into) -- so two lanes build the sequences once (one dependent add per crossing), and then every step of the walk is
 // independent: a lane finds how many X crossings precede its step with a merge-path binary search and does the step's
 // fill conversion, atomics and stores. 32 steps of the walk per pass instead of one.
-__global__ void __launch_bounds__(BIN_LONG_WARPS * 32) k_bin_long(BatchView b) {
+__global__ void __launch_bounds__(BIN_LONG_WARPS * 32) k_bin_long(BinArgs b) {
     __shared__ float chain[BIN_LONG_WARPS][2][BIN_CHAIN];
-    pdl_wait();
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_BIN | 0x100);
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t n_long = min(b.counters->n_long, b.line_capacity);
 #if BIN_PERMUTE
@@ -899,12 +907,12 @@ __global__ void __launch_bounds__(BIN_LONG_WARPS * 32) k_bin_long(BatchView b) {
 
 cudaError_t launch_bin(const BatchView &b, cudaStream_t s) {
     if (!b.segment_count) return cudaSuccess;
-    return launch_pdl(k_bin, sm_count() * 8, 128, 0, s, b);
+    return launch_pdl(k_bin, sm_count() * 8, 128, 0, s, BinArgs(b));
 }
 
 cudaError_t launch_bin_long(const BatchView &b, cudaStream_t s) {
     if (!b.segment_count) return cudaSuccess;
-    return launch_pdl(k_bin_long, sm_count() * 2, BIN_LONG_WARPS * 32, 0, s, b);
+    return launch_pdl(k_bin_long, sm_count() * 2, BIN_LONG_WARPS * 32, 0, s, BinArgs(b));
 }
 
 }  // namespace pfcu

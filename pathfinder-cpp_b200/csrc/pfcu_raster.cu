@@ -124,13 +124,210 @@ constexpr int FILL_ACC = 16 * FILL_CS;
 // memory as DIFFERENCES down its column: the tile's coverage is then one prefix sum per column, and "every row below
 // gets dX" is a single add. Sums are fixed point, so the result does not depend on the order in which pairs or atomics
 // land.
+// what fill needs of PaintView
+struct LutView {
+    cudaTextureObject_t lut_tex;
+    int lut_band;
+};
+
 struct __align__(16) FillShared {
     int acc[FILL_WARPS][FILL_GROUP][FILL_ACC];
 };
 
-__global__ void __launch_bounds__(FILL_WARPS * 32, FILL_CTAS_PER_SM) k_fill(BatchView b, PaintView p) {
+// The masks of up to G alpha tiles, rasterized by one warp. Lane g < G holds the record of tile g in `at` (tile | winding
+// << 31, clip mask slot, first fill, backdrop | fill count << 8; a tile index >= tile_count: nothing to do) and where its
+// mask goes in `dst_code` (a mask slot of b.masks; with CACHE, bit 31 marks a 256-byte slot of the shared-memory array
+// `cache` instead). `acc` = the warp's G accumulators: all zero on entry, all zero again on return.
+template <int G, bool CACHE, class B, class P>
+__device__ __forceinline__ void fill_group(uint4 at, const uint32_t dst_code, uint8_t *cache, int *const acc,
+                                           const B &b, const P &p, const unsigned lane) {
+    const bool band = p.lut_band != 0;
+    const bool visible = (at.x & 0x7fffffffu) < b.tile_count;  // else: fills that the clip made invisible, no mask
+    const uint32_t begin = min(at.z, b.fill_capacity);
+    const uint32_t count = visible ? min(at.w >> 8, b.fill_capacity - begin) : 0u;
+    // the fills of the group as one sequence: tile g owns [pre_g, pre_g + count_g)
+    uint32_t incl = count;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (unsigned)d) incl += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, G - 1);
+    uint32_t pre[G], rel[G];  // rel_g: address of the tile's fill j = rel_g + j
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        pre[g] = __shfl_sync(0xffffffffu, incl - count, g);
+        rel[g] = __shfl_sync(0xffffffffu, begin, g) - pre[g];
+    }
+
+    for (uint32_t chunk = 0; chunk < total; chunk += 32) {
+        // ---- one fill per lane: what only depends on the fill (fill.comp:53-64)
+        const uint32_t j = chunk + lane;
+        const bool vf = j < total;
+        float x_from = 0.f, x_to = 0.f, ly = 0.f, d = 0.f;
+        int c0 = 0, len = 0, g_own = 0;
+        if (vf) {
+            uint32_t r = rel[0];
+#pragma unroll
+            for (int g = 1; g < G; g++)
+                if (j >= pre[g]) {
+                    g_own = g;
+                    r = rel[g];
+                }
+            const uint2 f = __ldg(&b.fills[r + j]);
+            x_from = (float)(f.x & 0xffffu) * (1.0f / 256.0f);
+            x_to = (float)(f.y & 0xffffu) * (1.0f / 256.0f);
+            const float y_from = (float)(f.x >> 16) * (1.0f / 256.0f), y_to = (float)(f.y >> 16) * (1.0f / 256.0f);
+            const bool from_left = x_from < x_to;
+            ly = from_left ? y_from : y_to;
+            const float ry = from_left ? y_to : y_from;
+            d = (ry - ly) * __fdividef(1.0f, fabsf(x_to - x_from));  // bin never emits x_from == x_to
+            // pixel columns whose window [c, c + 1] the fill overlaps with positive length
+            const float xmin = fminf(x_from, x_to), xmax = fmaxf(x_from, x_to);
+            c0 = min((int)xmin, 15);
+            const int c1 = min((int)ceilf(xmax) - 1, 15);
+            len = max(c1 - c0 + 1, 1);
+        }
+        const int incl_p = (int)warp_incl_scan_u32((uint32_t)len, lane);
+        const int excl = incl_p - len;
+        const int n_pairs = __shfl_sync(0xffffffffu, incl_p, 31);
+        // column of pair p of this fill = p - pair_base; the fill's tile rides along in the low bits
+        const int pair_base_g = ((excl - c0) << 2) | g_own;
+
+        for (int p0 = 0; p0 < n_pairs; p0 += 32) {
+            // ---- which fill does pair p0 + lane belong to: the number of fills that start at or before it, minus one
+            // (every fill owns at least one pair, so fill k is lane k)
+            const unsigned starts = __reduce_or_sync(0xffffffffu, (vf && excl >= p0 && excl < p0 + 32) ? 1u << (excl - p0) : 0u);
+            const int before = __popc(__ballot_sync(0xffffffffu, vf && excl < p0));
+            const int k = before - 1 + __popc(starts & (0xffffffffu >> (31 - lane)));
+            const int srcl = k < 0 ? 0 : (k > 31 ? 31 : k);
+            const float xf = __shfl_sync(0xffffffffu, x_from, srcl), xt = __shfl_sync(0xffffffffu, x_to, srcl);
+            const float lyk = __shfl_sync(0xffffffffu, ly, srcl), dk = __shfl_sync(0xffffffffu, d, srcl);
+            const int pbg = __shfl_sync(0xffffffffu, pair_base_g, srcl);
+            const int pidx = p0 + (int)lane;
+            if (pidx >= n_pairs) continue;
+            const int c = pidx - (pbg >> 2);
+            const float col = (float)c;
+            // window = clamp(vec2(from.x, to.x), -0.5, 0.5) in fragment-centred coordinates (fill.comp:58)
+            const float wx = __saturatef(xf - col), wy = __saturatef(xt - col);
+            const float dX = wx - wy;
+            if (dX == 0.0f) continue;
+            // y of the line at the middle of the window (fill.comp:59-63), tile space
+            const float y_line = fmaf(dk, fmaf(0.5f, wx + wy, col - fminf(xf, xt)), lyk);
+            const float lut_y = fmaf(fabsf(dk * dX), 16.0f, -0.5f);  // v * 256 - 0.5
+            const float fy0 = floorf(lut_y), ay = lut_y - fy0;
+            // rows whose LUT value is not saturated: above r_lo the coverage is 0, below r_hi it is 1
+            int r_lo = 0, r_hi = 15;
+            if (band) {
+                const float hw = (lut_y + 1.0f) * (1.0f / 32.0f);
+                r_lo = (int)ceilf(y_line - hw - (17.0f / 16.0f + 1.0f / 64.0f));
+                r_hi = (int)floorf(y_line + hw + 1.0f / 64.0f);
+            }
+            // windows are the LUT's own 4-row groups (rows 0-3, 4-7, ...): its channels are NOT exact one-row shifts of
+            // each other for steep lines, so a row must be read from the channel fill.comp reads it from
+            const int r_start = max(r_lo, 0) & ~3, r_end = min(r_hi, 15);
+            const float ks = dX * FILL_SCALE;
+            const int v_full = __float2int_rn(ks);
+            int prev = 0;
+            int *const colp = acc + (pbg & 3) * FILL_ACC + c * FILL_CS;
+            int r0 = r_start;
+            for (; r0 <= r_end; r0 += 4) {
+                // texture(uAreaLUT, vec2((y + 8) / 16, v)) for the 4 rows r0 .. r0 + 3 (fill.comp:66-70), fp32 weights
+                const float lut_x = fmaf(y_line - (float)r0, 16.0f, 119.5f);
+                const float fx0 = floorf(lut_x), ax = lut_x - fx0;
+                const float w11 = ax * ay, w10 = ax - w11, w01 = ay - w11, w00 = (1.0f - ax) - w01;
+                const float k00 = w00 * ks, k10 = w10 * ks, k01 = w01 * ks, k11 = w11 * ks;
+                const float4 t00 = tex2D<float4>(p.lut_tex, fx0 + 0.5f, fy0 + 0.5f), t10 = tex2D<float4>(p.lut_tex, fx0 + 1.5f, fy0 + 0.5f);
+                const float4 t01 = tex2D<float4>(p.lut_tex, fx0 + 0.5f, fy0 + 1.5f), t11 = tex2D<float4>(p.lut_tex, fx0 + 1.5f, fy0 + 1.5f);
+                const int v0 = __float2int_rn(fmaf(t11.x, k11, fmaf(t01.x, k01, fmaf(t10.x, k10, t00.x * k00))));
+                const int v1 = __float2int_rn(fmaf(t11.y, k11, fmaf(t01.y, k01, fmaf(t10.y, k10, t00.y * k00))));
+                const int v2 = __float2int_rn(fmaf(t11.z, k11, fmaf(t01.z, k01, fmaf(t10.z, k10, t00.z * k00))));
+                const int v3 = __float2int_rn(fmaf(t11.w, k11, fmaf(t01.w, k01, fmaf(t10.w, k10, t00.w * k00))));
+                atomicAdd(colp + r0, v0 - prev);  // r0 <= 12 (a multiple of 4): rows r0 .. r0 + 3 exist
+                atomicAdd(colp + r0 + 1, v1 - v0);
+                atomicAdd(colp + r0 + 2, v2 - v1);
+                atomicAdd(colp + r0 + 3, v3 - v2);
+                prev = v3;
+            }
+            // every row below the sampled ones is fully covered by the window: one add (telescopes with `prev`)
+            const int tail = r0 > r_start ? r0 : max(r_hi + 1, 0);
+            if (tail <= 15) atomicAdd(colp + tail, v_full - prev);
+        }
+    }
+    __syncwarp();
+    // ---- per tile: coverage = prefix sum down each column (+ backdrop), fill rule, clip, RGBA8-unorm quantisation
+    // (fill.comp:131-153). Lane (c, h) = (lane & 15, lane >> 4) owns rows 8h .. 8h+7 of column c: two 16-byte loads of
+    // the accumulator (zeroed for the next group at once: nobody else reads them), a serial prefix sum in registers and
+    // ONE shuffle for the upper half's total (round 1 kept the mask's lane layout here -- 4 columns x 2 rows -- and paid
+    // a 3-level shuffle scan of 4 values: 135 instructions per tile, 37 % of the kernel). The bytes then go to the
+    // mask's layout by a 4 x 4 byte transpose among the 4 lanes of a column group (2 shuffles + 2 byte permutes per
+    // word) and two 4-byte stores per lane.
+    const int c_own = (int)(lane & 15u), h_own = (int)(lane >> 4), j_own = (int)(lane & 3u);
+    // byte selectors of the two transpose rounds (lane-dependent, tile-independent)
+    const uint32_t sel1 = (j_own & 1) ? 0x3715u : 0x6240u;  // odd: [t1, w1, t3, w3]; even: [w0, t0, w2, t2]
+    const uint32_t sel2 = (j_own & 2) ? 0x3276u : 0x5410u;  // upper: [u2, u3, w2, w3]; lower: [w0, w1, u0, u1]
+    // after the transpose this lane holds pixel row 8h + j (from the first word) and 8h + 4 + j (second word) of columns
+    // 4k .. 4k+3; the mask's layout (pfcu_device.h) puts row y, columns 4k .. 4k+3 at byte ((y >> 1) * 4 + k) * 8 + (y & 1) * 4
+    const int k_grp = c_own >> 2, y_a = h_own * 8 + j_own, y_b = y_a + 4;
+    const uint32_t off_a = (uint32_t)(((y_a >> 1) * 4 + k_grp) * 8 + (y_a & 1) * 4);
+    const uint32_t off_b = (uint32_t)(((y_b >> 1) * 4 + k_grp) * 8 + (y_b & 1) * 4);
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        const uint32_t at_x = __shfl_sync(0xffffffffu, at.x, g), at_y = __shfl_sync(0xffffffffu, at.y, g);
+        const uint32_t at_w = __shfl_sync(0xffffffffu, at.w, g);
+        const uint32_t code = __shfl_sync(0xffffffffu, dst_code, g);
+        if ((at_x & 0x7fffffffu) >= b.tile_count) continue;  // (warp-uniform)
+        int4 *const own = reinterpret_cast<int4 *>(acc + g * FILL_ACC + c_own * FILL_CS + h_own * 8);
+        const int4 ra = own[0], rb = own[1];
+        own[0] = make_int4(0, 0, 0, 0);
+        own[1] = make_int4(0, 0, 0, 0);
+        const int half_total = (ra.x + ra.y + ra.z) + (ra.w + rb.x + rb.y) + (rb.z + rb.w);
+        const int above = __shfl_xor_sync(0xffffffffu, half_total, 16);
+        int cv[8];
+        cv[0] = (int)(int8_t)(at_w & 0xffu) * FILL_ONE + (h_own ? above : 0) + ra.x;
+        cv[1] = cv[0] + ra.y; cv[2] = cv[1] + ra.z; cv[3] = cv[2] + ra.w;
+        cv[4] = cv[3] + rb.x; cv[5] = cv[4] + rb.y; cv[6] = cv[5] + rb.z; cv[7] = cv[6] + rb.w;
+        // round(v * 255) for v in [0, 1] as 12.20 fixed point = (v * 255 + 2^19) >> 20; scaled by 16 it is the TOP BYTE
+        // of a 32-bit product, which the byte permutes below pick up directly
+        uint32_t bytes[8];
+        if (at_x >> 31) {  // winding: min(|cv|, 1)
+#pragma unroll
+            for (int q = 0; q < 8; q++) bytes[q] = (uint32_t)min(abs(cv[q]), FILL_ONE) * (255u << 4) + (1u << 23);
+        } else {           // even-odd: 1 - |1 - mod(cv, 2)|
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int v = FILL_ONE - abs(FILL_ONE - (cv[q] & (2 * FILL_ONE - 1)));
+                bytes[q] = (uint32_t)v * (255u << 4) + (1u << 23);
+            }
+        }
+        // this lane's column as two words (rows 8h .. 8h+3, rows 8h+4 .. 8h+7), then the transposes
+        uint32_t wa = __byte_perm(__byte_perm(bytes[0], bytes[1], 0x0073), __byte_perm(bytes[2], bytes[3], 0x0073), 0x5410);
+        uint32_t wb = __byte_perm(__byte_perm(bytes[4], bytes[5], 0x0073), __byte_perm(bytes[6], bytes[7], 0x0073), 0x5410);
+        wa = __byte_perm(wa, __shfl_xor_sync(0xffffffffu, wa, 1), sel1);
+        wb = __byte_perm(wb, __shfl_xor_sync(0xffffffffu, wb, 1), sel1);
+        wa = __byte_perm(wa, __shfl_xor_sync(0xffffffffu, wa, 2), sel2);
+        wb = __byte_perm(wb, __shfl_xor_sync(0xffffffffu, wb, 2), sel2);
+        if ((int)at_y >= 0 && at_y < b.mask_capacity) {  // fill.comp:147-150: min() with the clip mask (warp-uniform)
+            const uint8_t *clip = b.masks + (size_t)at_y * 256;
+            wa = __vminu4(wa, __ldg(reinterpret_cast<const uint32_t *>(clip + off_a)));
+            wb = __vminu4(wb, __ldg(reinterpret_cast<const uint32_t *>(clip + off_b)));
+        }
+        if (CACHE && (code >> 31)) {
+            uint8_t *const dst = cache + (size_t)(code & 0x7fffffffu) * 256;
+            *reinterpret_cast<uint32_t *>(dst + off_a) = wa;
+            *reinterpret_cast<uint32_t *>(dst + off_b) = wb;
+        } else {
+            uint8_t *const dst = b.masks + (size_t)code * 256;
+            *reinterpret_cast<uint32_t *>(dst + off_a) = wa;
+            *reinterpret_cast<uint32_t *>(dst + off_b) = wb;
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(FILL_WARPS * 32, FILL_CTAS_PER_SM) k_fill(FillArgs b, LutView p) {
     __shared__ FillShared sh;
-    pdl_wait();
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_FILL);
     const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t first_alpha = b.counters->first_alpha;
@@ -148,12 +345,10 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, FILL_CTAS_PER_SM) k_fill(Batc
     int *const acc = &sh.acc[wib][0][0];
     for (int i = (int)lane; i < FILL_GROUP * FILL_ACC; i += 32) acc[i] = 0;
     __syncwarp();
-    const bool band = p.lut_band != 0;
 
     // (Handing the groups out through a global ticket counter instead -- one atomic per group, next ticket prefetched --
     // measured slower: 28.7 us against 24.6 us on tiger 4096^2, profiles/r01_tile_kernel_experiments.md.)
-    uint32_t a0 = warp * FILL_GROUP;
-    for (; a0 < n_alpha;) {
+    for (uint32_t a0 = warp * FILL_GROUP; a0 < n_alpha; a0 += n_warps * FILL_GROUP) {
         // ---- the group's alpha tile records, one per lane: tile | winding << 31, clip mask slot, first fill,
         // backdrop | fill count << 8
         uint4 at = make_uint4(0x7fffffffu, 0xffffffffu, 0u, 0u);
@@ -161,193 +356,19 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, FILL_CTAS_PER_SM) k_fill(Batc
             at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a0 + lane]));
         uint32_t fbt = 0xffffffffu;
         if (b.cull_fill && lane < FILL_GROUP && a0 + lane < n_alpha) fbt = __ldg(&b.alpha_map[a0 + lane]);
-        bool visible = (at.x & 0x7fffffffu) < b.tile_count;  // else: fills that the clip made invisible, no mask
         // a mask under an opaque whole-tile layer of a later path is never read (the list scatter leaves its tile out,
         // sort.comp:62): do not rasterize it. The z-buffer is final: propagate has finished.
-        if (fbt != 0xffffffffu && (int)(at.x & 0x7fffffffu) < b.fb[fbt].z) {
-            visible = false;
-            at.x = 0x7fffffffu;
-        }
-        const uint32_t begin = min(at.z, b.fill_capacity);
-        const uint32_t count = visible ? min(at.w >> 8, b.fill_capacity - begin) : 0u;
-        // the fills of the group as one sequence: tile g owns [pre_g, pre_g + count_g)
-        uint32_t incl = count;
-#pragma unroll
-        for (int d = 1; d < FILL_GROUP; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= (unsigned)d) incl += t;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, FILL_GROUP - 1);
-        uint32_t pre[FILL_GROUP], rel[FILL_GROUP];  // rel_g: address of the tile's fill j = rel_g + j
-#pragma unroll
-        for (int g = 0; g < FILL_GROUP; g++) {
-            pre[g] = __shfl_sync(0xffffffffu, incl - count, g);
-            rel[g] = __shfl_sync(0xffffffffu, begin, g) - pre[g];
-        }
-
-        for (uint32_t chunk = 0; chunk < total; chunk += 32) {
-            // ---- one fill per lane: what only depends on the fill (fill.comp:53-64)
-            const uint32_t j = chunk + lane;
-            const bool vf = j < total;
-            float x_from = 0.f, x_to = 0.f, ly = 0.f, d = 0.f;
-            int c0 = 0, len = 0, g_own = 0;
-            if (vf) {
-                uint32_t r = rel[0];
-#pragma unroll
-                for (int g = 1; g < FILL_GROUP; g++)
-                    if (j >= pre[g]) {
-                        g_own = g;
-                        r = rel[g];
-                    }
-                const uint2 f = __ldg(&b.fills[r + j]);
-                x_from = (float)(f.x & 0xffffu) * (1.0f / 256.0f);
-                x_to = (float)(f.y & 0xffffu) * (1.0f / 256.0f);
-                const float y_from = (float)(f.x >> 16) * (1.0f / 256.0f), y_to = (float)(f.y >> 16) * (1.0f / 256.0f);
-                const bool from_left = x_from < x_to;
-                ly = from_left ? y_from : y_to;
-                const float ry = from_left ? y_to : y_from;
-                d = (ry - ly) * __fdividef(1.0f, fabsf(x_to - x_from));  // bin never emits x_from == x_to
-                // pixel columns whose window [c, c + 1] the fill overlaps with positive length
-                const float xmin = fminf(x_from, x_to), xmax = fmaxf(x_from, x_to);
-                c0 = min((int)xmin, 15);
-                const int c1 = min((int)ceilf(xmax) - 1, 15);
-                len = max(c1 - c0 + 1, 1);
-            }
-            const int incl_p = (int)warp_incl_scan_u32((uint32_t)len, lane);
-            const int excl = incl_p - len;
-            const int n_pairs = __shfl_sync(0xffffffffu, incl_p, 31);
-            // column of pair p of this fill = p - pair_base; the fill's tile rides along in the low bits
-            const int pair_base_g = ((excl - c0) << 2) | g_own;
-
-            for (int p0 = 0; p0 < n_pairs; p0 += 32) {
-                // ---- which fill does pair p0 + lane belong to: the number of fills that start at or before it, minus one
-                // (every fill owns at least one pair, so fill k is lane k)
-                const unsigned starts = __reduce_or_sync(0xffffffffu, (vf && excl >= p0 && excl < p0 + 32) ? 1u << (excl - p0) : 0u);
-                const int before = __popc(__ballot_sync(0xffffffffu, vf && excl < p0));
-                const int k = before - 1 + __popc(starts & (0xffffffffu >> (31 - lane)));
-                const int srcl = k < 0 ? 0 : (k > 31 ? 31 : k);
-                const float xf = __shfl_sync(0xffffffffu, x_from, srcl), xt = __shfl_sync(0xffffffffu, x_to, srcl);
-                const float lyk = __shfl_sync(0xffffffffu, ly, srcl), dk = __shfl_sync(0xffffffffu, d, srcl);
-                const int pbg = __shfl_sync(0xffffffffu, pair_base_g, srcl);
-                const int pidx = p0 + (int)lane;
-                if (pidx >= n_pairs) continue;
-                const int c = pidx - (pbg >> 2);
-                const float col = (float)c;
-                // window = clamp(vec2(from.x, to.x), -0.5, 0.5) in fragment-centred coordinates (fill.comp:58)
-                const float wx = __saturatef(xf - col), wy = __saturatef(xt - col);
-                const float dX = wx - wy;
-                if (dX == 0.0f) continue;
-                // y of the line at the middle of the window (fill.comp:59-63), tile space
-                const float y_line = fmaf(dk, fmaf(0.5f, wx + wy, col - fminf(xf, xt)), lyk);
-                const float lut_y = fmaf(fabsf(dk * dX), 16.0f, -0.5f);  // v * 256 - 0.5
-                const float fy0 = floorf(lut_y), ay = lut_y - fy0;
-                // rows whose LUT value is not saturated: above r_lo the coverage is 0, below r_hi it is 1
-                int r_lo = 0, r_hi = 15;
-                if (band) {
-                    const float hw = (lut_y + 1.0f) * (1.0f / 32.0f);
-                    r_lo = (int)ceilf(y_line - hw - (17.0f / 16.0f + 1.0f / 64.0f));
-                    r_hi = (int)floorf(y_line + hw + 1.0f / 64.0f);
-                }
-                // windows are the LUT's own 4-row groups (rows 0-3, 4-7, ...): its channels are NOT exact one-row shifts of
-                // each other for steep lines, so a row must be read from the channel fill.comp reads it from
-                const int r_start = max(r_lo, 0) & ~3, r_end = min(r_hi, 15);
-                const float ks = dX * FILL_SCALE;
-                const int v_full = __float2int_rn(ks);
-                int prev = 0;
-                int *const colp = acc + (pbg & 3) * FILL_ACC + c * FILL_CS;
-                int r0 = r_start;
-                for (; r0 <= r_end; r0 += 4) {
-                    // texture(uAreaLUT, vec2((y + 8) / 16, v)) for the 4 rows r0 .. r0 + 3 (fill.comp:66-70), fp32 weights
-                    const float lut_x = fmaf(y_line - (float)r0, 16.0f, 119.5f);
-                    const float fx0 = floorf(lut_x), ax = lut_x - fx0;
-                    const float w11 = ax * ay, w10 = ax - w11, w01 = ay - w11, w00 = (1.0f - ax) - w01;
-                    const float k00 = w00 * ks, k10 = w10 * ks, k01 = w01 * ks, k11 = w11 * ks;
-                    const float4 t00 = tex2D<float4>(p.lut_tex, fx0 + 0.5f, fy0 + 0.5f), t10 = tex2D<float4>(p.lut_tex, fx0 + 1.5f, fy0 + 0.5f);
-                    const float4 t01 = tex2D<float4>(p.lut_tex, fx0 + 0.5f, fy0 + 1.5f), t11 = tex2D<float4>(p.lut_tex, fx0 + 1.5f, fy0 + 1.5f);
-                    const int v0 = __float2int_rn(fmaf(t11.x, k11, fmaf(t01.x, k01, fmaf(t10.x, k10, t00.x * k00))));
-                    const int v1 = __float2int_rn(fmaf(t11.y, k11, fmaf(t01.y, k01, fmaf(t10.y, k10, t00.y * k00))));
-                    const int v2 = __float2int_rn(fmaf(t11.z, k11, fmaf(t01.z, k01, fmaf(t10.z, k10, t00.z * k00))));
-                    const int v3 = __float2int_rn(fmaf(t11.w, k11, fmaf(t01.w, k01, fmaf(t10.w, k10, t00.w * k00))));
-                    atomicAdd(colp + r0, v0 - prev);  // r0 <= 12 (a multiple of 4): rows r0 .. r0 + 3 exist
-                    atomicAdd(colp + r0 + 1, v1 - v0);
-                    atomicAdd(colp + r0 + 2, v2 - v1);
-                    atomicAdd(colp + r0 + 3, v3 - v2);
-                    prev = v3;
-                }
-                // every row below the sampled ones is fully covered by the window: one add (telescopes with `prev`)
-                const int tail = r0 > r_start ? r0 : max(r_hi + 1, 0);
-                if (tail <= 15) atomicAdd(colp + tail, v_full - prev);
-            }
-        }
-        __syncwarp();
-        // ---- per tile: coverage = prefix sum down each column (+ backdrop), fill rule, clip, RGBA8-unorm quantisation
-        // (fill.comp:131-153). Lane (c, h) = (lane & 15, lane >> 4) owns rows 8h .. 8h+7 of column c: two 16-byte loads of
-        // the accumulator (zeroed for the next group at once: nobody else reads them), a serial prefix sum in registers and
-        // ONE shuffle for the upper half's total (round 1 kept the mask's lane layout here -- 4 columns x 2 rows -- and paid
-        // a 3-level shuffle scan of 4 values: 135 instructions per tile, 37 % of the kernel). The bytes then go to the
-        // mask's layout by a 4 x 4 byte transpose among the 4 lanes of a column group (2 shuffles + 2 byte permutes per
-        // word) and two 4-byte stores per lane.
-        const int c_own = (int)(lane & 15u), h_own = (int)(lane >> 4), j_own = (int)(lane & 3u);
-        // byte selectors of the two transpose rounds (lane-dependent, tile-independent)
-        const uint32_t sel1 = (j_own & 1) ? 0x3715u : 0x6240u;  // odd: [t1, w1, t3, w3]; even: [w0, t0, w2, t2]
-        const uint32_t sel2 = (j_own & 2) ? 0x3276u : 0x5410u;  // upper: [u2, u3, w2, w3]; lower: [w0, w1, u0, u1]
-        // after the transpose this lane holds pixel row 8h + j (from the first word) and 8h + 4 + j (second word) of columns
-        // 4k .. 4k+3; the mask's layout (pfcu_device.h) puts row y, columns 4k .. 4k+3 at byte ((y >> 1) * 4 + k) * 8 + (y & 1) * 4
-        const int k_grp = c_own >> 2, y_a = h_own * 8 + j_own, y_b = y_a + 4;
-        const uint32_t off_a = (uint32_t)(((y_a >> 1) * 4 + k_grp) * 8 + (y_a & 1) * 4);
-        const uint32_t off_b = (uint32_t)(((y_b >> 1) * 4 + k_grp) * 8 + (y_b & 1) * 4);
-#pragma unroll
-        for (int g = 0; g < FILL_GROUP; g++) {
-            const uint32_t at_x = __shfl_sync(0xffffffffu, at.x, g), at_y = __shfl_sync(0xffffffffu, at.y, g);
-            const uint32_t at_w = __shfl_sync(0xffffffffu, at.w, g);
-            if ((at_x & 0x7fffffffu) >= b.tile_count) continue;  // (warp-uniform)
-            int4 *const own = reinterpret_cast<int4 *>(acc + g * FILL_ACC + c_own * FILL_CS + h_own * 8);
-            const int4 ra = own[0], rb = own[1];
-            own[0] = make_int4(0, 0, 0, 0);
-            own[1] = make_int4(0, 0, 0, 0);
-            const int half_total = (ra.x + ra.y + ra.z) + (ra.w + rb.x + rb.y) + (rb.z + rb.w);
-            const int above = __shfl_xor_sync(0xffffffffu, half_total, 16);
-            int cv[8];
-            cv[0] = (int)(int8_t)(at_w & 0xffu) * FILL_ONE + (h_own ? above : 0) + ra.x;
-            cv[1] = cv[0] + ra.y; cv[2] = cv[1] + ra.z; cv[3] = cv[2] + ra.w;
-            cv[4] = cv[3] + rb.x; cv[5] = cv[4] + rb.y; cv[6] = cv[5] + rb.z; cv[7] = cv[6] + rb.w;
-            // round(v * 255) for v in [0, 1] as 12.20 fixed point = (v * 255 + 2^19) >> 20; scaled by 16 it is the TOP BYTE
-            // of a 32-bit product, which the byte permutes below pick up directly
-            uint32_t bytes[8];
-            if (at_x >> 31) {  // winding: min(|cv|, 1)
-#pragma unroll
-                for (int q = 0; q < 8; q++) bytes[q] = (uint32_t)min(abs(cv[q]), FILL_ONE) * (255u << 4) + (1u << 23);
-            } else {           // even-odd: 1 - |1 - mod(cv, 2)|
-#pragma unroll
-                for (int q = 0; q < 8; q++) {
-                    const int v = FILL_ONE - abs(FILL_ONE - (cv[q] & (2 * FILL_ONE - 1)));
-                    bytes[q] = (uint32_t)v * (255u << 4) + (1u << 23);
-                }
-            }
-            // this lane's column as two words (rows 8h .. 8h+3, rows 8h+4 .. 8h+7), then the transposes
-            uint32_t wa = __byte_perm(__byte_perm(bytes[0], bytes[1], 0x0073), __byte_perm(bytes[2], bytes[3], 0x0073), 0x5410);
-            uint32_t wb = __byte_perm(__byte_perm(bytes[4], bytes[5], 0x0073), __byte_perm(bytes[6], bytes[7], 0x0073), 0x5410);
-            wa = __byte_perm(wa, __shfl_xor_sync(0xffffffffu, wa, 1), sel1);
-            wb = __byte_perm(wb, __shfl_xor_sync(0xffffffffu, wb, 1), sel1);
-            wa = __byte_perm(wa, __shfl_xor_sync(0xffffffffu, wa, 2), sel2);
-            wb = __byte_perm(wb, __shfl_xor_sync(0xffffffffu, wb, 2), sel2);
-            if ((int)at_y >= 0 && at_y < b.mask_capacity) {  // fill.comp:147-150: min() with the clip mask (warp-uniform)
-                const uint8_t *clip = b.masks + (size_t)at_y * 256;
-                wa = __vminu4(wa, __ldg(reinterpret_cast<const uint32_t *>(clip + off_a)));
-                wb = __vminu4(wb, __ldg(reinterpret_cast<const uint32_t *>(clip + off_b)));
-            }
-            uint8_t *const dst = b.masks + (size_t)(first_alpha + a0 + g) * 256;
-            *reinterpret_cast<uint32_t *>(dst + off_a) = wa;
-            *reinterpret_cast<uint32_t *>(dst + off_b) = wb;
-        }
-        __syncwarp();
-        a0 += n_warps * FILL_GROUP;
+        if (fbt != 0xffffffffu && (int)(at.x & 0x7fffffffu) < b.fb[fbt].z) at.x = 0x7fffffffu;
+        fill_group<FILL_GROUP, false>(at, first_alpha + a0 + lane, nullptr, acc, b, p, lane);
     }
 }
 
 cudaError_t launch_fill(const BatchView &b, const PaintView &p, cudaStream_t s) {
-    if (!b.tile_count || !p.lut_tex) return cudaSuccess;
-    return launch_pdl(k_fill, sm_count() * FILL_CTAS_PER_SM, FILL_WARPS * 32, 0, s, b, p);
+    if (!b.tile_count || !p.lut_tex || b.fused_fill) return cudaSuccess;  // fused: the tile kernel rasterizes the masks
+    LutView lv;
+    lv.lut_tex = p.lut_tex;
+    lv.lut_band = p.lut_band;
+    return launch_pdl(k_fill, sm_count() * FILL_CTAS_PER_SM, FILL_WARPS * 32, 0, s, FillArgs(b), lv);
 }
 
 // ------------------------------------------------------------------------------------------------ tile
@@ -568,6 +589,9 @@ __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 constexpr int CT_WARPS = CT_WARPS_N;   // warps per CTA
 constexpr int CT_THREADS = CT_WARPS * 32;
 constexpr int CT_TILES = CT_WARPS * 4; // consecutive framebuffer tiles of one group (8 threads order one tile's list)
+#if CT_WARPS_N == 4
+static_assert(CT_TILES == GROUP_TILES, "the scan lays the headers out for groups of CT_TILES tiles");
+#endif
 constexpr int CT_PRIMS = 256;          // list entries staged per group (more: the CTA takes the group in several rounds)
 constexpr uint32_t KEY_MASK = 0x00ffffffu;
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {
@@ -672,7 +696,29 @@ __device__ __forceinline__ float2 mask_pair(uint2 mask8, int j, bool even_odd) {
     return c;
 }
 
-template <bool SOLID>
+#ifndef FUSE_GROUP_N
+#define FUSE_GROUP_N 2
+#endif
+#ifndef FUSE_MASKS_N
+#define FUSE_MASKS_N 32
+#endif
+constexpr int FUSE_GROUP = FUSE_GROUP_N;  // masks a warp of the tile kernel rasterizes together
+constexpr int FUSE_MASKS = FUSE_MASKS_N;  // masks of a tile group kept in shared memory (the others go through b.masks)
+
+// What the tile kernel needs on top of its own staging buffers to rasterize the masks of its tiles itself
+// (BatchView::fused_fill): accumulators, the finished masks, the alpha tile records fetched while the lists are ordered.
+template <bool FUSED>
+struct __align__(16) FusedShared {};
+template <>
+struct __align__(16) FusedShared<true> {
+    int acc[CT_WARPS][FUSE_GROUP][FILL_ACC];
+    uint2 cache[FUSE_MASKS][32];
+    uint4 at[FUSE_MASKS];
+    uint32_t alpha[CT_PRIMS];  // batch-local alpha tile of every mask the group needs
+    uint32_t n_masks, next_mask;
+};
+
+template <bool SOLID, bool FUSED>
 struct __align__(16) CompositeShared {
     uint4 fb[CT_TILES];                // list begin, slots (count before z-cull), z, entries
     uint4 raw[CT_PRIMS];               // the lists as the scatter left them
@@ -684,6 +730,7 @@ struct __align__(16) CompositeShared {
     uint16_t paint[SOLID ? 8 : CT_PRIMS]; // paint of every layer (textured layers look their constants up at blend time)
     uint16_t work[CT_TILES * 4];       // per-pixel work items: tile | pixel pairs (bit j = pair j of every lane) << 8
     uint32_t n_work, next, flat_mask;
+    FusedShared<FUSED> fz;
 };
 
 struct TileGeom {
@@ -696,8 +743,8 @@ struct TileGeom {
 // A general-format list entry (key, mask slot, paint | ctrl << 16 | backdrop << 24) resolved against the paint table:
 // key | LayerFlags << 24, mask slot, base colour as halfs. Frames whose paints are all plain colours get this from the list
 // scatter already (BatchView::solid_prims).
-template <bool SOLID>
-__device__ __forceinline__ uint4 resolve_prim(const uint4 q, const BatchView &b, const PaintView &p, uint32_t &paint) {
+template <bool SOLID, class B>
+__device__ __forceinline__ uint4 resolve_prim(const uint4 q, const B &b, const PaintView &p, uint32_t &paint) {
     if (SOLID || b.solid_prims) {
         paint = 0;
         return q;
@@ -715,15 +762,21 @@ __device__ __forceinline__ uint4 resolve_prim(const uint4 q, const BatchView &b,
     return make_uint4((q.x & KEY_MASK) | (fl << 24), q.y, *reinterpret_cast<const uint32_t *>(&rg), *reinterpret_cast<const uint32_t *>(&ba));
 }
 
-// One layer over the lane's 8 pixels (tile.comp:765-842 for one list entry).
-// the lane's 8 coverage bytes of a layer (all ones for a layer without a mask)
-__device__ __forceinline__ uint2 load_mask(const uint4 u, const BatchView &b, unsigned lane) {
+// the lane's 8 coverage bytes of a layer (all ones for a layer without a mask). FUSED: the masks this kernel rasterized
+// itself are in shared memory (slot | 1 << 31) or were written to b.masks by this CTA (no read-only path for those)
+template <bool FUSED, class B>
+__device__ __forceinline__ uint2 load_mask(const uint4 u, const B &b, const uint2 (*cache)[32], unsigned lane) {
     if (!(u.x & ((uint32_t)LF_MASKED << 24)) || (u.x & ((uint32_t)LF_SKIP << 24))) return make_uint2(0xffffffffu, 0xffffffffu);
+    if (FUSED) {
+        if (u.y >> 31) return cache[u.y & 0x7fffffffu][lane];
+        return __ldcg(reinterpret_cast<const uint2 *>(b.masks + (size_t)u.y * 256) + lane);
+    }
     return __ldg(reinterpret_cast<const uint2 *>(b.masks + (size_t)u.y * 256) + lane);
 }
 
-template <bool SOLID>
-__device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 u, const uint2 mask8, uint32_t paint, const BatchView &b,
+// One layer over the lane's 8 pixels (tile.comp:765-842 for one list entry).
+template <bool SOLID, class B>
+__device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 u, const uint2 mask8, uint32_t paint, const B &b,
                                             const PaintView &p, const ColorSampler &cs, const TileGeom &g,
                                             const TargetView &tg, unsigned lane, uint32_t pairs = 0xfu) {
     const uint32_t fl = u.x >> 24;
@@ -831,16 +884,38 @@ __device__ __forceinline__ uint4 clamp_header(uint4 f, uint32_t prim_capacity) {
 // headers and lists staged once by bulk copies (39 / 48 us); one warp per 2 / 4 / 8 tiles with no block-wide barrier at all
 // (41 - 50 us); a separate sort kernel + warp-per-tile blend kernel; streaming / evict-first / TMA tensor stores for the
 // framebuffer (no faster than plain 16-byte stores, tools/ubench/store_floor.cu).
-template <bool SOLID>
-__global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_TEX) k_composite(BatchView b, PaintView p, TargetView tg, int clear,
+//
+// FUSED (BatchView::fused_fill, PFCU_OPT_FUSED_FILL): the fill stage runs INSIDE this kernel. The layers that need a mask of
+// this batch are collected while the lists are ordered (their alpha tile records fetched, their fills prefetched); before
+// the per-pixel tiles are blended the CTA's warps rasterize those masks, FUSE_GROUP at a time, with fill's own code
+// (fill_group) into shared memory. Only masks that a list references are ever rasterized, none is written to or read from
+// HBM, and k_fill is not launched for the batch. Masks of other batches (clip masks) are read from b.masks as before.
+// Byte-identical frames, but measured SLOWER than the separate fill kernel on tiger 4096^2 (64.2 us against 24.6 us of fill
+// beside the list building + 29.1 us: 23.1 M warp instructions, SM-active 64 K .. 115 K of 118 K elapsed cycles -- the masked
+// tiles of a group serialise behind their CTA's four warps, and a quarter of the warp time waits at the barrier between
+// rasterizing and blending; profiles/r02_tile_kernel.md section 7), so it is off by default.
+template <bool SOLID, bool FUSED>
+__global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_TEX) k_composite(CompositeArgs b, PaintView p, TargetView tg, int clear,
                                                                       float4 clear_color, int origin, uint32_t tiles_per_cta,
-                                                                      uint32_t sub_tw, uint32_t sub_n) {
-    __shared__ CompositeShared<SOLID> sh;
-    pdl_wait();
+                                                                      uint32_t sub_tw, uint32_t sub_n, int ordered) {
+    __shared__ CompositeShared<SOLID, FUSED> sh;
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_COMPOSITE);
     const unsigned tid = threadIdx.x, lane = tid & 31;
+    const uint2(*mask_cache)[32] = nullptr;
+    uint32_t first_alpha = 0, n_alpha = 0;
+    bool acc_zeroed = false;
+    if constexpr (FUSED) {
+        mask_cache = sh.fz.cache;
+        first_alpha = __ldg(&b.counters->first_alpha);
+        n_alpha = min(__ldg(&b.counters->n_alpha), b.alpha_capacity);
+    }
     // the CTA's tiles: tiles_per_cta consecutive tiles of the sub_tw-wide rectangle of the tile grid that the target
     // covers (the whole grid for the destination; a render-target page is smaller than the scene's grid)
-    const uint32_t map0 = blockIdx.x * tiles_per_cta;
+    // `ordered` (the destination, GROUP_TILES tiles per CTA, groups sorted by cost: BatchView::fb_sorted): this CTA renders
+    // group group_of[blockIdx.x], whose headers the scan left at blockIdx.x * GROUP_TILES -- both loads go out together.
+    uint4 f_direct = make_uint4(0u, 0u, 0u, 0u);
+    if (ordered && tid < CT_TILES) f_direct = __ldg(reinterpret_cast<const uint4 *>(&b.fb_sorted[blockIdx.x * GROUP_TILES + tid]));
+    const uint32_t map0 = (ordered ? __ldg(&b.group_of[blockIdx.x]) : blockIdx.x) * tiles_per_cta;
     const uint32_t n_tiles = min(tiles_per_cta, sub_n - map0);
 
     // ---- stage 1: list headers
@@ -849,7 +924,8 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
         uint32_t xy = 0;
         if (tid < n_tiles) {
             const uint32_t at = map0 + tid, ty = at / sub_tw, tx = at - ty * sub_tw;
-            f = clamp_header(__ldg(reinterpret_cast<const uint4 *>(&b.fb[ty * (uint32_t)b.fb_tw + tx])), b.prim_capacity);
+            if (!ordered) f_direct = __ldg(reinterpret_cast<const uint4 *>(fb_header(b, ty * (uint32_t)b.fb_tw + tx)));
+            f = clamp_header(f_direct, b.prim_capacity);
             xy = tx | (ty << 16);
         }
         sh.fb[tid] = f;
@@ -883,6 +959,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
             sh.n_work = 0;
             sh.next = 0;
             sh.flat_mask = 0;
+            if constexpr (FUSED) sh.fz.n_masks = sh.fz.next_mask = 0;
         }
         if (range_n > CT_PRIMS) {
             // ---- a single tile whose list does not fit (te == tb + 1): one warp walks it by repeated selection of the
@@ -916,6 +993,31 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                     u = resolve_prim<SOLID>(__ldg(&list[best_i]), b, p, paint);
                     return true;
                 };
+                if constexpr (FUSED) {
+                    // the list's own masks first, through b.masks (where k_fill would have put them)
+                    int *const acc = &sh.fz.acc[0][0][0];
+                    if (!acc_zeroed) {
+                        for (int i = (int)lane; i < FUSE_GROUP * FILL_ACC; i += 32) acc[i] = 0;
+                        acc_zeroed = true;
+                        __syncwarp();
+                    }
+                    for (uint32_t i0 = 0; i0 < hdr.w; i0 += FUSE_GROUP) {
+                        uint4 at = make_uint4(0x7fffffffu, 0xffffffffu, 0u, 0u);
+                        uint32_t code = 0;
+                        if (lane < FUSE_GROUP && i0 + lane < hdr.w) {
+                            uint32_t paint;
+                            const uint4 u = resolve_prim<SOLID>(__ldg(&list[i0 + lane]), b, p, paint);
+                            const uint32_t a = u.y - first_alpha;
+                            if ((u.x & ((uint32_t)LF_MASKED << 24)) && u.y >= first_alpha && a < n_alpha) {
+                                at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]));
+                                code = u.y;
+                            }
+                        }
+                        fill_group<FUSE_GROUP, false>(at, code, nullptr, acc, b, p, lane);
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                }
                 {
                     PixelBlock px;
                     if (clear) px.set_all(clear_color);
@@ -923,7 +1025,8 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                     uint32_t last_key = 0, paint;
                     bool first = true;
                     uint4 u;
-                    while (next_layer(last_key, first, u, paint)) blend_layer<SOLID>(px, u, load_mask(u, b, lane), paint, b, p, cs, g, tg, lane);
+                    while (next_layer(last_key, first, u, paint))
+                        blend_layer<SOLID>(px, u, load_mask<FUSED>(u, b, mask_cache, lane), paint, b, p, cs, g, tg, lane);
                     if (clear || hdr.w) store_block<SOLID>(px, g, tg);
                 }
             }
@@ -954,10 +1057,28 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                     uint32_t rank = 0;
                     for (uint32_t j = 0; j < n; j++) rank += (sh.raw[off + j].x & KEY_MASK) < key ? 1u : 0u;
                     uint32_t paint;
-                    const uint4 u = resolve_prim<SOLID>(q, b, p, paint);
+                    uint4 u = resolve_prim<SOLID>(q, b, p, paint);
                     if ((u.x & ((uint32_t)LF_MASKED << 24))) {
-                        prefetch_l1(b.masks + (size_t)u.y * 256);
-                        prefetch_l1(b.masks + (size_t)u.y * 256 + 128);
+                        bool own = false;
+                        if constexpr (FUSED) {
+                            // a mask of this batch: this CTA rasterizes it (stage 3b). Fetch its record, start on its fills
+                            const uint32_t a = u.y - first_alpha;
+                            own = u.y >= first_alpha && a < n_alpha;
+                            if (own) {
+                                const uint32_t m = atomicAdd(&sh.fz.n_masks, 1u);
+                                sh.fz.alpha[m] = a;
+                                if (m < FUSE_MASKS) {
+                                    const uint4 at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]));
+                                    sh.fz.at[m] = at;
+                                    if (at.z < b.fill_capacity) prefetch_l1(&b.fills[at.z]);
+                                    u.y = 0x80000000u | m;
+                                }
+                            }
+                        }
+                        if (!own) {
+                            prefetch_l1(b.masks + (size_t)u.y * 256);
+                            prefetch_l1(b.masks + (size_t)u.y * 256 + 128);
+                        }
                     }
                     sh.sorted[off + rank] = u;
                     if (!SOLID) sh.paint[off + rank] = (uint16_t)paint;
@@ -1033,6 +1154,40 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
             }
         }
 
+        // ---- stage 3b (FUSED): the masks of this batch that the round's lists reference, FUSE_GROUP per warp and turn
+        if constexpr (FUSED) {
+            const uint32_t n_masks = sh.fz.n_masks;
+            if (n_masks) {
+                int *const acc = &sh.fz.acc[tid >> 5][0][0];
+                if (!acc_zeroed) {
+                    for (int i = (int)lane; i < FUSE_GROUP * FILL_ACC; i += 32) acc[i] = 0;
+                    acc_zeroed = true;
+                    __syncwarp();
+                }
+                while (true) {
+                    uint32_t m0 = 0;
+                    if (lane == 0) m0 = atomicAdd(&sh.fz.next_mask, (uint32_t)FUSE_GROUP);
+                    m0 = __shfl_sync(0xffffffffu, m0, 0);
+                    if (m0 >= n_masks) break;
+                    uint4 at = make_uint4(0x7fffffffu, 0xffffffffu, 0u, 0u);
+                    uint32_t code = 0;
+                    const uint32_t m = m0 + lane;
+                    if (lane < FUSE_GROUP && m < n_masks) {
+                        const uint32_t a = sh.fz.alpha[m];
+                        if (m < FUSE_MASKS) {
+                            at = sh.fz.at[m];
+                            code = 0x80000000u | m;
+                        } else if (first_alpha + a < b.mask_capacity) {
+                            at = __ldg(reinterpret_cast<const uint4 *>(&b.alpha_tiles[a]));
+                            code = first_alpha + a;
+                        }
+                    }
+                    fill_group<FUSE_GROUP, true>(at, code, reinterpret_cast<uint8_t *>(sh.fz.cache), acc, b, p, lane);
+                }
+                __syncthreads();  // (block-uniform: n_masks is)
+            }
+        }
+
         // ---- stage 4b: the other tiles, one warp per tile; the mask of layer i + 1 is fetched before layer i is blended
         {
             const uint32_t n_work = sh.n_work;
@@ -1049,7 +1204,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                 const uint32_t pairs = SOLID ? 0xfu : item >> 8;
                 uint32_t i = i0;
                 uint4 u = sh.sorted[off + i];
-                uint2 mask8 = load_mask(u, b, lane);
+                uint2 mask8 = load_mask<FUSED>(u, b, mask_cache, lane);
                 PixelBlock px;
                 if (clear) px.set_all(sh.start_color[t]);
                 else load_block(px, g, tg);
@@ -1058,7 +1213,7 @@ __global__ void __launch_bounds__(CT_THREADS, SOLID ? CT_MIN_CTAS : CT_MIN_CTAS_
                     uint2 mn = mask8;
                     if (i + 1 < n) {
                         un = sh.sorted[off + i + 1];
-                        mn = load_mask(un, b, lane);
+                        mn = load_mask<FUSED>(un, b, mask_cache, lane);
                     }
                     blend_layer<SOLID>(px, u, mask8, SOLID ? 0u : (uint32_t)sh.paint[off + i], b, p, cs, g, tg, lane, pairs);
                     if (++i >= n) break;
@@ -1086,11 +1241,17 @@ cudaError_t launch_composite(const BatchView &b, const PaintView &p, const Targe
     const float4 cc = make_float4(clear_color[0], clear_color[1], clear_color[2], clear_color[3]);
     // the plain-colour instantiation skips the saturation before the RGBA8 conversion: src-over of premultiplied colours
     // in [0, 1] stays in [0, 1]
+    // CTA j renders the j-th most expensive group: only when the pass walks the whole grid in groups of GROUP_TILES
+    // (the destination); other passes find their headers through slot_of
+    const int whole = b.fb_sorted && sub_tw == (uint32_t)b.fb_tw && sub_th == (uint32_t)b.fb_th;
+    int ordered = whole;
     bool unit = p.all_solid && p.unit_range && b.solid_prims;
     for (int i = 0; i < 4; i++) unit = unit && clear_color[i] >= 0.0f && clear_color[i] <= 1.0f;
     if (unit) {
         const uint32_t tpc = CT_TILES;
-        return launch_pdl(k_composite<true>, (n_fb + tpc - 1) / tpc, CT_THREADS, 0, s, b, p, t, clear, cc, origin, tpc, sub_tw, n_fb);
+        if (b.fused_fill)
+            return launch_pdl(k_composite<true, true>, (n_fb + tpc - 1) / tpc, CT_THREADS, 0, s, CompositeArgs(b), p, t, clear, cc, origin, tpc, sub_tw, n_fb, ordered);
+        return launch_pdl(k_composite<true, false>, (n_fb + tpc - 1) / tpc, CT_THREADS, 0, s, CompositeArgs(b), p, t, clear, cc, origin, tpc, sub_tw, n_fb, ordered);
     }
     // Textured passes on small targets (the blur passes of a shadow run on a render target of a few hundred tiles, and
     // a blurred pixel costs thousands of instructions): fewer tiles per CTA, so that the pass covers every SM instead of
@@ -1102,7 +1263,10 @@ cudaError_t launch_composite(const BatchView &b, const PaintView &p, const Targe
     // CTA, so that the hardware spreads them over all SMs (each is split over the CTA's four warps)
     if (heavy_paints) tpc = 1;
     if (tpc < 1) tpc = 1;
-    return launch_pdl(k_composite<false>, (n_fb + tpc - 1) / tpc, CT_THREADS, 0, s, b, p, t, clear, cc, origin, tpc, sub_tw, n_fb);
+    ordered = whole && tpc == (uint32_t)GROUP_TILES;
+    if (b.fused_fill)
+        return launch_pdl(k_composite<false, true>, (n_fb + tpc - 1) / tpc, CT_THREADS, 0, s, CompositeArgs(b), p, t, clear, cc, origin, tpc, sub_tw, n_fb, ordered);
+    return launch_pdl(k_composite<false, false>, (n_fb + tpc - 1) / tpc, CT_THREADS, 0, s, CompositeArgs(b), p, t, clear, cc, origin, tpc, sub_tw, n_fb, ordered);
 }
 
 }  // namespace pfcu

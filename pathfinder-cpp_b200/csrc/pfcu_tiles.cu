@@ -20,6 +20,10 @@
 //                    Ordering and z-culling happen on chip in the composite kernel.
 #include <cuda_fp16.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "pfcu_device.h"
 
 namespace pfcu {
@@ -42,6 +46,25 @@ int sm_count() {
     return counts[dev];
 }
 
+void prefer_carveout(const void *kernel) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void *>> done;
+    const std::pair<int, const void *> key(current_device(), kernel);
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto &k : done)
+        if (k == key) return;
+    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, PFCU_CARVEOUT_PCT);
+    done.push_back(key);
+}
+
+bool timeline_compiled() {
+#ifdef PFCU_TIMELINE
+    return true;
+#else
+    return false;
+#endif
+}
+
 #ifndef SCAN_THREADS_N
 #define SCAN_THREADS_N 256
 #endif
@@ -53,8 +76,8 @@ __host__ __device__ static inline uint32_t scan_tiles_for(uint32_t n) { return (
 
 // ------------------------------------------------------------------------------------------------ init
 
-__global__ void __launch_bounds__(256) k_init(BatchView b) {
-    pdl_wait();
+__global__ void __launch_bounds__(256) k_init(InitArgs b) {
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_INIT);
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t fbt = (uint32_t)(b.fb_tw * b.fb_th);
@@ -74,7 +97,7 @@ cudaError_t launch_init(const BatchView &b, cudaStream_t s) {
     const int cap = sm_count() * 8;
     if (grid > cap) grid = cap;
     if (grid < 1) grid = 1;
-    return launch_pdl(k_init, (unsigned)grid, 256, 0, s, b);
+    return launch_pdl(k_init, (unsigned)grid, 256, 0, s, InitArgs(b));
 }
 
 // ------------------------------------------------------------------------------------------------ scan
@@ -85,14 +108,19 @@ constexpr unsigned long long VALUE_MASK = ~FLAG_MASK;
 // WHICH 0: per dense tile, fills (tile_word & 0xffffff -> fill_cursor) and, in the same pass, tiles that have fills
 //          (-> alpha_rank: the tile's mask slot is first_alpha + rank, so propagate needs no allocation atomics).
 //          The scanned value packs both: fills in bits 0-31, tiles in bits 32-55.
-// WHICH 1: list entries per framebuffer tile (fb[t].count -> fb[t].begin).
+// WHICH 1: list entries per framebuffer tile (fb[t].count -> fb[t].begin). With ordered tile groups (BatchView::fb_sorted)
+//          the same pass counts the EXPENSIVE groups (bits 32-55 of the scanned value; a group's flag rides on its first
+//          tile): expensive group g goes to position (expensive groups before g), in grid order from the front, a cheap
+//          one to (groups - 1 - cheap groups before g), from the back -- a stable two-way partition that needs no total.
+//          The headers are written where the tile kernel's CTAs will look for them (fb_sorted).
 template <int WHICH>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanArgs b) {
     const uint32_t n = WHICH == 0 ? b.tile_count : (uint32_t)(b.fb_tw * b.fb_th);
     unsigned long long *desc = b.scan_desc[WHICH];
     __shared__ uint32_t s_tile;
     __shared__ unsigned long long s_warp[SCAN_THREADS / 32], s_prefix;
-    pdl_wait();
+    PFCU_KERNEL_BEGIN(b, WHICH ? PFCU_STAGE_SCAN_FB : PFCU_STAGE_SCAN_TILES);
+    const bool ordered = WHICH == 1 && b.fb_sorted != nullptr;
     if (threadIdx.x == 0) s_tile = atomicAdd(&b.counters->scan_ticket[WHICH], 1u);  // forward progress: tiles start in order
     __syncthreads();
     const uint32_t tile = s_tile;
@@ -100,6 +128,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
     unsigned long long v[SCAN_ITEMS];
     unsigned long long sum = 0;
     uint32_t raw[SCAN_ITEMS];
+    int32_t zs[WHICH == 1 ? SCAN_ITEMS : 1];
     if (WHICH == 0 && base + SCAN_ITEMS <= n) {  // 2 x 16-byte loads (SCAN_ITEMS == 8, base is a multiple of 8)
         const uint4 r0 = *reinterpret_cast<const uint4 *>(&b.tile_word[base]);
         const uint4 r1 = *reinterpret_cast<const uint4 *>(&b.tile_word[base + 4]);
@@ -110,7 +139,23 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
         for (int k = 0; k < SCAN_ITEMS; k++) {
             raw[k] = 0;
             if (base + k < n) raw[k] = WHICH == 0 ? b.tile_word[base + k] : b.fb[base + k].count;
+            if (WHICH == 1) zs[k] = (ordered && base + k < n) ? b.fb[base + k].z : 0;
         }
+    }
+    // (a thread's SCAN_ITEMS tiles are in one group: its first or its second half)
+    static_assert(GROUP_TILES == 2 * SCAN_ITEMS, "a thread scans half a group of tiles");
+    bool expensive = false;
+    if (WHICH == 1 && ordered) {
+        // propagate counted the masked entries of a tile in the high bits of its count: the group's cost is their sum over
+        // its two halves (this thread's and its neighbour's)
+        uint32_t masked = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; k++) {
+            masked += raw[k] >> FB_COUNT_BITS;
+            raw[k] &= (1u << FB_COUNT_BITS) - 1u;
+        }
+        masked += __shfl_xor_sync(0xffffffffu, masked, 1);
+        expensive = masked >= b.group_cost_min;
     }
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; k++) {
@@ -118,6 +163,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
         if (WHICH == 0) {
             x &= 0x00ffffffull;
             if (x) x |= 1ull << 32;
+        } else if (k == 0 && expensive && base % GROUP_TILES == 0) {
+            x |= 1ull << 32;
         }
         v[k] = sum;  // exclusive within the thread
         sum += x;
@@ -171,6 +218,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
     }
     __syncthreads();
     const unsigned long long off = s_prefix + warp_off + (incl - sum);
+    uint32_t sorted_base = 0;
+    if (WHICH == 1 && ordered && base < n) {
+        const uint32_t g = base / GROUP_TILES, n_groups = (n + GROUP_TILES - 1) / GROUP_TILES;
+        // expensive groups before g (the second half's prefix already holds the group's own flag)
+        const uint32_t before = (uint32_t)(off >> 32) - ((base % GROUP_TILES) && expensive ? 1u : 0u);
+        const uint32_t slot = expensive ? before : n_groups - 1 - (g - before);
+        sorted_base = slot * GROUP_TILES + base % GROUP_TILES;
+        if (base % GROUP_TILES == 0) {
+            b.slot_of[g] = slot;
+            b.group_of[slot] = g;
+        }
+    }
     if (WHICH == 0 && base + SCAN_ITEMS <= n) {
         uint32_t f[SCAN_ITEMS], a[SCAN_ITEMS];
 #pragma unroll
@@ -194,6 +253,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
                     b.fill_begin[base + k] = (uint32_t)o;
                     b.fill_cursor[base + k] = (uint32_t)o;
                     b.alpha_rank[base + k] = (uint32_t)(o >> 32);
+                } else if (ordered) {
+                    // the whole header, where the CTA that renders this tile's group will look for it (cursor = 0)
+                    *reinterpret_cast<uint4 *>(&b.fb_sorted[sorted_base + k]) = make_uint4((uint32_t)o, raw[k], (uint32_t)zs[k], 0u);
                 } else {
                     b.fb[base + k].begin = (uint32_t)o;
                 }
@@ -224,19 +286,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(BatchView b) {
 
 cudaError_t launch_scan_tiles(const BatchView &b, cudaStream_t s) {
     if (!b.tile_count) return cudaSuccess;
-    return launch_pdl(k_scan<0>, scan_tiles_for(b.tile_count), SCAN_THREADS, 0, s, b);
+    return launch_pdl(k_scan<0>, scan_tiles_for(b.tile_count), SCAN_THREADS, 0, s, ScanArgs(b));
 }
 
 cudaError_t launch_scan_fb(const BatchView &b, cudaStream_t s) {
     const uint32_t fbt = (uint32_t)(b.fb_tw * b.fb_th);
     if (!fbt) return cudaSuccess;
-    return launch_pdl(k_scan<1>, scan_tiles_for(fbt), SCAN_THREADS, 0, s, b);
+    return launch_pdl(k_scan<1>, scan_tiles_for(fbt), SCAN_THREADS, 0, s, ScanArgs(b));
 }
 
 // ------------------------------------------------------------------------------------------------ fill scatter
 
-__global__ void __launch_bounds__(256) k_fill_scatter(BatchView b) {
-    pdl_wait();
+__global__ void __launch_bounds__(256) k_fill_scatter(FillScatterArgs b) {
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_FILL_SCATTER);
     const uint32_t n = min(b.counters->n_staging, b.staging_capacity);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const uint4 f = *reinterpret_cast<const uint4 *>(&b.staging[i]);
@@ -248,7 +310,7 @@ __global__ void __launch_bounds__(256) k_fill_scatter(BatchView b) {
 
 cudaError_t launch_fill_scatter(const BatchView &b, cudaStream_t s) {
     if (!b.segment_count || !b.tile_count) return cudaSuccess;
-    return launch_pdl(k_fill_scatter, sm_count() * 8, 256, 0, s, b);
+    return launch_pdl(k_fill_scatter, sm_count() * 8, 256, 0, s, FillScatterArgs(b));
 }
 
 // ------------------------------------------------------------------------------------------------ propagate
@@ -262,7 +324,8 @@ struct ColumnInfo {
     bool has_clip, clip_ok;
 };
 
-__device__ __forceinline__ bool load_column(const BatchView &b, uint32_t col, ColumnInfo &ci) {
+template <class B>
+__device__ __forceinline__ bool load_column(const B &b, uint32_t col, ColumnInfo &ci) {
     ci.path = __ldg(&b.backdrops[col].path_index);
     ci.tx = __ldg(&b.backdrops[col].tile_x_offset);
     const int4 rect = __ldg(reinterpret_cast<const int4 *>(&b.meta[ci.path].tile_rect[0]));
@@ -288,7 +351,8 @@ __device__ __forceinline__ bool load_column(const BatchView &b, uint32_t col, Co
 
 // One tile of a column (propagate.comp:118-213, tiler.cpp:391-437): `cur` is the column's backdrop BEFORE this tile's
 // delta. No atomic returns a value: mask slots come from the scan, list positions are taken later by the list scatter.
-__device__ __forceinline__ void resolve_tile(const BatchView &b, const ColumnInfo &ci, uint32_t first_alpha, int ty, int cur,
+template <class B>
+__device__ __forceinline__ void resolve_tile(const B &b, const ColumnInfo &ci, uint32_t first_alpha, int ty, int cur,
                                              uint32_t word) {
     const uint32_t ti = ci.tile_offset + (uint32_t)ci.tx + (uint32_t)ci.w * (uint32_t)ty;
     const int delta = (int)(int8_t)(word >> 24);
@@ -360,7 +424,9 @@ __device__ __forceinline__ void resolve_tile(const BatchView &b, const ColumnInf
     if (backdrop != 0 && even_odd && (abs(backdrop) & 1) == 0) z_write = false;
     if (in_fb && z_write && backdrop != 0 && alpha < 0) atomicMax(&b.fb[map].z, (int)ti);
     // list membership (propagate.comp:209-212): count now, place after the scan (fire-and-forget reduction)
-    if (listed) atomicAdd(&b.fb[map].count, 1u);
+    // (ordered tile groups: a masked entry also counts in the high bits -- the scan over framebuffer tiles adds them up per
+    // group of tiles and splits the two numbers again)
+    if (listed) atomicAdd(&b.fb[map].count, 1u + ((b.fb_sorted && alpha >= 0) ? 1u << FB_COUNT_BITS : 0u));
 }
 
 #ifndef PROPAGATE_SHORT_N
@@ -376,8 +442,8 @@ constexpr int PROPAGATE_SHORT = PROPAGATE_SHORT_N;  // columns of up to this man
 //     first warp, ONE LANE per column, serially, as the reference does -- neighbouring lanes are neighbouring columns of
 //     the same path, so every row is one coalesced access and no lane idles below a 3-tile column. The other warps of
 //     the group find their column short and leave.
-__global__ void __launch_bounds__(128) k_propagate(BatchView b) {
-    pdl_wait();
+__global__ void __launch_bounds__(128) k_propagate(PropagateArgs b) {
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_PROPAGATE);
     // this warp's column (dealing consecutive columns to consecutive CTAs instead was measured: no change, 16.4 us)
     const uint32_t wcol = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const unsigned lane = threadIdx.x & 31;
@@ -425,7 +491,7 @@ __global__ void __launch_bounds__(128) k_propagate(BatchView b) {
 cudaError_t launch_propagate(const BatchView &b, cudaStream_t s) {
     if (!b.column_count) return cudaSuccess;
     const uint32_t warps_per_block = 4;
-    return launch_pdl(k_propagate, (b.column_count + warps_per_block - 1) / warps_per_block, 128, 0, s, b);
+    return launch_pdl(k_propagate, (b.column_count + warps_per_block - 1) / warps_per_block, 128, 0, s, PropagateArgs(b));
 }
 
 // ------------------------------------------------------------------------------------------------ list scatter
@@ -434,8 +500,8 @@ cudaError_t launch_propagate(const BatchView &b, cudaStream_t s) {
 // (sort.comp:62: tiles below the top-most occluder of their framebuffer tile) takes the next free position of its
 // framebuffer tile's range and writes what the composite kernel needs about it as one 16-byte record. Culled tiles
 // leave their slot unused: fb[].cursor ends up as the list length, fb[].count stays the slot count.
-__global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
-    pdl_wait();
+__global__ void __launch_bounds__(256) k_list_scatter(ListArgs b) {
+    PFCU_KERNEL_BEGIN(b, PFCU_STAGE_LIST_SCATTER);
     const unsigned lane = threadIdx.x & 31;
     uint32_t placed = 0, longest = 0;
     for (uint32_t ti0 = blockIdx.x * blockDim.x; ti0 < b.tile_count; ti0 += gridDim.x * blockDim.x) {
@@ -449,10 +515,11 @@ __global__ void __launch_bounds__(256) k_list_scatter(BatchView b) {
         const uint32_t w = (uint32_t)(rect.z - rect.x);
         const int fx = rect.x + (int)(local % w) - b.fb_tx0, fy = rect.y + (int)(local / w) - b.fb_ty0;
         const uint32_t map = (uint32_t)fy * (uint32_t)b.fb_tw + (uint32_t)fx;
-        const uint4 hdr = *reinterpret_cast<const uint4 *>(&b.fb[map]);  // begin and z are final; cursor is moving
+        FbTile *const fbh = fb_header(b, map);
+        const uint4 hdr = *reinterpret_cast<const uint4 *>(fbh);  // begin and z are final; cursor is moving
         if ((int)ti < (int)hdr.z) continue;
         const uint32_t pi = __ldg(reinterpret_cast<const uint32_t *>(&b.tpi[path]) + 3);  // color, ctrl, backdrop
-        const uint32_t at = atomicAdd(&b.fb[map].cursor, 1u);
+        const uint32_t at = atomicAdd(&fbh->cursor, 1u);
         const uint32_t pos = hdr.x + at;
         placed++;
         longest = max(longest, at + 1u);
@@ -493,7 +560,7 @@ cudaError_t launch_list_scatter(const BatchView &b, cudaStream_t s) {
     int grid = (int)((b.tile_count + 255) / 256);
     const int cap = sm_count() * 8;
     if (grid > cap) grid = cap;
-    return launch_pdl(k_list_scatter, (unsigned)grid, 256, 0, s, b);
+    return launch_pdl(k_list_scatter, (unsigned)grid, 256, 0, s, ListArgs(b));
 }
 
 }  // namespace pfcu

@@ -25,12 +25,15 @@ EXPORTS = [
     "pfcu_read_target", "pfcu_read_page", "pfcu_target_device_ptr", "pfcu_read_lines", "pfcu_read_fills",
     "pfcu_read_tiles", "pfcu_read_z", "pfcu_read_tile_lists", "pfcu_read_mask", "pfcu_set_profiling",
     "pfcu_get_stage_times", "pfcu_set_option", "pfcu_graph_capture", "pfcu_graph_launch", "pfcu_graph_finish",
+    "pfcu_set_timeline", "pfcu_read_timeline",
 ]
 STAGES = ["init", "dice", "bin", "scan_tiles", "fill_scatter", "propagate", "scan_fb", "list_scatter", "fill",
           "composite"]
 
 LINE_DT = np.dtype([("from_x", "<f4"), ("from_y", "<f4"), ("to_x", "<f4"), ("to_y", "<f4"), ("path_index", "<u4")])
 FILL_DT = np.dtype([("tile_index", "<u4"), ("from_x", "<u2"), ("from_y", "<u2"), ("to_x", "<u2"), ("to_y", "<u2")])
+TIMELINE_DT = np.dtype([("stage", "<u4"), ("sm", "<u4"), ("cta", "<u4"), ("n_ctas", "<u4"), ("t_placed_ns", "<u8"),
+                        ("t_start_ns", "<u8"), ("t_end_ns", "<u8")])
 TILE_DT = np.dtype([("alpha_tile_id", "<i4"), ("clip_alpha_tile_id", "<i4"), ("fill_count", "<i4"),
                     ("backdrop", "i1"), ("backdrop_delta", "i1"), ("backdrop_d3d9", "i1"), ("listed", "u1")])
 
@@ -116,6 +119,10 @@ def lib():
         L.pfcu_set_option.argtypes = [vp, i32, i32]
         L.pfcu_set_profiling.argtypes = [vp, i32]
         L.pfcu_get_stage_times.argtypes = [vp, vp, i32]
+        if hasattr(L, "pfcu_set_timeline"):  # (PFCU_LIB may name an older build in an A/B run)
+            L.pfcu_set_timeline.argtypes = [vp, C.c_uint32]
+            L.pfcu_read_timeline.argtypes = [vp, vp, C.c_int64]
+            L.pfcu_read_timeline.restype = C.c_int64
         L.pfcu_graph_capture.argtypes = [vp]
         L.pfcu_graph_launch.argtypes = [vp]
         L.pfcu_graph_finish.argtypes = [vp, C.POINTER(FrameStats)]
@@ -297,6 +304,15 @@ class Renderer:
         """PFCU_OPT_RETAIN_FRAME_GRAPH (default on): identical consecutive frames become one graph launch."""
         _check(self.L.pfcu_set_option(self.h, 0, int(bool(enabled))))
 
+    def set_fused_fill(self, enabled):
+        """PFCU_OPT_FUSED_FILL (default off): the tile kernel rasterizes a draw batch's masks itself (no separate fill)."""
+        _check(self.L.pfcu_set_option(self.h, 3, int(bool(enabled))))
+
+    def set_order_tile_groups(self, enabled):
+        """PFCU_OPT_ORDER_TILE_GROUPS (default 4): the tile kernel starts with the groups of 16 tiles that have at least
+        this many masked tiles; 0 / False = grid order."""
+        _check(self.L.pfcu_set_option(self.h, 4, 4 if enabled is True else int(enabled)))
+
     def set_fill_culled_tiles(self, enabled):
         """PFCU_OPT_FILL_CULLED_TILES (default off): rasterize the masks of z-culled tiles too, like fill.comp."""
         _check(self.L.pfcu_set_option(self.h, 1, int(bool(enabled))))
@@ -308,6 +324,19 @@ class Renderer:
         ms = np.zeros(len(STAGES), "<f4")
         _check(self.L.pfcu_get_stage_times(self.h, _p(ms), len(STAGES)))
         return dict(zip(STAGES, (float(x) for x in ms)))
+
+    def set_timeline(self, capacity):
+        """pfcu_set_timeline: record (stage, SM, placed / started / ended in %globaltimer ns) for every CTA; 0 = off."""
+        _check(self.L.pfcu_set_timeline(self.h, int(capacity)))
+        self._timeline_cap = int(capacity)
+
+    def read_timeline(self):
+        """The records since the last call (TIMELINE_DT); waits for the context first."""
+        out = np.zeros(self._timeline_cap, TIMELINE_DT)
+        n = self.L.pfcu_read_timeline(self.h, _p(out), len(out))
+        if n < 0:
+            raise PfcuError(self.L.pfcu_last_error().decode())
+        return out[: min(n, len(out))]
 
     def graph_capture(self):
         _check(self.L.pfcu_graph_capture(self.h))

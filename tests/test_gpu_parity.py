@@ -138,6 +138,105 @@ def test_masks_match_oracle(renderer, area_lut):
     fr.close()
 
 
+@pytest.mark.parametrize("name", GOLDEN + ["tiger_4096_scene"])
+def test_fused_fill_is_byte_identical_to_separate_fill(renderer, name):
+    """PFCU_OPT_FUSED_FILL: the tile kernel rasterizing its own masks in shared memory and the separate fill kernel (the
+    default) writing them to device memory run the same mask arithmetic -- the frames must be equal byte for byte, on every
+    fixture (clip masks, even-odd, render-target passes, LOAD frames included)."""
+    scene, _ = scenes.load_scene(scenes.golden_path(name))
+    frames = []
+    try:
+        for fused in (True, False):
+            renderer.set_fused_fill(fused)
+            renderer.set_scene(scene)
+            renderer.draw(clear=True)
+            st = renderer.draw(clear=True)
+            frames.append(renderer.pixels().copy())
+            # the separate mode launches one fill kernel more per draw batch
+            frames.append(st["kernel_launches"])
+    finally:
+        renderer.set_fused_fill(False)
+    assert frames[1] < frames[3], (frames[1], frames[3])
+    assert np.array_equal(frames[0], frames[2]), "%d bytes differ" % int((frames[0] != frames[2]).sum())
+
+
+@pytest.mark.parametrize("name", ["tiger_512", "features_2048", "demo_full_512", "paints_512", "tiger_4096_scene"])
+def test_ordered_tile_groups_change_nothing_but_the_order(renderer, name):
+    """PFCU_OPT_ORDER_TILE_GROUPS (default on): the tile kernel's CTAs take the groups of 16 tiles by descending cost and find
+    their list headers in that order. Pixels, z-buffer and the z-culled lists must be what the grid-order frame gives."""
+    scene, _ = scenes.load_scene(scenes.golden_path(name))
+    got = []
+    try:
+        for ordered in (True, False):
+            renderer.set_order_tile_groups(ordered)
+            renderer.set_scene(scene)
+            renderer.draw(clear=True)
+            st = renderer.draw(clear=True)
+            taps = []
+            for b in scene["draw_batches"]:
+                bid = int(b["info"][0])
+                taps.append((renderer.z(bid), renderer.tile_lists(bid)))
+            got.append((renderer.pixels().copy(), taps, st["kernel_launches"]))
+    finally:
+        renderer.set_order_tile_groups(True)
+    assert np.array_equal(got[0][0], got[1][0]), "%d bytes differ" % int((got[0][0] != got[1][0]).sum())
+    for (za, (oa, ta)), (zb, (ob, tb)) in zip(got[0][1], got[1][1]):
+        assert np.array_equal(za, zb) and np.array_equal(oa, ob) and np.array_equal(ta, tb)
+
+
+def test_device_timeline_of_the_trace_build(area_lut):
+    """pfcu_set_timeline (lib/libpfcu_trace.so, the build with -DPFCU_TIMELINE): one record per CTA of every kernel of the
+    frame, stamps in order, and the same pixels as the product library; the product library refuses the call."""
+    import os
+    import subprocess
+    import sys
+
+    import pfcu
+
+    r = pfcu.Renderer(0, area_lut)
+    with pytest.raises(pfcu.PfcuError):
+        r.set_timeline(1000)
+    scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+    r.set_scene(scene)
+    r.draw(clear=True)
+    want = r.pixels().copy()
+    r.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import sys, numpy as np
+sys.path[:0] = [%r, %r]
+import pfcu, scenes
+lut = np.load(%r)["lut"]
+r = pfcu.Renderer(0, lut)
+r.set_retain_frame_graph(False)
+r.set_timeline(100000)
+scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
+r.set_scene(scene)
+st = r.draw(clear=True)
+rec = r.read_timeline()
+assert len(rec) > 1000 and st["retries"] == 0, (len(rec), st)
+assert (rec["t_placed_ns"] <= rec["t_start_ns"]).all() and (rec["t_start_ns"] <= rec["t_end_ns"]).all()
+stages = set(int(x) & 0xff for x in rec["stage"])
+assert stages == set(range(10)), stages
+for s in stages:  # every CTA of every kernel reported exactly once
+    q = rec[(rec["stage"] & 0xff) == s]
+    for sub in set(int(x) for x in q["stage"]):
+        k = q[q["stage"] == sub]
+        assert len(k) == int(k["n_ctas"][0]) and len(set(int(c) for c in k["cta"])) == len(k), (sub, len(k))
+# the tile kernel starts after everything it depends on has ended
+comp = rec[rec["stage"] == 9]
+assert comp["t_start_ns"].min() >= rec[rec["stage"] == 8]["t_end_ns"].max()
+assert comp["t_start_ns"].min() >= rec[rec["stage"] == 7]["t_end_ns"].max()
+assert len(r.read_timeline()) == 0
+np.save(sys.argv[1], r.pixels())
+""" % (os.path.join(root, "pathfinder-cpp_b200"), os.path.join(root, "tests"), os.path.join(root, "tests", "golden", "area_lut.npz"))
+    out = os.path.join(root, "gpurun_out", "timeline_test_pixels.npy")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    env = dict(os.environ, PFCU_LIB=os.path.join(root, "pathfinder-cpp_b200", "lib", "libpfcu_trace.so"))
+    subprocess.run([sys.executable, "-c", code, out], check=True, env=env, timeout=300)
+    assert np.array_equal(np.load(out), want)
+
+
 def compare_with_oracle(renderer, area_lut, scene, what):
     """Geometry taps bit-exact + pixels within tolerance for a scene that has no reference fixture."""
     renderer.set_scene(scene)

@@ -17,12 +17,17 @@ frames = int(sys.argv[2]) if len(sys.argv) > 2 else 480
 scene = bench.load_workload(name)[0]
 lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
 main = torch.cuda.Stream()
-for n_ctx in (1, 2, 3, 4, 6, 8):
+for n_ctx in [int(x) for x in os.environ.get("CONTEXTS", "1,2,3,4,6,8").split(",")]:
     rs, streams = [], []
     for _ in range(n_ctx):
         q = pfcu.Renderer(0, lut)
         st = torch.cuda.Stream()
         q.set_stream(st.cuda_stream)
+        if "ORDER" in os.environ:
+            try:
+                q.set_order_tile_groups(int(os.environ["ORDER"]))
+            except pfcu.PfcuError:
+                pass  # (a library built before the option existed)
         q.set_scene(scene)
         q.draw(clear=True)
         q.draw(clear=True)

@@ -18,8 +18,13 @@ scene, _ = scenes.load_scene(scenes.golden_path(fixture))
 lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
 stream = torch.cuda.Stream()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for fused in (False,):
+for ordered in [int(x) for x in os.environ.get("ORDER", "4,0").split(",")]:
+    fused = False
     r = pfcu.Renderer(0, lut)
+    try:
+        r.set_order_tile_groups(ordered)
+    except pfcu.PfcuError:
+        pass  # (PFCU_LIB names a build from before the option)
     r.set_stream(stream.cuda_stream)
     r.set_scene(scene)
     r.draw(clear=True)
@@ -46,7 +51,7 @@ for fused in (False,):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e3)
     r.graph_finish()
-    print("%s %s graph %.1f us (min %.1f) | " % (os.environ.get("PFCU_LIB", "default").split("/")[-1], "fused" if fused else "split",
+    print("%s %s graph %.1f us (min %.1f) | " % (os.environ.get("PFCU_LIB", "default").split("/")[-1], "order>=%d" % ordered,
                                               float(np.median(ts[10:])), min(ts[10:])) +
           " ".join("%s %.1f" % (k, v) for k, v in med.items()))
     r.close()

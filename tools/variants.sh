@@ -14,9 +14,9 @@ while [ $# -ge 2 ]; do
     $NV $flags -c csrc/pfcu_api.cu -o build/pfcu_api_$name.o &
     $NV $flags -c csrc/pfcu_raster.cu -o build/pfcu_raster_$name.o &
     wait
-    /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o lib/libpfcu_$name.so build/pfcu_geom_$name.o build/pfcu_tiles_$name.o build/pfcu_api_$name.o build/pfcu_raster_$name.o
+    /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o lib/libpfcu_$name.so build/pfcu_geom_$name.o build/pfcu_stroke.o build/pfcu_tiles_$name.o build/pfcu_api_$name.o build/pfcu_raster_$name.o
   else
     $NV $flags -c csrc/pfcu_raster.cu -o build/pfcu_raster_$name.o
-    /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o lib/libpfcu_$name.so build/pfcu_geom.o build/pfcu_tiles.o build/pfcu_api.o build/pfcu_raster_$name.o
+    /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o lib/libpfcu_$name.so build/pfcu_geom.o build/pfcu_stroke.o build/pfcu_tiles.o build/pfcu_api.o build/pfcu_raster_$name.o
   fi
 done
