@@ -308,12 +308,13 @@ def run_ours(args, rank, world, local):
     # ---- per-kernel times (events around every kernel), for the roofline of the dominant kernel
     r.set_profiling(True)
     stage_samples = []
-    for _ in range(max(9, args.warmup)):
+    for _ in range(max(33, args.warmup)):
         flush_l2()
         r.draw(clear=True)
         stage_samples.append(r.stage_times())
     r.set_profiling(False)
-    stage_ms = {k: float(np.median([s[k] for s in stage_samples])) for k in stage_samples[0]}
+    # (CUDA event times come in steps of about 1 us: the mean of 30 frames, not the median, which flips between two steps)
+    stage_ms = {k: float(np.mean(sorted(s[k] for s in stage_samples[3:])[2:-2])) for k in stage_samples[0]}
 
     # ---- single-frame latency: whole frame as one CUDA graph, one at a time, L2 flushed before each
     r.draw(clear=True)

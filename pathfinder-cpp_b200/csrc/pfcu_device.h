@@ -392,18 +392,13 @@ struct CtaStamp {
     cta_stamp_.go()
 #endif
 
-// One shared-memory carve-out for every kernel of the frame. An SM cannot change its L1 / shared-memory split while CTAs
-// are resident, so a kernel whose preferred split differs from the resident kernel's waits for that SM to drain: the
-// timeline showed fill (4 x 40 KB) getting no CTA on the 32 SMs that held a CTA of the scan kernel (no shared memory to
-// speak of) until it had finished. PFCU_CARVEOUT_PCT < 0: leave the choice to the driver.
-#ifndef PFCU_CARVEOUT_PCT
-#define PFCU_CARVEOUT_PCT -1
-#endif
-void prefer_carveout(const void *kernel);  // once per kernel and device (pfcu_tiles.cu)
-
+// (One shared-memory carve-out for every kernel -- an SM cannot change its L1 / shared-memory split while CTAs are resident,
+// and the timeline shows fill getting no CTA on the 32 SMs that hold a CTA of the scan over framebuffer tiles until that
+// has finished -- was measured: cudaFuncAttributePreferredSharedMemoryCarveout = 72 % on all kernels, or only on fill and
+// the small kernels beside it, gains 0.6 - 0.8 us per frame in a stream of frames and loses 1.2 - 1.4 us on a frame
+// alone, the kernels that live on L1 hits paying for it; left to the driver. profiles/r02_tile_kernel.md section 10.)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, Args... args) {
-    if (PFCU_CARVEOUT_PCT >= 0) prefer_carveout(reinterpret_cast<const void *>(kernel));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(block, 1, 1);

@@ -20,10 +20,6 @@
 //                    Ordering and z-culling happen on chip in the composite kernel.
 #include <cuda_fp16.h>
 
-#include <mutex>
-#include <utility>
-#include <vector>
-
 #include "pfcu_device.h"
 
 namespace pfcu {
@@ -44,17 +40,6 @@ int sm_count() {
         counts[dev] = n > 0 ? n : 148;
     }
     return counts[dev];
-}
-
-void prefer_carveout(const void *kernel) {
-    static std::mutex mu;
-    static std::vector<std::pair<int, const void *>> done;
-    const std::pair<int, const void *> key(current_device(), kernel);
-    std::lock_guard<std::mutex> lock(mu);
-    for (const auto &k : done)
-        if (k == key) return;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, PFCU_CARVEOUT_PCT);
-    done.push_back(key);
 }
 
 bool timeline_compiled() {

@@ -198,10 +198,17 @@ class Renderer:
 
     # -- scene upload: RendererD3D11::upload_scene + Palette::build_paint_info's uploads
     def upload_segments(self, scene):
-        for which, name in ((0, "draw"), (1, "clip")):
-            pts = np.ascontiguousarray(scene[name + "_points"], "<f4")
-            idx = np.ascontiguousarray(scene[name + "_indices"], "<u4")
-            _check(self.L.pfcu_upload_scene(self.h, which, _p(pts), len(pts), _p(idx), len(idx)))
+        # (the arrays and their addresses are looked up once per scene object: this runs every frame in the e2e legs)
+        cached = getattr(self, "_seg_cache", None)
+        if cached is None or cached[0] is not scene:
+            args = []
+            for which, name in ((0, "draw"), (1, "clip")):
+                pts = np.ascontiguousarray(scene[name + "_points"], "<f4")
+                idx = np.ascontiguousarray(scene[name + "_indices"], "<u4")
+                args.append((which, _p(pts), len(pts), _p(idx), len(idx), pts, idx))
+            cached = self._seg_cache = (scene, args)
+        for which, pp, n_pts, ip, n_idx, _, _ in cached[1]:
+            _check(self.L.pfcu_upload_scene(self.h, which, pp, n_pts, ip, n_idx))
 
     def set_incremental_dice(self, enabled):
         """PFCU_OPT_INCREMENTAL_DICE (default off): later frames dice only the paths whose segments were updated."""
@@ -267,25 +274,32 @@ class Renderer:
         scene = self.scene
         if upload:
             self.upload_segments(scene)
-        L = self.L
-        _check(L.pfcu_begin_frame(self.h))
-        for d, b in reversed(list(zip(self._descs["clip"], scene["clip_batches"]))):
-            if d.path_count > 0:
-                _check(L.pfcu_prepare_batch(self.h, C.byref(d)))
+        L, h = self.L, self.h
+        _check(L.pfcu_begin_frame(h))
+        plan = getattr(self, "_draw_plan", None)
+        if plan is None or plan[0] is not self._descs:  # per scene: the calls of a frame, arguments resolved
+            clips = [C.byref(d) for d in reversed(self._descs["clip"]) if d.path_count > 0]
+            draws = []
+            for d, b in zip(self._descs["draw"], scene["draw_batches"]):
+                info = b["info"]
+                color_page = -1 if int(info[7]) == NONE else int(info[7])
+                flags = 0 if int(info[8]) == NONE else int(info[8])
+                target = -1 if int(info[10]) == NONE else int(info[11])
+                draws.append((C.byref(d), d.batch_id, target, color_page, flags))
+            plan = self._draw_plan = (self._descs, clips, draws, np.zeros(4, "<f4"))
+        _, clips, draws, zero = plan
+        for ref in clips:
+            _check(L.pfcu_prepare_batch(h, ref))
         cc = np.array(clear_color, "<f4")
-        zero = np.zeros(4, "<f4")
+        cc_p, zero_p = _p(cc), _p(zero)
         first = bool(clear)
-        for d, b in zip(self._descs["draw"], scene["draw_batches"]):
-            _check(L.pfcu_prepare_batch(self.h, C.byref(d)))
-            info = b["info"]
-            color_page = -1 if int(info[7]) == NONE else int(info[7])
-            flags = 0 if int(info[8]) == NONE else int(info[8])
-            if int(info[10]) == NONE:
-                for _ in range(int(os.environ.get("PFCU_EXP_DRAWS", "1"))):  # kernel experiments: the tile pass repeated
-                    _check(L.pfcu_draw_batch(self.h, d.batch_id, -1, color_page, flags, int(first), _p(cc)))
+        for ref, batch_id, target, color_page, flags in draws:
+            _check(L.pfcu_prepare_batch(h, ref))
+            if target < 0:
+                _check(L.pfcu_draw_batch(h, batch_id, -1, color_page, flags, int(first), cc_p))
                 first = False
             else:
-                _check(L.pfcu_draw_batch(self.h, d.batch_id, int(info[11]), color_page, flags, 1, _p(zero)))
+                _check(L.pfcu_draw_batch(h, batch_id, target, color_page, flags, 1, zero_p))
         if not wait:
             _check(L.pfcu_submit_frame(self.h))
             return None

@@ -11,6 +11,7 @@ timeout 900 python bench.py > $out/bench.json 2> $out/bench.err; cut -c1-400 $ou
 timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $out/bench_reference.json 2>&1
 timeout 300 python tools/stage_times.py > $out/stage_times.txt 2>&1; cat $out/stage_times.txt
 timeout 300 python tools/gpu_throughput.py tiger4096 > $out/gpu_throughput.txt 2>&1; cat $out/gpu_throughput.txt
+timeout 300 python tools/timeline.py > $out/timeline.txt 2>&1; head -16 $out/timeline.txt
 timeout 300 python bench.py --workload features2048 --no-cpu-baseline --no-sharded --steps 20 > $out/bench_features2048.json 2> $out/bench_features.err; cut -c1-200 $out/bench_features2048.json
 timeout 300 python bench.py --workload demo2048 --no-cpu-baseline --no-sharded --steps 4 --frames-per-step 64 > $out/bench_demo2048.json 2> $out/bench_demo.err; cut -c1-200 $out/bench_demo2048.json
 timeout 300 python tools/stroke_time.py > $out/stroke_time.txt 2>&1; cat $out/stroke_time.txt

@@ -9,5 +9,10 @@ for tool in memcheck racecheck synccheck; do
     echo "== compute-sanitizer --tool $tool  prof_frame.py --fixture $fx --frames 2" >> $out/sanitizer.txt
     timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/prof_frame.py --fixture $fx --frames 2 2>&1 | grep -v "^[0-9] {" | tail -8 >> $out/sanitizer.txt
   done
+  # the fill stage inside the tile kernel (PFCU_OPT_FUSED_FILL): shared-memory accumulators, masks and work queues
+  for fx in tiger_512 demo_full_512; do
+    echo "== compute-sanitizer --tool $tool  prof_frame.py --fixture $fx --frames 2 --fused" >> $out/sanitizer.txt
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/prof_frame.py --fixture $fx --frames 2 --fused 2>&1 | grep -v "^[0-9] {" | tail -8 >> $out/sanitizer.txt
+  done
 done
 cat $out/sanitizer.txt

@@ -16,11 +16,16 @@ import scenes  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--fixture", default="tiger_4096_scene")
 ap.add_argument("--frames", type=int, default=4)
-ap.add_argument("--split", action="store_true", help="(ignored: fill and tile are always separate kernels)")
+ap.add_argument("--fused", action="store_true", help="PFCU_OPT_FUSED_FILL = 1: the tile kernel rasterizes the masks itself")
+ap.add_argument("--grid-order", action="store_true", help="PFCU_OPT_ORDER_TILE_GROUPS = 0")
 args = ap.parse_args()
 scene, _ = scenes.load_scene(scenes.golden_path(args.fixture))
 lut = np.load(os.path.join(ROOT, "tests", "golden", "area_lut.npz"))["lut"]
 r = pfcu.Renderer(0, lut)
+if args.fused:
+    r.set_fused_fill(True)
+if args.grid_order:
+    r.set_order_tile_groups(0)
 r.set_scene(scene)
 for i in range(args.frames):
     st = r.draw(clear=True)
