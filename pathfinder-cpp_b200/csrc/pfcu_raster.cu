@@ -348,7 +348,14 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, FILL_CTAS_PER_SM) k_fill(Fill
 
     // (Handing the groups out through a global ticket counter instead -- one atomic per group, next ticket prefetched --
     // measured slower: 28.7 us against 24.6 us on tiger 4096^2, profiles/r01_tile_kernel_experiments.md.)
-    for (uint32_t a0 = warp * FILL_GROUP; a0 < n_alpha; a0 += n_warps * FILL_GROUP) {
+    // Round 2 tried again to hand out the groups beyond every warp's first dynamically, because CTAs do not all start
+    // together (tools/timeline.py: the 32 SMs that hold a CTA of the scan over framebuffer tiles get their fill CTAs 6 us late
+    // -- an SM keeps its shared-memory carve-out while CTAs are resident -- and those 128 CTAs are the kernel's tail): per
+    // warp and one group ahead 32.8 us, per warp on demand 27.6 us, one atomic per CTA for its 8 warps' second groups 26.6 us,
+    // against 24.6 us for the fixed assignment below (profiles/r02_tile_kernel.md section 12).
+    const uint32_t n_groups = (n_alpha + FILL_GROUP - 1) / FILL_GROUP;
+    for (uint32_t grp = warp; grp < n_groups; grp += n_warps) {
+        const uint32_t a0 = grp * FILL_GROUP;
         // ---- the group's alpha tile records, one per lane: tile | winding << 31, clip mask slot, first fill,
         // backdrop | fill count << 8
         uint4 at = make_uint4(0x7fffffffu, 0xffffffffu, 0u, 0u);
