@@ -353,6 +353,9 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, FILL_CTAS_PER_SM) k_fill(Fill
     // -- an SM keeps its shared-memory carve-out while CTAs are resident -- and those 128 CTAs are the kernel's tail): per
     // warp and one group ahead 32.8 us, per warp on demand 27.6 us, one atomic per CTA for its 8 warps' second groups 26.6 us,
     // against 24.6 us for the fixed assignment below (profiles/r02_tile_kernel.md section 12).
+    // Also measured there: the next group's records fetched by cp.async during the current group + L1 prefetches of its z-buffer
+    // entries and fills (no change: 24.6 us, and 690 us on the 200 k-path scene -- the loads are not what a round waits for);
+    // a grid that leaves out the SMs the scan over framebuffer tiles holds (464 CTAs: some warps take three groups, 30.7 us).
     const uint32_t n_groups = (n_alpha + FILL_GROUP - 1) / FILL_GROUP;
     for (uint32_t grp = warp; grp < n_groups; grp += n_warps) {
         const uint32_t a0 = grp * FILL_GROUP;
