@@ -56,8 +56,71 @@ class FrameStats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_ if n != "reserved"}
 
 
+class HostDraw(C.Structure):
+    _fields_ = [("batch_id", C.c_uint32), ("target_page", C.c_int32), ("color_page", C.c_int32), ("sampling_flags", C.c_uint32)]
+
+
+class HostScene(C.Structure):  # pfhost_scene, host/frame_streamer.h
+    _fields_ = [("points", C.c_void_p * 2), ("indices", C.c_void_p * 2), ("n_points", C.c_uint32 * 2),
+                ("n_segments", C.c_uint32 * 2), ("clip_batches", C.c_void_p), ("n_clip_batches", C.c_uint32),
+                ("draw_batches", C.c_void_p), ("draws", C.c_void_p), ("n_draw_batches", C.c_uint32),
+                ("clear_color", C.c_float * 4)]
+
+
 class PfcuError(RuntimeError):
     pass
+
+
+_host = None
+
+
+def host_lib():
+    """lib/libpfhost.so: the application-side C++ loop over the C-ABI (host/frame_streamer.h)."""
+    global _host
+    if _host is None:
+        lib()  # first: its symbols must be global
+        H = C.CDLL(os.path.join(_HERE, "lib", "libpfhost.so"))
+        H.pfhost_stream_frames.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_double),
+                                           C.POINTER(FrameStats), C.POINTER(C.c_uint32)]
+        _host = H
+    return _host
+
+
+def stream_frames(renderers, n_frames, clear_color=(0.0, 0.0, 0.0, 0.0), pixels=None):
+    """pfhost_stream_frames: n_frames frames of the renderers' (common) scene, frame i on renderers[i % n], every frame with
+    its uploads, its counters read back and -- pixels: one page-locked array per renderer -- its target read back.
+    Returns (wall seconds, statistics of the last frame, retries over all frames)."""
+    r0 = renderers[0]
+    scene = r0.scene
+    keep = []
+    hs = HostScene()
+    for which, name in ((0, "draw"), (1, "clip")):
+        pts = np.ascontiguousarray(scene[name + "_points"], "<f4")
+        idx = np.ascontiguousarray(scene[name + "_indices"], "<u4")
+        keep += [pts, idx]
+        hs.points[which], hs.indices[which] = pts.ctypes.data, idx.ctypes.data
+        hs.n_points[which], hs.n_segments[which] = len(pts), len(idx)
+    clips = (BatchDesc * max(1, len(r0._descs["clip"])))(*r0._descs["clip"])
+    draws_d = (BatchDesc * max(1, len(r0._descs["draw"])))(*r0._descs["draw"])
+    draws = (HostDraw * max(1, len(r0._descs["draw"])))()
+    for i, (d, b) in enumerate(zip(r0._descs["draw"], scene["draw_batches"])):
+        info = b["info"]
+        draws[i].batch_id = d.batch_id
+        draws[i].target_page = -1 if int(info[10]) == NONE else int(info[11])
+        draws[i].color_page = -1 if int(info[7]) == NONE else int(info[7])
+        draws[i].sampling_flags = 0 if int(info[8]) == NONE else int(info[8])
+    hs.clip_batches, hs.n_clip_batches = C.addressof(clips), len(r0._descs["clip"])
+    hs.draw_batches, hs.draws, hs.n_draw_batches = C.addressof(draws_d), C.addressof(draws), len(r0._descs["draw"])
+    for i in range(4):
+        hs.clear_color[i] = float(clear_color[i])
+    ctxs = (C.c_void_p * len(renderers))(*[q.h for q in renderers])
+    px = None
+    if pixels is not None:
+        px = (C.c_void_p * len(renderers))(*[p.ctypes.data for p in pixels])
+    wall, st, retries = C.c_double(), FrameStats(), C.c_uint32()
+    _check(host_lib().pfhost_stream_frames(ctxs, len(renderers), C.byref(hs), int(n_frames), px, C.byref(wall), C.byref(st),
+                                           C.byref(retries)))
+    return wall.value, st.as_dict(), retries.value
 
 
 _lib = None
@@ -70,7 +133,7 @@ def lib():
         if not os.path.exists(LIB_PATH):
             raise PfcuError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                             "(make -C pathfinder-cpp_b200)" % LIB_PATH)
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)  # (lib/libpfhost.so resolves its pfcu_* references against it)
         vp, u32, i32, sz = C.c_void_p, C.c_uint32, C.c_int, C.c_size_t
         L.pfcu_last_error.restype = C.c_char_p
         L.pfcu_create.argtypes = [i32, C.POINTER(vp)]

@@ -25,6 +25,22 @@ def test_library_exports_every_declared_symbol():
     assert lib.pfcu_abi_version() == 1
 
 
+def test_host_streamer_library_loads_and_only_depends_on_the_c_abi():
+    """lib/libpfhost.so (host/frame_streamer.cpp, the application-side C++ submit loop): loads next to libpfcu.so, exports
+    what its header declares, and every symbol it leaves undefined is one include/pfcu.h declares."""
+    import subprocess
+
+    import pfcu
+
+    assert hasattr(pfcu.host_lib(), "pfhost_stream_frames")
+    hdr = open(os.path.join(ROOT, "pathfinder-cpp_b200", "host", "frame_streamer.h")).read()
+    assert re.findall(r"\b(pfhost_[a-z_]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)) == ["pfhost_stream_frames"]
+    nm = subprocess.run(["nm", "-D", "--undefined-only", os.path.join(ROOT, "pathfinder-cpp_b200", "lib", "libpfhost.so")],
+                        capture_output=True, text=True, check=True).stdout
+    used = sorted(set(re.findall(r"\b(pfcu_[a-z0-9_]+)", nm)))
+    assert used and set(used) <= set(declared_symbols()), used
+
+
 def test_no_cpu_fallback_without_device():
     """Without a GPU the product path must fail loudly (PFCU_ERR_CUDA), never compute on the CPU."""
     import torch

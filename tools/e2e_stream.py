@@ -37,6 +37,8 @@ for n_ctx in (1, 2, 3, 4, 6, 8):
                 rs[k].wait()
         ms = (time.perf_counter() - t0) * 1e3 / steps
         best = ms if best is None else min(best, ms)
-    print("%s e2e, %d frame(s) in flight: %.1f us/frame" % (name, n_ctx, best * 1e3), flush=True)
+    cpp = min(pfcu.stream_frames(rs, steps)[0] for _ in range(3)) * 1e6 / steps
+    print("%s e2e, %d frame(s) in flight: %.1f us/frame (Python submit loop), %.1f us/frame (C++ loop, pfhost_stream_frames)" %
+          (name, n_ctx, best * 1e3, cpp), flush=True)
     for q in rs:
         q.close()

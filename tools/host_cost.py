@@ -42,6 +42,9 @@ for rep in range(3):
     t0 = time.perf_counter()
     loop(steps)
     print("tiger 512^2 e2e, %d in flight: %.1f us/frame wall" % (n_ctx, (time.perf_counter() - t0) * 1e6 / steps), flush=True)
+for rep in range(3):
+    wall = pfcu.stream_frames(rs, steps)[0]
+    print("the same through the C++ loop (pfhost_stream_frames): %.1f us/frame wall" % (wall * 1e6 / steps), flush=True)
 pr = cProfile.Profile()
 pr.enable()
 loop(1000)
