@@ -961,13 +961,19 @@ int pfcu_upload_paint_metadata(pfcu_ctx *c, const uint16_t *half_texels, uint32_
         p.base = texel(2);
         p.fp0 = texel(3);
         p.fp1 = texel(4);
+        p.fp2 = texel(5);
+        p.fp3 = texel(6);
+        p.fp4 = texel(7);
         p.ctrl = (int32_t)texel(8).x;  // int(extra.x), tile.comp:725
         if (p.ctrl != 0) all_solid = 0;
-        // tile.comp:184-227,394-404 also has a text (0x2) and a colour-matrix (0x4) filter; upstream never emits them
-        // (paint/palette.cpp:65-67) and they are not implemented here: refuse rather than sample the texture unfiltered
+        // filters: none, radial gradient (0x1), text (0x2), blur (0x3), colour matrix (0x4) -- tile.comp:407-456. Upstream
+        // emits neither text nor colour matrix (paint/palette.cpp:65-67) and binds a 1 x 1 dummy as the text filter's gamma
+        // LUT (d3d11/renderer.cpp:262-266): a paint that turns gamma correction on has no defined result and is refused
         const int filter = (p.ctrl >> 4) & 0xf;
-        if (((p.ctrl >> 8) & 0x3) != 0 && filter != 0x0 && filter != 0x1 && filter != 0x3)
-            return fail(PFCU_ERR_INVALID, "paint %u uses filter %d: only none / radial gradient / blur are implemented", i, filter);
+        if (((p.ctrl >> 8) & 0x3) != 0 && filter > 0x4)
+            return fail(PFCU_ERR_INVALID, "paint %u uses the unknown filter %d", i, filter);
+        if (((p.ctrl >> 8) & 0x3) != 0 && filter == 0x2 && p.fp2.w != 0.0f)
+            return fail(PFCU_ERR_INVALID, "paint %u: the text filter's gamma correction needs a gamma LUT the reference does not upload", i);
         for (float v : {p.base.x, p.base.y, p.base.z, p.base.w})
             if (!(v >= 0.0f && v <= 1.0f)) unit_range = 0;
         table[i] = p;

@@ -113,8 +113,9 @@ struct Paint {
     float4 fp0, fp1;
     int32_t ctrl;  // composite << 10 | combine << 8 | filter << 4
     int32_t pad[3];
+    float4 fp2, fp3, fp4;  // filter parameters 2 - 4: only the text and colour-matrix filters read them (from the table)
 };
-static_assert(sizeof(Paint) == 96, "Paint");
+static_assert(sizeof(Paint) == 144, "Paint");
 
 // Everything a kernel needs to know about one batch. Passed by value.
 struct BatchView {

@@ -444,6 +444,39 @@ __device__ float4 filter_blur(const ColorSampler &cs, float cu, float cv, float4
     return color;
 }
 
+// filterColorMatrix, tile.comp:394-404: mat4(p0 .. p3) * texel + p4 (the parameters are the matrix's COLUMNS)
+__device__ float4 filter_color_matrix(const ColorSampler &cs, float cu, float cv, const Paint *gp) {
+    const float4 s = cs(cu, cv);
+    const float4 c0 = __ldg(&gp->fp0), c1 = __ldg(&gp->fp1), c2 = __ldg(&gp->fp2), c3 = __ldg(&gp->fp3), o = __ldg(&gp->fp4);
+    return make_float4(c0.x * s.x + c1.x * s.y + c2.x * s.z + c3.x * s.w + o.x, c0.y * s.x + c1.y * s.y + c2.y * s.z + c3.y * s.w + o.y,
+                       c0.z * s.x + c1.z * s.y + c2.z * s.z + c3.z * s.w + o.z, c0.w * s.x + c1.w * s.y + c2.w * s.z + c3.w * s.w + o.w);
+}
+
+// filterText, tile.comp:136-227, without its gamma correction (the reference binds a 1 x 1 dummy as gamma LUT,
+// d3d11/renderer.cpp:262-266; paints that ask for it are refused at upload): coverage from the red channel, optionally
+// defringed by a 9-tap / 7-tap-per-channel horizontal kernel, then mix(background, foreground, coverage)
+__device__ float4 filter_text(const ColorSampler &cs, float cu, float cv, const Paint *gp) {
+    const float4 k = __ldg(&gp->fp0), bg = __ldg(&gp->fp1), fg = __ldg(&gp->fp2);
+    float ar, ag, ab;
+    if (k.w == 0.0f) {
+        ar = ag = ab = cs(cu, cv).x;
+    } else {
+        const float one = 1.0f / (float)cs.w;
+        const bool wide = k.x > 0.0f;
+        float t[9];  // taps -4 .. 4
+#pragma unroll
+        for (int i = 0; i < 9; i++) t[i] = ((i == 0 || i == 8) && !wide) ? 0.0f : cs(cu + (float)(i - 4) * one, cv).x;
+        // filterTextConvolve7Tap(alpha0, alpha1, kernel) = dot(alpha0, kernel) + dot(alpha1, kernel.zyx), centred on taps 3, 4, 5
+        auto conv = [&](int c) {
+            return (t[c - 3] * k.x + t[c - 2] * k.y + t[c - 1] * k.z + t[c] * k.w) + (t[c + 1] * k.z + t[c + 2] * k.y + t[c + 3] * k.x);
+        };
+        ar = conv(3);
+        ag = conv(4);
+        ab = conv(5);
+    }
+    return make_float4(mixf(bg.x, fg.x, ar), mixf(bg.y, fg.y, ag), mixf(bg.z, fg.z, ab), 1.0f);
+}
+
 // composite helpers, tile.comp:459-562
 __device__ __forceinline__ float comp_div(float n, float d) { return d != 0.0f ? n / d : 0.0f; }
 __device__ void rgb_to_hsl(const float rgb[3], float hsl[3]) {
@@ -516,7 +549,7 @@ __device__ void composite_rgb(const float d[3], const float s[3], int op, float 
 // (not inlined: one copy of the gradient / blur / blend-mode code per kernel instead of one per pixel and call site --
 // inlining it made the textured instantiation of the tile kernel 1 MB of SASS, an instruction-cache disaster)
 template <bool SOLID>
-__device__ __noinline__ float4 shade(const Paint &pc, const ColorSampler &cs, float fragx, float fragy,
+__device__ __noinline__ float4 shade(const Paint &pc, const Paint *gp, const ColorSampler &cs, float fragx, float fragy,
                                      float mask_alpha, float fb_w, float fb_h) {
     float4 color = pc.base;
     if (!SOLID) {
@@ -528,6 +561,8 @@ __device__ __noinline__ float4 shade(const Paint &pc, const ColorSampler &cs, fl
             float4 c0;
             if (filter == 0x1) c0 = filter_radial(cs, cu, cv, pc.fp0, pc.fp1);
             else if (filter == 0x3) c0 = filter_blur(cs, cu, cv, pc.fp0, pc.fp1);
+            else if (filter == 0x2) c0 = filter_text(cs, cu, cv, gp);
+            else if (filter == 0x4) c0 = filter_color_matrix(cs, cu, cv, gp);
             else c0 = cs(cu, cv);
             if (combine == 0x1) color = make_float4(c0.x, c0.y, c0.z, c0.w * color.w);  // SRC_IN, tile.comp:128-129
             else if (combine == 0x2) color.w = c0.w * color.w;                          // DEST_IN, tile.comp:130-131
@@ -820,8 +855,8 @@ __device__ __forceinline__ void blend_layer(PixelBlock &px, const uint4 u, const
             if (!((pairs >> j) & 1u)) continue;  // (a tile split over several warps: the other pairs are theirs)
             const float2 cov = mask_pair(mask8, j, even_odd);
             const float fy = g.fragy + (float)(j >> 1), fx = g.fragx + (float)((j & 1) * 2);
-            const float4 s0 = shade<false>(pc, cs, fx, fy, cov.x, (float)tg.width, (float)tg.height);
-            const float4 s1 = shade<false>(pc, cs, fx + 1.0f, fy, cov.y, (float)tg.width, (float)tg.height);
+            const float4 s0 = shade<false>(pc, &p.paints[paint], cs, fx, fy, cov.x, (float)tg.width, (float)tg.height);
+            const float4 s1 = shade<false>(pc, &p.paints[paint], cs, fx + 1.0f, fy, cov.y, (float)tg.width, (float)tg.height);
             px.over_pair(j, make_float2(s0.x, s1.x), make_float2(s0.y, s1.y), make_float2(s0.z, s1.z),
                          make_float2(s0.w, s1.w));
         }

@@ -533,6 +533,74 @@ def test_tiger_4096_pixels_against_live_reference_shaders(renderer, area_lut):
     assert d.max() <= PIXEL_TOL
 
 
+def _half_bits(values):
+    return np.asarray(values, "<f4").astype("<f2").view("<u2")
+
+
+def refiltered_paints_scene(ctrl, params):
+    """paints_512 with its image-pattern paint (entry 23: SRC_IN over pattern page 1) switched to another colour filter: ctrl
+    = composite << 10 | combine << 8 | filter << 4 (tile.comp:96-121), params = filterParams0 .. 4 (texels 3 .. 7 of the
+    paint's metadata entry, tile.comp:707-717)."""
+    scene, _ = scenes.load_scene(scenes.golden_path("paints_512"))
+    scene = dict(scene)
+    md = np.array(scene["metadata"], "<u2", copy=True).reshape(-1, 1280, 4)
+    entry = 23
+    assert int(md[0, entry * 10 + 8].view("<f2")[0]) == 0x100
+    for k, v in enumerate(params):
+        md[0, entry * 10 + 3 + k] = _half_bits(v)
+    md[0, entry * 10 + 8, 0] = _half_bits([float(ctrl)])[0]
+    scene["metadata"] = md.reshape(scene["metadata"].shape)
+    return scene
+
+
+TEXT_KERNEL_WIDE = [0.033165660, 0.102074051, 0.221434336, 0.286651906]  # a 9-tap kernel (kernel.x > 0), defringing on
+TEXT_KERNEL_NARROW = [0.0, 0.031372549, 0.301960784, 0.337254902]
+FILTER_CASES = {
+    # mat4 columns + offset: channels swapped and scaled, some of the alpha mixed in
+    "color_matrix": (0x140, [[0.1, 0.7, 0.0, 0.0], [0.8, 0.1, 0.2, 0.0], [0.0, 0.2, 0.6, 0.0], [0.05, 0.0, 0.1, 0.9],
+                             [0.02, 0.0, 0.05, 0.1]]),
+    "text_defringe_wide": (0x120, [TEXT_KERNEL_WIDE, [0.9, 0.85, 0.8, 0.0], [0.1, 0.15, 0.3, 0.0], [0.0] * 4, [0.0] * 4]),
+    "text_defringe_narrow": (0x120, [TEXT_KERNEL_NARROW, [1.0, 1.0, 1.0, 0.0], [0.0, 0.0, 0.0, 0.0], [0.0] * 4, [0.0] * 4]),
+    "text_plain": (0x120, [[0.0, 0.0, 0.0, 0.0], [0.2, 0.3, 0.4, 0.0], [1.0, 0.9, 0.1, 0.0], [0.0] * 4, [0.0] * 4]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(FILTER_CASES))
+def test_text_and_color_matrix_filters_against_the_reference_shader(renderer, area_lut, case):
+    """tile.comp's two remaining colour filters (filterText :136-227 without gamma correction, filterColorMatrix :394-404).
+    Upstream never emits them (paint/palette.cpp:65-67), so no scene of the reference reaches them: the metadata of a fixture's
+    image paint is rewritten and the frame compared with the reference's own tile.comp run on the CPU."""
+    pfshader = pytest.importorskip("pfshader")
+    if not pfshader.available():
+        pytest.skip("oracle/_ref/libpfshader.so not present")
+    import pforacle
+
+    ctrl, params = FILTER_CASES[case]
+    scene = refiltered_paints_scene(ctrl, params)
+    plain, _ = scenes.load_scene(scenes.golden_path("paints_512"))
+    fr = pforacle.Frame(plain, area_lut)
+    fr.render()  # geometry taps only: they do not depend on the paints
+    want, _, _ = pfshader.render_frame(scene, fr, area_lut)
+    base, _, _ = pfshader.render_frame(plain, fr, area_lut)
+    fr.close()
+    assert (np.abs(want.astype(int) - base.astype(int)).max(axis=2) > 8).mean() > 0.02, "the filter must change the picture"
+    renderer.set_scene(scene)
+    renderer.draw(clear=True)
+    d = np.abs(renderer.pixels().astype(np.int16) - want.astype(np.int16)).max(axis=2)
+    print("%s: %d of %d pixels differ from the reference shader's frame" % (case, int((d > 0).sum()), d.size))
+    assert d.max() <= PIXEL_TOL, "max diff %d at %s" % (d.max(), np.unravel_index(d.argmax(), d.shape))
+
+
+def test_text_filter_with_gamma_correction_is_refused(renderer):
+    """The reference binds a 1 x 1 dummy as the text filter's gamma LUT (d3d11/renderer.cpp:262-266): no defined result."""
+    import pfcu
+
+    scene = refiltered_paints_scene(0x120, [TEXT_KERNEL_WIDE, [1.0, 1.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0], [0.0] * 4, [0.0] * 4])
+    with pytest.raises(pfcu.PfcuError, match="gamma"):
+        renderer.set_scene(scene)
+    renderer.set_scene(scenes.load_scene(scenes.golden_path("paints_512"))[0])
+
+
 def test_config4_at_its_stated_size_against_the_oracle_fixture(renderer):
     """BASELINE.json configs[3] at FULL size -- 200,000 cubic blobs at 8192 x 8192 (16.7 M fills, 1.39 M masks: the
     only configuration that stresses the 24-bit tile ids and the multi-megabyte scans) -- against
