@@ -289,6 +289,23 @@ def test_synthetic_blobs_bit_exact_vs_oracle(renderer, area_lut):
     compare_with_oracle(renderer, area_lut, scene, "synthetic blobs")
 
 
+@pytest.mark.parametrize("size", [(1000, 700), (333, 517), (40, 1999)])
+def test_ragged_canvas_sizes_bit_exact_vs_oracle(renderer, area_lut, size):
+    """Canvases whose sides are not multiples of the 16-pixel tile and whose tile count is not a multiple of the 16-tile
+    groups of the tile kernel (the last group is partial; edge tiles store pixel by pixel): geometry taps bit-exact, pixels
+    within tolerance, with the tile groups in order of cost (the default) and in grid order."""
+    w, h = size
+    paths, colors = scenes.synthetic_paths(600, max(w, h))
+    scene = scenes.build_scene_from_outlines(w, h, paths, colors)
+    try:
+        for ordered in (True, False):
+            renderer.set_order_tile_groups(ordered)
+            compare_with_oracle(renderer, area_lut, scene, "ragged %dx%d ordered=%s" % (w, h, ordered))
+            assert renderer.pixels().shape == (h, w, 4)
+    finally:
+        renderer.set_order_tile_groups(True)
+
+
 def test_repeat_frames_are_identical_and_reuse_buffers(renderer):
     scene, _ = scenes.load_scene(scenes.golden_path("tiger_512"))
     renderer.set_scene(scene)
