@@ -343,7 +343,12 @@ __global__ void __launch_bounds__(FILL_WARPS * 32, FILL_CTAS_PER_SM) k_fill(Fill
     if (n_alpha >= n_warps * FILL_GROUP) warp = wib * gridDim.x + blockIdx.x;
 #endif
     int *const acc = &sh.acc[wib][0][0];
-    for (int i = (int)lane; i < FILL_GROUP * FILL_ACC; i += 32) acc[i] = 0;
+    {  // (16-byte stores: the scalar loop was 7 % of the kernel's instructions on tiger 4096^2)
+        static_assert((FILL_GROUP * FILL_ACC) % 128 == 0, "whole 16-byte stores per lane");
+        uint4 *const acc4 = reinterpret_cast<uint4 *>(acc);
+#pragma unroll
+        for (int i = 0; i < FILL_GROUP * FILL_ACC / 128; i++) acc4[i * 32 + (int)lane] = make_uint4(0u, 0u, 0u, 0u);
+    }
     __syncwarp();
 
     // (Handing the groups out through a global ticket counter instead -- one atomic per group, next ticket prefetched --
