@@ -230,8 +230,6 @@ class Renderer:
         self._descs = None
         if area_lut is not None:
             self.set_area_lut(area_lut)
-        if os.environ.get("PFCU_EXP_FILL_CULLED"):  # kernel experiments: rasterize z-culled masks too
-            self.set_fill_culled_tiles(True)
 
     def close(self):
         if getattr(self, "h", None):
