@@ -635,7 +635,9 @@ __device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
 #ifndef CT_MIN_CTAS
 #define CT_MIN_CTAS (28 / CT_WARPS_N)  // 7 CTAs per SM = 72 registers per thread (6: 78 registers measured 2 us slower; 64 registers spill)
 #endif
+#ifndef CT_MIN_CTAS_TEX
 #define CT_MIN_CTAS_TEX 4  // gradients / images / blend modes: up to 168 registers
+#endif
 constexpr int CT_WARPS = CT_WARPS_N;   // warps per CTA
 constexpr int CT_THREADS = CT_WARPS * 32;
 constexpr int CT_TILES = CT_WARPS * 4; // consecutive framebuffer tiles of one group (8 threads order one tile's list)
