@@ -997,6 +997,37 @@ static vec4 filter_blur(const sampler_t *s, float cu, float cv, vec4 p0, vec4 p1
     return color;
 }
 
+/* tile.comp:394-404 (filterColorMatrix): mat4(p0 .. p3) * texel + p4, the parameters being the matrix's columns */
+static vec4 filter_color_matrix(const sampler_t *s, float cu, float cv, const vec4 p[5]) {
+    vec4 src = tex(s, cu, cv), r;
+    for (int c = 0; c < 4; c++)
+        r.v[c] = p[0].v[c] * src.v[0] + p[1].v[c] * src.v[1] + p[2].v[c] * src.v[2] + p[3].v[c] * src.v[3] + p[4].v[c];
+    return r;
+}
+
+/* tile.comp:136-227 (filterText) with gamma correction off: the reference binds a 1 x 1 dummy as gamma LUT
+ * (core/d3d11/renderer.cpp:262-266), so a paint that turns it on has no defined result (the product refuses it) */
+static vec4 filter_text(const sampler_t *s, float cu, float cv, const vec4 p[5]) {
+    const float *k = p[0].v, *bg = p[1].v, *fg = p[2].v;
+    float alpha[3];
+    if (k[3] == 0.0f) {
+        alpha[0] = alpha[1] = alpha[2] = tex(s, cu, cv).v[0];
+    } else {
+        float one = 1.0f / (float)s->w, t[9];
+        int wide = k[0] > 0.0f;
+        for (int i = 0; i < 9; i++) /* taps -4 .. 4 (filterTextSample9Tap) */
+            t[i] = ((i == 0 || i == 8) && !wide) ? 0.0f : tex(s, cu + (float)(i - 4) * one, cv).v[0];
+        for (int c = 0; c < 3; c++) { /* filterTextConvolve7Tap centred on taps 3, 4, 5: dot(a0, k) + dot(a1, k.zyx) */
+            const float *a = t + c;
+            alpha[c] = (a[0] * k[0] + a[1] * k[1] + a[2] * k[2] + a[3] * k[3]) + (a[4] * k[2] + a[5] * k[1] + a[6] * k[0]);
+        }
+    }
+    vec4 r;
+    for (int c = 0; c < 3; c++) r.v[c] = bg[c] * (1.0f - alpha[c]) + fg[c] * alpha[c]; /* mix(bg, fg, alpha) */
+    r.v[3] = 1.0f;
+    return r;
+}
+
 /* tile.comp:459-562 (composite helpers) */
 static float comp_div(float n, float d) { return d != 0.0f ? n / d : 0.0f; }
 static void rgb_to_hsl(const float rgb[3], float hsl[3]) {
@@ -1152,7 +1183,11 @@ int pfo_frame_draw_batch(pfo_frame *f, int slot, int target_page, int color_page
                             vec4 c0;
                             if (filter == 0x1) c0 = filter_radial(&cs, cu, cv, fp0, fp1);
                             else if (filter == 0x3) c0 = filter_blur(&cs, cu, cv, fp0, fp1);
-                            else c0 = tex(&cs, cu, cv); /* text / colour-matrix filters are stubs host-side */
+                            else if (filter == 0x2 || filter == 0x4) { /* never emitted host-side (palette.cpp:65-67) */
+                                vec4 fp[5] = {fp0, fp1, metadata_texel(f, color_entry, 5), metadata_texel(f, color_entry, 6),
+                                              metadata_texel(f, color_entry, 7)};
+                                c0 = filter == 0x2 ? filter_text(&cs, cu, cv, fp) : filter_color_matrix(&cs, cu, cv, fp);
+                            } else c0 = tex(&cs, cu, cv);
                             if (combine == 0x1) { /* SRC_IN: vec4(src.rgb, src.a * dest.a) with dest = base colour */
                                 float a = c0.v[3] * color[3];
                                 color[0] = c0.v[0]; color[1] = c0.v[1]; color[2] = c0.v[2]; color[3] = a;

@@ -454,3 +454,37 @@ def tile_sums(px):
     of the fixtures that are too large to commit as frames (tests/golden/synthetic_200k_8192.npz)."""
     h, w, _ = px.shape
     return px.reshape(h // 16, 16, w // 16, 16, 4).astype(np.uint32).sum(axis=(1, 3)).astype("<u2")
+
+
+# ---- paints_512 with its image paint switched to one of the two colour filters upstream never emits
+
+def _half_bits(values):
+    return np.asarray(values, "<f4").astype("<f2").view("<u2")
+
+
+def refiltered_paints_scene(ctrl, params):
+    """paints_512 with its image-pattern paint (entry 23: SRC_IN over pattern page 1) switched to another colour filter: ctrl
+    = composite << 10 | combine << 8 | filter << 4 (tile.comp:96-121), params = filterParams0 .. 4 (texels 3 .. 7 of the
+    paint's metadata entry, tile.comp:707-717)."""
+    scene, _ = load_scene(golden_path("paints_512"))
+    scene = dict(scene)
+    md = np.array(scene["metadata"], "<u2", copy=True).reshape(-1, 1280, 4)
+    entry = 23
+    assert int(md[0, entry * 10 + 8].view("<f2")[0]) == 0x100
+    for k, v in enumerate(params):
+        md[0, entry * 10 + 3 + k] = _half_bits(v)
+    md[0, entry * 10 + 8, 0] = _half_bits([float(ctrl)])[0]
+    scene["metadata"] = md.reshape(scene["metadata"].shape)
+    return scene
+
+
+TEXT_KERNEL_WIDE = [0.033165660, 0.102074051, 0.221434336, 0.286651906]  # a 9-tap kernel (kernel.x > 0), defringing on
+TEXT_KERNEL_NARROW = [0.0, 0.031372549, 0.301960784, 0.337254902]
+FILTER_CASES = {
+    # mat4 columns + offset: channels swapped and scaled, some of the alpha mixed in
+    "color_matrix": (0x140, [[0.1, 0.7, 0.0, 0.0], [0.8, 0.1, 0.2, 0.0], [0.0, 0.2, 0.6, 0.0], [0.05, 0.0, 0.1, 0.9],
+                             [0.02, 0.0, 0.05, 0.1]]),
+    "text_defringe_wide": (0x120, [TEXT_KERNEL_WIDE, [0.9, 0.85, 0.8, 0.0], [0.1, 0.15, 0.3, 0.0], [0.0] * 4, [0.0] * 4]),
+    "text_defringe_narrow": (0x120, [TEXT_KERNEL_NARROW, [1.0, 1.0, 1.0, 0.0], [0.0, 0.0, 0.0, 0.0], [0.0] * 4, [0.0] * 4]),
+    "text_plain": (0x120, [[0.0, 0.0, 0.0, 0.0], [0.2, 0.3, 0.4, 0.0], [1.0, 0.9, 0.1, 0.0], [0.0] * 4, [0.0] * 4]),
+}
