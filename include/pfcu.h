@@ -244,7 +244,15 @@ enum {
      * grid order) and the others last, and writes the list headers in that order -- instead of wherever the scene puts
      * them in the grid (a group costs 1.2 .. 17 us, and expensive groups late in the grid leave most of the GPU idle
      * at the end of the kernel; tools/timeline.py). Same pixels, same lists. 0: groups in grid order. */
-    PFCU_OPT_ORDER_TILE_GROUPS = 4
+    PFCU_OPT_ORDER_TILE_GROUPS = 4,
+    /* 1 (default): the batches of a frame after its first are PREPARED side by side (bound .. fill of batch i on stream pair
+     * i mod 4), each after the clip batch it reads; the tile passes stay in submission order on the context's stream, each waiting for its own batch.
+     * The reference prepares and draws batch after batch (d3d11/renderer.cpp:318-336); a frame of many small batches -- the
+     * demo's primitives scene: 14 batches, render-target passes, a blurred shadow -- is then a chain of 150 tiny kernels.
+     * Demo scene at 2048^2: 1006 -> 724 us per frame alone, 690 -> 629 us streamed; a frame of one batch is enqueued as
+     * before. Mask slots are handed out in completion order, so alpha tile ids can differ from run to run; pixels do not.
+     * 0: batch after batch. */
+    PFCU_OPT_CONCURRENT_BATCHES = 5
 };
 int pfcu_set_option(pfcu_ctx *ctx, int option, int value);
 

@@ -123,6 +123,10 @@ struct BatchSlot {
     BatchView view{};
     bool prepared = false;
     bool heavy_paints = false;  // a path of the batch paints with a blur filter (tile.comp:354-392)
+    // PFCU_OPT_CONCURRENT_BATCHES: the ends of the batch's two kernel chains (on its lane's streams) and whether the
+    // context's stream has waited for them yet
+    cudaEvent_t lane_done[2] = {nullptr, nullptr};
+    bool lane_joined[2] = {true, true};
     // Incremental frames (PFCU_OPT_INCREMENTAL_DICE): the dice output of an earlier frame that this slot still holds.
     struct DiceBase {
         bool valid = false;
@@ -159,6 +163,13 @@ struct pfcu_ctx {
     std::vector<cudaEvent_t> sync_events;
     size_t sync_used = 0;
     cudaEvent_t aux_pending = nullptr;  // last event recorded on the aux stream that the main stream has not waited for
+    // PFCU_OPT_CONCURRENT_BATCHES: the batches of a frame prepare side by side, batch i on lane i % N_LANES (a lane = the
+    // two streams of a batch's kernel chains); only the tile passes stay in order on the context's stream
+    static constexpr int N_LANES = 4;
+    cudaStream_t lane_main[N_LANES] = {}, lane_aux[N_LANES] = {};
+    bool concurrent_batches = true;
+    cudaEvent_t frame_fork = nullptr;  // recorded on the context's stream at the frame's first batch: what the lanes wait for
+    bool lanes_unjoined = false;       // a lane holds work the context's stream has not waited for (a frame that was abandoned)
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     // asynchronous read-back of the target (pfcu_read_target_async): its own stream, ordered after the frame by an event
     cudaStream_t copy_stream = nullptr;
@@ -268,6 +279,13 @@ int find_slot(pfcu_ctx *c, uint32_t batch_id) {
 int sync_if_in_flight(pfcu_ctx *c) {
     if (c->in_flight) {
         if (c->aux_pending) CUDA_TRY(cudaStreamSynchronize(c->aux_stream));
+        if (c->lanes_unjoined) {
+            for (int i = 0; i < pfcu_ctx::N_LANES; i++) {
+                CUDA_TRY(cudaStreamSynchronize(c->lane_main[i]));
+                CUDA_TRY(cudaStreamSynchronize(c->lane_aux[i]));
+            }
+            c->lanes_unjoined = false;
+        }
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->in_flight = false;
         c->stage_busy[0] = c->stage_busy[1] = false;
@@ -316,6 +334,13 @@ int join_aux(pfcu_ctx *c) {
         CUDA_TRY(cudaStreamWaitEvent(c->stream, c->aux_pending, 0));
         c->aux_pending = nullptr;
     }
+    for (int i = 0; i < c->slots_used; i++)  // concurrent batches that nobody drew (clip batches)
+        for (int k = 0; k < 2; k++)
+            if (!c->slots[i].lane_joined[k] && c->slots[i].lane_done[k]) {
+                CUDA_TRY(cudaStreamWaitEvent(c->stream, c->slots[i].lane_done[k], 0));
+                c->slots[i].lane_joined[k] = true;
+            }
+    c->lanes_unjoined = false;  // every lane's work is ordered before what follows on the context's stream
     return PFCU_OK;
 }
 
@@ -471,6 +496,8 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
     }
     s.view = v;
     s.prepared = true;
+    s.lane_done[0] = s.lane_done[1] = nullptr;
+    s.lane_joined[0] = s.lane_joined[1] = true;
 
     PaintView pv;
     memset(&pv, 0, sizeof(pv));
@@ -488,66 +515,101 @@ int enqueue_prepare(pfcu_ctx *c, int slot_index, bool upload_meta = true) {
         sig_mix(c, &bytes, sizeof(bytes));
     }
     if (c->dry) return PFCU_OK;
-    if (s.meta_bytes && upload_meta) {
-        CUDA_TRY(cudaMemcpyAsync(s.dev_meta.p, s.host_meta.p, s.meta_bytes, cudaMemcpyHostToDevice, c->stream));
-        if (!c->capturing) c->uploaded_bytes += (uint32_t)s.meta_bytes;
-    }
-
-    {
-        int r = prof_mark(c, -1);
-        if (r) return r;
-    }
     // The frame forks and joins between two streams (graph branches when captured); per-stage profiling keeps
     // everything on one stream so that the event pairs bracket one kernel each.
     //   main: counters = 0, dice ........ bin (short walks) ..... scan, propagate, list building ......... tile
     //   aux :  init (zeroing) ........... bin (long walks) ...... fill scatter ........ fill ............../
     const bool two_streams = !c->profiling || c->capturing;
-    cudaStream_t aux = two_streams ? c->aux_stream : c->stream;
+    // PFCU_OPT_CONCURRENT_BATCHES: this batch's chains run on its lane, beside the other batches' (and beside the tile passes
+    // of the batches before it); they start after the frame's first batch was reached on the context's stream (uploads, the
+    // zeroed mask slot counter) and after the clip batch this one reads (its tile states and its masks)
+    // The FIRST batch of a frame stays on the context's own two streams: a frame of one batch (an SVG) is enqueued exactly
+    // as without the option.
+    const bool lanes_on = two_streams && c->concurrent_batches;
+    const bool lanes = lanes_on && slot_index > 0;
+    const int lane = slot_index % pfcu_ctx::N_LANES;
+    cudaStream_t ms = lanes ? c->lane_main[lane] : c->stream;
+    cudaStream_t aux = lanes ? c->lane_aux[lane] : (two_streams ? c->aux_stream : c->stream);
+    if (lanes_on) {
+        if (!c->frame_fork) {
+            int r = order_after(c, nullptr, c->stream, &c->frame_fork);
+            if (r) return r;
+        }
+        if (lanes) CUDA_TRY(cudaStreamWaitEvent(ms, c->frame_fork, 0));
+        if (d.clip_batch_id >= 0) {
+            const int cs = find_slot(c, (uint32_t)d.clip_batch_id);
+            if (cs >= 0 && cs != slot_index)
+                for (int k = 0; k < 2; k++)
+                    if (c->slots[cs].lane_done[k]) CUDA_TRY(cudaStreamWaitEvent(ms, c->slots[cs].lane_done[k], 0));
+        }
+    }
+    if (s.meta_bytes && upload_meta) {
+        CUDA_TRY(cudaMemcpyAsync(s.dev_meta.p, s.host_meta.p, s.meta_bytes, cudaMemcpyHostToDevice, ms));
+        if (!c->capturing) c->uploaded_bytes += (uint32_t)s.meta_bytes;
+    }
+
+
+    {
+        int r = prof_mark(c, -1);
+        if (r) return r;
+    }
     if (two_streams) {
-        int r = order_after(c, aux, c->stream);  // (also orders this batch's aux work after the previous batch's)
+        int r = order_after(c, aux, ms);  // (also orders this batch's aux work after the previous batch's)
         if (r) return r;
     }
     // (one 16 KB memset of every batch's counters at the start of the frame instead of a 64-byte one per batch was
     // measured: 2 us SLOWER per frame -- the small ones do not cost a kernel launch)
     if (v.dice_ranges)  // the retained lines, staging slots and long-line queue stay: the counters start where they ended
-        CUDA_TRY(cudaMemcpyAsync(v.counters, m + s.off_counters, sizeof(BatchCounters), cudaMemcpyDeviceToDevice, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(v.counters, m + s.off_counters, sizeof(BatchCounters), cudaMemcpyDeviceToDevice, ms));
     else
-        CUDA_TRY(cudaMemsetAsync(v.counters, 0, sizeof(BatchCounters), c->stream));
+        CUDA_TRY(cudaMemsetAsync(v.counters, 0, sizeof(BatchCounters), ms));
     LAUNCH_STAGE(PFCU_STAGE_INIT, launch_init(v, aux));
-    LAUNCH_STAGE(PFCU_STAGE_DICE, launch_dice(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_DICE, launch_dice(v, ms));
     if (two_streams) {  // bin needs the zeroed tile words; the long-walk kernel needs dice's lines
-        int r = order_after(c, c->stream, aux);
+        int r = order_after(c, ms, aux);
         if (r) return r;
-        r = order_after(c, aux, c->stream);
+        r = order_after(c, aux, ms);
         if (r) return r;
     }
-    LAUNCH_STAGE(PFCU_STAGE_BIN, launch_bin(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_BIN, launch_bin(v, ms));
     LAUNCH_STAGE(PFCU_STAGE_BIN, launch_bin_long(v, aux));
     if (two_streams) {
-        int r = order_after(c, c->stream, aux);
+        int r = order_after(c, ms, aux);
         if (r) return r;
     }
-    LAUNCH_STAGE(PFCU_STAGE_SCAN_TILES, launch_scan_tiles(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_SCAN_TILES, launch_scan_tiles(v, ms));
     // {fill scatter, fill} on the aux stream, {propagate, list building} on the main stream. fill needs propagate's
     // alpha-tile records; the tile kernel (enqueue_draw) needs both branches.
     if (two_streams) {
-        int r = order_after(c, aux, c->stream);
+        int r = order_after(c, aux, ms);
         if (r) return r;
     }
     LAUNCH_STAGE(PFCU_STAGE_FILL_SCATTER, launch_fill_scatter(v, aux));
-    LAUNCH_STAGE(PFCU_STAGE_PROPAGATE, launch_propagate(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_PROPAGATE, launch_propagate(v, ms));
     if (two_streams) {
-        int r = order_after(c, aux, c->stream);
+        int r = order_after(c, aux, ms);
         if (r) return r;
     }
-    LAUNCH_STAGE(PFCU_STAGE_SCAN_FB, launch_scan_fb(v, c->stream));
-    LAUNCH_STAGE(PFCU_STAGE_LIST_SCATTER, launch_list_scatter(v, c->stream));
+    LAUNCH_STAGE(PFCU_STAGE_SCAN_FB, launch_scan_fb(v, ms));
+    LAUNCH_STAGE(PFCU_STAGE_LIST_SCATTER, launch_list_scatter(v, ms));
     LAUNCH_STAGE(PFCU_STAGE_FILL, launch_fill(v, pv, aux));
     s.fill_done = nullptr;
-    if (two_streams) {
+    if (lanes) {  // the ends of both chains: the tile pass (enqueue_draw), batches clipped by this one, the frame's tail
+        int r = order_after(c, nullptr, ms, &s.lane_done[0]);
+        if (r) return r;
+        r = order_after(c, nullptr, aux, &s.lane_done[1]);
+        if (r) return r;
+        s.lane_joined[0] = s.lane_joined[1] = false;
+        c->lanes_unjoined = true;
+    } else if (two_streams) {
         int r = order_after(c, nullptr, aux, &s.fill_done);
         if (r) return r;
         c->aux_pending = s.fill_done;
+        if (lanes_on) {  // (the frame's first batch: what a batch clipped by it waits for; the context's stream joins as ever)
+            r = order_after(c, nullptr, ms, &s.lane_done[0]);
+            if (r) return r;
+            s.lane_done[1] = s.fill_done;
+        }
     }
     c->launches += v.fused_fill ? 9 : 10;
     c->in_flight = true;
@@ -611,6 +673,11 @@ int enqueue_draw(pfcu_ctx *c, const Cmd &cmd) {
         int r = prof_mark(c, -1);
         if (r) return r;
     }
+    for (int k = 0; k < 2; k++)  // concurrent batches: both chains of this batch
+        if (!s.lane_joined[k] && s.lane_done[k]) {
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, s.lane_done[k], 0));
+            s.lane_joined[k] = true;
+        }
     if (s.fill_done) {  // join: the masks of this batch (and, the aux stream being in order, of every earlier one)
         CUDA_TRY(cudaStreamWaitEvent(c->stream, s.fill_done, 0));
         if (c->aux_pending == s.fill_done) c->aux_pending = nullptr;
@@ -641,6 +708,7 @@ int capture_frame(pfcu_ctx *c, bool upload_meta, cudaGraph_t *graph, cudaGraphEx
         return fail(PFCU_ERR_CUDA, "cudaStreamBeginCapture: %s", cudaGetErrorString(e));
     }
     int rc = PFCU_OK;
+    c->frame_fork = nullptr;
     if (cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream) != cudaSuccess) rc = PFCU_ERR_CUDA;
     for (const Cmd &cmd : c->cmds) {
         if (rc) break;
@@ -679,6 +747,10 @@ int pfcu_create(int device_ordinal, pfcu_ctx **out) {
     c->device = device_ordinal;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < pfcu_ctx::N_LANES; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->lane_main[i], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->lane_aux[i], cudaStreamNonBlocking));
+    }
     c->stream = c->own_stream;
     CUDA_TRY(cudaEventCreate(&c->ev_begin));
     CUDA_TRY(cudaEventCreate(&c->ev_end));
@@ -698,6 +770,10 @@ int pfcu_create(int device_ordinal, pfcu_ctx **out) {
 void pfcu_destroy(pfcu_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    for (int i = 0; i < pfcu_ctx::N_LANES; i++) {
+        if (c->lane_main[i]) cudaStreamSynchronize(c->lane_main[i]);
+        if (c->lane_aux[i]) cudaStreamSynchronize(c->lane_aux[i]);
+    }
     cudaStreamSynchronize(c->aux_stream);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
@@ -743,6 +819,10 @@ void pfcu_destroy(pfcu_ctx *c) {
     drop_retained(c);
     for (cudaEvent_t e : c->sync_events) cudaEventDestroy(e);
     cudaStreamDestroy(c->aux_stream);
+    for (int i = 0; i < pfcu_ctx::N_LANES; i++) {
+        if (c->lane_main[i]) cudaStreamDestroy(c->lane_main[i]);
+        if (c->lane_aux[i]) cudaStreamDestroy(c->lane_aux[i]);
+    }
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -1305,6 +1385,7 @@ int pfcu_prepare_batch(pfcu_ctx *c, const pfcu_batch_desc *d) {
         CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
         c->event_begin_recorded = true;
         // first batch of the frame: reset the frame-global alpha tile counter
+        c->frame_fork = nullptr;
         CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
     }
     s.desc = *d;
@@ -1468,7 +1549,8 @@ int pfcu_submit_frame(pfcu_ctx *c) {
                 served_by_graph = true;
             } else {
                 drop_retained(c);
-                CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
+                c->frame_fork = nullptr;
+        CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
                 for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
                 for (const Cmd &cmd : c->cmds) {
                     const int r = cmd.kind == CMD_PREPARE ? enqueue_prepare(c, cmd.slot) : enqueue_draw(c, cmd);
@@ -1551,6 +1633,7 @@ int pfcu_wait_frame(pfcu_ctx *c, pfcu_frame_stats *stats) {
         c->sync_used = 0;
         for (int i = 0; i < c->slots_used; i++) c->slots[i].prepared = false;
         CUDA_TRY(cudaEventRecord(c->ev_begin, c->stream));
+        c->frame_fork = nullptr;
         CUDA_TRY(cudaMemsetAsync(frame_alpha_counter(c), 0, sizeof(BatchCounters), c->stream));
         for (const Cmd &cmd : c->cmds) {
             const int r = cmd.kind == CMD_PREPARE ? enqueue_prepare(c, cmd.slot) : enqueue_draw(c, cmd);
@@ -1648,6 +1731,10 @@ int pfcu_set_option(pfcu_ctx *c, int option, int value) {
             return PFCU_OK;
         case PFCU_OPT_FUSED_FILL:
             c->fused_fill = value != 0;
+            return PFCU_OK;
+        case PFCU_OPT_CONCURRENT_BATCHES:
+            c->concurrent_batches = value != 0;
+            drop_retained(c);
             return PFCU_OK;
         case PFCU_OPT_ORDER_TILE_GROUPS:
             c->order_groups = value < 0 ? 0 : value;

@@ -254,10 +254,9 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan(ScanArgs b) {
             const uint32_t fills = (uint32_t)total, alphas = (uint32_t)(total >> 32);
             b.counters->n_fills = fills;
             b.counters->n_alpha = alphas;
-            // batches of a frame are stream-ordered: plain read-modify-write of the frame-global mask slot counter
-            const uint32_t first = *b.frame_alpha_counter;
+            // the frame-global mask slot counter (the batches of a frame may prepare side by side: PFCU_OPT_CONCURRENT_BATCHES)
+            const uint32_t first = atomicAdd(b.frame_alpha_counter, alphas);
             b.counters->first_alpha = first;  // read by propagate and fill, which run after this kernel
-            *b.frame_alpha_counter = first + alphas;
             uint32_t ovf = 0;
             if (fills > b.fill_capacity) ovf |= OVF_FILLS;
             if (first + alphas > b.mask_capacity || alphas > b.alpha_capacity) ovf |= OVF_ALPHA;

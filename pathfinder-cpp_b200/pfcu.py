@@ -383,6 +383,10 @@ class Renderer:
         """PFCU_OPT_FUSED_FILL (default off): the tile kernel rasterizes a draw batch's masks itself (no separate fill)."""
         _check(self.L.pfcu_set_option(self.h, 3, int(bool(enabled))))
 
+    def set_concurrent_batches(self, enabled):
+        """PFCU_OPT_CONCURRENT_BATCHES (default on): the batches of a frame prepare side by side on four stream pairs."""
+        _check(self.L.pfcu_set_option(self.h, 5, int(bool(enabled))))
+
     def set_order_tile_groups(self, enabled):
         """PFCU_OPT_ORDER_TILE_GROUPS (default 4): the tile kernel starts with the groups of 16 tiles that have at least
         this many masked tiles; 0 / False = grid order."""

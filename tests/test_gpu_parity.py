@@ -237,6 +237,31 @@ np.save(sys.argv[1], r.pixels())
     assert np.array_equal(np.load(out), want)
 
 
+@pytest.mark.parametrize("name", ["demo_full_512", "demo_full_2048", "demo_clip_512", "paints_512", "features_2048", "tiger_512"])
+def test_concurrent_batches_render_the_same_frame(area_lut, name):
+    """PFCU_OPT_CONCURRENT_BATCHES: the batches of a frame prepared side by side on four stream pairs (clip batches first,
+    tile passes in order). Same pixels and same render-target pages as the batch-after-batch frame, eagerly and from the
+    retained frame graph (frames 3 .. 5 are graph launches)."""
+    import pfcu
+
+    scene, _ = scenes.load_scene(scenes.golden_path(name))
+    frames = []
+    for concurrent in (False, True):
+        r = pfcu.Renderer(0, area_lut)
+        r.set_concurrent_batches(concurrent)
+        r.set_scene(scene)
+        got = []
+        for _ in range(5):
+            st = r.draw(clear=True)
+            assert st["overflow_flags"] == 0
+            got.append(r.pixels().copy())
+        r.close()
+        for g in got[1:]:
+            assert np.array_equal(g, got[0]), "frames of one renderer differ (concurrent=%s)" % concurrent
+        frames.append(got[0])
+    assert np.array_equal(frames[0], frames[1]), "%d bytes differ" % int((frames[0] != frames[1]).sum())
+
+
 def compare_with_oracle(renderer, area_lut, scene, what):
     """Geometry taps bit-exact + pixels within tolerance for a scene that has no reference fixture."""
     renderer.set_scene(scene)

@@ -23,6 +23,8 @@ for n_ctx in [int(x) for x in os.environ.get("CONTEXTS", "1,2,3,4,6,8").split(",
         q = pfcu.Renderer(0, lut)
         st = torch.cuda.Stream()
         q.set_stream(st.cuda_stream)
+        if "CONCURRENT" in os.environ:
+            q.set_concurrent_batches(int(os.environ["CONCURRENT"]))
         if "ORDER" in os.environ:
             try:
                 q.set_order_tile_groups(int(os.environ["ORDER"]))
