@@ -76,6 +76,46 @@ __device__ __forceinline__ float4 sample_rgba8(const uint8_t *px, int w, int h, 
     return r;
 }
 
+// The same bilinear fetch with the two axes prepared separately (texel indices + weight per axis): a blur along x keeps the y
+// half for all of its taps and the other way round. Same operations in the same order as sample_rgba8, so the same bits.
+struct AxisTaps {
+    int i0, i1;
+    float a;
+};
+__device__ __forceinline__ AxisTaps axis_taps(float coord, int n, bool repeat) {
+    float x = coord * (float)n;
+    x -= 0.5f;
+    const float f0 = floorf(x);
+    AxisTaps t;
+    t.a = x - f0;
+    t.i0 = wrap_or_clamp((int)f0, n, repeat);
+    t.i1 = wrap_or_clamp((int)f0 + 1, n, repeat);
+    return t;
+}
+__device__ __forceinline__ float4 sample_axes(const uint8_t *px, int w, const AxisTaps &X, const AxisTaps &Y) {
+    const float ax = X.a, ay = Y.a;
+    const float4 a = ld_rgba8(px, w, X.i0, Y.i0), b = ld_rgba8(px, w, X.i1, Y.i0);
+    const float4 c = ld_rgba8(px, w, X.i0, Y.i1), d = ld_rgba8(px, w, X.i1, Y.i1);
+    float4 r;
+    {
+        const float t0 = a.x + (b.x - a.x) * ax, t1 = c.x + (d.x - c.x) * ax;
+        r.x = t0 + (t1 - t0) * ay;
+    }
+    {
+        const float t0 = a.y + (b.y - a.y) * ax, t1 = c.y + (d.y - c.y) * ax;
+        r.y = t0 + (t1 - t0) * ay;
+    }
+    {
+        const float t0 = a.z + (b.z - a.z) * ax, t1 = c.z + (d.z - c.z) * ax;
+        r.z = t0 + (t1 - t0) * ay;
+    }
+    {
+        const float t0 = a.w + (b.w - a.w) * ax, t1 = c.w + (d.w - c.w) * ax;
+        r.w = t0 + (t1 - t0) * ay;
+    }
+    return r;
+}
+
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 __device__ __forceinline__ float glsl_mod(float x, float y) { return x - y * floorf(x / y); }
@@ -420,13 +460,23 @@ __device__ float4 filter_radial(const ColorSampler &cs, float cu, float cv, floa
 }
 
 // filterBlur, tile.comp:354-392
-__device__ float4 filter_blur(const ColorSampler &cs, float cu, float cv, float4 p0, float4 p1) {
-    const float sox = p0.x / (float)cs.w, soy = p0.y / (float)cs.h;
+// AXIS 1 / 2: the blur runs along x / y only (what the reference's two-pass shadows do, canvas.cpp:91-151): the other
+// axis' texel rows / columns and weight are the same for every tap (cv - 0 * k == cv) and are prepared once.
+template <int AXIS>
+__device__ __forceinline__ float4 filter_blur_loop(const ColorSampler &cs, float cu, float cv, float sox, float soy, float4 p0, float4 p1) {
     const int support = (int)p0.z;
     float gx = p1.x, gy = p1.y;
     const float gz = p1.z;
     float gauss_sum = gx;
-    float4 color = cs(cu, cv);
+    AxisTaps fixed = {};
+    if (AXIS == 1) fixed = axis_taps(cv, cs.h, cs.repeat_v);
+    if (AXIS == 2) fixed = axis_taps(cu, cs.w, cs.repeat_u);
+    auto tap = [&](float u, float v) {
+        if (AXIS == 1) return sample_axes(cs.px, cs.w, axis_taps(u, cs.w, cs.repeat_u), fixed);
+        if (AXIS == 2) return sample_axes(cs.px, cs.w, fixed, axis_taps(v, cs.h, cs.repeat_v));
+        return cs(u, v);
+    };
+    float4 color = tap(cu, cv);
     color.x *= gx; color.y *= gx; color.z *= gx; color.w *= gx;
     gx *= gy;
     gy *= gz;
@@ -436,7 +486,7 @@ __device__ float4 filter_blur(const ColorSampler &cs, float cu, float cv, float4
         gy *= gz;
         partial += gx;
         const float k = (float)i + gx / partial;
-        const float4 a = cs(cu - sox * k, cv - soy * k), bq = cs(cu + sox * k, cv + soy * k);
+        const float4 a = tap(cu - sox * k, cv - soy * k), bq = tap(cu + sox * k, cv + soy * k);
         color.x += (a.x + bq.x) * partial;
         color.y += (a.y + bq.y) * partial;
         color.z += (a.z + bq.z) * partial;
@@ -447,6 +497,13 @@ __device__ float4 filter_blur(const ColorSampler &cs, float cu, float cv, float4
     }
     color.x /= gauss_sum; color.y /= gauss_sum; color.z /= gauss_sum; color.w /= gauss_sum;
     return color;
+}
+
+__device__ float4 filter_blur(const ColorSampler &cs, float cu, float cv, float4 p0, float4 p1) {
+    const float sox = p0.x / (float)cs.w, soy = p0.y / (float)cs.h;
+    if (!cs.nearest && soy == 0.0f) return filter_blur_loop<1>(cs, cu, cv, sox, soy, p0, p1);
+    if (!cs.nearest && sox == 0.0f) return filter_blur_loop<2>(cs, cu, cv, sox, soy, p0, p1);
+    return filter_blur_loop<0>(cs, cu, cv, sox, soy, p0, p1);
 }
 
 // filterColorMatrix, tile.comp:394-404: mat4(p0 .. p3) * texel + p4 (the parameters are the matrix's COLUMNS)
