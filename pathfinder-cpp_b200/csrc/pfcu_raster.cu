@@ -22,6 +22,40 @@
 
 namespace pfcu {
 
+// ---- packed f32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot, each half
+// rounded exactly like the scalar instruction)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
+
 __device__ __forceinline__ float4 ld_rgba8(const uint8_t *px, int w, int x, int y) {
     const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(px) + (size_t)y * w + x);
     // float(byte) without the conversion pipe (a quarter-rate I2F per channel is what a blur tap would spend most of its
@@ -92,28 +126,27 @@ __device__ __forceinline__ AxisTaps axis_taps(float coord, int n, bool repeat) {
     t.i1 = wrap_or_clamp((int)f0 + 1, n, repeat);
     return t;
 }
+// (packed f32x2: the byte -> float conversion and the three interpolations of two channels per instruction, each half
+// rounded like the scalar instruction it replaces -- a + (b - a) * t is one subtraction and one fused multiply-add there too)
+struct Texel2 {
+    float2 rg, ba;
+};
+__device__ __forceinline__ Texel2 ld_rgba8_2(const uint8_t *px, int w, int x, int y) {
+    const uint32_t v = __ldg(reinterpret_cast<const uint32_t *>(px) + (size_t)y * w + x);
+    const float2 m = splat(-8388608.0f), k = splat(1.0f / 255.0f);
+    Texel2 t;
+    t.rg = mul2(add2(make_float2(__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7540)), __uint_as_float(__byte_perm(v, 0x4b000000u, 0x7541))), m), k);
+    t.ba = mul2(add2(make_float2(__uint_as_float(__byte_perm(v, 0x4b000000u, 0x7542)), __uint_as_float(__byte_perm(v, 0x4b000000u, 0x7543))), m), k);
+    return t;
+}
+__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 t) { return fma2(fma2(a, splat(-1.0f), b), t, a); }
 __device__ __forceinline__ float4 sample_axes(const uint8_t *px, int w, const AxisTaps &X, const AxisTaps &Y) {
-    const float ax = X.a, ay = Y.a;
-    const float4 a = ld_rgba8(px, w, X.i0, Y.i0), b = ld_rgba8(px, w, X.i1, Y.i0);
-    const float4 c = ld_rgba8(px, w, X.i0, Y.i1), d = ld_rgba8(px, w, X.i1, Y.i1);
-    float4 r;
-    {
-        const float t0 = a.x + (b.x - a.x) * ax, t1 = c.x + (d.x - c.x) * ax;
-        r.x = t0 + (t1 - t0) * ay;
-    }
-    {
-        const float t0 = a.y + (b.y - a.y) * ax, t1 = c.y + (d.y - c.y) * ax;
-        r.y = t0 + (t1 - t0) * ay;
-    }
-    {
-        const float t0 = a.z + (b.z - a.z) * ax, t1 = c.z + (d.z - c.z) * ax;
-        r.z = t0 + (t1 - t0) * ay;
-    }
-    {
-        const float t0 = a.w + (b.w - a.w) * ax, t1 = c.w + (d.w - c.w) * ax;
-        r.w = t0 + (t1 - t0) * ay;
-    }
-    return r;
+    const float2 ax = splat(X.a), ay = splat(Y.a);
+    const Texel2 a = ld_rgba8_2(px, w, X.i0, Y.i0), b = ld_rgba8_2(px, w, X.i1, Y.i0);
+    const Texel2 c = ld_rgba8_2(px, w, X.i0, Y.i1), d = ld_rgba8_2(px, w, X.i1, Y.i1);
+    const float2 rg = lerp2(lerp2(a.rg, b.rg, ax), lerp2(c.rg, d.rg, ax), ay);
+    const float2 ba = lerp2(lerp2(a.ba, b.ba, ax), lerp2(c.ba, d.ba, ax), ay);
+    return make_float4(rg.x, rg.y, ba.x, ba.y);
 }
 
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
@@ -650,41 +683,6 @@ __device__ __noinline__ float4 shade(const Paint &pc, const Paint *gp, const Col
     color.z *= color.w;
     return color;
 }
-
-// ---- packed f32x2 arithmetic (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per issue slot, each half
-// rounded exactly like the scalar instruction)
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{.reg .b64 ra, rb, rc, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-        "mov.b64 {%0, %1}, rd;}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-    float2 d;
-    asm("{.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "mul.rn.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-    float2 d;
-    asm("{.reg .b64 ra, rb, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
-        "add.rn.f32x2 rd, ra, rb;\n\t"
-        "mov.b64 {%0, %1}, rd;}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
-    return d;
-}
-__device__ __forceinline__ float2 splat(float v) { return make_float2(v, v); }
-
 
 #ifndef CT_WARPS_N
 #define CT_WARPS_N 4
