@@ -47,18 +47,28 @@ extern "C" int pfhost_stream_frames(pfcu_ctx *const *contexts, uint32_t n_contex
         pending[k] = 0;
         return PFCU_OK;
     };
+    // on an error: the frames still in flight are waited for (their status is dropped), so that every context is usable again
+    auto bail = [&](int err) {
+        for (uint32_t k = 0; k < n_contexts; k++)
+            if (pending[k]) {
+                pfcu_wait_frame(contexts[k], nullptr);
+                if (pixels) pfcu_wait_read(contexts[k]);
+                pending[k] = 0;
+            }
+        return err;
+    };
     for (uint32_t i = 0; i < n_frames; i++) {
         const uint32_t k = i % n_contexts;
         int r;
-        if (pending[k] && (r = collect(k))) return r;
-        if ((r = submit_one(contexts[k], *scene, pixels ? pixels[k] : nullptr))) return r;
+        if (pending[k] && (r = collect(k))) return bail(r);
+        if ((r = submit_one(contexts[k], *scene, pixels ? pixels[k] : nullptr))) return bail(r);
         pending[k] = 1;
     }
     // collect in submission order, so that `last` is the last frame's
     for (uint32_t j = 0; j < n_contexts; j++) {
         const uint32_t k = (n_frames + j) % n_contexts;
         int r;
-        if (pending[k] && (r = collect(k))) return r;
+        if (pending[k] && (r = collect(k))) return bail(r);
     }
     if (wall_seconds) *wall_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (last) *last = st;
